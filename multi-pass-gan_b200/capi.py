@@ -1,0 +1,184 @@
+"""ctypes binding of libmpg_b200.so (the C ABI declared in include/mpg.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a handle
+without a B200, raises.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpg_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+BF16, F32 = 0, 1
+KIND_TCGEN05, KIND_DIRECT = 1, 2
+
+_ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
+
+
+class MpgError(RuntimeError):
+    """Raised for any non-zero status of the C ABI (mirrors TF's InvalidArgumentError role)."""
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int),
+        ("nseg", ctypes.c_int),
+        ("seg_cin", ctypes.c_int * 2),
+        ("seg_cstride", ctypes.c_int * 2),
+        ("seg_ksize", ctypes.c_int * 2),
+        ("cout", ctypes.c_int),
+        ("act", ctypes.c_int),
+        ("pixel_norm", ctypes.c_int),
+        ("upsample", ctypes.c_int),
+        ("in_upsample", ctypes.c_int),
+        ("stride", ctypes.c_int),
+        ("force_kind", ctypes.c_int),
+        ("in_dtype", ctypes.c_int),
+        ("out_dtype", ctypes.c_int),
+        ("out_cstride", ctypes.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpgError(
+            "libmpg_b200.so is missing (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback for the CUDA path." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ip, dp = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.mpg_version.restype = ip
+    L.mpg_last_error.restype = ctypes.c_char_p
+    L.mpg_create.argtypes = [ctypes.POINTER(vp), ip]
+    L.mpg_destroy.argtypes = [vp]
+    L.mpg_sm_count.argtypes = [vp]
+    L.mpg_conv_plan_create.argtypes = [vp, ctypes.POINTER(ConvDesc), fp, fp, fp, fp, fp, ctypes.POINTER(vp)]
+    L.mpg_conv_plan_run.argtypes = [vp, vp, vp, vp, vp]
+    L.mpg_conv_plan_destroy.argtypes = [vp]
+    L.mpg_conv_plan_kind.argtypes = [vp]
+    L.mpg_conv_plan_flops.argtypes = [vp]
+    L.mpg_conv_plan_flops.restype = dp
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().mpg_last_error().decode("utf-8", "replace")
+        raise MpgError("%s failed (status %d): %s" % (what, status, msg))
+
+
+class Handle:
+    """mpg_handle: one per (process, device)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib().mpg_create(ctypes.byref(self._h), int(device)), "mpg_create")
+        self.device = int(device)
+
+    @property
+    def ptr(self):
+        return self._h
+
+    @property
+    def sm_count(self):
+        return lib().mpg_sm_count(self._h)
+
+    def close(self):
+        if self._h:
+            lib().mpg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+_handles = {}
+
+
+def default_handle(device=0):
+    h = _handles.get(device)
+    if h is None:
+        h = _handles[device] = Handle(device)
+    return h
+
+
+def _fptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _f32c(a):
+    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class ConvPlan:
+    """mpg_conv_plan: fused conv (+shortcut segment) + shift + act + pixel_norm + x2 store.
+
+    weights: list of HWIO float32 arrays (already wscale-multiplied), one per segment.
+    """
+
+    def __init__(self, handle, n, h, w, weights, cstrides, cout, out_cstride, act=None, scales=None,
+                 shift=None, pixel_norm=False, upsample=1, in_upsample=1, stride=1,
+                 in_dtype=BF16, out_dtype=BF16, force_kind=0):
+        self.handle = handle
+        d = ConvDesc()
+        d.n, d.h, d.w = int(n), int(h), int(w)
+        d.nseg = len(weights)
+        ws = [_f32c(wt) for wt in weights]
+        for s, wt in enumerate(ws):
+            assert wt.ndim == 4 and wt.shape[0] == wt.shape[1] and wt.shape[3] == cout, wt.shape
+            d.seg_ksize[s] = wt.shape[0]
+            d.seg_cin[s] = wt.shape[2]
+            d.seg_cstride[s] = int(cstrides[s])
+        d.cout = int(cout)
+        d.act = _ACT_BY_NAME[act] if not isinstance(act, int) else act
+        d.pixel_norm = int(bool(pixel_norm))
+        d.upsample = int(upsample)
+        d.in_upsample = int(in_upsample)
+        d.stride = int(stride)
+        d.force_kind = int(force_kind)
+        d.in_dtype = int(in_dtype)
+        d.out_dtype = int(out_dtype)
+        d.out_cstride = int(out_cstride)
+        self.desc = d
+        scs = [None, None]
+        if scales is not None:
+            for s, sc in enumerate(scales):
+                scs[s] = _f32c(sc)
+        sh = _f32c(shift)
+        self._p = ctypes.c_void_p()
+        check(lib().mpg_conv_plan_create(handle.ptr, ctypes.byref(d), _fptr(ws[0]),
+                                         _fptr(ws[1]) if len(ws) > 1 else None, _fptr(scs[0]), _fptr(scs[1]),
+                                         _fptr(sh), ctypes.byref(self._p)), "mpg_conv_plan_create")
+        self.kind = lib().mpg_conv_plan_kind(self._p)
+        self.flops = lib().mpg_conv_plan_flops(self._p)
+        self.out_h = (d.h + d.stride - 1) // d.stride * d.upsample
+        self.out_w = (d.w + d.stride - 1) // d.stride * d.upsample
+
+    def run(self, x0, x1, y, stream=0):
+        """x0/x1/y: torch CUDA tensors (or raw device pointers); stream: cudaStream_t as int."""
+        p0 = x0.data_ptr() if hasattr(x0, "data_ptr") else int(x0)
+        p1 = None if x1 is None else (x1.data_ptr() if hasattr(x1, "data_ptr") else int(x1))
+        py = y.data_ptr() if hasattr(y, "data_ptr") else int(y)
+        check(lib().mpg_conv_plan_run(self._p, p0, p1, py, stream), "mpg_conv_plan_run")
+
+    def close(self):
+        if self._p:
+            lib().mpg_conv_plan_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

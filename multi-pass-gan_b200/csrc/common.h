@@ -1,0 +1,58 @@
+// Shared host-side plumbing of libmpg_b200: handle, error reporting, driver entry points.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mpg.h"
+
+namespace mpg {
+
+void set_error(const char* fmt, ...);
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace mpg
+
+struct mpg_handle_s {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  mpg::PFN_encodeTiled encode_tiled;
+};
+
+#define MPG_CHECK_ARG(cond, ...)  \
+  do {                            \
+    if (!(cond)) {                \
+      mpg::set_error(__VA_ARGS__); \
+      return MPG_EINVAL;          \
+    }                             \
+  } while (0)
+
+#define MPG_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      mpg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                   \
+                     cudaGetErrorString(e__));                                     \
+      return static_cast<int>(e__);                                                \
+    }                                                                              \
+  } while (0)
+
+namespace mpg {
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// Encode a tiled tensor map; returns 0 or a CUresult.
+int encode_tmap(mpg_handle h, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+                const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,
+                const uint32_t* box, CUtensorMapSwizzle swz);
+
+}  // namespace mpg

@@ -1,0 +1,315 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_igemm.cuh for the design).
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+namespace mpg {
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MPG_ACT_RELU:
+      return fmaxf(v, 0.0f);
+    case MPG_ACT_LRELU:
+      return 0.6f * v + 0.4f * fabsf(v);  // tools_wscale/GAN.py:733-737 (leak 0.2)
+    case MPG_ACT_TANH:
+      return tanhf(v);
+    default:
+      return v;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+struct TileCoord {
+  int n, y0, x0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, const IgemmParams& p) {
+  const int per_img = p.tiles_x * p.tiles_y;
+  TileCoord c;
+  c.n = t / per_img;
+  const int r = t - c.n * per_img;
+  const int ty = r / p.tiles_x;
+  c.y0 = ty * kIgTileH;
+  c.x0 = (r - ty * p.tiles_x) * kIgTileW;
+  return c;
+}
+
+template <int CK>
+__global__ void __launch_bounds__(kIgThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                  const __grid_constant__ CUtensorMap tm_w, const IgemmParams p) {
+  constexpr int RB = CK * 2;  // bytes per pixel row of one K-chunk == swizzle span
+  constexpr uint32_t LAYOUT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
+  constexpr uint32_t SBO = 8u * RB;  // 8 pixels per swizzle group
+  constexpr int KSTEPS = CK / 16;    // UMMA K = 16 bf16
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[kIgMaxStagesA], empty_a[kIgMaxStagesA];
+  __shared__ __align__(8) uint64_t full_b[kIgMaxStagesB], empty_b[kIgMaxStagesB];
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_shift[256];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + static_cast<size_t>(p.na) * p.a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.npad; i += kIgThreads) s_shift[i] = p.shift[i];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x0);
+    if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < p.na; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+    }
+    for (int i = 0; i < p.nb; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== A producer: one halo image per (segment, chunk, dx) ===============
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, p);
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ks = p.seg_ks[s];
+          const int pad = ks >> 1;
+          const uint32_t bytes = static_cast<uint32_t>((kIgTileH + ks - 1) * kIgTileW * RB);
+          const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
+          for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+            for (int dx = 0; dx < ks; ++dx) {
+              mbar_wait(&empty_a[st], ph ^ 1u);
+              mbar_arrive_expect_tx(&full_a[st], bytes);
+              tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK,
+                          tc.x0 + dx - pad, tc.y0 - pad, tc.n);
+              if (++st == p.na) {
+                st = 0;
+                ph ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: one weight tile per (segment, chunk, dx, dy) ==========
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = static_cast<uint32_t>(p.npad * RB);
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int kt = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nk = p.seg_nchunk[s] * p.seg_ks[s] * p.seg_ks[s];
+          for (int i = 0; i < nk; ++i, ++kt) {
+            mbar_wait(&empty_b[st], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_b[st], bytes);
+            tma_load_2d(smB + static_cast<size_t>(st) * p.b_stage_bytes, &tm_w, &full_b[st], 0,
+                        kt * p.npad);
+            if (++st == p.nb) {
+              st = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =========================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.npad);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ks = p.seg_ks[s];
+          for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+            for (int dx = 0; dx < ks; ++dx) {
+              mbar_wait(&full_a[sa], pa);
+              tc_fence_after();
+              const uint32_t a_base = smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes);
+              for (int dy = 0; dy < ks; ++dy) {
+                mbar_wait(&full_b[sb], pb);
+                tc_fence_after();
+                const uint32_t b_base = smem_u32(smB + static_cast<size_t>(sb) * p.b_stage_bytes);
+#pragma unroll
+                for (int acc = 0; acc < 2; ++acc) {
+                  const uint32_t a_row = a_base + static_cast<uint32_t>((dy * kIgTileW + acc * 128) * RB);
+                  const uint32_t d_addr = tmem_base + static_cast<uint32_t>((buf * 2 + acc) * p.npad);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    const uint64_t ad = umma_smem_desc(a_row + k * 32, SBO, LAYOUT);
+                    const uint64_t bd = umma_smem_desc(b_base + k * 32, SBO, LAYOUT);
+                    umma_bf16_ss(d_addr, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+                  }
+                }
+                accumulate = 1;
+                umma_commit(&empty_b[sb]);
+                if (++sb == p.nb) {
+                  sb = 0;
+                  pb ^= 1u;
+                }
+              }
+              umma_commit(&empty_a[sa]);
+              if (++sa == p.na) {
+                sa = 0;
+                pa ^= 1u;
+              }
+            }
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global ==============================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = ew * 32 + lane;
+    const int prow = m >> 4;
+    const int pcol = m & 15;
+    const int ups = p.upsample;
+    const int oh = p.h * ups, ow = p.w * ups;
+    const float inv_c = 1.0f / static_cast<float>(p.cout);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const TileCoord tc = decode_tile(t, p);
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int acc = 0; acc < 2; ++acc) {
+        const int y = tc.y0 + acc * 8 + prow;
+        const int x = tc.x0 + pcol;
+        const bool valid = (y < p.h) && (x < p.w);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                               static_cast<uint32_t>((buf * 2 + acc) * p.npad);
+        float rn = 1.0f;
+        if (p.pixel_norm) {
+          float ssq = 0.0f;
+          for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = apply_act(__uint_as_float(r[j]) + s_shift[c0 + j], p.act);
+              ssq = fmaf(v, v, ssq);
+            }
+          }
+          rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
+        }
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = apply_act(__uint_as_float(r[j]) + s_shift[c0 + j], p.act) * rn;
+          if (valid) {
+            for (int uy = 0; uy < ups; ++uy) {
+              for (int ux = 0; ux < ups; ++ux) {
+                const size_t pix = (static_cast<size_t>(tc.n) * oh + (y * ups + uy)) * ow + (x * ups + ux);
+                if (p.out_dtype == MPG_BF16) {
+                  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + c0;
+                  if (c0 + 8 <= p.out_cstride) {
+                    uint4 q;
+                    q.x = pack_bf16x2(v[0], v[1]);
+                    q.y = pack_bf16x2(v[2], v[3]);
+                    q.z = pack_bf16x2(v[4], v[5]);
+                    q.w = pack_bf16x2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(o) = q;
+                  }
+                  if (c0 + 16 <= p.out_cstride) {
+                    uint4 q;
+                    q.x = pack_bf16x2(v[8], v[9]);
+                    q.y = pack_bf16x2(v[10], v[11]);
+                    q.z = pack_bf16x2(v[12], v[13]);
+                    q.w = pack_bf16x2(v[14], v[15]);
+                    *reinterpret_cast<uint4*>(o + 8) = q;
+                  }
+                } else {
+                  float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + c0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.out_cstride) o[j] = (c0 + j < p.cout) ? v[j] : 0.0f;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+int igemm_set_smem_attr(int ck, size_t smem_bytes) {
+  cudaError_t e;
+  if (ck == 64)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_bytes));
+  else if (ck == 32)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_bytes));
+  else
+    e = cudaFuncSetAttribute(conv_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_bytes));
+  return static_cast<int>(e);
+}
+
+int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
+                 const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (ck == 64)
+    conv_igemm_kernel<64><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+  else if (ck == 32)
+    conv_igemm_kernel<32><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+  else
+    conv_igemm_kernel<16><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace mpg

@@ -1,0 +1,48 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// GEMM view: M = output pixels, N = Cout, K = taps x Cin.
+//   - one CTA per SM, persistent over 16x16-pixel output tiles (2 accumulators of M=128:
+//     8 image rows x 16 pixels each), TMEM double buffered (4 accumulators) so the epilogue of
+//     tile i overlaps the MMAs of tile i+1
+//   - A operand: for every (segment, Cin-chunk, dx) ONE TMA box [rows=16+k-1][16 px][CK ch] is
+//     staged in shared memory; the k vertical taps re-use it by advancing the UMMA descriptor
+//     start address by whole image rows (16 px * row_bytes, a multiple of the swizzle atom), so
+//     L2->smem traffic is k x lower than a load per tap. Out-of-image coordinates are zero
+//     filled by TMA, which IS the "SAME" zero padding of tf.nn.conv2d (tools_wscale/GAN.py:691)
+//   - B operand: packed weights [k-tile][Npad][CK], one TMA box per (segment, chunk, dx, dy)
+//   - epilogue: tcgen05.ld -> +shift -> act -> pixel_norm -> bf16/fp32 store (optionally x2
+//     nearest replicated), all fp32
+#pragma once
+#include "common.h"
+
+namespace mpg {
+
+constexpr int kIgTileW = 16;
+constexpr int kIgTileH = 16;
+constexpr int kIgThreads = 256;
+constexpr int kIgMaxStagesA = 4;
+constexpr int kIgMaxStagesB = 8;
+
+struct IgemmParams {
+  int n, h, w;
+  int tiles_x, tiles_y, num_tiles;
+  int nseg;
+  int seg_ks[2];
+  int seg_nchunk[2];
+  int npad;  // UMMA N
+  int cout;
+  int act, pixel_norm, upsample;
+  int out_dtype, out_cstride;
+  int na, nb;  // pipeline depth of the A / B rings
+  int a_stage_bytes, b_stage_bytes;
+  uint32_t tmem_cols;
+  const float* shift;  // [npad] device
+  void* out;
+};
+
+// ck in {16, 32, 64}; returns cudaError_t as int
+int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
+                 const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+int igemm_set_smem_attr(int ck, size_t smem_bytes);
+
+}  // namespace mpg

@@ -1,0 +1,333 @@
+// Convolution plans: argument validation, weight packing, kernel selection and launch.
+// C-ABI: mpg_conv_plan_* (include/mpg.h).
+#include <string.h>
+
+#include <vector>
+
+#include "common.h"
+#include "conv_direct.cuh"
+#include "conv_igemm.cuh"
+
+struct mpg_conv_plan_s {
+  mpg_handle h;
+  mpg_conv_desc d;
+  int kind;  // 1 igemm, 2 direct
+  double flops;
+  int oh, ow;
+  // ---- igemm
+  int ck, npad;
+  int seg_nchunk[2];
+  void* d_wpacked;
+  float* d_shift;
+  CUtensorMap tm_w;
+  CUtensorMap tm_x[2];
+  const void* tm_x_ptr[2];
+  mpg::IgemmParams ip;
+  size_t smem_bytes;
+  int grid;
+  // ---- direct
+  float* d_wdirect;
+  mpg::DirectParams dp;
+};
+
+namespace {
+
+using namespace mpg;
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+
+CUtensorMapSwizzle swizzle_for(int ck) {
+  return ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int same_pad_before(int in, int k, int s) {
+  const int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;  // TF: pad_before = floor(pad_total / 2)
+}
+
+bool igemm_eligible(const mpg_conv_desc& d) {
+  if (d.in_dtype != MPG_BF16 || d.stride != 1 || d.in_upsample != 1) return false;
+  if (d.cout > 128) return false;
+  if (d.upsample != 1 && d.upsample != 2) return false;
+  for (int s = 0; s < d.nseg; ++s) {
+    const int k = d.seg_ksize[s];
+    if (!(k == 1 || k == 3 || k == 5)) return false;
+    if (d.seg_cstride[s] % 8 != 0) return false;
+    if (d.seg_cin[s] > d.seg_cstride[s]) return false;
+  }
+  if (d.out_dtype == MPG_BF16 && d.out_cstride % 8 != 0) return false;
+  return true;
+}
+
+int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  int maxcin = 0;
+  for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
+  const int ck = maxcin > 32 ? 64 : (maxcin > 16 ? 32 : 16);
+  const int rb = ck * 2;
+  const int npad = round_up(d.cout, 16);
+  p->ck = ck;
+  p->npad = npad;
+  int ktiles = 0;
+  int maxks = 1;
+  for (int s = 0; s < d.nseg; ++s) {
+    p->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
+    ktiles += p->seg_nchunk[s] * d.seg_ksize[s] * d.seg_ksize[s];
+    maxks = d.seg_ksize[s] > maxks ? d.seg_ksize[s] : maxks;
+  }
+  // ---- pack weights: [ktile][npad][ck] bf16, ktile order = (seg, chunk, dx, dy)
+  std::vector<uint16_t> wp(static_cast<size_t>(ktiles) * npad * ck, 0);
+  size_t kt = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const int ks = d.seg_ksize[s], cin = d.seg_cin[s];
+    for (int ch = 0; ch < p->seg_nchunk[s]; ++ch)
+      for (int dx = 0; dx < ks; ++dx)
+        for (int dy = 0; dy < ks; ++dy, ++kt)
+          for (int n = 0; n < d.cout; ++n) {
+            const float sc = scale[s] ? scale[s][n] : 1.0f;
+            for (int c = 0; c < ck; ++c) {
+              const int ci = ch * ck + c;
+              if (ci >= cin) break;
+              const float v = w[s][((static_cast<size_t>(dy) * ks + dx) * cin + ci) * d.cout + n] * sc;
+              wp[(kt * npad + n) * ck + c] = f32_to_bf16_rn(v);
+            }
+          }
+  }
+  MPG_CUDA(cudaMalloc(&p->d_wpacked, wp.size() * 2));
+  MPG_CUDA(cudaMemcpy(p->d_wpacked, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> sh(npad, 0.0f);
+  if (shift)
+    for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
+  MPG_CUDA(cudaMalloc(&p->d_shift, npad * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
+
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ck), static_cast<uint64_t>(ktiles) * npad};
+    const uint64_t strides[1] = {static_cast<uint64_t>(rb)};
+    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(npad)};
+    int r = encode_tmap(p->h, &p->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_wpacked, dims, strides,
+                        box, swizzle_for(ck));
+    if (r) return r;
+  }
+
+  IgemmParams& ip = p->ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.n = d.n;
+  ip.h = d.h;
+  ip.w = d.w;
+  ip.tiles_x = ceil_div(d.w, kIgTileW);
+  ip.tiles_y = ceil_div(d.h, kIgTileH);
+  ip.num_tiles = ip.tiles_x * ip.tiles_y * d.n;
+  ip.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; ++s) {
+    ip.seg_ks[s] = d.seg_ksize[s];
+    ip.seg_nchunk[s] = p->seg_nchunk[s];
+  }
+  ip.npad = npad;
+  ip.cout = d.cout;
+  ip.act = d.act;
+  ip.pixel_norm = d.pixel_norm;
+  ip.upsample = d.upsample;
+  ip.out_dtype = d.out_dtype;
+  ip.out_cstride = d.out_cstride;
+  ip.a_stage_bytes = (kIgTileH + maxks - 1) * kIgTileW * rb;
+  ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
+  ip.b_stage_bytes = round_up(npad * rb, 1024);
+  const int budget = 200 * 1024;
+  ip.nb = 4;
+  int na = (budget - ip.nb * ip.b_stage_bytes) / ip.a_stage_bytes;
+  ip.na = na > kIgMaxStagesA ? kIgMaxStagesA : (na < 2 ? 2 : na);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
+  ip.tmem_cols = cols;
+  ip.shift = p->d_shift;
+  p->smem_bytes = static_cast<size_t>(ip.na) * ip.a_stage_bytes + static_cast<size_t>(ip.nb) * ip.b_stage_bytes + 1024;
+  p->grid = ip.num_tiles < p->h->sm_count ? ip.num_tiles : p->h->sm_count;
+  int r = igemm_set_smem_attr(ck, p->smem_bytes);
+  if (r) {
+    set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes,
+              cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
+  return 0;
+}
+
+int build_direct(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  DirectParams& dp = p->dp;
+  memset(&dp, 0, sizeof(dp));
+  const int coutp = round_up(d.cout, 8);
+  size_t total = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    dp.seg_woff[s] = static_cast<long long>(total);
+    total += static_cast<size_t>(d.seg_ksize[s]) * d.seg_ksize[s] * d.seg_cin[s] * coutp;
+  }
+  std::vector<float> wd(total + coutp, 0.0f);
+  for (int s = 0; s < d.nseg; ++s) {
+    const int ks = d.seg_ksize[s], cin = d.seg_cin[s];
+    for (int tap = 0; tap < ks * ks; ++tap)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int n = 0; n < d.cout; ++n)
+          wd[dp.seg_woff[s] + (static_cast<size_t>(tap) * cin + ci) * coutp + n] =
+              w[s][(static_cast<size_t>(tap) * cin + ci) * d.cout + n] * (scale[s] ? scale[s][n] : 1.0f);
+  }
+  if (shift)
+    for (int n = 0; n < d.cout; ++n) wd[total + n] = shift[n];
+  MPG_CUDA(cudaMalloc(&p->d_wdirect, wd.size() * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_wdirect, wd.data(), wd.size() * sizeof(float), cudaMemcpyHostToDevice));
+  dp.n = d.n;
+  dp.in_upsample = d.in_upsample;
+  dp.h = d.h;
+  dp.w = d.w;
+  dp.src_h = d.h / d.in_upsample;
+  dp.src_w = d.w / d.in_upsample;
+  dp.stride = d.stride;
+  dp.oh = p->oh;
+  dp.ow = p->ow;
+  dp.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; ++s) {
+    dp.seg_ks[s] = d.seg_ksize[s];
+    dp.seg_cin[s] = d.seg_cin[s];
+    dp.seg_cstride[s] = d.seg_cstride[s];
+    dp.seg_pad[s] = same_pad_before(d.h, d.seg_ksize[s], d.stride);
+  }
+  dp.shift = p->d_wdirect + total;
+  dp.cout = d.cout;
+  dp.coutp = coutp;
+  dp.act = d.act;
+  dp.pixel_norm = d.pixel_norm;
+  dp.upsample = d.upsample;
+  dp.in_dtype = d.in_dtype;
+  dp.out_dtype = d.out_dtype;
+  dp.out_cstride = d.out_cstride;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_seg0, const float* w_seg1,
+                         const float* scale_seg0, const float* scale_seg1, const float* shift,
+                         mpg_conv_plan* out) {
+  MPG_CHECK_ARG(h && dsc && out && w_seg0, "mpg_conv_plan_create: null argument");
+  mpg_conv_desc d = *dsc;
+  if (d.upsample <= 0) d.upsample = 1;
+  if (d.in_upsample <= 0) d.in_upsample = 1;
+  if (d.stride <= 0) d.stride = 1;
+  MPG_CHECK_ARG(d.n > 0 && d.h > 0 && d.w > 0, "conv: bad spatial size n=%d h=%d w=%d", d.n, d.h, d.w);
+  MPG_CHECK_ARG(d.nseg == 1 || d.nseg == 2, "conv: nseg must be 1 or 2 (got %d)", d.nseg);
+  MPG_CHECK_ARG(d.nseg == 1 || w_seg1 != nullptr, "conv: segment 1 weights missing");
+  MPG_CHECK_ARG(d.cout > 0 && d.out_cstride >= d.cout, "conv: cout=%d out_cstride=%d", d.cout, d.out_cstride);
+  MPG_CHECK_ARG(d.act >= MPG_ACT_NONE && d.act <= MPG_ACT_TANH, "conv: unknown activation %d", d.act);
+  MPG_CHECK_ARG(d.in_dtype == MPG_BF16 || d.in_dtype == MPG_F32, "conv: bad in_dtype %d", d.in_dtype);
+  MPG_CHECK_ARG(d.out_dtype == MPG_BF16 || d.out_dtype == MPG_F32, "conv: bad out_dtype %d", d.out_dtype);
+  MPG_CHECK_ARG(d.h % d.in_upsample == 0 && d.w % d.in_upsample == 0, "conv: h,w not divisible by in_upsample");
+  for (int s = 0; s < d.nseg; ++s) {
+    MPG_CHECK_ARG(d.seg_cin[s] > 0 && d.seg_cstride[s] >= d.seg_cin[s] && d.seg_ksize[s] > 0,
+                  "conv: segment %d cin=%d cstride=%d k=%d", s, d.seg_cin[s], d.seg_cstride[s], d.seg_ksize[s]);
+  }
+  int kind = d.force_kind;
+  const bool elig = igemm_eligible(d);
+  if (kind == 0) {
+    int mincin = d.seg_cin[0];
+    kind = (elig && d.cout >= 8 && mincin >= 8) ? 1 : 2;
+  }
+  if (kind == 1 && !elig) {
+    mpg::set_error("conv: tcgen05 path needs bf16 input, stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
+    return MPG_ENOSUP;
+  }
+  MPG_CHECK_ARG(kind == 1 || kind == 2, "conv: bad force_kind %d", d.force_kind);
+
+  mpg_conv_plan p = new mpg_conv_plan_s();
+  memset(p, 0, sizeof(*p));
+  p->h = h;
+  p->d = d;
+  p->kind = kind;
+  p->oh = (d.h + d.stride - 1) / d.stride;
+  p->ow = (d.w + d.stride - 1) / d.stride;
+  p->flops = 0.0;
+  for (int s = 0; s < d.nseg; ++s)
+    p->flops += 2.0 * d.n * p->oh * p->ow * static_cast<double>(d.seg_ksize[s]) * d.seg_ksize[s] * d.seg_cin[s] * d.cout;
+  const float* w[2] = {w_seg0, w_seg1};
+  const float* sc[2] = {scale_seg0, scale_seg1};
+  MPG_CUDA(cudaSetDevice(h->device));
+  int r = (kind == 1) ? build_igemm(p, w, sc, shift) : build_direct(p, w, sc, shift);
+  if (r) {
+    mpg_conv_plan_destroy(p);
+    return r;
+  }
+  *out = p;
+  return MPG_OK;
+}
+
+int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, void* stream) {
+  MPG_CHECK_ARG(p && x0 && y, "mpg_conv_plan_run: null argument");
+  MPG_CHECK_ARG(p->d.nseg == 1 || x1 != nullptr, "mpg_conv_plan_run: segment 1 input missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mpg_conv_desc& d = p->d;
+  if (p->kind == 1) {
+    const void* xs[2] = {x0, x1};
+    for (int s = 0; s < d.nseg; ++s) {
+      if (p->tm_x_ptr[s] == xs[s]) continue;
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(xs[s]) & 15) == 0, "conv: input %d not 16-byte aligned", s);
+      const uint64_t cs = static_cast<uint64_t>(d.seg_cstride[s]) * 2;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
+                                static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+      const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+      const uint32_t box[4] = {static_cast<uint32_t>(p->ck), mpg::kIgTileW,
+                               static_cast<uint32_t>(mpg::kIgTileH + d.seg_ksize[s] - 1), 1u};
+      int r = mpg::encode_tmap(p->h, &p->tm_x[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
+                               box, swizzle_for(p->ck));
+      if (r) return r;
+      p->tm_x_ptr[s] = xs[s];
+    }
+    if (d.out_dtype == MPG_BF16)
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
+    mpg::IgemmParams ip = p->ip;
+    ip.out = y;
+    int r = mpg::igemm_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w, ip, p->grid,
+                              p->smem_bytes, st);
+    if (r) {
+      mpg::set_error("conv igemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+      return r;
+    }
+    return MPG_OK;
+  }
+  mpg::DirectParams dp = p->dp;
+  dp.x[0] = x0;
+  dp.x[1] = x1;
+  dp.wts = p->d_wdirect;
+  dp.out = y;
+  int r = mpg::direct_launch(dp, st);
+  if (r) {
+    mpg::set_error("conv direct launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  return MPG_OK;
+}
+
+int mpg_conv_plan_destroy(mpg_conv_plan p) {
+  if (!p) return MPG_OK;
+  if (p->d_wpacked) cudaFree(p->d_wpacked);
+  if (p->d_shift) cudaFree(p->d_shift);
+  if (p->d_wdirect) cudaFree(p->d_wdirect);
+  delete p;
+  return MPG_OK;
+}
+
+int mpg_conv_plan_kind(mpg_conv_plan p) { return p ? p->kind : MPG_EINVAL; }
+double mpg_conv_plan_flops(mpg_conv_plan p) { return p ? p->flops : 0.0; }
+
+}  // extern "C"
