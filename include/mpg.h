@@ -39,6 +39,7 @@ extern "C" {
 
 #define MPG_BF16 0
 #define MPG_F32 1
+#define MPG_F16 2 /* IEEE half: same tcgen05 kind::f16 rate as bf16, 3 more mantissa bits */
 
 typedef struct mpg_handle_s* mpg_handle;
 typedef struct mpg_conv_plan_s* mpg_conv_plan;
@@ -78,8 +79,8 @@ typedef struct mpg_conv_desc {
   int in_upsample;    /* >=1: the conv reads a nearest-upsampled view of x (CUDA-core path) */
   int stride;         /* 1 (tensor-core path) or 2 (CUDA-core path, discriminator)         */
   int force_kind;     /* 0 auto, 1 tcgen05 implicit GEMM, 2 CUDA-core direct               */
-  int in_dtype;       /* MPG_BF16 (tensor-core path) or MPG_F32 (fp32 CUDA-core path)      */
-  int out_dtype;      /* MPG_BF16 or MPG_F32                                               */
+  int in_dtype;       /* MPG_BF16 / MPG_F16 (tensor-core path) or MPG_F32 (CUDA-core path) */
+  int out_dtype;      /* MPG_BF16 / MPG_F16 (same 16-bit type as in_dtype) or MPG_F32      */
   int out_cstride;    /* channel stride (elements) of y; channels >= cout are written as 0 */
 } mpg_conv_desc;
 
@@ -96,6 +97,85 @@ int mpg_conv_plan_destroy(mpg_conv_plan p);
 int mpg_conv_plan_kind(mpg_conv_plan p);
 /* algorithmic FLOPs of one run (2*MAC, un-padded channels) */
 double mpg_conv_plan_flops(mpg_conv_plan p);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor plumbing around the convolutions (bandwidth bound)
+ * -----------------------------------------------------------------------------------------*/
+typedef struct mpg_chan_src {
+  const void* ptr; /* NHWC device tensor [n, oh/factor_h, ow/factor_w, cstride]           */
+  int dtype;       /* MPG_BF16 / MPG_F16 / MPG_F32                                       */
+  int cstride;
+  int c0, nch;     /* channel range [c0, c0+nch) taken from this source                  */
+  int factor_h, factor_w; /* nearest-neighbour replication factors (src = floor(dst/f)) */
+} mpg_chan_src;
+
+/* out[n,y,x,:] = concat_s( src_s[n, y/fh_s, x/fw_s, c0_s : c0_s+nch_s] ), zero padded to out_cstride.
+ * Replaces tf.image.resize_images(.., method=1) / keras resize_images (tools_wscale/GAN.py:517,541;
+ * GAN/multipassGAN-out.py:357,363), tf.concat / tf.slice (GAN/multipassGAN-out.py:330-332,357)
+ * and the fp32 -> bf16 cast + channel padding the tensor-core kernels need. */
+int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* out, int out_dtype,
+                      int out_cstride, int n, int oh, int ow, void* stream);
+
+/* TF 1.x legacy bicubic resize (tf.image.resize_images(.., 2), align_corners=False, Keys A=-0.75,
+ * 1024-entry table; tools_wscale/GAN.py:541 with mode=2 from GAN/multipassGAN-out.py:330):
+ * per-axis tap indices/weights are precomputed once per (in,out) size. */
+int mpg_bicubic_plan_create(mpg_handle h, int in_h, int in_w, int out_h, int out_w, void** plan_out);
+int mpg_bicubic_plan_destroy(void* plan);
+
+/* out[n,y,x] = dens[n,y,x] + R(src[..., src_c])  with R = identity (mode 0, GAN/multipassGAN-out.py:332)
+ * or the TF1 bicubic resize (mode 2, GAN/multipassGAN-out.py:330). dens/out fp32 [n,out_h,out_w]. */
+int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_dtype, int src_cstride,
+                      int src_c, int mode, void* bicubic_plan, int n, int out_h, int out_w, int src_h,
+                      int src_w, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Volume pipeline (replaces the host numpy/scipy code of generate3DUniForNewNetwork,
+ * GAN/multipassGAN-out.py:390-618 and GAN/multipassGAN-4x.py:1090-1169)
+ * -----------------------------------------------------------------------------------------*/
+
+/* Slice assembler. Builds `count` consecutive network-input slices [count, H, W, out_cstride]
+ * starting at slice index `slice0` from the low-res field volume `vol` = fp32 [L0, L1, L2, vol_c].
+ *
+ * Output index (s, i, j) addresses source axis axis_of[0], axis_of[1], axis_of[2] respectively
+ * (a permutation of 0,1,2 = the numpy transposes of GAN/multipassGAN-out.py:402,408,414,466,472,478).
+ * Along each output index k the source coordinate is either the index itself (zoom[k] == 1) or the
+ * align-corners linear interpolation of scipy.ndimage.zoom(order=1) with factor zoom[k]:
+ * coord = o * (n_in-1)/(n_out-1), n_out = n_in*zoom[k] (GAN/multipassGAN-out.py:401-421,
+ * GAN/multipassGAN-4x.py:1095-1103).
+ * Channel c of the output is  chan_scale[c] * lerp(vol[..., chan_src[c]])  for c < nchan
+ * (the velocity-channel swaps of GAN/multipassGAN-out.py:403-405,409-411,473-475 and the
+ * velScale / *upRes factors of GAN/multipassGAN-4x.py:277-283).
+ * If `dens` != NULL, output channel 0 is instead read from the fp32 volume dens[S_s, H, W]
+ * (already laid out in slice order; first-pass density, GAN/multipassGAN-4x.py:1113) and the
+ * field channels follow from channel 1.
+ * If add_adj != 0 two more channels are appended: channel chan_src[0] of slice s-1 and s+1 of the
+ * interpolated stack, zero outside [0, n_slices) (GAN/multipassGAN-out.py:423-436).
+ * Remaining channels up to out_cstride are zero. */
+typedef struct mpg_assemble_desc {
+  int dims[3];      /* L0, L1, L2 of vol                                          */
+  int vol_c;        /* channels of vol                                            */
+  int axis_of[3];   /* source axis addressed by output index (slice, row, col)   */
+  int zoom[3];      /* integer zoom per OUTPUT index (1 = none)                   */
+  int nchan;        /* field channels to emit                                     */
+  int chan_src[8];
+  float chan_scale[8];
+  int add_adj;
+  int out_dtype;    /* MPG_BF16 / MPG_F16 / MPG_F32                               */
+  int out_cstride;
+} mpg_assemble_desc;
+
+int mpg_slice_assemble(mpg_handle h, const mpg_assemble_desc* d, const float* vol, const float* dens,
+                       int slice0, int count, void* out, void* stream);
+
+/* out = permute(in, perm) for a dense fp32 3-D volume in[d0,d1,d2]; out axis k is in axis perm[k]
+ * (numpy .transpose(perm); GAN/multipassGAN-out.py:459,521,587-590, GAN/multipassGAN-4x.py:1142-1144).
+ * If threshold > 0, values < threshold are written as 0 (GAN/multipassGAN-out.py:612-615). */
+int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, int d2, const int perm[3],
+                    float threshold, void* stream);
+
+/* in-place v < threshold -> 0 (GAN/multipassGAN-out.py:614-615, GAN/multipassGAN-4x.py:1156-1157) */
+int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream);
 
 #ifdef __cplusplus
 }

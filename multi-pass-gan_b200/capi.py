@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpg_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 KIND_TCGEN05, KIND_DIRECT = 1, 2
 
 _ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
@@ -42,6 +42,19 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class ChanSrc(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int), ("cstride", ctypes.c_int),
+                ("c0", ctypes.c_int), ("nch", ctypes.c_int), ("factor_h", ctypes.c_int),
+                ("factor_w", ctypes.c_int)]
+
+
+class AssembleDesc(ctypes.Structure):
+    _fields_ = [("dims", ctypes.c_int * 3), ("vol_c", ctypes.c_int), ("axis_of", ctypes.c_int * 3),
+                ("zoom", ctypes.c_int * 3), ("nchan", ctypes.c_int), ("chan_src", ctypes.c_int * 8),
+                ("chan_scale", ctypes.c_float * 8), ("add_adj", ctypes.c_int), ("out_dtype", ctypes.c_int),
+                ("out_cstride", ctypes.c_int)]
+
+
 _lib = None
 
 
@@ -68,6 +81,13 @@ def lib():
     L.mpg_conv_plan_kind.argtypes = [vp]
     L.mpg_conv_plan_flops.argtypes = [vp]
     L.mpg_conv_plan_flops.restype = dp
+    L.mpg_pack_channels.argtypes = [vp, ctypes.POINTER(ChanSrc), ip, vp, ip, ip, ip, ip, ip, vp]
+    L.mpg_bicubic_plan_create.argtypes = [vp, ip, ip, ip, ip, ctypes.POINTER(vp)]
+    L.mpg_bicubic_plan_destroy.argtypes = [vp]
+    L.mpg_dens_residual.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
+    L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
+    L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
+    L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
     _lib = L
     return L
 
@@ -182,3 +202,81 @@ class ConvPlan:
             self.close()
         except Exception:
             pass
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr() if hasattr(t, "data_ptr") else int(t)
+
+
+def pack_channels(handle, sources, out, out_dtype, out_cstride, n, oh, ow, stream=0):
+    """sources: list of (tensor_or_ptr, dtype, cstride, c0, nch, factor_h, factor_w)."""
+    arr = (ChanSrc * len(sources))()
+    for i, (t, dt, cs, c0, nch, fh, fw) in enumerate(sources):
+        arr[i].ptr = _ptr(t)
+        arr[i].dtype, arr[i].cstride, arr[i].c0, arr[i].nch = int(dt), int(cs), int(c0), int(nch)
+        arr[i].factor_h, arr[i].factor_w = int(fh), int(fw)
+    check(lib().mpg_pack_channels(handle.ptr, arr, len(sources), _ptr(out), int(out_dtype), int(out_cstride),
+                                  int(n), int(oh), int(ow), stream), "mpg_pack_channels")
+
+
+class BicubicPlan:
+    def __init__(self, handle, in_h, in_w, out_h, out_w):
+        self._p = ctypes.c_void_p()
+        check(lib().mpg_bicubic_plan_create(handle.ptr, in_h, in_w, out_h, out_w, ctypes.byref(self._p)),
+              "mpg_bicubic_plan_create")
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def close(self):
+        if self._p:
+            lib().mpg_bicubic_plan_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dens_residual(handle, dens, src, src_dtype, src_cstride, src_c, mode, bicubic_plan, n, out_h, out_w, src_h,
+                  src_w, out, stream=0):
+    check(lib().mpg_dens_residual(handle.ptr, _ptr(dens), _ptr(src), int(src_dtype), int(src_cstride), int(src_c),
+                                  int(mode), bicubic_plan.ptr if bicubic_plan is not None else None, int(n),
+                                  int(out_h), int(out_w), int(src_h), int(src_w), _ptr(out), stream),
+          "mpg_dens_residual")
+
+
+def make_assemble_desc(dims, vol_c, axis_of, zoom, chan_src, chan_scale=None, add_adj=False, out_dtype=BF16,
+                       out_cstride=8):
+    d = AssembleDesc()
+    for k in range(3):
+        d.dims[k], d.axis_of[k], d.zoom[k] = int(dims[k]), int(axis_of[k]), int(zoom[k])
+    d.vol_c = int(vol_c)
+    d.nchan = len(chan_src)
+    for c, src in enumerate(chan_src):
+        d.chan_src[c] = int(src)
+        d.chan_scale[c] = float(1.0 if chan_scale is None else chan_scale[c])
+    d.add_adj = int(bool(add_adj))
+    d.out_dtype = int(out_dtype)
+    d.out_cstride = int(out_cstride)
+    return d
+
+
+def slice_assemble(handle, desc, vol, dens, slice0, count, out, stream=0):
+    check(lib().mpg_slice_assemble(handle.ptr, ctypes.byref(desc), _ptr(vol), _ptr(dens), int(slice0), int(count),
+                                   _ptr(out), stream), "mpg_slice_assemble")
+
+
+def transpose3d(handle, src, dst, dims, perm, threshold=0.0, stream=0):
+    pa = (ctypes.c_int * 3)(*[int(x) for x in perm])
+    check(lib().mpg_transpose3d(handle.ptr, _ptr(src), _ptr(dst), int(dims[0]), int(dims[1]), int(dims[2]), pa,
+                                float(threshold), stream), "mpg_transpose3d")
+
+
+def threshold(handle, vol, count, thr, stream=0):
+    check(lib().mpg_threshold(handle.ptr, _ptr(vol), int(count), float(thr), stream), "mpg_threshold")

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -46,6 +47,24 @@ struct mpg_handle_s {
   } while (0)
 
 namespace mpg {
+
+// 16-bit activation element helpers; dtype is MPG_BF16 or MPG_F16 (both 2 bytes)
+__device__ __forceinline__ float h16_to_float(uint16_t raw, int dtype) {
+  if (dtype == MPG_F16) return __half2float(__ushort_as_half(raw));
+  return __uint_as_float(static_cast<uint32_t>(raw) << 16);
+}
+__device__ __forceinline__ uint16_t float_to_h16(float v, int dtype) {
+  if (dtype == MPG_F16) {
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);  // saturate instead of producing inf
+    return __half_as_ushort(__float2half_rn(v));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, int dtype) {
+  return static_cast<uint32_t>(float_to_h16(lo, dtype)) | (static_cast<uint32_t>(float_to_h16(hi, dtype)) << 16);
+}
+inline bool is_h16(int dtype) { return dtype == MPG_BF16 || dtype == MPG_F16; }
+inline bool is_dtype(int dtype) { return dtype == MPG_BF16 || dtype == MPG_F16 || dtype == MPG_F32; }
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

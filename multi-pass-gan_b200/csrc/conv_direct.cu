@@ -33,6 +33,10 @@ template <>
 __device__ __forceinline__ float ld_scalar<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
 }
+template <>
+__device__ __forceinline__ float ld_scalar<__half>(const __half* p) {
+  return __half2float(*p);
+}
 
 // 8 output channels per thread
 template <typename TIn>
@@ -90,12 +94,12 @@ conv_direct_kernel(const DirectParams p) {
   for (int uy = 0; uy < ups; ++uy) {
     for (int ux = 0; ux < ups; ++ux) {
       const long long opix = (static_cast<long long>(n) * fh + (oy * ups + uy)) * fw + (ox * ups + ux);
-      if (p.out_dtype == MPG_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + g * 8;
+      if (p.out_dtype != MPG_F32) {
+        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + opix * p.out_cstride + g * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (g * 8 + j < p.out_cstride)
-            o[j] = __float2bfloat16_rn((g * 8 + j < p.cout) ? act_f(acc[j], p.act) : 0.0f);
+            o[j] = float_to_h16((g * 8 + j < p.cout) ? act_f(acc[j], p.act) : 0.0f, p.out_dtype);
       } else {
         float* o = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + g * 8;
 #pragma unroll
@@ -107,21 +111,26 @@ conv_direct_kernel(const DirectParams p) {
 }
 
 // in-place x * rsqrt(mean_c(x^2) + 1e-8)  (tools_wscale/GAN.py:472-474); one warp per pixel
-template <typename T>
-__global__ void pixel_norm_kernel(T* x, long long npix, int c, int cstride) {
+__global__ void pixel_norm_kernel(void* x, int dtype, long long npix, int c, int cstride) {
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= npix) return;
-  T* px = x + warp * cstride;
+  float* pf = reinterpret_cast<float*>(x) + warp * cstride;
+  uint16_t* ph = reinterpret_cast<uint16_t*>(x) + warp * cstride;
   float ssq = 0.0f;
   for (int i = lane; i < c; i += 32) {
-    const float v = static_cast<float>(px[i]);
+    const float v = dtype == MPG_F32 ? pf[i] : h16_to_float(ph[i], dtype);
     ssq = fmaf(v, v, ssq);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
   const float rn = rsqrtf(ssq / static_cast<float>(c) + 1e-8f);
-  for (int i = lane; i < c; i += 32) px[i] = static_cast<T>(static_cast<float>(px[i]) * rn);
+  for (int i = lane; i < c; i += 32) {
+    if (dtype == MPG_F32)
+      pf[i] = pf[i] * rn;
+    else
+      ph[i] = float_to_h16(h16_to_float(ph[i], dtype) * rn, dtype);
+  }
 }
 
 }  // namespace
@@ -131,6 +140,8 @@ int direct_launch(const DirectParams& p, cudaStream_t stream) {
   dim3 grid(static_cast<unsigned>((npix + 127) / 128), static_cast<unsigned>(p.coutp / 8));
   if (p.in_dtype == MPG_F32)
     conv_direct_kernel<float><<<grid, 128, 0, stream>>>(p);
+  else if (p.in_dtype == MPG_F16)
+    conv_direct_kernel<__half><<<grid, 128, 0, stream>>>(p);
   else
     conv_direct_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -138,12 +149,7 @@ int direct_launch(const DirectParams& p, cudaStream_t stream) {
   if (p.pixel_norm) {
     const long long fpix = npix * p.upsample * p.upsample;
     const unsigned blocks = static_cast<unsigned>((fpix * 32 + 255) / 256);
-    if (p.out_dtype == MPG_F32)
-      pixel_norm_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<float*>(p.out), fpix, p.cout,
-                                                           p.out_cstride);
-    else
-      pixel_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
-          reinterpret_cast<__nv_bfloat16*>(p.out), fpix, p.cout, p.out_cstride);
+    pixel_norm_kernel<<<blocks, 256, 0, stream>>>(p.out, p.out_dtype, fpix, p.cout, p.out_cstride);
     e = cudaGetLastError();
   }
   return static_cast<int>(e);

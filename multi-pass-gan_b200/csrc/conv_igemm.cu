@@ -19,11 +19,6 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
 struct TileCoord {
   int n, y0, x0;
 };
@@ -144,7 +139,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =========================================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.npad);
+      const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -242,22 +237,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             for (int uy = 0; uy < ups; ++uy) {
               for (int ux = 0; ux < ups; ++ux) {
                 const size_t pix = (static_cast<size_t>(tc.n) * oh + (y * ups + uy)) * ow + (x * ups + ux);
-                if (p.out_dtype == MPG_BF16) {
-                  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + c0;
+                if (p.out_dtype != MPG_F32) {
+                  const int od = p.out_dtype;
+                  uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + c0;
                   if (c0 + 8 <= p.out_cstride) {
                     uint4 q;
-                    q.x = pack_bf16x2(v[0], v[1]);
-                    q.y = pack_bf16x2(v[2], v[3]);
-                    q.z = pack_bf16x2(v[4], v[5]);
-                    q.w = pack_bf16x2(v[6], v[7]);
+                    q.x = pack_h16x2(v[0], v[1], od);
+                    q.y = pack_h16x2(v[2], v[3], od);
+                    q.z = pack_h16x2(v[4], v[5], od);
+                    q.w = pack_h16x2(v[6], v[7], od);
                     *reinterpret_cast<uint4*>(o) = q;
                   }
                   if (c0 + 16 <= p.out_cstride) {
                     uint4 q;
-                    q.x = pack_bf16x2(v[8], v[9]);
-                    q.y = pack_bf16x2(v[10], v[11]);
-                    q.z = pack_bf16x2(v[12], v[13]);
-                    q.w = pack_bf16x2(v[14], v[15]);
+                    q.x = pack_h16x2(v[8], v[9], od);
+                    q.y = pack_h16x2(v[10], v[11], od);
+                    q.z = pack_h16x2(v[12], v[13], od);
+                    q.w = pack_h16x2(v[14], v[15], od);
                     *reinterpret_cast<uint4*>(o + 8) = q;
                   }
                 } else {
@@ -287,7 +283,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
 }  // namespace
 
+// The attribute is per kernel instantiation, not per plan: only ever raise it.
+static size_t g_smem_attr[3] = {0, 0, 0};
+
 int igemm_set_smem_attr(int ck, size_t smem_bytes) {
+  const int slot = ck == 64 ? 0 : (ck == 32 ? 1 : 2);
+  if (smem_bytes <= g_smem_attr[slot]) return 0;
   cudaError_t e;
   if (ck == 64)
     e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -298,6 +299,7 @@ int igemm_set_smem_attr(int ck, size_t smem_bytes) {
   else
     e = cudaFuncSetAttribute(conv_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem_bytes));
+  if (e == cudaSuccess) g_smem_attr[slot] = smem_bytes;
   return static_cast<int>(e);
 }
 

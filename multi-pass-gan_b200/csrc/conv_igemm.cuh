@@ -32,6 +32,7 @@ struct IgemmParams {
   int npad;  // UMMA N
   int cout;
   int act, pixel_norm, upsample;
+  int in_dtype;  // MPG_BF16 or MPG_F16 operands
   int out_dtype, out_cstride;
   int na, nb;  // pipeline depth of the A / B rings
   int a_stage_bytes, b_stage_bytes;

@@ -43,6 +43,13 @@ uint16_t f32_to_bf16_rn(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 
+uint16_t f32_to_f16_rn(float f) {
+  __half hv = __float2half_rn(f);
+  uint16_t r;
+  memcpy(&r, &hv, 2);
+  return r;
+}
+
 CUtensorMapSwizzle swizzle_for(int ck) {
   return ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                   : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -56,7 +63,8 @@ int same_pad_before(int in, int k, int s) {
 }
 
 bool igemm_eligible(const mpg_conv_desc& d) {
-  if (d.in_dtype != MPG_BF16 || d.stride != 1 || d.in_upsample != 1) return false;
+  if (!is_h16(d.in_dtype) || d.stride != 1 || d.in_upsample != 1) return false;
+  if (d.out_dtype != MPG_F32 && d.out_dtype != d.in_dtype) return false;
   if (d.cout > 128) return false;
   if (d.upsample != 1 && d.upsample != 2) return false;
   for (int s = 0; s < d.nseg; ++s) {
@@ -65,7 +73,7 @@ bool igemm_eligible(const mpg_conv_desc& d) {
     if (d.seg_cstride[s] % 8 != 0) return false;
     if (d.seg_cin[s] > d.seg_cstride[s]) return false;
   }
-  if (d.out_dtype == MPG_BF16 && d.out_cstride % 8 != 0) return false;
+  if (d.out_dtype != MPG_F32 && d.out_cstride % 8 != 0) return false;
   return true;
 }
 
@@ -99,7 +107,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
               const int ci = ch * ck + c;
               if (ci >= cin) break;
               const float v = w[s][((static_cast<size_t>(dy) * ks + dx) * cin + ci) * d.cout + n] * sc;
-              wp[(kt * npad + n) * ck + c] = f32_to_bf16_rn(v);
+              wp[(kt * npad + n) * ck + c] = d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v);
             }
           }
   }
@@ -115,7 +123,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     const uint64_t dims[2] = {static_cast<uint64_t>(ck), static_cast<uint64_t>(ktiles) * npad};
     const uint64_t strides[1] = {static_cast<uint64_t>(rb)};
     const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(npad)};
-    int r = encode_tmap(p->h, &p->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_wpacked, dims, strides,
+    int r = encode_tmap(p->h, &p->tm_w, d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_wpacked, dims, strides,
                         box, swizzle_for(ck));
     if (r) return r;
   }
@@ -138,6 +146,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.act = d.act;
   ip.pixel_norm = d.pixel_norm;
   ip.upsample = d.upsample;
+  ip.in_dtype = d.in_dtype;
   ip.out_dtype = d.out_dtype;
   ip.out_cstride = d.out_cstride;
   ip.a_stage_bytes = (kIgTileH + maxks - 1) * kIgTileW * rb;
@@ -231,8 +240,8 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   MPG_CHECK_ARG(d.nseg == 1 || w_seg1 != nullptr, "conv: segment 1 weights missing");
   MPG_CHECK_ARG(d.cout > 0 && d.out_cstride >= d.cout, "conv: cout=%d out_cstride=%d", d.cout, d.out_cstride);
   MPG_CHECK_ARG(d.act >= MPG_ACT_NONE && d.act <= MPG_ACT_TANH, "conv: unknown activation %d", d.act);
-  MPG_CHECK_ARG(d.in_dtype == MPG_BF16 || d.in_dtype == MPG_F32, "conv: bad in_dtype %d", d.in_dtype);
-  MPG_CHECK_ARG(d.out_dtype == MPG_BF16 || d.out_dtype == MPG_F32, "conv: bad out_dtype %d", d.out_dtype);
+  MPG_CHECK_ARG(mpg::is_dtype(d.in_dtype), "conv: bad in_dtype %d", d.in_dtype);
+  MPG_CHECK_ARG(mpg::is_dtype(d.out_dtype), "conv: bad out_dtype %d", d.out_dtype);
   MPG_CHECK_ARG(d.h % d.in_upsample == 0 && d.w % d.in_upsample == 0, "conv: h,w not divisible by in_upsample");
   for (int s = 0; s < d.nseg; ++s) {
     MPG_CHECK_ARG(d.seg_cin[s] > 0 && d.seg_cstride[s] >= d.seg_cin[s] && d.seg_ksize[s] > 0,
@@ -241,11 +250,14 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   int kind = d.force_kind;
   const bool elig = igemm_eligible(d);
   if (kind == 0) {
-    int mincin = d.seg_cin[0];
-    kind = (elig && d.cout >= 8 && mincin >= 8) ? 1 : 2;
+    // thin layers (few input or output channels) are HBM-bound: CUDA cores; the rest: tensor cores.
+    // Narrow shortcut segments (e.g. the 4-channel 1x1 of ru1) ride along, zero-filled by TMA.
+    int maxcin = 0;
+    for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
+    kind = (elig && d.cout >= 8 && maxcin >= 8) ? 1 : 2;
   }
   if (kind == 1 && !elig) {
-    mpg::set_error("conv: tcgen05 path needs bf16 input, stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
+    mpg::set_error("conv: tcgen05 path needs bf16/f16 input (same 16-bit output type or f32), stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
     return MPG_ENOSUP;
   }
   MPG_CHECK_ARG(kind == 1 || kind == 2, "conv: bad force_kind %d", d.force_kind);
@@ -288,12 +300,12 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
       const uint32_t box[4] = {static_cast<uint32_t>(p->ck), mpg::kIgTileW,
                                static_cast<uint32_t>(mpg::kIgTileH + d.seg_ksize[s] - 1), 1u};
-      int r = mpg::encode_tmap(p->h, &p->tm_x[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
+      int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
                                box, swizzle_for(p->ck));
       if (r) return r;
       p->tm_x_ptr[s] = xs[s];
     }
-    if (d.out_dtype == MPG_BF16)
+    if (d.out_dtype != MPG_F32)
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
     mpg::IgemmParams ip = p->ip;
     ip.out = y;

@@ -1,0 +1,239 @@
+// Bandwidth-bound tensor plumbing around the convolutions:
+//   mpg_pack_channels   nearest-neighbour resize + channel slice/concat + dtype cast + channel padding
+//                       (tf.image.resize_images(...,1) tools_wscale/GAN.py:517,541, GAN/multipassGAN-out.py:357;
+//                        tf.concat / tf.slice GAN/multipassGAN-out.py:330-332,357)
+//   mpg_dens_residual   out = dens + {channel | TF1 legacy bicubic resize of channel} of the network input
+//                       (addBicubicUpsample, GAN/multipassGAN-out.py:327-332 -> tools_wscale/GAN.py:541 mode 2)
+#include <vector>
+
+#include "common.h"
+
+namespace mpg {
+namespace {
+
+constexpr int kMaxSrc = 8;
+
+struct PackSrc {
+  const void* ptr;
+  int dtype, cstride, c0, nch, fh, fw;
+};
+struct PackParams {
+  PackSrc src[kMaxSrc];
+  int nsrc;
+  int n, oh, ow;
+  int out_dtype, out_cstride;
+  void* out;
+};
+
+__global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(p.n) * p.oh * p.ow;
+  if (pix >= npix) return;
+  const int x = static_cast<int>(pix % p.ow);
+  const long long r = pix / p.ow;
+  const int y = static_cast<int>(r % p.oh);
+  const int n = static_cast<int>(r / p.oh);
+  int oc = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const PackSrc& q = p.src[s];
+    const int sh = p.oh / q.fh, sw = p.ow / q.fw;
+    const long long spix = (static_cast<long long>(n) * sh + y / q.fh) * sw + x / q.fw;
+    for (int c = 0; c < q.nch; ++c, ++oc) {
+      float v;
+      if (q.dtype == MPG_F32)
+        v = __ldg(reinterpret_cast<const float*>(q.ptr) + spix * q.cstride + q.c0 + c);
+      else
+        v = h16_to_float(reinterpret_cast<const uint16_t*>(q.ptr)[spix * q.cstride + q.c0 + c], q.dtype);
+      if (p.out_dtype == MPG_F32)
+        reinterpret_cast<float*>(p.out)[pix * p.out_cstride + oc] = v;
+      else
+        reinterpret_cast<uint16_t*>(p.out)[pix * p.out_cstride + oc] = float_to_h16(v, p.out_dtype);
+    }
+  }
+  for (; oc < p.out_cstride; ++oc) {
+    if (p.out_dtype == MPG_F32)
+      reinterpret_cast<float*>(p.out)[pix * p.out_cstride + oc] = 0.0f;
+    else
+      reinterpret_cast<uint16_t*>(p.out)[pix * p.out_cstride + oc] = 0;
+  }
+}
+
+struct DensParams {
+  const float* dens;  // [n, oh, ow]
+  const void* src;    // [n, sh, sw, cstride]
+  int src_dtype, src_cstride, src_c;
+  int mode;  // 0: same-resolution channel add, 2: TF1 legacy bicubic
+  int n, oh, ow, sh, sw;
+  const int* iy;    // [oh][4]
+  const float* wy;  // [oh][4]
+  const int* ix;    // [ow][4]
+  const float* wx;  // [ow][4]
+  float* out;       // [n, oh, ow]
+};
+
+__device__ __forceinline__ float src_at(const DensParams& p, int n, int y, int x) {
+  const long long o = ((static_cast<long long>(n) * p.sh + y) * p.sw + x) * p.src_cstride + p.src_c;
+  if (p.src_dtype == MPG_F32) return __ldg(reinterpret_cast<const float*>(p.src) + o);
+  return h16_to_float(reinterpret_cast<const uint16_t*>(p.src)[o], p.src_dtype);
+}
+
+__global__ void __launch_bounds__(256) dens_residual_kernel(const DensParams p) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(p.n) * p.oh * p.ow;
+  if (pix >= npix) return;
+  const int x = static_cast<int>(pix % p.ow);
+  const long long r = pix / p.ow;
+  const int y = static_cast<int>(r % p.oh);
+  const int n = static_cast<int>(r / p.oh);
+  float add;
+  if (p.mode == 0) {
+    add = src_at(p, n, y, x);
+  } else {
+    // TF1 ResizeBicubic: interpolate along x for each of the 4 rows, then along y (fp32)
+    add = 0.0f;
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+      const int sy = p.iy[y * 4 + ty];
+      float row = 0.0f;
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx) row += src_at(p, n, sy, p.ix[x * 4 + tx]) * p.wx[x * 4 + tx];
+      add += row * p.wy[y * 4 + ty];
+    }
+  }
+  p.out[pix] = p.dens[pix] + add;
+}
+
+// TF1 bicubic coefficient table (Keys, A = -0.75, 1024 entries), fp32 like resize_bicubic_op.cc
+void bicubic_axis(int in_size, int out_size, std::vector<int>& idx, std::vector<float>& wts) {
+  static float tab[1025][2];
+  static bool init = false;
+  if (!init) {
+    const float a = -0.75f;
+    for (int i = 0; i <= 1024; ++i) {
+      float x = static_cast<float>(i) / 1024.0f;
+      tab[i][0] = ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+      x += 1.0f;
+      tab[i][1] = ((a * x - 5.0f * a) * x + 8.0f * a) * x - 4.0f * a;
+    }
+    init = true;
+  }
+  idx.resize(static_cast<size_t>(out_size) * 4);
+  wts.resize(static_cast<size_t>(out_size) * 4);
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  for (int o = 0; o < out_size; ++o) {
+    const float in_f = static_cast<float>(o) * scale;
+    const int i = static_cast<int>(floorf(in_f));
+    const float delta = in_f - static_cast<float>(i);
+    const int off = static_cast<int>(lrintf(delta * 1024.0f));
+    wts[o * 4 + 0] = tab[off][1];
+    wts[o * 4 + 1] = tab[off][0];
+    wts[o * 4 + 2] = tab[1024 - off][0];
+    wts[o * 4 + 3] = tab[1024 - off][1];
+    for (int t = 0; t < 4; ++t) {
+      int s = i - 1 + t;
+      s = s < 0 ? 0 : (s > in_size - 1 ? in_size - 1 : s);
+      idx[o * 4 + t] = s;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mpg
+
+extern "C" {
+
+int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* out, int out_dtype, int out_cstride,
+                      int n, int oh, int ow, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && srcs && out, "mpg_pack_channels: null argument");
+  MPG_CHECK_ARG(nsrc >= 1 && nsrc <= kMaxSrc, "mpg_pack_channels: nsrc %d not in [1,%d]", nsrc, kMaxSrc);
+  PackParams p;
+  int total = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    MPG_CHECK_ARG(srcs[s].ptr && srcs[s].factor_h >= 1 && srcs[s].factor_w >= 1 && is_dtype(srcs[s].dtype),
+                  "pack: bad source %d", s);
+    MPG_CHECK_ARG(oh % srcs[s].factor_h == 0 && ow % srcs[s].factor_w == 0, "pack: size not divisible by factor");
+    MPG_CHECK_ARG(srcs[s].c0 >= 0 && srcs[s].nch > 0 && srcs[s].c0 + srcs[s].nch <= srcs[s].cstride,
+                  "pack: channel range of source %d", s);
+    p.src[s] = {srcs[s].ptr, srcs[s].dtype, srcs[s].cstride, srcs[s].c0, srcs[s].nch, srcs[s].factor_h,
+                srcs[s].factor_w};
+    total += srcs[s].nch;
+  }
+  MPG_CHECK_ARG(total <= out_cstride, "pack: %d channels do not fit out_cstride %d", total, out_cstride);
+  p.nsrc = nsrc;
+  p.n = n;
+  p.oh = oh;
+  p.ow = ow;
+  p.out_dtype = out_dtype;
+  p.out_cstride = out_cstride;
+  p.out = out;
+  const long long npix = static_cast<long long>(n) * oh * ow;
+  pack_channels_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_bicubic_plan_create(mpg_handle h, int in_h, int in_w, int out_h, int out_w, void** plan_out) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && plan_out && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "bicubic plan: bad argument");
+  std::vector<int> iy, ix;
+  std::vector<float> wy, wx;
+  bicubic_axis(in_h, out_h, iy, wy);
+  bicubic_axis(in_w, out_w, ix, wx);
+  // layout: [iy | ix] ints then [wy | wx] floats in one allocation
+  const size_t ni = iy.size() + ix.size();
+  const size_t bytes = ni * sizeof(int) + ni * sizeof(float);
+  char* d = nullptr;
+  MPG_CUDA(cudaMalloc(&d, bytes));
+  MPG_CUDA(cudaMemcpy(d, iy.data(), iy.size() * 4, cudaMemcpyHostToDevice));
+  MPG_CUDA(cudaMemcpy(d + iy.size() * 4, ix.data(), ix.size() * 4, cudaMemcpyHostToDevice));
+  MPG_CUDA(cudaMemcpy(d + ni * 4, wy.data(), wy.size() * 4, cudaMemcpyHostToDevice));
+  MPG_CUDA(cudaMemcpy(d + ni * 4 + wy.size() * 4, wx.data(), wx.size() * 4, cudaMemcpyHostToDevice));
+  *plan_out = d;
+  return MPG_OK;
+}
+
+int mpg_bicubic_plan_destroy(void* plan) {
+  if (plan) cudaFree(plan);
+  return MPG_OK;
+}
+
+int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_dtype, int src_cstride, int src_c,
+                      int mode, void* bicubic_plan, int n, int out_h, int out_w, int src_h, int src_w, float* out,
+                      void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && dens && src && out, "mpg_dens_residual: null argument");
+  MPG_CHECK_ARG(mode == 0 || mode == 2, "mpg_dens_residual: mode must be 0 (channel add) or 2 (TF1 bicubic)");
+  MPG_CHECK_ARG(mode == 2 || (src_h == out_h && src_w == out_w), "mpg_dens_residual: mode 0 needs equal sizes");
+  MPG_CHECK_ARG(mode == 0 || bicubic_plan != nullptr, "mpg_dens_residual: bicubic plan missing");
+  DensParams p;
+  p.dens = dens;
+  p.src = src;
+  p.src_dtype = src_dtype;
+  p.src_cstride = src_cstride;
+  p.src_c = src_c;
+  p.mode = mode;
+  p.n = n;
+  p.oh = out_h;
+  p.ow = out_w;
+  p.sh = src_h;
+  p.sw = src_w;
+  if (mode == 2) {
+    const char* d = static_cast<const char*>(bicubic_plan);
+    const size_t ni = static_cast<size_t>(out_h + out_w) * 4;
+    p.iy = reinterpret_cast<const int*>(d);
+    p.ix = p.iy + static_cast<size_t>(out_h) * 4;
+    p.wy = reinterpret_cast<const float*>(d + ni * 4);
+    p.wx = p.wy + static_cast<size_t>(out_h) * 4;
+  } else {
+    p.iy = p.ix = nullptr;
+    p.wy = p.wx = nullptr;
+  }
+  p.out = out;
+  const long long npix = static_cast<long long>(n) * out_h * out_w;
+  dens_residual_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // extern "C"

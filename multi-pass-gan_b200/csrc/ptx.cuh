@@ -154,9 +154,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo,
   d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// kind::f16 instruction descriptor: (bf16 x bf16 | f16 x f16) -> fp32, both operands K-major.
+// ab_format: 1 = BF16, 0 = F16 (PTX instruction-descriptor a_format/b_format fields).
+__host__ __device__ constexpr uint32_t umma_idesc_f16kind(int m, int n, uint32_t ab_format) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 

@@ -1,0 +1,262 @@
+// Volume pipeline kernels (HBM-bandwidth bound): slice assembler, 3-D axis permutation, threshold.
+// They replace the host-side numpy / scipy code of generate3DUniForNewNetwork
+// (GAN/multipassGAN-out.py:390-618, GAN/multipassGAN-4x.py:1090-1169); see include/mpg.h.
+#include "common.h"
+
+namespace mpg {
+namespace {
+
+struct AsmParams {
+  int dims[3];
+  int vol_c;
+  int axis_of[3];
+  int zoom[3];
+  int nchan;
+  int chan_src[8];
+  float chan_scale[8];
+  int add_adj;
+  int out_dtype, out_cstride;
+  int odims[3];  // n_slices, H, W of the interpolated stack
+  long long vstride[3];
+  const float* vol;
+  const float* dens;
+  int slice0, count;
+  void* out;
+};
+
+struct Lerp {
+  int lo, hi;
+  float t;
+};
+
+// align-corners coordinate of scipy.ndimage.zoom(order=1): o * (n_in-1)/(n_out-1)
+__device__ __forceinline__ Lerp lerp_coord(int o, int n_in, int zoom) {
+  Lerp l;
+  if (zoom == 1) {
+    l.lo = l.hi = o;
+    l.t = 0.0f;
+    return l;
+  }
+  const int n_out = n_in * zoom;
+  const double c = (n_out > 1) ? static_cast<double>(o) * static_cast<double>(n_in - 1) / static_cast<double>(n_out - 1) : 0.0;
+  int lo = static_cast<int>(floor(c));
+  lo = lo < 0 ? 0 : (lo > n_in - 1 ? n_in - 1 : lo);
+  l.lo = lo;
+  l.hi = lo + 1 > n_in - 1 ? n_in - 1 : lo + 1;
+  l.t = static_cast<float>(c - static_cast<double>(lo));
+  return l;
+}
+
+__device__ __forceinline__ float sample(const AsmParams& p, const Lerp (&l)[3], int ch) {
+  // l[k] addresses source axis axis_of[k]; up to 8 corners, skipping zero-weight ones
+  float acc = 0.0f;
+#pragma unroll
+  for (int c0 = 0; c0 < 2; ++c0) {
+    const float w0 = c0 ? l[0].t : 1.0f - l[0].t;
+    if (w0 == 0.0f) continue;
+    const long long o0 = static_cast<long long>(c0 ? l[0].hi : l[0].lo) * p.vstride[0];
+#pragma unroll
+    for (int c1 = 0; c1 < 2; ++c1) {
+      const float w1 = c1 ? l[1].t : 1.0f - l[1].t;
+      if (w1 == 0.0f) continue;
+      const long long o1 = o0 + static_cast<long long>(c1 ? l[1].hi : l[1].lo) * p.vstride[1];
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const float w2 = c2 ? l[2].t : 1.0f - l[2].t;
+        if (w2 == 0.0f) continue;
+        const long long o2 = o1 + static_cast<long long>(c2 ? l[2].hi : l[2].lo) * p.vstride[2];
+        acc = fmaf(w0 * w1 * w2, __ldg(p.vol + o2 * p.vol_c + ch), acc);
+      }
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) slice_assemble_kernel(const AsmParams p) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int H = p.odims[1], W = p.odims[2];
+  const long long npix = static_cast<long long>(p.count) * H * W;
+  if (pix >= npix) return;
+  const int j = static_cast<int>(pix % W);
+  const long long r = pix / W;
+  const int i = static_cast<int>(r % H);
+  const int s = p.slice0 + static_cast<int>(r / H);
+
+  Lerp l[3];
+  l[0] = lerp_coord(s, p.dims[p.axis_of[0]], p.zoom[0]);
+  l[1] = lerp_coord(i, p.dims[p.axis_of[1]], p.zoom[1]);
+  l[2] = lerp_coord(j, p.dims[p.axis_of[2]], p.zoom[2]);
+
+  float v[16];
+  int oc = 0;
+  if (p.dens) v[oc++] = __ldg(p.dens + (static_cast<long long>(s) * H + i) * W + j);
+  for (int c = 0; c < p.nchan; ++c) v[oc++] = p.chan_scale[c] * sample(p, l, p.chan_src[c]);
+  if (p.add_adj) {
+    for (int d = -1; d <= 1; d += 2) {
+      const int sn = s + d;
+      float a = 0.0f;
+      if (sn >= 0 && sn < p.odims[0]) {
+        Lerp ln[3] = {lerp_coord(sn, p.dims[p.axis_of[0]], p.zoom[0]), l[1], l[2]};
+        a = p.chan_scale[0] * sample(p, ln, p.chan_src[0]);
+      }
+      v[oc++] = a;
+    }
+  }
+  if (p.out_dtype == MPG_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride;
+    for (int c = 0; c < p.out_cstride; ++c) o[c] = c < oc ? v[c] : 0.0f;
+  } else {
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride;
+    for (int c = 0; c < p.out_cstride; ++c) o[c] = float_to_h16(c < oc ? v[c] : 0.0f, p.out_dtype);
+  }
+}
+
+// 32x32 shared-memory tile transpose between input axis 2 (x) and input axis `a` (y); axis `b` is batch.
+__global__ void __launch_bounds__(256)
+transpose_tile_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, long long in_sy,
+                      long long in_sb, long long out_sx, long long out_sb, float threshold) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const long long bi = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int x = bx + tx, y = by + ty + k;
+    if (x < nx && y < ny) tile[ty + k][tx] = in[bi * in_sb + static_cast<long long>(y) * in_sy + x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int y = by + tx, x = bx + ty + k;
+    if (x < nx && y < ny) {
+      float v = tile[tx][ty + k];
+      if (v < threshold) v = 0.0f;
+      out[bi * out_sb + static_cast<long long>(x) * out_sx + y] = v;
+    }
+  }
+}
+
+// perm[2] == 2: rows stay contiguous, only the two outer axes move (or nothing moves)
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int d0, int d1, int d2, long long so0,
+                    long long so1, float threshold) {
+  const long long row = blockIdx.x;  // input row index = i0 * d1 + i1
+  const int i0 = static_cast<int>(row / d1), i1 = static_cast<int>(row % d1);
+  const float* src = in + row * d2;
+  float* dst = out + i0 * so0 + i1 * so1;
+  for (int x = threadIdx.x; x < d2; x += blockDim.x) {
+    float v = src[x];
+    if (v < threshold) v = 0.0f;
+    dst[x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) threshold_kernel(float* v, long long n, float thr) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = v[i];
+    if (x < thr) v[i] = 0.0f;
+  }
+}
+
+}  // namespace
+}  // namespace mpg
+
+extern "C" {
+
+int mpg_slice_assemble(mpg_handle h, const mpg_assemble_desc* d, const float* vol, const float* dens, int slice0,
+                       int count, void* out, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && d && vol && out, "mpg_slice_assemble: null argument");
+  int seen[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    MPG_CHECK_ARG(d->axis_of[k] >= 0 && d->axis_of[k] < 3, "assemble: axis_of[%d]=%d", k, d->axis_of[k]);
+    seen[d->axis_of[k]]++;
+    MPG_CHECK_ARG(d->zoom[k] >= 1 && d->dims[k] >= 1, "assemble: zoom/dims must be >= 1");
+  }
+  MPG_CHECK_ARG(seen[0] == 1 && seen[1] == 1 && seen[2] == 1, "assemble: axis_of is not a permutation");
+  MPG_CHECK_ARG(d->nchan >= 1 && d->nchan <= 8, "assemble: nchan %d not in [1,8]", d->nchan);
+  const int total = d->nchan + (dens ? 1 : 0) + (d->add_adj ? 2 : 0);
+  MPG_CHECK_ARG(total <= d->out_cstride && total <= 16, "assemble: %d channels > out_cstride %d", total, d->out_cstride);
+  AsmParams p;
+  for (int k = 0; k < 3; ++k) {
+    p.dims[k] = d->dims[k];
+    p.axis_of[k] = d->axis_of[k];
+    p.zoom[k] = d->zoom[k];
+  }
+  const long long st[3] = {static_cast<long long>(d->dims[1]) * d->dims[2], d->dims[2], 1};
+  for (int k = 0; k < 3; ++k) {
+    p.odims[k] = d->dims[d->axis_of[k]] * d->zoom[k];
+    p.vstride[k] = st[d->axis_of[k]];
+  }
+  p.vol_c = d->vol_c;
+  p.nchan = d->nchan;
+  for (int c = 0; c < 8; ++c) {
+    p.chan_src[c] = d->chan_src[c];
+    p.chan_scale[c] = d->chan_scale[c];
+    if (c < d->nchan) MPG_CHECK_ARG(d->chan_src[c] >= 0 && d->chan_src[c] < d->vol_c, "assemble: chan_src[%d]", c);
+  }
+  p.add_adj = d->add_adj;
+  p.out_dtype = d->out_dtype;
+  p.out_cstride = d->out_cstride;
+  p.vol = vol;
+  p.dens = dens;
+  p.slice0 = slice0;
+  p.count = count;
+  p.out = out;
+  MPG_CHECK_ARG(slice0 >= 0 && count >= 1 && slice0 + count <= p.odims[0], "assemble: slices [%d,%d) outside [0,%d)",
+                slice0, slice0 + count, p.odims[0]);
+  const long long npix = static_cast<long long>(count) * p.odims[1] * p.odims[2];
+  slice_assemble_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, int d2, const int perm[3],
+                    float threshold, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && in && out && perm, "mpg_transpose3d: null argument");
+  MPG_CHECK_ARG(in != out, "mpg_transpose3d: in-place permutation is not supported");
+  const int d[3] = {d0, d1, d2};
+  int seen[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    MPG_CHECK_ARG(perm[k] >= 0 && perm[k] < 3, "transpose3d: perm[%d]=%d", k, perm[k]);
+    seen[perm[k]]++;
+  }
+  MPG_CHECK_ARG(seen[0] == 1 && seen[1] == 1 && seen[2] == 1, "transpose3d: perm is not a permutation");
+  MPG_CHECK_ARG(d0 > 0 && d1 > 0 && d2 > 0, "transpose3d: empty volume");
+  const long long od[3] = {d[perm[0]], d[perm[1]], d[perm[2]]};
+  const long long st_out[3] = {od[1] * od[2], od[2], 1};
+  long long so[3];  // output stride of each INPUT axis
+  for (int k = 0; k < 3; ++k) so[perm[k]] = st_out[k];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float thr = threshold > 0.0f ? threshold : -INFINITY;
+  if (perm[2] == 2) {
+    permute_rows_kernel<<<static_cast<unsigned>(static_cast<long long>(d0) * d1), 256, 0, st>>>(in, out, d0, d1, d2,
+                                                                                                so[0], so[1], thr);
+  } else {
+    const int a = perm[2];
+    const int b = 3 - 2 - a;  // the remaining axis (0 or 1)
+    const long long st_in[3] = {static_cast<long long>(d1) * d2, d2, 1};
+    MPG_CHECK_ARG(d[b] <= 65535, "transpose3d: batch axis %d exceeds 65535", d[b]);
+    dim3 grid(static_cast<unsigned>(ceil_div(d2, 32)), static_cast<unsigned>(ceil_div(d[a], 32)),
+              static_cast<unsigned>(d[b]));
+    transpose_tile_kernel<<<grid, 256, 0, st>>>(in, out, d2, d[a], st_in[a], st_in[b], so[2], so[b], thr);
+  }
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && vol && count >= 0, "mpg_threshold: bad argument");
+  if (count == 0) return MPG_OK;
+  long long blocks = (count + 255) / 256;
+  const long long cap = static_cast<long long>(h->sm_count) * 16;
+  if (blocks > cap) blocks = cap;
+  threshold_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(vol, count, threshold);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // extern "C"

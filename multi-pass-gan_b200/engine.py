@@ -1,0 +1,412 @@
+"""Lowers a recorded graph (graph.py) to fused sm_100a kernel launches through the C ABI (capi.py).
+
+Plays the role of `sess.run(sampler, feed_dict)` (GAN/multipassGAN-out.py:446,508,570;
+GAN/multipassGAN-4x.py:1128) for one fixed slice-batch size.  Fusion rules (SURVEY table 2.2):
+  conv + bias + inference BN + activation                      -> one conv plan (K1-K4)
+  relu(convB + conv1x1_shortcut) of a resBlock                 -> 2-segment implicit GEMM (K5)
+  pixel_norm after the activation                              -> conv epilogue (K6)
+  nearest x2 resize of a block output                          -> replicated store in the epilogue (K7)
+  nearest resize / slice / concat / cast feeding a conv        -> one pack_channels launch (K7, K9)
+  dens + bicubic(input density) | dens + input density         -> dens_residual (K8)
+Inputs stay on the device; activations are fp16 (default) or bf16 with fp32 accumulation, or fp32 end to end.
+"""
+import numpy as np
+import torch
+
+from . import capi
+
+_BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (tools_wscale/GAN.py:110)
+
+
+_TORCH_DTYPE = {capi.BF16: torch.bfloat16, capi.F16: torch.float16, capi.F32: torch.float32}
+
+
+def _round_up(a, b):
+    return -(-a // b) * b
+
+
+class Buf:
+    """A device tensor [n, h, w, cstride]; `ptr` may be rebound per run (placeholders, final output)."""
+
+    def __init__(self, n, h, w, c, cstride, dtype, tensor=None, name=None, root=None):
+        self.n, self.h, self.w, self.c, self.cstride, self.dtype = n, h, w, c, cstride, dtype
+        self.tensor = tensor
+        self.ptr = tensor.data_ptr() if tensor is not None else None
+        self.name = name
+        self.root = root  # reshape aliases resolve their pointer through the root buffer
+
+    @property
+    def nbytes(self):
+        return self.n * self.h * self.w * self.cstride * (4 if self.dtype == capi.F32 else 2)
+
+
+class View:
+    """Lazy NHWC tensor: concatenation of channel ranges of buffers, each nearest-replicated."""
+
+    def __init__(self, h, w, sources, bicubic_of=None):
+        self.h, self.w = h, w
+        self.sources = sources  # list of (Buf, c0, nch, fh, fw)
+        self.c = sum(s[2] for s in sources)
+        self.bicubic_of = bicubic_of  # (View, ) for a TF1-bicubic resize that is not materialisable lazily
+        self._mat = {}
+
+    def whole_buf(self):
+        """The single buffer this view aliases 1:1, or None."""
+        if self.bicubic_of is None and len(self.sources) == 1:
+            b, c0, nch, fh, fw = self.sources[0]
+            if c0 == 0 and nch == b.c and fh == 1 and fw == 1 and b.h == self.h and b.w == self.w:
+                return b
+        return None
+
+
+class Group:
+    def __init__(self, conv):
+        self.convs = [conv]
+        self.act = None
+        self.pn = False
+        self.ups = 1
+        self.out_node = conv
+
+
+class CompiledNet:
+    def __init__(self, output, weights, batch, precision="fp16", handle=None, device=0, verbose=False, dry=False):
+        """dry=True records the fused launch list without touching the GPU (host-logic tests)."""
+        assert precision in ("bf16", "fp16", "fp32")
+        self.dry = dry
+        self.h = None if dry else (handle or capi.default_handle(device))
+        self.device = None if dry else torch.device("cuda", self.h.device)
+        self.batch = int(batch)
+        self.precision = precision
+        self.weights = weights
+        self.act_dtype = {"bf16": capi.BF16, "fp16": capi.F16, "fp32": capi.F32}[precision]
+        self.steps = []  # (label, callable(stream))
+        self.launches = 0
+        self.flops = 0.0
+        self.plans = []
+        self.placeholders = {}  # name -> Buf
+        self.activation_bytes = 0
+        self.verbose = verbose
+        self._lower(output)
+
+    # ------------------------------------------------------------------ helpers
+    def _alloc(self, h, w, c, dtype, cstride=None, name=None):
+        if cstride is None:
+            cstride = c if dtype == capi.F32 else _round_up(c, 8)
+        t = None
+        if not self.dry:
+            t = torch.empty((self.batch, h, w, cstride), dtype=_TORCH_DTYPE[dtype], device=self.device)
+        b = Buf(self.batch, h, w, c, cstride, dtype, t, name)
+        self.activation_bytes += b.nbytes
+        return b
+
+    def _materialize(self, view, dtype):
+        """Return a Buf holding `view` in `dtype` with a conv-friendly channel stride."""
+        if view.bicubic_of is not None:
+            raise NotImplementedError("bicubic resize is only supported as the additive density residual")
+        b = view.whole_buf()
+        if b is not None and b.dtype == dtype and (dtype == capi.F32 or b.cstride % 8 == 0):
+            return b
+        if dtype in view._mat:
+            return view._mat[dtype]
+        out = self._alloc(view.h, view.w, view.c, dtype)
+        srcs = [(sb, sb.dtype, sb.cstride, c0, nch, fh, fw) for (sb, c0, nch, fh, fw) in view.sources]
+        handle = self.h
+
+        def step(stream, srcs=srcs, out=out):
+            capi.pack_channels(handle, [(self._p(s[0]),) + s[1:] for s in srcs], self._p(out), out.dtype,
+                               out.cstride, out.n, out.h, out.w, stream)
+
+        self.steps.append(("pack %dx%dx%d" % (view.h, view.w, view.c), step))
+        view._mat[dtype] = out
+        return out
+
+    def _w(self, var):
+        try:
+            return self.weights[var.name]
+        except KeyError:
+            raise KeyError("no value for variable '%s' in the injected weights" % var.name)
+
+    def _conv_affine(self, node):
+        """(W_eff HWIO fp32, per-cout scale or None, per-cout shift) of one conv node."""
+        wv = node.attrs["weight"]
+        w_eff = self._w(wv["var"]).astype(np.float32) * np.float32(wv["wscale"])  # tools_wscale/GAN.py:668
+        bias = self._w(node.attrs["bias"]).astype(np.float32)
+        bn = node.attrs["bn"]
+        if bn is None:
+            return w_eff, None, bias
+        if bn["train"] not in (False, None):
+            raise NotImplementedError("training-mode batch norm is handled by the training step, not CompiledNet")
+        gamma, beta = self._w(bn["gamma"]).astype(np.float64), self._w(bn["beta"]).astype(np.float64)
+        mean, var = self._w(bn["moving_mean"]).astype(np.float64), self._w(bn["moving_variance"]).astype(np.float64)
+        scale = gamma / np.sqrt(var + _BN_EPS)
+        shift = (bias.astype(np.float64) - mean) * scale + beta
+        return w_eff, scale.astype(np.float32), shift.astype(np.float32)
+
+    # ------------------------------------------------------------------ lowering
+    def _lower(self, output):
+        g = output.graph
+        # reachable sub-DAG
+        need = set()
+        stack = [output.node]
+        while stack:
+            n = stack.pop()
+            if n.id in need:
+                continue
+            need.add(n.id)
+            stack.extend(t.node for t in n.inputs)
+        nodes = [n for n in g.nodes if n.id in need]
+        uses = {n.id: [] for n in nodes}
+        for n in nodes:
+            for t in n.inputs:
+                uses[t.node.id].append(n)
+
+        # ---- group formation
+        absorbed = {}
+        groups_by_out = {}
+        for n in nodes:
+            if n.op != "conv" or n.id in absorbed:
+                continue
+            grp = Group(n)
+            t = n
+            while True:
+                us = uses[t.id]
+                if len(us) != 1 or t is output.node:
+                    break
+                u = us[0]
+                if u.op == "act" and grp.act is None and not grp.pn:
+                    grp.act = u.attrs["kind"]
+                elif u.op == "add" and grp.act is None and not grp.pn and len(grp.convs) == 1:
+                    other = u.inputs[1].node if u.inputs[0].node is t else u.inputs[0].node
+                    ok = (other.op == "conv" and other is not t and other.id > n.id and other.id not in absorbed
+                          and len(uses[other.id]) == 1 and other.attrs["stride"] == 1 and n.attrs["stride"] == 1
+                          and other.out.shape == n.out.shape)
+                    if not ok:
+                        break
+                    grp.convs.append(other)
+                    absorbed[other.id] = grp
+                elif u.op == "pixel_norm" and not grp.pn:
+                    grp.pn = True
+                elif (u.op == "resize" and u.attrs["method"] == 1 and n.attrs["stride"] == 1
+                      and u.out.shape[1] == 2 * t.out.shape[1] and u.out.shape[2] == 2 * t.out.shape[2]):
+                    grp.ups = 2
+                    absorbed[u.id] = grp
+                    t = u
+                    break
+                else:
+                    break
+                absorbed[u.id] = grp
+                t = u
+            grp.out_node = t
+            absorbed[n.id] = grp
+            groups_by_out[t.id] = grp
+
+        views = {}
+        for n in nodes:
+            if n.id in groups_by_out:
+                views[n.id] = self._emit_group(groups_by_out[n.id], views)
+                continue
+            if n.id in absorbed:
+                continue
+            op = n.op
+            if op == "placeholder":
+                per = int(np.prod(n.out.shape[1:]))
+                b = Buf(self.batch, 1, 1, per, per, capi.F32, None, n.attrs["name"])
+                self.placeholders[n.attrs["name"]] = b
+                views[n.id] = View(1, 1, [(b, 0, per, 1, 1)])
+            elif op == "reshape":
+                views[n.id] = self._lower_reshape(n, views[n.inputs[0].node.id])
+            elif op == "slice":
+                views[n.id] = self._lower_slice(n, views[n.inputs[0].node.id])
+            elif op == "concat":
+                vs = [views[t.node.id] for t in n.inputs]
+                srcs = []
+                for v in vs:
+                    if v.bicubic_of is not None:
+                        raise NotImplementedError("concat of a bicubic resize")
+                    srcs.extend(v.sources)
+                views[n.id] = View(n.out.shape[1], n.out.shape[2], srcs)
+            elif op == "resize":
+                views[n.id] = self._lower_resize(n, views[n.inputs[0].node.id])
+            elif op == "add":
+                views[n.id] = self._lower_add(n, views)
+            else:
+                raise NotImplementedError("op '%s' is not fusable into a conv on this path and has no standalone "
+                                          "kernel (node %d)" % (op, n.id))
+        outv = views[output.node.id]
+        ob = outv.whole_buf()
+        if ob is None or ob.dtype != capi.F32:
+            ob = self._materialize(outv, capi.F32)
+        self.out_buf = ob
+        self.out_shape = tuple(output.shape[1:])
+        self.launches = len(self.steps)
+
+    def _lower_reshape(self, n, v):
+        shp = n.out.shape
+        if len(shp) == 4 and (shp[1], shp[2], shp[3]) == (v.h, v.w, v.c):
+            return v  # NHWC -> same NHWC: no-op (GAN/multipassGAN-out.py:297 on the concatenated input)
+        b = v.whole_buf()
+        if b is None or b.cstride != b.c:
+            b = self._materialize(v, capi.F32 if (b is None or b.dtype == capi.F32) else b.dtype)
+            if b.cstride != b.c:
+                raise NotImplementedError("reshape of a channel-padded tensor")
+        if len(shp) == 2:
+            h, w, c = 1, 1, shp[1]
+        else:
+            h, w, c = shp[1], shp[2], shp[3]
+        assert h * w * c == b.h * b.w * b.c
+        alias = Buf(b.n, h, w, c, c, b.dtype, None, b.name, root=b.root or b)
+        return View(h, w, [(alias, 0, c, 1, 1)])
+
+    def _lower_slice(self, n, v):
+        if v.bicubic_of is not None:
+            raise NotImplementedError("slice of a bicubic resize")
+        c0, c1 = n.attrs["c0"], n.attrs["c1"]
+        srcs, pos = [], 0
+        for (b, s0, nch, fh, fw) in v.sources:
+            lo, hi = max(c0, pos), min(c1, pos + nch)
+            if lo < hi:
+                srcs.append((b, s0 + lo - pos, hi - lo, fh, fw))
+            pos += nch
+        return View(v.h, v.w, srcs)
+
+    def _lower_resize(self, n, v):
+        oh, ow = n.out.shape[1], n.out.shape[2]
+        m = n.attrs["method"]
+        if m == 1:
+            if oh % v.h or ow % v.w:
+                raise NotImplementedError("nearest resize with a non-integer factor")
+            fh, fw = oh // v.h, ow // v.w
+            if v.bicubic_of is not None:
+                raise NotImplementedError("nearest resize of a bicubic resize")
+            return View(oh, ow, [(b, c0, nch, f0 * fh, f1 * fw) for (b, c0, nch, f0, f1) in v.sources])
+        if m == 2:
+            return View(oh, ow, list(v.sources), bicubic_of=v)
+        raise NotImplementedError("resize method %d (bilinear) is unused by the shipped configurations" % m)
+
+    def _lower_add(self, n, views):
+        va, vb = views[n.inputs[0].node.id], views[n.inputs[1].node.id]
+        if n.out.shape[3] != 1:
+            raise NotImplementedError("standalone add is only implemented for the 1-channel density residual")
+        dens = va.whole_buf()
+        other = vb
+        if dens is None or dens.dtype != capi.F32:
+            dens, other = vb.whole_buf(), va
+        if dens is None or dens.dtype != capi.F32:
+            raise NotImplementedError("density residual: neither operand is a dense fp32 tensor")
+        out = self._alloc(dens.h, dens.w, 1, capi.F32)
+        handle = self.h
+        if other.bicubic_of is not None:
+            sv = other.bicubic_of
+            (sb, c0, nch, fh, fw), = sv.sources
+            assert nch == 1 and fh == 1 and fw == 1
+            plan = None
+            if not self.dry:
+                plan = capi.BicubicPlan(handle, sv.h, sv.w, dens.h, dens.w)
+                self.plans.append(plan)
+            mode, sh, sw = 2, sv.h, sv.w
+        else:
+            (sb, c0, nch, fh, fw), = other.sources
+            if fh != 1 or fw != 1:
+                sb = self._materialize(other, capi.F32)
+                c0 = 0
+            plan, mode, sh, sw = None, 0, dens.h, dens.w
+
+        def step(stream):
+            capi.dens_residual(handle, self._p(dens), self._p(sb), sb.dtype, sb.cstride, c0, mode, plan, out.n, dens.h,
+                               dens.w, sh, sw, self._p(out), stream)
+
+        self.steps.append(("dens_residual mode %d" % mode, step))
+        return View(out.h, out.w, [(out, 0, 1, 1, 1)])
+
+    @staticmethod
+    def _p(buf):
+        return buf.root.ptr if buf.root is not None else buf.ptr
+
+    def _emit_group(self, grp, views):
+        convs = sorted(grp.convs, key=lambda c: -c.attrs["ksize"])
+        first = convs[0]
+        ws, scs, shift_total, ins = [], [], None, []
+        any_scale = False
+        for c in convs:
+            w_eff, sc, sh = self._conv_affine(c)
+            ws.append(w_eff)
+            scs.append(sc)
+            any_scale = any_scale or sc is not None
+            shift_total = sh if shift_total is None else shift_total + sh
+            ins.append(self._materialize(views[c.inputs[0].node.id], self.act_dtype))
+        cout = first.out.shape[3]
+        ih, iw = first.inputs[0].shape[1], first.inputs[0].shape[2]
+        stride = first.attrs["stride"]
+        out_dtype = capi.F32 if (self.precision == "fp32" or cout == 1) else self.act_dtype
+        oh, ow = -(-ih // stride) * grp.ups, -(-iw // stride) * grp.ups
+        out = self._alloc(oh, ow, cout, out_dtype)
+        flops = sum(2.0 * self.batch * (oh // grp.ups) * (ow // grp.ups) * c.attrs["ksize"] ** 2
+                    * c.inputs[0].shape[3] * cout for c in convs)
+        self.flops += flops
+        x0 = ins[0]
+        x1 = ins[1] if len(ins) > 1 else None
+        if self.dry:
+            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride)
+        else:
+            plan = capi.ConvPlan(self.h, self.batch, ih, iw, ws, [b.cstride for b in ins], cout, out.cstride,
+                                 act=grp.act, scales=scs if any_scale else None, shift=shift_total,
+                                 pixel_norm=grp.pn, upsample=grp.ups, stride=stride, in_dtype=self.act_dtype,
+                                 out_dtype=out_dtype)
+            self.plans.append(plan)
+            kind = plan.kind
+            assert abs(plan.flops - flops) < 1e-6 * flops
+
+        def step(stream):
+            plan.run(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out), stream)
+
+        label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s" % (
+            "tc" if kind == capi.KIND_TCGEN05 else "cc",
+            "+".join(c.attrs["weight"]["var"].name.rsplit("/", 2)[-2] for c in convs),
+            "/".join(str(c.attrs["ksize"]) for c in convs),
+            "/".join(str(c.inputs[0].shape[3]) for c in convs), cout, ih, iw,
+            " " + grp.act if grp.act else "", " pn" if grp.pn else "", " up2" if grp.ups == 2 else "")
+        if self.verbose:
+            print(label)
+        self.steps.append((label, step))
+        return View(oh, ow, [(out, 0, cout, 1, 1)])
+
+    def _predict_kind(self, convs, ins, cout, out_dtype, stride):
+        """Mirror of the auto rule in csrc/conv_plan.cu (dry runs only)."""
+        if self.act_dtype == capi.F32 or stride != 1 or cout > 128 or cout < 8:
+            return capi.KIND_DIRECT
+        if any(c.attrs["ksize"] not in (1, 3, 5) for c in convs) or any(b.cstride % 8 for b in ins):
+            return capi.KIND_DIRECT
+        return capi.KIND_TCGEN05 if max(c.inputs[0].shape[3] for c in convs) >= 8 else capi.KIND_DIRECT
+
+    # ------------------------------------------------------------------ execution
+    def run(self, feeds, out=None, stream=None):
+        """feeds: placeholder name -> device tensor / pointer holding [batch, n_flat] fp32 rows.
+        out: optional device tensor / pointer receiving the [batch, n_output] fp32 rows; returns the
+        output tensor when `out` is None."""
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if self.dry:
+            raise RuntimeError("dry CompiledNet cannot run")
+        for name, b in self.placeholders.items():
+            if name not in feeds:
+                raise KeyError("placeholder '%s' was not fed" % name)
+            f = feeds[name]
+            b.ptr = f.data_ptr() if hasattr(f, "data_ptr") else int(f)
+        ob = self.out_buf
+        root = ob.root or ob
+        saved = root.ptr
+        if out is not None:
+            root.ptr = out.data_ptr() if hasattr(out, "data_ptr") else int(out)
+        try:
+            for _, step in self.steps:
+                step(st)
+        finally:
+            root.ptr = saved
+        if out is None:
+            return root.tensor.view(self.batch, -1)
+        return out
+
+    def close(self):
+        for p in self.plans:
+            if p is not None:
+                p.close()
+        self.plans = []

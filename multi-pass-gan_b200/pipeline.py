@@ -1,0 +1,270 @@
+"""Device-resident multi-pass volume pipelines (the per-frame hot loop of the reference).
+
+  MultiPass4x   the shipped 4x recipe, GAN/example_run_output.py:6,8 = two runs of
+                GAN/multipassGAN-4x.py:1090-1169 (pass 1 `upsamplingMode 2`, pass 2 `upsamplingMode 1`)
+  MultiPassOut  generate3DUniForNewNetwork of GAN/multipassGAN-out.py:390-618 (1-3 chained generators)
+
+In the reference every slice batch crosses the host boundary twice (feed + fetch of `sess.run`) and the
+volume lives in host numpy memory between passes; here the low-res fields are uploaded once, slice
+batches are assembled on the device (mpg_slice_assemble), each network writes its rows straight into the
+pass volume, and the axis changes between passes are mpg_transpose3d launches.  Slices of one pass are
+independent, so a rank may own any contiguous slice range (`slice_range`); the exchange between passes
+is then an all-to-all (parallel.py).
+"""
+import numpy as np
+import torch
+
+from . import capi, engine
+from . import graph as G
+from . import networks as N
+from . import weights as W
+
+THRESHOLD = 0.0005  # GAN/multipassGAN-out.py:614, GAN/multipassGAN-4x.py:1156
+
+# GAN/multipassGAN-out.py:398-421 / :464-485 / :526-547 as (axis_of, channel permutation) per transposeAxis:
+# output index (slice,row,col) -> source axis of the [Z,Y,X,C] field volume; the zoomed axis is axis_of[0].
+_PASS_GEOM = {
+    1: {0: ((0, 1, 2), (0, 1, 2, 3)), 1: ((1, 0, 2), (0, 1, 3, 2)), 2: ((2, 1, 0), (0, 3, 2, 1)),
+        3: ((2, 0, 1), (0, 2, 3, 1))},
+    2: {3: ((1, 0, 2), (0, 1, 3, 2)), 0: ((2, 1, 0), (0, 3, 2, 1)), 1: ((2, 0, 1), (0, 2, 3, 1)),
+        2: ((0, 1, 2), (0, 1, 2, 3))},
+    # pass 3: transposeAxis 2 indexes channel 13 and 3 reshapes a mis-shaped array in the reference (dead branches)
+    3: {0: ((1, 0, 2), (0, 1, 3, 2)), 1: ((0, 1, 2), (0, 1, 2, 3))},
+}
+
+
+def _dev_f32(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+
+
+def _pick_batch(n, pref):
+    """Largest batch <= pref dividing n (the reference drops the remainder, App. D.4)."""
+    b = min(pref, n)
+    while n % b:
+        b -= 1
+    return b
+
+
+class _PassNet:
+    """One generator compiled for a fixed slice batch, fed by the slice assembler."""
+
+    def __init__(self, handle, build_fn, weights, batch, precision):
+        G.reset_default_graph()
+        self.out_t = build_fn()
+        self.graph = G.get_default_graph()
+        self.net = engine.CompiledNet(self.out_t, weights, batch, precision=precision, handle=handle)
+        self.batch = batch
+
+
+class MultiPass4x:
+    """Two-pass 4x super-resolution of one frame: [L,L,L,4] -> [4L,4L,4L] (z,y,x), fp32."""
+
+    def __init__(self, L, weights_pass1, weights_pass2, upRes=4, precision="fp16", batch=8, velScale=1.0,
+                 batch_norm=True, device=0, threshold=THRESHOLD):
+        self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
+        self.h = capi.default_handle(device)
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        self.velScale = float(velScale)
+        self.threshold = float(threshold)
+        L, S, u = self.L, self.S, self.u
+        self.batch = _pick_batch(S, batch)
+        cfg1 = N.config_4x(L, upRes=u, upsampling_mode=2, batch_norm=batch_norm)
+        cfg2 = N.config_4x(L, upRes=u, upsampling_mode=1, batch_norm=batch_norm)
+        self.p1 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg1), weights_pass1,
+                           self.batch, precision)
+        self.p2 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, S * S * 4], "x"), cfg2), weights_pass2,
+                           self.batch, precision)
+        vs = self.velScale
+        # pass 1: zoom(x,[u,1,1,1]) (GAN/multipassGAN-4x.py:1103); velocities * velScale (:283)
+        self.asm1 = capi.make_assemble_desc((L, L, L), 4, (0, 1, 2), (u, 1, 1), (0, 1, 2, 3), (1.0, vs, vs, vs),
+                                            out_dtype=capi.F32, out_cstride=4)
+        # pass 2: concat(x_2, zoom(vel*u,[u,u,u,1])).transpose(0,3,1,2,4) + swaps 2<->3, 3<->1 (:1113-1119):
+        # slices along x of (z,y) planes, channels (d, vy, vz, vx); velScale hits vy,vz only (App. D.10)
+        self.asm2 = capi.make_assemble_desc((L, L, L), 4, (2, 0, 1), (u, u, u), (2, 3, 1),
+                                            (u * vs, u * vs, float(u)), out_dtype=capi.F32, out_cstride=4)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.in1 = torch.empty((self.batch, L, L, 4), **f32)
+        self.in2 = torch.empty((self.batch, S, S, 4), **f32)
+        self.vol_a = torch.empty((S, S, S), **f32)
+        self.vol_b = torch.empty((S, S, S), **f32)
+        self.flops = (self.p1.net.flops + self.p2.net.flops) / self.batch * S
+        self.launches_per_frame = (S // self.batch) * (self.p1.net.launches + self.p2.net.launches + 2) + 2
+        self.events = None
+
+    def __call__(self, x, slice_range=None, record=False):
+        """x: [L,L,L,4] float32 (numpy or device tensor). Returns the device tensor [S,S,S] (z,y,x)."""
+        S, B = self.S, self.batch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        vol = _dev_f32(x, self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if ev:
+            ev[0].record()
+        # ---- pass 1: xy slices along (interpolated) z; rows land in vol_a[z] = [Zu, Yu, Xu]
+        for s0 in range(0, S, B):
+            capi.slice_assemble(self.h, self.asm1, vol, None, s0, B, self.in1, st)
+            self.p1.net.run({"x": self.in1}, out=self.vol_a[s0], stream=st)
+        if ev:
+            ev[1].record()
+        # ---- the .uni hand-over between the two processes: threshold (:1155-1157), then pass 2 slices along x
+        capi.transpose3d(self.h, self.vol_a, self.vol_b, (S, S, S), (2, 0, 1), self.threshold, st)  # [Xu,Zu,Yu]
+        for s0 in range(0, S, B):
+            capi.slice_assemble(self.h, self.asm2, vol, self.vol_b, s0, B, self.in2, st)
+            self.p2.net.run({"x": self.in2}, out=self.vol_a[s0], stream=st)
+        if ev:
+            ev[2].record()
+        # rows [Xu, Zu, Yu] -> .transpose(1,2,0) -> [Zu, Yu, Xu] (:1142), threshold (:1155-1157)
+        capi.transpose3d(self.h, self.vol_a, self.vol_b, (S, S, S), (1, 2, 0), self.threshold, st)
+        if ev:
+            ev[3].record()
+            self.events = ev
+        return self.vol_b
+
+    def pass1_only(self, x):
+        """First-pass volume [Zu,Yu,Xu] after the threshold (what pass 2 reads from density_low_2x2_*.uni)."""
+        S, B = self.S, self.batch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        vol = _dev_f32(x, self.device)
+        for s0 in range(0, S, B):
+            capi.slice_assemble(self.h, self.asm1, vol, None, s0, B, self.in1, st)
+            self.p1.net.run({"x": self.in1}, out=self.vol_a[s0], stream=st)
+        capi.threshold(self.h, self.vol_a, S * S * S, self.threshold, st)
+        return self.vol_a
+
+    def pass_times_ms(self):
+        e = self.events
+        return dict(pass1=e[0].elapsed_time(e[1]), pass2=e[1].elapsed_time(e[2]), final=e[2].elapsed_time(e[3]))
+
+
+def make_weights_4x(L, seed, upRes=4, batch_norm=True, randomize_bn=False):
+    """Random-init weights for the two 4x generators (separate variables per pass, same names)."""
+    out = []
+    for p, mode in ((1, 2), (2, 1)):
+        G.reset_default_graph()
+        cfg = N.config_4x(L, upRes=upRes, upsampling_mode=mode, batch_norm=batch_norm)
+        n_in = L * L * 4 if mode == 2 else (L * upRes) ** 2 * 4
+        N.gen_resnet(G.placeholder([None, n_in], "x"), cfg)
+        w = W.init_graph_variables(G.get_default_graph(), seed * 10 + p)
+        if randomize_bn:
+            w = W.randomize_bn_stats(w, seed * 10 + p)
+        out.append(w)
+    return out
+
+
+class NetSpec:
+    """Per-network flags of GAN/multipassGAN-out.py (use_res_netN, add_adj_idcsN, startFmsN, maxFmsN, filterSizeN)."""
+
+    def __init__(self, use_res_net=False, add_adj_idcs=False, startFms=512, maxFms=256, filterSize=3,
+                 first_nn_arch=False):
+        self.use_res_net, self.add_adj_idcs = bool(use_res_net), bool(add_adj_idcs)
+        self.startFms, self.maxFms, self.filterSize = int(startFms), int(maxFms), int(filterSize)
+        self.first_nn_arch = bool(first_nn_arch)
+
+
+SHIPPED_8X = {  # GAN/example_run_output.py:18-47
+    1: NetSpec(use_res_net=True, add_adj_idcs=True, startFms=256, maxFms=256, filterSize=3, first_nn_arch=True),
+    2: NetSpec(use_res_net=True, add_adj_idcs=False, startFms=192, maxFms=192, filterSize=5),
+    3: NetSpec(use_res_net=False, add_adj_idcs=False, startFms=192, maxFms=96, filterSize=5),
+}
+
+
+def build_out_graph(idx, spec, cfg):
+    """Sampler wiring of GAN/multipassGAN-out.py:349-365 for generator `idx` (1-based)."""
+    L, S, C = cfg.tileSizeLow, cfg.tileSizeHigh, cfg.n_inputChannels
+    cu = N.log2i(cfg.upRes)
+    with G.variable_scope("gen_%d" % idx):
+        if idx == 1:
+            cin = C + (2 if spec.add_adj_idcs else 0)
+            x = G.placeholder([None, L * L * cin], "x")
+            return N.growing_gen(x, cfg, use_batch_norm=cfg.batch_norm, currentUpres=cu, output=True, firstGen=True,
+                                 filterSize=spec.filterSize, startFms=spec.startFms, maxFms=spec.maxFms,
+                                 add_adj_idcs=spec.add_adj_idcs, first_nn_arch=spec.first_nn_arch,
+                                 use_res_net=spec.use_res_net)
+        if spec.add_adj_idcs:
+            raise NotImplementedError("add_adj_idcs2/3 raise in the reference as well (App. D.7)")
+        x = G.placeholder([None, L * L * C], "x")
+        y = G.placeholder([None, S * S], "y")
+        x_in = N.sampler_2_input(x, y, cfg)
+        return N.growing_gen(x_in, cfg, use_batch_norm=cfg.batch_norm, currentUpres=cu, output=True, firstGen=False,
+                             filterSize=spec.filterSize, startFms=spec.startFms, maxFms=spec.maxFms,
+                             add_adj_idcs=False, first_nn_arch=False, use_res_net=spec.use_res_net)
+
+
+def make_weights_out(L, seed, upRes=8, specs=None, nets=(1, 2), **cfg_kw):
+    specs = specs or SHIPPED_8X
+    cfg = N.config_out(L, upRes=upRes, **cfg_kw)
+    out = {}
+    for idx in nets:
+        G.reset_default_graph()
+        build_out_graph(idx, specs[idx], cfg)
+        out[idx] = W.init_graph_variables(G.get_default_graph(), seed)
+    return out
+
+
+class MultiPassOut:
+    """generate3DUniForNewNetwork (GAN/multipassGAN-out.py:390-618) for one frame, on the device."""
+
+    def __init__(self, L, weights, upRes=8, specs=None, precision="fp16", transposeAxis=0, batches=(8, 2, 2),
+                 device=0, threshold=THRESHOLD, **cfg_kw):
+        self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
+        self.h = capi.default_handle(device)
+        self.device = torch.device("cuda", device)
+        self.specs = specs or SHIPPED_8X
+        self.cfg = N.config_out(self.L, upRes=self.u, **cfg_kw)
+        self.ta = int(transposeAxis)
+        self.threshold = float(threshold)
+        self.nets = sorted(weights.keys())
+        L, S, u = self.L, self.S, self.u
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.passes = {}
+        self.flops = 0.0
+        for idx in self.nets:
+            spec = self.specs[idx]
+            if self.ta not in _PASS_GEOM[idx]:
+                raise NotImplementedError("transposeAxis %d is a dead branch for generator %d (App. D.7)" % (self.ta, idx))
+            axis_of, chans = _PASS_GEOM[idx][self.ta]
+            B = _pick_batch(S, batches[idx - 1])
+            pn = _PassNet(self.h, lambda idx=idx, spec=spec: build_out_graph(idx, spec, self.cfg), weights[idx], B,
+                          precision)
+            adj = bool(spec.add_adj_idcs) and idx == 1
+            cin = 4 + (2 if adj else 0)
+            desc = capi.make_assemble_desc((L, L, L), 4, axis_of, (u, 1, 1), chans, None, add_adj=adj,
+                                           out_dtype=capi.F32, out_cstride=cin)
+            self.passes[idx] = dict(net=pn, desc=desc, batch=B, inbuf=torch.empty((B, L, L, cin), **f32))
+            self.flops += pn.net.flops / B * S
+        self.vol_rows = torch.empty((S, S, S), **f32)
+        self.vol_dim = torch.empty((S, S, S), **f32)
+
+    def __call__(self, x):
+        """x: [L,L,L,4] float32, velocities already scaled by velScale (GAN/multipassGAN-out.py:138)."""
+        S = self.S
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        vol = _dev_f32(x, self.device)
+        rows, dim = self.vol_rows, self.vol_dim
+        post = {1: (2, 1, 0), 2: (1, 2, 0), 3: (0, 1, 2)}  # :459, :521, :583
+        for idx in self.nets:
+            p = self.passes[idx]
+            B = p["batch"]
+            for s0 in range(0, S, B):
+                capi.slice_assemble(self.h, p["desc"], vol, None, s0, B, p["inbuf"], st)
+                feeds = {"x": p["inbuf"]}
+                if idx > 1:
+                    feeds["y"] = dim[s0]
+                p["net"].net.run(feeds, out=rows[s0], stream=st)
+            # np.array(rows).reshape(S,S,S).transpose(post): the old `dim` (this pass's `y`) is dead now
+            capi.transpose3d(self.h, rows, dim, (S, S, S), post[idx], 0.0, st)
+        cur = dim
+        other = rows
+        # :587-590 -- undo the pass transposes
+        if 2 in self.nets:
+            capi.transpose3d(self.h, cur, other, (S, S, S), (2, 0, 1), 0.0, st)
+            cur, other = other, cur
+        if 1 in self.nets:
+            capi.transpose3d(self.h, cur, other, (S, S, S), (2, 1, 0), 0.0, st)
+            cur, other = other, cur
+        if self.threshold > 0:
+            capi.threshold(self.h, cur, S * S * S, self.threshold, st)  # :612-615
+        self.vol_rows, self.vol_dim = other, cur
+        return cur

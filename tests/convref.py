@@ -8,8 +8,8 @@ import mpgan_b200  # noqa: F401
 from mpgan_b200 import capi
 
 
-def bf16_round(a):
-    return torch.as_tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float32)
+_TDT = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}
+_CODE = {"bf16": capi.BF16, "f16": capi.F16, "f32": capi.F32}
 
 
 def tf_same_pad(size, k, s):
@@ -18,7 +18,7 @@ def tf_same_pad(size, k, s):
     return total // 2, total - total // 2
 
 
-def ref_conv(xs, ws, scales, shift, act, pixel_norm, upsample, in_upsample=1, stride=1, round_w_bf16=True):
+def ref_conv(xs, ws, scales, shift, act, pixel_norm, upsample, in_upsample=1, stride=1, round_w=None):
     """xs: list of NHWC fp32 tensors (already holding the values the kernel sees); ws: HWIO fp32."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -27,8 +27,8 @@ def ref_conv(xs, ws, scales, shift, act, pixel_norm, upsample, in_upsample=1, st
         w = torch.as_tensor(w, dtype=torch.float32, device=x.device)
         if sc is not None:
             w = w * torch.as_tensor(sc, dtype=torch.float32, device=x.device)
-        if round_w_bf16:
-            w = w.to(torch.bfloat16).to(torch.float32)
+        if round_w is not None:
+            w = w.to(round_w).to(torch.float32)
         xi = x.permute(0, 3, 1, 2)
         if in_upsample > 1:
             xi = xi.repeat_interleave(in_upsample, 2).repeat_interleave(in_upsample, 3)
@@ -61,15 +61,15 @@ def run_case(n, h, w, cins, ks, cout, act=None, pixel_norm=False, upsample=1, in
     g = torch.Generator(device="cpu").manual_seed(seed)
     nseg = len(cins)
     if cstrides is None:
-        cstrides = [(-(-c // 8) * 8) if in_dtype == "bf16" else c for c in cins]
+        cstrides = [(-(-c // 8) * 8) if in_dtype != "f32" else c for c in cins]
     if out_cstride is None:
-        out_cstride = (-(-cout // 8) * 8) if out_dtype == "bf16" else cout
+        out_cstride = (-(-cout // 8) * 8) if out_dtype != "f32" else cout
     sh, sw = h // in_upsample, w // in_upsample
     xs_dev, xs_val, ws, scs = [], [], [], []
     for s in range(nseg):
         x = torch.randn(n, sh, sw, cstrides[s], generator=g)
-        if in_dtype == "bf16":
-            xd = x.to(torch.bfloat16).to(dev)
+        if in_dtype != "f32":
+            xd = x.to(_TDT[in_dtype]).to(dev)
             xv = xd.float()[..., :cins[s]]
         else:
             xd = x.to(dev)
@@ -83,14 +83,13 @@ def run_case(n, h, w, cins, ks, cout, act=None, pixel_norm=False, upsample=1, in
     plan = capi.ConvPlan(capi.default_handle(0), n, h, w, ws, cstrides, cout, out_cstride, act=act,
                          scales=scs if with_scale else None, shift=shift, pixel_norm=pixel_norm,
                          upsample=upsample, in_upsample=in_upsample, stride=stride,
-                         in_dtype=capi.BF16 if in_dtype == "bf16" else capi.F32,
-                         out_dtype=capi.BF16 if out_dtype == "bf16" else capi.F32, force_kind=force_kind)
+                         in_dtype=_CODE[in_dtype], out_dtype=_CODE[out_dtype], force_kind=force_kind)
     y = torch.full((n, plan.out_h, plan.out_w, out_cstride), float("nan"),
-                   dtype=torch.bfloat16 if out_dtype == "bf16" else torch.float32, device=dev)
+                   dtype=_TDT[out_dtype], device=dev)
     plan.run(xs_dev[0], xs_dev[1] if nseg > 1 else None, y, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref = ref_conv(xs_val, ws, scs, shift, act, pixel_norm, upsample, in_upsample, stride,
-                   round_w_bf16=(plan.kind == capi.KIND_TCGEN05))
+                   round_w=_TDT[in_dtype] if plan.kind == capi.KIND_TCGEN05 else None)
     got = y.double()
     pad_ok = True
     if out_cstride > cout:

@@ -1,0 +1,55 @@
+"""GPU parity of the fused convolution kernels (through the C ABI) vs a plain fp32/fp64 torch reference."""
+import pytest
+
+import mpgan_b200  # noqa: F401
+from convref import run_case
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "k1_64to128": dict(n=1, h=32, w=32, cins=[64], ks=[1], cout=128),
+    "k3_64to64": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64),
+    "k5_128to128": dict(n=1, h=64, w=64, cins=[128], ks=[5], cout=128, act="relu"),
+    "k5_128to32": dict(n=2, h=48, w=48, cins=[128], ks=[5], cout=32, act="relu"),
+    "k5_32to128_ck32": dict(n=1, h=64, w=64, cins=[32], ks=[5], cout=128, act="relu"),
+    "k5_16to32_ck16": dict(n=1, h=64, w=64, cins=[16], ks=[5], cout=32, act="relu"),
+    "k5_8to32_4s": dict(n=1, h=32, w=32, cins=[8, 4], ks=[5, 1], cout=32, cstrides=[8, 8], act="relu"),
+    "2seg_128k5_32k1": dict(n=1, h=64, w=64, cins=[128, 32], ks=[5, 1], cout=128, act="relu"),
+    "2seg_32k5_128k1_to8": dict(n=1, h=64, w=64, cins=[32, 128], ks=[5, 1], cout=8, act="relu"),
+    "k3_pn_up2": dict(n=1, h=32, w=32, cins=[128], ks=[3], cout=128, act="relu", pixel_norm=True, upsample=2),
+    "ragged_37x45": dict(n=3, h=37, w=45, cins=[64], ks=[5], cout=48, act="lrelu"),
+    "tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="tanh"),
+    "k5_f32out": dict(n=1, h=32, w=32, cins=[128], ks=[5], cout=24, out_dtype="f32"),
+    "k5_96to48": dict(n=1, h=40, w=40, cins=[96, 48], ks=[5, 1], cout=48, act="relu", pixel_norm=True),
+    "k5_24to12": dict(n=1, h=40, w=40, cins=[24], ks=[5], cout=12, act="relu", pixel_norm=True),
+    "direct_f32_k5_4to8_up4": dict(n=2, h=64, w=64, cins=[4], ks=[5], cout=8, in_dtype="f32", in_upsample=4, act="relu"),
+    "direct_k5_8to2": dict(n=1, h=40, w=40, cins=[8], ks=[5], cout=2, act="relu"),
+    "direct_2seg_to1_f32": dict(n=1, h=40, w=40, cins=[2, 8], ks=[5, 1], cout=1, out_dtype="f32", act="relu"),
+    "direct_f32_k4s2": dict(n=2, h=64, w=64, cins=[2], ks=[4], cout=32, in_dtype="f32", out_dtype="f32", stride=2, act="lrelu"),
+    "direct_f32_k4s1": dict(n=2, h=8, w=8, cins=[16], ks=[4], cout=24, in_dtype="f32", out_dtype="f32", stride=1, act="lrelu"),
+    "direct_f32_128_pn_up2": dict(n=1, h=24, w=24, cins=[128, 6], ks=[3, 1], cout=128, in_dtype="f32", out_dtype="f32",
+                                  act="relu", pixel_norm=True, upsample=2),
+    "forced_direct_16bit": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64, force_kind=2, act="relu"),
+}
+
+
+@pytest.mark.parametrize("half", ["bf16", "f16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_conv_case(name, half):
+    kw = dict(CASES[name])
+    if kw.get("in_dtype", "bf16") == "f32" and half == "f16" and kw.get("out_dtype", "bf16") == "f32":
+        pytest.skip("pure fp32 case does not depend on the 16-bit type")
+    for key in ("in_dtype", "out_dtype"):
+        if kw.get(key, "bf16") == "bf16":
+            kw[key] = half
+    r = run_case(**kw)
+    out16 = kw["out_dtype"] != "f32"
+    tol = (6e-3 if half == "bf16" else 8e-4) if out16 else 2e-5
+    assert r["finite"] and r["pad_ok"], r
+    assert r["rel_l2"] < tol, (name, r)
+
+
+def test_flagship_shape_one_slice():
+    """ru2_B + shortcut at 512x512 (config 2 resolution), one slice."""
+    r = run_case(n=1, h=512, w=512, cins=[128, 32], ks=[5, 1], cout=128, act="relu")
+    assert r["kind"] == 1 and r["rel_l2"] < 6e-3, r

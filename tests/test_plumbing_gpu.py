@@ -1,0 +1,151 @@
+"""GPU parity of the bandwidth kernels against numpy / scipy / the oracle op restatements (bit-exact
+for pure data movement, 1e-6 for fp32 interpolation)."""
+import numpy as np
+import pytest
+import torch
+
+import mpgan_b200  # noqa: F401
+from mpgan_b200 import capi
+from oracle import pipeline as op
+from oracle import tf_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def H():
+    return capi.default_handle(0)
+
+
+@pytest.mark.parametrize("perm", [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)])
+@pytest.mark.parametrize("dims", [(8, 8, 8), (5, 33, 70), (64, 64, 64), (1, 37, 2)])
+def test_transpose3d_exact(perm, dims):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal(dims).astype(np.float32)
+    src = torch.from_numpy(a).cuda()
+    dst = torch.full(tuple(dims[p] for p in perm), float("nan"), device="cuda")
+    capi.transpose3d(H(), src, dst, dims, perm)
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), a.transpose(perm))
+
+
+def test_transpose3d_threshold_and_threshold():
+    rng = np.random.default_rng(1)
+    a = (rng.random((16, 24, 40)).astype(np.float32) * 0.002)
+    src = torch.from_numpy(a).cuda()
+    dst = torch.empty((40, 16, 24), device="cuda")
+    capi.transpose3d(H(), src, dst, a.shape, (2, 0, 1), 0.0005)
+    ref = a.transpose(2, 0, 1).copy()
+    ref[ref < 0.0005] = 0
+    assert np.array_equal(dst.cpu().numpy(), ref)
+    v = torch.from_numpy(a).cuda()
+    capi.threshold(H(), v, a.size, 0.0005)
+    r2 = a.copy()
+    r2[r2 < 0.0005] = 0
+    assert np.array_equal(v.cpu().numpy(), r2)
+
+
+@pytest.mark.parametrize("ta", [0, 1, 2, 3])
+@pytest.mark.parametrize("adj", [False, True])
+def test_slice_assemble_pass1_matches_reference_numpy(ta, adj):
+    """GAN/multipassGAN-out.py:398-436 restated in oracle.pipeline.out_pass1_input."""
+    from mpgan_b200.pipeline import _PASS_GEOM
+    L, u, C = 6, 4, 4
+    S = L * u
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((L, L, L, C)).astype(np.float32)
+    ref = op.out_pass1_input(x, L, S, u, C, ta, adj)
+    axis_of, chans = _PASS_GEOM[1][ta]
+    cout = C + (2 if adj else 0)
+    d = capi.make_assemble_desc((L, L, L), C, axis_of, (u, 1, 1), chans, None, add_adj=adj, out_dtype=capi.F32,
+                                out_cstride=cout)
+    out = torch.full((S, L, L, cout), float("nan"), device="cuda")
+    capi.slice_assemble(H(), d, torch.from_numpy(x).cuda(), None, 0, S, out)
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("ta", [0, 1, 2, 3])
+def test_slice_assemble_pass2_matches_reference_numpy(ta):
+    from mpgan_b200.pipeline import _PASS_GEOM
+    L, u, C = 5, 4, 4
+    S = L * u
+    x = np.random.default_rng(3).standard_normal((L, L, L, C)).astype(np.float32)
+    ref = op.out_pass2_input(x, L, S, u, C, ta)
+    axis_of, chans = _PASS_GEOM[2][ta]
+    d = capi.make_assemble_desc((L, L, L), C, axis_of, (u, 1, 1), chans, None, out_dtype=capi.F32, out_cstride=C)
+    out = torch.empty((S, L, L, C), device="cuda")
+    # assembled in two ragged chunks to exercise slice0/count
+    capi.slice_assemble(H(), d, torch.from_numpy(x).cuda(), None, 0, 7, out)
+    capi.slice_assemble(H(), d, torch.from_numpy(x).cuda(), None, 7, S - 7, out[7])
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_slice_assemble_4x_pass2_trilinear_with_density():
+    """GAN/multipassGAN-4x.py:1095,1113-1119: trilinear zoom of vel*u + first-pass density, (d,vy,vz,vx)."""
+    L, u = 6, 4  # S = 24: a multiple of the reference's batch of 8 (App. D.4)
+    S = L * u
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((L, L, L, 4)).astype(np.float32)
+    dens = rng.random((S, S, S, 1)).astype(np.float32)
+    captured = {}
+
+    def net(rows):
+        captured.setdefault("rows", []).append(np.array(rows))
+        return np.zeros((rows.shape[0], S * S), np.float32)
+
+    op.apply_4x_pass(net, u, 1, x[..., 1:4] * u, x_2=dens)
+    ref = np.concatenate(captured["rows"]).reshape(-1, S, S, 4)
+    n_ref = ref.shape[0]
+    d = capi.make_assemble_desc((L, L, L), 4, (2, 0, 1), (u, u, u), (2, 3, 1), (u, u, u), out_dtype=capi.F32,
+                                out_cstride=4)
+    dens_t = np.ascontiguousarray(dens[..., 0].transpose(2, 0, 1))  # [X, Z, Y]
+    out = torch.empty((S, S, S, 4), device="cuda")
+    capi.slice_assemble(H(), d, torch.from_numpy(x).cuda(), torch.from_numpy(dens_t).cuda(), 0, S, out)
+    got = out.cpu().numpy()[:n_ref]
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16", "f16"])
+def test_pack_channels(out_dtype):
+    n, h, w = 2, 12, 20
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((n, h // 4, w // 4, 4)).astype(np.float32)  # nearest x4
+    b = rng.standard_normal((n, h, w, 8)).astype(np.float32)
+    tb = torch.from_numpy(b).cuda().to(torch.bfloat16)
+    code = {"f32": capi.F32, "bf16": capi.BF16, "f16": capi.F16}[out_dtype]
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[out_dtype]
+    out = torch.full((n, h, w, 8), float("nan"), dtype=tdt, device="cuda")
+    capi.pack_channels(H(), [(tb, capi.BF16, 8, 2, 1, 1, 1), (torch.from_numpy(a).cuda(), capi.F32, 4, 0, 4, 4, 4)],
+                       out, code, 8, n, h, w)
+    ref = np.zeros((n, h, w, 8), np.float32)
+    ref[..., 0] = tb.float().cpu().numpy()[..., 2]
+    ref[..., 1:5] = a.repeat(4, axis=1).repeat(4, axis=2)
+    ref_t = torch.from_numpy(ref).to(tdt).float().numpy()
+    assert np.array_equal(out.float().cpu().numpy(), ref_t)
+
+
+@pytest.mark.parametrize("factor", [2, 4, 8])
+def test_dens_residual_bicubic_matches_oracle_tf1_resize(factor):
+    n, L = 2, 9
+    S = L * factor
+    rng = np.random.default_rng(6)
+    x = rng.random((n, L, L, 6)).astype(np.float32)
+    dens = rng.standard_normal((n, S, S)).astype(np.float32)
+    plan = capi.BicubicPlan(H(), L, L, S, S)
+    out = torch.empty((n, S, S), device="cuda")
+    capi.dens_residual(H(), torch.from_numpy(dens).cuda(), torch.from_numpy(x).cuda(), capi.F32, 6, 0, 2, plan, n, S, S,
+                       L, L, out)
+    ref = dens + tf_ops.resize_bicubic_tf1(torch.from_numpy(x[..., 0:1]), S, S).numpy()[..., 0]
+    assert np.abs(out.cpu().numpy() - ref).max() <= 2e-6
+    out0 = torch.empty((n, L, L), device="cuda")
+    d0 = rng.standard_normal((n, L, L)).astype(np.float32)
+    capi.dens_residual(H(), torch.from_numpy(d0).cuda(), torch.from_numpy(x).cuda(), capi.F32, 6, 3, 0, None, n, L, L, L,
+                       L, out0)
+    assert np.array_equal(out0.cpu().numpy(), d0 + x[..., 3])
+
+
+def test_error_paths_raise():
+    with pytest.raises(capi.MpgError):
+        capi.transpose3d(H(), torch.empty(8, device="cuda"), torch.empty(8, device="cuda"), (2, 2, 2), (0, 0, 1))
+    with pytest.raises(capi.MpgError):
+        capi.ConvPlan(H(), 1, 8, 8, [np.zeros((3, 3, 4, 8), np.float32)], [4], 8, 8, force_kind=1)  # cstride % 8
