@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the Multi-pass-GAN generator hot path on B200.
+
+Metric (BASELINE.json): output voxels/sec of the 4x two-pass super-resolution (config 2:
+multipassGAN-4x two-pass 128^3 -> 512^3, random-init weights, synthetic volume).  One "step" = one
+frame through both passes (slice assembly, every conv, the inter-pass axis change, thresholds).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU path (see below)
+
+`value`  : device-timed (CUDA events, max over ranks) with the low-res input resident in HBM.
+`e2e`    : same metric through the public API with HOST buffers: pinned H2D of the frame and D2H of the
+           finished volume inside the timed region.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv of ru2: 5x5 128->128 + 1x1 32->128 shortcut),
+           algorithmic FLOPs per launch / mean launch duration measured live with CUDA events, against the
+           driver-measured dense bf16 peak (MEASURED_PEAKS.json; fp16 runs at the same kind::f16 rate).
+`cpu_baseline` / `--impl reference`: TensorFlow cannot be installed here (no wheel, no network), so the
+           reference's CPU path is timed as the oracle port (torch-CPU fp32 restatement of
+           tools_wscale/GAN.py + gen_resnet) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "multipassGAN-4x two-pass 128^3->512^3 (BASELINE.json configs[1])"
+FLOP_PER_VOXEL = 2534824  # 2 x 1 267 412
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(source="measured", hbm=d["hbm_gbs"], tflops=d["bf16_tflops"],
+                    tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]))
+    return dict(source="fallback", hbm=6650.0, tflops=1590.0, tflops_sustained=1400.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, samples=len(sm), reasons=sorted(reasons))
+
+
+# ============================================================================ reference / CPU arm
+def cpu_reference_sample(L, u, seed, slices, threads=None):
+    """Time the oracle port of the reference generator on `slices` slices per pass; returns
+    (seconds for the sample, extrapolated voxel/s for the full two-pass frame, cores used)."""
+    import numpy as np
+    import torch
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import pipeline as P, synth
+    from oracle import gan as og, networks as on
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    S = L * u
+    w1, w2 = P.make_weights_4x(L, seed, upRes=u)
+    x = synth.synthetic_volume(L, seed=seed)
+    rng = np.random.default_rng(seed)
+    z0 = int(rng.integers(0, L - 2))
+    # pass 1 input rows: `slices` consecutive lerped z slices (GAN/multipassGAN-4x.py:1103)
+    t = np.linspace(z0, z0 + 1, slices, dtype=np.float32)[:, None, None, None]
+    b1 = (x[z0] * (1 - t) + x[z0 + 1] * t).reshape(slices, -1)
+    b2 = rng.random((slices, S * S * 4), dtype=np.float32)  # pass 2 rows: full-res 4-channel slices
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for rows, w, mode in ((b1, w1, 2), (b2, w2, 1)):
+            ctx = og.Context(og.VarStore(values=w), torch.float32)
+            on.gen_resnet(torch.from_numpy(rows), ctx, on.make_cfg_4x(L, upRes=u, upsampling_mode=mode))
+    dt = time.perf_counter() - t0
+    frame_s = dt * (S / slices)
+    return dt, S ** 3 / frame_s, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    L, u = args.L, 4
+    slices = args.cpu_slices
+    for _ in range(args.warmup):
+        cpu_reference_sample(L, u, 1, slices)
+    t = []
+    v = []
+    cores = 0
+    for _ in range(args.steps):
+        dt, vox, cores = cpu_reference_sample(L, u, 1, slices)
+        t.append(dt)
+        v.append(vox)
+    val = sum(v) / len(v)
+    sample = ("oracle port (torch-CPU fp32, oneDNN) of gen_resnet on %d of %d slices per pass at %dx%d, "
+              "extrapolated x%d (slices are independent and equal-cost); host zoom/transposes excluded"
+              % (slices, L * u, L * u, L * u, L * u // slices))
+    line = dict(impl="reference", metric="output voxels/sec", value=val, unit="voxel/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * sum(t) / len(t), higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=WORKLOAD, L=L, upRes=u, step="bounded CPU sample, see cpu_baseline.sample"),
+                cpu_baseline=dict(value=val, unit="voxel/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="voxel/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="TensorFlow 1.x is not installable in this image (no wheel / no network): the reference arm "
+                     "is the CPU restatement of the reference algorithm (oracle/), not TF itself")
+    print(json.dumps(line))
+    return 0
+
+
+# ============================================================================ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import capi, parallel as par, pipeline as P, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference)")
+    rank, local, world = par.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L, u = args.L, 4
+    S = L * u
+    w1, w2 = P.make_weights_4x(L, 1, upRes=u)
+    x_host = synth.synthetic_volume(L, seed=1)
+    mp = P.MultiPass4x(L, w1, w2, upRes=u, precision=args.precision, batch=args.batch, device=local, rank=rank,
+                       world=world, group=None)
+    x_dev = mp.upload(x_host)
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    out_pin = torch.empty((mp.S_loc, S, S), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # dominant kernel: bracket every launch of the biggest conv of pass 1 and pass 2 with events
+    for pn in (mp.p1.net, mp.p2.net):
+        idx, label, fl = pn.dominant_step()
+        pn.timed_step = idx
+    dom_idx, dom_label, dom_flops = mp.p1.net.dominant_step()
+
+    # ---------------- device-resident timing
+    for _ in range(args.warmup):
+        mp(x_dev)
+    for pn in (mp.p1.net, mp.p2.net):
+        pn.timed_events = []
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mp(x_dev, record=True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = S ** 3 / (ms_step * 1e-3)
+    pass_ms = mp.pass_times_ms()
+    kern_ms = [a.elapsed_time(b) for pn in (mp.p1.net, mp.p2.net) for (a, b) in pn.timed_events]
+    kern_avg_ms = sum(kern_ms) / len(kern_ms)
+    kern_share = sum(kern_ms) / (e0.elapsed_time(e1))
+
+    # ---------------- end to end through the public API with host buffers
+    for pn in (mp.p1.net, mp.p2.net):
+        pn.timed_step = None
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        xd = x_pin.to(dev, non_blocking=True)
+        res = mp(xd)
+        out_pin.copy_(res, non_blocking=True)
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    checksum = float(out_pin.double().sum())
+
+    if rank != 0:
+        return 0
+    peaks = load_peaks()
+    achieved = dom_flops / (kern_avg_ms * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"]
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        dt, vox, cores = cpu_reference_sample(L, u, 1, args.cpu_slices)
+        cpu = dict(value=vox, unit="voxel/s", cores=cores, kind="port",
+                   sample="oracle port (torch-CPU fp32) of gen_resnet on %d of %d slices per pass at %dx%d (%.1f s), "
+                          "extrapolated x%d; host zoom/transposes excluded" % (args.cpu_slices, S, S, S, dt,
+                                                                                S // args.cpu_slices))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    line = dict(
+        metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+        dtype={"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
+        config=dict(workload=WORKLOAD, L=L, upRes=u, slice_batch=mp.batch, precision=args.precision,
+                    parallelism="slice-sharded x%d, all-to-all between passes" % world if world > 1 else "single GPU",
+                    l2="per-step working set (>= 0.5 GB activations per layer and slice batch) exceeds the 126 MB L2",
+                    algorithmic_tflop_per_step=S ** 3 * FLOP_PER_VOXEL / 1e12),
+        algorithmic_tflops=S ** 3 * FLOP_PER_VOXEL / (ms_step * 1e-3) / 1e12,
+        frac_of_bf16_peak=dict(burst=S ** 3 * FLOP_PER_VOXEL / (ms_step * 1e-3) / 1e12 / peaks["tflops"] / world,
+                               sustained=S ** 3 * FLOP_PER_VOXEL / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"] / world,
+                               peaks=peaks["source"]),
+        pass_ms=pass_ms,
+        e2e=dict(value=S ** 3 / (e2e_ms * 1e-3), unit="voxel/s", ms_per_step=e2e_ms,
+                 h2d_bytes_per_step=int(x_pin.numel() * 4), d2h_bytes_per_step=int(out_pin.numel() * 4),
+                 checksum=checksum),
+        gpu_launches=int(mp.launches_per_frame * args.steps),
+        roofline=dict(bound="tensor", kernel="conv_igemm_kernel<64> " + dom_label, achieved=achieved, peak=peak,
+                      unit="TFLOP/s", frac=achieved / peak, frac_of_burst=achieved / peaks["tflops"],
+                      peak_source=peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                      flops_per_launch=dom_flops, avg_launch_ms=kern_avg_ms, launches_timed=len(kern_ms),
+                      share_of_step=kern_share, traffic=traffic),
+        clocks=clocks,
+    )
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=8, help="slices per network launch (reference: 8)")
+    ap.add_argument("--L", type=int, default=128, help="low-res edge (config 2: 128)")
+    ap.add_argument("--cpu-slices", type=int, default=4, help="slices per pass timed on the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -148,7 +148,7 @@ int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_
  * velScale / *upRes factors of GAN/multipassGAN-4x.py:277-283).
  * If `dens` != NULL, output channel 0 is instead read from the fp32 volume dens[S_s, H, W]
  * (already laid out in slice order; first-pass density, GAN/multipassGAN-4x.py:1113) and the
- * field channels follow from channel 1.
+ * field channels follow from channel 1; dens row 0 is slice `dens_slice0` (a rank's slab).
  * If add_adj != 0 two more channels are appended: channel chan_src[0] of slice s-1 and s+1 of the
  * interpolated stack, zero outside [0, n_slices) (GAN/multipassGAN-out.py:423-436).
  * Remaining channels up to out_cstride are zero. */
@@ -163,6 +163,7 @@ typedef struct mpg_assemble_desc {
   int add_adj;
   int out_dtype;    /* MPG_BF16 / MPG_F16 / MPG_F32                               */
   int out_cstride;
+  int dens_slice0;  /* absolute slice index of dens[0] (0 unless the volume is sharded)  */
 } mpg_assemble_desc;
 
 int mpg_slice_assemble(mpg_handle h, const mpg_assemble_desc* d, const float* vol, const float* dens,

@@ -52,7 +52,7 @@ class AssembleDesc(ctypes.Structure):
     _fields_ = [("dims", ctypes.c_int * 3), ("vol_c", ctypes.c_int), ("axis_of", ctypes.c_int * 3),
                 ("zoom", ctypes.c_int * 3), ("nchan", ctypes.c_int), ("chan_src", ctypes.c_int * 8),
                 ("chan_scale", ctypes.c_float * 8), ("add_adj", ctypes.c_int), ("out_dtype", ctypes.c_int),
-                ("out_cstride", ctypes.c_int)]
+                ("out_cstride", ctypes.c_int), ("dens_slice0", ctypes.c_int)]
 
 
 _lib = None
@@ -252,7 +252,7 @@ def dens_residual(handle, dens, src, src_dtype, src_cstride, src_c, mode, bicubi
 
 
 def make_assemble_desc(dims, vol_c, axis_of, zoom, chan_src, chan_scale=None, add_adj=False, out_dtype=BF16,
-                       out_cstride=8):
+                       out_cstride=8, dens_slice0=0):
     d = AssembleDesc()
     for k in range(3):
         d.dims[k], d.axis_of[k], d.zoom[k] = int(dims[k]), int(axis_of[k]), int(zoom[k])
@@ -264,6 +264,7 @@ def make_assemble_desc(dims, vol_c, axis_of, zoom, chan_src, chan_scale=None, ad
     d.add_adj = int(bool(add_adj))
     d.out_dtype = int(out_dtype)
     d.out_cstride = int(out_cstride)
+    d.dens_slice0 = int(dens_slice0)
     return d
 
 

@@ -114,20 +114,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
     }
   } else if (warp == 3) {
-    // ===================== B producer: one weight tile per (segment, chunk, dx, dy) ==========
+    // ===================== B producer: weight tiles, `bgroup` consecutive dy taps per stage =====
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = static_cast<uint32_t>(p.npad * RB);
+      const uint32_t tile_bytes = static_cast<uint32_t>(p.npad * RB);
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         int kt = 0;
         for (int s = 0; s < p.nseg; ++s) {
-          const int nk = p.seg_nchunk[s] * p.seg_ks[s] * p.seg_ks[s];
-          for (int i = 0; i < nk; ++i, ++kt) {
+          const int ks = p.seg_ks[s];
+          const int gb = p.bgroup ? ks : 1;
+          const int ngroups = p.seg_nchunk[s] * ks * (ks / gb);
+          for (int i = 0; i < ngroups; ++i) {
             mbar_wait(&empty_b[st], ph ^ 1u);
-            mbar_arrive_expect_tx(&full_b[st], bytes);
-            tma_load_2d(smB + static_cast<size_t>(st) * p.b_stage_bytes, &tm_w, &full_b[st], 0,
-                        kt * p.npad);
+            mbar_arrive_expect_tx(&full_b[st], tile_bytes * gb);
+            uint8_t* dst = smB + static_cast<size_t>(st) * p.b_stage_bytes;
+            for (int g = 0; g < gb; ++g, ++kt)
+              tma_load_2d(dst + static_cast<size_t>(g) * p.b_tile_bytes, &tm_w, &full_b[st], 0, kt * p.npad);
             if (++st == p.nb) {
               st = 0;
               ph ^= 1u;
@@ -137,56 +140,69 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =========================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
-        tc_fence_after();
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const int ks = p.seg_ks[s];
-          for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
-            for (int dx = 0; dx < ks; ++dx) {
-              mbar_wait(&full_a[sa], pa);
+    // ===================== MMA issuer ==========================================================
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
+    // registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
+    // smem-descriptor words: hi = SBO | version 1 | layout type; lo = (addr >> 4) | LBO(1)
+    constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t DESC_LO = 1u << 16;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>((buf * 2) * p.npad);
+      const uint32_t d1 = d0 + static_cast<uint32_t>(p.npad);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int ks = p.seg_ks[s];
+        const int gb = p.bgroup ? ks : 1;
+        for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+          for (int dx = 0; dx < ks; ++dx) {
+            mbar_wait(&full_a[sa], pa);
+            tc_fence_after();
+            const uint32_t a_lo = ((smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+            for (int dy0 = 0; dy0 < ks; dy0 += gb) {
+              mbar_wait(&full_b[sb], pb);
               tc_fence_after();
-              const uint32_t a_base = smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes);
-              for (int dy = 0; dy < ks; ++dy) {
-                mbar_wait(&full_b[sb], pb);
-                tc_fence_after();
-                const uint32_t b_base = smem_u32(smB + static_cast<size_t>(sb) * p.b_stage_bytes);
-#pragma unroll
-                for (int acc = 0; acc < 2; ++acc) {
-                  const uint32_t a_row = a_base + static_cast<uint32_t>((dy * kIgTileW + acc * 128) * RB);
-                  const uint32_t d_addr = tmem_base + static_cast<uint32_t>((buf * 2 + acc) * p.npad);
+              const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(sb) * p.b_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+              if (elect_one()) {
+                for (int g = 0; g < gb; ++g) {
+                  const uint32_t ag = a_lo + static_cast<uint32_t>(((dy0 + g) * kIgTileW * RB) >> 4);
+                  const uint32_t bg = b_lo + static_cast<uint32_t>((g * p.b_tile_bytes) >> 4);
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
-                    const uint64_t ad = umma_smem_desc(a_row + k * 32, SBO, LAYOUT);
-                    const uint64_t bd = umma_smem_desc(b_base + k * 32, SBO, LAYOUT);
-                    umma_bf16_ss(d_addr, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+                    const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
+                    const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
+                    const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
+                    umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                    umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
                   }
+                  accumulate = 1;
                 }
-                accumulate = 1;
                 umma_commit(&empty_b[sb]);
-                if (++sb == p.nb) {
-                  sb = 0;
-                  pb ^= 1u;
-                }
               }
-              umma_commit(&empty_a[sa]);
-              if (++sa == p.na) {
-                sa = 0;
-                pa ^= 1u;
+              __syncwarp();
+              accumulate = 1;
+              if (++sb == p.nb) {
+                sb = 0;
+                pb ^= 1u;
               }
+            }
+            if (elect_one()) umma_commit(&empty_a[sa]);
+            __syncwarp();
+            if (++sa == p.na) {
+              sa = 0;
+              pa ^= 1u;
             }
           }
         }
-        umma_commit(&tmem_full[buf]);
       }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global ==============================
@@ -207,7 +223,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       for (int acc = 0; acc < 2; ++acc) {
         const int y = tc.y0 + acc * 8 + prow;
         const int x = tc.x0 + pcol;
-        const bool valid = (y < p.h) && (x < p.w);
+        const bool valid = (y < p.h) && (x < p.w) && !(p.dbg & 1);
+        if (p.dbg & 2) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                                static_cast<uint32_t>((buf * 2 + acc) * p.npad);
         float rn = 1.0f;

@@ -21,7 +21,7 @@ constexpr int kIgTileW = 16;
 constexpr int kIgTileH = 16;
 constexpr int kIgThreads = 256;
 constexpr int kIgMaxStagesA = 4;
-constexpr int kIgMaxStagesB = 8;
+constexpr int kIgMaxStagesB = 12;
 
 struct IgemmParams {
   int n, h, w;
@@ -36,6 +36,9 @@ struct IgemmParams {
   int out_dtype, out_cstride;
   int na, nb;  // pipeline depth of the A / B rings
   int a_stage_bytes, b_stage_bytes;
+  int b_tile_bytes;  // one (seg,chunk,dx,dy) weight tile
+  int bgroup;        // 1: a B stage holds all ks dy-taps of a (chunk,dx) (same cadence as A); 0: one tap
+  int dbg;  // profiling only (env MPG_IGEMM_DBG): bit0 skip global stores, bit1 skip the TMEM loads too
   uint32_t tmem_cols;
   const float* shift;  // [npad] device
   void* out;

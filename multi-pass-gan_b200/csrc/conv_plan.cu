@@ -1,5 +1,6 @@
 // Convolution plans: argument validation, weight packing, kernel selection and launch.
 // C-ABI: mpg_conv_plan_* (include/mpg.h).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -151,11 +152,31 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.out_cstride = d.out_cstride;
   ip.a_stage_bytes = (kIgTileH + maxks - 1) * kIgTileW * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
-  ip.b_stage_bytes = round_up(npad * rb, 1024);
+  ip.b_tile_bytes = round_up(npad * rb, 1024);
+  // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: the MMA
+  // thread then waits/commits once per 2*ks*CK/16 MMAs instead of once per 2*CK/16 (issue-latency bound)
+  ip.bgroup = (maxks * ip.b_tile_bytes <= 40 * 1024) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_BGROUP")) ip.bgroup = atoi(e) ? 1 : 0;
+  ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
+  // Ring depths: one B stage only carries 2*CK/16 MMAs (~0.1-0.35 us of tensor work) but a TMA
+  // round trip is ~1 us, so small weight tiles need a deep ring; A stages carry ks times more work.
   const int budget = 200 * 1024;
-  ip.nb = 4;
-  int na = (budget - ip.nb * ip.b_stage_bytes) / ip.a_stage_bytes;
-  ip.na = na > kIgMaxStagesA ? kIgMaxStagesA : (na < 2 ? 2 : na);
+  int nb = (96 * 1024) / ip.b_stage_bytes;
+  nb = nb > kIgMaxStagesB ? kIgMaxStagesB : (nb < 4 ? 4 : nb);
+  if (ip.bgroup && nb > 4) nb = 4;
+  while (nb > 2 && nb * ip.b_stage_bytes + 2 * ip.a_stage_bytes > budget) --nb;
+  if (const char* e = getenv("MPG_IGEMM_NB")) nb = atoi(e);
+  int na = (budget - nb * ip.b_stage_bytes) / ip.a_stage_bytes;
+  na = na > kIgMaxStagesA ? kIgMaxStagesA : (na < 2 ? 2 : na);
+  if (const char* e = getenv("MPG_IGEMM_NA")) na = atoi(e);
+  if (nb < 1 || nb > kIgMaxStagesB || na < 1 || na > kIgMaxStagesA ||
+      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes > 220 * 1024) {
+    set_error("conv: bad pipeline depth na=%d nb=%d", na, nb);
+    return MPG_EINVAL;
+  }
+  ip.nb = nb;
+  ip.na = na;
+  if (const char* e = getenv("MPG_IGEMM_DBG")) ip.dbg = atoi(e);
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
   ip.tmem_cols = cols;
@@ -250,11 +271,10 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   int kind = d.force_kind;
   const bool elig = igemm_eligible(d);
   if (kind == 0) {
-    // thin layers (few input or output channels) are HBM-bound: CUDA cores; the rest: tensor cores.
-    // Narrow shortcut segments (e.g. the 4-channel 1x1 of ru1) ride along, zero-filled by TMA.
-    int maxcin = 0;
-    for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
-    kind = (elig && d.cout >= 8 && maxcin >= 8) ? 1 : 2;
+    // Every 16-bit stride-1 conv goes to the tensor cores, thin layers included: a 25-tap conv with
+    // Cin <= 16 is 25 K=16 MMAs per 128 pixels, far cheaper than the CUDA-core loop (TMA zero-fills
+    // the missing channels, the weights of padded output channels are zero).
+    kind = elig ? 1 : 2;
   }
   if (kind == 1 && !elig) {
     mpg::set_error("conv: tcgen05 path needs bf16/f16 input (same 16-bit output type or f32), stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");

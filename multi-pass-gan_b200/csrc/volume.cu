@@ -20,7 +20,7 @@ struct AsmParams {
   long long vstride[3];
   const float* vol;
   const float* dens;
-  int slice0, count;
+  int slice0, count, dens_slice0;
   void* out;
 };
 
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) slice_assemble_kernel(const AsmParams p) 
 
   float v[16];
   int oc = 0;
-  if (p.dens) v[oc++] = __ldg(p.dens + (static_cast<long long>(s) * H + i) * W + j);
+  if (p.dens) v[oc++] = __ldg(p.dens + (static_cast<long long>(s - p.dens_slice0) * H + i) * W + j);
   for (int c = 0; c < p.nchan; ++c) v[oc++] = p.chan_scale[c] * sample(p, l, p.chan_src[c]);
   if (p.add_adj) {
     for (int d = -1; d <= 1; d += 2) {
@@ -203,6 +203,8 @@ int mpg_slice_assemble(mpg_handle h, const mpg_assemble_desc* d, const float* vo
   p.dens = dens;
   p.slice0 = slice0;
   p.count = count;
+  p.dens_slice0 = d->dens_slice0;
+  MPG_CHECK_ARG(!dens || slice0 >= d->dens_slice0, "assemble: slice0 %d precedes dens_slice0 %d", slice0, d->dens_slice0);
   p.out = out;
   MPG_CHECK_ARG(slice0 >= 0 && count >= 1 && slice0 + count <= p.odims[0], "assemble: slices [%d,%d) outside [0,%d)",
                 slice0, slice0 + count, p.odims[0]);

@@ -80,12 +80,15 @@ class CompiledNet:
         self.weights = weights
         self.act_dtype = {"bf16": capi.BF16, "fp16": capi.F16, "fp32": capi.F32}[precision]
         self.steps = []  # (label, callable(stream))
+        self.step_flops = {}
         self.launches = 0
         self.flops = 0.0
         self.plans = []
         self.placeholders = {}  # name -> Buf
         self.activation_bytes = 0
         self.verbose = verbose
+        self.timed_step = None  # index into self.steps bracketed by CUDA events when set (bench roofline)
+        self.timed_events = []
         self._lower(output)
 
     # ------------------------------------------------------------------ helpers
@@ -367,16 +370,17 @@ class CompiledNet:
             " " + grp.act if grp.act else "", " pn" if grp.pn else "", " up2" if grp.ups == 2 else "")
         if self.verbose:
             print(label)
+        self.step_flops[len(self.steps)] = flops
         self.steps.append((label, step))
         return View(oh, ow, [(out, 0, cout, 1, 1)])
 
     def _predict_kind(self, convs, ins, cout, out_dtype, stride):
         """Mirror of the auto rule in csrc/conv_plan.cu (dry runs only)."""
-        if self.act_dtype == capi.F32 or stride != 1 or cout > 128 or cout < 8:
+        if self.act_dtype == capi.F32 or stride != 1 or cout > 128:
             return capi.KIND_DIRECT
         if any(c.attrs["ksize"] not in (1, 3, 5) for c in convs) or any(b.cstride % 8 for b in ins):
             return capi.KIND_DIRECT
-        return capi.KIND_TCGEN05 if max(c.inputs[0].shape[3] for c in convs) >= 8 else capi.KIND_DIRECT
+        return capi.KIND_TCGEN05
 
     # ------------------------------------------------------------------ execution
     def run(self, feeds, out=None, stream=None):
@@ -397,13 +401,32 @@ class CompiledNet:
         if out is not None:
             root.ptr = out.data_ptr() if hasattr(out, "data_ptr") else int(out)
         try:
-            for _, step in self.steps:
-                step(st)
+            if self.timed_step is None:
+                for _, step in self.steps:
+                    step(st)
+            else:
+                cur = torch.cuda.current_stream(self.device)
+                ts = cur if cur.cuda_stream == st else torch.cuda.ExternalStream(st, device=self.device)
+                for i, (_, step) in enumerate(self.steps):
+                    if i == self.timed_step:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record(ts)
+                        step(st)
+                        e1.record(ts)
+                        self.timed_events.append((e0, e1))
+                    else:
+                        step(st)
         finally:
             root.ptr = saved
         if out is None:
             return root.tensor.view(self.batch, -1)
         return out
+
+    def dominant_step(self):
+        """Index, label and FLOPs of the conv step with the most algorithmic FLOPs."""
+        best = max(range(len(self.steps)), key=lambda i: self.step_flops.get(i, 0.0))
+        return best, self.steps[best][0], self.step_flops[best]
 
     def close(self):
         for p in self.plans:

@@ -1,0 +1,83 @@
+"""Slice sharding of the multi-pass pipeline across the GPUs of one box.
+
+Within a pass every slice is an independent 2-D inference (GAN/multipassGAN-out.py:443-447), so rank g
+owns the contiguous slice range [g*S/G, (g+1)*S/G) of the pass's slice axis.  The only communication is
+the axis change between passes (the `np.array(rows).reshape(S,S,S).transpose(...)` of
+GAN/multipassGAN-out.py:459,521 / GAN/multipassGAN-4x.py:1142): a slab along the old slice axis must
+become a slab along the new one = ONE all-to-all of S^3/G^2-element blocks per rank pair, packed and
+unpacked by the transpose kernel.  NCCL over NVLink 5 / NVSwitch on the GPUs (`torch.distributed`
+backend "nccl"); the same code runs under "gloo" on CPU tensors for the host-logic tests.
+
+`permute3(src, dst, dims, perm, threshold)` is the 3-D axis permutation primitive: on the GPU it is
+capi.transpose3d (mpg_transpose3d), in the CPU tests a torch.permute.
+"""
+import torch
+import torch.distributed as dist
+
+
+def slab_range(rank, world, n):
+    """Contiguous slice range owned by `rank`; requires world | n (the reference drops ragged batches)."""
+    if n % world:
+        raise ValueError("slice count %d is not divisible by the number of ranks %d" % (n, world))
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def _all_to_all(recv, send, group):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    else:
+        recv.view(-1).copy_(send.view(-1))
+
+
+def reslab(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0):
+    """Turn this rank's slab along axis 0 into its slab along (old) axis 2, permuted by `final_perm`.
+
+    slab      [S/G, S, S]   (a_loc, b, c)  rows of the finished pass, a = old slice axis
+    out       the rank's part of the re-sliced volume:  permute(recv[(A), b, c_loc], final_perm)
+              where recv is the full-A extent restricted to this rank's c range.
+    scratch_* two buffers of S^3/G elements.
+    Steps: pack [a_loc*b, G, c_loc] -> [G, a_loc*b, c_loc]; all-to-all; the received chunks, ordered by
+    source rank, ARE [A, b, c_loc]; one final permutation (with the optional threshold fused).
+    """
+    per = S // world
+    if world == 1:
+        permute3(slab, out, (S, S, S), final_perm, threshold)
+        return out
+    permute3(slab, scratch_a, (per * S, world, per), (1, 0, 2), 0.0)
+    _all_to_all(scratch_b, scratch_a, group)
+    permute3(scratch_b, out, (S, S, per), final_perm, threshold)
+    return out
+
+
+def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0):
+    """Same as `reslab` but the NEW slab axis is the old axis 1 (b):  [a_loc, B, c] -> perm([A, b_loc, c]).
+
+    pack [a_loc, G, b_loc*c] -> [G, a_loc, b_loc*c]; all-to-all -> [A, b_loc, c]; final permutation.
+    """
+    per = S // world
+    if world == 1:
+        permute3(slab, out, (S, S, S), final_perm, threshold)
+        return out
+    permute3(slab, scratch_a, (per, world, per * S), (1, 0, 2), 0.0)
+    _all_to_all(scratch_b, scratch_a, group)
+    permute3(scratch_b, out, (S, per, S), final_perm, threshold)
+    return out
+
+
+def init_from_env(device_index=None):
+    """One process per GPU under torchrun: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local if device_index is None else device_index)
+            dist.init_process_group("nccl", rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local if device_index is None else device_index))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    return rank, local, world

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import capi, engine
+from . import parallel as par
 from . import graph as G
 from . import networks as N
 from . import weights as W
@@ -59,18 +60,25 @@ class _PassNet:
 
 
 class MultiPass4x:
-    """Two-pass 4x super-resolution of one frame: [L,L,L,4] -> [4L,4L,4L] (z,y,x), fp32."""
+    """Two-pass 4x super-resolution of one frame: [L,L,L,4] -> [4L,4L,4L] (z,y,x), fp32.
+
+    With world > 1 the volume is sharded by slice: the rank computes z-slab [S/G,S,S] in pass 1, the
+    all-to-all turns z-slabs into x-slabs for pass 2, and a second one returns canonical z-slabs, so
+    `__call__` returns this rank's [S/G, S, S] part of the output (rank-major == z order)."""
 
     def __init__(self, L, weights_pass1, weights_pass2, upRes=4, precision="fp16", batch=8, velScale=1.0,
-                 batch_norm=True, device=0, threshold=THRESHOLD):
+                 batch_norm=True, device=0, threshold=THRESHOLD, rank=0, world=1, group=None):
         self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
         self.precision = precision
         self.velScale = float(velScale)
         self.threshold = float(threshold)
+        self.rank, self.world, self.group = int(rank), int(world), group
         L, S, u = self.L, self.S, self.u
-        self.batch = _pick_batch(S, batch)
+        self.s0, self.s1 = par.slab_range(self.rank, self.world, S)
+        self.S_loc = self.s1 - self.s0
+        self.batch = _pick_batch(self.S_loc, batch)
         cfg1 = N.config_4x(L, upRes=u, upsampling_mode=2, batch_norm=batch_norm)
         cfg2 = N.config_4x(L, upRes=u, upsampling_mode=1, batch_norm=batch_norm)
         self.p1 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg1), weights_pass1,
@@ -84,58 +92,78 @@ class MultiPass4x:
         # pass 2: concat(x_2, zoom(vel*u,[u,u,u,1])).transpose(0,3,1,2,4) + swaps 2<->3, 3<->1 (:1113-1119):
         # slices along x of (z,y) planes, channels (d, vy, vz, vx); velScale hits vy,vz only (App. D.10)
         self.asm2 = capi.make_assemble_desc((L, L, L), 4, (2, 0, 1), (u, u, u), (2, 3, 1),
-                                            (u * vs, u * vs, float(u)), out_dtype=capi.F32, out_cstride=4)
+                                            (u * vs, u * vs, float(u)), out_dtype=capi.F32, out_cstride=4,
+                                            dens_slice0=self.s0)
         f32 = dict(dtype=torch.float32, device=self.device)
         self.in1 = torch.empty((self.batch, L, L, 4), **f32)
         self.in2 = torch.empty((self.batch, S, S, 4), **f32)
-        self.vol_a = torch.empty((S, S, S), **f32)
-        self.vol_b = torch.empty((S, S, S), **f32)
-        self.flops = (self.p1.net.flops + self.p2.net.flops) / self.batch * S
-        self.launches_per_frame = (S // self.batch) * (self.p1.net.launches + self.p2.net.launches + 2) + 2
+        self.vol_a = torch.empty((self.S_loc, S, S), **f32)
+        self.vol_b = torch.empty((self.S_loc, S, S), **f32)
+        if self.world > 1:
+            self.scr_a = torch.empty((self.S_loc, S, S), **f32)
+            self.scr_b = torch.empty((self.S_loc, S, S), **f32)
+        else:
+            self.scr_a = self.scr_b = None
+        nb = self.S_loc // self.batch
+        self.flops = (self.p1.net.flops + self.p2.net.flops) / self.batch * self.S_loc  # this rank's share
+        self.launches_per_frame = nb * (self.p1.net.launches + self.p2.net.launches + 2) + (2 if world == 1 else 4)
         self.events = None
 
-    def __call__(self, x, slice_range=None, record=False):
-        """x: [L,L,L,4] float32 (numpy or device tensor). Returns the device tensor [S,S,S] (z,y,x)."""
+    def _permute3(self, src, dst, dims, perm, thr):
+        capi.transpose3d(self.h, src, dst, dims, perm, thr, torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload(self, x):
+        return _dev_f32(x, self.device)
+
+    def __call__(self, x, record=False):
+        """x: [L,L,L,4] float32 (numpy or device tensor, replicated on every rank).
+        Returns the device tensor [S/G,S,S] (z,y,x): this rank's z-slab of the output."""
         S, B = self.S, self.batch
         st = torch.cuda.current_stream(self.device).cuda_stream
         vol = _dev_f32(x, self.device)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
         if ev:
             ev[0].record()
-        # ---- pass 1: xy slices along (interpolated) z; rows land in vol_a[z] = [Zu, Yu, Xu]
-        for s0 in range(0, S, B):
-            capi.slice_assemble(self.h, self.asm1, vol, None, s0, B, self.in1, st)
-            self.p1.net.run({"x": self.in1}, out=self.vol_a[s0], stream=st)
+        # ---- pass 1: xy slices along (interpolated) z; rows land in vol_a[z - s0] = [Zu_loc, Yu, Xu]
+        for s in range(self.s0, self.s1, B):
+            capi.slice_assemble(self.h, self.asm1, vol, None, s, B, self.in1, st)
+            self.p1.net.run({"x": self.in1}, out=self.vol_a[s - self.s0], stream=st)
         if ev:
             ev[1].record()
-        # ---- the .uni hand-over between the two processes: threshold (:1155-1157), then pass 2 slices along x
-        capi.transpose3d(self.h, self.vol_a, self.vol_b, (S, S, S), (2, 0, 1), self.threshold, st)  # [Xu,Zu,Yu]
-        for s0 in range(0, S, B):
-            capi.slice_assemble(self.h, self.asm2, vol, self.vol_b, s0, B, self.in2, st)
-            self.p2.net.run({"x": self.in2}, out=self.vol_a[s0], stream=st)
+        # ---- the .uni hand-over between the two processes: threshold (:1155-1157) + axis change to
+        #      slices along x: [Zu,Yu,Xu] -> [Xu_loc, Zu, Yu]
+        par.reslab(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
+                   (2, 0, 1), self.threshold)
         if ev:
             ev[2].record()
-        # rows [Xu, Zu, Yu] -> .transpose(1,2,0) -> [Zu, Yu, Xu] (:1142), threshold (:1155-1157)
-        capi.transpose3d(self.h, self.vol_a, self.vol_b, (S, S, S), (1, 2, 0), self.threshold, st)
+        for s in range(self.s0, self.s1, B):
+            capi.slice_assemble(self.h, self.asm2, vol, self.vol_b, s, B, self.in2, st)
+            self.p2.net.run({"x": self.in2}, out=self.vol_a[s - self.s0], stream=st)
         if ev:
             ev[3].record()
+        # rows [Xu_loc, Zu, Yu] -> .transpose(1,2,0) -> [Zu_loc, Yu, Xu] (:1142), threshold (:1155-1157)
+        par.reslab_mid(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
+                       (1, 2, 0), self.threshold)
+        if ev:
+            ev[4].record()
             self.events = ev
         return self.vol_b
 
     def pass1_only(self, x):
-        """First-pass volume [Zu,Yu,Xu] after the threshold (what pass 2 reads from density_low_2x2_*.uni)."""
+        """First-pass volume [Zu_loc,Yu,Xu] after the threshold (what pass 2 reads from density_low_2x2_*.uni)."""
         S, B = self.S, self.batch
         st = torch.cuda.current_stream(self.device).cuda_stream
         vol = _dev_f32(x, self.device)
-        for s0 in range(0, S, B):
-            capi.slice_assemble(self.h, self.asm1, vol, None, s0, B, self.in1, st)
-            self.p1.net.run({"x": self.in1}, out=self.vol_a[s0], stream=st)
-        capi.threshold(self.h, self.vol_a, S * S * S, self.threshold, st)
+        for s in range(self.s0, self.s1, B):
+            capi.slice_assemble(self.h, self.asm1, vol, None, s, B, self.in1, st)
+            self.p1.net.run({"x": self.in1}, out=self.vol_a[s - self.s0], stream=st)
+        capi.threshold(self.h, self.vol_a, self.S_loc * S * S, self.threshold, st)
         return self.vol_a
 
     def pass_times_ms(self):
         e = self.events
-        return dict(pass1=e[0].elapsed_time(e[1]), pass2=e[1].elapsed_time(e[2]), final=e[2].elapsed_time(e[3]))
+        return dict(pass1=e[0].elapsed_time(e[1]), exchange1=e[1].elapsed_time(e[2]), pass2=e[2].elapsed_time(e[3]),
+                    exchange2=e[3].elapsed_time(e[4]))
 
 
 def make_weights_4x(L, seed, upRes=4, batch_norm=True, randomize_bn=False):
