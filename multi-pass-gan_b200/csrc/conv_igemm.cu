@@ -19,6 +19,27 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// Branch-free activation: act(v) = ca*v + cb*|v| covers none (1,0), relu (0.5,0.5: exact) and the
+// reference's lrelu 0.6*x + 0.4*|x| (tools_wscale/GAN.py:733-737); tanh is a rare separate pass.
+__device__ __forceinline__ void epi_chunk16(uint32_t taddr, const float* __restrict__ shift16, float ca, float cb,
+                                            bool is_tanh, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+  const float4* s4 = reinterpret_cast<const float4*>(shift16);
+  const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
+  const float sh[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float x = __uint_as_float(r[j]) + sh[j];
+    v[j] = fmaf(cb, fabsf(x), ca * x);
+  }
+  if (is_tanh) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = tanhf(__uint_as_float(r[j]) + sh[j]);
+  }
+}
+
 struct TileCoord {
   int n, y0, x0;
 };
@@ -36,7 +57,8 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const IgemmParams& p) {
 template <int CK>
 __global__ void __launch_bounds__(kIgThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
-                  const __grid_constant__ CUtensorMap tm_w, const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+                  const IgemmParams p) {
   constexpr int RB = CK * 2;  // bytes per pixel row of one K-chunk == swizzle span
   constexpr uint32_t LAYOUT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
   constexpr uint32_t SBO = 8u * RB;  // 8 pixels per swizzle group
@@ -47,7 +69,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   __shared__ __align__(8) uint64_t full_b[kIgMaxStagesB], empty_b[kIgMaxStagesB];
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_shift[256];
+  __shared__ __align__(16) float s_shift[256];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -63,6 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     tma_prefetch_desc(&tm_x0);
     if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_w);
+    if (p.tma_store) tma_prefetch_desc(&tm_y);
     for (int i = 0; i < p.na; ++i) {
       mbar_init(&full_a[i], 1);
       mbar_init(&empty_a[i], 1);
@@ -85,6 +108,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const float act_a = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.6f : 1.0f);
+  const float act_b = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.4f : 0.0f);
+  const bool act_tanh = p.act == MPG_ACT_TANH;
 
   if (warp == 0) {
     // ===================== A producer: one halo image per (segment, chunk, dx) ===============
@@ -178,8 +204,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                     const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
                     const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
                     const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
-                    umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                    umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                    if (!(p.dbg & 4)) {
+                      umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                      umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                    }
                   }
                   accumulate = 1;
                 }
@@ -204,8 +232,100 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       if (elect_one()) umma_commit(&tmem_full[buf]);
       __syncwarp();
     }
+  } else if (warp >= 4 && p.tma_store) {
+    // ===================== epilogue A: TMEM -> registers -> swizzled smem -> TMA store =========
+    // (16-bit outputs) each thread owns one pixel row of the accumulator; its 16-byte channel chunks
+    // go to a staging tile laid out like a TMA box [128 px][box_c ch], one elected thread stores it.
+    const int ew = warp & 3;
+    const int m = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const float inv_c = 1.0f / static_cast<float>(p.cout);
+    const int od = p.out_dtype;
+    const int box_c = p.box_c;
+    const int row_b = box_c * 2;                // bytes per staged pixel row
+    const int cpb = box_c >> 3;                 // 16-byte chunks per box row
+    const uint32_t swz = (box_c == 64) ? static_cast<uint32_t>(m & 7)
+                         : (box_c == 32) ? static_cast<uint32_t>((m >> 1) & 3)
+                         : (box_c == 16) ? static_cast<uint32_t>((m >> 2) & 1) : 0u;
+    uint8_t* stg = smem + p.stage_off;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const TileCoord tc = decode_tile(t, p);
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      if (it > 0) {  // the previous tile's stores must have finished reading the staging tiles
+        if (et == 0) tma_store_wait_read();
+        named_bar_sync(1, 128);
+      }
+      if (!(p.dbg & 2)) {
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                                 static_cast<uint32_t>((buf * 2 + acc) * p.npad);
+          uint8_t* srow = stg + static_cast<size_t>(acc) * p.stage_bytes + static_cast<size_t>(m) * row_b;
+          float rn = 1.0f;
+          if (p.pixel_norm) {
+            float ssq = 0.0f;
+            for (int c0 = 0; c0 < p.npad; c0 += 16) {
+              float v[16];
+              epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ssq = fmaf(v[j], v[j], ssq);
+            }
+            rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
+          }
+          for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            float v[16];
+            epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= rn;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const int cb = c0 + hq * 8;  // first channel of this 16-byte chunk
+              if (cb < p.out_cstride) {
+                const int bx = cb / box_c;
+                const uint32_t j = static_cast<uint32_t>((cb - bx * box_c) >> 3);
+                uint4 q;
+                q.x = pack_h16x2(v[hq * 8 + 0], v[hq * 8 + 1], od);
+                q.y = pack_h16x2(v[hq * 8 + 2], v[hq * 8 + 3], od);
+                q.z = pack_h16x2(v[hq * 8 + 4], v[hq * 8 + 5], od);
+                q.w = pack_h16x2(v[hq * 8 + 6], v[hq * 8 + 7], od);
+                *reinterpret_cast<uint4*>(srow + static_cast<size_t>(bx) * (128 * row_b) + ((j ^ swz) << 4)) = q;
+              }
+            }
+          }
+        }
+      }
+      // accumulators are drained: hand the TMEM buffer back before the stores are issued
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (et == 0 && !(p.dbg & 1)) {
+        for (int acc = 0; acc < 2; ++acc) {
+          const int y = tc.y0 + acc * 8;
+          if (y >= p.h) continue;
+          for (int bx = 0; bx < p.nbox; ++bx) {
+            const uint8_t* src = stg + static_cast<size_t>(acc) * p.stage_bytes + static_cast<size_t>(bx) * (128 * row_b);
+            if (p.upsample == 1) {
+              tma_store_4d(&tm_y, src, bx * box_c, tc.x0, y, tc.n);
+            } else {
+              // output viewed as [N, H, 2, W, 2*cstride]: (ux, c) innermost, uy between W and H
+              for (int uy = 0; uy < 2; ++uy)
+                for (int ux = 0; ux < 2; ++ux)
+                  tma_store_5d(&tm_y, src, ux * p.out_cstride + bx * box_c, tc.x0, uy, y, tc.n);
+            }
+          }
+        }
+        tma_store_commit();
+      }
+      (void)cpb;
+    }
+    if (et == 0) tma_store_wait_all();
   } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> global ==============================
+    // ===================== epilogue B (fp32 outputs): TMEM -> registers -> global ==============================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     const int m = ew * 32 + lane;
     const int prow = m >> 4;
@@ -231,25 +351,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         if (p.pixel_norm) {
           float ssq = 0.0f;
           for (int c0 = 0; c0 < p.npad; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
+            float v[16];
+            epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float v = apply_act(__uint_as_float(r[j]) + s_shift[c0 + j], p.act);
-              ssq = fmaf(v, v, ssq);
-            }
+            for (int j = 0; j < 16; ++j) ssq = fmaf(v[j], v[j], ssq);
           }
           rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
         }
         for (int c0 = 0; c0 < p.npad; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
           float v[16];
+          epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = apply_act(__uint_as_float(r[j]) + s_shift[c0 + j], p.act) * rn;
+          for (int j = 0; j < 16; ++j) v[j] *= rn;
           if (valid) {
             for (int uy = 0; uy < ups; ++uy) {
               for (int ux = 0; ux < ups; ++ux) {
@@ -321,13 +434,13 @@ int igemm_set_smem_attr(int ck, size_t smem_bytes) {
 }
 
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
-                 const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
+                 const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
   if (ck == 64)
-    conv_igemm_kernel<64><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+    conv_igemm_kernel<64><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
   else if (ck == 32)
-    conv_igemm_kernel<32><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+    conv_igemm_kernel<32><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
   else
-    conv_igemm_kernel<16><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+    conv_igemm_kernel<16><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
   return static_cast<int>(cudaGetLastError());
 }
 

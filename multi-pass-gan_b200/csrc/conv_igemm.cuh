@@ -38,6 +38,8 @@ struct IgemmParams {
   int a_stage_bytes, b_stage_bytes;
   int b_tile_bytes;  // one (seg,chunk,dx,dy) weight tile
   int bgroup;        // 1: a B stage holds all ks dy-taps of a (chunk,dx) (same cadence as A); 0: one tap
+  // TMA-store epilogue (16-bit outputs): rows are staged in smem as [box][128 px][box_c ch] (swizzled)
+  int tma_store, box_c, nbox, stage_off, stage_bytes;
   int dbg;  // profiling only (env MPG_IGEMM_DBG): bit0 skip global stores, bit1 skip the TMEM loads too
   uint32_t tmem_cols;
   const float* shift;  // [npad] device
@@ -46,7 +48,7 @@ struct IgemmParams {
 
 // ck in {16, 32, 64}; returns cudaError_t as int
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
-                 const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+                 const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
 int igemm_set_smem_attr(int ck, size_t smem_bytes);
 
 }  // namespace mpg

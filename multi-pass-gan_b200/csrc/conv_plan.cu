@@ -23,6 +23,8 @@ struct mpg_conv_plan_s {
   CUtensorMap tm_w;
   CUtensorMap tm_x[2];
   const void* tm_x_ptr[2];
+  CUtensorMap tm_y;
+  const void* tm_y_ptr;
   mpg::IgemmParams ip;
   size_t smem_bytes;
   int grid;
@@ -160,7 +162,15 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
   // Ring depths: one B stage only carries 2*CK/16 MMAs (~0.1-0.35 us of tensor work) but a TMA
   // round trip is ~1 us, so small weight tiles need a deep ring; A stages carry ks times more work.
-  const int budget = 200 * 1024;
+  // TMA-store epilogue staging (16-bit outputs): two accumulators x [128 px][out_cstride] 16-bit
+  // measured on B200: the direct 16-byte st.global epilogue beats the staged TMA store (2 extra
+  // block barriers per tile), so the TMA-store epilogue is opt-in (MPG_IGEMM_TMASTORE=1)
+  ip.tma_store = 0;
+  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32) ? 1 : 0;
+  ip.box_c = (d.out_cstride % 64 == 0) ? 64 : (d.out_cstride % 32 == 0) ? 32 : (d.out_cstride % 16 == 0) ? 16 : 8;
+  ip.nbox = d.out_cstride / ip.box_c;
+  ip.stage_bytes = ip.tma_store ? round_up(128 * d.out_cstride * 2, 1024) : 0;
+  const int budget = 210 * 1024 - 2 * ip.stage_bytes;
   int nb = (96 * 1024) / ip.b_stage_bytes;
   nb = nb > kIgMaxStagesB ? kIgMaxStagesB : (nb < 4 ? 4 : nb);
   if (ip.bgroup && nb > 4) nb = 4;
@@ -170,7 +180,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   na = na > kIgMaxStagesA ? kIgMaxStagesA : (na < 2 ? 2 : na);
   if (const char* e = getenv("MPG_IGEMM_NA")) na = atoi(e);
   if (nb < 1 || nb > kIgMaxStagesB || na < 1 || na > kIgMaxStagesA ||
-      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes > 220 * 1024) {
+      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + 2 * ip.stage_bytes > 224 * 1024) {
     set_error("conv: bad pipeline depth na=%d nb=%d", na, nb);
     return MPG_EINVAL;
   }
@@ -181,7 +191,8 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
   ip.tmem_cols = cols;
   ip.shift = p->d_shift;
-  p->smem_bytes = static_cast<size_t>(ip.na) * ip.a_stage_bytes + static_cast<size_t>(ip.nb) * ip.b_stage_bytes + 1024;
+  ip.stage_off = ip.na * ip.a_stage_bytes + ip.nb * ip.b_stage_bytes;
+  p->smem_bytes = static_cast<size_t>(ip.stage_off) + 2 * static_cast<size_t>(ip.stage_bytes) + 1024;
   p->grid = ip.num_tiles < p->h->sm_count ? ip.num_tiles : p->h->sm_count;
   int r = igemm_set_smem_attr(ck, p->smem_bytes);
   if (r) {
@@ -190,6 +201,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     return r;
   }
   p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
+  p->tm_y_ptr = nullptr;
   return 0;
 }
 
@@ -329,8 +341,33 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
     mpg::IgemmParams ip = p->ip;
     ip.out = y;
-    int r = mpg::igemm_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w, ip, p->grid,
-                              p->smem_bytes, st);
+    if (ip.tma_store && p->tm_y_ptr != y) {
+      const CUtensorMapDataType dt = d.out_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      const CUtensorMapSwizzle sw = ip.box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : ip.box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                    : ip.box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+      const uint64_t cs = static_cast<uint64_t>(d.out_cstride) * 2;
+      int r;
+      if (d.upsample == 1) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(d.out_cstride), static_cast<uint64_t>(d.w),
+                                  static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+        const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+        const uint32_t box[4] = {static_cast<uint32_t>(ip.box_c), mpg::kIgTileW, 8u, 1u};
+        r = mpg::encode_tmap(p->h, &p->tm_y, dt, 4, y, dims, strides, box, sw);
+      } else {
+        // [N, H, 2, W, 2*cstride] view of the [N, 2H, 2W, cstride] output: each pixel is stored 4 times
+        const uint64_t ow = 2ull * d.w;
+        const uint64_t dims[5] = {2ull * d.out_cstride, static_cast<uint64_t>(d.w), 2ull, static_cast<uint64_t>(d.h),
+                                  static_cast<uint64_t>(d.n)};
+        const uint64_t strides[4] = {2 * cs, ow * cs, 2 * ow * cs, 2ull * d.h * ow * cs};
+        const uint32_t box[5] = {static_cast<uint32_t>(ip.box_c), mpg::kIgTileW, 1u, 8u, 1u};
+        r = mpg::encode_tmap(p->h, &p->tm_y, dt, 5, y, dims, strides, box, sw);
+      }
+      if (r) return r;
+      p->tm_y_ptr = y;
+    }
+    int r = mpg::igemm_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w,
+                              ip.tma_store ? p->tm_y : p->tm_w, ip, p->grid, p->smem_bytes, st);
     if (r) {
       mpg::set_error("conv igemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
       return r;
