@@ -124,10 +124,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           const int pad = ks >> 1;
           const uint32_t bytes = static_cast<uint32_t>((kIgTileH + ks - 1) * kIgTileW * RB);
           const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
+          const uint32_t hbytes = static_cast<uint32_t>((kIgTileH + ks - 1) * (kIgTileW + ks - 1) * RB);
           for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
-            for (int dx = 0; dx < ks; ++dx) {
+            for (int dx = 0; dx < (p.halo ? 1 : ks); ++dx) {
               mbar_wait(&empty_a[st], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_a[st], bytes);
+              mbar_arrive_expect_tx(&full_a[st], p.halo ? hbytes : bytes);
               tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK,
                           tc.x0 + dx - pad, tc.y0 - pad, tc.n);
               if (++st == p.na) {
@@ -186,27 +187,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       for (int s = 0; s < p.nseg; ++s) {
         const int ks = p.seg_ks[s];
         const int gb = p.bgroup ? ks : 1;
+        const int pw = kIgTileW + ks - 1;  // halo image pitch in pixels (halo mode)
         for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
           for (int dx = 0; dx < ks; ++dx) {
-            mbar_wait(&full_a[sa], pa);
-            tc_fence_after();
-            const uint32_t a_lo = ((smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+            if (!p.halo || dx == 0) {
+              mbar_wait(&full_a[sa], pa);
+              tc_fence_after();
+            }
+            const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes);
+            const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | DESC_LO;
             for (int dy0 = 0; dy0 < ks; dy0 += gb) {
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
               const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(sb) * p.b_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
               if (elect_one()) {
                 for (int g = 0; g < gb; ++g) {
-                  const uint32_t ag = a_lo + static_cast<uint32_t>(((dy0 + g) * kIgTileW * RB) >> 4);
                   const uint32_t bg = b_lo + static_cast<uint32_t>((g * p.b_tile_bytes) >> 4);
+                  if (!p.halo) {
+                    const uint32_t ag = a_lo + static_cast<uint32_t>(((dy0 + g) * kIgTileW * RB) >> 4);
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) {
-                    const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
-                    const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
-                    const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
-                    if (!(p.dbg & 4)) {
-                      umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                      umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
+                      const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
+                      const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
+                      if (!(p.dbg & 4)) {
+                        umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                        umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                      }
+                    }
+                  } else {
+                    // 16 image rows x 8 px per accumulator: group stride = one halo row; the start is
+                    // shifted by whole pixels, i.e. NOT aligned to the swizzle atom
+                    const uint32_t off0 = static_cast<uint32_t>(((dy0 + g) * pw + dx) * RB);
+                    const uint32_t off1 = off0 + 8u * RB;
+                    const uint32_t hi = ((static_cast<uint32_t>(pw) * RB) >> 4) | (1u << 14) | (LAYOUT << 29);
+                    uint32_t hi0 = hi, hi1 = hi;
+                    if (p.halo_bo) {  // base_offset = (start >> 7) & 7, descriptor bits [49,52)
+                      hi0 |= (((a_addr + off0) >> 7) & 7u) << 17;
+                      hi1 |= (((a_addr + off1) >> 7) & 7u) << 17;
+                    }
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
+                      const uint64_t ad0 = (static_cast<uint64_t>(hi0) << 32) | (a_lo + (off0 >> 4) + k * 2);
+                      const uint64_t ad1 = (static_cast<uint64_t>(hi1) << 32) | (a_lo + (off1 >> 4) + k * 2);
+                      if (!(p.dbg & 4)) {
+                        umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                        umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                      }
                     }
                   }
                   accumulate = 1;
@@ -220,11 +248,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                 pb ^= 1u;
               }
             }
-            if (elect_one()) umma_commit(&empty_a[sa]);
-            __syncwarp();
-            if (++sa == p.na) {
-              sa = 0;
-              pa ^= 1u;
+            if (!p.halo || dx == ks - 1) {
+              if (elect_one()) umma_commit(&empty_a[sa]);
+              __syncwarp();
+              if (++sa == p.na) {
+                sa = 0;
+                pa ^= 1u;
+              }
             }
           }
         }
@@ -328,8 +358,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     // ===================== epilogue B (fp32 outputs): TMEM -> registers -> global ==============================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     const int m = ew * 32 + lane;
-    const int prow = m >> 4;
-    const int pcol = m & 15;
+    // accumulator row m -> pixel: 8 rows x 16 px (dx-image mode) or 16 rows x 8 px (halo mode)
+    const int prow = p.halo ? (m >> 3) : (m >> 4);
+    const int pcol = p.halo ? (m & 7) : (m & 15);
     const int ups = p.upsample;
     const int oh = p.h * ups, ow = p.w * ups;
     const float inv_c = 1.0f / static_cast<float>(p.cout);
@@ -341,8 +372,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       tc_fence_after();
 #pragma unroll 1
       for (int acc = 0; acc < 2; ++acc) {
-        const int y = tc.y0 + acc * 8 + prow;
-        const int x = tc.x0 + pcol;
+        const int y = tc.y0 + (p.halo ? 0 : acc * 8) + prow;
+        const int x = tc.x0 + (p.halo ? acc * 8 : 0) + pcol;
         const bool valid = (y < p.h) && (x < p.w) && !(p.dbg & 1);
         if (p.dbg & 2) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +

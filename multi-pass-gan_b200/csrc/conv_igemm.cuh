@@ -40,6 +40,9 @@ struct IgemmParams {
   int bgroup;        // 1: a B stage holds all ks dy-taps of a (chunk,dx) (same cadence as A); 0: one tap
   // TMA-store epilogue (16-bit outputs): rows are staged in smem as [box][128 px][box_c ch] (swizzled)
   int tma_store, box_c, nbox, stage_off, stage_bytes;
+  // halo mode: ONE TMA halo image [16+k-1][16+k-1][CK] per (segment, chunk); every (dy,dx) tap is a
+  // shifted UMMA descriptor into it (accumulator = 16 rows x 8 px). halo_bo: descriptor base_offset rule
+  int halo, halo_bo;
   int dbg;  // profiling only (env MPG_IGEMM_DBG): bit0 skip global stores, bit1 skip the TMEM loads too
   uint32_t tmem_cols;
   const float* shift;  // [npad] device

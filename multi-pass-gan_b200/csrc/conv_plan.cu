@@ -152,7 +152,11 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.in_dtype = d.in_dtype;
   ip.out_dtype = d.out_dtype;
   ip.out_cstride = d.out_cstride;
-  ip.a_stage_bytes = (kIgTileH + maxks - 1) * kIgTileW * rb;
+  ip.halo = 0;
+  if (const char* e = getenv("MPG_IGEMM_HALO")) ip.halo = atoi(e) ? 1 : 0;
+  ip.halo_bo = 0;
+  if (const char* e = getenv("MPG_IGEMM_HALO_BO")) ip.halo_bo = atoi(e) ? 1 : 0;
+  ip.a_stage_bytes = (kIgTileH + maxks - 1) * (ip.halo ? (kIgTileW + maxks - 1) : kIgTileW) * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
   ip.b_tile_bytes = round_up(npad * rb, 1024);
   // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: the MMA
@@ -166,7 +170,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   // measured on B200: the direct 16-byte st.global epilogue beats the staged TMA store (2 extra
   // block barriers per tile), so the TMA-store epilogue is opt-in (MPG_IGEMM_TMASTORE=1)
   ip.tma_store = 0;
-  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32 && !ip.halo) ? 1 : 0;
   ip.box_c = (d.out_cstride % 64 == 0) ? 64 : (d.out_cstride % 32 == 0) ? 32 : (d.out_cstride % 16 == 0) ? 16 : 8;
   ip.nbox = d.out_cstride / ip.box_c;
   ip.stage_bytes = ip.tma_store ? round_up(128 * d.out_cstride * 2, 1024) : 0;
@@ -330,7 +334,8 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
                                 static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
       const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
-      const uint32_t box[4] = {static_cast<uint32_t>(p->ck), mpg::kIgTileW,
+      const uint32_t box[4] = {static_cast<uint32_t>(p->ck),
+                               static_cast<uint32_t>(mpg::kIgTileW + (p->ip.halo ? d.seg_ksize[s] - 1 : 0)),
                                static_cast<uint32_t>(mpg::kIgTileH + d.seg_ksize[s] - 1), 1u};
       int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
                                box, swizzle_for(p->ck));

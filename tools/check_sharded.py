@@ -1,0 +1,36 @@
+"""torchrun --nproc-per-node G tools/check_sharded.py : slice-sharded MultiPass4x (NCCL all-to-all between
+passes) must reproduce the single-GPU volume bit for bit."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import mpgan_b200  # noqa: F401
+from mpgan_b200 import parallel as par, pipeline as P, synth
+
+rank, local, world = par.init_from_env()
+torch.cuda.set_device(local)
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+x = synth.synthetic_volume(L, seed=5)
+w1, w2 = P.make_weights_4x(L, 5, randomize_bn=True)
+single = P.MultiPass4x(L, w1, w2, precision="fp16", device=local)(x).clone()
+mp = P.MultiPass4x(L, w1, w2, precision="fp16", device=local, rank=rank, world=world)
+part = mp(x)
+torch.cuda.synchronize()
+ref = single[mp.s0:mp.s1]
+same = bool(torch.equal(part, ref))
+maxd = float((part - ref).abs().max())
+flag = torch.tensor([1 if same else 0], device="cuda")
+if world > 1:
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+print("rank %d/%d slab [%d,%d): bit-exact=%s max|d|=%.3e  nonzero=%.3f" % (rank, world, mp.s0, mp.s1, same, maxd,
+                                                                        float((part != 0).float().mean())))
+if rank == 0:
+    print("SHARDED_OK" if int(flag.item()) == 1 else "SHARDED_MISMATCH")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
