@@ -146,7 +146,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       int st = 0;
       uint32_t ph = 0;
       const uint32_t tile_bytes = static_cast<uint32_t>(p.npad * RB);
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      if (p.bres) {
+        // resident weights: every k-tile is loaded once per CTA and stays in shared memory
+        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+        for (int kt = 0; kt < p.ktiles; ++kt)
+          tma_load_2d(smB + static_cast<size_t>(kt) * p.b_tile_bytes, &tm_w, &full_b[0], 0, kt * p.npad);
+      }
+      for (int t = blockIdx.x; t < p.num_tiles && !p.bres; t += gridDim.x) {
         int kt = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
@@ -177,6 +183,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
+    if (p.bres) mbar_wait(&full_b[0], 0);
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
@@ -184,6 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       const uint32_t d0 = tmem_base + static_cast<uint32_t>((buf * 2) * p.npad);
       const uint32_t d1 = d0 + static_cast<uint32_t>(p.npad);
       uint32_t accumulate = 0;
+      int kt = 0;  // k-tile index (resident-weights mode)
       for (int s = 0; s < p.nseg; ++s) {
         const int ks = p.seg_ks[s];
         const int gb = p.bgroup ? ks : 1;
@@ -196,10 +204,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             }
             const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes);
             const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | DESC_LO;
-            for (int dy0 = 0; dy0 < ks; dy0 += gb) {
-              mbar_wait(&full_b[sb], pb);
-              tc_fence_after();
-              const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(sb) * p.b_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+            for (int dy0 = 0; dy0 < ks; dy0 += gb, kt += gb) {
+              if (!p.bres) {
+                mbar_wait(&full_b[sb], pb);
+                tc_fence_after();
+              }
+              const uint32_t b_lo = ((smem_u32(smB + (p.bres ? static_cast<size_t>(kt) * p.b_tile_bytes
+                                                               : static_cast<size_t>(sb) * p.b_stage_bytes)) & 0x3FFFFu) >> 4) | DESC_LO;
               if (elect_one()) {
                 for (int g = 0; g < gb; ++g) {
                   const uint32_t bg = b_lo + static_cast<uint32_t>((g * p.b_tile_bytes) >> 4);
@@ -239,11 +250,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                   }
                   accumulate = 1;
                 }
-                umma_commit(&empty_b[sb]);
+                if (!p.bres) umma_commit(&empty_b[sb]);
               }
               __syncwarp();
               accumulate = 1;
-              if (++sb == p.nb) {
+              if (!p.bres && ++sb == p.nb) {
                 sb = 0;
                 pb ^= 1u;
               }

@@ -43,6 +43,8 @@ struct IgemmParams {
   // halo mode: ONE TMA halo image [16+k-1][16+k-1][CK] per (segment, chunk); every (dy,dx) tap is a
   // shifted UMMA descriptor into it (accumulator = 16 rows x 8 px). halo_bo: descriptor base_offset rule
   int halo, halo_bo;
+  // resident weights: all `ktiles` weight tiles live in smem for the CTA's lifetime (thin layers)
+  int bres, ktiles;
   int dbg;  // profiling only (env MPG_IGEMM_DBG): bit0 skip global stores, bit1 skip the TMEM loads too
   uint32_t tmem_cols;
   const float* shift;  // [npad] device

@@ -84,7 +84,20 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   const mpg_conv_desc& d = p->d;
   int maxcin = 0;
   for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
-  const int ck = maxcin > 32 ? 64 : (maxcin > 16 ? 32 : 16);
+  // K-chunk (= swizzle span): zero-padded channels cost real MMAs, so take the chunk with the fewest
+  // K=16 steps summed over the segments, preferring the larger one unless a smaller saves >= 20 %
+  auto ksteps_for = [&](int c) {
+    int t = 0;
+    for (int s = 0; s < d.nseg; ++s) t += d.seg_ksize[s] * d.seg_ksize[s] * ceil_div(d.seg_cin[s], c) * (c / 16);
+    return t;
+  };
+  int ck = maxcin > 32 ? 64 : (maxcin > 16 ? 32 : 16);
+  for (int c = ck / 2; c >= 16; c /= 2)
+    if (ksteps_for(c) * 5 <= ksteps_for(ck) * 4) ck = c;
+  if (const char* e = getenv("MPG_IGEMM_CK")) {
+    const int c = atoi(e);
+    if (c == 16 || c == 32 || c == 64) ck = c;
+  }
   const int rb = ck * 2;
   const int npad = round_up(d.cout, 16);
   p->ck = ck;
@@ -152,52 +165,71 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.in_dtype = d.in_dtype;
   ip.out_dtype = d.out_dtype;
   ip.out_cstride = d.out_cstride;
-  ip.halo = 0;
+  // halo mode (one TMA halo image per (segment, chunk), taps = shifted descriptors) is the default
+  ip.halo = 1;
   if (const char* e = getenv("MPG_IGEMM_HALO")) ip.halo = atoi(e) ? 1 : 0;
   ip.halo_bo = 0;
-  if (const char* e = getenv("MPG_IGEMM_HALO_BO")) ip.halo_bo = atoi(e) ? 1 : 0;
+  ip.tma_store = 0;
+  // measured on B200: the direct 16-byte st.global epilogue beats the staged TMA store (2 extra
+  // block barriers per tile), so the TMA-store epilogue is opt-in (MPG_IGEMM_TMASTORE=1, dx-image mode)
+  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32) ? 1 : 0;
+  if (ip.tma_store) ip.halo = 0;
   ip.a_stage_bytes = (kIgTileH + maxks - 1) * (ip.halo ? (kIgTileW + maxks - 1) : kIgTileW) * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
   ip.b_tile_bytes = round_up(npad * rb, 1024);
+  ip.ktiles = ktiles;
+  // resident weights: thin layers keep every weight tile in shared memory for the CTA's lifetime, which
+  // removes the per-tile weight TMA round trips that bound them (measured: 0.18 of 0.22 ms was load skeleton)
+  ip.bres = (static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 64 * 1024) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_BRES")) ip.bres = (atoi(e) && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 160 * 1024) ? 1 : 0;
   // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: the MMA
   // thread then waits/commits once per 2*ks*CK/16 MMAs instead of once per 2*CK/16 (issue-latency bound)
   ip.bgroup = (maxks * ip.b_tile_bytes <= 40 * 1024) ? 1 : 0;
   if (const char* e = getenv("MPG_IGEMM_BGROUP")) ip.bgroup = atoi(e) ? 1 : 0;
   ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
-  // Ring depths: one B stage only carries 2*CK/16 MMAs (~0.1-0.35 us of tensor work) but a TMA
-  // round trip is ~1 us, so small weight tiles need a deep ring; A stages carry ks times more work.
-  // TMA-store epilogue staging (16-bit outputs): two accumulators x [128 px][out_cstride] 16-bit
-  // measured on B200: the direct 16-byte st.global epilogue beats the staged TMA store (2 extra
-  // block barriers per tile), so the TMA-store epilogue is opt-in (MPG_IGEMM_TMASTORE=1)
-  ip.tma_store = 0;
-  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32 && !ip.halo) ? 1 : 0;
   ip.box_c = (d.out_cstride % 64 == 0) ? 64 : (d.out_cstride % 32 == 0) ? 32 : (d.out_cstride % 16 == 0) ? 16 : 8;
   ip.nbox = d.out_cstride / ip.box_c;
   ip.stage_bytes = ip.tma_store ? round_up(128 * d.out_cstride * 2, 1024) : 0;
-  const int budget = 210 * 1024 - 2 * ip.stage_bytes;
-  int nb = (96 * 1024) / ip.b_stage_bytes;
-  nb = nb > kIgMaxStagesB ? kIgMaxStagesB : (nb < 4 ? 4 : nb);
-  if (ip.bgroup && nb > 4) nb = 4;
-  while (nb > 2 && nb * ip.b_stage_bytes + 2 * ip.a_stage_bytes > budget) --nb;
-  if (const char* e = getenv("MPG_IGEMM_NB")) nb = atoi(e);
-  int na = (budget - nb * ip.b_stage_bytes) / ip.a_stage_bytes;
-  na = na > kIgMaxStagesA ? kIgMaxStagesA : (na < 2 ? 2 : na);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
+  // CTAs per SM: thin layers are latency bound per tile (TMA round trips), not throughput bound, so two
+  // small CTAs per SM hide it (registers cap it at 2); wide layers keep one CTA with deep rings
+  const int b_res_bytes = ip.bres ? ktiles * ip.b_tile_bytes : 0;
+  int occ = 1;
+  if (cols <= 256 && (ip.bres ? b_res_bytes : 3 * ip.b_stage_bytes) + 2 * ip.a_stage_bytes <= 100 * 1024) occ = 2;
+  if (const char* e = getenv("MPG_IGEMM_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
+  const int budget = (210 * 1024) / occ - 2 * ip.stage_bytes - (occ > 1 ? 2048 : 0);
+  int nb, na;
+  if (ip.bres) {
+    nb = 1;
+    ip.b_stage_bytes = b_res_bytes;
+  } else {
+    // Ring depths: one B stage only carries 2*CK/16 MMAs (~0.1-0.35 us of tensor work) but a TMA
+    // round trip is ~1 us, so small weight tiles need a deep ring; A stages carry ks times more work.
+    nb = (96 * 1024 / occ) / ip.b_stage_bytes;
+    nb = nb > kIgMaxStagesB ? kIgMaxStagesB : (nb < 4 ? 4 : nb);
+    if (ip.bgroup && nb > 4) nb = 4;
+    while (nb > 2 && nb * ip.b_stage_bytes + 2 * ip.a_stage_bytes > budget) --nb;
+    if (const char* e = getenv("MPG_IGEMM_NB")) nb = atoi(e);
+  }
+  na = (budget - nb * ip.b_stage_bytes) / ip.a_stage_bytes;
+  na = na > kIgMaxStagesA ? kIgMaxStagesA : na;
   if (const char* e = getenv("MPG_IGEMM_NA")) na = atoi(e);
-  if (nb < 1 || nb > kIgMaxStagesB || na < 1 || na > kIgMaxStagesA ||
-      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + 2 * ip.stage_bytes > 224 * 1024) {
-    set_error("conv: bad pipeline depth na=%d nb=%d", na, nb);
+  if (nb < 1 || nb > kIgMaxStagesB || na < 2 || na > kIgMaxStagesA ||
+      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + 2 * ip.stage_bytes > 224 * 1024 ||
+      cols * static_cast<uint32_t>(occ) > 512u) {
+    set_error("conv: bad pipeline depth na=%d nb=%d occ=%d (a_stage %d B, b_stage %d B)", na, nb, occ, ip.a_stage_bytes,
+              ip.b_stage_bytes);
     return MPG_EINVAL;
   }
   ip.nb = nb;
   ip.na = na;
   if (const char* e = getenv("MPG_IGEMM_DBG")) ip.dbg = atoi(e);
-  uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
   ip.tmem_cols = cols;
   ip.shift = p->d_shift;
   ip.stage_off = ip.na * ip.a_stage_bytes + ip.nb * ip.b_stage_bytes;
   p->smem_bytes = static_cast<size_t>(ip.stage_off) + 2 * static_cast<size_t>(ip.stage_bytes) + 1024;
-  p->grid = ip.num_tiles < p->h->sm_count ? ip.num_tiles : p->h->sm_count;
+  p->grid = ip.num_tiles < p->h->sm_count * occ ? ip.num_tiles : p->h->sm_count * occ;
   int r = igemm_set_smem_attr(ck, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes,

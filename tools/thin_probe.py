@@ -1,0 +1,90 @@
+"""Which stage bounds each conv of the 4x generator?  Times every layer shape of gen_resnet (8x512x512) under
+pipeline-knob / knock-out settings of the igemm kernel (env is read at plan creation).
+python tools/thin_probe.py [config ...]   -> gpurun_out/thin_probe.json"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+
+import mpgan_b200  # noqa: F401
+from mpgan_b200 import capi
+
+SHAPES = [
+    ("cA0 4->8", dict(cins=[4], ks=[5], cout=8)),
+    ("cB0+s0 8/4->32", dict(cins=[8, 4], ks=[5, 1], cout=32)),
+    ("cA1 32->128", dict(cins=[32], ks=[5], cout=128)),
+    ("cB1+s1 128/32->128", dict(cins=[128, 32], ks=[5, 1], cout=128)),
+    ("cA2 128->32", dict(cins=[128], ks=[5], cout=32)),
+    ("cB2+s2 32/128->8", dict(cins=[32, 128], ks=[5, 1], cout=8)),
+    ("cA3 8->2", dict(cins=[8], ks=[5], cout=2)),
+    ("cB3+s3 2/8->1 f32", dict(cins=[2, 8], ks=[5, 1], cout=1, f32out=True)),
+]
+CONFIGS = {
+    "default": {},
+    "old": {"MPG_IGEMM_OCC": "1", "MPG_IGEMM_HALO": "0", "MPG_IGEMM_BRES": "0"},
+    "nobres": {"MPG_IGEMM_BRES": "0"},
+    "occ1": {"MPG_IGEMM_OCC": "1"},
+    "nohalo": {"MPG_IGEMM_HALO": "0"},
+    "nostore": {"MPG_IGEMM_DBG": "1"},
+    "noepi": {"MPG_IGEMM_DBG": "3"},
+    "nomma": {"MPG_IGEMM_DBG": "4"},
+    "nomma_noepi": {"MPG_IGEMM_DBG": "7"},
+}
+KEYS = sorted({k for c in CONFIGS.values() for k in c})
+
+
+def time_shape(sh, iters=5):
+    n, h, w = 8, 512, 512
+    rng = np.random.default_rng(0)
+    ws = [(rng.standard_normal((k, k, c, sh["cout"])) * np.sqrt(2.0 / (k * k * c))).astype(np.float32)
+          for k, c in zip(sh["ks"], sh["cins"])]
+    cs = [-(-c // 8) * 8 for c in sh["cins"]]
+    f32 = sh.get("f32out", False)
+    oc = sh["cout"] if f32 else -(-sh["cout"] // 8) * 8
+    plan = capi.ConvPlan(capi.default_handle(0), n, h, w, ws, cs, sh["cout"], oc, act="relu", in_dtype=capi.F16,
+                         out_dtype=capi.F32 if f32 else capi.F16)
+    xs = [torch.randn(n, h, w, c, device="cuda").to(torch.float16) for c in cs]
+    y = torch.empty(n, h, w, oc, dtype=torch.float32 if f32 else torch.float16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        plan.run(xs[0], xs[1] if len(xs) > 1 else None, y, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        plan.run(xs[0], xs[1] if len(xs) > 1 else None, y, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fl = plan.flops
+    plan.close()
+    return ms, fl
+
+
+def main():
+    which = sys.argv[1:] or list(CONFIGS)
+    res = {}
+    for cname in which:
+        for k in KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(CONFIGS[cname])
+        row = {}
+        for name, sh in SHAPES:
+            try:
+                ms, fl = time_shape(sh)
+                row[name] = ms
+            except Exception as e:  # keep the table going
+                row[name] = None
+                print("  %s / %s: %r" % (cname, name, e))
+        res[cname] = row
+        print("%-12s " % cname + "  ".join("%s=%.3f" % (k.split()[0], v) if v is not None else "%s=ERR" % k.split()[0]
+                                            for k, v in row.items()), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/thin_probe.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
