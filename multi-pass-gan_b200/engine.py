@@ -81,6 +81,7 @@ class CompiledNet:
         self.act_dtype = {"bf16": capi.BF16, "fp16": capi.F16, "fp32": capi.F32}[precision]
         self.steps = []  # (label, callable(stream))
         self.step_flops = {}
+        self.step_bufs = {}  # step index -> output Buf (debugging / per-layer parity)
         self.launches = 0
         self.flops = 0.0
         self.plans = []
@@ -371,6 +372,7 @@ class CompiledNet:
         if self.verbose:
             print(label)
         self.step_flops[len(self.steps)] = flops
+        self.step_bufs[len(self.steps)] = out
         self.steps.append((label, step))
         return View(oh, ow, [(out, 0, cout, 1, 1)])
 

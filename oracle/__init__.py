@@ -5,8 +5,16 @@ path of maxwerhahn/Multi-pass-GAN.  Only tests/, __graft_entry__.smoke() and ben
 reference legs may import this package; the product path (multi-pass-gan_b200/) never does and fails
 loudly when its CUDA library is missing.
 
-PARITY UNPINNED: the reference has no tests, golden vectors or fixtures for this path
-and TensorFlow 1.x / Keras cannot be installed in this image, so the oracle restates the published op
-semantics and follows the reference call sites cited in every docstring.  Its own pins
-are the known-answer tests in tests/test_oracle_*.py and the committed vectors in tests/golden/.
+PARITY PINNING: the reference has no tests, golden vectors or fixtures for this path
+and TensorFlow 1.x / Keras cannot be installed in this image.  What IS pinned, by executing the
+reference's own Python here (tests/golden/make_golden.py -> tests/golden/*.npz, checked by
+tests/test_golden.py):
+  * the volume pipeline (generate3DUniForNewNetwork of multipassGAN-out.py / multipassGAN-4x.py, run
+    with stand-in row functions for `sess.run`): oracle/pipeline.py reproduces it bit-exactly;
+  * layer wiring, variable names/shapes, wscale constants, BN/bias/activation order and the cursor
+    quirks (the real tools_wscale/GAN.py class + growing_gen / gen_resnet / disc_binclass executed on a
+    numpy TF1 shim): the fp64 oracle reproduces those outputs to 1e-9.
+What stays UNPINNED (restated from the published TF semantics): the arithmetic of
+tf.nn.conv2d SAME, contrib batch_norm and resize_images (nearest / TF1 legacy bicubic) themselves -
+the shim and oracle/tf_ops.py are two independent restatements that agree, not TensorFlow output.
 """

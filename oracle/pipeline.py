@@ -5,7 +5,9 @@ Line-by-line numpy restatement of the per-frame volume pipelines of the referenc
   apply_4x_pass    GAN/multipassGAN-4x.py:1090-1169 (one generator pass, upsampling modes 1/2/3)
   two_pass_4x      GAN/example_run_output.py:6,8 (pass 1 mode 2 -> .uni -> pass 2 mode 1)
 The networks are injected as callables on flat rows exactly like `sess.run(sampler, feed_dict)`, so
-the axis / channel bookkeeping can be tested with identity "networks".  PARITY UNPINNED.
+the axis / channel bookkeeping can be tested with identity "networks".  PINNED bit-exactly against the
+reference's own generate3DUniForNewNetwork executed with stand-in networks (tests/golden/pipeline.npz,
+tests/test_golden.py).
 """
 import numpy as np
 import scipy.ndimage

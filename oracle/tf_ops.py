@@ -3,8 +3,9 @@
 CPU restatement of the TensorFlow-1.x / scipy op semantics the reference's generator hot path relies
 on.  TensorFlow and Keras are not installable in this image, so these functions
 restate the *published* op definitions and are anchored on the reference call sites cited per
-function.  PARITY UNPINNED: the reference ships no tests / golden vectors for this path (SURVEY §4);
-the pins are the known-answer tests in tests/test_oracle_ops.py.
+function.  OP ARITHMETIC UNPINNED against TensorFlow itself (not installable; the reference ships no vectors):
+the pins are the known-answer tests in tests/test_oracle_ops.py and the independent numpy restatement in
+tests/golden/tf1_numpy_shim.py that the reference's own layer code was executed on (tests/test_golden.py).
 
 All tensors are NHWC torch CPU tensors; `dtype` float32 restates what TF fp32 computes, float64 is
 the ground truth both the fp32 oracle and the CUDA path are measured against.

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN PYTHON.
+
+Run in the authoring container only (needs /root/reference; the GPU box and the tests never do):
+
+    python tests/golden/make_golden.py
+
+Nothing from the reference is copied into the repo: the function bodies are read from
+/root/reference at generation time (ast -> compile -> exec) and run on top of test doubles:
+
+  pipeline_*.npz   generate3DUniForNewNetwork of GAN/multipassGAN-out.py:390-618 and
+                   GAN/multipassGAN-4x.py:1090-1169 with `sess.run` replaced by the deterministic
+                   stand-in row functions of tests/golden/standin.py.  PINS the zoom / slice-axis
+                   permutation / velocity-channel swaps / adjacent-slice channels / slice batching /
+                   inter-pass transposes / threshold, i.e. SURVEY §8 rows a14-a18, against the real code
+                   (scipy.ndimage.zoom is the real library call).
+  net_*.npz        tools_wscale/GAN.py (the real class) + resBlock / growBlockGen / growing_gen /
+                   gen_resnet / disc_binclass of the scripts, executed eagerly on the numpy TF1 shim
+                   (tests/golden/tf1_numpy_shim.py).  PINS layer wiring, variable names and shapes,
+                   wscale constants, bias/BN/activation order and the cursor quirks (App. D) against the
+                   real code; the op arithmetic itself stays a restatement of TF semantics (TensorFlow
+                   cannot be installed here) - see the shim's docstring.
+"""
+import ast
+import importlib.util
+import json
+import math
+import os
+import sys
+import types
+import zlib
+
+import numpy as np
+import scipy.ndimage
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import standin  # noqa: E402
+import tf1_numpy_shim as tfs  # noqa: E402
+import mpgan_b200  # noqa: E402,F401
+from mpgan_b200 import synth, weights as W  # noqa: E402
+
+
+def ref_functions(path, names):
+    """Source of the named top-level functions of a reference script, compiled on its own."""
+    with open(path) as fh:
+        src = fh.read()
+    tree = ast.parse(src)
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in picked} == set(names), (path, names)
+    mod = ast.Module(body=picked, type_ignores=[])
+    return compile(mod, path, "exec")
+
+
+# =============================================================================== pipelines
+class _StubSess:
+    def __init__(self, fn_by_sampler, log):
+        self.fn, self.log = fn_by_sampler, log
+
+    def run(self, sampler, feed_dict=None, **kw):
+        xs = np.array(feed_dict["x"])
+        ys = np.array(feed_dict["y"]) if "y" in feed_dict else None
+        self.log.append((sampler, xs, ys))
+        return self.fn[sampler](xs, ys)
+
+
+class _Uni:
+    def __init__(self):
+        self.written = {}
+
+    def readUni(self, path):
+        return {"dimX": 0, "dimY": 0, "dimZ": 0}, None
+
+    def writeUni(self, path, head, data):
+        self.written[os.path.basename(path)] = (dict(head), np.array(data))
+
+
+def run_out_pipeline(x_vol, u, nets, transposeAxis, add_adj1):
+    """GAN/multipassGAN-out.py:390-618 on x_vol [L,L,L,4] with stand-in networks `nets` (subset of 1,2,3)."""
+    L = x_vol.shape[0]
+    S = L * u
+    code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-out.py"), ["generate3DUniForNewNetwork"])
+    log, uni = [], _Uni()
+    fns = {
+        "sampler": lambda xs, ys: standin.net_first(xs, L, u, 6 if add_adj1 else 4),
+        "sampler_2": lambda xs, ys: standin.net_refine(xs, ys, L, u, 2),
+        "sampler_3": lambda xs, ys: standin.net_refine(xs, ys, L, u, 3),
+    }
+    ns = dict(
+        np=np, scipy=scipy, time=__import__("time"), tf=types.SimpleNamespace(RunMetadata=lambda: None),
+        x_3d=np.array(x_vol, dtype=np.float32)[None], upRes=u, simSizeLow=L, simSizeHigh=S, tileSizeHigh=S,
+        n_inputChannels=4, n_input=L * L * 4, n_output=S * S, transposeAxis=transposeAxis,
+        add_adj_idcs1=add_adj1, add_adj_idcs2=False, add_adj_idcs3=False,
+        load_model_test_1=0 if 1 in nets else -1, load_model_test_2=0 if 2 in nets else -1,
+        load_model_test_3=0 if 3 in nets else -1,
+        load_model_no_1=0 if 1 in nets else -1, load_model_no_2=0 if 2 in nets else -1,
+        load_model_no_3=0 if 3 in nets else -1,
+        sess=_StubSess(fns, log), sampler="sampler", sampler_2="sampler_2", sampler_3="sampler_3",
+        x="x", y="y", percentage="percentage", train="train",
+        save_img_3d=lambda *a, **k: None, save_img=lambda *a, **k: None,
+        uniio=uni, packedSimPath="/nonexistent/", fromSim=1000, frame_min=0, generateUni=True,
+    )
+    exec(code, ns)
+    ns["generate3DUniForNewNetwork"](imageindex=0, outPath="/nonexistent/", head={"dimX": 0, "dimY": 0, "dimZ": 0})
+    (head, vol), = uni.written.values()
+    assert head["dimX"] == S and vol.shape == (S, S, S)
+    feeds = {}
+    for name in ("sampler", "sampler_2", "sampler_3"):
+        xs = [a for (s, a, b) in log if s == name]
+        if xs:
+            feeds[name + "_x"] = np.concatenate(xs, axis=0)
+    return vol.astype(np.float32), feeds
+
+
+def run_4x_pass(mode, u, x_3d, x_2=None):
+    """GAN/multipassGAN-4x.py:1090-1169, one frame, upsampleFirst=1, genUni=1."""
+    L = x_3d.shape[0]
+    S = L * u
+    code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-4x.py"), ["generate3DUniForNewNetwork"])
+    log, uni = [], _Uni()
+    fn = (lambda xs, ys: standin.net_first(xs, L, u, 4)) if mode == 2 else (lambda xs, ys: standin.net_fullres(xs, S))
+    ns = dict(
+        np=np, scipy=scipy, time=__import__("time"), upsampling_mode=mode, upsampleFirst=1, upRes=u,
+        x_3d=np.array(x_3d, dtype=np.float32)[None], x_2=None if x_2 is None else np.array(x_2, np.float32)[None],
+        simSizeLow=L, simSizeHigh=S, n_inputChannels=4, n_input=(L * L if mode == 2 else S * S) * 4,
+        sess=_StubSess({"sampler": fn}, log), sampler="sampler", x="x", keep_prob="keep_prob", dropoutOutput=1.0,
+        train="train", save_img_3d=lambda *a, **k: None, uniio=uni, packedSimPath="/nonexistent/", fromSim=1000,
+        frame_min=0, generateUni=True, test_path="/nonexistent/",
+    )
+    exec(code, ns)
+    ns["generate3DUniForNewNetwork"](imageindex=0, outPath="/nonexistent/")
+    (head, vol), = uni.written.values()
+    feeds = np.concatenate([a for (s, a, b) in log], axis=0)
+    return vol.astype(np.float32), feeds
+
+
+def make_pipeline_fixtures():
+    out = {}
+    L, u = 4, 4  # S = 16: 16 slices -> two batches of 8 (net 1) / eight batches of 2 (nets 2, 3)
+    x = synth.synthetic_volume(L, seed=21)
+    for ta, nets, adj in ((0, (1, 2), True), (0, (1, 2, 3), True), (1, (1, 2, 3), False), (3, (1, 2), True),
+                          (2, (1,), True), (0, (1,), False)):
+        vol, feeds = run_out_pipeline(x, u, nets, ta, adj)
+        key = "out_ta%d_n%s_adj%d" % (ta, "".join(map(str, nets)), int(adj))
+        out[key + "_vol"] = vol
+        for k, v in feeds.items():
+            out[key + "_" + k] = v.astype(np.float32)
+    # 4x: pass 1 (mode 2) -> thresholded volume -> pass 2 (mode 1) and the mode-3 variant
+    p1, f1 = run_4x_pass(2, u, x)
+    vel = x[..., 1:4] * u  # GAN/multipassGAN-4x.py:277-278 (velScale 1.0)
+    p2, f2 = run_4x_pass(1, u, vel, x_2=p1[..., None])
+    p3, f3 = run_4x_pass(3, u, vel, x_2=p1[..., None])
+    out.update({"x": x, "L": L, "u": u, "x4_p1_vol": p1, "x4_p1_feed": f1, "x4_p2_vol": p2, "x4_p2_feed": f2,
+                "x4_p3_vol": p3, "x4_p3_feed": f3})
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+    print("pipeline.npz:", sorted(out))
+
+
+# =============================================================================== networks
+def load_ref_gan():
+    """Import the REAL tools_wscale/GAN.py with `tensorflow` / `keras` resolved to the numpy shim."""
+    sys.modules["tensorflow"] = tfs
+    keras = types.ModuleType("keras")
+    keras.backend = tfs.keras_backend
+    sys.modules["keras"] = keras
+    spec = importlib.util.spec_from_file_location("ref_GAN", os.path.join(REF, "tools_wscale", "GAN.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Provider(dict):
+    """Variable values keyed by the reference's full variable name, generated on first request with the
+    repo's deterministic initialiser (weights.py) + non-trivial BN statistics."""
+
+    def __init__(self, seed):
+        super().__init__()
+        self.seed = seed
+        self.kinds = {}
+
+    def __contains__(self, name):
+        return True
+
+    def __missing__(self, name):
+        raise KeyError(name)
+
+
+def _provide(seed):
+    store = {}
+
+    def get_variable(name, shape=None, initializer=None, dtype=None, trainable=True):
+        full = "/".join(tfs.STATE.scopes + [name])
+        shape = tuple(int(s) for s in shape)
+        tfs.STATE.requested[full] = shape
+        if full not in store:
+            if name in ("gamma", "beta", "moving_mean", "moving_variance"):
+                base = {"gamma": 1.0, "beta": 0.0, "moving_mean": 0.0, "moving_variance": 1.0}[name]
+                v = W.init_variable(seed, full, shape, ("const", base))
+                v = W.randomize_bn_stats({full: v}, seed)[full]
+            elif initializer[0] == "normal":
+                v = W.init_variable(seed, full, shape, "normal")
+            elif initializer[0] == "const":
+                v = W.init_variable(seed, full, shape, ("const", initializer[1]))
+            else:
+                raise NotImplementedError(initializer)
+            store[full] = v
+        assert store[full].shape == shape
+        return tfs.T(store[full])
+
+    return store, get_variable
+
+
+def _names_blob(requested):
+    return json.dumps([[k, list(v)] for k, v in requested.items()])
+
+
+def _wsum(store):
+    return float(sum(np.float64(zlib.crc32(np.ascontiguousarray(v).tobytes())) for v in store.values()))
+
+
+def make_net_fixtures():
+    ref_gan = load_ref_gan()
+    out_code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-out.py"), ["resBlock", "growBlockGen", "growing_gen"])
+    x4_code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-4x.py"), ["resBlock", "gen_resnet", "disc_binclass"])
+    fixtures = {}
+    rng = np.random.default_rng(5)
+
+    def run_out(tag, seed, L, u, firstGen, spec, pixel_norm=True, addBicubic=True, use_bn=False):
+        S = L * u
+        store, getv = _provide(seed)
+        tfs.reset({})
+        tfs.get_variable = getv
+        C = 4
+        ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, train=False, pixel_norm=pixel_norm,
+                  usePixelShuffle=False, upsampleMode=1, addBicubicUpsample=addBicubic, n_inputChannels=C,
+                  tileSizeLow=L, tileSizeHigh=S, n_output=S * S, rbId=0, print=lambda *a, **k: None)
+        exec(out_code, ns)
+        B = 2
+        cin = C + (2 if spec["add_adj_idcs"] else 0)
+        idx = spec["idx"]
+        x_rows = rng.random((B, L * L * (cin if firstGen else C)), dtype=np.float32)
+        y_rows = None
+        with tfs.variable_scope("gen_%d" % idx):
+            if firstGen:
+                _in = tfs.T(x_rows)
+            else:
+                # sampler wiring of GAN/multipassGAN-out.py:357 (module-level code, restated here)
+                y_rows = rng.random((B, S * S), dtype=np.float32)
+                lo = tfs.reshape(tfs.T(x_rows), [-1, L, L, C])
+                _in = tfs.concat((tfs.reshape(tfs.T(y_rows), [-1, S, S, 1]),
+                                  tfs.image.resize_images(lo, tfs.constant([S, S]), method=1)), axis=3)
+            res = ns["growing_gen"](_in, percentage=None, use_batch_norm=use_bn, reuse=tfs.AUTO_REUSE,
+                                    currentUpres=int(round(math.log(u, 2))), train=False, output=True,
+                                    firstGen=firstGen, filterSize=spec["filterSize"], startFms=spec["startFms"],
+                                    maxFms=spec["maxFms"], add_adj_idcs=spec["add_adj_idcs"],
+                                    first_nn_arch=spec["first_nn_arch"], use_res_net=spec["use_res_net"])
+        fixtures[tag + "_x"] = x_rows
+        if y_rows is not None:
+            fixtures[tag + "_y"] = y_rows
+        fixtures[tag + "_out"] = res.a
+        fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
+        fixtures[tag + "_wsum"] = _wsum(store)
+        fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, firstGen=firstGen, spec=spec, pixel_norm=pixel_norm,
+                                                 addBicubic=addBicubic))
+        print(tag, res.a.shape, "vars", len(tfs.STATE.requested), "|out| max", float(np.abs(res.a).max()))
+
+    run_out("out_net1", 31, 8, 4, True, dict(idx=1, use_res_net=True, add_adj_idcs=True, startFms=32, maxFms=32,
+                                             filterSize=3, first_nn_arch=True))
+    run_out("out_net1_u8", 32, 4, 8, True, dict(idx=1, use_res_net=True, add_adj_idcs=True, startFms=128, maxFms=64,
+                                                filterSize=3, first_nn_arch=True))
+    run_out("out_net2", 33, 4, 4, False, dict(idx=2, use_res_net=True, add_adj_idcs=False, startFms=64, maxFms=64,
+                                              filterSize=5, first_nn_arch=False))
+    run_out("out_net3", 34, 4, 4, False, dict(idx=3, use_res_net=False, add_adj_idcs=False, startFms=64, maxFms=32,
+                                              filterSize=5, first_nn_arch=False))
+
+    def run_4x(tag, seed, L, u, mode, use_bn=True):
+        S = L * u
+        store, getv = _provide(seed)
+        tfs.reset({})
+        tfs.get_variable = getv
+        ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, dataDimension=2, train=False, rbId=0,
+                  upsampling_mode=mode, tileSizeLow=L, tileSizeHigh=S, n_inputChannels=4, n_output=S * S,
+                  useAvgDepool=False, upRes=u, n_input=(L * L if mode == 2 else S * S) * 4, bn_decay=0.999,
+                  print=lambda *a, **k: None)
+        exec(x4_code, ns)
+        B = 2
+        n_in = ns["n_input"]
+        x_rows = (rng.random((B, n_in), dtype=np.float32) * np.tile([1, .5, .5, .5], n_in // 4)).astype(np.float32)
+        res = ns["gen_resnet"](tfs.T(x_rows), reuse=False, use_batch_norm=use_bn, train=False)
+        fixtures[tag + "_x"] = x_rows
+        fixtures[tag + "_out"] = res.a
+        fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
+        fixtures[tag + "_wsum"] = _wsum(store)
+        fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, mode=mode, batch_norm=use_bn))
+        print(tag, res.a.shape, "vars", len(tfs.STATE.requested), "|out| max", float(np.abs(res.a).max()))
+        if mode == 2:
+            # spatial discriminator on (x, G(x)) -- inference-mode BN (moving statistics)
+            tfs.STATE.requested = {}
+            g_rows = np.maximum(res.a, 0).astype(np.float32)
+            d = ns["disc_binclass"](tfs.T(x_rows), tfs.T(g_rows), reuse=False, use_batch_norm=use_bn, train=False)
+            fixtures[tag + "_disc_y"] = g_rows
+            fixtures[tag + "_disc_logits"] = d[0].a
+            for i in range(1, 5):
+                fixtures[tag + "_disc_d%d" % i] = d[i].a
+            fixtures[tag + "_disc_vars"] = _names_blob(tfs.STATE.requested)
+            fixtures[tag + "_disc_wsum"] = _wsum(store)
+            print(tag + "_disc", d[0].a.ravel(), [t.a.shape for t in d[1:]])
+
+    run_4x("x4_mode2", 41, 16, 4, 2)   # tile 16 -> 64: the training-tile shape, so the disc head is 8x8x256
+    run_4x("x4_mode1", 42, 4, 4, 1)
+    run_4x("x4_mode2_nobn", 43, 4, 4, 2, use_bn=False)
+    np.savez_compressed(os.path.join(HERE, "nets.npz"), **fixtures)
+    print("nets.npz written:", len(fixtures), "arrays")
+
+
+if __name__ == "__main__":
+    assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
+    make_pipeline_fixtures()
+    make_net_fixtures()
