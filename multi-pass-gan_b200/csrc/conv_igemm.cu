@@ -375,6 +375,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const int ups = p.upsample;
     const int oh = p.h * ups, ow = p.w * ups;
     const float inv_c = 1.0f / static_cast<float>(p.cout);
+    const bool st32 = (p.out_cstride % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && !(p.dbg & 8);
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -412,21 +413,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                 if (p.out_dtype != MPG_F32) {
                   const int od = p.out_dtype;
                   uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + c0;
-                  if (c0 + 8 <= p.out_cstride) {
-                    uint4 q;
-                    q.x = pack_h16x2(v[0], v[1], od);
-                    q.y = pack_h16x2(v[2], v[3], od);
-                    q.z = pack_h16x2(v[4], v[5], od);
-                    q.w = pack_h16x2(v[6], v[7], od);
-                    *reinterpret_cast<uint4*>(o) = q;
-                  }
-                  if (c0 + 16 <= p.out_cstride) {
-                    uint4 q;
-                    q.x = pack_h16x2(v[8], v[9], od);
-                    q.y = pack_h16x2(v[10], v[11], od);
-                    q.z = pack_h16x2(v[12], v[13], od);
-                    q.w = pack_h16x2(v[14], v[15], od);
-                    *reinterpret_cast<uint4*>(o + 8) = q;
+                  if (st32 && c0 + 16 <= p.out_cstride) {
+                    // one 32-byte store = one full L2 sector per lane (two 16-byte halves cost two partial writes)
+                    st_global_v8(o, pack_h16x2(v[0], v[1], od), pack_h16x2(v[2], v[3], od), pack_h16x2(v[4], v[5], od),
+                                 pack_h16x2(v[6], v[7], od), pack_h16x2(v[8], v[9], od), pack_h16x2(v[10], v[11], od),
+                                 pack_h16x2(v[12], v[13], od), pack_h16x2(v[14], v[15], od));
+                  } else {
+                    if (c0 + 8 <= p.out_cstride) {
+                      uint4 q;
+                      q.x = pack_h16x2(v[0], v[1], od);
+                      q.y = pack_h16x2(v[2], v[3], od);
+                      q.z = pack_h16x2(v[4], v[5], od);
+                      q.w = pack_h16x2(v[6], v[7], od);
+                      *reinterpret_cast<uint4*>(o) = q;
+                    }
+                    if (c0 + 16 <= p.out_cstride) {
+                      uint4 q;
+                      q.x = pack_h16x2(v[8], v[9], od);
+                      q.y = pack_h16x2(v[10], v[11], od);
+                      q.z = pack_h16x2(v[12], v[13], od);
+                      q.w = pack_h16x2(v[14], v[15], od);
+                      *reinterpret_cast<uint4*>(o + 8) = q;
+                    }
                   }
                 } else {
                   float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + c0;

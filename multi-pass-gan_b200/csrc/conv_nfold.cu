@@ -1,0 +1,304 @@
+// Tap-folded tcgen05 convolution for narrow Cout (design: conv_nfold.cuh).
+#include "conv_nfold.cuh"
+#include "ptx.cuh"
+
+namespace mpg {
+
+namespace {
+
+struct NfTile {
+  int n, y0, gx0, ox0;  // gx0: global x of lane 0 of the window; ox0: first output x of the tile
+};
+__device__ __forceinline__ NfTile nf_decode(int t, const NfoldParams& p) {
+  const int per_img = p.tiles_x * p.tiles_y;
+  NfTile c;
+  c.n = t / per_img;
+  const int r = t - c.n * per_img;
+  const int ty = r / p.tiles_x;
+  c.y0 = ty * p.rows;
+  c.ox0 = (r - ty * p.tiles_x) * p.valid_w;
+  c.gx0 = c.ox0 - (p.seg_ks[0] >> 1);
+  return c;
+}
+
+template <int CK, int KS>
+__global__ void __launch_bounds__(kNfThreads, 2)
+conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                  const __grid_constant__ CUtensorMap tm_w, const NfoldParams p) {
+  constexpr int RB = CK * 2;  // bytes per pixel of one K-chunk == swizzle span
+  constexpr uint32_t LAYOUT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
+  constexpr uint32_t SBO = 8u * RB;
+  constexpr int KSTEPS = CK / 16;
+  constexpr uint32_t ROW_BYTES = kNfWin * RB;  // one image row of the window in smem
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[kNfMaxStagesA], empty_a[kNfMaxStagesA];
+  __shared__ __align__(8) uint64_t full_b[kNfMaxStagesB], empty_b[kNfMaxStagesB];
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_shift[32];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + static_cast<size_t>(p.na) * p.a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x < 32) s_shift[threadIdx.x] = threadIdx.x < p.cp ? p.shift[threadIdx.x] : 0.0f;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x0);
+    if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
+    for (int i = 0; i < p.na; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+    }
+    for (int i = 0; i < kNfMaxStagesB; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== A producer: one window image per (segment, chunk) =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const NfTile tc = nf_decode(t, p);
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ks = p.seg_ks[s];
+          const uint32_t bytes = static_cast<uint32_t>(p.rows + ks - 1) * ROW_BYTES;
+          const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
+          for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+            mbar_wait(&empty_a[st], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_a[st], bytes);
+            tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, tc.gx0,
+                        tc.y0 - (ks >> 1), tc.n);
+            if (++st == p.na) {
+              st = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== B producer: weight tiles [Npad][CK] per (segment, chunk, dy) ============
+    if (lane == 0) {
+      // weight tiles live in global memory in their swizzled smem image: plain bulk copies (see ptx.cuh)
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
+      const uint32_t tile_bytes = static_cast<uint32_t>(p.b_tile_bytes);
+      if (p.bres) {
+        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+        bulk_load_1d(smB, wsrc, tile_bytes * static_cast<uint32_t>(p.ktiles), &full_b[0]);
+      } else {
+        int st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+          for (int kt = 0; kt < p.ktiles; ++kt) {
+            mbar_wait(&empty_b[st], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_b[st], tile_bytes);
+            bulk_load_1d(smB + static_cast<size_t>(st) * p.b_tile_bytes, wsrc + static_cast<size_t>(kt) * p.b_tile_bytes,
+                         tile_bytes, &full_b[st]);
+            if (++st == p.nb) {
+              st = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
+    constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t DESC_LO = 1u << 16;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    if (p.bres) {
+      mbar_wait(&full_b[0], 0);
+      tc_fence_after();
+    }
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it % p.nbuf;
+      const uint32_t use = static_cast<uint32_t>(it / p.nbuf);
+      mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * p.naccs * p.npad);
+      int kt = 0;
+      bool first = true;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int ks = p.seg_ks[s];
+        for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+          mbar_wait(&full_a[sa], pa);
+          tc_fence_after();
+          const uint32_t a_lo = ((smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+          for (int dy = 0; dy < ks; ++dy, ++kt) {
+            if (!p.bres) {
+              mbar_wait(&full_b[sb], pb);
+              tc_fence_after();
+            }
+            const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(p.bres ? kt : sb) * p.b_tile_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+            if (elect_one()) {
+              for (int acc = 0; acc < p.naccs; ++acc) {
+                const uint32_t ag = a_lo + ((static_cast<uint32_t>(acc * kNfRowsAcc + dy) * ROW_BYTES) >> 4);
+                const uint32_t d = dbase + static_cast<uint32_t>(acc * p.npad);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + k * 2);
+                  const uint64_t ad = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
+                  if (!(p.dbg & 4)) umma_bf16_ss(d, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              if (!p.bres) umma_commit(&empty_b[sb]);
+            }
+            __syncwarp();
+            first = false;
+            if (!p.bres && ++sb == p.nb) {
+              sb = 0;
+              pb ^= 1u;
+            }
+          }
+          if (elect_one()) umma_commit(&empty_a[sa]);
+          __syncwarp();
+          if (++sa == p.na) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+      }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: shifted sum over dx (warp shuffles) + shift + act + store ====
+    const int ew = warp & 3;  // TMEM lane quarter == image row within the accumulator
+    constexpr int pad0 = KS >> 1;
+    const bool lane_valid = (lane >= pad0) && (lane < kNfWin - pad0);
+    const float act_a = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.6f : 1.0f);
+    const float act_b = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.4f : 0.0f);
+    const float inv_c = 1.0f / static_cast<float>(p.cout);
+    const int nchunks = p.cp >> 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it % p.nbuf;
+      const uint32_t use = static_cast<uint32_t>(it / p.nbuf);
+      const NfTile tc = nf_decode(t, p);
+      mbar_wait(&tmem_full[buf], use & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int acc = 0; acc < p.naccs; ++acc) {
+        if (p.dbg & 2) continue;
+        const int y = tc.y0 + acc * kNfRowsAcc + ew;
+        const int gx = tc.gx0 + lane;
+        const bool valid = lane_valid && (y < p.h) && (gx < p.w) && !(p.dbg & 1);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                               static_cast<uint32_t>((buf * p.naccs + acc) * p.npad);
+        float o[32];
+        float ssq = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t r[KS][8];
+#pragma unroll
+            for (int dx = 0; dx < KS; ++dx) tmem_ld8(taddr + static_cast<uint32_t>(dx * p.cp + c * 8), r[dx]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float t[KS];
+#pragma unroll
+              for (int dx = 0; dx < KS; ++dx)  // independent shuffles: lane x takes column block dx of lane x+dx-pad
+                t[dx] = __shfl_sync(0xFFFFFFFFu, __uint_as_float(r[dx][j]), (lane + dx - pad0) & 31);
+              float a = t[0];
+#pragma unroll
+              for (int dx = 1; dx < KS; ++dx) a += t[dx];
+              const float x = a + s_shift[c * 8 + j];
+              const float v = fmaf(act_b, fabsf(x), act_a * x);
+              o[c * 8 + j] = v;
+              ssq = fmaf(v, v, ssq);
+            }
+          }
+        }
+        const float rn = p.pixel_norm ? rsqrtf(ssq * inv_c + 1e-8f) : 1.0f;  // tools_wscale/GAN.py:472-474
+        if (valid) {
+          const size_t pix = (static_cast<size_t>(tc.n) * p.h + y) * p.w + gx;
+          if (p.out_dtype != MPG_F32) {
+            const int od = p.out_dtype;
+            uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < nchunks) {
+                uint4 q;
+                q.x = pack_h16x2(o[c * 8 + 0] * rn, o[c * 8 + 1] * rn, od);
+                q.y = pack_h16x2(o[c * 8 + 2] * rn, o[c * 8 + 3] * rn, od);
+                q.z = pack_h16x2(o[c * 8 + 4] * rn, o[c * 8 + 5] * rn, od);
+                q.w = pack_h16x2(o[c * 8 + 6] * rn, o[c * 8 + 7] * rn, od);
+                *reinterpret_cast<uint4*>(op + c * 8) = q;
+              }
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_cstride;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < p.out_cstride) op[j] = (j < p.cout) ? o[j] * rn : 0.0f;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+typedef void (*NfKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const NfoldParams);
+
+static NfKernel nf_kernel(int ck, int ks) {
+  if (ks == 5) return ck == 64 ? conv_nfold_kernel<64, 5> : (ck == 32 ? conv_nfold_kernel<32, 5> : conv_nfold_kernel<16, 5>);
+  return ck == 64 ? conv_nfold_kernel<64, 3> : (ck == 32 ? conv_nfold_kernel<32, 3> : conv_nfold_kernel<16, 3>);
+}
+
+static size_t g_nf_smem_attr[6] = {0, 0, 0, 0, 0, 0};
+
+int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes) {
+  const int slot = (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3);
+  if (smem_bytes <= g_nf_smem_attr[slot]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(nf_kernel(ck, ks), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem_bytes));
+  if (e == cudaSuccess) g_nf_smem_attr[slot] = smem_bytes;
+  return static_cast<int>(e);
+}
+
+int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
+                 const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
+  nf_kernel(ck, p.seg_ks[0])<<<grid, kNfThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace mpg

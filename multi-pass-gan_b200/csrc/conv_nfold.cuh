@@ -1,0 +1,58 @@
+// Tap-folded implicit-GEMM convolution for NARROW output-channel counts (tcgen05 + TMEM + TMA).
+//
+// Why: an SS-mode tcgen05.mma spends >= 64 cycles streaming its 128 x 16 A block out of shared memory
+// whatever N is, so the tap-by-tap kernel (conv_igemm.cu: N = Cout) runs a Cout = 32 layer at 25 % and a
+// Cout = 8 layer at 6 % of the tensor pipe.  Here the k horizontal taps become extra GEMM columns:
+//
+//     P[y][x][dx*Cp + co] = sum_{dy,ci} X[y+dy-pad][x][ci] * W[dy][dx][ci][co]      (N = k*Cp per MMA)
+//     out[y][x][co]       = act( sum_dx P[y][x+dx-pad][dx*Cp + co] + shift[co] )    (epilogue)
+//
+// so one A block feeds k taps at once (5x fewer MMAs for a 5x5 conv).  The shifted sum over dx runs in the
+// epilogue: an accumulator holds 4 image rows x 32 pixels (lane = row*32 + x), each epilogue warp owns one
+// image row, and the +-pad pixel shifts are warp shuffles.  A 32-pixel window therefore yields 32-(k-1)
+// output pixels; neighbouring tiles overlap by k-1 columns.
+//   - A operand: per (segment, Cin chunk) ONE TMA box [R+k-1 rows][32 px][CK]; vertical taps = UMMA
+//     descriptor start advanced by whole image rows (swizzle-atom aligned).  Zero fill = SAME padding.
+//   - B operand: packed weights [k-tile=(seg,chunk,dy)][Npad][CK]; resident in smem when small.
+//   - optional 1x1 shortcut segment: extra K-slabs whose weight tile is non-zero only in the centre-dx
+//     column block.
+#pragma once
+#include "common.h"
+
+namespace mpg {
+
+constexpr int kNfWin = 32;      // pixels per image row held by an accumulator
+constexpr int kNfRowsAcc = 4;   // image rows per accumulator (4 * 32 = 128 MMA rows)
+constexpr int kNfThreads = 256;
+constexpr int kNfMaxStagesA = 4;
+constexpr int kNfMaxStagesB = 8;
+
+struct NfoldParams {
+  int n, h, w;
+  int tiles_x, tiles_y, num_tiles;
+  int valid_w;  // 32 - (ks0 - 1)
+  int rows;     // output rows per tile = naccs * 4
+  int naccs, nbuf;
+  int nseg;
+  int seg_ks[2];
+  int seg_nchunk[2];
+  int npad;  // UMMA N = round_up(ks0 * cp, 16)
+  int cp;    // cout rounded up to 8
+  int cout;
+  int act, pixel_norm;
+  int in_dtype, out_dtype, out_cstride;
+  int na, nb;
+  int a_stage_bytes, b_tile_bytes;
+  int bres, ktiles;
+  int dbg;  // profiling only (env MPG_NFOLD_DBG): bit0 skip stores, bit1 skip the whole epilogue body, bit2 skip MMAs
+  uint32_t tmem_cols;
+  const float* shift;  // [cp] device
+  const void* wpacked;  // device: weight tiles in their swizzled smem image, b_tile_bytes apart
+  void* out;
+};
+
+int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
+                 const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
+int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes);
+
+}  // namespace mpg

@@ -8,11 +8,13 @@
 #include "common.h"
 #include "conv_direct.cuh"
 #include "conv_igemm.cuh"
+#include "conv_nfold.cuh"
 
 struct mpg_conv_plan_s {
   mpg_handle h;
   mpg_conv_desc d;
-  int kind;  // 1 igemm, 2 direct
+  int kind;  // 1 igemm, 2 direct, 3 tap-folded igemm (narrow Cout)
+  mpg::NfoldParams np;
   double flops;
   int oh, ow;
   // ---- igemm
@@ -56,6 +58,16 @@ uint16_t f32_to_f16_rn(float f) {
 CUtensorMapSwizzle swizzle_for(int ck) {
   return ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                   : (ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// Element offset of (row n, K-element c) inside one weight tile stored as the SWIZZLED shared-memory image
+// the UMMA descriptor expects (rows of rb = 2*ck bytes; the TMA/UMMA swizzle XORs the 16-byte chunk index
+// with address bits [7,10) / [7,9) / [7,8) for 128 / 64 / 32-byte rows; tiles are 1024-byte aligned).
+size_t swz_elem(int n, int c, int ck) {
+  const int rb = ck * 2;
+  const int chunk = (c * 2) >> 4;
+  const int x = rb == 128 ? (n & 7) : (rb == 64 ? ((n >> 1) & 3) : ((n >> 2) & 1));
+  return (static_cast<size_t>(n) * rb + static_cast<size_t>((chunk ^ x) << 4) + ((c * 2) & 15)) / 2;
 }
 
 int same_pad_before(int in, int k, int s) {
@@ -109,7 +121,8 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     ktiles += p->seg_nchunk[s] * d.seg_ksize[s] * d.seg_ksize[s];
     maxks = d.seg_ksize[s] > maxks ? d.seg_ksize[s] : maxks;
   }
-  // ---- pack weights: [ktile][npad][ck] bf16, ktile order = (seg, chunk, dx, dy)
+  // ---- pack weights: [ktile][npad][ck] 16-bit, ktile order = (seg, chunk, dx, dy); loaded by tiled TMA (measured:
+  //      for the streamed 16 KB tiles of the wide layers the tiled path beats 1-D bulk copies, 1.02 vs 1.39 ms skeleton)
   std::vector<uint16_t> wp(static_cast<size_t>(ktiles) * npad * ck, 0);
   size_t kt = 0;
   for (int s = 0; s < d.nseg; ++s) {
@@ -134,15 +147,15 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
   MPG_CUDA(cudaMalloc(&p->d_shift, npad * sizeof(float)));
   MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
-
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ck), static_cast<uint64_t>(ktiles) * npad};
     const uint64_t strides[1] = {static_cast<uint64_t>(rb)};
     const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(npad)};
-    int r = encode_tmap(p->h, &p->tm_w, d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_wpacked, dims, strides,
-                        box, swizzle_for(ck));
+    int r = encode_tmap(p->h, &p->tm_w, d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        p->d_wpacked, dims, strides, box, swizzle_for(ck));
     if (r) return r;
   }
+
 
   IgemmParams& ip = p->ip;
   memset(&ip, 0, sizeof(ip));
@@ -230,6 +243,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.stage_off = ip.na * ip.a_stage_bytes + ip.nb * ip.b_stage_bytes;
   p->smem_bytes = static_cast<size_t>(ip.stage_off) + 2 * static_cast<size_t>(ip.stage_bytes) + 1024;
   p->grid = ip.num_tiles < p->h->sm_count * occ ? ip.num_tiles : p->h->sm_count * occ;
+  if (const char* e = getenv("MPG_IGEMM_GRID")) p->grid = atoi(e) > 0 ? atoi(e) : p->grid;
   int r = igemm_set_smem_attr(ck, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes,
@@ -238,6 +252,152 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   }
   p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
   p->tm_y_ptr = nullptr;
+  return 0;
+}
+
+bool nfold_eligible(const mpg_conv_desc& d) {
+  if (!igemm_eligible(d) || d.upsample != 1 || d.cout > 32 || d.act == MPG_ACT_TANH) return false;
+  if (d.seg_ksize[0] != 3 && d.seg_ksize[0] != 5) return false;
+  if (d.nseg == 2 && d.seg_ksize[1] != 1) return false;
+  const int cp = round_up(d.cout, 8);
+  if (d.out_dtype == MPG_F32 ? d.out_cstride > 32 : d.out_cstride != cp) return false;
+  return true;
+}
+
+// Tap-folded kernel (conv_nfold.cu): weights packed as [k-tile=(seg,chunk,dy)][Npad][CK] with row
+// n = dx*cp + co; the 1x1 shortcut segment only fills the centre-dx column block.
+int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  int maxcin = 0;
+  for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
+  auto ksteps_for = [&](int c) {
+    int t = 0;
+    for (int s = 0; s < d.nseg; ++s) t += d.seg_ksize[s] * ceil_div(d.seg_cin[s], c) * (c / 16);
+    return t;
+  };
+  int ck = maxcin > 32 ? 64 : (maxcin > 16 ? 32 : 16);
+  for (int c = ck / 2; c >= 16; c /= 2)
+    if (ksteps_for(c) * 5 <= ksteps_for(ck) * 4) ck = c;
+  if (const char* e = getenv("MPG_NFOLD_CK")) {
+    const int c = atoi(e);
+    if (c == 16 || c == 32 || c == 64) ck = c;
+  }
+  const int rb = ck * 2;
+  const int ks0 = d.seg_ksize[0], pad0 = ks0 / 2;
+  const int cp = round_up(d.cout, 8);
+  const int npad = round_up(ks0 * cp, 16);
+  p->ck = ck;
+  p->npad = npad;
+  int ktiles = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    p->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
+    ktiles += p->seg_nchunk[s] * d.seg_ksize[s];
+  }
+  const size_t tile_elems = static_cast<size_t>(round_up(npad * rb, 1024)) / 2;
+  std::vector<uint16_t> wp(static_cast<size_t>(ktiles) * tile_elems, 0);
+  size_t kt = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const int ks = d.seg_ksize[s], cin = d.seg_cin[s];
+    for (int ch = 0; ch < p->seg_nchunk[s]; ++ch)
+      for (int dy = 0; dy < ks; ++dy, ++kt)
+        for (int dx = 0; dx < ks; ++dx) {
+          const int col_dx = (ks == 1) ? pad0 : dx;  // shortcut: centre column block of the main segment
+          for (int n = 0; n < d.cout; ++n) {
+            const float sc = scale[s] ? scale[s][n] : 1.0f;
+            for (int c = 0; c < ck; ++c) {
+              const int ci = ch * ck + c;
+              if (ci >= cin) break;
+              const float v = w[s][((static_cast<size_t>(dy) * ks + dx) * cin + ci) * d.cout + n] * sc;
+              wp[kt * tile_elems + swz_elem(col_dx * cp + n, c, ck)] = d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v);
+            }
+          }
+        }
+  }
+  MPG_CUDA(cudaMalloc(&p->d_wpacked, wp.size() * 2));
+  MPG_CUDA(cudaMemcpy(p->d_wpacked, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> sh(32, 0.0f);
+  if (shift)
+    for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
+  MPG_CUDA(cudaMalloc(&p->d_shift, 32 * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), 32 * sizeof(float), cudaMemcpyHostToDevice));
+  NfoldParams& q = p->np;
+  memset(&q, 0, sizeof(q));
+  q.n = d.n;
+  q.h = d.h;
+  q.w = d.w;
+  q.valid_w = kNfWin - (ks0 - 1);
+  if (8 * npad <= 512) {
+    q.naccs = 4;
+    q.nbuf = 2;
+  } else if (4 * npad <= 512) {
+    q.naccs = 2;
+    q.nbuf = 2;
+  } else {
+    q.naccs = 512 / npad;
+    q.nbuf = 1;
+  }
+  if (const char* e = getenv("MPG_NFOLD_NACCS")) {
+    const int a = atoi(e);
+    if (a >= 1 && a * npad * q.nbuf <= 512) q.naccs = a;
+  }
+  q.rows = q.naccs * kNfRowsAcc;
+  q.tiles_x = ceil_div(d.w, q.valid_w);
+  q.tiles_y = ceil_div(d.h, q.rows);
+  q.num_tiles = q.tiles_x * q.tiles_y * d.n;
+  q.nseg = d.nseg;
+  for (int s = 0; s < d.nseg; ++s) {
+    q.seg_ks[s] = d.seg_ksize[s];
+    q.seg_nchunk[s] = p->seg_nchunk[s];
+  }
+  q.npad = npad;
+  q.cp = cp;
+  q.cout = d.cout;
+  q.act = d.act;
+  q.pixel_norm = d.pixel_norm;
+  q.in_dtype = d.in_dtype;
+  q.out_dtype = d.out_dtype;
+  q.out_cstride = d.out_cstride;
+  q.a_stage_bytes = (q.rows + ks0 - 1) * kNfWin * rb;
+  q.b_tile_bytes = round_up(npad * rb, 1024);
+  q.ktiles = ktiles;
+  q.bres = (static_cast<size_t>(ktiles) * q.b_tile_bytes <= 64 * 1024) ? 1 : 0;
+  if (const char* e = getenv("MPG_NFOLD_BRES")) q.bres = (atoi(e) && static_cast<size_t>(ktiles) * q.b_tile_bytes <= 128 * 1024) ? 1 : 0;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(q.nbuf * q.naccs * npad)) cols <<= 1;
+  q.tmem_cols = cols;
+  const int b_bytes_min = q.bres ? ktiles * q.b_tile_bytes : 3 * q.b_tile_bytes;
+  int occ = (cols <= 256 && b_bytes_min + 2 * q.a_stage_bytes <= 100 * 1024) ? 2 : 1;
+  if (const char* e = getenv("MPG_NFOLD_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
+  const int budget = (210 * 1024) / occ - (occ > 1 ? 2048 : 0);
+  int nb;
+  if (q.bres) {
+    nb = ktiles;
+  } else {
+    nb = (budget - 2 * q.a_stage_bytes) / q.b_tile_bytes;
+    nb = nb > kNfMaxStagesB ? kNfMaxStagesB : nb;
+    if (nb > 4 && (budget - nb * q.b_tile_bytes) / q.a_stage_bytes < 3) nb = 4;
+  }
+  int na = (budget - nb * q.b_tile_bytes) / q.a_stage_bytes;
+  na = na > kNfMaxStagesA ? kNfMaxStagesA : na;
+  if (nb < 1 || na < 2 || cols * static_cast<uint32_t>(occ) > 512u) {
+    set_error("conv(nfold): bad pipeline depth na=%d nb=%d occ=%d (a_stage %d B, b_tile %d B)", na, nb, occ,
+              q.a_stage_bytes, q.b_tile_bytes);
+    return MPG_EINVAL;
+  }
+  q.na = na;
+  q.nb = q.bres ? 1 : nb;
+  q.shift = p->d_shift;
+  q.wpacked = p->d_wpacked;
+  if (const char* e = getenv("MPG_NFOLD_DBG")) q.dbg = atoi(e);
+  p->smem_bytes = static_cast<size_t>(na) * q.a_stage_bytes + static_cast<size_t>(nb) * q.b_tile_bytes + 1024;
+  p->grid = q.num_tiles < p->h->sm_count * occ ? q.num_tiles : p->h->sm_count * occ;
+  int r = nfold_set_smem_attr(ck, ks0, p->smem_bytes);
+  if (r) {
+    set_error("cudaFuncSetAttribute(nfold, max dynamic smem %zu) failed: %s", p->smem_bytes,
+              cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
   return 0;
 }
 
@@ -323,12 +483,24 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     // Cin <= 16 is 25 K=16 MMAs per 128 pixels, far cheaper than the CUDA-core loop (TMA zero-fills
     // the missing channels, the weights of padded output channels are zero).
     kind = elig ? 1 : 2;
+    // narrow Cout: fold the horizontal taps into the GEMM N dimension (conv_nfold.cu)
+    // (pays off when the folded N stays small, or when K is deep enough that the 5x fewer MMAs outweigh the
+    //  un-overlapped epilogue of the N=160 single-buffered configuration; measured: tools/thin_probe.py)
+    int cin_total = 0;
+    for (int s = 0; s < d.nseg; ++s) cin_total += d.seg_cin[s];
+    bool nf = nfold_eligible(d) && (round_up(d.cout, 8) * d.seg_ksize[0] <= 64 || cin_total >= 64);
+    if (const char* e = getenv("MPG_CONV_NFOLD")) nf = nf && atoi(e) != 0;
+    if (kind == 1 && nf) kind = 3;
+  }
+  if (kind == 3 && !nfold_eligible(d)) {
+    mpg::set_error("conv: tap-folded path needs the tcgen05 constraints plus cout <= 32, k0 in {3,5}, 1x1 shortcut, no upsample");
+    return MPG_ENOSUP;
   }
   if (kind == 1 && !elig) {
     mpg::set_error("conv: tcgen05 path needs bf16/f16 input (same 16-bit output type or f32), stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
     return MPG_ENOSUP;
   }
-  MPG_CHECK_ARG(kind == 1 || kind == 2, "conv: bad force_kind %d", d.force_kind);
+  MPG_CHECK_ARG(kind >= 1 && kind <= 3, "conv: bad force_kind %d", d.force_kind);
 
   mpg_conv_plan p = new mpg_conv_plan_s();
   memset(p, 0, sizeof(*p));
@@ -343,7 +515,7 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   const float* w[2] = {w_seg0, w_seg1};
   const float* sc[2] = {scale_seg0, scale_seg1};
   MPG_CUDA(cudaSetDevice(h->device));
-  int r = (kind == 1) ? build_igemm(p, w, sc, shift) : build_direct(p, w, sc, shift);
+  int r = (kind == 1) ? build_igemm(p, w, sc, shift) : (kind == 3 ? build_nfold(p, w, sc, shift) : build_direct(p, w, sc, shift));
   if (r) {
     mpg_conv_plan_destroy(p);
     return r;
@@ -407,6 +579,34 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
                               ip.tma_store ? p->tm_y : p->tm_w, ip, p->grid, p->smem_bytes, st);
     if (r) {
       mpg::set_error("conv igemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+      return r;
+    }
+    return MPG_OK;
+  }
+  if (p->kind == 3) {
+    const void* xs[2] = {x0, x1};
+    for (int s = 0; s < d.nseg; ++s) {
+      if (p->tm_x_ptr[s] == xs[s]) continue;
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(xs[s]) & 15) == 0, "conv: input %d not 16-byte aligned", s);
+      const uint64_t cs = static_cast<uint64_t>(d.seg_cstride[s]) * 2;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
+                                static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+      const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+      const uint32_t box[4] = {static_cast<uint32_t>(p->ck), static_cast<uint32_t>(mpg::kNfWin),
+                               static_cast<uint32_t>(p->np.rows + d.seg_ksize[s] - 1), 1u};
+      int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
+                               box, swizzle_for(p->ck));
+      if (r) return r;
+      p->tm_x_ptr[s] = xs[s];
+    }
+    if (d.out_dtype != MPG_F32)
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
+    mpg::NfoldParams q = p->np;
+    q.out = y;
+    int r = mpg::nfold_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w, q, p->grid,
+                              p->smem_bytes, st);
+    if (r) {
+      mpg::set_error("conv nfold launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
       return r;
     }
     return MPG_OK;

@@ -350,7 +350,7 @@ class CompiledNet:
         x0 = ins[0]
         x1 = ins[1] if len(ins) > 1 else None
         if self.dry:
-            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride)
+            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride, grp.ups, out.cstride)
         else:
             plan = capi.ConvPlan(self.h, self.batch, ih, iw, ws, [b.cstride for b in ins], cout, out.cstride,
                                  act=grp.act, scales=scs if any_scale else None, shift=shift_total,
@@ -364,7 +364,7 @@ class CompiledNet:
             plan.run(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out), stream)
 
         label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s" % (
-            "tc" if kind == capi.KIND_TCGEN05 else "cc",
+            {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf"}.get(kind, "cc"),
             "+".join(c.attrs["weight"]["var"].name.rsplit("/", 2)[-2] for c in convs),
             "/".join(str(c.attrs["ksize"]) for c in convs),
             "/".join(str(c.inputs[0].shape[3]) for c in convs), cout, ih, iw,
@@ -376,12 +376,18 @@ class CompiledNet:
         self.steps.append((label, step))
         return View(oh, ow, [(out, 0, cout, 1, 1)])
 
-    def _predict_kind(self, convs, ins, cout, out_dtype, stride):
+    def _predict_kind(self, convs, ins, cout, out_dtype, stride, ups=1, out_cstride=None):
         """Mirror of the auto rule in csrc/conv_plan.cu (dry runs only)."""
         if self.act_dtype == capi.F32 or stride != 1 or cout > 128:
             return capi.KIND_DIRECT
         if any(c.attrs["ksize"] not in (1, 3, 5) for c in convs) or any(b.cstride % 8 for b in ins):
             return capi.KIND_DIRECT
+        cp = _round_up(cout, 8)
+        if (ups == 1 and cout <= 32 and convs[0].attrs["ksize"] in (3, 5)
+                and (len(convs) == 1 or convs[1].attrs["ksize"] == 1)
+                and (out_cstride <= 32 if out_dtype == capi.F32 else out_cstride == cp)
+                and (cp * convs[0].attrs["ksize"] <= 64 or sum(c.inputs[0].shape[3] for c in convs) >= 64)):
+            return capi.KIND_NFOLD
         return capi.KIND_TCGEN05
 
     # ------------------------------------------------------------------ execution

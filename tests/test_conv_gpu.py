@@ -19,9 +19,18 @@ CASES = {
     "k3_pn_up2": dict(n=1, h=32, w=32, cins=[128], ks=[3], cout=128, act="relu", pixel_norm=True, upsample=2),
     "ragged_37x45": dict(n=3, h=37, w=45, cins=[64], ks=[5], cout=48, act="lrelu"),
     "tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="tanh"),
+    "nf_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=3),
     "k5_f32out": dict(n=1, h=32, w=32, cins=[128], ks=[5], cout=24, out_dtype="f32"),
     "k5_96to48": dict(n=1, h=40, w=40, cins=[96, 48], ks=[5, 1], cout=48, act="relu", pixel_norm=True),
     "k5_24to12": dict(n=1, h=40, w=40, cins=[24], ks=[5], cout=12, act="relu", pixel_norm=True),
+    # tap-folded tcgen05 path (narrow Cout): every thin layer of gen_resnet + pixel-norm / k3 / ragged variants
+    "nf_k5_4to8": dict(n=1, h=64, w=64, cins=[4], ks=[5], cout=8, act="relu", force_kind=3),
+    "nf_k5_8to2": dict(n=2, h=40, w=40, cins=[8], ks=[5], cout=2, act="relu", force_kind=3),
+    "nf_2seg_2k5_8k1_to1_f32": dict(n=1, h=40, w=72, cins=[2, 8], ks=[5, 1], cout=1, out_dtype="f32", act="relu", force_kind=3),
+    "nf_k3_32to32_pn": dict(n=1, h=48, w=48, cins=[32], ks=[3], cout=32, act="lrelu", pixel_norm=True, force_kind=3),
+    "nf_k3_64to32_s": dict(n=1, h=32, w=64, cins=[64, 64], ks=[3, 1], cout=32, act="relu", pixel_norm=True, force_kind=3),
+    "nf_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", force_kind=3),
+    "nf_k5_128to32_256": dict(n=1, h=256, w=256, cins=[128], ks=[5], cout=32, act="relu", force_kind=3),
     "direct_f32_k5_4to8_up4": dict(n=2, h=64, w=64, cins=[4], ks=[5], cout=8, in_dtype="f32", in_upsample=4, act="relu"),
     "direct_k5_8to2": dict(n=1, h=40, w=40, cins=[8], ks=[5], cout=2, act="relu"),
     "direct_2seg_to1_f32": dict(n=1, h=40, w=40, cins=[2, 8], ks=[5, 1], cout=1, out_dtype="f32", act="relu"),
@@ -47,6 +56,8 @@ def test_conv_case(name, half):
     tol = (6e-3 if half == "bf16" else 8e-4) if out16 else 2e-5
     assert r["finite"] and r["pad_ok"], r
     assert r["rel_l2"] < tol, (name, r)
+    if name.startswith("nf_"):
+        assert r["kind"] == 3, r
 
 
 def test_flagship_shape_one_slice():

@@ -23,16 +23,14 @@ SHAPES = [
     ("cB3+s3 2/8->1 f32", dict(cins=[2, 8], ks=[5, 1], cout=1, f32out=True)),
 ]
 CONFIGS = {
-    "default": {},
-    "old": {"MPG_IGEMM_OCC": "1", "MPG_IGEMM_HALO": "0", "MPG_IGEMM_BRES": "0"},
-    "nobres": {"MPG_IGEMM_BRES": "0"},
-    "occ1": {"MPG_IGEMM_OCC": "1"},
-    "nohalo": {"MPG_IGEMM_HALO": "0"},
-    "nostore": {"MPG_IGEMM_DBG": "1"},
-    "noepi": {"MPG_IGEMM_DBG": "3"},
-    "nomma": {"MPG_IGEMM_DBG": "4"},
-    "nomma_noepi": {"MPG_IGEMM_DBG": "7"},
+    "skel": {"MPG_IGEMM_DBG": "7"},
+    "skel_nb3": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "3"},
+    "skel_nb2": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "2"},
+    "skel_nb7": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "7", "MPG_IGEMM_NA": "2"},
+    "nb3": {"MPG_IGEMM_NB": "3"},
+    "nb7": {"MPG_IGEMM_NB": "7", "MPG_IGEMM_NA": "2"},
 }
+SHAPES = [x for x in SHAPES if x[0].startswith(("cA1", "cB1"))]
 KEYS = sorted({k for c in CONFIGS.values() for k in c})
 
 
