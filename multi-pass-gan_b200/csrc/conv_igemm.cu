@@ -1,4 +1,6 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_igemm.cuh for the design).
+#include <string.h>
+
 #include "conv_igemm.cuh"
 #include "ptx.cuh"
 
@@ -54,7 +56,11 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const IgemmParams& p) {
   return c;
 }
 
-template <int CK>
+// PAIR: the two CTAs of a cluster form a cta_group::2 pair. Each CTA owns its own 16x16-pixel tile (A operand,
+// accumulators, epilogue) but holds only HALF of every weight tile; the leader issues M=256 MMAs that read both
+// halves, so the L2->SM weight traffic per SM halves (measured: an SM ingests ~27 B/clk from L2, which bounds
+// the single-CTA kernel at 970 KB per tile vs 26 K MMA cycles).
+template <int CK, bool PAIR>
 __global__ void __launch_bounds__(kIgThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
@@ -78,6 +84,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // tile schedule: CTA (or CTA pair) q takes tiles q, q+G, ...; in PAIR mode the pair takes tiles (2q, 2q+1) and
+  // both CTAs run the same number of iterations (an odd last tile is recomputed by the peer, not stored)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tstep = PAIR ? static_cast<int>(gridDim.x >> 1) * 2 : static_cast<int>(gridDim.x);
+  const int tfirst = PAIR ? static_cast<int>(blockIdx.x >> 1) * 2 + static_cast<int>(rank) : static_cast<int>(blockIdx.x);
+#define MPG_TILE_LOOP(t) for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep)
+#define MPG_TILE_CLAMP(t) ((t) < p.num_tiles ? (t) : p.num_tiles - 1)
 
   for (int i = threadIdx.x; i < p.npad; i += kIgThreads) s_shift[i] = p.shift[i];
 
@@ -96,16 +109,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in PAIR mode)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(&tmem_base_slot, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const float act_a = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.6f : 1.0f);
@@ -117,8 +136,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(t, p);
+      MPG_TILE_LOOP(t) {
+        const TileCoord tc = decode_tile(MPG_TILE_CLAMP(t), p);
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
           const int pad = ks >> 1;
@@ -128,9 +147,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
             for (int dx = 0; dx < (p.halo ? 1 : ks); ++dx) {
               mbar_wait(&empty_a[st], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_a[st], p.halo ? hbytes : bytes);
-              tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK,
-                          tc.x0 + dx - pad, tc.y0 - pad, tc.n);
+              if (PAIR) {
+                // both CTAs' images complete on the LEADER's barrier, which expects the bytes of both
+                if (rank == 0) mbar_arrive_expect_tx(&full_a[st], 2u * (p.halo ? hbytes : bytes));
+                tma_load_4d_2cta(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, mapa_u32(smem_u32(&full_a[st]), 0),
+                                 ch * CK, tc.x0 + dx - pad, tc.y0 - pad, tc.n);
+              } else {
+                mbar_arrive_expect_tx(&full_a[st], p.halo ? hbytes : bytes);
+                tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK,
+                            tc.x0 + dx - pad, tc.y0 - pad, tc.n);
+              }
               if (++st == p.na) {
                 st = 0;
                 ph ^= 1u;
@@ -145,14 +171,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      const uint32_t tile_bytes = static_cast<uint32_t>(p.npad * RB);
+      const int nrows = PAIR ? p.npad / 2 : p.npad;  // PAIR: this CTA holds weight rows [rank*N/2, (rank+1)*N/2)
+      const int row0 = PAIR ? static_cast<int>(rank) * nrows : 0;
+      const uint32_t tile_bytes = static_cast<uint32_t>(nrows * RB);
       if (p.bres) {
         // resident weights: every k-tile is loaded once per CTA and stays in shared memory
         mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
         for (int kt = 0; kt < p.ktiles; ++kt)
           tma_load_2d(smB + static_cast<size_t>(kt) * p.b_tile_bytes, &tm_w, &full_b[0], 0, kt * p.npad);
       }
-      for (int t = blockIdx.x; t < p.num_tiles && !p.bres; t += gridDim.x) {
+      MPG_TILE_LOOP(t) {
+        if (p.bres) break;
         int kt = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
@@ -160,10 +189,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           const int ngroups = p.seg_nchunk[s] * ks * (ks / gb);
           for (int i = 0; i < ngroups; ++i) {
             mbar_wait(&empty_b[st], ph ^ 1u);
-            mbar_arrive_expect_tx(&full_b[st], tile_bytes * gb);
             uint8_t* dst = smB + static_cast<size_t>(st) * p.b_stage_bytes;
-            for (int g = 0; g < gb; ++g, ++kt)
-              tma_load_2d(dst + static_cast<size_t>(g) * p.b_tile_bytes, &tm_w, &full_b[st], 0, kt * p.npad);
+            if (PAIR) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_b[st], 2u * tile_bytes * gb);
+              const uint32_t bar = mapa_u32(smem_u32(&full_b[st]), 0);
+              for (int g = 0; g < gb; ++g, ++kt)
+                tma_load_2d_2cta(dst + static_cast<size_t>(g) * p.b_tile_bytes, &tm_w, bar, 0, kt * p.npad + row0);
+            } else {
+              mbar_arrive_expect_tx(&full_b[st], tile_bytes * gb);
+              for (int g = 0; g < gb; ++g, ++kt)
+                tma_load_2d(dst + static_cast<size_t>(g) * p.b_tile_bytes, &tm_w, &full_b[st], 0, kt * p.npad);
+            }
             if (++st == p.nb) {
               st = 0;
               ph ^= 1u;
@@ -172,11 +208,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer ==========================================================
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
+    // ===================== MMA issuer (PAIR: leader CTA only) ==========================================================
     // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
     // registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
-    const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
+    const uint32_t idesc = umma_idesc_f16kind(PAIR ? 256 : 128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
     // smem-descriptor words: hi = SBO | version 1 | layout type; lo = (addr >> 4) | LBO(1)
     constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
     constexpr uint32_t DESC_LO = 1u << 16;
@@ -184,7 +220,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     uint32_t pa = 0, pb = 0;
     int it = 0;
     if (p.bres) mbar_wait(&full_b[0], 0);
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it & 1;
       mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
@@ -222,8 +258,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                       const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
                       const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
                       if (!(p.dbg & 4)) {
-                        umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                        umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                        if (PAIR) umma_bf16_ss_2cta(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                        if (PAIR) umma_bf16_ss_2cta(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
                       }
                     }
                   } else {
@@ -243,14 +279,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                       const uint64_t ad0 = (static_cast<uint64_t>(hi0) << 32) | (a_lo + (off0 >> 4) + k * 2);
                       const uint64_t ad1 = (static_cast<uint64_t>(hi1) << 32) | (a_lo + (off1 >> 4) + k * 2);
                       if (!(p.dbg & 4)) {
-                        umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                        umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                        if (PAIR) umma_bf16_ss_2cta(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
+                        if (PAIR) umma_bf16_ss_2cta(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
                       }
                     }
                   }
                   accumulate = 1;
                 }
-                if (!p.bres) umma_commit(&empty_b[sb]);
+                if (!p.bres) { if (PAIR) umma_commit_2cta(&empty_b[sb], 3); else umma_commit(&empty_b[sb]); }
               }
               __syncwarp();
               accumulate = 1;
@@ -260,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
               }
             }
             if (!p.halo || dx == ks - 1) {
-              if (elect_one()) umma_commit(&empty_a[sa]);
+              if (elect_one()) { if (PAIR) umma_commit_2cta(&empty_a[sa], 3); else umma_commit(&empty_a[sa]); }
               __syncwarp();
               if (++sa == p.na) {
                 sa = 0;
@@ -270,7 +306,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           }
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[buf]);
+      if (elect_one()) { if (PAIR) umma_commit_2cta(&tmem_full[buf], 3); else umma_commit(&tmem_full[buf]); }
       __syncwarp();
     }
   } else if (warp >= 4 && p.tma_store) {
@@ -290,9 +326,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                          : (box_c == 16) ? static_cast<uint32_t>((m >> 2) & 1) : 0u;
     uint8_t* stg = smem + p.stage_off;
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it & 1;
-      const TileCoord tc = decode_tile(t, p);
+      const TileCoord tc = decode_tile(MPG_TILE_CLAMP(t), p);
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       if (it > 0) {  // the previous tile's stores must have finished reading the staging tiles
@@ -341,7 +377,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       // accumulators are drained: hand the TMEM buffer back before the stores are issued
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
+        else mbar_arrive(&tmem_empty[buf]);
+      }
       fence_proxy_async();
       named_bar_sync(1, 128);
       if (et == 0 && !(p.dbg & 1)) {
@@ -377,16 +416,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const float inv_c = 1.0f / static_cast<float>(p.cout);
     const bool st32 = (p.out_cstride % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && !(p.dbg & 8);
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it & 1;
-      const TileCoord tc = decode_tile(t, p);
+      const TileCoord tc = decode_tile(MPG_TILE_CLAMP(t), p);
       mbar_wait(&tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int acc = 0; acc < 2; ++acc) {
         const int y = tc.y0 + (p.halo ? 0 : acc * 8) + prow;
         const int x = tc.x0 + (p.halo ? acc * 8 : 0) + pcol;
-        const bool valid = (y < p.h) && (x < p.w) && !(p.dbg & 1);
+        const bool valid = (y < p.h) && (x < p.w) && (t < p.num_tiles) && !(p.dbg & 1);
         if (p.dbg & 2) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                                static_cast<uint32_t>((buf * 2 + acc) * p.npad);
@@ -449,49 +488,66 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#undef MPG_TILE_LOOP
+#undef MPG_TILE_CLAMP
 }
 
 }  // namespace
 
-// The attribute is per kernel instantiation, not per plan: only ever raise it.
-static size_t g_smem_attr[3] = {0, 0, 0};
+typedef void (*IgKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams);
 
-int igemm_set_smem_attr(int ck, size_t smem_bytes) {
-  const int slot = ck == 64 ? 0 : (ck == 32 ? 1 : 2);
+static IgKernel ig_kernel(int ck, int pair) {
+  if (pair) return ck == 64 ? conv_igemm_kernel<64, true> : (ck == 32 ? conv_igemm_kernel<32, true> : conv_igemm_kernel<16, true>);
+  return ck == 64 ? conv_igemm_kernel<64, false> : (ck == 32 ? conv_igemm_kernel<32, false> : conv_igemm_kernel<16, false>);
+}
+
+// The attribute is per kernel instantiation, not per plan: only ever raise it.
+static size_t g_smem_attr[6] = {0, 0, 0, 0, 0, 0};
+
+int igemm_set_smem_attr(int ck, int pair, size_t smem_bytes) {
+  const int slot = (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (pair ? 3 : 0);
   if (smem_bytes <= g_smem_attr[slot]) return 0;
-  cudaError_t e;
-  if (ck == 64)
-    e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes));
-  else if (ck == 32)
-    e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes));
-  else
-    e = cudaFuncSetAttribute(conv_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_bytes));
+  cudaError_t e = cudaFuncSetAttribute(ig_kernel(ck, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem_bytes));
   if (e == cudaSuccess) g_smem_attr[slot] = smem_bytes;
   return static_cast<int>(e);
 }
 
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
-  if (ck == 64)
-    conv_igemm_kernel<64><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
-  else if (ck == 32)
-    conv_igemm_kernel<32><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
-  else
-    conv_igemm_kernel<16><<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
-  return static_cast<int>(cudaGetLastError());
+  if (!p.pair) {
+    ig_kernel(ck, 0)<<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(kIgThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, ig_kernel(ck, 1), tm_x0, tm_x1, tm_w, tm_y, p));
 }
 
 }  // namespace mpg

@@ -43,6 +43,7 @@ struct IgemmParams {
   // halo mode: ONE TMA halo image [16+k-1][16+k-1][CK] per (segment, chunk); every (dy,dx) tap is a
   // shifted UMMA descriptor into it (accumulator = 16 rows x 8 px). halo_bo: descriptor base_offset rule
   int halo, halo_bo;
+  int pair;  // cta_group::2 CTA pairs: each CTA holds half of every weight tile (wide, weight-streaming layers)
   // resident weights: all `ktiles` weight tiles live in smem for the CTA's lifetime (thin layers)
   int bres, ktiles;
   int dbg;  // profiling only (env MPG_IGEMM_DBG): bit0 skip global stores, bit1 skip the TMEM loads too
@@ -54,6 +55,6 @@ struct IgemmParams {
 // ck in {16, 32, 64}; returns cudaError_t as int
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
-int igemm_set_smem_attr(int ck, size_t smem_bytes);
+int igemm_set_smem_attr(int ck, int pair, size_t smem_bytes);
 
 }  // namespace mpg

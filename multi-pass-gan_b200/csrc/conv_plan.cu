@@ -147,14 +147,6 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
   MPG_CUDA(cudaMalloc(&p->d_shift, npad * sizeof(float)));
   MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(ck), static_cast<uint64_t>(ktiles) * npad};
-    const uint64_t strides[1] = {static_cast<uint64_t>(rb)};
-    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(npad)};
-    int r = encode_tmap(p->h, &p->tm_w, d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                        p->d_wpacked, dims, strides, box, swizzle_for(ck));
-    if (r) return r;
-  }
 
 
   IgemmParams& ip = p->ip;
@@ -189,14 +181,28 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   if (ip.tma_store) ip.halo = 0;
   ip.a_stage_bytes = (kIgTileH + maxks - 1) * (ip.halo ? (kIgTileW + maxks - 1) : kIgTileW) * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
-  ip.b_tile_bytes = round_up(npad * rb, 1024);
   ip.ktiles = ktiles;
+  // CTA pairs (cta_group::2) for the layers that stream their weights: each CTA keeps half of every weight tile
+  ip.pair = (ip.halo && !ip.tma_store && npad % 32 == 0 && ip.tiles_x * ip.tiles_y * d.n >= 2 &&
+             static_cast<size_t>(ktiles) * round_up(npad * rb, 1024) > 64 * 1024) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_PAIR")) ip.pair = (atoi(e) && ip.halo && !ip.tma_store && npad % 32 == 0) ? 1 : 0;
+  const int brows = ip.pair ? npad / 2 : npad;
+  ip.b_tile_bytes = round_up(brows * rb, 1024);
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ck), static_cast<uint64_t>(ktiles) * npad};
+    const uint64_t strides[1] = {static_cast<uint64_t>(rb)};
+    const uint32_t box[2] = {static_cast<uint32_t>(ck), static_cast<uint32_t>(brows)};
+    int r = encode_tmap(p->h, &p->tm_w, d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        p->d_wpacked, dims, strides, box, swizzle_for(ck));
+    if (r) return r;
+  }
   // resident weights: thin layers keep every weight tile in shared memory for the CTA's lifetime, which
   // removes the per-tile weight TMA round trips that bound them (measured: 0.18 of 0.22 ms was load skeleton)
-  ip.bres = (static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 64 * 1024) ? 1 : 0;
-  if (const char* e = getenv("MPG_IGEMM_BRES")) ip.bres = (atoi(e) && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 160 * 1024) ? 1 : 0;
-  // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: the MMA
-  // thread then waits/commits once per 2*ks*CK/16 MMAs instead of once per 2*CK/16 (issue-latency bound)
+  ip.bres = (!ip.pair && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 64 * 1024) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_BRES")) ip.bres = (!ip.pair && atoi(e) && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 160 * 1024) ? 1 : 0;
+  // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: every stage
+  // hand-over (mbarrier wait + tcgen05.commit round trip) costs ~450 cycles on top of bytes/27 B/clk (measured,
+  // tools/thin_probe.py), so the MMA thread should wait/commit once per 2*ks*CK/16 MMAs, not once per 2*CK/16
   ip.bgroup = (maxks * ip.b_tile_bytes <= 40 * 1024) ? 1 : 0;
   if (const char* e = getenv("MPG_IGEMM_BGROUP")) ip.bgroup = atoi(e) ? 1 : 0;
   ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
@@ -211,6 +217,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   int occ = 1;
   if (cols <= 256 && (ip.bres ? b_res_bytes : 3 * ip.b_stage_bytes) + 2 * ip.a_stage_bytes <= 100 * 1024) occ = 2;
   if (const char* e = getenv("MPG_IGEMM_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
+  if (ip.pair) occ = 1;
   const int budget = (210 * 1024) / occ - 2 * ip.stage_bytes - (occ > 1 ? 2048 : 0);
   int nb, na;
   if (ip.bres) {
@@ -244,7 +251,13 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   p->smem_bytes = static_cast<size_t>(ip.stage_off) + 2 * static_cast<size_t>(ip.stage_bytes) + 1024;
   p->grid = ip.num_tiles < p->h->sm_count * occ ? ip.num_tiles : p->h->sm_count * occ;
   if (const char* e = getenv("MPG_IGEMM_GRID")) p->grid = atoi(e) > 0 ? atoi(e) : p->grid;
-  int r = igemm_set_smem_attr(ck, p->smem_bytes);
+  if (ip.pair) {  // whole pairs only; a pair covers two tiles
+    const int pairs_needed = (ip.num_tiles + 1) / 2;
+    int pairs = p->h->sm_count / 2;
+    if (pairs > pairs_needed) pairs = pairs_needed;
+    p->grid = pairs * 2;
+  }
+  int r = igemm_set_smem_attr(ck, ip.pair, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes,
               cudaGetErrorString(static_cast<cudaError_t>(r)));

@@ -23,14 +23,13 @@ SHAPES = [
     ("cB3+s3 2/8->1 f32", dict(cins=[2, 8], ks=[5, 1], cout=1, f32out=True)),
 ]
 CONFIGS = {
+    "default": {},
+    "bgroup": {"MPG_IGEMM_BGROUP": "1"},
     "skel": {"MPG_IGEMM_DBG": "7"},
-    "skel_nb3": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "3"},
-    "skel_nb2": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "2"},
-    "skel_nb7": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_NB": "7", "MPG_IGEMM_NA": "2"},
-    "nb3": {"MPG_IGEMM_NB": "3"},
-    "nb7": {"MPG_IGEMM_NB": "7", "MPG_IGEMM_NA": "2"},
+    "skel_bgroup": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_BGROUP": "1"},
+    "nopair_bgroup0": {"MPG_IGEMM_PAIR": "0", "MPG_IGEMM_BGROUP": "0"},
+    "nopair_skel_bgroup0": {"MPG_IGEMM_PAIR": "0", "MPG_IGEMM_BGROUP": "0", "MPG_IGEMM_DBG": "7"},
 }
-SHAPES = [x for x in SHAPES if x[0].startswith(("cA1", "cB1"))]
 KEYS = sorted({k for c in CONFIGS.values() for k in c})
 
 
