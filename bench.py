@@ -243,7 +243,9 @@ def run_ours(args):
         return 0
     peaks = load_peaks()
     achieved = dom_flops / (kern_avg_ms * 1e-3) / 1e12
-    peak = peaks["tflops_sustained"]
+    # denominator: the driver-measured cuBLAS bf16 BURST figure - the kernel sustains more than the 4-s
+    # "sustained" cuBLAS number inside the step, so the stricter (larger) peak is the honest one
+    peak = peaks["tflops"]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         dt, vox, cores = cpu_reference_sample(L, u, 1, args.cpu_slices)
@@ -252,7 +254,9 @@ def run_ours(args):
                           "extrapolated x%d; host zoom/transposes excluded" % (args.cpu_slices, S, S, S, dt,
                                                                                 S // args.cpu_slices))
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic_pair.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
@@ -273,9 +277,9 @@ def run_ours(args):
                  h2d_bytes_per_step=int(x_pin.numel() * 4), d2h_bytes_per_step=int(out_pin.numel() * 4),
                  checksum=checksum),
         gpu_launches=int(mp.launches_per_frame * args.steps),
-        roofline=dict(bound="tensor", kernel="conv_igemm_kernel<64> " + dom_label, achieved=achieved, peak=peak,
-                      unit="TFLOP/s", frac=achieved / peak, frac_of_burst=achieved / peaks["tflops"],
-                      peak_source=peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+        roofline=dict(bound="tensor", kernel="conv_igemm_kernel<64,pair> " + dom_label, achieved=achieved, peak=peak,
+                      unit="TFLOP/s", frac=achieved / peak, frac_of_sustained=achieved / peaks["tflops_sustained"],
+                      peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops); fp16 operands run at the same kind::f16 rate",
                       flops_per_launch=dom_flops, avg_launch_ms=kern_avg_ms, launches_timed=len(kern_ms),
                       share_of_step=kern_share, traffic=traffic),
         clocks=clocks,
@@ -295,7 +299,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=8, help="slices per network launch (reference: 8)")
     ap.add_argument("--L", type=int, default=128, help="low-res edge (config 2: 128)")
-    ap.add_argument("--cpu-slices", type=int, default=4, help="slices per pass timed on the CPU baseline")
+    ap.add_argument("--cpu-slices", type=int, default=16, help="slices per pass timed on the CPU baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

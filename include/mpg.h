@@ -178,6 +178,55 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
 /* in-place v < threshold -> 0 (GAN/multipassGAN-out.py:614-615, GAN/multipassGAN-4x.py:1156-1157) */
 int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step of the 4x model (generator + spatial discriminator, GAN/multipassGAN-4x.py:528-620,
+ * 744-768, 889-902, loop :1316-1397).  All tensors fp32 NHWC, weights HWIO fp32 in DEVICE memory
+ * (Adam rewrites them every step).  `scratch` is caller-owned device memory of the stated size.
+ * -----------------------------------------------------------------------------------------*/
+
+/* y = conv2d_SAME(nearest_up(x, in_up), w, stride) + bias   (tools_wscale/GAN.py:94,105; max_depool :517) */
+int mpg_train_conv_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int n, int hh,
+                       int ww, int cin, int cout, int k, int stride, int in_up, void* stream);
+/* dx (+)= d loss / d x of that convolution (tf.gradients -> Conv2DBackpropInput) */
+int mpg_train_conv_dgrad(mpg_handle h, const float* dy, const float* w, float* dx, int n, int hh, int ww, int cin,
+                         int cout, int k, int stride, int accumulate, void* stream);
+/* dw += Conv2DBackpropFilter, dbias += sum dy (dbias may be NULL); scratch: cout doubles */
+int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* dw, float* dbias, double* scratch,
+                         int n, int hh, int ww, int cin, int cout, int k, int stride, int in_up, void* stream);
+/* tf.contrib.layers.batch_norm(is_training=True) (+ activation) and its moving-average update
+ * (tools_wscale/GAN.py:110; UPDATE_OPS GAN/multipassGAN-4x.py:776-779). scratch: 2*c doubles */
+int mpg_train_bn_fwd(mpg_handle h, const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                     float* var, float* invstd, float* moving_mean, float* moving_var, double* scratch,
+                     long long rows, int c, float eps, float decay, int act, void* stream);
+int mpg_train_bn_bwd(mpg_handle h, const float* x, const float* y, const float* dy, const float* gamma,
+                     const float* mean, const float* invstd, float* dz, float* dx, float* dgamma, float* dbeta,
+                     double* scratch, long long rows, int c, int act, void* stream);
+int mpg_train_act_fwd(mpg_handle h, const float* x, float* y, long long count, int act, void* stream);
+int mpg_train_add_act_fwd(mpg_handle h, const float* a, const float* b, float* y, long long count, int act,
+                          void* stream); /* relu(tf.add(B, s)) GAN/multipassGAN-4x.py:523 */
+int mpg_train_act_bwd(mpg_handle h, const float* y, const float* dy, float* dz, long long count, int act,
+                      void* stream);
+int mpg_train_axpy(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream);
+/* out = a * b: run-time weight scaling W_eff = v * wscale (tools_wscale/GAN.py:664-668) and its gradient */
+int mpg_train_mul(mpg_handle h, float* out, const float* a, const float* b, long long count, void* stream);
+/* losses (GAN/multipassGAN-4x.py:751-768): *loss (device double) += scale * value, gradient (+)= into d* */
+int mpg_train_bce_logits(mpg_handle h, const float* logits, float label, float scale, double* loss,
+                         float* dlogits, long long count, int accumulate, void* stream);
+int mpg_train_l1_mean(mpg_handle h, const float* y, const float* g, float scale, double* loss, float* dg,
+                      long long count, int accumulate, void* stream);
+int mpg_train_l2_half(mpg_handle h, const float* a, const float* b, float scale, double* loss, float* db,
+                      long long count, int accumulate, void* stream);
+/* tf.train.AdamOptimizer update, TF1 "epsilon hat" form (GAN/multipassGAN-4x.py:889-898), one flat launch */
+int mpg_train_adam(mpg_handle h, float* param, const float* grad, float* m, float* v, long long count, float lr_t,
+                   float beta1, float beta2, float eps, void* stream);
+/* GAN.fully_connected_layer with one output (tools_wscale/GAN.py:438-456; d_l5) */
+int mpg_train_fc_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int rows, int nin,
+                     void* stream);
+int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                     float* dbias, int rows, int nin, void* stream);
+int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long npix, int cstride, int c,
+                           int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

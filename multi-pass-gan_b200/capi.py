@@ -88,6 +88,24 @@ def lib():
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
     L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
+    ll, fl = ctypes.c_longlong, ctypes.c_float
+    L.mpg_train_conv_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_conv_dgrad.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_conv_wgrad.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ip, fl, fl, ip, vp]
+    L.mpg_train_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ip, ip, vp]
+    L.mpg_train_act_fwd.argtypes = [vp, vp, vp, ll, ip, vp]
+    L.mpg_train_add_act_fwd.argtypes = [vp, vp, vp, vp, ll, ip, vp]
+    L.mpg_train_act_bwd.argtypes = [vp, vp, vp, vp, ll, ip, vp]
+    L.mpg_train_axpy.argtypes = [vp, vp, vp, fl, ll, vp]
+    L.mpg_train_mul.argtypes = [vp, vp, vp, vp, ll, vp]
+    L.mpg_train_bce_logits.argtypes = [vp, vp, fl, fl, vp, vp, ll, ip, vp]
+    L.mpg_train_l1_mean.argtypes = [vp, vp, vp, fl, vp, vp, ll, ip, vp]
+    L.mpg_train_l2_half.argtypes = [vp, vp, vp, fl, vp, vp, ll, ip, vp]
+    L.mpg_train_adam.argtypes = [vp, vp, vp, vp, vp, ll, fl, fl, fl, fl, vp]
+    L.mpg_train_fc_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp]
+    L.mpg_train_fc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip, vp]
+    L.mpg_train_take_channel.argtypes = [vp, vp, vp, ll, ip, ip, ip, vp]
     _lib = L
     return L
 
@@ -281,3 +299,9 @@ def transpose3d(handle, src, dst, dims, perm, threshold=0.0, stream=0):
 
 def threshold(handle, vol, count, thr, stream=0):
     check(lib().mpg_threshold(handle.ptr, _ptr(vol), int(count), float(thr), stream), "mpg_threshold")
+
+
+def train_call(name, handle, *args):
+    """Generic checked call of an mpg_train_* entry point; tensors are passed as torch tensors / None / ints."""
+    conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr")) else a) for a in args]
+    check(getattr(lib(), "mpg_train_" + name)(handle.ptr, *conv), "mpg_train_" + name)

@@ -1,0 +1,700 @@
+// Training-step kernels (GAN/multipassGAN-4x.py:572-620,744-768,889-902): fp32 NHWC
+// forward / dgrad / wgrad convolutions on HWIO weights that live in device memory (they change every Adam step),
+// training-mode batch norm, activations, the GAN losses, TF1 Adam and the BN moving-average update.
+// C-ABI: mpg_train_* (include/mpg.h).  The training tiles are tiny (16 x 64 x 64 pixels), so these are
+// register-tiled CUDA-core kernels; the inference path keeps the tcgen05 kernels.
+#include "common.h"
+
+namespace mpg {
+namespace {
+
+__host__ __device__ inline int same_pad_before_tf(int in, int k, int s) {
+  const int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tiled direct convolution: out[n,oy,ox,co] = sum_{ky,kx,ci} in[n, oy*s - pad + ky, ox*s - pad + kx, ci] * W(ky,kx,ci,co) (+ bias)
+// `wmode` 0: W = w[ky][kx][ci][co] (forward, HWIO with wci = cin, wco = cout)
+//         1: W = w[k-1-ky][k-1-kx][co][ci]  (stride-1 dgrad: the kernel is run with cin := Cout_fwd, cout := Cin_fwd)
+// `in_up`: the conv reads a nearest-upsampled view of `in` (in is [n, h/in_up, w/in_up, cin]).
+// Block = 256 threads -> 8 x 16 output pixels x 64 output channels; thread tile 4 pixels x 8 channels.
+struct ConvArgs {
+  const float* in;
+  const float* w;
+  const float* bias;
+  float* out;
+  int n, h, w_, cin, cout, k, stride, pad, oh, ow, in_up, wmode, accumulate;
+};
+
+constexpr int kTP = 128;  // pixels per block (8 rows x 16 cols)
+constexpr int kTC = 64;   // output channels per block
+constexpr int kKC = 16;   // input channels per smem chunk
+
+__global__ void __launch_bounds__(256) conv_tiled_kernel(const ConvArgs a) {
+  __shared__ float xs[kTP][kKC + 1];
+  __shared__ __align__(16) float ws[kKC][kTC];
+  const int tiles_x = (a.ow + 15) / 16, tiles_y = (a.oh + 7) / 8;
+  int b = blockIdx.x;
+  const int tx_ = b % tiles_x;
+  b /= tiles_x;
+  const int ty_ = b % tiles_y;
+  const int n = b / tiles_y;
+  const int co0 = blockIdx.y * kTC;
+  const int tid = threadIdx.x;
+  const int cg = tid & 7;   // channel group: 8 channels
+  const int pg = tid >> 3;  // pixel group: 4 pixels (one row segment)
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  const int sh = a.h / a.in_up, sw = a.w_ / a.in_up;
+  for (int ky = 0; ky < a.k; ++ky) {
+    for (int kx = 0; kx < a.k; ++kx) {
+      for (int c0 = 0; c0 < a.cin; c0 += kKC) {
+        __syncthreads();
+        // ---- stage inputs: 128 pixels x 16 channels
+        for (int e = tid; e < kTP * kKC; e += 256) {
+          const int p = e / kKC, c = e % kKC;
+          const int oy = ty_ * 8 + (p >> 4), ox = tx_ * 16 + (p & 15);
+          const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+          float v = 0.0f;
+          if (c0 + c < a.cin && iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
+            v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + c0 + c];
+          xs[p][c] = v;
+        }
+        // ---- stage weights: 16 input channels x 64 output channels
+        for (int e = tid; e < kKC * kTC; e += 256) {
+          const int c = e / kTC, o = e % kTC;
+          float v = 0.0f;
+          if (c0 + c < a.cin && co0 + o < a.cout) {
+            if (a.wmode == 0)
+              v = a.w[((static_cast<size_t>(ky) * a.k + kx) * a.cin + c0 + c) * a.cout + co0 + o];
+            else
+              v = a.w[((static_cast<size_t>(a.k - 1 - ky) * a.k + (a.k - 1 - kx)) * a.cout + co0 + o) * a.cin + c0 + c];
+          }
+          ws[c][o] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < kKC; ++c) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[c][cg * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[c][cg * 8 + 4]);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xv = xs[pg * 4 + i][c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = pg * 4 + i;
+    const int oy = ty_ * 8 + (p >> 4), ox = tx_ * 16 + (p & 15);
+    if (oy >= a.oh || ox >= a.ow) continue;
+    float* o = a.out + ((static_cast<size_t>(n) * a.oh + oy) * a.ow + ox) * a.cout;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = co0 + cg * 8 + j;
+      if (co < a.cout) {
+        float v = acc[i][j] + (a.bias ? a.bias[co] : 0.0f);
+        if (a.accumulate) v += o[co];
+        o[co] = v;
+      }
+    }
+  }
+}
+
+// Strided dgrad (discriminator convs, k=4 s=2): gather form, one thread per (pixel, ci).
+struct DgradArgs {
+  const float* dy;
+  const float* w;
+  float* dx;
+  int n, h, w_, cin, cout, k, stride, pad, oh, ow, accumulate;
+};
+__global__ void __launch_bounds__(256) dgrad_gather_kernel(const DgradArgs a) {
+  const long long total = static_cast<long long>(a.n) * a.h * a.w_ * a.cin;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ci = static_cast<int>(e % a.cin);
+    long long r = e / a.cin;
+    const int x = static_cast<int>(r % a.w_);
+    r /= a.w_;
+    const int y = static_cast<int>(r % a.h);
+    const int n = static_cast<int>(r / a.h);
+    float acc = 0.0f;
+    for (int ky = 0; ky < a.k; ++ky) {
+      const int ty = y + a.pad - ky;
+      if (ty < 0 || ty % a.stride) continue;
+      const int oy = ty / a.stride;
+      if (oy >= a.oh) continue;
+      for (int kx = 0; kx < a.k; ++kx) {
+        const int tx = x + a.pad - kx;
+        if (tx < 0 || tx % a.stride) continue;
+        const int ox = tx / a.stride;
+        if (ox >= a.ow) continue;
+        const float* d = a.dy + ((static_cast<size_t>(n) * a.oh + oy) * a.ow + ox) * a.cout;
+        const float* wp = a.w + ((static_cast<size_t>(ky) * a.k + kx) * a.cin + ci) * a.cout;
+        for (int co = 0; co < a.cout; ++co) acc = fmaf(d[co], wp[co], acc);
+      }
+    }
+    if (a.accumulate) acc += a.dx[e];
+    a.dx[e] = acc;
+  }
+}
+
+// wgrad: dW[ky][kx][ci][co] = sum_{n,oy,ox} in[n, oy*s-pad+ky, ox*s-pad+kx, ci] * dY[n,oy,ox,co]
+// grid = (taps * ci_tiles * co_tiles, pixel splits); block tile 32 ci x 64 co, thread tile 1 ci x 8 co; atomicAdd.
+struct WgradArgs {
+  const float* in;
+  const float* dy;
+  float* dw;
+  int n, h, w_, cin, cout, k, stride, pad, oh, ow, in_up, px_per_split;
+};
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
+  __shared__ float xs[32][33];
+  __shared__ __align__(16) float ys[32][64];
+  const int ci_tiles = (a.cin + 31) / 32, co_tiles = (a.cout + 63) / 64;
+  int b = blockIdx.x;
+  const int cot = b % co_tiles;
+  b /= co_tiles;
+  const int cit = b % ci_tiles;
+  const int tap = b / ci_tiles;
+  const int ky = tap / a.k, kx = tap % a.k;
+  const int tid = threadIdx.x;
+  const int ci_l = tid >> 3, cg = tid & 7;
+  const long long npix = static_cast<long long>(a.n) * a.oh * a.ow;
+  const long long p_begin = static_cast<long long>(blockIdx.y) * a.px_per_split;
+  long long p_end = p_begin + a.px_per_split;
+  if (p_end > npix) p_end = npix;
+  const int sh = a.h / a.in_up, sw = a.w_ / a.in_up;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+    __syncthreads();
+    for (int e = tid; e < 32 * 32; e += 256) {
+      const int pl = e >> 5, c = e & 31;
+      const long long p = p0 + pl;
+      float v = 0.0f;
+      if (p < p_end && cit * 32 + c < a.cin) {
+        const int ox = static_cast<int>(p % a.ow);
+        const long long r = p / a.ow;
+        const int oy = static_cast<int>(r % a.oh);
+        const int n = static_cast<int>(r / a.oh);
+        const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
+          v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + cit * 32 + c];
+      }
+      xs[pl][c] = v;
+    }
+    for (int e = tid; e < 32 * 64; e += 256) {
+      const int pl = e >> 6, o = e & 63;
+      const long long p = p0 + pl;
+      float v = 0.0f;
+      if (p < p_end && cot * 64 + o < a.cout) v = a.dy[p * a.cout + cot * 64 + o];
+      ys[pl][o] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pl = 0; pl < 32; ++pl) {
+      const float xv = xs[pl][ci_l];
+      const float4 y0 = *reinterpret_cast<const float4*>(&ys[pl][cg * 8]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&ys[pl][cg * 8 + 4]);
+      acc[0] = fmaf(xv, y0.x, acc[0]);
+      acc[1] = fmaf(xv, y0.y, acc[1]);
+      acc[2] = fmaf(xv, y0.z, acc[2]);
+      acc[3] = fmaf(xv, y0.w, acc[3]);
+      acc[4] = fmaf(xv, y1.x, acc[4]);
+      acc[5] = fmaf(xv, y1.y, acc[5]);
+      acc[6] = fmaf(xv, y1.z, acc[6]);
+      acc[7] = fmaf(xv, y1.w, acc[7]);
+    }
+  }
+  const int ci = cit * 32 + ci_l;
+  if (ci < a.cin) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = cot * 64 + cg * 8 + j;
+      if (co < a.cout) atomicAdd(&a.dw[(static_cast<size_t>(tap) * a.cin + ci) * a.cout + co], acc[j]);
+    }
+  }
+}
+
+// per-channel double-precision sums over `rows` rows of a [rows, c] matrix: out[0..c) += sum a*b?, out[c..2c) ...
+// mode 0: s0 = sum x, s1 = sum x^2          (BN statistics)
+// mode 1: s0 = sum dz, s1 = sum dz * xhat    (BN backward; xhat = (x - mean) * invstd)
+// mode 2: s0 = sum x                         (bias gradient)
+__global__ void __launch_bounds__(256) colstats_kernel(const float* x, const float* dz, const float* mean,
+                                                        const float* invstd, double* out, long long rows, int c,
+                                                        int mode) {
+  // thread -> channel (tid % c) when c <= 256, rows strided
+  const int lanes_per_row = c < 256 ? c : 256;
+  const int rows_per_iter = 256 / lanes_per_row;
+  const int ch_l = threadIdx.x % lanes_per_row;
+  const int r_l = threadIdx.x / lanes_per_row;
+  if (r_l >= rows_per_iter) return;
+  for (int ch = ch_l; ch < c; ch += lanes_per_row) {
+    double s0 = 0.0, s1 = 0.0;
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + r_l; r < rows;
+         r += static_cast<long long>(gridDim.x) * rows_per_iter) {
+      const float xv = x[r * c + ch];
+      if (mode == 0) {
+        s0 += xv;
+        s1 += static_cast<double>(xv) * xv;
+      } else if (mode == 1) {
+        const float d = dz[r * c + ch];
+        s0 += d;
+        s1 += static_cast<double>(d) * ((xv - mean[ch]) * invstd[ch]);
+      } else {
+        s0 += xv;
+      }
+    }
+    atomicAdd(&out[ch], s0);
+    if (mode != 2) atomicAdd(&out[c + ch], s1);
+  }
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == MPG_ACT_RELU) return fmaxf(z, 0.0f);
+  if (act == MPG_ACT_LRELU) return 0.6f * z + 0.4f * fabsf(z);  // tools_wscale/GAN.py:733-737
+  if (act == MPG_ACT_TANH) return tanhf(z);
+  return z;
+}
+// derivative expressed through the OUTPUT y = act(z) (relu / lrelu keep the sign of z)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  if (act == MPG_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  if (act == MPG_ACT_LRELU) return y > 0.0f ? 1.0f : (y < 0.0f ? 0.2f : 0.6f);  // d/dz (0.6 z + 0.4 |z|), 0.6 at z = 0
+  if (act == MPG_ACT_TANH) return 1.0f - y * y;
+  return 1.0f;
+}
+
+// finalize BN statistics: mean, biased variance, invstd; EMA of the moving statistics (tf.contrib batch_norm)
+__global__ void bn_finalize_kernel(const double* sums, float* mean, float* var, float* invstd, float* moving_mean,
+                                   float* moving_var, long long rows, int c, float eps, float decay) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double m = sums[ch] / static_cast<double>(rows);
+  double v = sums[c + ch] / static_cast<double>(rows) - m * m;
+  if (v < 0.0) v = 0.0;
+  mean[ch] = static_cast<float>(m);
+  var[ch] = static_cast<float>(v);
+  invstd[ch] = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+  if (moving_mean) {  // moving = moving * decay + batch * (1 - decay)
+    moving_mean[ch] = moving_mean[ch] * decay + static_cast<float>(m) * (1.0f - decay);
+    moving_var[ch] = moving_var[ch] * decay + static_cast<float>(v) * (1.0f - decay);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const float* gamma, const float* beta,
+                                                        const float* mean, const float* invstd, float* y,
+                                                        long long total, int c, int act) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % c);
+    const float z = (x[e] - mean[ch]) * invstd[ch] * gamma[ch] + beta[ch];
+    y[e] = act_fwd(z, act);
+  }
+}
+
+// dz = dy * act'(y)   (in place allowed)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* y, const float* dy, float* dz, long long total, int act) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    dz[e] = dy[e] * act_grad_from_out(y[e], act);
+}
+
+// dx = gamma * invstd / N * (N * dz - dbeta - xhat * dgamma);  dgamma/dbeta are read from `sums` (double)
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const float* x, const float* dz, const float* gamma,
+                                                      const float* mean, const float* invstd, const double* sums,
+                                                      float* dx, float* dgamma, float* dbeta, long long rows, int c) {
+  const long long total = rows * c;
+  const float inv_n = 1.0f / static_cast<float>(rows);
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % c);
+    const float db = static_cast<float>(sums[ch]), dg = static_cast<float>(sums[c + ch]);
+    const float xh = (x[e] - mean[ch]) * invstd[ch];
+    dx[e] = gamma[ch] * invstd[ch] * (dz[e] - inv_n * (db + xh * dg));
+    if (e < c) {
+      dgamma[e] += static_cast<float>(sums[c + e]);
+      dbeta[e] += static_cast<float>(sums[e]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* x, float* y, long long total, int act) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    y[e] = act_fwd(x[e], act);
+}
+__global__ void __launch_bounds__(256) add_act_kernel(const float* a, const float* b, float* y, long long total, int act) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    y[e] = act_fwd(a[e] + b[e], act);
+}
+__global__ void __launch_bounds__(256) axpy_kernel(float* y, const float* x, float alpha, long long total) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    y[e] += alpha * x[e];
+}
+__global__ void __launch_bounds__(256) mul_kernel(float* out, const float* a, const float* b, long long total) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    out[e] = a[e] * b[e];
+}
+__global__ void __launch_bounds__(256) dsum_to_f32_kernel(const double* s, float* out, int c, int accumulate) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < c) out[i] = (accumulate ? out[i] : 0.0f) + static_cast<float>(s[i]);
+}
+
+// ---- losses: each writes dloss/dinput (scaled) and atomically adds the loss value (double) to *loss
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < 8) r = sh[threadIdx.x];
+  if (threadIdx.x < 32)
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xFFFFFFFFu, r, o);
+  __syncthreads();
+  return r;
+}
+// tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log(1 + exp(-|x|)); mean over `count`, times scale
+__global__ void __launch_bounds__(256) bce_kernel(const float* x, float z, float scale, double* loss, float* dx,
+                                                   long long count, int accumulate) {
+  double part = 0.0;
+  const float inv = scale / static_cast<float>(count);
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < count; e += static_cast<long long>(gridDim.x) * 256) {
+    const float v = x[e];
+    part += static_cast<double>(fmaxf(v, 0.0f) - v * z + log1pf(expf(-fabsf(v))));
+    const float g = (1.0f / (1.0f + expf(-v)) - z) * inv;
+    if (dx) dx[e] = (accumulate ? dx[e] : 0.0f) + g;
+  }
+  part = block_sum(part);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, part * static_cast<double>(inv));
+}
+// mean |y - g| * scale ; dg = -sign(y - g) * scale / count
+__global__ void __launch_bounds__(256) l1_kernel(const float* y, const float* g, float scale, double* loss, float* dg,
+                                                  long long count, int accumulate) {
+  double part = 0.0;
+  const float inv = scale / static_cast<float>(count);
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < count; e += static_cast<long long>(gridDim.x) * 256) {
+    const float d = y[e] - g[e];
+    part += static_cast<double>(fabsf(d));
+    const float s = d > 0.0f ? -1.0f : (d < 0.0f ? 1.0f : 0.0f);
+    if (dg) dg[e] = (accumulate ? dg[e] : 0.0f) + s * inv;
+  }
+  part = block_sum(part);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, part * static_cast<double>(inv));
+}
+// tf.nn.l2_loss(a - b) * scale = 0.5 * sum (a-b)^2 * scale ; db = -(a - b) * scale
+__global__ void __launch_bounds__(256) l2half_kernel(const float* a, const float* b, float scale, double* loss, float* db,
+                                                      long long count, int accumulate) {
+  double part = 0.0;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < count; e += static_cast<long long>(gridDim.x) * 256) {
+    const float d = a[e] - b[e];
+    part += 0.5 * static_cast<double>(d) * d;
+    if (db) db[e] = (accumulate ? db[e] : 0.0f) - d * scale;
+  }
+  part = block_sum(part);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, part * static_cast<double>(scale));
+}
+
+// TF1 Adam ("epsilon hat"): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t * m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, float* m, float* v, long long count,
+                                                    float lr_t, float b1, float b2, float eps) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < count; e += static_cast<long long>(gridDim.x) * 256) {
+    const float gv = g[e];
+    const float mv = b1 * m[e] + (1.0f - b1) * gv;
+    const float vv = b2 * v[e] + (1.0f - b2) * gv * gv;
+    m[e] = mv;
+    v[e] = vv;
+    p[e] -= lr_t * mv / (sqrtf(vv) + eps);
+  }
+}
+
+// fully connected head [rows, nin] x [nin] -> [rows]: forward, dgrad, wgrad
+__global__ void __launch_bounds__(256) fc_fwd_kernel(const float* x, const float* w, const float* bias, float* y, int nin) {
+  double part = 0.0;
+  const float* xr = x + static_cast<size_t>(blockIdx.x) * nin;
+  for (int i = threadIdx.x; i < nin; i += 256) part += static_cast<double>(xr[i]) * w[i];
+  part = block_sum(part);
+  if (threadIdx.x == 0) y[blockIdx.x] = static_cast<float>(part) + bias[0];
+}
+__global__ void __launch_bounds__(256) fc_bwd_kernel(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                                                      float* dbias, int rows, int nin) {
+  // one thread per input feature: dx[r][i] = dy[r] * w[i]; dw[i] += sum_r dy[r] * x[r][i]
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < nin) {
+    float acc = 0.0f;
+    for (int r = 0; r < rows; ++r) {
+      const float d = dy[r];
+      if (dx) dx[static_cast<size_t>(r) * nin + i] = d * w[i];
+      acc = fmaf(d, x[static_cast<size_t>(r) * nin + i], acc);
+    }
+    dw[i] += acc;
+  }
+  if (i == 0) {
+    float s = 0.0f;
+    for (int r = 0; r < rows; ++r) s += dy[r];
+    dbias[0] += s;
+  }
+}
+
+// out[e] = in[e * cstride + c]  /  in-place strided scatter-add (channel extraction of the D input gradient)
+__global__ void __launch_bounds__(256) take_channel_kernel(const float* in, float* out, long long npix, int cstride, int c,
+                                                            int accumulate) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < npix; e += static_cast<long long>(gridDim.x) * 256)
+    out[e] = (accumulate ? out[e] : 0.0f) + in[e * cstride + c];
+}
+
+inline int grid_for(long long total, int sm) {
+  long long b = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm) * 8;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+}  // namespace mpg
+
+using namespace mpg;
+
+extern "C" {
+
+int mpg_train_conv_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int n, int hh, int ww,
+                       int cin, int cout, int k, int stride, int in_up, void* stream) {
+  MPG_CHECK_ARG(h && x && w && y && n > 0 && hh > 0 && ww > 0 && cin > 0 && cout > 0 && k > 0 && stride > 0 && in_up > 0,
+                "mpg_train_conv_fwd: bad argument");
+  ConvArgs a;
+  a.in = x;
+  a.w = w;
+  a.bias = bias;
+  a.out = y;
+  a.n = n;
+  a.h = hh;
+  a.w_ = ww;
+  a.cin = cin;
+  a.cout = cout;
+  a.k = k;
+  a.stride = stride;
+  a.pad = same_pad_before_tf(hh, k, stride);
+  a.oh = (hh + stride - 1) / stride;
+  a.ow = (ww + stride - 1) / stride;
+  a.in_up = in_up;
+  a.wmode = 0;
+  a.accumulate = 0;
+  dim3 grid(static_cast<unsigned>(n * ((a.oh + 7) / 8) * ((a.ow + 15) / 16)), static_cast<unsigned>((cout + kTC - 1) / kTC));
+  conv_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* dx[n,hh,ww,cin] (+)= dgrad of y = conv2d_SAME(x, w, stride) given dy[n,oh,ow,cout] */
+int mpg_train_conv_dgrad(mpg_handle h, const float* dy, const float* w, float* dx, int n, int hh, int ww, int cin,
+                         int cout, int k, int stride, int accumulate, void* stream) {
+  MPG_CHECK_ARG(h && dy && w && dx && n > 0 && cin > 0 && cout > 0 && k > 0 && stride > 0, "mpg_train_conv_dgrad: bad argument");
+  const int pad = same_pad_before_tf(hh, k, stride);
+  if (stride == 1) {
+    ConvArgs a;
+    a.in = dy;
+    a.w = w;
+    a.bias = nullptr;
+    a.out = dx;
+    a.n = n;
+    a.h = hh;
+    a.w_ = ww;
+    a.cin = cout;  // roles swap
+    a.cout = cin;
+    a.k = k;
+    a.stride = 1;
+    a.pad = k - 1 - pad;
+    a.oh = hh;
+    a.ow = ww;
+    a.in_up = 1;
+    a.wmode = 1;
+    a.accumulate = accumulate;
+    dim3 grid(static_cast<unsigned>(n * ((hh + 7) / 8) * ((ww + 15) / 16)), static_cast<unsigned>((cin + kTC - 1) / kTC));
+    conv_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    DgradArgs a;
+    a.dy = dy;
+    a.w = w;
+    a.dx = dx;
+    a.n = n;
+    a.h = hh;
+    a.w_ = ww;
+    a.cin = cin;
+    a.cout = cout;
+    a.k = k;
+    a.stride = stride;
+    a.pad = pad;
+    a.oh = (hh + stride - 1) / stride;
+    a.ow = (ww + stride - 1) / stride;
+    a.accumulate = accumulate;
+    dgrad_gather_kernel<<<grid_for(static_cast<long long>(n) * hh * ww * cin, h->sm_count), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(a);
+  }
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* dw[k,k,cin,cout] += wgrad ; dbias[cout] += sum dy (dbias may be NULL); `scratch`: >= cout doubles */
+int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* dw, float* dbias, double* scratch, int n,
+                         int hh, int ww, int cin, int cout, int k, int stride, int in_up, void* stream) {
+  MPG_CHECK_ARG(h && x && dy && dw && n > 0 && cin > 0 && cout > 0 && k > 0 && stride > 0 && in_up > 0,
+                "mpg_train_conv_wgrad: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradArgs a;
+  a.in = x;
+  a.dy = dy;
+  a.dw = dw;
+  a.n = n;
+  a.h = hh;
+  a.w_ = ww;
+  a.cin = cin;
+  a.cout = cout;
+  a.k = k;
+  a.stride = stride;
+  a.pad = same_pad_before_tf(hh, k, stride);
+  a.oh = (hh + stride - 1) / stride;
+  a.ow = (ww + stride - 1) / stride;
+  a.in_up = in_up;
+  const long long npix = static_cast<long long>(n) * a.oh * a.ow;
+  const int tiles = k * k * ((cin + 31) / 32) * ((cout + 63) / 64);
+  int splits = (h->sm_count * 4 + tiles - 1) / tiles;
+  if (splits < 1) splits = 1;
+  long long per = (npix + splits - 1) / splits;
+  per = (per + 31) / 32 * 32;
+  if (per < 32) per = 32;
+  splits = static_cast<int>((npix + per - 1) / per);
+  a.px_per_split = static_cast<int>(per);
+  wgrad_kernel<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits)), 256, 0, st>>>(a);
+  MPG_CUDA(cudaGetLastError());
+  if (dbias) {
+    MPG_CHECK_ARG(scratch != nullptr, "mpg_train_conv_wgrad: scratch missing");
+    MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * cout, st));
+    colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(dy, nullptr, nullptr, nullptr, scratch, npix, cout, 2);
+    dsum_to_f32_kernel<<<(cout + 255) / 256, 256, 0, st>>>(scratch, dbias, cout, 1);
+    MPG_CUDA(cudaGetLastError());
+  }
+  return MPG_OK;
+}
+
+/* training-mode batch norm (tf.contrib.layers.batch_norm, is_training=True, tools_wscale/GAN.py:110):
+ * batch mean / biased variance over all rows, y = act(gamma * (x - mean) * rsqrt(var + eps) + beta);
+ * moving statistics updated in place with `decay` when moving_mean != NULL. scratch: 2*c doubles. */
+int mpg_train_bn_fwd(mpg_handle h, const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                     float* var, float* invstd, float* moving_mean, float* moving_var, double* scratch, long long rows,
+                     int c, float eps, float decay, int act, void* stream) {
+  MPG_CHECK_ARG(h && x && gamma && beta && y && mean && var && invstd && scratch && rows > 0 && c > 0, "mpg_train_bn_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * c, st));
+  colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, rows, c, 0);
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, mean, var, invstd, moving_mean, moving_var, rows, c, eps, decay);
+  bn_apply_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, gamma, beta, mean, invstd, y, rows * c, c, act);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* backward of mpg_train_bn_fwd: dy is the gradient w.r.t. the activated output y; dgamma/dbeta accumulate.
+ * dz (scratch, rows*c floats, may alias dy) receives dy * act'(y). scratch: 2*c doubles. */
+int mpg_train_bn_bwd(mpg_handle h, const float* x, const float* y, const float* dy, const float* gamma, const float* mean,
+                     const float* invstd, float* dz, float* dx, float* dgamma, float* dbeta, double* scratch, long long rows,
+                     int c, int act, void* stream) {
+  MPG_CHECK_ARG(h && x && y && dy && gamma && mean && invstd && dz && dx && dgamma && dbeta && scratch, "mpg_train_bn_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  act_bwd_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(y, dy, dz, rows * c, act);
+  MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * c, st));
+  colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(x, dz, mean, invstd, scratch, rows, c, 1);
+  bn_bwd_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, dz, gamma, mean, invstd, scratch, dx, dgamma, dbeta, rows, c);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_train_act_fwd(mpg_handle h, const float* x, float* y, long long count, int act, void* stream) {
+  MPG_CHECK_ARG(h && x && y, "mpg_train_act_fwd: bad argument");
+  bias_act_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, count, act);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_add_act_fwd(mpg_handle h, const float* a, const float* b, float* y, long long count, int act, void* stream) {
+  MPG_CHECK_ARG(h && a && b && y, "mpg_train_add_act_fwd: bad argument");
+  add_act_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, y, count, act);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* dz = dy * act'(y) (dz may alias dy) */
+int mpg_train_act_bwd(mpg_handle h, const float* y, const float* dy, float* dz, long long count, int act, void* stream) {
+  MPG_CHECK_ARG(h && y && dy && dz, "mpg_train_act_bwd: bad argument");
+  act_bwd_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, dy, dz, count, act);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_axpy(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream) {
+  MPG_CHECK_ARG(h && x && y, "mpg_train_axpy: bad argument");
+  axpy_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, alpha, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* out = a * b elementwise (run-time weight scaling W_eff = v * wscale, tools_wscale/GAN.py:664-668, and its gradient) */
+int mpg_train_mul(mpg_handle h, float* out, const float* a, const float* b, long long count, void* stream) {
+  MPG_CHECK_ARG(h && out && a && b, "mpg_train_mul: bad argument");
+  mul_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, a, b, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* losses: *loss (device double) += value; d* (+)= gradient */
+int mpg_train_bce_logits(mpg_handle h, const float* logits, float label, float scale, double* loss, float* dlogits,
+                         long long count, int accumulate, void* stream) {
+  MPG_CHECK_ARG(h && logits && count > 0, "mpg_train_bce_logits: bad argument");
+  bce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, label, scale, loss, dlogits, count, accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_l1_mean(mpg_handle h, const float* y, const float* g, float scale, double* loss, float* dg, long long count,
+                      int accumulate, void* stream) {
+  MPG_CHECK_ARG(h && y && g && count > 0, "mpg_train_l1_mean: bad argument");
+  l1_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, g, scale, loss, dg, count, accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_l2_half(mpg_handle h, const float* a, const float* b, float scale, double* loss, float* db, long long count,
+                      int accumulate, void* stream) {
+  MPG_CHECK_ARG(h && a && b && count > 0, "mpg_train_l2_half: bad argument");
+  l2half_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, scale, loss, db, count, accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_train_adam(mpg_handle h, float* param, const float* grad, float* m, float* v, long long count, float lr_t,
+                   float beta1, float beta2, float eps, void* stream) {
+  MPG_CHECK_ARG(h && param && grad && m && v && count > 0, "mpg_train_adam: bad argument");
+  adam_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, m, v, count, lr_t, beta1, beta2, eps);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_train_fc_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int rows, int nin, void* stream) {
+  MPG_CHECK_ARG(h && x && w && bias && y && rows > 0 && nin > 0, "mpg_train_fc_fwd: bad argument");
+  fc_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, nin);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
+                     int rows, int nin, void* stream) {
+  MPG_CHECK_ARG(h && x && w && dy && dw && dbias && rows > 0 && nin > 0, "mpg_train_fc_bwd: bad argument");
+  fc_bwd_kernel<<<(nin + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, dy, dx, dw, dbias, rows, nin);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long npix, int cstride, int c, int accumulate,
+                           void* stream) {
+  MPG_CHECK_ARG(h && in && out && npix > 0 && c >= 0 && c < cstride, "mpg_train_take_channel: bad argument");
+  take_channel_kernel<<<grid_for(npix, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, npix, cstride, c, accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+}  // extern "C"

@@ -65,6 +65,15 @@ def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final
     return out
 
 
+def allreduce_mean(flat, group=None):
+    """Data-parallel gradient exchange of the training step: ONE all-reduce over the flat gradient buffer of an
+    optimizer, averaged over the ranks (each rank draws its own tile batch; BN batch statistics stay per rank)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / dist.get_world_size(group))
+    return flat
+
+
 def init_from_env(device_index=None):
     """One process per GPU under torchrun: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env."""
     import os

@@ -125,8 +125,13 @@ class GAN(object):
         if train:
             y, mean, var = tf_ops.batch_norm_training(x, gamma, beta)
             d = self.bn_decay
-            self.ctx.bn_updates[mm_name] = mm * d + mean.detach() * (1 - d)
-            self.ctx.bn_updates[mv_name] = mv * d + var.detach() * (1 - d)
+            # assign_moving_average: a scope that is evaluated twice in one step (the discriminator on real and on
+            # generated input, GAN/multipassGAN-4x.py:729-730) updates the same variables twice; TF leaves the order
+            # of the two UPDATE_OPS undefined - this oracle applies them in graph-construction order (real, fake)
+            mm_cur = self.ctx.bn_updates.get(mm_name, mm.detach())
+            mv_cur = self.ctx.bn_updates.get(mv_name, mv.detach())
+            self.ctx.bn_updates[mm_name] = mm_cur * d + mean.detach() * (1 - d)
+            self.ctx.bn_updates[mv_name] = mv_cur * d + var.detach() * (1 - d)
             return y
         return tf_ops.batch_norm_inference(x, gamma, beta, mm, mv)
 

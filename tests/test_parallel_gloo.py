@@ -75,3 +75,30 @@ def test_sharded_two_pass_equals_single_rank(tmp_path, world):
     mp.spawn(_worker, args=(world, port, S, ref_path, str(tmp_path)), nprocs=world, join=True)
     parts = [np.load(str(tmp_path / ("out_%d.npy" % r))) for r in range(world)]
     assert np.array_equal(np.concatenate(parts, axis=0), single)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import parallel as par
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1) + 0.25 * rank  # this rank's flat gradient buffer
+    par.allreduce_mean(g)
+    np.save(os.path.join(out_dir, "g_%d.npy" % rank), g.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_gradient_exchange_is_the_rank_mean(tmp_path):
+    """Data-parallel training step: one all-reduce over the flat gradient, averaged (parallel.allreduce_mean)."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_grad_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    base = np.arange(1000, dtype=np.float32)
+    want = (base * 1 + base * 2 + 0.25) / 2
+    for r in range(world):
+        np.testing.assert_allclose(np.load(str(tmp_path / ("g_%d.npy" % r))), want, rtol=1e-6)

@@ -1,0 +1,106 @@
+"""GPU parity of the 4x training step (generator + spatial discriminator fwd/bwd, losses, TF1 Adam, BN moving
+averages) against the fp64 autograd oracle (oracle/training.py), through the C ABI (mpg_train_*)."""
+import numpy as np
+import pytest
+import torch
+
+import mpgan_b200  # noqa: F401
+from mpgan_b200 import capi, training as T
+from oracle import networks as on, training as ot
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.mark.parametrize("bn", [True, False])
+def test_training_iteration_matches_oracle(bn):
+    L, u, B = 8, 4, 4
+    S = L * u
+    rng = np.random.default_rng(5)
+    hp = dict(kk=5.0, kk2=1e-5, seed=9, weight_dld=1.0)
+    batches = [(rng.random((B, L * L * 4), dtype=np.float32), rng.random((B, S * S), dtype=np.float32)) for _ in range(2)]
+    tr = T.Trainer4x(L, u, B, seed=9, batch_norm=bn)
+    values = {k: v.copy() for k, v in tr.values().items()}
+    cfg = on.make_cfg_4x(L, upRes=u, upsampling_mode=2, batch_norm=bn)
+    od, og_ = ot.Adam(2e-4, 0.5), ot.Adam(2e-4, 0.5)
+    for it in range(2):  # two iterations: the second one exercises non-zero Adam moments and moved BN statistics
+        ref = ot.train_iteration(values, [batches[it]], [batches[it]], cfg, hp, od, og_)
+        got = tr.iteration([batches[it]], [batches[it]], kk=hp["kk"], kk2=hp["kk2"])
+        assert abs(got["disc_loss"] - ref["disc_loss"]) <= 1e-4 * max(1.0, abs(ref["disc_loss"])), (got, ref)
+        assert abs(got["gen_loss"] - ref["gen_loss"]) <= 1e-4, (got, ref)
+        assert abs(got["gen_loss_complete"] - ref["gen_loss_complete"]) <= 2e-4 * max(1.0, abs(ref["gen_loss_complete"])), (got, ref)
+        gg = tr.grads("g")
+        for name, g in ref["grads_g"].items():
+            scale = np.abs(g).max()
+            if scale < 1e-12:
+                continue
+            assert _rel(gg[name], g) <= 2e-3, (it, name, _rel(gg[name], g))
+        now = tr.values()
+        lr = 2e-4
+        ref_g = dict(ref["grads_d"])
+        ref_g.update(ref["grads_g"])
+        for name, v in values.items():
+            d = np.abs(now[name].astype(np.float64) - np.asarray(v, np.float64))
+            if name.endswith(("moving_mean", "moving_variance")):
+                assert d.max() <= 1e-5 * max(1.0, np.abs(v).max()), (it, name, d.max())
+            else:
+                # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is ~0 may differ by 2 lr
+                assert d.max() <= 2.2 * lr * (it + 1), (it, name, d.max())
+                # a bias in front of a batch norm has a mathematically zero gradient: fp32 rounding noise of the size
+                # of Adam's epsilon makes it random-walk by < lr per step (TF fp32 does the same) - only bounded above
+                if np.abs(ref_g[name]).max() > 1e-9:
+                    assert (d > 2e-6).sum() <= max(2, 0.02 * d.size), (it, name, int((d > 2e-6).sum()), d.size)
+
+
+def test_adam_kernel_tf1_form():
+    h = capi.default_handle(0)
+    n = 1000
+    rng = np.random.default_rng(0)
+    p, g = rng.standard_normal(n).astype(np.float32), (rng.standard_normal(n) * 1e-3).astype(np.float32)
+    m, v = rng.random(n).astype(np.float32) * 1e-3, rng.random(n).astype(np.float32) * 1e-6
+    dp, dg, dm, dv = [torch.from_numpy(a.copy()).cuda() for a in (p, g, m, v)]
+    capi.train_call("adam", h, dp, dg, dm, dv, n, 1.5e-4, 0.5, 0.999, 1e-8, 0)
+    m2 = 0.5 * m.astype(np.float64) + 0.5 * g
+    v2 = 0.999 * v.astype(np.float64) + 0.001 * g.astype(np.float64) ** 2
+    ref = p - 1.5e-4 * m2 / (np.sqrt(v2) + 1e-8)
+    np.testing.assert_allclose(dp.cpu().numpy(), ref, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(dm.cpu().numpy(), m2, rtol=1e-5)
+
+
+def test_train_conv_kernels_vs_torch_autograd():
+    """fwd / dgrad / wgrad of every conv geometry of the training graphs vs torch autograd (fp64 on CPU)."""
+    h = capi.default_handle(0)
+    from oracle import tf_ops
+    rng = np.random.default_rng(1)
+    for (n, hh, cin, cout, k, s, up) in [(2, 16, 4, 8, 5, 1, 4), (2, 16, 8, 32, 5, 1, 1), (1, 16, 32, 128, 1, 1, 1),
+                                          (2, 16, 2, 32, 4, 2, 1), (2, 8, 64, 128, 4, 2, 1), (2, 8, 128, 256, 4, 1, 1),
+                                          (2, 12, 2, 1, 5, 1, 1)]:
+        sh = hh // up
+        x = rng.standard_normal((n, sh, sh, cin)).astype(np.float32)
+        w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+        b = rng.standard_normal(cout).astype(np.float32)
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+        xu = tf_ops.resize_nearest(xt, hh, hh) if up > 1 else xt
+        yt = tf_ops.conv2d_same(xu, wt, s) + torch.tensor(b, dtype=torch.float64)
+        dy = rng.standard_normal(tuple(yt.shape)).astype(np.float32)
+        yt.backward(torch.tensor(dy, dtype=torch.float64))
+        oh = yt.shape[1]
+        dx_, dw_, dy_d = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(dy).cuda()
+        y_d = torch.empty((n, oh, oh, cout), device="cuda")
+        capi.train_call("conv_fwd", h, dx_, dw_, torch.from_numpy(b).cuda(), y_d, n, hh, hh, cin, cout, k, s, up, 0)
+        assert _rel(y_d.cpu().numpy(), yt.detach().numpy()) < 1e-5, ("fwd", cin, cout, k, s)
+        gw = torch.zeros_like(dw_)
+        gb = torch.zeros(cout, device="cuda")
+        scratch = torch.zeros(1024, dtype=torch.float64, device="cuda")
+        capi.train_call("conv_wgrad", h, dx_, dy_d, gw, gb, scratch, n, hh, hh, cin, cout, k, s, up, 0)
+        assert _rel(gw.cpu().numpy(), wt.grad.numpy()) < 1e-5, ("wgrad", cin, cout, k, s)
+        assert _rel(gb.cpu().numpy(), dy.astype(np.float64).sum(axis=(0, 1, 2))) < 1e-5
+        if up == 1:
+            gx = torch.empty_like(dx_)
+            capi.train_call("conv_dgrad", h, dy_d, dw_, gx, n, hh, hh, cin, cout, k, s, 0, 0)
+            assert _rel(gx.cpu().numpy(), xt.grad.numpy()) < 1e-5, ("dgrad", cin, cout, k, s)
