@@ -51,8 +51,10 @@ def test_variable_split_and_losses():
         changed = not np.array_equal(before[n], values[n])
         if n.endswith(("moving_mean", "moving_variance")):
             assert changed, n
-        else:
-            assert changed == ot.is_d_var(n), n
+        elif not ot.is_d_var(n):
+            assert not changed, n
+        elif n.endswith("weight"):  # (a bias in front of a batch norm has zero gradient and may stay put)
+            assert changed, n
 
 
 def test_discriminator_variables_match_reference_code():
