@@ -179,6 +179,22 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
 int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tile cut / overlap-crop stitch of 2-D slices (tools_wscale/tilecreator_t.py: createTiles :403-434,
+ * cutTile :436-450, concatTiles :886-918).  Tiles are ordered (frame, tile row, tile column); NHWC, any
+ * 2- or 4-byte element type.
+ * -----------------------------------------------------------------------------------------*/
+/* number of tiles along one axis: (extent - tile) // stride + 1  (stride <= 0 means stride = tile) */
+int mpg_tiles_count(int extent, int tile, int stride);
+/* out[n*ty*tx, th+2*pad, tw+2*pad, c]: tile (iy,ix) starts at (iy*stride_y, ix*stride_x); stride < tile gives
+ * overlapping tiles; pad > 0 replicates the tile's own edge pixels (np.pad(tile, 'edge')). */
+int mpg_tiles_cut(mpg_handle h, const void* in, void* out, int n, int hh, int ww, int c, int elem_bytes, int th,
+                  int tw, int stride_y, int stride_x, int pad, void* stream);
+/* out[n, ty*(th-2*border), tx*(tw-2*border), c]: crop `border` from every side of every tile and concatenate
+ * x, then y (concatTiles with tileBorder). */
+int mpg_tiles_stitch(mpg_handle h, const void* tiles, void* out, int n, int ty, int tx, int th, int tw, int c,
+                     int elem_bytes, int border, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training step of the 4x model (generator + spatial discriminator, GAN/multipassGAN-4x.py:528-620,
  * 744-768, 889-902, loop :1316-1397).  All tensors fp32 NHWC, weights HWIO fp32 in DEVICE memory
  * (Adam rewrites them every step).  `scratch` is caller-owned device memory of the stated size.

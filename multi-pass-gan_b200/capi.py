@@ -88,6 +88,9 @@ def lib():
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
     L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
+    L.mpg_tiles_count.argtypes = [ip, ip, ip]
+    L.mpg_tiles_cut.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_tiles_stitch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     ll, fl = ctypes.c_longlong, ctypes.c_float
     L.mpg_train_conv_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_train_conv_dgrad.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
@@ -305,3 +308,19 @@ def train_call(name, handle, *args):
     """Generic checked call of an mpg_train_* entry point; tensors are passed as torch tensors / None / ints."""
     conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr")) else a) for a in args]
     check(getattr(lib(), "mpg_train_" + name)(handle.ptr, *conv), "mpg_train_" + name)
+
+
+def tiles_count(extent, tile, stride):
+    return lib().mpg_tiles_count(int(extent), int(tile), int(stride))
+
+
+def tiles_cut(handle, src, dst, n, h, w, c, elem_bytes, th, tw, stride_y=-1, stride_x=-1, pad=0, stream=0):
+    """TileCreator.createTiles on device NHWC frames -> [n*ty*tx, th+2*pad, tw+2*pad, c]."""
+    check(lib().mpg_tiles_cut(handle.ptr, _ptr(src), _ptr(dst), int(n), int(h), int(w), int(c), int(elem_bytes), int(th),
+                              int(tw), int(stride_y), int(stride_x), int(pad), stream), "mpg_tiles_cut")
+
+
+def tiles_stitch(handle, tiles, dst, n, ty, tx, th, tw, c, elem_bytes, border=0, stream=0):
+    """TileCreator.concatTiles (tileBorder crop + concatenation) on device tiles."""
+    check(lib().mpg_tiles_stitch(handle.ptr, _ptr(tiles), _ptr(dst), int(n), int(ty), int(tx), int(th), int(tw), int(c),
+                                 int(elem_bytes), int(border), stream), "mpg_tiles_stitch")

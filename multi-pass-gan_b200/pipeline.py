@@ -235,8 +235,12 @@ class MultiPassOut:
     """generate3DUniForNewNetwork (GAN/multipassGAN-out.py:390-618) for one frame, on the device."""
 
     def __init__(self, L, weights, upRes=8, specs=None, precision="fp16", transposeAxis=0, batches=(8, 2, 2),
-                 device=0, threshold=THRESHOLD, **cfg_kw):
+                 device=0, threshold=THRESHOLD, rank=0, world=1, group=None, **cfg_kw):
+        """With world > 1 (generators 1+2, transposeAxis 0: the shipped 8x two-pass recipe) the volume is sharded by
+        slice: z-slabs in pass 1, x-slabs in pass 2, one all-to-all per axis change; `__call__` then returns this
+        rank's canonical z-slab [S/G, S, S]."""
         self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
+        self.rank, self.world, self.group = int(rank), int(world), group
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
         self.specs = specs or SHIPPED_8X
@@ -248,12 +252,16 @@ class MultiPassOut:
         f32 = dict(dtype=torch.float32, device=self.device)
         self.passes = {}
         self.flops = 0.0
+        if self.world > 1 and (self.nets != [1, 2] or self.ta != 0):
+            raise NotImplementedError("slice sharding is implemented for generators 1+2 with transposeAxis 0")
+        self.s0, self.s1 = par.slab_range(self.rank, self.world, S)
+        self.S_loc = self.s1 - self.s0
         for idx in self.nets:
             spec = self.specs[idx]
             if self.ta not in _PASS_GEOM[idx]:
                 raise NotImplementedError("transposeAxis %d is a dead branch for generator %d (App. D.7)" % (self.ta, idx))
             axis_of, chans = _PASS_GEOM[idx][self.ta]
-            B = _pick_batch(S, batches[idx - 1])
+            B = _pick_batch(self.S_loc, batches[idx - 1])
             pn = _PassNet(self.h, lambda idx=idx, spec=spec: build_out_graph(idx, spec, self.cfg), weights[idx], B,
                           precision)
             adj = bool(spec.add_adj_idcs) and idx == 1
@@ -261,12 +269,40 @@ class MultiPassOut:
             desc = capi.make_assemble_desc((L, L, L), 4, axis_of, (u, 1, 1), chans, None, add_adj=adj,
                                            out_dtype=capi.F32, out_cstride=cin)
             self.passes[idx] = dict(net=pn, desc=desc, batch=B, inbuf=torch.empty((B, L, L, cin), **f32))
-            self.flops += pn.net.flops / B * S
-        self.vol_rows = torch.empty((S, S, S), **f32)
-        self.vol_dim = torch.empty((S, S, S), **f32)
+            self.flops += pn.net.flops / B * self.S_loc  # this rank's share
+        self.vol_rows = torch.empty((self.S_loc, S, S), **f32)
+        self.vol_dim = torch.empty((self.S_loc, S, S), **f32)
+        if self.world > 1:
+            self.scr_a = torch.empty((self.S_loc, S, S), **f32)
+            self.scr_b = torch.empty((self.S_loc, S, S), **f32)
+
+    def _permute3(self, src, dst, dims, perm, thr):
+        capi.transpose3d(self.h, src, dst, dims, perm, thr, torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call_sharded(self, x):
+        """Generators 1+2 on this rank's slices (App. C): rows [Zu_loc,Yu,Xu] -> all-to-all -> dim_output slab
+        [Xu_loc,Yu,Zu] (= the `y` feeds of pass 2, :459) -> rows [Xu_loc,Yu,Zu] -> all-to-all -> [Zu_loc,Yu,Xu]
+        (the composition of :521 and :587-590 is .transpose(2,1,0) of the pass-2 rows), threshold fused (:612-615)."""
+        S = self.S
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        vol = _dev_f32(x, self.device)
+        rows, dim = self.vol_rows, self.vol_dim
+        p = self.passes[1]
+        for s in range(self.s0, self.s1, p["batch"]):
+            capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
+            p["net"].net.run({"x": p["inbuf"]}, out=rows[s - self.s0], stream=st)
+        par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), 0.0)
+        p = self.passes[2]
+        for s in range(self.s0, self.s1, p["batch"]):
+            capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
+            p["net"].net.run({"x": p["inbuf"], "y": dim[s - self.s0]}, out=rows[s - self.s0], stream=st)
+        par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), self.threshold)
+        return dim
 
     def __call__(self, x):
         """x: [L,L,L,4] float32, velocities already scaled by velScale (GAN/multipassGAN-out.py:138)."""
+        if self.world > 1:
+            return self._call_sharded(x)
         S = self.S
         st = torch.cuda.current_stream(self.device).cuda_stream
         vol = _dev_f32(x, self.device)

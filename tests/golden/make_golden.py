@@ -317,7 +317,56 @@ def make_net_fixtures():
     print("nets.npz written:", len(fixtures), "arrays")
 
 
+def ref_methods(path, cls, names):
+    """The named methods of a reference class, compiled as plain functions."""
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    c = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls][0]
+    picked = [n for n in c.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in picked} == set(names)
+    return compile(ast.Module(body=picked, type_ignores=[]), path, "exec")
+
+
+def make_tile_fixtures():
+    """TileCreator.createTiles / cutTile / concatTiles (tools_wscale/tilecreator_t.py; the module itself cannot be
+    imported on py3.12 - `import imp` - so the three methods are compiled on their own and bound to a stub self)."""
+    code = ref_methods(os.path.join(REF, "tools_wscale", "tilecreator_t.py"), "TileCreator",
+                       ["createTiles", "cutTile", "concatTiles"])
+    ns = dict(np=np)
+    exec(code, ns)
+
+    class Stub:
+        def __init__(self, padding):
+            self.padding = padding
+
+        def TCError(self, msg):
+            raise RuntimeError(msg)
+
+    for name in ("createTiles", "cutTile", "concatTiles"):
+        setattr(Stub, name, ns[name])
+    rng = np.random.default_rng(77)
+    frame = rng.random((1, 24, 40, 3), dtype=np.float32)
+    out = {"frame": frame}
+    # regular grid and overlapping grid (stride < tile).  padding > 0 is NOT pinned: the reference's
+    # np.pad(currTile, [p,p,p,0], 'edge') (tilecreator_t.py:430) raises for a 4-D tile in numpy, i.e. the branch never ran
+    for tag, (tile, stride, pad) in {"reg": ([1, 8, 8], -1, 0), "ovl": ([1, 12, 16], 4, 0), "ovl2": ([1, 8, 10], 6, 0)}.items():
+        t = Stub(pad).createTiles(frame, list(tile), stride)
+        out["tiles_" + tag] = np.asarray(t, np.float32)
+    # stitch: 2 x 3 tiles of 12 x 16 with a 2-pixel border cropped (and the uncropped variant)
+    tiles = rng.random((6, 1, 12, 16, 3), dtype=np.float32)
+    out["stitch_in"] = tiles
+    out["stitch_b2"] = np.asarray(Stub(0).concatTiles(tiles, [1, 2, 3], [0, 2, 2, 0]), np.float32)
+    out["stitch_b0"] = np.asarray(Stub(0).concatTiles(tiles, [1, 2, 3], [0, 0, 0, 0]), np.float32)
+    np.savez_compressed(os.path.join(HERE, "tiles.npz"), **out)
+    print("tiles.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
-    make_pipeline_fixtures()
-    make_net_fixtures()
+    which = sys.argv[1:] or ["pipeline", "nets", "tiles"]
+    if "pipeline" in which:
+        make_pipeline_fixtures()
+    if "nets" in which:
+        make_net_fixtures()
+    if "tiles" in which:
+        make_tile_fixtures()

@@ -148,3 +148,18 @@ def test_gen_resnet_and_disc_match_reference_code(nets, tag):
     _close(d[0].numpy(), nets[tag + "_disc_logits"])
     for i in range(1, 5):
         _close(d[i].numpy(), nets[tag + "_disc_d%d" % i])
+
+
+# ------------------------------------------------------------------------------ tiles (a19)
+def test_tile_cut_and_stitch_match_reference_code():
+    from oracle import tiles as otl
+    g = np.load(os.path.join(GOLD, "tiles.npz"))
+    frame = g["frame"]
+    for tag, (tile, stride, pad) in {"reg": ([1, 8, 8], -1, 0), "ovl": ([1, 12, 16], 4, 0), "ovl2": ([1, 8, 10], 6, 0)}.items():
+        np.testing.assert_array_equal(otl.create_tiles(frame, tile, stride, pad), g["tiles_" + tag])
+    # edge padding (not pinned, see make_golden.py): the tile's own border pixels are replicated in y and x
+    t = otl.create_tiles(frame, [1, 8, 10], 6, 2)
+    assert t.shape[1:] == (1, 12, 14, 3) and np.array_equal(t[:, :, 2:-2, 2:-2], g["tiles_ovl2"])
+    assert np.array_equal(t[:, :, 0, 2:-2], g["tiles_ovl2"][:, :, 0]) and np.array_equal(t[:, :, 2:-2, -1], g["tiles_ovl2"][:, :, :, -1])
+    np.testing.assert_array_equal(otl.concat_tiles(g["stitch_in"], [1, 2, 3], (0, 2, 2, 0)), g["stitch_b2"])
+    np.testing.assert_array_equal(otl.concat_tiles(g["stitch_in"], [1, 2, 3]), g["stitch_b0"])

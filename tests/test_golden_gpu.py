@@ -139,3 +139,32 @@ def test_4x_two_pass_pipeline_vs_reference_code(pipe):
     assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
     p1 = mp.pass1_only(x).cpu().numpy()
     assert np.abs(p1 - pipe["x4_p1_vol"]).max() <= 2e-5 * max(1.0, np.abs(pipe["x4_p1_vol"]).max())
+
+
+# ------------------------------------------------------------------------------ tiles (a19)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_tile_cut_and_stitch_vs_reference_code(dtype):
+    from mpgan_b200 import capi
+    g = np.load(os.path.join(GOLD, "tiles.npz"))
+    h = capi.default_handle(0)
+    frame = torch.from_numpy(g["frame"]).to(dtype).cuda()  # [1, 24, 40, 3]
+    eb = frame.element_size()
+    from oracle import tiles as otl
+    for tag, (th, tw, stride, pad) in {"reg": (8, 8, -1, 0), "ovl": (12, 16, 4, 0), "ovl2": (8, 10, 6, 0), "pad": (8, 10, 6, 2)}.items():
+        if tag == "pad":  # edge padding: checked against the oracle (the reference branch raises, see make_golden.py)
+            ref = torch.from_numpy(otl.create_tiles(g["frame"], [1, th, tw], stride, pad)).to(dtype)
+        else:
+            ref = torch.from_numpy(g["tiles_" + tag]).to(dtype)  # [tiles, 1, th, tw, 3]
+        ty, tx = capi.tiles_count(24, th, stride), capi.tiles_count(40, tw, stride)
+        assert ty * tx == ref.shape[0]
+        out = torch.empty((ty * tx, th + 2 * pad, tw + 2 * pad, 3), dtype=dtype, device="cuda")
+        capi.tiles_cut(h, frame, out, 1, 24, 40, 3, eb, th, tw, stride, stride, pad)
+        assert torch.equal(out.cpu(), ref[:, 0])
+    tiles = torch.from_numpy(g["stitch_in"]).to(dtype).cuda()  # [6, 1, 12, 16, 3]
+    for border, key in ((2, "stitch_b2"), (0, "stitch_b0")):
+        ref = torch.from_numpy(g[key]).to(dtype)
+        out = torch.empty(tuple(ref.shape), dtype=dtype, device="cuda")
+        capi.tiles_stitch(h, tiles, out, 1, 2, 3, 12, 16, 3, eb, border)
+        assert torch.equal(out.cpu(), ref)
+    with pytest.raises(capi.MpgError):
+        capi.tiles_cut(h, frame, frame, 1, 24, 40, 3, eb, 64, 8)  # tile larger than the frame (TilecreatorError role)

@@ -14,10 +14,17 @@ from mpgan_b200 import parallel as par, pipeline as P, synth
 rank, local, world = par.init_from_env()
 torch.cuda.set_device(local)
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+which = sys.argv[2] if len(sys.argv) > 2 else "4x"
 x = synth.synthetic_volume(L, seed=5)
-w1, w2 = P.make_weights_4x(L, 5, randomize_bn=True)
-single = P.MultiPass4x(L, w1, w2, precision="fp16", device=local)(x).clone()
-mp = P.MultiPass4x(L, w1, w2, precision="fp16", device=local, rank=rank, world=world)
+if which == "4x":
+    w1, w2 = P.make_weights_4x(L, 5, randomize_bn=True)
+    single = P.MultiPass4x(L, w1, w2, precision="fp16", device=local)(x).clone()
+    mp = P.MultiPass4x(L, w1, w2, precision="fp16", device=local, rank=rank, world=world)
+else:  # the shipped 8x two-pass recipe (GAN/example_run_output.py:18-48) with small feature counts
+    specs = {1: P.NetSpec(True, True, 64, 64, 3, True), 2: P.NetSpec(True, False, 48, 48, 5)}
+    w = P.make_weights_out(L, 5, upRes=8, specs=specs, nets=(1, 2))
+    single = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local)(x).clone()
+    mp = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local, rank=rank, world=world)
 part = mp(x)
 torch.cuda.synchronize()
 ref = single[mp.s0:mp.s1]
