@@ -275,6 +275,8 @@ class MultiPassOut:
         if self.world > 1:
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
+        self.launches_per_frame = sum((self.S_loc // p["batch"]) * (p["net"].net.launches + 1) for p in self.passes.values()) \
+            + (len(self.nets) + 3 if self.world == 1 else 4)
 
     def _permute3(self, src, dst, dims, perm, thr):
         capi.transpose3d(self.h, src, dst, dims, perm, thr, torch.cuda.current_stream(self.device).cuda_stream)
