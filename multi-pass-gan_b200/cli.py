@@ -1,0 +1,138 @@
+"""Drop-in command line of `GAN/multipassGAN-out.py` (the apply-model entry point) on the B200 path.
+
+    python multipassGAN-out.py  key value  key value ...        (flags: GAN/multipassGAN-out.py:28-99, App. E)
+
+Same flag grammar as the reference's paramhelpers (`name value` pairs, names case-insensitive, values strings,
+an unknown / unused flag aborts with exit code 1: tools_wscale/paramhelpers.py:16-37), same input files
+(`packedSimPath/sim_%04d/density_low_%04d.uni` + `velocity_low_%04d.uni`, frames [frame_min, frame_max)) and the
+same output files (`packedSimPath/sim_%04d/source_%04d.uni`, GAN/multipassGAN-out.py:616).  Differences:
+  * weights: the reference can only restore TF1 checkpoints (:367-386); a checkpoint reader is not part of this
+    build, so `randomInit <seed>` selects deterministic random-init weights and `weightsNpz <file>`
+    loads a {variable name: array} archive with the reference's checkpoint keys.  Asking for a checkpoint without
+    either aborts.
+  * PNG previews (scipy.misc.imsave, gone from scipy) are not written.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+
+class Params:
+    """tools_wscale/paramhelpers.py:16-37 semantics on an explicit argv."""
+
+    def __init__(self, argv):
+        self.argv = list(argv)
+        self.used = [0] * len(self.argv)
+        self.values = {}
+
+    def get(self, name, default):
+        v = default
+        for i in range(1, len(self.argv)):
+            if self.argv[i].lower() == name.lower() and i + 1 < len(self.argv):
+                self.used[i] = self.used[i + 1] = 1
+                v = self.argv[i + 1]
+        self.values[name] = v
+        return v
+
+    def check_unused(self):
+        bad = [(i, a) for i, a in enumerate(self.argv) if i >= 1 and not self.used[i]]
+        for i, a in bad:
+            print("Error: param %d '%s' not used!" % (i, a))
+        if bad:
+            raise SystemExit(1)
+
+
+def load_frames(sim_path, frame_min, frame_max, use_velocities, vel_scale):
+    """FluidDataLoader with multi_file_list ['density','velocity'] (GAN/multipassGAN-out.py:116-138): frames
+    [Z,Y,X,C], C = (d, vx, vy, vz); velocity channels scaled by velScale (:138)."""
+    from . import uni
+    frames, head0 = [], None
+    for f in range(frame_min, frame_max):
+        head, dens = uni.read_uni(os.path.join(sim_path, "density_low_%04d.uni" % f))
+        head0 = head0 or head
+        chans = [dens.astype(np.float32)]
+        if use_velocities:
+            _, vel = uni.read_uni(os.path.join(sim_path, "velocity_low_%04d.uni" % f))
+            chans.append(vel.astype(np.float32) * np.float32(vel_scale))
+        frames.append(np.concatenate(chans, axis=-1))
+    return frames, head0
+
+
+def main(argv=None):
+    argv = sys.argv if argv is None else argv
+    ph = Params(argv)
+    g = ph.get
+    out_flag = int(g("out", 1))
+    basePath = g("basePath", "../2ddata_gan/")
+    randSeed = int(g("randSeed", 1))
+    load = {i: (int(g("load_model_test_%d" % i, -1)), int(g("load_model_no_%d" % i, -1))) for i in (1, 2, 3)}
+    simSizeLow = int(g("simSize", 64))
+    tileSizeLow = int(g("tileSize", 16))
+    upRes = int(g("upRes", 4))
+    packedSimPath = g("packedSimPath", "../2ddata_sim/")
+    fromSim = int(g("fromSim", 1000))
+    frame_min = int(g("frame_min", 0))
+    for name in ("genModel", "discModel", "testPathStartNo", "change_velocity", "upsamplingMode", "upsampledData", "gpu",
+                 "useVorticities", "useFlags", "useK_Eps_Turb", "usePixelShuffle", "use_mb_stddev", "loadEmas"):
+        g(name, 0)  # accepted for compatibility; they do not change the shipped apply path
+    batch_norm = int(g("batchNorm", 0)) != 0
+    pixel_norm = int(g("pixelNorm", 1)) != 0
+    useVelocities = int(g("useVelocities", 0))
+    transposeAxis = int(g("transposeAxis", 0))
+    frame_max = int(g("frame_max", 200))
+    genUni = int(g("genUni", 0))
+    addBicubic = int(g("addBicubicUpsample", 0)) != 0
+    firstNNArch = int(g("firstNNArch", 1)) != 0
+    upsampleMode = int(g("upsampleMode", 1))
+    velScale = float(g("velScale", 1.0))
+    specs = {}
+    from . import pipeline as P
+    for i in (1, 2, 3):
+        specs[i] = P.NetSpec(use_res_net=int(g("use_res_net%d" % i, 0)) != 0, add_adj_idcs=int(g("add_adj_idcs%d" % i, 0)) != 0,
+                             startFms=int(g("startFms%d" % i, 512)), maxFms=int(g("maxFms%d" % i, 256)),
+                             filterSize=int(g("filterSize%d" % i, 3)), first_nn_arch=(firstNNArch and i == 1))
+    random_init = g("randomInit", None)        # extension, see module docstring
+    weights_npz = g("weightsNpz", None)        # extension
+    precision = g("precision", "fp16")         # extension: fp16 | bf16 | fp32
+    ph.check_unused()
+    if tileSizeLow != simSizeLow:
+        raise SystemExit("multipassGAN-out: the apply path slices whole frames (tileSize must equal simSize, as in "
+                         "GAN/example_run_output.py)")
+    nets = tuple(i for i in (1, 2, 3) if load[i][0] != -1)
+    if not nets:
+        print("At least one network has to be loaded.")
+        raise SystemExit(1)
+    if not useVelocities:
+        raise SystemExit("multipassGAN-out: the shipped generators take (density, vx, vy, vz): useVelocities 1 is required")
+    import torch
+    if weights_npz:
+        arch = np.load(weights_npz)
+        weights = {i: {k: arch[k] for k in arch.files if k.startswith("gen_%d/" % i)} for i in nets}
+    elif random_init is not None:
+        weights = P.make_weights_out(simSizeLow, int(random_init), upRes=upRes, specs=specs, nets=nets,
+                                     pixel_norm=pixel_norm, batch_norm=batch_norm, upsampleMode=upsampleMode,
+                                     addBicubicUpsample=addBicubic)
+    else:
+        raise SystemExit("multipassGAN-out: restoring TF1 checkpoints (%stest_%04d/model_%04d.ckpt) is not implemented; "
+                         "pass `randomInit <seed>` or `weightsNpz <file>`" % (basePath, load[nets[0]][0], load[nets[0]][1]))
+    sim_path = os.path.join(packedSimPath, "sim_%04d" % fromSim)
+    frames, head = load_frames(sim_path, frame_min, frame_max, useVelocities, velScale)
+    mp = P.MultiPassOut(simSizeLow, weights, upRes=upRes, specs=specs, precision=precision, transposeAxis=transposeAxis,
+                        threshold=P.THRESHOLD if genUni else 0.0, pixel_norm=pixel_norm, batch_norm=batch_norm,
+                        upsampleMode=upsampleMode, addBicubicUpsample=addBicubic)
+    S = simSizeLow * upRes
+    print("*****OUTPUT ONLY*****")
+    from . import uni
+    for n, x in enumerate(frames):
+        t0 = time.time()
+        vol = mp(x)
+        torch.cuda.synchronize()
+        print("%d  time for %d network(s): %.6f" % (frame_min + n, len(nets), time.time() - t0))
+        if genUni:
+            head = dict(head)
+            head["dimX"] = head["dimY"] = head["dimZ"] = S  # GAN/multipassGAN-out.py:608-610
+            uni.write_uni(os.path.join(sim_path, "source_%04d.uni" % (frame_min + n)), head, vol.cpu().numpy())
+            print("stored .uni file")
+    return 0

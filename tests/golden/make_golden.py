@@ -361,12 +361,35 @@ def make_tile_fixtures():
     print("tiles.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_uni_fixtures():
+    """Two small grids written by the reference's own tools_wscale/uniio.writeUni (importable as-is)."""
+    spec = importlib.util.spec_from_file_location("ref_uniio", os.path.join(REF, "tools_wscale", "uniio.py"))
+    uniio = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(uniio)
+    rng = np.random.default_rng(3)
+    dens = rng.random((3, 4, 5, 1), dtype=np.float32)
+    vel = rng.standard_normal((3, 4, 5, 3)).astype(np.float32)
+    from collections import OrderedDict
+    def head(et):
+        return OrderedDict([("dimX", 5), ("dimY", 4), ("dimZ", 3), ("gridType", 1 if et == 1 else 4), ("elementType", et),
+                            ("bytesPerElement", 12 if et == 2 else 4), ("info", b"mantaflow test grid".ljust(252, b"\0")),
+                            ("dimT", 0), ("timestamp", 1234567890123)])
+    uniio.writeUni(os.path.join(HERE, "ref_density.uni"), head(1), dens)
+    uniio.writeUni(os.path.join(HERE, "ref_velocity.uni"), head(2), vel)
+    h, d = uniio.readUni(os.path.join(HERE, "ref_density.uni"))
+    assert np.array_equal(d, dens)
+    np.savez_compressed(os.path.join(HERE, "uni.npz"), dens=dens, vel=vel)
+    print("ref_density.uni / ref_velocity.uni / uni.npz written")
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
-    which = sys.argv[1:] or ["pipeline", "nets", "tiles"]
+    which = sys.argv[1:] or ["pipeline", "nets", "tiles", "uni"]
     if "pipeline" in which:
         make_pipeline_fixtures()
     if "nets" in which:
         make_net_fixtures()
     if "tiles" in which:
         make_tile_fixtures()
+    if "uni" in which:
+        make_uni_fixtures()
