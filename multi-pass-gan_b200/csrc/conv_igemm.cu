@@ -61,7 +61,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const IgemmParams& p) {
 // halves, so the L2->SM weight traffic per SM halves (measured: an SM ingests ~27 B/clk from L2, which bounds
 // the single-CTA kernel at 970 KB per tile vs 26 K MMA cycles).
 template <int CK, bool PAIR>
-__global__ void __launch_bounds__(kIgThreads, 1)
+__global__ void __launch_bounds__(kIgMaxThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
                   const IgemmParams p) {
@@ -92,7 +92,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 #define MPG_TILE_LOOP(t) for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep)
 #define MPG_TILE_CLAMP(t) ((t) < p.num_tiles ? (t) : p.num_tiles - 1)
 
-  for (int i = threadIdx.x; i < p.npad; i += kIgThreads) s_shift[i] = p.shift[i];
+  for (int i = threadIdx.x; i < p.npad; i += blockDim.x) s_shift[i] = p.shift[i];
+  // epilogue warps: 4 (256-thread launch) or 8 (384-thread launch: two warps per TMEM lane quarter split the columns)
+  const int n_epi_warps = (static_cast<int>(blockDim.x) >> 5) - 4;
+  const int epi_active = (n_epi_warps == 8 && !p.pixel_norm && !p.tma_store) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
@@ -109,7 +112,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in PAIR mode)
+      mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * epi_active);  // one arrive per active epilogue warp (both CTAs in PAIR mode)
     }
     fence_barrier_init();
   }
@@ -309,7 +312,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       if (elect_one()) { if (PAIR) umma_commit_2cta(&tmem_full[buf], 3); else umma_commit(&tmem_full[buf]); }
       __syncwarp();
     }
-  } else if (warp >= 4 && p.tma_store) {
+  } else if (warp >= 4 && warp < 8 && p.tma_store) {
     // ===================== epilogue A: TMEM -> registers -> swizzled smem -> TMA store =========
     // (16-bit outputs) each thread owns one pixel row of the accumulator; its 16-byte channel chunks
     // go to a staging tile laid out like a TMA box [128 px][box_c ch], one elected thread stores it.
@@ -404,7 +407,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       (void)cpb;
     }
     if (et == 0) tma_store_wait_all();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + epi_active && !p.tma_store) {
     // ===================== epilogue B (fp32 outputs): TMEM -> registers -> global ==============================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     const int m = ew * 32 + lane;
@@ -414,6 +417,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const int ups = p.upsample;
     const int oh = p.h * ups, ow = p.w * ups;
     const float inv_c = 1.0f / static_cast<float>(p.cout);
+    const int nchunk16 = p.npad >> 4;
+    const int csplit = (epi_active == 8) ? ((nchunk16 + 1) >> 1) * 16 : p.npad;
+    const int cbeg = (warp >= 8) ? csplit : 0;
+    const int cend = (warp >= 8) ? p.npad : csplit;
     const bool st32 = (p.out_cstride % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && !(p.dbg & 8);
     int it = 0;
     for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
@@ -440,7 +447,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           }
           rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
         }
-        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
           float v[16];
           epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
 #pragma unroll
@@ -531,13 +538,13 @@ int igemm_set_smem_attr(int ck, int pair, size_t smem_bytes) {
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
   if (!p.pair) {
-    ig_kernel(ck, 0)<<<grid, kIgThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
+    ig_kernel(ck, 0)<<<grid, p.threads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, tm_y, p);
     return static_cast<int>(cudaGetLastError());
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-  cfg.blockDim = dim3(kIgThreads, 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(p.threads), 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

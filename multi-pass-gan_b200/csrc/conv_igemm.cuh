@@ -19,7 +19,8 @@ namespace mpg {
 
 constexpr int kIgTileW = 16;
 constexpr int kIgTileH = 16;
-constexpr int kIgThreads = 256;
+constexpr int kIgThreads = 256;     // 4 role warps + 4 epilogue warps
+constexpr int kIgMaxThreads = 384;  // ... or + 8 epilogue warps (one CTA per SM plans)
 constexpr int kIgMaxStagesA = 4;
 constexpr int kIgMaxStagesB = 12;
 
@@ -43,6 +44,7 @@ struct IgemmParams {
   // halo mode: ONE TMA halo image [16+k-1][16+k-1][CK] per (segment, chunk); every (dy,dx) tap is a
   // shifted UMMA descriptor into it (accumulator = 16 rows x 8 px). halo_bo: descriptor base_offset rule
   int halo, halo_bo;
+  int threads;  // 256 or 384 (launch block size)
   int pair;  // cta_group::2 CTA pairs: each CTA holds half of every weight tile (wide, weight-streaming layers)
   // resident weights: all `ktiles` weight tiles live in smem for the CTA's lifetime (thin layers)
   int bres, ktiles;

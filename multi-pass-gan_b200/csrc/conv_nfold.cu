@@ -22,19 +22,25 @@ __device__ __forceinline__ NfTile nf_decode(int t, const NfoldParams& p) {
 }
 
 template <int CK, int KS>
-__global__ void __launch_bounds__(kNfThreads, 2)
+__global__ void __maxnreg__(128)
 conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const __grid_constant__ CUtensorMap tm_w, const NfoldParams p) {
-  constexpr int RB = CK * 2;  // bytes per pixel of one K-chunk == swizzle span
-  constexpr uint32_t LAYOUT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
+  // CK == 8 ("NS8"): thin inputs (<= 8 channels, pixel stride 16 B). The window image is staged UN-swizzled with
+  // whole image rows as the TMA inner dimension (one TMA row per image row instead of one per pixel: the tiled
+  // TMA path costs ~7 cycles per box row whatever its size), which is exactly the no-swizzle K-major core-matrix
+  // layout: 8 consecutive pixels x 8 channels = one 8x16-byte core matrix. The second K half of a K=16 MMA is the
+  // SAME pixels one image row below (LBO = row pitch), so one MMA covers two vertical taps.
+  constexpr bool NS8 = (CK == 8);
+  constexpr int RB = CK * 2;  // bytes per pixel of one K-chunk (== swizzle span when swizzled)
+  constexpr uint32_t LAYOUT = NS8 ? 0u : ((RB == 128) ? 2u : (RB == 64 ? 4u : 6u));
   constexpr uint32_t SBO = 8u * RB;
-  constexpr int KSTEPS = CK / 16;
+  constexpr int KSTEPS = NS8 ? 1 : CK / 16;
   constexpr uint32_t ROW_BYTES = kNfWin * RB;  // one image row of the window in smem
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_a[kNfMaxStagesA], empty_a[kNfMaxStagesA];
   __shared__ __align__(8) uint64_t full_b[kNfMaxStagesB], empty_b[kNfMaxStagesB];
-  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t tmem_full[kNfMaxBufs], tmem_empty[kNfMaxBufs];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[32];
 
@@ -47,6 +53,9 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x < 32) s_shift[threadIdx.x] = threadIdx.x < p.cp ? p.shift[threadIdx.x] : 0.0f;
+  // 4 epilogue warps (256-thread launch, two CTAs per SM) or 8 (384 threads: two warps per TMEM lane quarter take
+  // the even / odd 8-channel chunks; pixel_norm needs a whole pixel in one thread and keeps 4)
+  const int epi_active = ((blockDim.x >> 5) - 4 == 8 && !p.pixel_norm && p.cp > 8) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
@@ -59,9 +68,9 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       mbar_init(&full_b[i], 1);
       mbar_init(&empty_b[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNfMaxBufs; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], epi_active);
     }
     fence_barrier_init();
   }
@@ -83,13 +92,17 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const NfTile tc = nf_decode(t, p);
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
-          const uint32_t bytes = static_cast<uint32_t>(p.rows + ks - 1) * ROW_BYTES;
+          // NS8 loads one more row: the unused second half of the last tap pair must read finite data
+          const uint32_t bytes = static_cast<uint32_t>(p.rows + ks - (NS8 ? 0 : 1)) * ROW_BYTES;
           const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
           for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
             mbar_wait(&empty_a[st], ph ^ 1u);
             mbar_arrive_expect_tx(&full_a[st], bytes);
-            tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, tc.gx0,
-                        tc.y0 - (ks >> 1), tc.n);
+            if (NS8)  // tensor viewed as [N][H][W*8]: inner coordinate in elements
+              tma_load_3d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], tc.gx0 * 8, tc.y0 - (ks >> 1), tc.n);
+            else
+              tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, tc.gx0,
+                          tc.y0 - (ks >> 1), tc.n);
             if (++st == p.na) {
               st = 0;
               ph ^= 1u;
@@ -128,7 +141,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) ================
     const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
     constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-    constexpr uint32_t DESC_LO = 1u << 16;
+    // leading-dimension byte offset (distance between the two K halves): ignored when swizzled; NS8: A = one image
+    // row, B = the npad/8 core matrices of the first K half
+    constexpr uint32_t DESC_LO = NS8 ? ((ROW_BYTES >> 4) << 16) : (1u << 16);
+    const uint32_t b_desc_lo = NS8 ? ((static_cast<uint32_t>(p.npad) * 16u) >> 4) << 16 : (1u << 16);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
@@ -150,12 +166,12 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           mbar_wait(&full_a[sa], pa);
           tc_fence_after();
           const uint32_t a_lo = ((smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
-          for (int dy = 0; dy < ks; ++dy, ++kt) {
+          for (int dy = 0; dy < ks; dy += (NS8 ? 2 : 1), ++kt) {
             if (!p.bres) {
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
             }
-            const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(p.bres ? kt : sb) * p.b_tile_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
+            const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(p.bres ? kt : sb) * p.b_tile_bytes) & 0x3FFFFu) >> 4) | b_desc_lo;
             if (elect_one()) {
               for (int acc = 0; acc < p.naccs; ++acc) {
                 const uint32_t ag = a_lo + ((static_cast<uint32_t>(acc * kNfRowsAcc + dy) * ROW_BYTES) >> 4);
@@ -187,7 +203,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       if (elect_one()) umma_commit(&tmem_full[buf]);
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + epi_active) {
     // ===================== epilogue: shifted sum over dx (warp shuffles) + shift + act + store ====
     const int ew = warp & 3;  // TMEM lane quarter == image row within the accumulator
     constexpr int pad0 = KS >> 1;
@@ -196,6 +212,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const float act_b = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.4f : 0.0f);
     const float inv_c = 1.0f / static_cast<float>(p.cout);
     const int nchunks = p.cp >> 3;
+    const int cgrp = (warp - 4) >> 2;           // chunk parity this warp handles when 8 warps are active
+    const bool all_chunks = epi_active == 4;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int buf = it % p.nbuf;
@@ -215,7 +233,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         float ssq = 0.0f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (c < nchunks) {
+          if (c < nchunks && (all_chunks || (c & 1) == cgrp)) {
             uint32_t r[KS][8];
 #pragma unroll
             for (int dx = 0; dx < KS; ++dx) tmem_ld8(taddr + static_cast<uint32_t>(dx * p.cp + c * 8), r[dx]);
@@ -244,7 +262,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              if (c < nchunks) {
+              if (c < nchunks && (all_chunks || (c & 1) == cgrp)) {
                 uint4 q;
                 q.x = pack_h16x2(o[c * 8 + 0] * rn, o[c * 8 + 1] * rn, od);
                 q.y = pack_h16x2(o[c * 8 + 2] * rn, o[c * 8 + 3] * rn, od);
@@ -257,7 +275,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             float* op = reinterpret_cast<float*>(p.out) + pix * p.out_cstride;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < p.out_cstride) op[j] = (j < p.cout) ? o[j] * rn : 0.0f;
+              if (j < p.out_cstride && (j >> 3) < nchunks && (all_chunks || ((j >> 3) & 1) == cgrp))
+                op[j] = (j < p.cout) ? o[j] * rn : 0.0f;
           }
         }
       }
@@ -280,14 +299,15 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 typedef void (*NfKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const NfoldParams);
 
 static NfKernel nf_kernel(int ck, int ks) {
+  if (ck == 8) return ks == 5 ? conv_nfold_kernel<8, 5> : conv_nfold_kernel<8, 3>;
   if (ks == 5) return ck == 64 ? conv_nfold_kernel<64, 5> : (ck == 32 ? conv_nfold_kernel<32, 5> : conv_nfold_kernel<16, 5>);
   return ck == 64 ? conv_nfold_kernel<64, 3> : (ck == 32 ? conv_nfold_kernel<32, 3> : conv_nfold_kernel<16, 3>);
 }
 
-static size_t g_nf_smem_attr[6] = {0, 0, 0, 0, 0, 0};
+static size_t g_nf_smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes) {
-  const int slot = (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3);
+  const int slot = (ck == 8) ? (ks == 5 ? 6 : 7) : (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3);
   if (smem_bytes <= g_nf_smem_attr[slot]) return 0;
   cudaError_t e = cudaFuncSetAttribute(nf_kernel(ck, ks), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
@@ -297,7 +317,7 @@ int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes) {
 
 int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
-  nf_kernel(ck, p.seg_ks[0])<<<grid, kNfThreads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+  nf_kernel(ck, p.seg_ks[0])<<<grid, p.threads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -23,9 +23,11 @@ namespace mpg {
 
 constexpr int kNfWin = 32;      // pixels per image row held by an accumulator
 constexpr int kNfRowsAcc = 4;   // image rows per accumulator (4 * 32 = 128 MMA rows)
-constexpr int kNfThreads = 256;
+constexpr int kNfThreads = 256;     // 4 role warps + 4 epilogue warps (two CTAs per SM)
+constexpr int kNfMaxThreads = 384;  // + 8 epilogue warps (one CTA per SM)
 constexpr int kNfMaxStagesA = 4;
 constexpr int kNfMaxStagesB = 8;
+constexpr int kNfMaxBufs = 10;  // TMEM accumulator buffers (tiles in flight between the MMA and epilogue warps)
 
 struct NfoldParams {
   int n, h, w;
@@ -44,6 +46,7 @@ struct NfoldParams {
   int na, nb;
   int a_stage_bytes, b_tile_bytes;
   int bres, ktiles;
+  int threads;  // launch block size: 256 or 384
   int dbg;  // profiling only (env MPG_NFOLD_DBG): bit0 skip stores, bit1 skip the whole epilogue body, bit2 skip MMAs
   uint32_t tmem_cols;
   const float* shift;  // [cp] device

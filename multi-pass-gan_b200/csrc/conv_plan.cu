@@ -218,6 +218,9 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   if (cols <= 256 && (ip.bres ? b_res_bytes : 3 * ip.b_stage_bytes) + 2 * ip.a_stage_bytes <= 100 * 1024) occ = 2;
   if (const char* e = getenv("MPG_IGEMM_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
   if (ip.pair) occ = 1;
+  // 8 epilogue warps when the SM holds one CTA (two 256-thread CTAs need the registers)
+  ip.threads = (occ == 1) ? kIgMaxThreads : kIgThreads;
+  if (const char* e = getenv("MPG_IGEMM_THREADS")) ip.threads = atoi(e) == 384 ? 384 : 256;
   const int budget = (210 * 1024) / occ - 2 * ip.stage_bytes - (occ > 1 ? 2048 : 0);
   int nb, na;
   if (ip.bres) {
@@ -295,6 +298,12 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     const int c = atoi(e);
     if (c == 16 || c == 32 || c == 64) ck = c;
   }
+  // thin inputs (every segment <= 8 channels at pixel stride 8): un-swizzled whole-row staging, two vertical taps
+  // per K=16 MMA (conv_nfold.cu "NS8")
+  bool ns8 = true;
+  for (int s = 0; s < d.nseg; ++s) ns8 = ns8 && d.seg_cin[s] <= 8 && d.seg_cstride[s] == 8;
+  if (const char* e = getenv("MPG_NFOLD_NS8")) ns8 = ns8 && atoi(e) != 0;
+  if (ns8) ck = 8;
   const int rb = ck * 2;
   const int ks0 = d.seg_ksize[0], pad0 = ks0 / 2;
   const int cp = round_up(d.cout, 8);
@@ -304,12 +313,36 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   int ktiles = 0;
   for (int s = 0; s < d.nseg; ++s) {
     p->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
-    ktiles += p->seg_nchunk[s] * d.seg_ksize[s];
+    ktiles += ns8 ? (d.seg_ksize[s] + 1) / 2 : p->seg_nchunk[s] * d.seg_ksize[s];
   }
-  const size_t tile_elems = static_cast<size_t>(round_up(npad * rb, 1024)) / 2;
+  const size_t tile_elems = static_cast<size_t>(round_up(npad * (ns8 ? 32 : rb), 1024)) / 2;
   std::vector<uint16_t> wp(static_cast<size_t>(ktiles) * tile_elems, 0);
   size_t kt = 0;
-  for (int s = 0; s < d.nseg; ++s) {
+  if (ns8) {
+    // tile = (segment, tap pair j): K index = t*8 + ci with dy = 2j + t; no-swizzle K-major core matrices:
+    // element (n, k) at ((k/8) * (npad/8) + n/8) * 64 + (n%8) * 8 + (k%8)   [in 16-bit elements]
+    for (int s = 0; s < d.nseg; ++s) {
+      const int ks = d.seg_ksize[s], cin = d.seg_cin[s];
+      for (int j = 0; j < (ks + 1) / 2; ++j, ++kt)
+        for (int t = 0; t < 2; ++t) {
+          const int dy = 2 * j + t;
+          if (dy >= ks) continue;
+          for (int dx = 0; dx < ks; ++dx) {
+            const int col_dx = (ks == 1) ? pad0 : dx;
+            for (int n = 0; n < d.cout; ++n) {
+              const float sc = scale[s] ? scale[s][n] : 1.0f;
+              const int row = col_dx * cp + n;
+              for (int ci = 0; ci < cin; ++ci) {
+                const float v = w[s][((static_cast<size_t>(dy) * ks + dx) * cin + ci) * d.cout + n] * sc;
+                const size_t off = (static_cast<size_t>(t) * (npad / 8) + row / 8) * 64 + (row % 8) * 8 + ci;
+                wp[kt * tile_elems + off] = d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v);
+              }
+            }
+          }
+        }
+    }
+  }
+  for (int s = 0; s < d.nseg && !ns8; ++s) {
     const int ks = d.seg_ksize[s], cin = d.seg_cin[s];
     for (int ch = 0; ch < p->seg_nchunk[s]; ++ch)
       for (int dy = 0; dy < ks; ++dy, ++kt)
@@ -339,7 +372,12 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   q.h = d.h;
   q.w = d.w;
   q.valid_w = kNfWin - (ks0 - 1);
-  if (8 * npad <= 512) {
+  if (4 * npad <= 256) {
+    // thin layers: the serial per-CTA roles (one producer thread, one MMA thread, 4 epilogue warps) bound them, so
+    // two small CTAs per SM (256 TMEM columns each) beat one CTA with deeper buffering (measured, thin_probe.py)
+    q.naccs = 2;
+    q.nbuf = 2;
+  } else if (8 * npad <= 512) {
     q.naccs = 4;
     q.nbuf = 2;
   } else if (4 * npad <= 512) {
@@ -351,8 +389,13 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   }
   if (const char* e = getenv("MPG_NFOLD_NACCS")) {
     const int a = atoi(e);
-    if (a >= 1 && a * npad * q.nbuf <= 512) q.naccs = a;
+    if (a >= 1 && a * npad <= 512) q.naccs = a;
   }
+  if (const char* e = getenv("MPG_NFOLD_NBUF")) {
+    const int b = atoi(e);
+    if (b >= 1 && b <= kNfMaxBufs) q.nbuf = b;
+  }
+  while (q.nbuf > 1 && q.nbuf * q.naccs * npad > 512) --q.nbuf;
   q.rows = q.naccs * kNfRowsAcc;
   q.tiles_x = ceil_div(d.w, q.valid_w);
   q.tiles_y = ceil_div(d.h, q.rows);
@@ -370,8 +413,8 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   q.in_dtype = d.in_dtype;
   q.out_dtype = d.out_dtype;
   q.out_cstride = d.out_cstride;
-  q.a_stage_bytes = (q.rows + ks0 - 1) * kNfWin * rb;
-  q.b_tile_bytes = round_up(npad * rb, 1024);
+  q.a_stage_bytes = round_up((q.rows + ks0 - (ns8 ? 0 : 1)) * kNfWin * rb, 1024);
+  q.b_tile_bytes = round_up(npad * (ns8 ? 32 : rb), 1024);
   q.ktiles = ktiles;
   q.bres = (static_cast<size_t>(ktiles) * q.b_tile_bytes <= 64 * 1024) ? 1 : 0;
   if (const char* e = getenv("MPG_NFOLD_BRES")) q.bres = (atoi(e) && static_cast<size_t>(ktiles) * q.b_tile_bytes <= 128 * 1024) ? 1 : 0;
@@ -381,6 +424,8 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   const int b_bytes_min = q.bres ? ktiles * q.b_tile_bytes : 3 * q.b_tile_bytes;
   int occ = (cols <= 256 && b_bytes_min + 2 * q.a_stage_bytes <= 100 * 1024) ? 2 : 1;
   if (const char* e = getenv("MPG_NFOLD_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
+  q.threads = (occ == 1) ? kNfMaxThreads : kNfThreads;
+  if (const char* e = getenv("MPG_NFOLD_THREADS")) q.threads = atoi(e) == 384 ? 384 : 256;
   const int budget = (210 * 1024) / occ - (occ > 1 ? 2048 : 0);
   int nb;
   if (q.bres) {
@@ -501,8 +546,11 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     //  un-overlapped epilogue of the N=160 single-buffered configuration; measured: tools/thin_probe.py)
     int cin_total = 0;
     for (int s = 0; s < d.nseg; ++s) cin_total += d.seg_cin[s];
+    bool thin_in = true;  // every segment <= 8 channels at pixel stride 8: the un-swizzled two-taps-per-MMA staging applies
+    for (int s = 0; s < d.nseg; ++s) thin_in = thin_in && d.seg_cin[s] <= 8 && d.seg_cstride[s] == 8;
+    (void)thin_in;
     bool nf = nfold_eligible(d) && (round_up(d.cout, 8) * d.seg_ksize[0] <= 64 || cin_total >= 64);
-    if (const char* e = getenv("MPG_CONV_NFOLD")) nf = nf && atoi(e) != 0;
+    if (const char* e = getenv("MPG_CONV_NFOLD")) nf = (atoi(e) == 2) ? nfold_eligible(d) : (nf && atoi(e) != 0);
     if (kind == 1 && nf) kind = 3;
   }
   if (kind == 3 && !nfold_eligible(d)) {
@@ -602,13 +650,22 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       if (p->tm_x_ptr[s] == xs[s]) continue;
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(xs[s]) & 15) == 0, "conv: input %d not 16-byte aligned", s);
       const uint64_t cs = static_cast<uint64_t>(d.seg_cstride[s]) * 2;
-      const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
-                                static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
-      const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
-      const uint32_t box[4] = {static_cast<uint32_t>(p->ck), static_cast<uint32_t>(mpg::kNfWin),
-                               static_cast<uint32_t>(p->np.rows + d.seg_ksize[s] - 1), 1u};
-      int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
-                               box, swizzle_for(p->ck));
+      int r;
+      if (p->ck == 8) {  // NS8: [N][H][W*8] view, whole 32-pixel rows as the inner box dimension, no swizzle
+        const uint64_t dims[3] = {static_cast<uint64_t>(d.w) * 8, static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+        const uint64_t strides[2] = {cs * d.w, cs * d.w * d.h};
+        const uint32_t box[3] = {static_cast<uint32_t>(mpg::kNfWin * 8), static_cast<uint32_t>(p->np.rows + d.seg_ksize[s]), 1u};
+        r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs[s], dims,
+                             strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      } else {
+        const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
+                                  static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+        const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+        const uint32_t box[4] = {static_cast<uint32_t>(p->ck), static_cast<uint32_t>(mpg::kNfWin),
+                                 static_cast<uint32_t>(p->np.rows + d.seg_ksize[s] - 1), 1u};
+        r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
+                             box, swizzle_for(p->ck));
+      }
       if (r) return r;
       p->tm_x_ptr[s] = xs[s];
     }

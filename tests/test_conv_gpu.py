@@ -30,6 +30,9 @@ CASES = {
     "nf_k3_32to32_pn": dict(n=1, h=48, w=48, cins=[32], ks=[3], cout=32, act="lrelu", pixel_norm=True, force_kind=3),
     "nf_k3_64to32_s": dict(n=1, h=32, w=64, cins=[64, 64], ks=[3, 1], cout=32, act="relu", pixel_norm=True, force_kind=3),
     "nf_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", force_kind=3),
+    "nf_ns8_8and4_to32": dict(n=2, h=40, w=72, cins=[8, 4], ks=[5, 1], cout=32, act="relu", force_kind=3),
+    "nf_ns8_k3_8to8_pn": dict(n=1, h=33, w=47, cins=[8], ks=[3], cout=8, act="lrelu", pixel_norm=True, force_kind=3),
+    "nf_ns8_narrow_w20": dict(n=1, h=12, w=20, cins=[4], ks=[5], cout=8, act="relu", force_kind=3),
     "nf_k5_128to32_256": dict(n=1, h=256, w=256, cins=[128], ks=[5], cout=32, act="relu", force_kind=3),
     "direct_f32_k5_4to8_up4": dict(n=2, h=64, w=64, cins=[4], ks=[5], cout=8, in_dtype="f32", in_upsample=4, act="relu"),
     "direct_k5_8to2": dict(n=1, h=40, w=40, cins=[8], ks=[5], cout=2, act="relu"),

@@ -24,11 +24,7 @@ SHAPES = [
 ]
 CONFIGS = {
     "default": {},
-    "bgroup": {"MPG_IGEMM_BGROUP": "1"},
-    "skel": {"MPG_IGEMM_DBG": "7"},
-    "skel_bgroup": {"MPG_IGEMM_DBG": "7", "MPG_IGEMM_BGROUP": "1"},
-    "nopair_bgroup0": {"MPG_IGEMM_PAIR": "0", "MPG_IGEMM_BGROUP": "0"},
-    "nopair_skel_bgroup0": {"MPG_IGEMM_PAIR": "0", "MPG_IGEMM_BGROUP": "0", "MPG_IGEMM_DBG": "7"},
+    "nf256": {"MPG_NFOLD_THREADS": "256"},
 }
 KEYS = sorted({k for c in CONFIGS.values() for k in c})
 
