@@ -93,6 +93,11 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* d, const float* w_se
 int mpg_conv_plan_run(mpg_conv_plan p, const void* x_seg0, const void* x_seg1, void* y,
                       void* stream);
 int mpg_conv_plan_destroy(mpg_conv_plan p);
+/* Training: refresh the packed weights / shift of a tcgen05 plan (force_kind 1) from DEVICE fp32 HWIO tensors,
+ * stream ordered. mode 0: w_seg is this conv's weight; mode 1: w_seg is the weight of the FORWARD conv whose
+ * input gradient this plan computes (taps flipped, channels swapped = Conv2DBackpropInput). */
+int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
+                         const float* shift_dev, void* stream);
 /* which kernel the plan dispatches to: 1 = tcgen05 implicit GEMM, 2 = CUDA-core direct */
 int mpg_conv_plan_kind(mpg_conv_plan p);
 /* algorithmic FLOPs of one run (2*MAC, un-padded channels) */

@@ -78,6 +78,7 @@ def lib():
     L.mpg_conv_plan_create.argtypes = [vp, ctypes.POINTER(ConvDesc), fp, fp, fp, fp, fp, ctypes.POINTER(vp)]
     L.mpg_conv_plan_run.argtypes = [vp, vp, vp, vp, vp]
     L.mpg_conv_plan_destroy.argtypes = [vp]
+    L.mpg_conv_plan_update.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     L.mpg_conv_plan_kind.argtypes = [vp]
     L.mpg_conv_plan_flops.argtypes = [vp]
     L.mpg_conv_plan_flops.restype = dp
@@ -212,6 +213,11 @@ class ConvPlan:
         p1 = None if x1 is None else (x1.data_ptr() if hasattr(x1, "data_ptr") else int(x1))
         py = y.data_ptr() if hasattr(y, "data_ptr") else int(y)
         check(lib().mpg_conv_plan_run(self._p, p0, p1, py, stream), "mpg_conv_plan_run")
+
+    def update(self, w0, w1=None, mode0=0, mode1=0, shift=None, stream=0):
+        """Refresh the packed weights from device fp32 HWIO tensors (training; tcgen05 plans only)."""
+        check(lib().mpg_conv_plan_update(self._p, _ptr(w0), _ptr(w1), int(mode0), int(mode1), _ptr(shift), stream),
+              "mpg_conv_plan_update")
 
     def close(self):
         if self._p:

@@ -70,6 +70,43 @@ size_t swz_elem(int n, int c, int ck) {
   return (static_cast<size_t>(n) * rb + static_cast<size_t>((chunk ^ x) << 4) + ((c * 2) & 15)) / 2;
 }
 
+// Device-side re-pack of fp32 HWIO weights into the igemm tile layout [ktile][npad][ck] (ktile order
+// (segment, chunk, dx, dy)), used by the training step where the weights change every optimizer step.
+// mode 0: W(dy,dx,ci,n) = w[dy][dx][ci][n]                      (forward; w is [k,k,cin,cout])
+// mode 1: W(dy,dx,ci,n) = w[k-1-dy][k-1-dx][n][ci]              (dgrad; w is the FORWARD tensor [k,k,cout_d,cin_d])
+struct RepackArgs {
+  const float* w[2];
+  int mode[2];
+  int ks[2], cin[2], nchunk[2], kt0[2];
+  int nseg, ck, npad, cout, f16;
+  uint16_t* out;
+  long long total;
+};
+__global__ void __launch_bounds__(256) repack_igemm_kernel(const RepackArgs a) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < a.total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(e % a.ck);
+    long long r = e / a.ck;
+    const int n = static_cast<int>(r % a.npad);
+    const int kt = static_cast<int>(r / a.npad);
+    const int s = (a.nseg > 1 && kt >= a.kt0[1]) ? 1 : 0;
+    const int ks = a.ks[s];
+    int q = kt - a.kt0[s];
+    const int dy = q % ks;
+    q /= ks;
+    const int dx = q % ks;
+    const int ch = q / ks;
+    const int ci = ch * a.ck + c;
+    float v = 0.0f;
+    if (ci < a.cin[s] && n < a.cout) {
+      if (a.mode[s] == 0)
+        v = a.w[s][((static_cast<size_t>(dy) * ks + dx) * a.cin[s] + ci) * a.cout + n];
+      else
+        v = a.w[s][((static_cast<size_t>(ks - 1 - dy) * ks + (ks - 1 - dx)) * a.cout + n) * a.cin[s] + ci];
+    }
+    a.out[e] = a.f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+}
+
 int same_pad_before(int in, int k, int s) {
   const int out = (in + s - 1) / s;
   int total = (out - 1) * s + k - in;
@@ -691,6 +728,44 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
     mpg::set_error("conv direct launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
     return r;
   }
+  return MPG_OK;
+}
+
+/* Training: refresh the packed weights / shift of a tcgen05 (kind 1) plan from DEVICE fp32 tensors, stream ordered.
+ * mode 0: w_seg is this conv's HWIO weight; mode 1: w_seg is the HWIO weight of the FORWARD conv whose input
+ * gradient this plan computes (flipped taps, swapped channels). shift_dev may be NULL (= keep). */
+int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
+                         const float* shift_dev, void* stream) {
+  MPG_CHECK_ARG(p && w_seg0_dev, "mpg_conv_plan_update: null argument");
+  MPG_CHECK_ARG(p->kind == 1, "mpg_conv_plan_update: only tcgen05 igemm plans (force_kind 1) can be refreshed on the device");
+  MPG_CHECK_ARG(p->d.nseg == 1 || w_seg1_dev, "mpg_conv_plan_update: segment 1 weights missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RepackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w[0] = w_seg0_dev;
+  a.w[1] = w_seg1_dev;
+  a.mode[0] = mode0;
+  a.mode[1] = mode1;
+  int kt = 0;
+  for (int s = 0; s < p->d.nseg; ++s) {
+    a.ks[s] = p->d.seg_ksize[s];
+    a.cin[s] = p->d.seg_cin[s];
+    a.nchunk[s] = p->seg_nchunk[s];
+    a.kt0[s] = kt;
+    kt += p->seg_nchunk[s] * a.ks[s] * a.ks[s];
+  }
+  a.nseg = p->d.nseg;
+  a.ck = p->ck;
+  a.npad = p->npad;
+  a.cout = p->d.cout;
+  a.f16 = p->d.in_dtype == MPG_F16 ? 1 : 0;
+  a.out = static_cast<uint16_t*>(p->d_wpacked);
+  a.total = static_cast<long long>(kt) * p->npad * p->ck;
+  long long blocks = (a.total + 255) / 256;
+  if (blocks > p->h->sm_count * 8) blocks = p->h->sm_count * 8;
+  repack_igemm_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  MPG_CUDA(cudaGetLastError());
+  if (shift_dev) MPG_CUDA(cudaMemcpyAsync(p->d_shift, shift_dev, sizeof(float) * p->d.cout, cudaMemcpyDeviceToDevice, st));
   return MPG_OK;
 }
 

@@ -77,14 +77,44 @@ class _Conv:
             self.gamma = ps.add(scope + "/gamma", (cout,))
             tr.moving[scope + "/moving_mean"] = None
             tr.moving[scope + "/moving_variance"] = None
+        # tensor-core path (precision "fp16"): forward on the tcgen05 implicit-GEMM kernel with fp16 operands, dgrad on
+        # the same kernel with bf16 gradients (range) and flipped/transposed weights; wgrad stays fp32
+        self.fast = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1 and cin % 8 == 0
+                     and cout % 8 == 0 and max(cin, cout) >= 32)
+        self.plan_f = self.plan_d = None
+
+    def build_plans(self, n, h, w):
+        if not self.fast or self.plan_f is not None:
+            return
+        tr = self.tr
+        zf = np.zeros((self.k, self.k, self.cin, self.cout), np.float32)
+        zd = np.zeros((self.k, self.k, self.cout, self.cin), np.float32)
+        self.plan_f = capi.ConvPlan(tr.h, n, h, w, [zf], [self.cin], self.cout, self.cout, act=None,
+                                    shift=np.zeros(self.cout, np.float32), in_dtype=capi.F16, out_dtype=capi.F32, force_kind=1)
+        self.plan_d = capi.ConvPlan(tr.h, n, h, w, [zd], [self.cout], self.cin, self.cin, act=None,
+                                    shift=np.zeros(self.cin, np.float32), in_dtype=capi.BF16, out_dtype=capi.F32, force_kind=1)
+
+    def refresh(self):
+        if self.plan_f is None:
+            return
+        ps, tr = self.ps, self.tr
+        self.plan_f.update(ps.view(ps.w, self.wn), mode0=0, shift=ps.view(ps.w, self.bn_), stream=tr.st)
+        self.plan_d.update(ps.view(ps.w, self.wn), mode0=1, stream=tr.st)
+        tr.launches += 2
 
     def forward(self, x, n, h, w):
         """x: [n, h/in_up, w/in_up, cin]; h, w: conv input size. Returns (y, saved)."""
         tr, ps = self.tr, self.ps
         oh, ow = -(-h // self.stride), -(-w // self.stride)
         lin = tr.buf((n, oh, ow, self.cout))
-        tr.call("conv_fwd", x, ps.view(ps.w, self.wn), ps.view(ps.w, self.bn_), lin, n, h, w, self.cin, self.cout, self.k,
-                self.stride, self.in_up, tr.st)
+        if self.fast:
+            x16 = tr.buf16((n, h, w, self.cin), torch.float16)
+            capi.pack_channels(tr.h, [(x, capi.F32, self.cin, 0, self.cin, 1, 1)], x16, capi.F16, self.cin, n, h, w, tr.st)
+            self.plan_f.run(x16, None, lin, tr.st)
+            tr.launches += 2
+        else:
+            tr.call("conv_fwd", x, ps.view(ps.w, self.wn), ps.view(ps.w, self.bn_), lin, n, h, w, self.cin, self.cout, self.k,
+                    self.stride, self.in_up, tr.st)
         rows = n * oh * ow
         sv = dict(x=x, lin=lin, n=n, h=h, w=w, rows=rows)
         if self.bn:
@@ -120,15 +150,31 @@ class _Conv:
                     sv["h"], sv["w"], self.cin, self.cout, self.k, self.stride, self.in_up, tr.st)
         if dx is not None:
             assert self.in_up == 1
-            tr.call("conv_dgrad", dlin, ps.view(ps.w, self.wn), dx, sv["n"], sv["h"], sv["w"], self.cin, self.cout, self.k,
-                    self.stride, 1 if accumulate else 0, tr.st)
+            if self.fast:
+                g16 = tr.buf16(tuple(dlin.shape), torch.bfloat16)
+                capi.pack_channels(tr.h, [(dlin, capi.F32, self.cout, 0, self.cout, 1, 1)], g16, capi.BF16, self.cout, sv["n"],
+                                   sv["h"], sv["w"], tr.st)
+                tgt = tr.buf(tuple(dx.shape)) if accumulate else dx
+                self.plan_d.run(g16, None, tgt, tr.st)
+                tr.launches += 2
+                if accumulate:
+                    tr.call("axpy", dx, tgt, 1.0, dx.numel(), tr.st)
+            else:
+                tr.call("conv_dgrad", dlin, ps.view(ps.w, self.wn), dx, sv["n"], sv["h"], sv["w"], self.cin, self.cout, self.k,
+                        self.stride, 1 if accumulate else 0, tr.st)
 
 
 class Trainer4x:
     """multipassGAN-4x.py training loop body for `upsampling_mode 2` tiles (tileSizeLow^2 x 4 -> (4 tileSizeLow)^2)."""
 
     def __init__(self, tileSizeLow=16, upRes=4, batch=16, values=None, seed=1, batch_norm=True, bn_decay=0.999,
-                 learning_rate=2e-4, adam_beta1=0.5, weight_dld=1.0, k2_l=(1.0, 1.0, 1.0, 1.0), device=0, group=None):
+                 learning_rate=2e-4, adam_beta1=0.5, weight_dld=1.0, k2_l=(1.0, 1.0, 1.0, 1.0), device=0, group=None,
+                 precision="fp32"):
+        """precision "fp32": every kernel fp32 (the parity mode, what the reference computes); "fp16": the wide stride-1
+        convolutions run forward / dgrad on the tcgen05 kernel (fp16 activations, bf16 gradients, fp32 accumulation and
+        fp32 master weights / optimizer), everything else stays fp32."""
+        assert precision in ("fp32", "fp16")
+        self.precision = precision
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
         self.L, self.u, self.S, self.B, self.C = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(batch), 4
@@ -176,6 +222,9 @@ class Trainer4x:
             if init is None:
                 init = np.full((c,), 0.0 if name.endswith("moving_mean") else 1.0, np.float32)
             self.moving[name] = torch.from_numpy(np.ascontiguousarray(init, np.float32)).to(self.device)
+        for a, b, sc in self.rbs:
+            for c in (a, b, sc):
+                c.build_plans(self.B, self.S, self.S)
         self.scratch = torch.zeros(4096, dtype=torch.float64, device=self.device)
         self.losses = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.st = 0
@@ -191,6 +240,11 @@ class Trainer4x:
         self._bufs.append(t)
         return t
 
+    def buf16(self, shape, dtype):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self._bufs.append(t)
+        return t
+
     def call(self, name, *args):
         self.launches += 1
         capi.train_call(name, self.h, *args)
@@ -203,6 +257,9 @@ class Trainer4x:
     def _refresh_weights(self):
         for ps in (self.pg, self.pd):
             self.call("mul", ps.w, ps.v, ps.scale, ps.total, self.st)  # W_eff = v * wscale (tools_wscale/GAN.py:668)
+        for a, b, sc in self.rbs:
+            for c in (a, b, sc):
+                c.refresh()
 
     # ------------------------------------------------------------------ networks
     def gen_forward(self, x):

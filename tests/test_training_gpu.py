@@ -104,3 +104,24 @@ def test_train_conv_kernels_vs_torch_autograd():
             gx = torch.empty_like(dx_)
             capi.train_call("conv_dgrad", h, dy_d, dw_, gx, n, hh, hh, cin, cout, k, s, 0, 0)
             assert _rel(gx.cpu().numpy(), xt.grad.numpy()) < 1e-5, ("dgrad", cin, cout, k, s)
+
+
+def test_training_tensor_core_mode_tracks_oracle():
+    """precision="fp16": wide convs forward/dgrad on tcgen05 (fp16 activations, bf16 gradients). One iteration must
+    stay close to the fp64 oracle (losses 1e-2 relative, generator gradients of the wide layers 5e-2 rel-L2)."""
+    L, u, B = 8, 4, 4
+    S = L * u
+    rng = np.random.default_rng(6)
+    hp = dict(kk=5.0, kk2=1e-5, seed=11, weight_dld=1.0)
+    xb, yb = rng.random((B, L * L * 4), dtype=np.float32), rng.random((B, S * S), dtype=np.float32)
+    tr = T.Trainer4x(L, u, B, seed=11, precision="fp16")
+    assert any(c.fast for rb in tr.rbs for c in rb)
+    values = {k: v.copy() for k, v in tr.values().items()}
+    cfg = on.make_cfg_4x(L, upRes=u, upsampling_mode=2, batch_norm=True)
+    ref = ot.train_iteration(values, [(xb, yb)], [(xb, yb)], cfg, hp, ot.Adam(2e-4, 0.5), ot.Adam(2e-4, 0.5))
+    got = tr.iteration([(xb, yb)], [(xb, yb)], kk=hp["kk"], kk2=hp["kk2"])
+    assert abs(got["disc_loss"] - ref["disc_loss"]) <= 1e-2 * max(1.0, abs(ref["disc_loss"])), (got, ref)
+    assert abs(got["gen_loss_complete"] - ref["gen_loss_complete"]) <= 1e-2 * max(1.0, abs(ref["gen_loss_complete"])), (got, ref)
+    gg = tr.grads("g")
+    for name in ("generator/g_cB1/weight", "generator/g_cA1/weight", "generator/g_cA2/weight", "generator/g_cA0/weight"):
+        assert _rel(gg[name], ref["grads_g"][name]) <= 5e-2, (name, _rel(gg[name], ref["grads_g"][name]))

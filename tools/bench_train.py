@@ -35,12 +35,13 @@ def main():
     ap.add_argument("--disc-runs", type=int, default=1)
     ap.add_argument("--gen-runs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16"])
     args = ap.parse_args()
     rank, local, world = par.init_from_env()
     torch.cuda.set_device(local)
     L, u, B = 16, 4, args.batch
     S = L * u
-    tr = T.Trainer4x(L, u, B, seed=1, device=local)
+    tr = T.Trainer4x(L, u, B, seed=1, device=local, precision=args.precision)
     rng = np.random.default_rng(100 + rank)
     xs = torch.from_numpy(rng.random((B, L * L * 4), dtype=np.float32)).pin_memory()
     ys = torch.from_numpy(rng.random((B, S * S), dtype=np.float32)).pin_memory()
@@ -74,7 +75,8 @@ def main():
     flop_it = B * (args.disc_runs * (G_FWD + 2 * D_FWD * 3) + args.gen_runs * (G_FWD * 3 + 2 * D_FWD + 2 * D_FWD))
     line = dict(metric="training loop bodies/sec (4x G + spatial D, tiles 16x16->64x64)", value=world * 1e3 / it_ms,
                 unit="iteration/s", tiles_per_s=world * B * 1e3 / it_ms, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=it_ms, higher_is_better=True, scaling="weak", dtype="f32", data="synthetic",
+                ms_per_step=it_ms, higher_is_better=True, scaling="weak",
+                dtype="f32" if args.precision == "fp32" else "f16 fwd / bf16 dgrad on tcgen05, f32 wgrad + optimizer", data="synthetic",
                 config=dict(workload="multipassGAN-4x training step (BASELINE.json configs[3])", batch_per_gpu=B,
                             discRuns=args.disc_runs, genRuns=args.gen_runs, tile="16x16 -> 64x64"),
                 algorithmic_tflops=world * flop_it / (it_ms * 1e-3) / 1e12,
