@@ -179,9 +179,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       const uint32_t tile_bytes = static_cast<uint32_t>(nrows * RB);
       if (p.bres) {
         // resident weights: every k-tile is loaded once per CTA and stays in shared memory
-        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
-        for (int kt = 0; kt < p.ktiles; ++kt)
-          tma_load_2d(smB + static_cast<size_t>(kt) * p.b_tile_bytes, &tm_w, &full_b[0], 0, kt * p.npad);
+        // (PAIR: each CTA keeps its half of every tile; both halves complete on the leader's barrier)
+        if (PAIR) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_b[0], 2u * tile_bytes * static_cast<uint32_t>(p.ktiles));
+          const uint32_t bar = mapa_u32(smem_u32(&full_b[0]), 0);
+          for (int kt = 0; kt < p.ktiles; ++kt)
+            tma_load_2d_2cta(smB + static_cast<size_t>(kt) * p.b_tile_bytes, &tm_w, bar, 0, kt * p.npad + row0);
+        } else {
+          mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+          for (int kt = 0; kt < p.ktiles; ++kt)
+            tma_load_2d(smB + static_cast<size_t>(kt) * p.b_tile_bytes, &tm_w, &full_b[0], 0, kt * p.npad);
+        }
       }
       MPG_TILE_LOOP(t) {
         if (p.bres) break;
@@ -222,7 +230,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
-    if (p.bres) mbar_wait(&full_b[0], 0);
+    if (p.bres) {
+      mbar_wait(&full_b[0], 0);
+      tc_fence_after();
+    }
     for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it & 1;
       mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);

@@ -9,11 +9,12 @@
 #include "conv_direct.cuh"
 #include "conv_igemm.cuh"
 #include "conv_nfold.cuh"
+#include "conv_tiny.cuh"
 
 struct mpg_conv_plan_s {
   mpg_handle h;
   mpg_conv_desc d;
-  int kind;  // 1 igemm, 2 direct, 3 tap-folded igemm (narrow Cout)
+  int kind;  // 1 igemm, 2 direct, 3 tap-folded igemm (narrow Cout), 4 CUDA-core tiny (Cout <= 2, Cin <= 8)
   mpg::NfoldParams np;
   double flops;
   int oh, ow;
@@ -33,6 +34,8 @@ struct mpg_conv_plan_s {
   // ---- direct
   float* d_wdirect;
   mpg::DirectParams dp;
+  // ---- tiny
+  mpg::TinyParams tp;
 };
 
 namespace {
@@ -236,7 +239,11 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   // resident weights: thin layers keep every weight tile in shared memory for the CTA's lifetime, which
   // removes the per-tile weight TMA round trips that bound them (measured: 0.18 of 0.22 ms was load skeleton)
   ip.bres = (!ip.pair && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 64 * 1024) ? 1 : 0;
-  if (const char* e = getenv("MPG_IGEMM_BRES")) ip.bres = (!ip.pair && atoi(e) && static_cast<size_t>(ktiles) * ip.b_tile_bytes <= 160 * 1024) ? 1 : 0;
+  // CTA pairs: a CTA only holds half of every tile, so e.g. the 5x5 32->128 layer (25 x 4 KB halves) stays
+  // resident next to three halo images and the MMA thread never waits on a weight stage
+  if (ip.pair && static_cast<size_t>(ktiles) * ip.b_tile_bytes + 3 * static_cast<size_t>(ip.a_stage_bytes) <= 200 * 1024) ip.bres = 1;
+  if (const char* e = getenv("MPG_IGEMM_BRES"))
+    ip.bres = (atoi(e) && static_cast<size_t>(ktiles) * ip.b_tile_bytes + 2 * static_cast<size_t>(ip.a_stage_bytes) <= 200 * 1024) ? 1 : 0;
   // group the ks vertical taps of one (chunk,dx) into a single B stage when that stays small: every stage
   // hand-over (mbarrier wait + tcgen05.commit round trip) costs ~450 cycles on top of bytes/27 B/clk (measured,
   // tools/thin_probe.py), so the MMA thread should wait/commit once per 2*ks*CK/16 MMAs, not once per 2*CK/16
@@ -547,6 +554,33 @@ int build_direct(mpg_conv_plan p, const float* w[2], const float* scale[2], cons
   return 0;
 }
 
+// CUDA-core kernel for the channel-less tail layers (conv_tiny.cu): weights go into the kernel parameter block as
+// [dy][dx][ci bucket][cout], scale folded.
+int build_tiny(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  TinyParams& t = p->tp;
+  memset(&t, 0, sizeof(t));
+  t.n = d.n;
+  t.h = d.h;
+  t.w = d.w;
+  t.act = d.act;
+  t.in_dtype = d.in_dtype;
+  t.out_dtype = d.out_dtype;
+  t.out_cstride = d.out_cstride;
+  const int ks = d.seg_ksize[0], cin = d.seg_cin[0];
+  const int cb = cin <= 2 ? 2 : (cin <= 4 ? 4 : 8);
+  for (int tap = 0; tap < ks * ks; ++tap)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int n = 0; n < d.cout; ++n)
+        t.w0[(tap * cb + ci) * d.cout + n] = w[0][(static_cast<size_t>(tap) * cin + ci) * d.cout + n] * (scale[0] ? scale[0][n] : 1.0f);
+  if (d.nseg == 2)
+    for (int ci = 0; ci < d.seg_cin[1]; ++ci)
+      for (int n = 0; n < d.cout; ++n)
+        t.w1[ci * d.cout + n] = w[1][static_cast<size_t>(ci) * d.cout + n] * (scale[1] ? scale[1][n] : 1.0f);
+  for (int n = 0; n < d.cout; ++n) t.shift[n] = shift ? shift[n] : 0.0f;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -589,6 +623,14 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     bool nf = nfold_eligible(d) && (round_up(d.cout, 8) * d.seg_ksize[0] <= 64 || cin_total >= 64);
     if (const char* e = getenv("MPG_CONV_NFOLD")) nf = (atoi(e) == 2) ? nfold_eligible(d) : (nf && atoi(e) != 0);
     if (kind == 1 && nf) kind = 3;
+    // Cout <= 2 from <= 8 channels: a bandwidth kernel on CUDA cores beats the per-tile hand-overs of the tensor path
+    bool tiny = tiny_eligible(d);
+    if (const char* e = getenv("MPG_CONV_TINY")) tiny = tiny && atoi(e) != 0;
+    if (tiny) kind = 4;
+  }
+  if (kind == 4 && !tiny_eligible(d)) {
+    mpg::set_error("conv: tiny CUDA-core path needs 16-bit input at channel stride 8, cin <= 8, cout <= 2, k0 in {3,5}, 1x1 shortcut, stride 1");
+    return MPG_ENOSUP;
   }
   if (kind == 3 && !nfold_eligible(d)) {
     mpg::set_error("conv: tap-folded path needs the tcgen05 constraints plus cout <= 32, k0 in {3,5}, 1x1 shortcut, no upsample");
@@ -598,7 +640,7 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     mpg::set_error("conv: tcgen05 path needs bf16/f16 input (same 16-bit output type or f32), stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
     return MPG_ENOSUP;
   }
-  MPG_CHECK_ARG(kind >= 1 && kind <= 3, "conv: bad force_kind %d", d.force_kind);
+  MPG_CHECK_ARG(kind >= 1 && kind <= 4, "conv: bad force_kind %d", d.force_kind);
 
   mpg_conv_plan p = new mpg_conv_plan_s();
   memset(p, 0, sizeof(*p));
@@ -613,7 +655,8 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   const float* w[2] = {w_seg0, w_seg1};
   const float* sc[2] = {scale_seg0, scale_seg1};
   MPG_CUDA(cudaSetDevice(h->device));
-  int r = (kind == 1) ? build_igemm(p, w, sc, shift) : (kind == 3 ? build_nfold(p, w, sc, shift) : build_direct(p, w, sc, shift));
+  int r = (kind == 1) ? build_igemm(p, w, sc, shift)
+          : (kind == 3 ? build_nfold(p, w, sc, shift) : (kind == 4 ? build_tiny(p, w, sc, shift) : build_direct(p, w, sc, shift)));
   if (r) {
     mpg_conv_plan_destroy(p);
     return r;
@@ -714,6 +757,21 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
                               p->smem_bytes, st);
     if (r) {
       mpg::set_error("conv nfold launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+      return r;
+    }
+    return MPG_OK;
+  }
+  if (p->kind == 4) {
+    MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(x0) & 15) == 0 && (reinterpret_cast<uintptr_t>(x1) & 15) == 0 &&
+                      (d.out_dtype == MPG_F32 || (reinterpret_cast<uintptr_t>(y) & 15) == 0),
+                  "conv: tensors not 16-byte aligned");
+    mpg::TinyParams t = p->tp;
+    t.x0 = x0;
+    t.x1 = x1;
+    t.out = y;
+    int r = mpg::tiny_launch(d, t, st);
+    if (r) {
+      mpg::set_error("conv tiny launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
       return r;
     }
     return MPG_OK;

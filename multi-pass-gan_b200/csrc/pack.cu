@@ -34,6 +34,45 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
   const int y = static_cast<int>(r % p.oh);
   const int n = static_cast<int>(r / p.oh);
   int oc = 0;
+  if (p.out_dtype != MPG_F32 && (p.out_cstride & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    // 16-bit output at a 16-byte pixel granularity: gather 8 channels in registers, one 128-bit store per chunk
+    // (the scalar 2-byte stores of the generic path ran at a tenth of the HBM rate)
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride);
+    unsigned long long lo = 0ull, hi = 0ull;  // dynamic shifts instead of a dynamically indexed array (stays in registers)
+    for (int s = 0; s < p.nsrc; ++s) {
+      const PackSrc& q = p.src[s];
+      const int sh = p.oh / q.fh, sw = p.ow / q.fw;
+      const long long spix = (static_cast<long long>(n) * sh + y / q.fh) * sw + x / q.fw;
+      const bool vec4 = q.dtype == MPG_F32 && q.nch == 4 && ((spix * q.cstride + q.c0) & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0;
+      float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec4) f4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q.ptr) + spix * q.cstride + q.c0));
+      for (int c = 0; c < q.nch; ++c, ++oc) {
+        float v;
+        if (vec4)
+          v = c == 0 ? f4.x : (c == 1 ? f4.y : (c == 2 ? f4.z : f4.w));
+        else if (q.dtype == MPG_F32)
+          v = __ldg(reinterpret_cast<const float*>(q.ptr) + spix * q.cstride + q.c0 + c);
+        else
+          v = h16_to_float(reinterpret_cast<const uint16_t*>(q.ptr)[spix * q.cstride + q.c0 + c], q.dtype);
+        const int k = oc & 7;
+        const unsigned long long hv = static_cast<unsigned long long>(float_to_h16(v, p.out_dtype)) << ((k & 3) * 16);
+        if (k < 4) lo |= hv; else hi |= hv;
+        if (k == 7) {
+          o[oc >> 3] = make_uint4(static_cast<uint32_t>(lo), static_cast<uint32_t>(lo >> 32), static_cast<uint32_t>(hi),
+                                  static_cast<uint32_t>(hi >> 32));
+          lo = hi = 0ull;
+        }
+      }
+    }
+    if (oc & 7) {
+      o[oc >> 3] = make_uint4(static_cast<uint32_t>(lo), static_cast<uint32_t>(lo >> 32), static_cast<uint32_t>(hi),
+                              static_cast<uint32_t>(hi >> 32));
+      oc = (oc | 7) + 1;
+    }
+    for (; oc < p.out_cstride; oc += 8) o[oc >> 3] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   for (int s = 0; s < p.nsrc; ++s) {
     const PackSrc& q = p.src[s];
     const int sh = p.oh / q.fh, sw = p.ow / q.fw;

@@ -364,7 +364,7 @@ class CompiledNet:
             plan.run(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out), stream)
 
         label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s" % (
-            {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf"}.get(kind, "cc"),
+            {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf", capi.KIND_TINY: "ct"}.get(kind, "cc"),
             "+".join(c.attrs["weight"]["var"].name.rsplit("/", 2)[-2] for c in convs),
             "/".join(str(c.attrs["ksize"]) for c in convs),
             "/".join(str(c.inputs[0].shape[3]) for c in convs), cout, ih, iw,
@@ -383,6 +383,11 @@ class CompiledNet:
         if any(c.attrs["ksize"] not in (1, 3, 5) for c in convs) or any(b.cstride % 8 for b in ins):
             return capi.KIND_DIRECT
         cp = _round_up(cout, 8)
+        if (ups == 1 and cout <= 2 and convs[0].attrs["ksize"] in (3, 5)
+                and (len(convs) == 1 or convs[1].attrs["ksize"] == 1)
+                and all(c.inputs[0].shape[3] <= 8 for c in convs) and all(b.cstride == 8 for b in ins)
+                and (out_dtype == capi.F32 or out_cstride % 8 == 0)):
+            return capi.KIND_TINY
         if (ups == 1 and cout <= 32 and convs[0].attrs["ksize"] in (3, 5)
                 and (len(convs) == 1 or convs[1].attrs["ksize"] == 1)
                 and (out_cstride <= 32 if out_dtype == capi.F32 else out_cstride == cp)

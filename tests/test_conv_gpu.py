@@ -41,6 +41,12 @@ CASES = {
     "direct_f32_k4s1": dict(n=2, h=8, w=8, cins=[16], ks=[4], cout=24, in_dtype="f32", out_dtype="f32", stride=1, act="lrelu"),
     "direct_f32_128_pn_up2": dict(n=1, h=24, w=24, cins=[128, 6], ks=[3, 1], cout=128, in_dtype="f32", out_dtype="f32",
                                   act="relu", pixel_norm=True, upsample=2),
+    # CUDA-core kernel for the channel-less tail layers (conv_tiny.cu): ru3 of gen_resnet + ragged / k3 / lrelu variants
+    "ct_k5_8to2": dict(n=2, h=40, w=72, cins=[8], ks=[5], cout=2, act="relu", force_kind=4),
+    "ct_2seg_2k5_8k1_to1_f32": dict(n=2, h=40, w=136, cins=[2, 8], ks=[5, 1], cout=1, out_dtype="f32", act="relu", force_kind=4),
+    "ct_ragged_37x45_k3_4to2": dict(n=3, h=37, w=45, cins=[4, 5], ks=[3, 1], cout=2, act="lrelu", with_scale=True, force_kind=4),
+    "ct_k5_3to1_16bit_out": dict(n=1, h=19, w=130, cins=[3], ks=[5], cout=1, act="tanh", force_kind=4),
+    "ct_k3_8to1_f32_cs4": dict(n=1, h=16, w=64, cins=[8], ks=[3], cout=1, out_dtype="f32", out_cstride=4, force_kind=4),
     "forced_direct_16bit": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64, force_kind=2, act="relu"),
 }
 
@@ -61,6 +67,8 @@ def test_conv_case(name, half):
     assert r["rel_l2"] < tol, (name, r)
     if name.startswith("nf_"):
         assert r["kind"] == 3, r
+    if name.startswith("ct_") or name in ("direct_k5_8to2", "direct_2seg_to1_f32"):
+        assert r["kind"] == 4, r
 
 
 def test_flagship_shape_one_slice():
