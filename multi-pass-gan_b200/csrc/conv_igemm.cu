@@ -95,13 +95,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) s_shift[i] = p.shift[i];
   // epilogue warps: 4 (256-thread launch) or 8 (384-thread launch: two warps per TMEM lane quarter split the columns)
   const int n_epi_warps = (static_cast<int>(blockDim.x) >> 5) - 4;
-  const int epi_active = (n_epi_warps == 8 && !p.pixel_norm && !p.tma_store) ? 8 : 4;
+  const int epi_active = (n_epi_warps == 8 && !p.pixel_norm) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
     if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_w);
-    if (p.tma_store) tma_prefetch_desc(&tm_y);
     for (int i = 0; i < p.na; ++i) {
       mbar_init(&full_a[i], 1);
       mbar_init(&empty_a[i], 1);
@@ -135,7 +134,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   const bool act_tanh = p.act == MPG_ACT_TANH;
 
   if (warp == 0) {
-    // ===================== A producer: one halo image per (segment, chunk, dx) ===============
+    // ===================== A producer: one halo image per (segment, chunk) ===============
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
@@ -144,26 +143,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
           const int pad = ks >> 1;
-          const uint32_t bytes = static_cast<uint32_t>((kIgTileH + ks - 1) * kIgTileW * RB);
           const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
           const uint32_t hbytes = static_cast<uint32_t>((kIgTileH + ks - 1) * (kIgTileW + ks - 1) * RB);
           for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
-            for (int dx = 0; dx < (p.halo ? 1 : ks); ++dx) {
-              mbar_wait(&empty_a[st], ph ^ 1u);
-              if (PAIR) {
-                // both CTAs' images complete on the LEADER's barrier, which expects the bytes of both
-                if (rank == 0) mbar_arrive_expect_tx(&full_a[st], 2u * (p.halo ? hbytes : bytes));
-                tma_load_4d_2cta(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, mapa_u32(smem_u32(&full_a[st]), 0),
-                                 ch * CK, tc.x0 + dx - pad, tc.y0 - pad, tc.n);
-              } else {
-                mbar_arrive_expect_tx(&full_a[st], p.halo ? hbytes : bytes);
-                tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK,
-                            tc.x0 + dx - pad, tc.y0 - pad, tc.n);
-              }
-              if (++st == p.na) {
-                st = 0;
-                ph ^= 1u;
-              }
+            mbar_wait(&empty_a[st], ph ^ 1u);
+            if (PAIR) {
+              // both CTAs' images complete on the LEADER's barrier, which expects the bytes of both
+              if (rank == 0) mbar_arrive_expect_tx(&full_a[st], 2u * hbytes);
+              tma_load_4d_2cta(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, mapa_u32(smem_u32(&full_a[st]), 0),
+                               ch * CK, tc.x0 - pad, tc.y0 - pad, tc.n);
+            } else {
+              mbar_arrive_expect_tx(&full_a[st], hbytes);
+              tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, tc.x0 - pad,
+                          tc.y0 - pad, tc.n);
+            }
+            if (++st == p.na) {
+              st = 0;
+              ph ^= 1u;
             }
           }
         }
@@ -221,16 +217,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
   } else if (warp == 1 && (!PAIR || rank == 0)) {
     // ===================== MMA issuer (PAIR: leader CTA only) ==========================================================
-    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
-    // registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers); one lane,
+    // elected once, issues the tcgen05.mma / tcgen05.commit instructions. The loop body is kept to a few 32-bit adds
+    // per MMA: with CK = 32 a (dx, dy) tap is only 4 MMAs (256 tensor-pipe cycles), and the earlier loop (64-bit stage
+    // address products, per-tap re-derivation of both descriptor words) took ~290 cycles per tap -- the 32->128 layer
+    // was bound by this thread, not by the tensor pipe (knock-out runs, tools/thin_probe.py "skeleton").
     const uint32_t idesc = umma_idesc_f16kind(PAIR ? 256 : 128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
     // smem-descriptor words: hi = SBO | version 1 | layout type; lo = (addr >> 4) | LBO(1)
-    constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
-    constexpr uint32_t DESC_LO = 1u << 16;
+    constexpr uint32_t B_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t PX16 = RB >> 4;  // one pixel of the halo image in 16-byte descriptor units
+    const uint32_t smA_lo = ((smem_u32(smA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t smB_lo = ((smem_u32(smB) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+    const uint32_t b_stage16 = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+    const uint32_t b_tile16 = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
+    const uint32_t npad = static_cast<uint32_t>(p.npad);
+    const bool bres = p.bres != 0;
+    const bool do_mma = !(p.dbg & 4);
+    const int na = p.na, nb = p.nb, nseg = p.nseg;
+    const bool leader = elect_one() != 0;
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
-    if (p.bres) {
+    if (bres) {
       mbar_wait(&full_b[0], 0);
       tc_fence_after();
     }
@@ -238,193 +247,94 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       const int buf = it & 1;
       mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + static_cast<uint32_t>((buf * 2) * p.npad);
-      const uint32_t d1 = d0 + static_cast<uint32_t>(p.npad);
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(buf * 2) * npad;
+      const uint32_t d1 = d0 + npad;
       uint32_t accumulate = 0;
-      int kt = 0;  // k-tile index (resident-weights mode)
-      for (int s = 0; s < p.nseg; ++s) {
+      uint32_t b_res = smB_lo;  // resident-weights cursor (k-tile order == issue order)
+      for (int s = 0; s < nseg; ++s) {
         const int ks = p.seg_ks[s];
         const int gb = p.bgroup ? ks : 1;
-        const int pw = kIgTileW + ks - 1;  // halo image pitch in pixels (halo mode)
-        for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+        // 16 image rows x 8 px per accumulator: 8-row-group stride = one halo row; the start is shifted by whole
+        // pixels, i.e. NOT aligned to the swizzle atom (legal: the swizzle is a function of the absolute address)
+        const uint32_t row16 = static_cast<uint32_t>(kIgTileW + ks - 1) * PX16;
+        const uint32_t a_hi = row16 | (1u << 14) | (LAYOUT << 29);
+        const int nchunk = p.seg_nchunk[s];
+        for (int ch = 0; ch < nchunk; ++ch) {
+          mbar_wait(&full_a[sa], pa);
+          tc_fence_after();
+          const uint32_t a_img = smA_lo + static_cast<uint32_t>(sa) * a_stage16;
           for (int dx = 0; dx < ks; ++dx) {
-            if (!p.halo || dx == 0) {
-              mbar_wait(&full_a[sa], pa);
-              tc_fence_after();
-            }
-            const uint32_t a_addr = smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes);
-            const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | DESC_LO;
-            for (int dy0 = 0; dy0 < ks; dy0 += gb, kt += gb) {
-              if (!p.bres) {
+            uint32_t a_tap = a_img + static_cast<uint32_t>(dx) * PX16;
+            for (int dy0 = 0; dy0 < ks; dy0 += gb) {
+              uint32_t b_lo;
+              if (bres) {
+                b_lo = b_res;
+                b_res += static_cast<uint32_t>(gb) * b_tile16;
+              } else {
                 mbar_wait(&full_b[sb], pb);
                 tc_fence_after();
+                b_lo = smB_lo + static_cast<uint32_t>(sb) * b_stage16;
               }
-              const uint32_t b_lo = ((smem_u32(smB + (p.bres ? static_cast<size_t>(kt) * p.b_tile_bytes
-                                                               : static_cast<size_t>(sb) * p.b_stage_bytes)) & 0x3FFFFu) >> 4) | DESC_LO;
-              if (elect_one()) {
-                for (int g = 0; g < gb; ++g) {
-                  const uint32_t bg = b_lo + static_cast<uint32_t>((g * p.b_tile_bytes) >> 4);
-                  if (!p.halo) {
-                    const uint32_t ag = a_lo + static_cast<uint32_t>(((dy0 + g) * kIgTileW * RB) >> 4);
+              if (leader) {
+                uint32_t a_g = a_tap, b_g = b_lo, acc = accumulate;
+                if (do_mma) {
+                  for (int g = 0; g < gb; ++g) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
-                      const uint64_t ad0 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
-                      const uint64_t ad1 = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2 + ((128 * RB) >> 4));
-                      if (!(p.dbg & 4)) {
-                        if (PAIR) umma_bf16_ss_2cta(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                        if (PAIR) umma_bf16_ss_2cta(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
+                      const uint64_t bd = (static_cast<uint64_t>(B_HI) << 32) | (b_g + k * 2);
+                      const uint64_t ad0 = (static_cast<uint64_t>(a_hi) << 32) | (a_g + k * 2);
+                      const uint64_t ad1 = (static_cast<uint64_t>(a_hi) << 32) | (a_g + 8u * PX16 + k * 2);
+                      if (PAIR) {
+                        umma_bf16_ss_2cta(d0, ad0, bd, idesc, (k > 0) ? 1u : acc);
+                        umma_bf16_ss_2cta(d1, ad1, bd, idesc, (k > 0) ? 1u : acc);
+                      } else {
+                        umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : acc);
+                        umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : acc);
                       }
                     }
-                  } else {
-                    // 16 image rows x 8 px per accumulator: group stride = one halo row; the start is
-                    // shifted by whole pixels, i.e. NOT aligned to the swizzle atom
-                    const uint32_t off0 = static_cast<uint32_t>(((dy0 + g) * pw + dx) * RB);
-                    const uint32_t off1 = off0 + 8u * RB;
-                    const uint32_t hi = ((static_cast<uint32_t>(pw) * RB) >> 4) | (1u << 14) | (LAYOUT << 29);
-                    uint32_t hi0 = hi, hi1 = hi;
-                    if (p.halo_bo) {  // base_offset = (start >> 7) & 7, descriptor bits [49,52)
-                      hi0 |= (((a_addr + off0) >> 7) & 7u) << 17;
-                      hi1 |= (((a_addr + off1) >> 7) & 7u) << 17;
-                    }
-#pragma unroll
-                    for (int k = 0; k < KSTEPS; ++k) {
-                      const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (bg + k * 2);
-                      const uint64_t ad0 = (static_cast<uint64_t>(hi0) << 32) | (a_lo + (off0 >> 4) + k * 2);
-                      const uint64_t ad1 = (static_cast<uint64_t>(hi1) << 32) | (a_lo + (off1 >> 4) + k * 2);
-                      if (!(p.dbg & 4)) {
-                        if (PAIR) umma_bf16_ss_2cta(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d0, ad0, bd, idesc, (k > 0) ? 1u : accumulate);
-                        if (PAIR) umma_bf16_ss_2cta(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate); else umma_bf16_ss(d1, ad1, bd, idesc, (k > 0) ? 1u : accumulate);
-                      }
-                    }
+                    acc = 1;
+                    a_g += row16;
+                    b_g += b_tile16;
                   }
-                  accumulate = 1;
                 }
-                if (!p.bres) { if (PAIR) umma_commit_2cta(&empty_b[sb], 3); else umma_commit(&empty_b[sb]); }
+                if (!bres) {
+                  if (PAIR) umma_commit_2cta(&empty_b[sb], 3);
+                  else umma_commit(&empty_b[sb]);
+                }
               }
               __syncwarp();
               accumulate = 1;
-              if (!p.bres && ++sb == p.nb) {
+              a_tap += static_cast<uint32_t>(gb) * row16;
+              if (!bres && ++sb == nb) {
                 sb = 0;
                 pb ^= 1u;
               }
             }
-            if (!p.halo || dx == ks - 1) {
-              if (elect_one()) { if (PAIR) umma_commit_2cta(&empty_a[sa], 3); else umma_commit(&empty_a[sa]); }
-              __syncwarp();
-              if (++sa == p.na) {
-                sa = 0;
-                pa ^= 1u;
-              }
-            }
+          }
+          if (leader) {
+            if (PAIR) umma_commit_2cta(&empty_a[sa], 3);
+            else umma_commit(&empty_a[sa]);
+          }
+          __syncwarp();
+          if (++sa == na) {
+            sa = 0;
+            pa ^= 1u;
           }
         }
       }
-      if (elect_one()) { if (PAIR) umma_commit_2cta(&tmem_full[buf], 3); else umma_commit(&tmem_full[buf]); }
+      if (leader) {
+        if (PAIR) umma_commit_2cta(&tmem_full[buf], 3);
+        else umma_commit(&tmem_full[buf]);
+      }
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8 && p.tma_store) {
-    // ===================== epilogue A: TMEM -> registers -> swizzled smem -> TMA store =========
-    // (16-bit outputs) each thread owns one pixel row of the accumulator; its 16-byte channel chunks
-    // go to a staging tile laid out like a TMA box [128 px][box_c ch], one elected thread stores it.
-    const int ew = warp & 3;
-    const int m = ew * 32 + lane;
-    const int et = threadIdx.x - 128;
-    const float inv_c = 1.0f / static_cast<float>(p.cout);
-    const int od = p.out_dtype;
-    const int box_c = p.box_c;
-    const int row_b = box_c * 2;                // bytes per staged pixel row
-    const int cpb = box_c >> 3;                 // 16-byte chunks per box row
-    const uint32_t swz = (box_c == 64) ? static_cast<uint32_t>(m & 7)
-                         : (box_c == 32) ? static_cast<uint32_t>((m >> 1) & 3)
-                         : (box_c == 16) ? static_cast<uint32_t>((m >> 2) & 1) : 0u;
-    uint8_t* stg = smem + p.stage_off;
-    int it = 0;
-    for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
-      const int buf = it & 1;
-      const TileCoord tc = decode_tile(MPG_TILE_CLAMP(t), p);
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-      tc_fence_after();
-      if (it > 0) {  // the previous tile's stores must have finished reading the staging tiles
-        if (et == 0) tma_store_wait_read();
-        named_bar_sync(1, 128);
-      }
-      if (!(p.dbg & 2)) {
-#pragma unroll 1
-        for (int acc = 0; acc < 2; ++acc) {
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                                 static_cast<uint32_t>((buf * 2 + acc) * p.npad);
-          uint8_t* srow = stg + static_cast<size_t>(acc) * p.stage_bytes + static_cast<size_t>(m) * row_b;
-          float rn = 1.0f;
-          if (p.pixel_norm) {
-            float ssq = 0.0f;
-            for (int c0 = 0; c0 < p.npad; c0 += 16) {
-              float v[16];
-              epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) ssq = fmaf(v[j], v[j], ssq);
-            }
-            rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
-          }
-          for (int c0 = 0; c0 < p.npad; c0 += 16) {
-            float v[16];
-            epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= rn;
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const int cb = c0 + hq * 8;  // first channel of this 16-byte chunk
-              if (cb < p.out_cstride) {
-                const int bx = cb / box_c;
-                const uint32_t j = static_cast<uint32_t>((cb - bx * box_c) >> 3);
-                uint4 q;
-                q.x = pack_h16x2(v[hq * 8 + 0], v[hq * 8 + 1], od);
-                q.y = pack_h16x2(v[hq * 8 + 2], v[hq * 8 + 3], od);
-                q.z = pack_h16x2(v[hq * 8 + 4], v[hq * 8 + 5], od);
-                q.w = pack_h16x2(v[hq * 8 + 6], v[hq * 8 + 7], od);
-                *reinterpret_cast<uint4*>(srow + static_cast<size_t>(bx) * (128 * row_b) + ((j ^ swz) << 4)) = q;
-              }
-            }
-          }
-        }
-      }
-      // accumulators are drained: hand the TMEM buffer back before the stores are issued
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
-        else mbar_arrive(&tmem_empty[buf]);
-      }
-      fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (et == 0 && !(p.dbg & 1)) {
-        for (int acc = 0; acc < 2; ++acc) {
-          const int y = tc.y0 + acc * 8;
-          if (y >= p.h) continue;
-          for (int bx = 0; bx < p.nbox; ++bx) {
-            const uint8_t* src = stg + static_cast<size_t>(acc) * p.stage_bytes + static_cast<size_t>(bx) * (128 * row_b);
-            if (p.upsample == 1) {
-              tma_store_4d(&tm_y, src, bx * box_c, tc.x0, y, tc.n);
-            } else {
-              // output viewed as [N, H, 2, W, 2*cstride]: (ux, c) innermost, uy between W and H
-              for (int uy = 0; uy < 2; ++uy)
-                for (int ux = 0; ux < 2; ++ux)
-                  tma_store_5d(&tm_y, src, ux * p.out_cstride + bx * box_c, tc.x0, uy, y, tc.n);
-            }
-          }
-        }
-        tma_store_commit();
-      }
-      (void)cpb;
-    }
-    if (et == 0) tma_store_wait_all();
-  } else if (warp >= 4 && warp < 4 + epi_active && !p.tma_store) {
+  } else if (warp >= 4 && warp < 4 + epi_active) {
     // ===================== epilogue B (fp32 outputs): TMEM -> registers -> global ==============================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
     const int m = ew * 32 + lane;
-    // accumulator row m -> pixel: 8 rows x 16 px (dx-image mode) or 16 rows x 8 px (halo mode)
-    const int prow = p.halo ? (m >> 3) : (m >> 4);
-    const int pcol = p.halo ? (m & 7) : (m & 15);
+    // accumulator row m -> pixel: 16 image rows x 8 px
+    const int prow = m >> 3;
+    const int pcol = m & 7;
     const int ups = p.upsample;
     const int oh = p.h * ups, ow = p.w * ups;
     const float inv_c = 1.0f / static_cast<float>(p.cout);
@@ -441,8 +351,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       tc_fence_after();
 #pragma unroll 1
       for (int acc = 0; acc < 2; ++acc) {
-        const int y = tc.y0 + (p.halo ? 0 : acc * 8) + prow;
-        const int x = tc.x0 + (p.halo ? acc * 8 : 0) + pcol;
+        const int y = tc.y0 + prow;
+        const int x = tc.x0 + acc * 8 + pcol;
         const bool valid = (y < p.h) && (x < p.w) && (t < p.num_tiles) && !(p.dbg & 1);
         if (p.dbg & 2) continue;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +

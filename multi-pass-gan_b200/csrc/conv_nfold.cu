@@ -138,70 +138,93 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    // ===================== MMA issuer (warp-uniform loop, one lane elected once issues) ================
+    // lean 32-bit descriptor arithmetic only (see conv_igemm.cu: the issue loop, not the tensor pipe, bounded CK<=32 layers)
     const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
     constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
     // leading-dimension byte offset (distance between the two K halves): ignored when swizzled; NS8: A = one image
     // row, B = the npad/8 core matrices of the first K half
     constexpr uint32_t DESC_LO = NS8 ? ((ROW_BYTES >> 4) << 16) : (1u << 16);
+    constexpr uint32_t ROW16 = ROW_BYTES >> 4;
     const uint32_t b_desc_lo = NS8 ? ((static_cast<uint32_t>(p.npad) * 16u) >> 4) << 16 : (1u << 16);
+    const uint32_t smA_lo = ((smem_u32(smA) & 0x3FFFFu) >> 4) | DESC_LO;
+    const uint32_t smB_lo = ((smem_u32(smB) & 0x3FFFFu) >> 4) | b_desc_lo;
+    const uint32_t a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+    const uint32_t b_tile16 = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
+    const uint32_t npad = static_cast<uint32_t>(p.npad);
+    const int naccs = p.naccs, nbuf = p.nbuf, na = p.na, nb = p.nb, nseg = p.nseg;
+    const bool bres = p.bres != 0;
+    const bool do_mma = !(p.dbg & 4);
+    const bool leader = elect_one() != 0;
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    int it = 0;
-    if (p.bres) {
+    int buf = 0;
+    uint32_t use = 0;
+    if (bres) {
       mbar_wait(&full_b[0], 0);
       tc_fence_after();
     }
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const int buf = it % p.nbuf;
-      const uint32_t use = static_cast<uint32_t>(it / p.nbuf);
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * p.naccs * p.npad);
-      int kt = 0;
-      bool first = true;
-      for (int s = 0; s < p.nseg; ++s) {
+      const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * naccs) * npad;
+      uint32_t b_res = smB_lo;
+      uint32_t accumulate = 0;
+      for (int s = 0; s < nseg; ++s) {
         const int ks = p.seg_ks[s];
-        for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+        const int nchunk = p.seg_nchunk[s];
+        for (int ch = 0; ch < nchunk; ++ch) {
           mbar_wait(&full_a[sa], pa);
           tc_fence_after();
-          const uint32_t a_lo = ((smem_u32(smA + static_cast<size_t>(sa) * p.a_stage_bytes) & 0x3FFFFu) >> 4) | DESC_LO;
-          for (int dy = 0; dy < ks; dy += (NS8 ? 2 : 1), ++kt) {
-            if (!p.bres) {
+          uint32_t a_row = smA_lo + static_cast<uint32_t>(sa) * a_stage16;  // image row dy of the window
+          for (int dy = 0; dy < ks; dy += (NS8 ? 2 : 1)) {
+            uint32_t b_lo;
+            if (bres) {
+              b_lo = b_res;
+              b_res += b_tile16;
+            } else {
               mbar_wait(&full_b[sb], pb);
               tc_fence_after();
+              b_lo = smB_lo + static_cast<uint32_t>(sb) * b_tile16;
             }
-            const uint32_t b_lo = ((smem_u32(smB + static_cast<size_t>(p.bres ? kt : sb) * p.b_tile_bytes) & 0x3FFFFu) >> 4) | b_desc_lo;
-            if (elect_one()) {
-              for (int acc = 0; acc < p.naccs; ++acc) {
-                const uint32_t ag = a_lo + ((static_cast<uint32_t>(acc * kNfRowsAcc + dy) * ROW_BYTES) >> 4);
-                const uint32_t d = dbase + static_cast<uint32_t>(acc * p.npad);
+            if (leader) {
+              if (do_mma) {
+                uint32_t ag = a_row, d = dbase;
+                for (int acc = 0; acc < naccs; ++acc) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + k * 2);
-                  const uint64_t ad = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
-                  if (!(p.dbg & 4)) umma_bf16_ss(d, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + k * 2);
+                    const uint64_t ad = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
+                    umma_bf16_ss(d, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+                  }
+                  ag += static_cast<uint32_t>(kNfRowsAcc) * ROW16;
+                  d += npad;
                 }
               }
-              if (!p.bres) umma_commit(&empty_b[sb]);
+              if (!bres) umma_commit(&empty_b[sb]);
             }
             __syncwarp();
-            first = false;
-            if (!p.bres && ++sb == p.nb) {
+            accumulate = 1;
+            a_row += (NS8 ? 2u : 1u) * ROW16;
+            if (!bres && ++sb == nb) {
               sb = 0;
               pb ^= 1u;
             }
           }
-          if (elect_one()) umma_commit(&empty_a[sa]);
+          if (leader) umma_commit(&empty_a[sa]);
           __syncwarp();
-          if (++sa == p.na) {
+          if (++sa == na) {
             sa = 0;
             pa ^= 1u;
           }
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[buf]);
+      if (leader) umma_commit(&tmem_full[buf]);
       __syncwarp();
+      if (++buf == nbuf) {
+        buf = 0;
+        ++use;
+      }
     }
   } else if (warp >= 4 && warp < 4 + epi_active) {
     // ===================== epilogue: shifted sum over dx (warp shuffles) + shift + act + store ====

@@ -210,22 +210,18 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.in_dtype = d.in_dtype;
   ip.out_dtype = d.out_dtype;
   ip.out_cstride = d.out_cstride;
-  // halo mode (one TMA halo image per (segment, chunk), taps = shifted descriptors) is the default
+  // one TMA halo image per (segment, chunk); every (dy,dx) tap is a shifted UMMA descriptor into it. (The earlier
+  // per-dx-image staging and the staged TMA-store epilogue both measured slower on B200 and were removed.)
   ip.halo = 1;
-  if (const char* e = getenv("MPG_IGEMM_HALO")) ip.halo = atoi(e) ? 1 : 0;
   ip.halo_bo = 0;
   ip.tma_store = 0;
-  // measured on B200: the direct 16-byte st.global epilogue beats the staged TMA store (2 extra
-  // block barriers per tile), so the TMA-store epilogue is opt-in (MPG_IGEMM_TMASTORE=1, dx-image mode)
-  if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ip.tma_store = (atoi(e) && d.out_dtype != MPG_F32) ? 1 : 0;
-  if (ip.tma_store) ip.halo = 0;
   ip.a_stage_bytes = (kIgTileH + maxks - 1) * (ip.halo ? (kIgTileW + maxks - 1) : kIgTileW) * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
   ip.ktiles = ktiles;
   // CTA pairs (cta_group::2) for the layers that stream their weights: each CTA keeps half of every weight tile
-  ip.pair = (ip.halo && !ip.tma_store && npad % 32 == 0 && ip.tiles_x * ip.tiles_y * d.n >= 2 &&
+  ip.pair = (npad % 32 == 0 && ip.tiles_x * ip.tiles_y * d.n >= 2 &&
              static_cast<size_t>(ktiles) * round_up(npad * rb, 1024) > 64 * 1024) ? 1 : 0;
-  if (const char* e = getenv("MPG_IGEMM_PAIR")) ip.pair = (atoi(e) && ip.halo && !ip.tma_store && npad % 32 == 0) ? 1 : 0;
+  if (const char* e = getenv("MPG_IGEMM_PAIR")) ip.pair = (atoi(e) && npad % 32 == 0) ? 1 : 0;
   const int brows = ip.pair ? npad / 2 : npad;
   ip.b_tile_bytes = round_up(brows * rb, 1024);
   {

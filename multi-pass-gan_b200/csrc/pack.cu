@@ -26,13 +26,13 @@ struct PackParams {
 };
 
 __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) {
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long npix = static_cast<long long>(p.n) * p.oh * p.ow;
-  if (pix >= npix) return;
-  const int x = static_cast<int>(pix % p.ow);
-  const long long r = pix / p.ow;
-  const int y = static_cast<int>(r % p.oh);
-  const int n = static_cast<int>(r / p.oh);
+  // grid = (ceil(ow/256), n*oh): no 64-bit divisions per pixel (they, not the memory system, bounded this kernel)
+  const int x = static_cast<int>(blockIdx.x) * 256 + static_cast<int>(threadIdx.x);
+  if (x >= p.ow) return;
+  const int row = static_cast<int>(blockIdx.y);
+  const int n = row / p.oh;
+  const int y = row - n * p.oh;
+  const long long pix = static_cast<long long>(row) * p.ow + x;
   int oc = 0;
   if (p.out_dtype != MPG_F32 && (p.out_cstride & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
     // 16-bit output at a 16-byte pixel granularity: gather 8 channels in registers, one 128-bit store per chunk
@@ -206,8 +206,8 @@ int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* ou
   p.out_dtype = out_dtype;
   p.out_cstride = out_cstride;
   p.out = out;
-  const long long npix = static_cast<long long>(n) * oh * ow;
-  pack_channels_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CHECK_ARG(static_cast<long long>(n) * oh <= 65535, "pack: n*oh = %lld rows exceed the grid limit", static_cast<long long>(n) * oh);
+  pack_channels_kernel<<<dim3(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>(n * oh)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

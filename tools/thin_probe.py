@@ -25,6 +25,15 @@ SHAPES = [
 CONFIGS = {
     "default": {},
     "nf256": {"MPG_NFOLD_THREADS": "256"},
+    # knock-outs (results are wrong, timing only): bit0 no global stores, bit1 no epilogue at all, bit2 no MMAs
+    "nostore": {"MPG_IGEMM_DBG": "1", "MPG_NFOLD_DBG": "1"},
+    "noepi": {"MPG_IGEMM_DBG": "2", "MPG_NFOLD_DBG": "2"},
+    "nomma": {"MPG_IGEMM_DBG": "4", "MPG_NFOLD_DBG": "4"},
+    "skeleton": {"MPG_IGEMM_DBG": "6", "MPG_NFOLD_DBG": "6"},
+    "nobres": {"MPG_IGEMM_BRES": "0"},
+    "nopair": {"MPG_IGEMM_PAIR": "0"},
+    "nfck32": {"MPG_NFOLD_CK": "32"},
+    "nfck32_skel": {"MPG_NFOLD_CK": "32", "MPG_NFOLD_DBG": "6", "MPG_IGEMM_DBG": "6"},
 }
 KEYS = sorted({k for c in CONFIGS.values() for k in c})
 
