@@ -1,4 +1,6 @@
 // Tap-folded tcgen05 convolution for narrow Cout (design: conv_nfold.cuh).
+#include <string.h>
+
 #include "conv_nfold.cuh"
 #include "ptx.cuh"
 
@@ -21,7 +23,12 @@ __device__ __forceinline__ NfTile nf_decode(int t, const NfoldParams& p) {
   return c;
 }
 
-template <int CK, int KS>
+// PAIR (cta_group::2, cluster of 2; deep-K layers such as 5x5 128->32): each CTA keeps HALF of every weight tile
+// resident in shared memory for its whole lifetime (the full set does not fit next to the window images), the leader
+// issues M=256 MMAs over both CTAs' windows. With no weight traffic left a tile is ONE accumulator, so three of
+// them rotate through TMEM (3 x 160 columns) and the shuffle-sum epilogue of tile i overlaps the MMAs of i+1, i+2 --
+// the single-CTA configuration had to hold 3 accumulators per weight pass and could not overlap its epilogue.
+template <int CK, int KS, bool PAIR>
 __global__ void __maxnreg__(128)
 conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const __grid_constant__ CUtensorMap tm_w, const NfoldParams p) {
@@ -41,6 +48,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   __shared__ __align__(8) uint64_t full_a[kNfMaxStagesA], empty_a[kNfMaxStagesA];
   __shared__ __align__(8) uint64_t full_b[kNfMaxStagesB], empty_b[kNfMaxStagesB];
   __shared__ __align__(8) uint64_t tmem_full[kNfMaxBufs], tmem_empty[kNfMaxBufs];
+  __shared__ __align__(8) uint64_t b_ready;  // PAIR: both CTAs' resident weights have landed (leader's copy is used)
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[32];
 
@@ -51,6 +59,13 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // tile schedule: CTA q takes tiles q, q+G, ...; a PAIR takes tiles (2q, 2q+1) and both CTAs run the same number
+  // of iterations (an odd last tile is recomputed by the peer, not stored)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tstep = PAIR ? static_cast<int>(gridDim.x >> 1) * 2 : static_cast<int>(gridDim.x);
+  const int tfirst = PAIR ? static_cast<int>(blockIdx.x >> 1) * 2 + static_cast<int>(rank) : static_cast<int>(blockIdx.x);
+#define NF_TILE_LOOP(t) for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep)
+#define NF_TILE_CLAMP(t) ((t) < p.num_tiles ? (t) : p.num_tiles - 1)
 
   if (threadIdx.x < 32) s_shift[threadIdx.x] = threadIdx.x < p.cp ? p.shift[threadIdx.x] : 0.0f;
   // 4 epilogue warps (256-thread launch, two CTAs per SM) or 8 (384 threads: two warps per TMEM lane quarter take
@@ -70,16 +85,23 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
     for (int i = 0; i < kNfMaxBufs; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], epi_active);
+      mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * epi_active);  // one arrive per active epilogue warp (both CTAs in PAIR mode)
     }
+    mbar_init(&b_ready, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(&tmem_base_slot, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -88,8 +110,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const NfTile tc = nf_decode(t, p);
+      NF_TILE_LOOP(t) {
+        const NfTile tc = nf_decode(NF_TILE_CLAMP(t), p);
         for (int s = 0; s < p.nseg; ++s) {
           const int ks = p.seg_ks[s];
           // NS8 loads one more row: the unused second half of the last tap pair must read finite data
@@ -97,12 +119,18 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
           for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
             mbar_wait(&empty_a[st], ph ^ 1u);
+            if (PAIR) {  // both CTAs' windows complete on the LEADER's barrier, which expects the bytes of both
+              if (rank == 0) mbar_arrive_expect_tx(&full_a[st], 2u * bytes);
+              tma_load_4d_2cta(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, mapa_u32(smem_u32(&full_a[st]), 0),
+                               ch * CK, tc.gx0, tc.y0 - (ks >> 1), tc.n);
+            } else {
             mbar_arrive_expect_tx(&full_a[st], bytes);
             if (NS8)  // tensor viewed as [N][H][W*8]: inner coordinate in elements
               tma_load_3d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], tc.gx0 * 8, tc.y0 - (ks >> 1), tc.n);
             else
               tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, tc.gx0,
                           tc.y0 - (ks >> 1), tc.n);
+            }
             if (++st == p.na) {
               st = 0;
               ph ^= 1u;
@@ -117,7 +145,15 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       // weight tiles live in global memory in their swizzled smem image: plain bulk copies (see ptx.cuh)
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
       const uint32_t tile_bytes = static_cast<uint32_t>(p.b_tile_bytes);
-      if (p.bres) {
+      if (PAIR) {
+        // resident halves: k-tile kt of this CTA = rows [rank*N/2, (rank+1)*N/2) of the full tile (whole swizzle atoms)
+        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+        for (int kt = 0; kt < p.ktiles; ++kt)
+          bulk_load_1d(smB + static_cast<size_t>(kt) * tile_bytes,
+                       wsrc + (static_cast<size_t>(kt) * 2 + rank) * tile_bytes, tile_bytes, &full_b[0]);
+        mbar_wait(&full_b[0], 0);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready), 0));
+      } else if (p.bres) {
         mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
         bulk_load_1d(smB, wsrc, tile_bytes * static_cast<uint32_t>(p.ktiles), &full_b[0]);
       } else {
@@ -137,10 +173,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one lane elected once issues) ================
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
+    // ===================== MMA issuer (warp-uniform loop, one lane elected once issues; PAIR: leader CTA only) =====
     // lean 32-bit descriptor arithmetic only (see conv_igemm.cu: the issue loop, not the tensor pipe, bounded CK<=32 layers)
-    const uint32_t idesc = umma_idesc_f16kind(128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
+    const uint32_t idesc = umma_idesc_f16kind(PAIR ? 256 : 128, p.npad, p.in_dtype == MPG_F16 ? 0u : 1u);
     constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);
     // leading-dimension byte offset (distance between the two K halves): ignored when swizzled; NS8: A = one image
     // row, B = the npad/8 core matrices of the first K half
@@ -160,11 +196,14 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     uint32_t pa = 0, pb = 0;
     int buf = 0;
     uint32_t use = 0;
-    if (bres) {
+    if (PAIR) {
+      mbar_wait_cluster(&b_ready, 0);
+      tc_fence_after();
+    } else if (bres) {
       mbar_wait(&full_b[0], 0);
       tc_fence_after();
     }
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    NF_TILE_LOOP(t) {
       mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t dbase = tmem_base + static_cast<uint32_t>(buf * naccs) * npad;
@@ -195,7 +234,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                   for (int k = 0; k < KSTEPS; ++k) {
                     const uint64_t bd = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + k * 2);
                     const uint64_t ad = (static_cast<uint64_t>(DESC_HI) << 32) | (ag + k * 2);
-                    umma_bf16_ss(d, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+                    if (PAIR) umma_bf16_ss_2cta(d, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+                    else umma_bf16_ss(d, ad, bd, idesc, (k > 0) ? 1u : accumulate);
                   }
                   ag += static_cast<uint32_t>(kNfRowsAcc) * ROW16;
                   d += npad;
@@ -211,7 +251,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
               pb ^= 1u;
             }
           }
-          if (leader) umma_commit(&empty_a[sa]);
+          if (leader) {
+            if (PAIR) umma_commit_2cta(&empty_a[sa], 3);
+            else umma_commit(&empty_a[sa]);
+          }
           __syncwarp();
           if (++sa == na) {
             sa = 0;
@@ -219,7 +262,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           }
         }
       }
-      if (leader) umma_commit(&tmem_full[buf]);
+      if (leader) {
+        if (PAIR) umma_commit_2cta(&tmem_full[buf], 3);
+        else umma_commit(&tmem_full[buf]);
+      }
       __syncwarp();
       if (++buf == nbuf) {
         buf = 0;
@@ -238,10 +284,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const int cgrp = (warp - 4) >> 2;           // chunk parity this warp handles when 8 warps are active
     const bool all_chunks = epi_active == 4;
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it % p.nbuf;
       const uint32_t use = static_cast<uint32_t>(it / p.nbuf);
-      const NfTile tc = nf_decode(t, p);
+      const NfTile tc = nf_decode(NF_TILE_CLAMP(t), p);
       mbar_wait(&tmem_full[buf], use & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -249,7 +295,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         if (p.dbg & 2) continue;
         const int y = tc.y0 + acc * kNfRowsAcc + ew;
         const int gx = tc.gx0 + lane;
-        const bool valid = lane_valid && (y < p.h) && (gx < p.w) && !(p.dbg & 1);
+        const bool valid = lane_valid && (y < p.h) && (gx < p.w) && (t < p.num_tiles) && !(p.dbg & 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                                static_cast<uint32_t>((buf * p.naccs + acc) * p.npad);
         float o[32];
@@ -305,34 +351,47 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
+#undef NF_TILE_LOOP
+#undef NF_TILE_CLAMP
 }
 
 }  // namespace
 
 typedef void (*NfKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const NfoldParams);
 
-static NfKernel nf_kernel(int ck, int ks) {
-  if (ck == 8) return ks == 5 ? conv_nfold_kernel<8, 5> : conv_nfold_kernel<8, 3>;
-  if (ks == 5) return ck == 64 ? conv_nfold_kernel<64, 5> : (ck == 32 ? conv_nfold_kernel<32, 5> : conv_nfold_kernel<16, 5>);
-  return ck == 64 ? conv_nfold_kernel<64, 3> : (ck == 32 ? conv_nfold_kernel<32, 3> : conv_nfold_kernel<16, 3>);
+static NfKernel nf_kernel(int ck, int ks, int pair) {
+  if (pair) {
+    if (ks == 5) return ck == 64 ? conv_nfold_kernel<64, 5, true> : conv_nfold_kernel<32, 5, true>;
+    return ck == 64 ? conv_nfold_kernel<64, 3, true> : conv_nfold_kernel<32, 3, true>;
+  }
+  if (ck == 8) return ks == 5 ? conv_nfold_kernel<8, 5, false> : conv_nfold_kernel<8, 3, false>;
+  if (ks == 5)
+    return ck == 64 ? conv_nfold_kernel<64, 5, false> : (ck == 32 ? conv_nfold_kernel<32, 5, false> : conv_nfold_kernel<16, 5, false>);
+  return ck == 64 ? conv_nfold_kernel<64, 3, false> : (ck == 32 ? conv_nfold_kernel<32, 3, false> : conv_nfold_kernel<16, 3, false>);
 }
 
-static size_t g_nf_smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static size_t g_nf_smem_attr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes) {
-  const int slot = (ck == 8) ? (ks == 5 ? 6 : 7) : (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3);
+int nfold_set_smem_attr(int ck, int ks, int pair, size_t smem_bytes) {
+  const int slot = pair ? 8 + (ck == 64 ? 0 : 1) + (ks == 5 ? 0 : 2)
+                        : ((ck == 8) ? (ks == 5 ? 6 : 7) : (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3));
   if (smem_bytes <= g_nf_smem_attr[slot]) return 0;
-  cudaError_t e = cudaFuncSetAttribute(nf_kernel(ck, ks), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(nf_kernel(ck, ks, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
   if (e == cudaSuccess) g_nf_smem_attr[slot] = smem_bytes;
   return static_cast<int>(e);
@@ -340,8 +399,24 @@ int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes) {
 
 int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream) {
-  nf_kernel(ck, p.seg_ks[0])<<<grid, p.threads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
-  return static_cast<int>(cudaGetLastError());
+  if (!p.pair) {
+    nf_kernel(ck, p.seg_ks[0], 0)<<<grid, p.threads, smem_bytes, stream>>>(tm_x0, tm_x1, tm_w, p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(p.threads), 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, nf_kernel(ck, p.seg_ks[0], 1), tm_x0, tm_x1, tm_w, p));
 }
 
 }  // namespace mpg

@@ -46,6 +46,7 @@ struct NfoldParams {
   int na, nb;
   int a_stage_bytes, b_tile_bytes;
   int bres, ktiles;
+  int pair;  // cta_group::2 CTA pairs with resident half weight tiles, one accumulator per tile (conv_nfold.cu)
   int threads;  // launch block size: 256 or 384
   int dbg;  // profiling only (env MPG_NFOLD_DBG): bit0 skip stores, bit1 skip the whole epilogue body, bit2 skip MMAs
   uint32_t tmem_cols;
@@ -56,6 +57,6 @@ struct NfoldParams {
 
 int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
-int nfold_set_smem_attr(int ck, int ks, size_t smem_bytes);
+int nfold_set_smem_attr(int ck, int ks, int pair, size_t smem_bytes);
 
 }  // namespace mpg

@@ -427,6 +427,24 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     q.naccs = 512 / npad;
     q.nbuf = 1;
   }
+  // CTA pairs with resident half weight tiles (conv_nfold.cu PAIR): deep-K layers whose weights neither fit one CTA's
+  // shared memory nor leave TMEM room to double-buffer a 3-accumulator weight pass (5x5 128->32: N = 160)
+  {
+    int cin_total = 0;
+    for (int s = 0; s < d.nseg; ++s) cin_total += d.seg_cin[s];
+    const size_t half = static_cast<size_t>(npad / 2) * rb;
+    const size_t a_stage1 = round_up((kNfRowsAcc + ks0 - 1) * kNfWin * rb, 1024);
+    bool pair = !ns8 && ck >= 32 && npad % 32 == 0 && half % 1024 == 0 && cin_total >= 64 && 2 * npad <= 512 &&
+                static_cast<size_t>(ktiles) * round_up(npad * rb, 1024) > 64 * 1024 &&
+                static_cast<size_t>(ktiles) * half + 3 * a_stage1 <= 200 * 1024 &&
+                d.n * ceil_div(d.h, kNfRowsAcc) * ceil_div(d.w, kNfWin - (ks0 - 1)) >= 2;
+    if (const char* e = getenv("MPG_NFOLD_PAIR")) pair = pair && atoi(e) != 0;
+    q.pair = pair ? 1 : 0;
+    if (pair) {
+      q.naccs = 1;
+      q.nbuf = 512 / npad > 4 ? 4 : 512 / npad;
+    }
+  }
   if (const char* e = getenv("MPG_NFOLD_NACCS")) {
     const int a = atoi(e);
     if (a >= 1 && a * npad <= 512) q.naccs = a;
@@ -458,12 +476,17 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   q.ktiles = ktiles;
   q.bres = (static_cast<size_t>(ktiles) * q.b_tile_bytes <= 64 * 1024) ? 1 : 0;
   if (const char* e = getenv("MPG_NFOLD_BRES")) q.bres = (atoi(e) && static_cast<size_t>(ktiles) * q.b_tile_bytes <= 128 * 1024) ? 1 : 0;
+  if (q.pair) {
+    q.b_tile_bytes = (npad / 2) * rb;  // this CTA's half of a k-tile
+    q.bres = 1;
+  }
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(q.nbuf * q.naccs * npad)) cols <<= 1;
   q.tmem_cols = cols;
   const int b_bytes_min = q.bres ? ktiles * q.b_tile_bytes : 3 * q.b_tile_bytes;
   int occ = (cols <= 256 && b_bytes_min + 2 * q.a_stage_bytes <= 100 * 1024) ? 2 : 1;
   if (const char* e = getenv("MPG_NFOLD_OCC")) occ = atoi(e) > 0 ? atoi(e) : 1;
+  if (q.pair) occ = 1;
   q.threads = (occ == 1) ? kNfMaxThreads : kNfThreads;
   if (const char* e = getenv("MPG_NFOLD_THREADS")) q.threads = atoi(e) == 384 ? 384 : 256;
   const int budget = (210 * 1024) / occ - (occ > 1 ? 2048 : 0);
@@ -489,7 +512,13 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   if (const char* e = getenv("MPG_NFOLD_DBG")) q.dbg = atoi(e);
   p->smem_bytes = static_cast<size_t>(na) * q.a_stage_bytes + static_cast<size_t>(nb) * q.b_tile_bytes + 1024;
   p->grid = q.num_tiles < p->h->sm_count * occ ? q.num_tiles : p->h->sm_count * occ;
-  int r = nfold_set_smem_attr(ck, ks0, p->smem_bytes);
+  if (q.pair) {  // whole pairs only; a pair covers two tiles
+    const int pairs_needed = (q.num_tiles + 1) / 2;
+    int pairs = p->h->sm_count / 2;
+    if (pairs > pairs_needed) pairs = pairs_needed;
+    p->grid = pairs * 2;
+  }
+  int r = nfold_set_smem_attr(ck, ks0, q.pair, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(nfold, max dynamic smem %zu) failed: %s", p->smem_bytes,
               cudaGetErrorString(static_cast<cudaError_t>(r)));

@@ -37,6 +37,11 @@ CASES = {
     "direct_f32_k5_4to8_up4": dict(n=2, h=64, w=64, cins=[4], ks=[5], cout=8, in_dtype="f32", in_upsample=4, act="relu"),
     "direct_k5_8to2": dict(n=1, h=40, w=40, cins=[8], ks=[5], cout=2, act="relu"),
     "direct_2seg_to1_f32": dict(n=1, h=40, w=40, cins=[2, 8], ks=[5, 1], cout=1, out_dtype="f32", act="relu"),
+    # tap-folded CTA-pair configuration (resident half weight tiles, one accumulator per tile, 3 TMEM buffers)
+    "nfp_k5_128to32_odd_tiles": dict(n=1, h=12, w=28, cins=[128], ks=[5], cout=32, act="relu", force_kind=3),
+    "nfp_k5_128to32_ragged": dict(n=3, h=37, w=45, cins=[128], ks=[5], cout=32, act="lrelu", force_kind=3),
+    "nfp_k3_128to32_pn": dict(n=2, h=40, w=72, cins=[128], ks=[3], cout=32, act="relu", pixel_norm=True, force_kind=3),
+    "nfp_k5_96and32_to24_f32": dict(n=1, h=33, w=64, cins=[96, 32], ks=[5, 1], cout=24, out_dtype="f32", act="relu", force_kind=3),
     "direct_f32_k4s2": dict(n=2, h=64, w=64, cins=[2], ks=[4], cout=32, in_dtype="f32", out_dtype="f32", stride=2, act="lrelu"),
     "direct_f32_k4s1": dict(n=2, h=8, w=8, cins=[16], ks=[4], cout=24, in_dtype="f32", out_dtype="f32", stride=1, act="lrelu"),
     "direct_f32_128_pn_up2": dict(n=1, h=24, w=24, cins=[128, 6], ks=[3, 1], cout=128, in_dtype="f32", out_dtype="f32",
