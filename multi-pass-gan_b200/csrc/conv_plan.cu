@@ -248,7 +248,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
   ip.box_c = (d.out_cstride % 64 == 0) ? 64 : (d.out_cstride % 32 == 0) ? 32 : (d.out_cstride % 16 == 0) ? 16 : 8;
   ip.nbox = d.out_cstride / ip.box_c;
-  ip.stage_bytes = ip.tma_store ? round_up(128 * d.out_cstride * 2, 1024) : 0;
+  ip.stage_bytes = 0;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
   // CTAs per SM: thin layers are latency bound per tile (TMA round trips), not throughput bound, so two
@@ -261,7 +261,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   // 8 epilogue warps when the SM holds one CTA (two 256-thread CTAs need the registers)
   ip.threads = (occ == 1) ? kIgMaxThreads : kIgThreads;
   if (const char* e = getenv("MPG_IGEMM_THREADS")) ip.threads = atoi(e) == 384 ? 384 : 256;
-  const int budget = (210 * 1024) / occ - 2 * ip.stage_bytes - (occ > 1 ? 2048 : 0);
+  const int budget = (210 * 1024) / occ - (occ > 1 ? 2048 : 0);
   int nb, na;
   if (ip.bres) {
     nb = 1;
@@ -279,11 +279,26 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   na = na > kIgMaxStagesA ? kIgMaxStagesA : na;
   if (const char* e = getenv("MPG_IGEMM_NA")) na = atoi(e);
   if (nb < 1 || nb > kIgMaxStagesB || na < 2 || na > kIgMaxStagesA ||
-      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + 2 * ip.stage_bytes > 224 * 1024 ||
+      static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes > 224 * 1024 ||
       cols * static_cast<uint32_t>(occ) > 512u) {
     set_error("conv: bad pipeline depth na=%d nb=%d occ=%d (a_stage %d B, b_stage %d B)", na, nb, occ, ip.a_stage_bytes,
               ip.b_stage_bytes);
     return MPG_EINVAL;
+  }
+  // per-warp staged TMA-store epilogue (conv_igemm.cu): 16-bit outputs made of whole 64-channel groups; needs 4 KB of
+  // staging per epilogue warp next to the rings (one A stage is given up for it when that keeps >= 2)
+  {
+    const int epi_warps = (ip.threads == kIgMaxThreads && !d.pixel_norm) ? 8 : 4;
+    bool ts = is_h16(d.out_dtype) && d.upsample == 1 && d.cout % 64 == 0 && d.out_cstride == d.cout && occ == 1 &&
+              (epi_warps == 4 || npad % 128 == 0);
+    if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ts = ts && atoi(e) != 0;
+    const size_t staging = static_cast<size_t>(epi_warps) * 4096;
+    if (ts) {
+      while (na > 2 && static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + staging > 223 * 1024) --na;
+      ts = static_cast<size_t>(na) * ip.a_stage_bytes + static_cast<size_t>(nb) * ip.b_stage_bytes + staging <= 223 * 1024;
+    }
+    ip.tma_store = ts ? 1 : 0;
+    ip.stage_bytes = ts ? static_cast<int>(staging) : 0;
   }
   ip.nb = nb;
   ip.na = na;
@@ -291,7 +306,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.tmem_cols = cols;
   ip.shift = p->d_shift;
   ip.stage_off = ip.na * ip.a_stage_bytes + ip.nb * ip.b_stage_bytes;
-  p->smem_bytes = static_cast<size_t>(ip.stage_off) + 2 * static_cast<size_t>(ip.stage_bytes) + 1024;
+  p->smem_bytes = static_cast<size_t>(ip.stage_off) + static_cast<size_t>(ip.stage_bytes) + 1024;
   p->grid = ip.num_tiles < p->h->sm_count * occ ? ip.num_tiles : p->h->sm_count * occ;
   if (const char* e = getenv("MPG_IGEMM_GRID")) p->grid = atoi(e) > 0 ? atoi(e) : p->grid;
   if (ip.pair) {  // whole pairs only; a pair covers two tiles
@@ -717,27 +732,14 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
     mpg::IgemmParams ip = p->ip;
     ip.out = y;
     if (ip.tma_store && p->tm_y_ptr != y) {
+      // per-warp store box: 64 channels x 8 px x 4 image rows, 128B-swizzled staging
       const CUtensorMapDataType dt = d.out_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-      const CUtensorMapSwizzle sw = ip.box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                    : ip.box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                    : ip.box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
       const uint64_t cs = static_cast<uint64_t>(d.out_cstride) * 2;
-      int r;
-      if (d.upsample == 1) {
-        const uint64_t dims[4] = {static_cast<uint64_t>(d.out_cstride), static_cast<uint64_t>(d.w),
-                                  static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
-        const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
-        const uint32_t box[4] = {static_cast<uint32_t>(ip.box_c), mpg::kIgTileW, 8u, 1u};
-        r = mpg::encode_tmap(p->h, &p->tm_y, dt, 4, y, dims, strides, box, sw);
-      } else {
-        // [N, H, 2, W, 2*cstride] view of the [N, 2H, 2W, cstride] output: each pixel is stored 4 times
-        const uint64_t ow = 2ull * d.w;
-        const uint64_t dims[5] = {2ull * d.out_cstride, static_cast<uint64_t>(d.w), 2ull, static_cast<uint64_t>(d.h),
-                                  static_cast<uint64_t>(d.n)};
-        const uint64_t strides[4] = {2 * cs, ow * cs, 2 * ow * cs, 2ull * d.h * ow * cs};
-        const uint32_t box[5] = {static_cast<uint32_t>(ip.box_c), mpg::kIgTileW, 1u, 8u, 1u};
-        r = mpg::encode_tmap(p->h, &p->tm_y, dt, 5, y, dims, strides, box, sw);
-      }
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.out_cstride), static_cast<uint64_t>(d.w),
+                                static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+      const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+      const uint32_t box[4] = {64u, 8u, 4u, 1u};
+      int r = mpg::encode_tmap(p->h, &p->tm_y, dt, 4, y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (r) return r;
       p->tm_y_ptr = y;
     }
