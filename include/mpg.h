@@ -215,6 +215,16 @@ int mpg_train_conv_dgrad(mpg_handle h, const float* dy, const float* w, float* d
 /* dw += Conv2DBackpropFilter, dbias += sum dy (dbias may be NULL); scratch: cout doubles */
 int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* dw, float* dbias, double* scratch,
                          int n, int hh, int ww, int cin, int cout, int k, int stride, int in_up, void* stream);
+/* Tensor-core filter gradient (csrc/conv_wgrad_tc.cu): dw[k,k,cin,cout] (fp32 HWIO) += Conv2DBackpropFilter(x, dy)
+ * of a stride-1 SAME conv, x / dy bf16 NHWC with channel stride == channel count. Supported: k in {1,3,5},
+ * w % 16 == 0, one of (cin, cout) == 128 and the other in {32, 64, 128}; other shapes return MPG_ENOSUP
+ * (use mpg_train_conv_wgrad). Replaces the backward of tf.nn.conv2d (tools_wscale/GAN.py:691) inside
+ * tf.train.AdamOptimizer.minimize (GAN/multipassGAN-4x.py:889-898). */
+int mpg_train_conv_wgrad_tc(mpg_handle h, const void* x, const void* dy, float* dw, int n, int hh, int ww, int cin,
+                            int cout, int k, void* stream);
+/* dbias[cout] += column sums of dy[rows, cout]; scratch: >= cout doubles */
+int mpg_train_bias_grad(mpg_handle h, const float* dy, float* dbias, double* scratch, long long rows, int cout,
+                        void* stream);
 /* tf.contrib.layers.batch_norm(is_training=True) (+ activation) and its moving-average update
  * (tools_wscale/GAN.py:110; UPDATE_OPS GAN/multipassGAN-4x.py:776-779). scratch: 2*c doubles */
 int mpg_train_bn_fwd(mpg_handle h, const float* x, const float* gamma, const float* beta, float* y, float* mean,

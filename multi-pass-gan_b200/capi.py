@@ -96,6 +96,8 @@ def lib():
     L.mpg_train_conv_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_train_conv_dgrad.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_train_conv_wgrad.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_conv_wgrad_tc.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_bias_grad.argtypes = [vp, vp, vp, vp, ll, ip, vp]
     L.mpg_train_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ip, fl, fl, ip, vp]
     L.mpg_train_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, ip, ip, vp]
     L.mpg_train_act_fwd.argtypes = [vp, vp, vp, ll, ip, vp]

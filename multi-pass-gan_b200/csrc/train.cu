@@ -579,6 +579,18 @@ int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* d
   return MPG_OK;
 }
 
+/* dbias[cout] += sum over rows of dy[rows, cout] (the bias half of mpg_train_conv_wgrad, for callers that compute the
+ * filter gradient with mpg_train_conv_wgrad_tc); `scratch`: >= cout doubles */
+int mpg_train_bias_grad(mpg_handle h, const float* dy, float* dbias, double* scratch, long long rows, int cout, void* stream) {
+  MPG_CHECK_ARG(h && dy && dbias && scratch && rows > 0 && cout > 0, "mpg_train_bias_grad: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * cout, st));
+  colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(dy, nullptr, nullptr, nullptr, scratch, rows, cout, 2);
+  dsum_to_f32_kernel<<<(cout + 255) / 256, 256, 0, st>>>(scratch, dbias, cout, 1);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
 /* training-mode batch norm (tf.contrib.layers.batch_norm, is_training=True, tools_wscale/GAN.py:110):
  * batch mean / biased variance over all rows, y = act(gamma * (x - mean) * rsqrt(var + eps) + beta);
  * moving statistics updated in place with `decay` when moving_mean != NULL. scratch: 2*c doubles. */

@@ -81,6 +81,9 @@ class _Conv:
         # the same kernel with bf16 gradients (range) and flipped/transposed weights; wgrad stays fp32
         self.fast = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1 and cin % 8 == 0
                      and cout % 8 == 0 and max(cin, cout) >= 32)
+        # filter gradient on the tensor cores (csrc/conv_wgrad_tc.cu): bf16 copies of the input and of the output gradient
+        self.fast_w = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1
+                       and ((cin == 128 and cout in (32, 64, 128)) or (cout == 128 and cin in (32, 64))))
         self.plan_f = self.plan_d = None
 
     def build_plans(self, n, h, w):
@@ -145,18 +148,30 @@ class _Conv:
             tr.call("act_bwd", sv["y"], dy, dlin, rows * self.cout, self.act, tr.st)
         else:
             dlin = dy
-        if param_grads:
+        g16 = None
+        use_wtc = param_grads and self.fast_w and sv["w"] % 16 == 0
+        if use_wtc or (dx is not None and self.fast):
+            g16 = tr.buf16(tuple(dlin.shape), torch.bfloat16)
+            capi.pack_channels(tr.h, [(dlin, capi.F32, self.cout, 0, self.cout, 1, 1)], g16, capi.BF16, self.cout, sv["n"],
+                               sv["h"], sv["w"], tr.st)
+            tr.launches += 1
+        if use_wtc:
+            xb = tr.buf16(tuple(sv["x"].shape), torch.bfloat16)
+            capi.pack_channels(tr.h, [(sv["x"], capi.F32, self.cin, 0, self.cin, 1, 1)], xb, capi.BF16, self.cin, sv["n"],
+                               sv["h"], sv["w"], tr.st)
+            tr.launches += 1
+            tr.call("conv_wgrad_tc", xb, g16, ps.view(ps.gw, self.wn), sv["n"], sv["h"], sv["w"], self.cin, self.cout, self.k,
+                    tr.st)
+            tr.call("bias_grad", dlin, ps.view(ps.gw, self.bn_), tr.scratch, rows, self.cout, tr.st)
+        elif param_grads:
             tr.call("conv_wgrad", sv["x"], dlin, ps.view(ps.gw, self.wn), ps.view(ps.gw, self.bn_), tr.scratch, sv["n"],
                     sv["h"], sv["w"], self.cin, self.cout, self.k, self.stride, self.in_up, tr.st)
         if dx is not None:
             assert self.in_up == 1
             if self.fast:
-                g16 = tr.buf16(tuple(dlin.shape), torch.bfloat16)
-                capi.pack_channels(tr.h, [(dlin, capi.F32, self.cout, 0, self.cout, 1, 1)], g16, capi.BF16, self.cout, sv["n"],
-                                   sv["h"], sv["w"], tr.st)
                 tgt = tr.buf(tuple(dx.shape)) if accumulate else dx
                 self.plan_d.run(g16, None, tgt, tr.st)
-                tr.launches += 2
+                tr.launches += 1
                 if accumulate:
                     tr.call("axpy", dx, tgt, 1.0, dx.numel(), tr.st)
             else:

@@ -125,3 +125,39 @@ def test_training_tensor_core_mode_tracks_oracle():
     gg = tr.grads("g")
     for name in ("generator/g_cB1/weight", "generator/g_cA1/weight", "generator/g_cA2/weight", "generator/g_cA0/weight"):
         assert _rel(gg[name], ref["grads_g"][name]) <= 5e-2, (name, _rel(gg[name], ref["grads_g"][name]))
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 64, 128, 128, 5), (3, 9, 32, 32, 128, 5), (2, 16, 16, 128, 32, 5),
+                                   (2, 8, 32, 32, 128, 1), (1, 10, 48, 64, 128, 3), (2, 7, 32, 128, 64, 3)])
+def test_wgrad_tensor_core_vs_torch_autograd(shape):
+    """mpg_train_conv_wgrad_tc (tcgen05, MN-major operands straight from NHWC) vs torch autograd in fp64 on the SAME
+    bf16-rounded inputs: the only difference left is fp32 accumulation order, so the bound is tight (2e-5 rel-L2).
+    Covers both operand roles (Cin = 128 / Cout = 128), the 64-byte-swizzle 32-channel operand, k = 1/3/5, non-square
+    images and a second call accumulating on top of the first (dw += ...)."""
+    n, hh, ww, cin, cout, k = shape
+    h = capi.default_handle(0)
+    from oracle import tf_ops
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((n, hh, ww, cin)).astype(np.float32)).to(torch.bfloat16)
+    dy = torch.from_numpy((rng.standard_normal((n, hh, ww, cout)) * 1e-3).astype(np.float32)).to(torch.bfloat16)
+    wt = torch.zeros((k, k, cin, cout), dtype=torch.float64, requires_grad=True)
+    yt = tf_ops.conv2d_same(x.double(), wt, 1)
+    yt.backward(dy.double())
+    ref = wt.grad.numpy()
+    gw = torch.zeros((k, k, cin, cout), device="cuda")
+    xd, dyd = x.cuda().contiguous(), dy.cuda().contiguous()
+    capi.train_call("conv_wgrad_tc", h, xd, dyd, gw, n, hh, ww, cin, cout, k, 0)
+    torch.cuda.synchronize()
+    assert _rel(gw.cpu().numpy(), ref) < 2e-5, (shape, _rel(gw.cpu().numpy(), ref))
+    capi.train_call("conv_wgrad_tc", h, xd, dyd, gw, n, hh, ww, cin, cout, k, 0)
+    torch.cuda.synchronize()
+    assert _rel(gw.cpu().numpy(), 2.0 * ref) < 2e-5, shape
+
+
+def test_wgrad_tensor_core_rejects_unsupported_shapes():
+    h = capi.default_handle(0)
+    x = torch.zeros((1, 8, 16, 32), dtype=torch.bfloat16, device="cuda")
+    dy = torch.zeros((1, 8, 16, 8), dtype=torch.bfloat16, device="cuda")
+    gw = torch.zeros((5, 5, 32, 8), device="cuda")
+    with pytest.raises(Exception):
+        capi.train_call("conv_wgrad_tc", h, x, dy, gw, 1, 8, 16, 32, 8, 5, 0)
