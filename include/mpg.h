@@ -252,6 +252,9 @@ int mpg_train_l2_half(mpg_handle h, const float* a, const float* b, float scale,
 int mpg_train_adam(mpg_handle h, float* param, const float* grad, float* m, float* v, long long count, float lr_t,
                    float beta1, float beta2, float eps, void* stream);
 /* GAN.fully_connected_layer with one output (tools_wscale/GAN.py:438-456; d_l5) */
+/* same, lr_t read from a device scalar (so a captured CUDA graph of the step can be replayed) */
+int mpg_train_adam_dev(mpg_handle h, float* param, const float* grad, float* m, float* v, long long count,
+                       const float* lr_t_dev, float beta1, float beta2, float eps, void* stream);
 int mpg_train_fc_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int rows, int nin,
                      void* stream);
 int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* dy, float* dx, float* dw,

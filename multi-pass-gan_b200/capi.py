@@ -109,6 +109,7 @@ def lib():
     L.mpg_train_l1_mean.argtypes = [vp, vp, vp, fl, vp, vp, ll, ip, vp]
     L.mpg_train_l2_half.argtypes = [vp, vp, vp, fl, vp, vp, ll, ip, vp]
     L.mpg_train_adam.argtypes = [vp, vp, vp, vp, vp, ll, fl, fl, fl, fl, vp]
+    L.mpg_train_adam_dev.argtypes = [vp, vp, vp, vp, vp, ll, vp, fl, fl, fl, vp]
     L.mpg_train_fc_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_fc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_take_channel.argtypes = [vp, vp, vp, ll, ip, ip, ip, vp]

@@ -19,6 +19,12 @@ __host__ __device__ inline int same_pad_before_tf(int in, int k, int s) {
 // Tiled direct convolution: out[n,oy,ox,co] = sum_{ky,kx,ci} in[n, oy*s - pad + ky, ox*s - pad + kx, ci] * W(ky,kx,ci,co) (+ bias)
 // `wmode` 0: W = w[ky][kx][ci][co] (forward, HWIO with wci = cin, wco = cout)
 //         1: W = w[k-1-ky][k-1-kx][co][ci]  (stride-1 dgrad: the kernel is run with cin := Cout_fwd, cout := Cin_fwd)
+//         2: strided dgrad (discriminator k4 s2 convs): `in` = dy [n,h,w_,cin := Cout_fwd], out = dx [n,oh,ow,cout := Cin_fwd];
+//            tap (ky,kx) of output pixel (oy,ox) reads dy at ((oy+pad-ky)/stride, (ox+pad-kx)/stride) when both divide
+//            exactly, W = w[ky][kx][co][ci]. Three quarters of the staged taps are zeros at stride 2 -- accepted: the layers
+//            are tiny and this keeps them on the tiled/split-K kernel instead of a one-thread-per-element gather.
+// Small grids (the 8x8 / 16x16 discriminator maps give 16-64 blocks) are split over K along blockIdx.z and combined
+// with atomicAdd into a zeroed output; bias is added by split 0.
 // `in_up`: the conv reads a nearest-upsampled view of `in` (in is [n, h/in_up, w/in_up, cin]).
 // Block = 256 threads -> 8 x 16 output pixels x 64 output channels; thread tile 4 pixels x 8 channels.
 struct ConvArgs {
@@ -27,6 +33,7 @@ struct ConvArgs {
   const float* bias;
   float* out;
   int n, h, w_, cin, cout, k, stride, pad, oh, ow, in_up, wmode, accumulate;
+  int its_per_split;  // split-K: K-iterations ((ky,kx,cin chunk) triples) per blockIdx.z; > total = no split
 };
 
 constexpr int kTP = 128;  // pixels per block (8 rows x 16 cols)
@@ -52,48 +59,63 @@ __global__ void __launch_bounds__(256) conv_tiled_kernel(const ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
   const int sh = a.h / a.in_up, sw = a.w_ / a.in_up;
-  for (int ky = 0; ky < a.k; ++ky) {
-    for (int kx = 0; kx < a.k; ++kx) {
-      for (int c0 = 0; c0 < a.cin; c0 += kKC) {
-        __syncthreads();
-        // ---- stage inputs: 128 pixels x 16 channels
-        for (int e = tid; e < kTP * kKC; e += 256) {
-          const int p = e / kKC, c = e % kKC;
-          const int oy = ty_ * 8 + (p >> 4), ox = tx_ * 16 + (p & 15);
-          const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
-          float v = 0.0f;
-          if (c0 + c < a.cin && iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
-            v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + c0 + c];
-          xs[p][c] = v;
+  const int nchunk = (a.cin + kKC - 1) / kKC;
+  const int total_its = a.k * a.k * nchunk;
+  const int it0 = static_cast<int>(blockIdx.z) * a.its_per_split;
+  const int it1 = (it0 + a.its_per_split) < total_its ? (it0 + a.its_per_split) : total_its;
+  // each thread stages the same 8 input elements / 4 weight elements every iteration: precompute their coordinates
+  for (int it = it0; it < it1; ++it) {
+    const int tap = it / nchunk;
+    const int c0 = (it - tap * nchunk) * kKC;
+    const int ky = tap / a.k, kx = tap - ky * a.k;
+    __syncthreads();
+    // ---- stage inputs: 128 pixels x 16 channels
+    for (int e = tid; e < kTP * kKC; e += 256) {
+      const int p = e >> 4, c = e & 15;
+      const int oy = ty_ * 8 + (p >> 4), ox = tx_ * 16 + (p & 15);
+      float v = 0.0f;
+      if (a.wmode == 2) {
+        const int ty = oy + a.pad - ky, tx = ox + a.pad - kx;
+        if (c0 + c < a.cin && ty >= 0 && tx >= 0 && ty % a.stride == 0 && tx % a.stride == 0) {
+          const int iy = ty / a.stride, ix = tx / a.stride;
+          if (iy < a.h && ix < a.w_) v = a.in[((static_cast<size_t>(n) * a.h + iy) * a.w_ + ix) * a.cin + c0 + c];
         }
-        // ---- stage weights: 16 input channels x 64 output channels
-        for (int e = tid; e < kKC * kTC; e += 256) {
-          const int c = e / kTC, o = e % kTC;
-          float v = 0.0f;
-          if (c0 + c < a.cin && co0 + o < a.cout) {
-            if (a.wmode == 0)
-              v = a.w[((static_cast<size_t>(ky) * a.k + kx) * a.cin + c0 + c) * a.cout + co0 + o];
-            else
-              v = a.w[((static_cast<size_t>(a.k - 1 - ky) * a.k + (a.k - 1 - kx)) * a.cout + co0 + o) * a.cin + c0 + c];
-          }
-          ws[c][o] = v;
-        }
-        __syncthreads();
+      } else {
+        const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+        if (c0 + c < a.cin && iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
+          v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + c0 + c];
+      }
+      xs[p][c] = v;
+    }
+    // ---- stage weights: 16 input channels x 64 output channels
+    for (int e = tid; e < kKC * kTC; e += 256) {
+      const int c = e >> 6, o = e & 63;
+      float v = 0.0f;
+      if (c0 + c < a.cin && co0 + o < a.cout) {
+        if (a.wmode == 0)
+          v = a.w[((static_cast<size_t>(ky) * a.k + kx) * a.cin + c0 + c) * a.cout + co0 + o];
+        else if (a.wmode == 1)
+          v = a.w[((static_cast<size_t>(a.k - 1 - ky) * a.k + (a.k - 1 - kx)) * a.cout + co0 + o) * a.cin + c0 + c];
+        else
+          v = a.w[((static_cast<size_t>(ky) * a.k + kx) * a.cout + co0 + o) * a.cin + c0 + c];
+      }
+      ws[c][o] = v;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int c = 0; c < kKC; ++c) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&ws[c][cg * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&ws[c][cg * 8 + 4]);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int c = 0; c < kKC; ++c) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[c][cg * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[c][cg * 8 + 4]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float xv = xs[pg * 4 + i][c];
+      for (int i = 0; i < 4; ++i) {
+        const float xv = xs[pg * 4 + i][c];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
-          }
-        }
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
       }
     }
   }
+  const bool split = gridDim.z > 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = pg * 4 + i;
@@ -104,48 +126,15 @@ __global__ void __launch_bounds__(256) conv_tiled_kernel(const ConvArgs a) {
     for (int j = 0; j < 8; ++j) {
       const int co = co0 + cg * 8 + j;
       if (co < a.cout) {
-        float v = acc[i][j] + (a.bias ? a.bias[co] : 0.0f);
-        if (a.accumulate) v += o[co];
-        o[co] = v;
+        float v = acc[i][j] + ((a.bias && blockIdx.z == 0) ? a.bias[co] : 0.0f);
+        if (split) {
+          atomicAdd(&o[co], v);
+        } else {
+          if (a.accumulate) v += o[co];
+          o[co] = v;
+        }
       }
     }
-  }
-}
-
-// Strided dgrad (discriminator convs, k=4 s=2): gather form, one thread per (pixel, ci).
-struct DgradArgs {
-  const float* dy;
-  const float* w;
-  float* dx;
-  int n, h, w_, cin, cout, k, stride, pad, oh, ow, accumulate;
-};
-__global__ void __launch_bounds__(256) dgrad_gather_kernel(const DgradArgs a) {
-  const long long total = static_cast<long long>(a.n) * a.h * a.w_ * a.cin;
-  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
-    const int ci = static_cast<int>(e % a.cin);
-    long long r = e / a.cin;
-    const int x = static_cast<int>(r % a.w_);
-    r /= a.w_;
-    const int y = static_cast<int>(r % a.h);
-    const int n = static_cast<int>(r / a.h);
-    float acc = 0.0f;
-    for (int ky = 0; ky < a.k; ++ky) {
-      const int ty = y + a.pad - ky;
-      if (ty < 0 || ty % a.stride) continue;
-      const int oy = ty / a.stride;
-      if (oy >= a.oh) continue;
-      for (int kx = 0; kx < a.k; ++kx) {
-        const int tx = x + a.pad - kx;
-        if (tx < 0 || tx % a.stride) continue;
-        const int ox = tx / a.stride;
-        if (ox >= a.ow) continue;
-        const float* d = a.dy + ((static_cast<size_t>(n) * a.oh + oy) * a.ow + ox) * a.cout;
-        const float* wp = a.w + ((static_cast<size_t>(ky) * a.k + kx) * a.cin + ci) * a.cout;
-        for (int co = 0; co < a.cout; ++co) acc = fmaf(d[co], wp[co], acc);
-      }
-    }
-    if (a.accumulate) acc += a.dx[e];
-    a.dx[e] = acc;
   }
 }
 
@@ -221,6 +210,82 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     for (int j = 0; j < 8; ++j) {
       const int co = cot * 64 + cg * 8 + j;
       if (co < a.cout) atomicAdd(&a.dw[(static_cast<size_t>(tap) * a.cin + ci) * a.cout + co], acc[j]);
+    }
+  }
+}
+
+// Filter gradient of the THIN stride-1 convolutions (cout <= 32, any cin; generator layers 4->8, 8->32, 32->8, 8->2,
+// 2->1 and the narrow 1x1 shortcuts): thread = one (tap, ci) pair holding all cout partial sums in registers, block =
+// 8 x 16 output pixels staged in shared memory (input window with halo for <= CI channels, dy tile), persistent over
+// tiles so every block issues its atomics once per channel chunk. The generic wgrad_kernel above tiles 32 ci x 64 co
+// per tap, which leaves >90 % of its threads idle on these shapes (1.1 ms per layer at 16 x 64 x 64).
+constexpr int kWtTH = 8, kWtTW = 16;
+constexpr int kWtXsFloats = 4352;
+template <int CO>
+__global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradArgs a, int ci_chunk) {
+  __shared__ float xs[kWtXsFloats];
+  __shared__ __align__(16) float dys[kWtTH * kWtTW][CO];
+  const int k = a.k, pad = a.pad;
+  const int hw = kWtTW + k - 1, hh = kWtTH + k - 1;
+  const int tiles_x = (a.ow + kWtTW - 1) / kWtTW, tiles_y = (a.oh + kWtTH - 1) / kWtTH;
+  const int ntiles = a.n * tiles_x * tiles_y;
+  const int sh = a.h / a.in_up, sw = a.w_ / a.in_up;
+  const int tid = threadIdx.x;
+  const int npairs = k * k * ci_chunk;
+  const int tap = tid / ci_chunk, cl = tid - tap * ci_chunk;
+  const int ky = tap / k, kx = tap - ky * k;
+  const bool active = tid < npairs;
+  for (int c0 = 0; c0 < a.cin; c0 += ci_chunk) {
+    float acc[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = 0.0f;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int n = t / (tiles_x * tiles_y);
+      const int r = t - n * tiles_x * tiles_y;
+      const int ty = r / tiles_x, tx = r - ty * tiles_x;
+      const int oy0 = ty * kWtTH, ox0 = tx * kWtTW;
+      __syncthreads();
+      for (int e = tid; e < hh * hw * ci_chunk; e += 256) {
+        const int c = e % ci_chunk, q = e / ci_chunk;
+        const int wy = q / hw, wx = q - wy * hw;
+        const int iy = oy0 - pad + wy, ix = ox0 - pad + wx;
+        float v = 0.0f;
+        if (c0 + c < a.cin && iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
+          v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + c0 + c];
+        xs[q * ci_chunk + c] = v;
+      }
+      for (int e = tid; e < kWtTH * kWtTW * CO; e += 256) {
+        const int co = e % CO, q = e / CO;
+        const int oy = oy0 + q / kWtTW, ox = ox0 + q % kWtTW;
+        float v = 0.0f;
+        if (co < a.cout && oy < a.oh && ox < a.ow) v = a.dy[((static_cast<size_t>(n) * a.oh + oy) * a.ow + ox) * a.cout + co];
+        dys[q][co] = v;
+      }
+      __syncthreads();
+      if (active) {
+        for (int py = 0; py < kWtTH; ++py) {
+          const float* xr = xs + ((py + ky) * hw + kx) * ci_chunk + cl;
+#pragma unroll 4
+          for (int px = 0; px < kWtTW; ++px) {
+            const float xv = xr[px * ci_chunk];
+            const float4* d4 = reinterpret_cast<const float4*>(&dys[py * kWtTW + px][0]);
+#pragma unroll
+            for (int j4 = 0; j4 < CO / 4; ++j4) {
+              const float4 d = d4[j4];
+              acc[j4 * 4 + 0] = fmaf(xv, d.x, acc[j4 * 4 + 0]);
+              acc[j4 * 4 + 1] = fmaf(xv, d.y, acc[j4 * 4 + 1]);
+              acc[j4 * 4 + 2] = fmaf(xv, d.z, acc[j4 * 4 + 2]);
+              acc[j4 * 4 + 3] = fmaf(xv, d.w, acc[j4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    if (active && c0 + cl < a.cin) {
+      float* o = a.dw + (static_cast<size_t>(tap) * a.cin + c0 + cl) * a.cout;
+#pragma unroll
+      for (int j = 0; j < CO; ++j)
+        if (j < a.cout) atomicAdd(&o[j], acc[j]);
     }
   }
 }
@@ -412,6 +477,21 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
   }
 }
 
+// same update with the bias-corrected step size read from device memory (CUDA-graph replays: the value changes every
+// step, a by-value kernel argument would be frozen at capture time)
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* p, const float* g, float* m, float* v, long long count,
+                                                        const float* lr_t_dev, float b1, float b2, float eps) {
+  const float lr_t = *lr_t_dev;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < count; e += static_cast<long long>(gridDim.x) * 256) {
+    const float gv = g[e];
+    const float mv = b1 * m[e] + (1.0f - b1) * gv;
+    const float vv = b2 * v[e] + (1.0f - b2) * gv * gv;
+    m[e] = mv;
+    v[e] = vv;
+    p[e] -= lr_t * mv / (sqrtf(vv) + eps);
+  }
+}
+
 // fully connected head [rows, nin] x [nin] -> [rows]: forward, dgrad, wgrad
 __global__ void __launch_bounds__(256) fc_fwd_kernel(const float* x, const float* w, const float* bias, float* y, int nin) {
   double part = 0.0;
@@ -458,6 +538,27 @@ inline int grid_for(long long total, int sm) {
 
 using namespace mpg;
 
+// Launch conv_tiled_kernel; grids that leave most SMs idle are split over K (blockIdx.z) into a zeroed output.
+static int launch_conv_tiled(mpg_handle h, ConvArgs a, cudaStream_t st) {
+  const unsigned gx = static_cast<unsigned>(a.n * ((a.oh + 7) / 8) * ((a.ow + 15) / 16));
+  const unsigned gy = static_cast<unsigned>((a.cout + kTC - 1) / kTC);
+  const int total_its = a.k * a.k * ((a.cin + kKC - 1) / kKC);
+  int nsplit = 1;
+  const long long blocks = static_cast<long long>(gx) * gy;
+  if (blocks < 2LL * h->sm_count && total_its >= 8) {
+    nsplit = static_cast<int>((3LL * h->sm_count + blocks - 1) / blocks);
+    if (nsplit > total_its / 4) nsplit = total_its / 4;
+    if (nsplit < 1) nsplit = 1;
+  }
+  a.its_per_split = (total_its + nsplit - 1) / nsplit;
+  nsplit = (total_its + a.its_per_split - 1) / a.its_per_split;
+  if (nsplit > 1 && !a.accumulate)
+    MPG_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * static_cast<size_t>(a.n) * a.oh * a.ow * a.cout, st));
+  conv_tiled_kernel<<<dim3(gx, gy, static_cast<unsigned>(nsplit)), 256, 0, st>>>(a);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
 extern "C" {
 
 int mpg_train_conv_fwd(mpg_handle h, const float* x, const float* w, const float* bias, float* y, int n, int hh, int ww,
@@ -482,10 +583,7 @@ int mpg_train_conv_fwd(mpg_handle h, const float* x, const float* w, const float
   a.in_up = in_up;
   a.wmode = 0;
   a.accumulate = 0;
-  dim3 grid(static_cast<unsigned>(n * ((a.oh + 7) / 8) * ((a.ow + 15) / 16)), static_cast<unsigned>((cout + kTC - 1) / kTC));
-  conv_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  MPG_CUDA(cudaGetLastError());
-  return MPG_OK;
+  return launch_conv_tiled(h, a, static_cast<cudaStream_t>(stream));
 }
 
 /* dx[n,hh,ww,cin] (+)= dgrad of y = conv2d_SAME(x, w, stride) given dy[n,oh,ow,cout] */
@@ -512,29 +610,27 @@ int mpg_train_conv_dgrad(mpg_handle h, const float* dy, const float* w, float* d
     a.in_up = 1;
     a.wmode = 1;
     a.accumulate = accumulate;
-    dim3 grid(static_cast<unsigned>(n * ((hh + 7) / 8) * ((ww + 15) / 16)), static_cast<unsigned>((cin + kTC - 1) / kTC));
-    conv_tiled_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  } else {
-    DgradArgs a;
-    a.dy = dy;
-    a.w = w;
-    a.dx = dx;
-    a.n = n;
-    a.h = hh;
-    a.w_ = ww;
-    a.cin = cin;
-    a.cout = cout;
-    a.k = k;
-    a.stride = stride;
-    a.pad = pad;
-    a.oh = (hh + stride - 1) / stride;
-    a.ow = (ww + stride - 1) / stride;
-    a.accumulate = accumulate;
-    dgrad_gather_kernel<<<grid_for(static_cast<long long>(n) * hh * ww * cin, h->sm_count), 256, 0,
-                          static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_conv_tiled(h, a, static_cast<cudaStream_t>(stream));
   }
-  MPG_CUDA(cudaGetLastError());
-  return MPG_OK;
+  ConvArgs a;  // strided dgrad on the tiled kernel (wmode 2)
+  a.in = dy;
+  a.w = w;
+  a.bias = nullptr;
+  a.out = dx;
+  a.n = n;
+  a.h = (hh + stride - 1) / stride;  // dy spatial size
+  a.w_ = (ww + stride - 1) / stride;
+  a.cin = cout;  // roles swap
+  a.cout = cin;
+  a.k = k;
+  a.stride = stride;
+  a.pad = pad;
+  a.oh = hh;
+  a.ow = ww;
+  a.in_up = 1;
+  a.wmode = 2;
+  a.accumulate = accumulate;
+  return launch_conv_tiled(h, a, static_cast<cudaStream_t>(stream));
 }
 
 /* dw[k,k,cin,cout] += wgrad ; dbias[cout] += sum dy (dbias may be NULL); `scratch`: >= cout doubles */
@@ -559,6 +655,18 @@ int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* d
   a.ow = (ww + stride - 1) / stride;
   a.in_up = in_up;
   const long long npix = static_cast<long long>(n) * a.oh * a.ow;
+  if (stride == 1 && (k == 1 || k == 3 || k == 5) && cout <= 32) {
+    // thin layers: (tap, ci)-per-thread kernel, persistent over 8x16-pixel tiles
+    int ci_chunk = k == 5 ? 8 : (k == 3 ? 24 : 32);
+    if (ci_chunk > cin) ci_chunk = cin;
+    const int ntiles = n * ((a.oh + kWtTH - 1) / kWtTH) * ((a.ow + kWtTW - 1) / kWtTW);
+    int grid = h->sm_count * 2;
+    if (grid > ntiles) grid = ntiles;
+    if (cout <= 4) wgrad_thin_kernel<4><<<grid, 256, 0, st>>>(a, ci_chunk);
+    else if (cout <= 8) wgrad_thin_kernel<8><<<grid, 256, 0, st>>>(a, ci_chunk);
+    else wgrad_thin_kernel<32><<<grid, 256, 0, st>>>(a, ci_chunk);
+    MPG_CUDA(cudaGetLastError());
+  } else {
   const int tiles = k * k * ((cin + 31) / 32) * ((cout + 63) / 64);
   int splits = (h->sm_count * 4 + tiles - 1) / tiles;
   if (splits < 1) splits = 1;
@@ -569,6 +677,7 @@ int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* d
   a.px_per_split = static_cast<int>(per);
   wgrad_kernel<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits)), 256, 0, st>>>(a);
   MPG_CUDA(cudaGetLastError());
+  }
   if (dbias) {
     MPG_CHECK_ARG(scratch != nullptr, "mpg_train_conv_wgrad: scratch missing");
     MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * cout, st));
@@ -683,6 +792,15 @@ int mpg_train_adam(mpg_handle h, float* param, const float* grad, float* m, floa
                    float beta1, float beta2, float eps, void* stream) {
   MPG_CHECK_ARG(h && param && grad && m && v && count > 0, "mpg_train_adam: bad argument");
   adam_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, m, v, count, lr_t, beta1, beta2, eps);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* mpg_train_adam with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from a device scalar (graph replays) */
+int mpg_train_adam_dev(mpg_handle h, float* param, const float* grad, float* m, float* v, long long count,
+                       const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {
+  MPG_CHECK_ARG(h && param && grad && m && v && lr_t_dev && count > 0, "mpg_train_adam_dev: bad argument");
+  adam_dev_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, m, v, count, lr_t_dev, beta1, beta2, eps);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

@@ -184,12 +184,16 @@ class Trainer4x:
 
     def __init__(self, tileSizeLow=16, upRes=4, batch=16, values=None, seed=1, batch_norm=True, bn_decay=0.999,
                  learning_rate=2e-4, adam_beta1=0.5, weight_dld=1.0, k2_l=(1.0, 1.0, 1.0, 1.0), device=0, group=None,
-                 precision="fp32"):
-        """precision "fp32": every kernel fp32 (the parity mode, what the reference computes); "fp16": the wide stride-1
+                 precision="fp32", graphs=False):
+        """graphs: replay each optimizer step as ONE captured CUDA graph (single-GPU only; the first call of a step runs
+        eagerly, the second is captured, later ones are replays). The step is ~2300 launches of a few microseconds each,
+        so without the graph the host launch path, not the GPU, bounds it.
+        precision "fp32": every kernel fp32 (the parity mode, what the reference computes); "fp16": the wide stride-1
         convolutions run forward / dgrad on the tcgen05 kernel (fp16 activations, bf16 gradients, fp32 accumulation and
         fp32 master weights / optimizer), everything else stays fp32."""
         assert precision in ("fp32", "fp16")
         self.precision = precision
+        self._graphs = {}
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
         self.L, self.u, self.S, self.B, self.C = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(batch), 4
@@ -198,6 +202,7 @@ class Trainer4x:
         self.weight_dld, self.k2_l = float(weight_dld), tuple(float(k) for k in k2_l)
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.use_graphs = bool(graphs) and self.world == 1
         self.moving = {}
         self.pg, self.pd = ParamSet(self.device), ParamSet(self.device)
         C = self.C
@@ -355,16 +360,24 @@ class Trainer4x:
         return dxin
 
     # ------------------------------------------------------------------ optimizer
+    def _prep_adam(self, ps):
+        """Host half of tf.train.AdamOptimizer: step count and bias-corrected step size (into a device scalar)."""
+        ps.t += 1
+        ps.lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** ps.t) / (1.0 - self.beta1 ** ps.t)
+        if self.use_graphs:
+            if not hasattr(ps, "lr_dev"):
+                ps.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+            ps.lr_dev.fill_(ps.lr_t)
+
     def _adam(self, ps):
         self.call("mul", ps.g, ps.gw, ps.scale, ps.total, self.st)  # d/dv = d/dW_eff * wscale
         par.allreduce_mean(ps.g, self.group)
-        ps.t += 1
-        lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** ps.t) / (1.0 - self.beta1 ** ps.t)
-        self.call("adam", ps.v, ps.g, ps.m, ps.vv, ps.total, lr_t, self.beta1, self.beta2, self.eps, self.st)
+        if self.use_graphs:
+            self.call("adam_dev", ps.v, ps.g, ps.m, ps.vv, ps.total, ps.lr_dev, self.beta1, self.beta2, self.eps, self.st)
+        else:
+            self.call("adam", ps.v, ps.g, ps.m, ps.vv, ps.total, ps.lr_t, self.beta1, self.beta2, self.eps, self.st)
 
-    def _forward_all(self, x_rows, y_rows):
-        x = self._dev(x_rows)
-        y = self._dev(y_rows)
+    def _forward_all(self, x, y):
         self._refresh_weights()
         gen_part, gsaved = self.gen_forward(x)
         in_low = x[:, : self.L * self.L].contiguous()  # App. D.5: first n_input/C floats of the interleaved row
@@ -372,11 +385,47 @@ class Trainer4x:
         gen, gfeat, gsv = self.disc_forward(in_low, gen_part.view(self.B, -1))
         return x, y, gen_part, gsaved, (disc, dfeat, dsv), (gen, gfeat, gsv)
 
+    def _run_step(self, key, ps, body, x_rows, y_rows):
+        """Run one optimizer step eagerly, or (graphs=True) capture it on its second call and replay it afterwards."""
+        x, y = self._dev(x_rows), self._dev(y_rows)
+        self._prep_adam(ps)
+        if not self.use_graphs:
+            self._bufs = []
+            self.st = torch.cuda.current_stream(self.device).cuda_stream
+            body(x, y)
+            return self.losses
+        ent = self._graphs.get(key)
+        if ent is None:  # warm-up: plans, shared-memory attributes and allocator pools settle outside any capture
+            self._bufs = []
+            self.st = torch.cuda.current_stream(self.device).cuda_stream
+            body(x, y)
+            self._graphs[key] = "warm"
+            return self.losses
+        if ent == "warm":
+            sx, sy = x.clone(), y.clone()
+            launches = self.launches
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._bufs = []
+                self.st = torch.cuda.current_stream(self.device).cuda_stream
+                body(sx, sy)
+            ent = dict(graph=g, bufs=self._bufs, x=sx, y=sy, launches=self.launches - launches)
+            self._graphs[key] = ent
+            self._bufs = []
+        else:
+            ent["x"].copy_(x)
+            ent["y"].copy_(y)
+            self.launches += ent["launches"]
+        ent["graph"].replay()
+        return self.losses
+
     def disc_step(self, x_rows, y_rows):
         """sess.run(disc_optimizer, ...) (:1321): Adam on the d_ variables with disc_loss (:751-755)."""
-        self._bufs = []
-        self.st = torch.cuda.current_stream(self.device).cuda_stream
-        x, y, gen_part, gsaved, (disc, dfeat, dsv), (gen, gfeat, gsv) = self._forward_all(x_rows, y_rows)
+        return self._run_step(("d",), self.pd, self._disc_body, x_rows, y_rows)
+
+    def _disc_body(self, x, y):
+        x, y, gen_part, gsaved, (disc, dfeat, dsv), (gen, gfeat, gsv) = self._forward_all(x, y)
         self.pd.gw.zero_()
         self.losses.zero_()
         dl_r, dl_f = self.buf(disc.shape), self.buf(gen.shape)
@@ -385,13 +434,13 @@ class Trainer4x:
         self.disc_backward(dsv, dfeat, dl_r)
         self.disc_backward(gsv, gfeat, dl_f)
         self._adam(self.pd)
-        return self.losses
 
     def gen_step(self, x_rows, y_rows, kk, kk2):
         """sess.run(gen_optimizer, ...) (:1352): Adam on the g_ variables with gen_loss_complete (:757-768)."""
-        self._bufs = []
-        self.st = torch.cuda.current_stream(self.device).cuda_stream
-        x, y, gen_part, gsaved, (disc, dfeat, dsv), (gen, gfeat, gsv) = self._forward_all(x_rows, y_rows)
+        return self._run_step(("g", float(kk), float(kk2)), self.pg, lambda x, y: self._gen_body(x, y, kk, kk2), x_rows, y_rows)
+
+    def _gen_body(self, x, y, kk, kk2):
+        x, y, gen_part, gsaved, (disc, dfeat, dsv), (gen, gfeat, gsv) = self._forward_all(x, y)
         self.pg.gw.zero_()
         self.losses.zero_()
         dl_f = self.buf(gen.shape)
@@ -407,7 +456,6 @@ class Trainer4x:
         self.call("take_channel", dxin, dgen, self.B * self.S * self.S, 2, 1, 1, self.st)
         self.gen_backward(gsaved, dgen)
         self._adam(self.pg)
-        return self.losses
 
     def iteration(self, batches_d, batches_g, kk=5.0, kk2=1e-5):
         """One loop body (:1316-1397). Returns python floats (one D2H read of the loss vector per step)."""

@@ -36,12 +36,13 @@ def main():
     ap.add_argument("--gen-runs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16"])
+    ap.add_argument("--graphs", type=int, default=1, help="replay each optimizer step as a captured CUDA graph (single GPU)")
     args = ap.parse_args()
     rank, local, world = par.init_from_env()
     torch.cuda.set_device(local)
     L, u, B = 16, 4, args.batch
     S = L * u
-    tr = T.Trainer4x(L, u, B, seed=1, device=local, precision=args.precision)
+    tr = T.Trainer4x(L, u, B, seed=1, device=local, precision=args.precision, graphs=bool(args.graphs))
     rng = np.random.default_rng(100 + rank)
     xs = torch.from_numpy(rng.random((B, L * L * 4), dtype=np.float32)).pin_memory()
     ys = torch.from_numpy(rng.random((B, S * S), dtype=np.float32)).pin_memory()
@@ -76,9 +77,9 @@ def main():
     line = dict(metric="training loop bodies/sec (4x G + spatial D, tiles 16x16->64x64)", value=world * 1e3 / it_ms,
                 unit="iteration/s", tiles_per_s=world * B * 1e3 / it_ms, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=it_ms, higher_is_better=True, scaling="weak",
-                dtype="f32" if args.precision == "fp32" else "f16 fwd / bf16 dgrad on tcgen05, f32 wgrad + optimizer", data="synthetic",
+                dtype="f32" if args.precision == "fp32" else "f16 fwd / bf16 dgrad + wgrad on tcgen05, f32 thin layers + optimizer", data="synthetic",
                 config=dict(workload="multipassGAN-4x training step (BASELINE.json configs[3])", batch_per_gpu=B,
-                            discRuns=args.disc_runs, genRuns=args.gen_runs, tile="16x16 -> 64x64"),
+                            discRuns=args.disc_runs, genRuns=args.gen_runs, tile="16x16 -> 64x64", cuda_graphs=bool(tr.use_graphs)),
                 algorithmic_tflops=world * flop_it / (it_ms * 1e-3) / 1e12,
                 gpu_launches=int((tr.launches - l0)), losses=out,
                 e2e=dict(value=world * 1e3 / it_ms, unit="iteration/s", h2d_bytes_per_step=int(xs.numel() * 4 + ys.numel() * 4),
