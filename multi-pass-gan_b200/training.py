@@ -77,10 +77,11 @@ class _Conv:
             self.gamma = ps.add(scope + "/gamma", (cout,))
             tr.moving[scope + "/moving_mean"] = None
             tr.moving[scope + "/moving_variance"] = None
-        # tensor-core path (precision "fp16"): forward on the tcgen05 implicit-GEMM kernel with fp16 operands, dgrad on
-        # the same kernel with bf16 gradients (range) and flipped/transposed weights; wgrad stays fp32
-        self.fast = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1 and cin % 8 == 0
-                     and cout % 8 == 0 and max(cin, cout) >= 32)
+        # tensor-core path (precision "fp16"): every stride-1 conv runs forward on the tcgen05 implicit-GEMM kernel with fp16
+        # operands and dgrad on the same kernel with bf16 gradients (range) and flipped/transposed weights; channel counts
+        # are padded to 8 in the 16-bit copies (zero channels), nearest-upsampled inputs are materialised by the pack
+        self.fast = tr.precision == "fp16" and k in (1, 3, 5) and stride == 1
+        self.cpi, self.cpo = -(-cin // 8) * 8, -(-cout // 8) * 8
         # filter gradient on the tensor cores (csrc/conv_wgrad_tc.cu): bf16 copies of the input and of the output gradient
         self.fast_w = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1
                        and ((cin == 128 and cout in (32, 64, 128)) or (cout == 128 and cin in (32, 64))))
@@ -92,18 +93,21 @@ class _Conv:
         tr = self.tr
         zf = np.zeros((self.k, self.k, self.cin, self.cout), np.float32)
         zd = np.zeros((self.k, self.k, self.cout, self.cin), np.float32)
-        self.plan_f = capi.ConvPlan(tr.h, n, h, w, [zf], [self.cin], self.cout, self.cout, act=None,
+        self.plan_f = capi.ConvPlan(tr.h, n, h, w, [zf], [self.cpi], self.cout, self.cout, act=None,
                                     shift=np.zeros(self.cout, np.float32), in_dtype=capi.F16, out_dtype=capi.F32, force_kind=1)
-        self.plan_d = capi.ConvPlan(tr.h, n, h, w, [zd], [self.cout], self.cin, self.cin, act=None,
-                                    shift=np.zeros(self.cin, np.float32), in_dtype=capi.BF16, out_dtype=capi.F32, force_kind=1)
+        if self.in_up == 1:  # layers fed by the (upsampled) data never need an input gradient
+            self.plan_d = capi.ConvPlan(tr.h, n, h, w, [zd], [self.cpo], self.cin, self.cin, act=None,
+                                        shift=np.zeros(self.cin, np.float32), in_dtype=capi.BF16, out_dtype=capi.F32, force_kind=1)
 
     def refresh(self):
         if self.plan_f is None:
             return
         ps, tr = self.ps, self.tr
         self.plan_f.update(ps.view(ps.w, self.wn), mode0=0, shift=ps.view(ps.w, self.bn_), stream=tr.st)
-        self.plan_d.update(ps.view(ps.w, self.wn), mode0=1, stream=tr.st)
-        tr.launches += 2
+        tr.launches += 1
+        if self.plan_d is not None:
+            self.plan_d.update(ps.view(ps.w, self.wn), mode0=1, stream=tr.st)
+            tr.launches += 1
 
     def forward(self, x, n, h, w):
         """x: [n, h/in_up, w/in_up, cin]; h, w: conv input size. Returns (y, saved)."""
@@ -111,8 +115,9 @@ class _Conv:
         oh, ow = -(-h // self.stride), -(-w // self.stride)
         lin = tr.buf((n, oh, ow, self.cout))
         if self.fast:
-            x16 = tr.buf16((n, h, w, self.cin), torch.float16)
-            capi.pack_channels(tr.h, [(x, capi.F32, self.cin, 0, self.cin, 1, 1)], x16, capi.F16, self.cin, n, h, w, tr.st)
+            x16 = tr.buf16((n, h, w, self.cpi), torch.float16)
+            capi.pack_channels(tr.h, [(x, capi.F32, self.cin, 0, self.cin, self.in_up, self.in_up)], x16, capi.F16, self.cpi, n, h,
+                               w, tr.st)
             self.plan_f.run(x16, None, lin, tr.st)
             tr.launches += 2
         else:
@@ -151,8 +156,8 @@ class _Conv:
         g16 = None
         use_wtc = param_grads and self.fast_w and sv["w"] % 16 == 0
         if use_wtc or (dx is not None and self.fast):
-            g16 = tr.buf16(tuple(dlin.shape), torch.bfloat16)
-            capi.pack_channels(tr.h, [(dlin, capi.F32, self.cout, 0, self.cout, 1, 1)], g16, capi.BF16, self.cout, sv["n"],
+            g16 = tr.buf16(tuple(dlin.shape[:3]) + (self.cpo,), torch.bfloat16)
+            capi.pack_channels(tr.h, [(dlin, capi.F32, self.cout, 0, self.cout, 1, 1)], g16, capi.BF16, self.cpo, sv["n"],
                                sv["h"], sv["w"], tr.st)
             tr.launches += 1
         if use_wtc:
