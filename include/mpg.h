@@ -199,6 +199,12 @@ int mpg_tiles_cut(mpg_handle h, const void* in, void* out, int n, int hh, int ww
  * x, then y (concatTiles with tileBorder). */
 int mpg_tiles_stitch(mpg_handle h, const void* tiles, void* out, int n, int ty, int tx, int th, int tw, int c,
                      int elem_bytes, int border, void* stream);
+/* Overlap-crop stitch that also keeps the outer border of frame-edge tiles: exact inverse of mpg_tiles_cut with
+ * stride = tile - 2*border, pad = 0 on a frame of t*(tile - 2*border) + 2*border pixels per axis. With
+ * border >= the generator's receptive-field radius a per-tile apply is bit-identical to the
+ * whole-slice apply; TileCreator.concatTiles (tools_wscale/tilecreator_t.py:886-918) drops that band instead. */
+int mpg_tiles_stitch_overlap(mpg_handle h, const void* tiles, void* out, int n, int ty, int tx, int th, int tw, int c,
+                             int elem_bytes, int border, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training step of the 4x model (generator + spatial discriminator, GAN/multipassGAN-4x.py:528-620,

@@ -92,6 +92,7 @@ def lib():
     L.mpg_tiles_count.argtypes = [ip, ip, ip]
     L.mpg_tiles_cut.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_tiles_stitch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_tiles_stitch_overlap.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     ll, fl = ctypes.c_longlong, ctypes.c_float
     L.mpg_train_conv_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_train_conv_dgrad.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
@@ -333,3 +334,9 @@ def tiles_stitch(handle, tiles, dst, n, ty, tx, th, tw, c, elem_bytes, border=0,
     """TileCreator.concatTiles (tileBorder crop + concatenation) on device tiles."""
     check(lib().mpg_tiles_stitch(handle.ptr, _ptr(tiles), _ptr(dst), int(n), int(ty), int(tx), int(th), int(tw), int(c),
                                  int(elem_bytes), int(border), stream), "mpg_tiles_stitch")
+
+
+def tiles_stitch_overlap(handle, tiles, dst, n, ty, tx, th, tw, c, elem_bytes, border, stream=0):
+    """Inverse of tiles_cut(stride = tile - 2*border, pad=0): centres of all tiles + the outer border of frame-edge tiles."""
+    check(lib().mpg_tiles_stitch_overlap(handle.ptr, _ptr(tiles), _ptr(dst), int(n), int(ty), int(tx), int(th), int(tw), int(c),
+                                         int(elem_bytes), int(border), stream), "mpg_tiles_stitch_overlap")

@@ -64,6 +64,34 @@ __global__ void __launch_bounds__(256) tiles_stitch_kernel(const TileArgs a) {
   }
 }
 
+// Exact inverse of an overlapped cut (stride = tile - 2*border, no padding) of a frame of size
+// t*(tile - 2*border) + 2*border: every tile contributes its centre, tiles on a frame edge also keep their outer
+// border (there the tile edge IS the frame edge, so a network applied per tile saw the same zero padding as one
+// applied to the whole frame). This is what makes a tiled apply bit-identical to the untiled one when
+// border >= receptive-field radius; concatTiles (tilecreator_t.py:886-918) drops that band.
+template <typename WordT>
+__global__ void __launch_bounds__(256) tiles_stitch_overlap_kernel(const TileArgs a) {
+  const int ch = a.th - 2 * a.pad, cw = a.tw - 2 * a.pad;
+  const int fh = a.ty * ch + 2 * a.pad, fw = a.tx * cw + 2 * a.pad;
+  const long long total = static_cast<long long>(a.n) * fh * fw * a.row_words;
+  const WordT* in = reinterpret_cast<const WordT*>(a.in);
+  WordT* out = reinterpret_cast<WordT*>(a.out);
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(e % a.row_words);
+    long long r = e / a.row_words;
+    const int x = static_cast<int>(r % fw);
+    r /= fw;
+    const int y = static_cast<int>(r % fh);
+    const int n = static_cast<int>(r / fh);
+    int iy = (y - a.pad) / ch, ix = (x - a.pad) / cw;
+    iy = (y < a.pad) ? 0 : (iy >= a.ty ? a.ty - 1 : iy);
+    ix = (x < a.pad) ? 0 : (ix >= a.tx ? a.tx - 1 : ix);
+    const int yy = y - iy * ch, xx = x - ix * cw;
+    const long long tile = (static_cast<long long>(n) * a.ty + iy) * a.tx + ix;
+    out[e] = in[((tile * a.th + yy) * a.tw + xx) * a.row_words + c];
+  }
+}
+
 inline int grid_of(long long total, int sm) {
   long long b = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm) * 16;
@@ -139,6 +167,39 @@ int mpg_tiles_stitch(mpg_handle h, const void* tiles, void* out, int n, int ty, 
     a.row_words = row_bytes / 2;
     const long long total = static_cast<long long>(n) * ty * (th - 2 * border) * tx * (tw - 2 * border) * a.row_words;
     tiles_stitch_kernel<uint16_t><<<grid_of(total, h->sm_count), 256, 0, st>>>(a);
+  }
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* out[n, ty*(th-2b)+2b, tx*(tw-2b)+2b, c]: overlap-crop stitch that keeps the outer border of frame-edge tiles
+ * (inverse of mpg_tiles_cut with stride = tile - 2*border, pad = 0). */
+int mpg_tiles_stitch_overlap(mpg_handle h, const void* tiles, void* out, int n, int ty, int tx, int th, int tw, int c,
+                             int elem_bytes, int border, void* stream) {
+  MPG_CHECK_ARG(h && tiles && out && n > 0 && ty > 0 && tx > 0 && th > 0 && tw > 0 && c > 0 && border >= 0,
+                "mpg_tiles_stitch_overlap: bad argument");
+  MPG_CHECK_ARG(elem_bytes == 2 || elem_bytes == 4, "mpg_tiles_stitch_overlap: elem_bytes must be 2 or 4");
+  MPG_CHECK_ARG(th > 2 * border && tw > 2 * border, "mpg_tiles_stitch_overlap: border %d leaves nothing of a %dx%d tile", border, th, tw);
+  TileArgs a;
+  a.in = tiles;
+  a.out = out;
+  a.n = n;
+  a.h = a.w = 0;
+  a.th = th;
+  a.tw = tw;
+  a.sy = a.sx = 0;
+  a.ty = ty;
+  a.tx = tx;
+  a.pad = border;
+  const int row_bytes = c * elem_bytes;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long px = static_cast<long long>(n) * (ty * (th - 2 * border) + 2 * border) * (tx * (tw - 2 * border) + 2 * border);
+  if (row_bytes % 4 == 0) {
+    a.row_words = row_bytes / 4;
+    tiles_stitch_overlap_kernel<uint32_t><<<grid_of(px * a.row_words, h->sm_count), 256, 0, st>>>(a);
+  } else {
+    a.row_words = row_bytes / 2;
+    tiles_stitch_overlap_kernel<uint16_t><<<grid_of(px * a.row_words, h->sm_count), 256, 0, st>>>(a);
   }
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;

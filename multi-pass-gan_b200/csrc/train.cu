@@ -305,8 +305,18 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
   if (r_l >= rows_per_iter) return;
   for (int ch = ch_l; ch < c; ch += lanes_per_row) {
     double s0 = 0.0, s1 = 0.0;
-    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + r_l; r < rows;
-         r += static_cast<long long>(gridDim.x) * rows_per_iter) {
+    const long long rstep = static_cast<long long>(gridDim.x) * rows_per_iter;
+    long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + r_l;
+    if (mode != 1) {
+      // four independent loads in flight (the plain loop is bound by one load latency per row and thread)
+      for (; r + 3 * rstep < rows; r += 4 * rstep) {
+        const float x0 = x[r * c + ch], x1 = x[(r + rstep) * c + ch], x2 = x[(r + 2 * rstep) * c + ch], x3 = x[(r + 3 * rstep) * c + ch];
+        s0 += (static_cast<double>(x0) + x1) + (static_cast<double>(x2) + x3);
+        if (mode == 0)
+          s1 += (static_cast<double>(x0) * x0 + static_cast<double>(x1) * x1) + (static_cast<double>(x2) * x2 + static_cast<double>(x3) * x3);
+      }
+    }
+    for (; r < rows; r += rstep) {
       const float xv = x[r * c + ch];
       if (mode == 0) {
         s0 += xv;

@@ -59,6 +59,51 @@ class _PassNet:
         self.batch = batch
 
 
+class _TiledPassNet:
+    """A generator applied to whole [H,H] slices through overlapping [T,T] tiles (the reference's
+    TileCreator.createTiles / concatTiles, tools_wscale/tilecreator_t.py:403-450,886-918, used the B200 way):
+    mpg_tiles_cut (stride = core, tile = core + 2*halo) -> ONE network launch over batch*nt*nt tiles ->
+    mpg_tiles_stitch_overlap (crop `halo`, keep the outer band of frame-edge tiles). With halo >= the receptive-field
+    radius of the generator (16 output pixels for gen_resnet, App. A.6) the result is bit-identical to the whole-slice
+    apply, so slices that exceed HBM can be processed at any tile size."""
+
+    def __init__(self, handle, device, build_fn, weights, batch, precision, H, core, halo, cin, scale):
+        if (H - 2 * halo) % core or core <= 0:
+            raise ValueError("tiled apply: (H - 2*halo) = %d is not a multiple of the tile core %d" % (H - 2 * halo, core))
+        self.h, self.H, self.core, self.halo, self.cin, self.scale = handle, H, core, halo, cin, scale
+        self.T = core + 2 * halo
+        self.nt = (H - 2 * halo) // core
+        self.batch = batch
+        nb = batch * self.nt * self.nt
+        G.reset_default_graph()
+        self.out_t = build_fn(self.T)
+        self.net = engine.CompiledNet(self.out_t, weights, nb, precision=precision, handle=handle)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.tin = torch.empty((nb, self.T, self.T, cin), **f32)
+        self.tout = torch.empty((nb, self.T * scale, self.T * scale), **f32)
+
+    def run(self, feeds, out, stream):
+        x = feeds["x"]
+        capi.tiles_cut(self.h, x, self.tin, self.batch, self.H, self.H, self.cin, 4, self.T, self.T, self.core, self.core, 0,
+                       stream)
+        self.net.run({"x": self.tin}, out=self.tout, stream=stream)
+        capi.tiles_stitch_overlap(self.h, self.tout, out, self.batch, self.nt, self.nt, self.T * self.scale,
+                                  self.T * self.scale, 1, 4, self.halo * self.scale, stream)
+
+    @property
+    def flops(self):
+        return self.net.flops
+
+    @property
+    def launches(self):
+        return self.net.launches + 2
+
+
+class _TiledHolder:
+    def __init__(self, net):
+        self.net = net
+
+
 class MultiPass4x:
     """Two-pass 4x super-resolution of one frame: [L,L,L,4] -> [4L,4L,4L] (z,y,x), fp32.
 
@@ -67,7 +112,10 @@ class MultiPass4x:
     `__call__` returns this rank's [S/G, S, S] part of the output (rank-major == z order)."""
 
     def __init__(self, L, weights_pass1, weights_pass2, upRes=4, precision="fp16", batch=8, velScale=1.0,
-                 batch_norm=True, device=0, threshold=THRESHOLD, rank=0, world=1, group=None):
+                 batch_norm=True, device=0, threshold=THRESHOLD, rank=0, world=1, group=None, tile=None):
+        """tile: None = whole slices per launch (the reference's behaviour), or (core1, core2): pass 1 is applied to
+        overlapping low-res tiles of core1 + 2*4 pixels, pass 2 to high-res tiles of core2 + 2*16 pixels
+        (_TiledPassNet; (L - 8) % core1 == 0, (S - 32) % core2 == 0, core2 % upRes == 0) -- same result, bounded memory."""
         self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
@@ -84,7 +132,26 @@ class MultiPass4x:
         self.p1 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg1), weights_pass1,
                            self.batch, precision)
         self.p2 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, S * S * 4], "x"), cfg2), weights_pass2,
-                           self.batch, precision)
+                           self.batch, precision) if tile is None else None
+        if tile is not None:
+            core1, core2 = int(tile[0]), int(tile[1])
+            halo_hi = 16  # receptive-field radius of gen_resnet: 8 convs of k=5 (App. A.6)
+            if halo_hi % u or core2 % u:
+                raise ValueError("tiled apply: upRes must divide the halo (16) and the pass-2 tile core")
+            self.p1.net.close()
+
+            def build1(T):
+                return N.gen_resnet(G.placeholder([None, T * T * 4], "x"),
+                                    N.config_4x(T, upRes=u, upsampling_mode=2, batch_norm=batch_norm))
+
+            def build2(T):
+                return N.gen_resnet(G.placeholder([None, T * T * 4], "x"),
+                                    N.config_4x(T // u, upRes=u, upsampling_mode=1, batch_norm=batch_norm))
+
+            self.p1 = _TiledHolder(_TiledPassNet(self.h, self.device, build1, weights_pass1, self.batch, precision, L, core1,
+                                                 halo_hi // u, 4, u))
+            self.p2 = _TiledHolder(_TiledPassNet(self.h, self.device, build2, weights_pass2, self.batch, precision, S, core2,
+                                                 halo_hi, 4, 1))
         vs = self.velScale
         # pass 1: zoom(x,[u,1,1,1]) (GAN/multipassGAN-4x.py:1103); velocities * velScale (:283)
         self.asm1 = capi.make_assemble_desc((L, L, L), 4, (0, 1, 2), (u, 1, 1), (0, 1, 2, 3), (1.0, vs, vs, vs),

@@ -76,3 +76,20 @@ def test_out_three_nets_axis_bookkeeping_fp32(ta):
     nets = [oracle_growing_gen(w[i], i, specs[i], L, upRes=u) for i in (1, 2, 3)]
     ref = op.out_generate3d(x, u, nets[0], nets[1], nets[2], transposeAxis=ta, add_adj_idcs1=True)
     _check("out.py 3 nets ta=%d" % ta, got, ref, "fp32")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_two_pass_4x_tiled_apply_is_bit_identical(precision):
+    """SURVEY 8 a19 wired into the pipeline: both passes applied through overlapping tiles (mpg_tiles_cut -> network on
+    batch*nt*nt tiles -> mpg_tiles_stitch_overlap, halo = receptive-field radius 16 px) must reproduce the whole-slice
+    apply exactly (same kernels, same accumulation order per pixel; frame-edge tiles keep their zero-padded edge)."""
+    L, u = 24, 4  # S = 96: pass-1 tiles 8+2*4 low-res px (2x2 per slice), pass-2 tiles 32+2*16 px (2x2 per slice)
+    x = synth.synthetic_volume(L, seed=21)
+    w1, w2 = P.make_weights_4x(L, 5, upRes=u, randomize_bn=True)
+    whole = P.MultiPass4x(L, w1, w2, upRes=u, precision=precision, batch=4)
+    ref = whole(x).cpu().numpy().copy()
+    tiled = P.MultiPass4x(L, w1, w2, upRes=u, precision=precision, batch=4, tile=(8, 32))
+    assert tiled.p1.net.nt == 2 and tiled.p2.net.nt == 2
+    got = tiled(x).cpu().numpy()
+    assert np.isfinite(got).all() and float(np.abs(ref).max()) > 0
+    assert np.array_equal(got, ref), float(np.abs(got - ref).max())
