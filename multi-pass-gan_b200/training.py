@@ -190,8 +190,8 @@ class Trainer4x:
     def __init__(self, tileSizeLow=16, upRes=4, batch=16, values=None, seed=1, batch_norm=True, bn_decay=0.999,
                  learning_rate=2e-4, adam_beta1=0.5, weight_dld=1.0, k2_l=(1.0, 1.0, 1.0, 1.0), device=0, group=None,
                  precision="fp32", graphs=False):
-        """graphs: replay each optimizer step as ONE captured CUDA graph (single-GPU only; the first call of a step runs
-        eagerly, the second is captured, later ones are replays). The step is ~2300 launches of a few microseconds each,
+        """graphs: replay each optimizer step as ONE captured CUDA graph (the first call of a step runs eagerly, the
+        second is captured, later ones are replays; with world > 1 the graph ends before the gradient all-reduce). The step is ~2300 launches of a few microseconds each,
         so without the graph the host launch path, not the GPU, bounds it.
         precision "fp32": every kernel fp32 (the parity mode, what the reference computes); "fp16": the wide stride-1
         convolutions run forward / dgrad on the tcgen05 kernel (fp16 activations, bf16 gradients, fp32 accumulation and
@@ -207,7 +207,7 @@ class Trainer4x:
         self.weight_dld, self.k2_l = float(weight_dld), tuple(float(k) for k in k2_l)
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.use_graphs = bool(graphs) and self.world == 1
+        self.use_graphs = bool(graphs)  # world > 1: the gradient all-reduce and the Adam launch stay outside the graph
         self.moving = {}
         self.pg, self.pd = ParamSet(self.device), ParamSet(self.device)
         C = self.C
@@ -376,6 +376,11 @@ class Trainer4x:
 
     def _adam(self, ps):
         self.call("mul", ps.g, ps.gw, ps.scale, ps.total, self.st)  # d/dv = d/dW_eff * wscale
+        if self.use_graphs and self.world > 1:
+            return  # captured part ends here; _run_step all-reduces and applies Adam eagerly
+        self._adam_apply(ps)
+
+    def _adam_apply(self, ps):
         par.allreduce_mean(ps.g, self.group)
         if self.use_graphs:
             self.call("adam_dev", ps.v, ps.g, ps.m, ps.vv, ps.total, ps.lr_dev, self.beta1, self.beta2, self.eps, self.st)
@@ -404,6 +409,7 @@ class Trainer4x:
             self._bufs = []
             self.st = torch.cuda.current_stream(self.device).cuda_stream
             body(x, y)
+            self._after_graph(ps)
             self._graphs[key] = "warm"
             return self.losses
         if ent == "warm":
@@ -423,7 +429,13 @@ class Trainer4x:
             ent["y"].copy_(y)
             self.launches += ent["launches"]
         ent["graph"].replay()
+        self._after_graph(ps)
         return self.losses
+
+    def _after_graph(self, ps):
+        if self.use_graphs and self.world > 1:
+            self.st = torch.cuda.current_stream(self.device).cuda_stream
+            self._adam_apply(ps)
 
     def disc_step(self, x_rows, y_rows):
         """sess.run(disc_optimizer, ...) (:1321): Adam on the d_ variables with disc_loss (:751-755)."""
