@@ -172,8 +172,9 @@ def run_ours(args):
         L, u = (64 if args.L == 128 else args.L), 8
         S = L * u
         x_host = synth.synthetic_volume(L, seed=1)
+        batches = tuple(int(b) for b in args.batches.split(",")) + (2,) if args.batches else None
         mp = P.MultiPassOut(L, P.make_weights_out(L, 1, upRes=u, nets=(1, 2)), upRes=u, precision=args.precision,
-                            device=local, rank=rank, world=world, group=None)
+                            device=local, rank=rank, world=world, group=None, batches=batches)
         nets = [mp.passes[1]["net"].net, mp.passes[2]["net"].net]
         flop_per_voxel, workload = 2067984, "multipassGAN-out 8x two-pass %d^3->%d^3 (BASELINE.json configs[2])" % (L, S)
         run_frame = lambda xd, record=False: mp(xd)
@@ -278,7 +279,7 @@ def run_ours(args):
         metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype={"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
-        config=dict(workload=workload, L=L, upRes=u, slice_batch=getattr(mp, "batch", None), precision=args.precision,
+        config=dict(workload=workload, L=L, upRes=u, slice_batch=getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())], precision=args.precision,
                     parallelism="slice-sharded x%d, all-to-all between passes" % world if world > 1 else "single GPU",
                     l2="per-step working set (>= 0.5 GB activations per layer and slice batch) exceeds the 126 MB L2",
                     algorithmic_tflop_per_step=S ** 3 * flop_per_voxel / 1e12),
@@ -314,6 +315,7 @@ def main():
                     help="4x: BASELINE.json configs[1] (the headline, default); 8x: configs[2] (out.py nets 1+2, 64^3->512^3)")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=8, help="slices per network launch (reference: 8)")
+    ap.add_argument("--batches", default="", help="8x workload: slices per launch of generators 1,2 (e.g. 8,2 = the reference's; default: auto)")
     ap.add_argument("--L", type=int, default=128, help="low-res edge (config 2: 128)")
     ap.add_argument("--cpu-slices", type=int, default=16, help="slices per pass timed on the CPU baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -60,8 +60,15 @@ __device__ __forceinline__ uint16_t float_to_h16(float v, int dtype) {
   }
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
+// two floats -> packed 16-bit pair, round-to-nearest-even, saturating at the largest finite value: ONE F2FP.SATFINITE
+// instruction (the clamp + convert + permute sequence it replaces was 6 instructions per pair in every epilogue)
 __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi, int dtype) {
-  return static_cast<uint32_t>(float_to_h16(lo, dtype)) | (static_cast<uint32_t>(float_to_h16(hi, dtype)) << 16);
+  uint32_t r;
+  if (dtype == MPG_F16)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 inline bool is_h16(int dtype) { return dtype == MPG_BF16 || dtype == MPG_F16; }
 inline bool is_dtype(int dtype) { return dtype == MPG_BF16 || dtype == MPG_F16 || dtype == MPG_F32; }

@@ -31,6 +31,11 @@ __device__ __forceinline__ void epi_chunk16(uint32_t taddr, const float* __restr
   const float4 s0 = s4[0], s1 = s4[1], s2 = s4[2], s3 = s4[3];
   const float sh[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
   tmem_ld_wait();
+  if (ca == 0.5f && cb == 0.5f) {  // relu: one FMNMX instead of FMUL + FFMA (same bits: 0.5x + 0.5|x| is exact)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + sh[j], 0.0f);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float x = __uint_as_float(r[j]) + sh[j];
@@ -76,6 +81,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[256];
+  __shared__ float s_pn[2][2][128];  // pixel_norm partial sums: [accumulator][column half][accumulator row]
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -95,7 +101,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) s_shift[i] = p.shift[i];
   // epilogue warps: 4 (256-thread launch) or 8 (384-thread launch: two warps per TMEM lane quarter split the columns)
   const int n_epi_warps = (static_cast<int>(blockDim.x) >> 5) - 4;
-  const int epi_active = (n_epi_warps == 8 && !p.pixel_norm) ? 8 : 4;
+  // (pixel_norm needs the whole pixel's sum of squares: the two warps of a lane quarter each reduce their column half
+  //  and exchange the partial sums through shared memory -- s_pn below -- so all 8 warps stay usable)
+  const int epi_active = (n_epi_warps == 8) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
@@ -362,11 +370,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         float rn = 1.0f;
         if (p.pixel_norm) {
           float ssq = 0.0f;
-          for (int c0 = 0; c0 < p.npad; c0 += 16) {
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float v[16];
             epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) ssq = fmaf(v[j], v[j], ssq);
+          }
+          if (epi_active == 8) {  // add the partner warp's half (same lane quarter, other column half)
+            s_pn[acc][warp >= 8 ? 1 : 0][m] = ssq;
+            quarter_pair_sync(ew);
+            ssq += s_pn[acc][warp >= 8 ? 0 : 1][m];
           }
           rn = rsqrtf(ssq * inv_c + 1e-8f);  // tools_wscale/GAN.py:472-474
         }

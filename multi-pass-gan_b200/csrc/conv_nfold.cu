@@ -51,6 +51,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   __shared__ __align__(8) uint64_t b_ready;  // PAIR: both CTAs' resident weights have landed (leader's copy is used)
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[32];
+  __shared__ float s_pn[2][2][128];  // pixel_norm partial sums: [slot][chunk parity][accumulator row]
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -69,8 +70,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
   if (threadIdx.x < 32) s_shift[threadIdx.x] = threadIdx.x < p.cp ? p.shift[threadIdx.x] : 0.0f;
   // 4 epilogue warps (256-thread launch, two CTAs per SM) or 8 (384 threads: two warps per TMEM lane quarter take
-  // the even / odd 8-channel chunks; pixel_norm needs a whole pixel in one thread and keeps 4)
-  const int epi_active = ((blockDim.x >> 5) - 4 == 8 && !p.pixel_norm && p.cp > 8) ? 8 : 4;
+  // the even / odd 8-channel chunks; for pixel_norm they exchange their partial sums of squares through s_pn)
+  const int epi_active = ((blockDim.x >> 5) - 4 == 8 && p.cp > 8) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
@@ -279,10 +280,12 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const bool lane_valid = (lane >= pad0) && (lane < kNfWin - pad0);
     const float act_a = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.6f : 1.0f);
     const float act_b = p.act == MPG_ACT_RELU ? 0.5f : (p.act == MPG_ACT_LRELU ? 0.4f : 0.0f);
+    const bool is_relu = p.act == MPG_ACT_RELU;
     const float inv_c = 1.0f / static_cast<float>(p.cout);
     const int nchunks = p.cp >> 3;
     const int cgrp = (warp - 4) >> 2;           // chunk parity this warp handles when 8 warps are active
     const bool all_chunks = epi_active == 4;
+    int pn_slot = 0;
     int it = 0;
     for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it % p.nbuf;
@@ -317,11 +320,17 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 #pragma unroll
               for (int dx = 1; dx < KS; ++dx) a += t[dx];
               const float x = a + s_shift[c * 8 + j];
-              const float v = fmaf(act_b, fabsf(x), act_a * x);
+              const float v = is_relu ? fmaxf(x, 0.0f) : fmaf(act_b, fabsf(x), act_a * x);
               o[c * 8 + j] = v;
               ssq = fmaf(v, v, ssq);
             }
           }
+        }
+        if (p.pixel_norm && epi_active == 8) {  // add the partner warp's chunks (same image row, other chunk parity)
+          s_pn[pn_slot][cgrp][ew * 32 + lane] = ssq;
+          quarter_pair_sync(ew);
+          ssq += s_pn[pn_slot][cgrp ^ 1][ew * 32 + lane];
+          pn_slot ^= 1;
         }
         const float rn = p.pixel_norm ? rsqrtf(ssq * inv_c + 1e-8f) : 1.0f;  // tools_wscale/GAN.py:472-474
         if (valid) {

@@ -288,7 +288,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   // per-warp staged TMA-store epilogue (conv_igemm.cu): 16-bit outputs made of whole 64-channel groups; needs 4 KB of
   // staging per epilogue warp next to the rings (one A stage is given up for it when that keeps >= 2)
   {
-    const int epi_warps = (ip.threads == kIgMaxThreads && !d.pixel_norm) ? 8 : 4;
+    const int epi_warps = (ip.threads == kIgMaxThreads) ? 8 : 4;
     bool ts = is_h16(d.out_dtype) && d.upsample == 1 && d.cout % 64 == 0 && d.out_cstride == d.cout && occ == 1 &&
               (epi_warps == 4 || npad % 128 == 0);
     if (const char* e = getenv("MPG_IGEMM_TMASTORE")) ts = ts && atoi(e) != 0;
@@ -660,6 +660,8 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     bool thin_in = true;  // every segment <= 8 channels at pixel stride 8: the un-swizzled two-taps-per-MMA staging applies
     for (int s = 0; s < d.nseg; ++s) thin_in = thin_in && d.seg_cin[s] <= 8 && d.seg_cstride[s] == 8;
     (void)thin_in;
+    // (re-measured with the lean issue loops on the 8x generators, tools/step_times_8x.py: widening the rule to 5x5 layers
+    //  with >= 24 input channels, or padding N = 48 to 64 for CTA pairs, both left the frame time unchanged or worse)
     bool nf = nfold_eligible(d) && (round_up(d.cout, 8) * d.seg_ksize[0] <= 64 || cin_total >= 64);
     if (const char* e = getenv("MPG_CONV_NFOLD")) nf = (atoi(e) == 2) ? nfold_eligible(d) : (nf && atoi(e) != 0);
     if (kind == 1 && nf) kind = 3;

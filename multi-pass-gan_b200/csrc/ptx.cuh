@@ -131,6 +131,17 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// 64-thread barrier of the two epilogue warps that share TMEM lane quarter `q` (ids 1..4, immediate operands so the
+// kernel reserves 5 hardware barriers instead of all 16)
+__device__ __forceinline__ void quarter_pair_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
 // 256-bit global store (sm_100+): one full 32-byte sector per lane
 __device__ __forceinline__ void st_global_v8(void* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
                                              uint32_t f, uint32_t g, uint32_t h) {

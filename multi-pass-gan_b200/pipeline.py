@@ -301,7 +301,7 @@ def make_weights_out(L, seed, upRes=8, specs=None, nets=(1, 2), **cfg_kw):
 class MultiPassOut:
     """generate3DUniForNewNetwork (GAN/multipassGAN-out.py:390-618) for one frame, on the device."""
 
-    def __init__(self, L, weights, upRes=8, specs=None, precision="fp16", transposeAxis=0, batches=(8, 2, 2),
+    def __init__(self, L, weights, upRes=8, specs=None, precision="fp16", transposeAxis=0, batches=None,
                  device=0, threshold=THRESHOLD, rank=0, world=1, group=None, **cfg_kw):
         """With world > 1 (generators 1+2, transposeAxis 0: the shipped 8x two-pass recipe) the volume is sharded by
         slice: z-slabs in pass 1, x-slabs in pass 2, one all-to-all per axis change; `__call__` then returns this
@@ -311,6 +311,13 @@ class MultiPassOut:
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
         self.specs = specs or SHIPPED_8X
+        if batches is None:
+            # The reference feeds 8 slices per sess.run to generator 1 and 2 to generators 2/3 (GAN/multipassGAN-out.py:
+            # 439-447,501-509) because of its GPU memory; slices are independent at inference (no batch statistics), so the
+            # batch only sets how many pixels one launch covers. ~8M output pixels per launch keep all 148 SMs busy for
+            # many tiles at every stage (32 slices of 512^2, 2 of 2048^2) and bound the activations per layer.
+            px = self.S * self.S
+            batches = (max(2, min(32, (1 << 23) // px)), max(1, min(16, (1 << 22) // px)), max(1, min(16, (1 << 22) // px)))
         self.cfg = N.config_out(self.L, upRes=self.u, **cfg_kw)
         self.ta = int(transposeAxis)
         self.threshold = float(threshold)

@@ -22,6 +22,18 @@ SHAPES = [
     ("cA3 8->2", dict(cins=[8], ks=[5], cout=2)),
     ("cB3+s3 2/8->1 f32", dict(cins=[2, 8], ks=[5, 1], cout=1, f32out=True)),
 ]
+SHAPES_8X = [
+    ("n2 48->96", dict(cins=[48], ks=[5], cout=96, pn=True)),
+    ("n2 96/48->96", dict(cins=[96, 48], ks=[5, 1], cout=96, pn=True)),
+    ("n2 96->48", dict(cins=[96], ks=[5], cout=48, pn=True)),
+    ("n2 48/96->48", dict(cins=[48, 96], ks=[5, 1], cout=48, pn=True)),
+    ("n2 48->48", dict(cins=[48], ks=[5], cout=48, pn=True)),
+    ("n2 24/12->48", dict(cins=[24, 12], ks=[5, 1], cout=48, pn=True)),
+    ("n1 64->64k3", dict(cins=[64], ks=[3], cout=64, pn=True)),
+    ("n1 32->32k3", dict(cins=[32], ks=[3], cout=32, pn=True)),
+]
+if os.environ.get("PROBE_8X"):
+    SHAPES = SHAPES_8X
 CONFIGS = {
     "default": {},
     "nf256": {"MPG_NFOLD_THREADS": "256"},
@@ -32,6 +44,11 @@ CONFIGS = {
     "skeleton": {"MPG_IGEMM_DBG": "6", "MPG_NFOLD_DBG": "6"},
     "nobres": {"MPG_IGEMM_BRES": "0"},
     "nopair": {"MPG_IGEMM_PAIR": "0"},
+    "occ1": {"MPG_IGEMM_OCC": "1"},
+    "occ1_nomma": {"MPG_IGEMM_OCC": "1", "MPG_IGEMM_DBG": "4"},
+    "occ1_notma": {"MPG_IGEMM_OCC": "1", "MPG_IGEMM_TMASTORE": "0"},
+    "ck64": {"MPG_IGEMM_CK": "64"},
+    "ck32": {"MPG_IGEMM_CK": "32"},
     "nfck32": {"MPG_NFOLD_CK": "32"},
     "nfck32_skel": {"MPG_NFOLD_CK": "32", "MPG_NFOLD_DBG": "6", "MPG_IGEMM_DBG": "6"},
 }
@@ -47,7 +64,7 @@ def time_shape(sh, iters=5):
     f32 = sh.get("f32out", False)
     oc = sh["cout"] if f32 else -(-sh["cout"] // 8) * 8
     plan = capi.ConvPlan(capi.default_handle(0), n, h, w, ws, cs, sh["cout"], oc, act="relu", in_dtype=capi.F16,
-                         out_dtype=capi.F32 if f32 else capi.F16)
+                         out_dtype=capi.F32 if f32 else capi.F16, pixel_norm=bool(sh.get("pn", False)))
     xs = [torch.randn(n, h, w, c, device="cuda").to(torch.float16) for c in cs]
     y = torch.empty(n, h, w, oc, dtype=torch.float32 if f32 else torch.float16, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
@@ -82,7 +99,7 @@ def main():
                 row[name] = None
                 print("  %s / %s: %r" % (cname, name, e))
         res[cname] = row
-        print("%-12s " % cname + "  ".join("%s=%.3f" % (k.split()[0], v) if v is not None else "%s=ERR" % k.split()[0]
+        print("%-12s " % cname + "  ".join("%s=%.3f" % (k.replace(" ", "_"), v) if v is not None else "%s=ERR" % k.replace(" ", "_")
                                             for k, v in row.items()), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/thin_probe.json", "w"), indent=1)
