@@ -399,8 +399,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             for (int q4 = 0; q4 < 4; ++q4) {
               float v[16];
               epi_chunk16(taddr + cg + q4 * 16, &s_shift[cg + q4 * 16], act_a, act_b, act_tanh, v);
+              if (p.pixel_norm) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= rn;
+                for (int j = 0; j < 16; ++j) v[j] *= rn;
+              }
               uint4 lo, hi;
               lo.x = pack_h16x2(v[0], v[1], od);
               lo.y = pack_h16x2(v[2], v[3], od);
@@ -426,8 +428,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         for (int c0 = cbeg; c0 < cend; c0 += 16) {
           float v[16];
           epi_chunk16(taddr + c0, &s_shift[c0], act_a, act_b, act_tanh, v);
+          if (p.pixel_norm) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= rn;
+            for (int j = 0; j < 16; ++j) v[j] *= rn;
+          }
           if (valid) {
             for (int uy = 0; uy < ups; ++uy) {
               for (int ux = 0; ux < ups; ++ux) {
