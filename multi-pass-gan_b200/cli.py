@@ -6,10 +6,11 @@ Same flag grammar as the reference's paramhelpers (`name value` pairs, names cas
 an unknown / unused flag aborts with exit code 1: tools_wscale/paramhelpers.py:16-37), same input files
 (`packedSimPath/sim_%04d/density_low_%04d.uni` + `velocity_low_%04d.uni`, frames [frame_min, frame_max)) and the
 same output files (`packedSimPath/sim_%04d/source_%04d.uni`, GAN/multipassGAN-out.py:616).  Differences:
-  * weights: the reference can only restore TF1 checkpoints (:367-386); a checkpoint reader is not part of this
-    build, so `randomInit <seed>` selects deterministic random-init weights and `weightsNpz <file>`
-    loads a {variable name: array} archive with the reference's checkpoint keys.  Asking for a checkpoint without
-    either aborts.
+  * weights: like the reference (:153-186,367-386) `load_model_test_N` / `load_model_no_N` restore
+    `basePath/test_%04d/model_%04d.ckpt` (`loadEmas 1`: `model_ema_%04d.ckpt`), read by `tfckpt.py` without
+    TensorFlow (checkpoint V2 index + data files).  Two extensions for runs without a trained model:
+    `randomInit <seed>` selects deterministic random-init weights and `weightsNpz <file>` loads a
+    {variable name: array} archive with the reference's variable names.
   * PNG previews (scipy.misc.imsave, gone from scipy) are not written.
 """
 import os
@@ -75,8 +76,9 @@ def main(argv=None):
     fromSim = int(g("fromSim", 1000))
     frame_min = int(g("frame_min", 0))
     for name in ("genModel", "discModel", "testPathStartNo", "change_velocity", "upsamplingMode", "upsampledData", "gpu",
-                 "useVorticities", "useFlags", "useK_Eps_Turb", "usePixelShuffle", "use_mb_stddev", "loadEmas"):
+                 "useVorticities", "useFlags", "useK_Eps_Turb", "usePixelShuffle", "use_mb_stddev"):
         g(name, 0)  # accepted for compatibility; they do not change the shipped apply path
+    load_emas = int(g("loadEmas", 0)) != 0  # model_ema_%04d.ckpt instead of model_%04d.ckpt (:156-160)
     batch_norm = int(g("batchNorm", 0)) != 0
     pixel_norm = int(g("pixelNorm", 1)) != 0
     useVelocities = int(g("useVelocities", 0))
@@ -115,8 +117,24 @@ def main(argv=None):
                                      pixel_norm=pixel_norm, batch_norm=batch_norm, upsampleMode=upsampleMode,
                                      addBicubicUpsample=addBicubic)
     else:
-        raise SystemExit("multipassGAN-out: restoring TF1 checkpoints (%stest_%04d/model_%04d.ckpt) is not implemented; "
-                         "pass `randomInit <seed>` or `weightsNpz <file>`" % (basePath, load[nets[0]][0], load[nets[0]][1]))
+        # the reference's own path (GAN/multipassGAN-out.py:153-186,367-386): basePath/test_%04d/model[_ema]_%04d.ckpt,
+        # Saver keys = variable names without the `gen_N/` scope
+        from . import tfckpt
+        names = P.make_weights_out(simSizeLow, 0, upRes=upRes, specs=specs, nets=nets, pixel_norm=pixel_norm,
+                                   batch_norm=batch_norm, upsampleMode=upsampleMode, addBicubicUpsample=addBicubic)
+        weights = {}
+        for i in nets:
+            prefix = os.path.join(basePath, "test_%04d" % load[i][0],
+                                  ("model_ema_%04d.ckpt" if load_emas else "model_%04d.ckpt") % load[i][1])
+            if not os.path.exists(prefix + ".index"):
+                raise SystemExit("multipassGAN-out: checkpoint %s.index not found; pass `randomInit <seed>` or "
+                                 "`weightsNpz <file>` to run without a trained model" % prefix)
+            weights[i] = tfckpt.load_generator_weights(prefix, sorted(names[i]), "gen_%d" % i)
+            for n, ref in names[i].items():
+                if weights[i][n].shape != ref.shape:
+                    raise SystemExit("multipassGAN-out: %s: '%s' has shape %s, the graph built from the flags needs %s"
+                                     % (prefix, n, weights[i][n].shape, ref.shape))
+            print("Model %d restored from %s." % (i, prefix))
     sim_path = os.path.join(packedSimPath, "sim_%04d" % fromSim)
     frames, head = load_frames(sim_path, frame_min, frame_max, useVelocities, velScale)
     mp = P.MultiPassOut(simSizeLow, weights, upRes=upRes, specs=specs, precision=precision, transposeAxis=transposeAxis,
