@@ -98,6 +98,8 @@ def main(argv=None):
     random_init = g("randomInit", None)        # extension, see module docstring
     weights_npz = g("weightsNpz", None)        # extension
     precision = g("precision", "fp16")         # extension: fp16 | bf16 | fp32
+    io_threads = int(g("ioThreads", 4))        # extension: gzip writer threads of the frame pipeline (io_pipeline.py)
+    uni_chunk_mb = int(g("uniChunkMB", 0))     # extension: >0 = multi-member gzip output deflated on ioThreads threads
     ph.check_unused()
     if tileSizeLow != simSizeLow:
         raise SystemExit("multipassGAN-out: the apply path slices whole frames (tileSize must equal simSize, as in "
@@ -136,21 +138,43 @@ def main(argv=None):
                                      % (prefix, n, weights[i][n].shape, ref.shape))
             print("Model %d restored from %s." % (i, prefix))
     sim_path = os.path.join(packedSimPath, "sim_%04d" % fromSim)
-    frames, head = load_frames(sim_path, frame_min, frame_max, useVelocities, velScale)
     mp = P.MultiPassOut(simSizeLow, weights, upRes=upRes, specs=specs, precision=precision, transposeAxis=transposeAxis,
                         threshold=P.THRESHOLD if genUni else 0.0, pixel_norm=pixel_norm, batch_norm=batch_norm,
                         upsampleMode=upsampleMode, addBicubicUpsample=addBicubic)
     S = simSizeLow * upRes
     print("*****OUTPUT ONLY*****")
-    from . import uni
-    for n, x in enumerate(frames):
+    from . import io_pipeline, uni
+    # header of frame 0 for every output, like the reference (GAN/multipassGAN-out.py:629, :606-610)
+    head_path = os.path.join(sim_path, "density_low_%04d.uni" % 0)
+    if not os.path.exists(head_path):
+        head_path = os.path.join(sim_path, "density_low_%04d.uni" % frame_min)
+    head, _ = uni.read_uni(head_path)
+    head = dict(head)
+    head["dimX"] = head["dimY"] = head["dimZ"] = S
+
+    def load(f):
+        return load_frames(sim_path, f, f + 1, useVelocities, velScale)[0][0]
+
+    def compute(f, x):
         t0 = time.time()
         vol = mp(x)
+        host = vol.cpu().numpy() if genUni else None  # the D2H copy synchronises
         torch.cuda.synchronize()
-        print("%d  time for %d network(s): %.6f" % (frame_min + n, len(nets), time.time() - t0))
-        if genUni:
-            head = dict(head)
-            head["dimX"] = head["dimY"] = head["dimZ"] = S  # GAN/multipassGAN-out.py:608-610
-            uni.write_uni(os.path.join(sim_path, "source_%04d.uni" % (frame_min + n)), head, vol.cpu().numpy())
-            print("stored .uni file")
+        print("%d  time for %d network(s): %.6f" % (f, len(nets), time.time() - t0))
+        return host
+
+    def store(f, host):
+        if host is None:
+            return
+        out_path = os.path.join(sim_path, "source_%04d.uni" % f)
+        if uni_chunk_mb > 0:
+            io_pipeline.write_uni_parallel(out_path, head, host, threads=io_threads, chunk_bytes=uni_chunk_mb << 20)
+        else:
+            uni.write_uni(out_path, head, host)
+        print("stored .uni file")
+
+    stats = io_pipeline.FramePipeline(load, compute, store, prefetch=2, readers=1, writers=io_threads).run(
+        range(frame_min, frame_max))
+    print("frames %d: wall %.2f s (load %.2f, networks %.2f, store %.2f s of thread time)" % (
+        stats["frames"], stats["wall_s"], stats["load_s"], stats["compute_s"], stats["store_s"]))
     return 0
