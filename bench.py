@@ -269,12 +269,25 @@ def run_ours(args):
                           "extrapolated x%d; host zoom/transposes excluded" % (args.cpu_slices, S, S, S, dt,
                                                                                 S // args.cpu_slices))
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic_pair.json")
-    if not os.path.exists(tpath):
-        tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
-    if os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "r01b_dominant_kernels.json")
+    if os.path.exists(tpath):  # ncu --set full capture of the current build (dram__bytes_read.sum + dram__bytes_write.sum)
         with open(tpath) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            k0 = json.load(fh)["kernels"][0]
+            traffic = int(k0["dram_bytes_read"] + k0["dram_bytes_write"])
+    else:
+        tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic_pair.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+    # the bandwidth-bound kernels of the step: the two axis changes (transpose3d + fused threshold), 2 * S^3 * 4 B each
+    bw = None
+    if pass_ms and world == 1:
+        bts = 2.0 * S ** 3 * 4
+        bw = {k: dict(ms=pass_ms[k], achieved_GBps=bts / (pass_ms[k] * 1e-3) / 1e9,
+                      frac_of_hbm_peak=bts / (pass_ms[k] * 1e-3) / 1e9 / peaks["hbm"])
+              for k in ("exchange1", "exchange2")}
+        bw["algorithmic_bytes_each"] = bts
+        bw["peak_GBps"] = peaks["hbm"]
     line = dict(
         metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -288,6 +301,7 @@ def run_ours(args):
                                sustained=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"] / world,
                                peaks=peaks["source"]),
         pass_ms=pass_ms,
+        bandwidth_kernels=bw,
         e2e=dict(value=S ** 3 / (e2e_ms * 1e-3), unit="voxel/s", ms_per_step=e2e_ms,
                  h2d_bytes_per_step=int(x_pin.numel() * 4), d2h_bytes_per_step=int(out_pin.numel() * 4),
                  checksum=checksum),
