@@ -17,7 +17,7 @@ def H():
 
 
 @pytest.mark.parametrize("perm", [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)])
-@pytest.mark.parametrize("dims", [(8, 8, 8), (5, 33, 70), (64, 64, 64), (1, 37, 2)])
+@pytest.mark.parametrize("dims", [(8, 8, 8), (5, 33, 70), (64, 64, 64), (1, 37, 2), (12, 68, 100), (4, 132, 60)])
 def test_transpose3d_exact(perm, dims):
     rng = np.random.default_rng(0)
     a = rng.standard_normal(dims).astype(np.float32)
