@@ -12,6 +12,7 @@ namespace mpg {
 namespace {
 
 constexpr int kMaxSrc = 8;
+constexpr int kPackRows = 8;
 
 struct PackSrc {
   const void* ptr;
@@ -29,7 +30,11 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
   // grid = (ceil(ow/256), n*oh): no 64-bit divisions per pixel (they, not the memory system, bounded this kernel)
   const int x = static_cast<int>(blockIdx.x) * 256 + static_cast<int>(threadIdx.x);
   if (x >= p.ow) return;
-  const int row = static_cast<int>(blockIdx.y);
+  // kPackRows image rows per block: one-row blocks finish in well under a microsecond and the kernel was bound by the
+  // block launch rate (8192 blocks for 8 x 512^2), not by memory
+  for (int rr = 0; rr < kPackRows; ++rr) {
+  const int row = static_cast<int>(blockIdx.y) * kPackRows + rr;
+  if (row >= p.n * p.oh) return;
   const int n = row / p.oh;
   const int y = row - n * p.oh;
   const long long pix = static_cast<long long>(row) * p.ow + x;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
       oc = (oc | 7) + 1;
     }
     for (; oc < p.out_cstride; oc += 8) o[oc >> 3] = make_uint4(0u, 0u, 0u, 0u);
-    return;
+    continue;
   }
   for (int s = 0; s < p.nsrc; ++s) {
     const PackSrc& q = p.src[s];
@@ -94,6 +99,7 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
       reinterpret_cast<float*>(p.out)[pix * p.out_cstride + oc] = 0.0f;
     else
       reinterpret_cast<uint16_t*>(p.out)[pix * p.out_cstride + oc] = 0;
+  }
   }
 }
 
@@ -206,8 +212,8 @@ int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* ou
   p.out_dtype = out_dtype;
   p.out_cstride = out_cstride;
   p.out = out;
-  MPG_CHECK_ARG(static_cast<long long>(n) * oh <= 65535, "pack: n*oh = %lld rows exceed the grid limit", static_cast<long long>(n) * oh);
-  pack_channels_kernel<<<dim3(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>(n * oh)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CHECK_ARG((static_cast<long long>(n) * oh + kPackRows - 1) / kPackRows <= 65535, "pack: n*oh = %lld rows exceed the grid limit", static_cast<long long>(n) * oh);
+  pack_channels_kernel<<<dim3(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>((n * oh + kPackRows - 1) / kPackRows)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }
