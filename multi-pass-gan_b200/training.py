@@ -494,7 +494,7 @@ class Trainer4x:
         return out
 
     def save_checkpoint(self, prefix):
-        """saver.save(sess, test_path + 'model_%04d.ckpt') (GAN/multipassGAN-4x.py:1404-1410): all generator /
+        """saver.save(sess, test_path + 'model_%04d.ckpt') (GAN/multipassGAN-4x.py:1173): all generator /
         discriminator variables and BN moving statistics as a TF checkpoint-V2 bundle (tfckpt.py)."""
         from . import tfckpt
         tfckpt.write_checkpoint(prefix, self.values())
