@@ -182,6 +182,14 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
                     float threshold, void* stream);
 
 /* in-place v < threshold -> 0 (GAN/multipassGAN-out.py:614-615, GAN/multipassGAN-4x.py:1156-1157) */
+/* Multi-GPU axis change between passes as ONE kernel (replaces the np.array(rows).reshape(S,S,S).transpose(..)
+ * of GAN/multipassGAN-out.py:459,521 / -4x.py:1142 when the volume is sharded by slice): this rank's slab [S/G,S,S] is
+ * transposed and every element is stored directly into the output slab of the rank that owns it in the next pass
+ * (peer_out[r] = peer-mapped device pointer of rank r's slab, NVLink / NVSwitch). split_axis 2: received block
+ * [A, b, c_loc]; 1: [A, b_loc, c]; final_perm: permutation of the received block (final_perm[2] != 2). The caller
+ * brackets the launch with cross-rank barriers. */
+int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int world, int rank, int S, int split_axis,
+                   const int final_perm[3], float threshold, void* stream);
 int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------

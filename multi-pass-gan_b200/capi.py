@@ -89,6 +89,7 @@ def lib():
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
     L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
+    L.mpg_reslab_p2p.argtypes = [vp, vp, ctypes.POINTER(vp), ip, ip, ip, ip, ctypes.POINTER(ip), ctypes.c_float, vp]
     L.mpg_tiles_count.argtypes = [ip, ip, ip]
     L.mpg_tiles_cut.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_tiles_stitch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
@@ -308,6 +309,15 @@ def transpose3d(handle, src, dst, dims, perm, threshold=0.0, stream=0):
     pa = (ctypes.c_int * 3)(*[int(x) for x in perm])
     check(lib().mpg_transpose3d(handle.ptr, _ptr(src), _ptr(dst), int(dims[0]), int(dims[1]), int(dims[2]), pa,
                                 float(threshold), stream), "mpg_transpose3d")
+
+
+def reslab_p2p(handle, slab, peer_ptrs, rank, S, split_axis, final_perm, threshold=0.0, stream=0):
+    """Fused transpose + direct stores into every rank's output slab (peer_ptrs: device pointers, one per rank)."""
+    world = len(peer_ptrs)
+    pp = (ctypes.c_void_p * world)(*[int(x) for x in peer_ptrs])
+    pa = (ctypes.c_int * 3)(*[int(x) for x in final_perm])
+    check(lib().mpg_reslab_p2p(handle.ptr, _ptr(slab), pp, world, int(rank), int(S), int(split_axis), pa, float(threshold),
+                               stream), "mpg_reslab_p2p")
 
 
 def threshold(handle, vol, count, thr, stream=0):

@@ -172,6 +172,63 @@ transpose_tile64_kernel(const float* __restrict__ in, float* __restrict__ out, i
   }
 }
 
+// Axis change between passes on several GPUs as ONE kernel: the rank's slab [d0 = S/G, d1, d2] is transposed
+// tile by tile exactly like transpose_tile64_kernel, but every float4 is stored straight into the OUTPUT slab of the rank
+// that owns it in the next pass -- peer memory mapped over NVLink / NVSwitch (CUDA VMM handles from
+// torch.distributed._symmetric_memory). This replaces pack-transpose -> ncclAllToAll -> unpack-permute (three passes over
+// the slab and a staging copy) by one read of the slab and one remote write.
+//   axis roles: x = input axis 2 (contiguous), y = input axis `ay` (becomes contiguous in the output), b = the third.
+//   `split`: the input axis that is sliced across ranks (index / per = destination rank, index % per = local index);
+//   axis 0 carries this rank's offset rank*per (the received slabs are ordered by source rank).
+struct P2PArgs {
+  float* peer[16];
+  int d[3];            // input dims
+  long long so[3];     // output stride of each INPUT axis (in the destination slab)
+  int ay, ab;          // input axes playing y / batch
+  int split, per, rank;
+  float threshold;
+};
+__global__ void __launch_bounds__(256) transpose_p2p_kernel(const float* __restrict__ in, const P2PArgs a) {
+  __shared__ float tile[64][65];
+  const int nx = a.d[2], ny = a.d[a.ay];
+  const int bx = blockIdx.x * 64, by = blockIdx.y * 64;
+  const int bi = blockIdx.z;
+  const long long in_sy = a.ay == 1 ? a.d[2] : static_cast<long long>(a.d[1]) * a.d[2];
+  const long long in_sb = a.ab == 1 ? a.d[2] : static_cast<long long>(a.d[1]) * a.d[2];
+  const int c4 = threadIdx.x & 15, r = threadIdx.x >> 4;
+#pragma unroll
+  for (int k = 0; k < 64; k += 16) {
+    const int x = bx + 4 * c4, y = by + r + k;
+    if (x < nx && y < ny) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(in + bi * in_sb + static_cast<long long>(y) * in_sy + x));
+      tile[r + k][4 * c4 + 0] = v.x;
+      tile[r + k][4 * c4 + 1] = v.y;
+      tile[r + k][4 * c4 + 2] = v.z;
+      tile[r + k][4 * c4 + 3] = v.w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 64; k += 16) {
+    const int x = bx + r + k, y = by + 4 * c4;
+    if (x < nx && y < ny) {
+      int idx[3];
+      idx[2] = x;
+      idx[a.ay] = y;
+      idx[a.ab] = bi;
+      const int dst = idx[a.split] / a.per;
+      idx[a.split] -= dst * a.per;
+      idx[0] += a.rank * a.per;
+      float4 v = make_float4(tile[4 * c4 + 0][r + k], tile[4 * c4 + 1][r + k], tile[4 * c4 + 2][r + k], tile[4 * c4 + 3][r + k]);
+      v.x = v.x < a.threshold ? 0.0f : v.x;
+      v.y = v.y < a.threshold ? 0.0f : v.y;
+      v.z = v.z < a.threshold ? 0.0f : v.z;
+      v.w = v.w < a.threshold ? 0.0f : v.w;
+      *reinterpret_cast<float4*>(a.peer[dst] + idx[0] * a.so[0] + idx[1] * a.so[1] + idx[2] * a.so[2]) = v;
+    }
+  }
+}
+
 // perm[2] == 2: rows stay contiguous, only the two outer axes move (or nothing moves)
 __global__ void __launch_bounds__(256)
 permute_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int d0, int d1, int d2, long long so0,
@@ -288,6 +345,52 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
       transpose_tile_kernel<<<grid, 256, 0, st>>>(in, out, d2, d[a], st_in[a], st_in[b], so[2], so[b], thr);
     }
   }
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* Fused axis change across ranks (see transpose_p2p_kernel). slab: this rank's [S/G, S, S] rows of the finished pass;
+ * peer_out[r]: device pointer (peer-mapped) of rank r's output slab; split_axis: 2 = the new slab axis is the old axis 2
+ * (received block [A, b, c_loc]), 1 = the old axis 1 ([A, b_loc, c]); final_perm: permutation applied to the received
+ * block (as in mpg_transpose3d), final_perm[2] must not be 2. Needs S/G % 4 == 0. The caller brackets the launch with
+ * cross-rank barriers (all ranks done reading the previous contents / all stores landed). */
+int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int world, int rank, int S, int split_axis,
+                   const int final_perm[3], float threshold, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && slab && peer_out && final_perm, "mpg_reslab_p2p: null argument");
+  MPG_CHECK_ARG(world >= 2 && world <= 16 && rank >= 0 && rank < world && S % world == 0, "mpg_reslab_p2p: world=%d rank=%d S=%d", world, rank, S);
+  MPG_CHECK_ARG(split_axis == 1 || split_axis == 2, "mpg_reslab_p2p: split_axis must be 1 or 2");
+  const int per = S / world;
+  MPG_CHECK_ARG(per % 4 == 0 && S % 4 == 0, "mpg_reslab_p2p: S/G = %d must be a multiple of 4", per);
+  int seen[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    MPG_CHECK_ARG(final_perm[k] >= 0 && final_perm[k] < 3, "mpg_reslab_p2p: final_perm[%d]=%d", k, final_perm[k]);
+    ++seen[final_perm[k]];
+  }
+  MPG_CHECK_ARG(seen[0] == 1 && seen[1] == 1 && seen[2] == 1 && final_perm[2] != 2, "mpg_reslab_p2p: unsupported permutation");
+  P2PArgs a;
+  for (int r = 0; r < world; ++r) {
+    MPG_CHECK_ARG(peer_out[r] && (reinterpret_cast<uintptr_t>(peer_out[r]) & 15) == 0, "mpg_reslab_p2p: peer pointer %d", r);
+    a.peer[r] = static_cast<float*>(peer_out[r]);
+  }
+  a.d[0] = per;
+  a.d[1] = S;
+  a.d[2] = S;
+  // received block dims: split 2 -> (S, S, per); split 1 -> (S, per, S); output = permute(received, final_perm)
+  const long long rd[3] = {S, split_axis == 1 ? per : S, split_axis == 2 ? per : S};
+  const long long od[3] = {rd[final_perm[0]], rd[final_perm[1]], rd[final_perm[2]]};
+  const long long st_out[3] = {od[1] * od[2], od[2], 1};
+  for (int k = 0; k < 3; ++k) a.so[final_perm[k]] = st_out[k];
+  a.ay = final_perm[2];
+  a.ab = 3 - 2 - a.ay;
+  a.split = split_axis;
+  a.per = per;
+  a.rank = rank;
+  a.threshold = threshold > 0.0f ? threshold : -INFINITY;
+  MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(slab) & 15) == 0, "mpg_reslab_p2p: slab not 16-byte aligned");
+  dim3 grid(static_cast<unsigned>(ceil_div(a.d[2], 64)), static_cast<unsigned>(ceil_div(a.d[a.ay], 64)),
+            static_cast<unsigned>(a.d[a.ab]));
+  transpose_p2p_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(slab, a);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

@@ -65,6 +65,38 @@ def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final
     return out
 
 
+class PeerSlab:
+    """An output slab allocated in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped
+    into every rank of the group over NVLink / NVSwitch), so that the axis change between passes can be ONE kernel that
+    stores straight into the slab of the rank owning each element (capi.reslab_p2p) instead of pack -> all-to-all ->
+    unpack. `exchange(handle, slab, ...)` = barrier (everyone is done reading the previous contents) -> kernel ->
+    barrier (all remote stores have landed), all on the current stream."""
+
+    def __init__(self, shape, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.tensor = symm_mem.empty(tuple(shape), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.tensor, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+
+    def exchange(self, capi, handle, slab, S, split_axis, final_perm, threshold=0.0):
+        st = torch.cuda.current_stream(self.tensor.device).cuda_stream
+        self.hdl.barrier(channel=0)
+        capi.reslab_p2p(handle, slab, self.ptrs, self.rank, S, split_axis, final_perm, threshold, st)
+        self.hdl.barrier(channel=1)
+        return self.tensor
+
+
+def p2p_usable(S, world):
+    """The fused peer-store exchange needs CUDA, an initialised NCCL group and S/G % 4 == 0 (128-bit stores)."""
+    import os
+    if os.environ.get("MPG_EXCHANGE", "p2p") != "p2p":
+        return False
+    return (world > 1 and torch.cuda.is_available() and dist.is_available() and dist.is_initialized()
+            and dist.get_backend() == "nccl" and (S // world) % 4 == 0)
+
+
 def allreduce_mean(flat, group=None):
     """Data-parallel gradient exchange of the training step: ONE all-reduce over the flat gradient buffer of an
     optimizer, averaged over the ranks (each rank draws its own tile batch; BN batch statistics stay per rank)."""

@@ -165,8 +165,9 @@ class MultiPass4x:
         self.in1 = torch.empty((self.batch, L, L, 4), **f32)
         self.in2 = torch.empty((self.batch, S, S, 4), **f32)
         self.vol_a = torch.empty((self.S_loc, S, S), **f32)
-        self.vol_b = torch.empty((self.S_loc, S, S), **f32)
-        if self.world > 1:
+        self.peer = par.PeerSlab((self.S_loc, S, S), self.device, group) if par.p2p_usable(S, self.world) else None
+        self.vol_b = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
+        if self.world > 1 and self.peer is None:  # NCCL all-to-all path: pack / receive staging
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
         else:
@@ -199,8 +200,11 @@ class MultiPass4x:
             ev[1].record()
         # ---- the .uni hand-over between the two processes: threshold (:1155-1157) + axis change to
         #      slices along x: [Zu,Yu,Xu] -> [Xu_loc, Zu, Yu]
-        par.reslab(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
-                   (2, 0, 1), self.threshold)
+        if self.peer:  # one kernel: transpose + stores into the owning rank's slab over NVLink (parallel.PeerSlab)
+            self.peer.exchange(capi, self.h, self.vol_a, S, 2, (2, 0, 1), self.threshold)
+        else:
+            par.reslab(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
+                       (2, 0, 1), self.threshold)
         if ev:
             ev[2].record()
         for s in range(self.s0, self.s1, B):
@@ -209,8 +213,11 @@ class MultiPass4x:
         if ev:
             ev[3].record()
         # rows [Xu_loc, Zu, Yu] -> .transpose(1,2,0) -> [Zu_loc, Yu, Xu] (:1142), threshold (:1155-1157)
-        par.reslab_mid(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
-                       (1, 2, 0), self.threshold)
+        if self.peer:
+            self.peer.exchange(capi, self.h, self.vol_a, S, 1, (1, 2, 0), self.threshold)
+        else:
+            par.reslab_mid(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
+                           (1, 2, 0), self.threshold)
         if ev:
             ev[4].record()
             self.events = ev
@@ -345,8 +352,9 @@ class MultiPassOut:
             self.passes[idx] = dict(net=pn, desc=desc, batch=B, inbuf=torch.empty((B, L, L, cin), **f32))
             self.flops += pn.net.flops / B * self.S_loc  # this rank's share
         self.vol_rows = torch.empty((self.S_loc, S, S), **f32)
-        self.vol_dim = torch.empty((self.S_loc, S, S), **f32)
-        if self.world > 1:
+        self.peer = par.PeerSlab((self.S_loc, S, S), self.device, group) if par.p2p_usable(S, self.world) else None
+        self.vol_dim = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
+        if self.world > 1 and self.peer is None:
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
         self.launches_per_frame = sum((self.S_loc // p["batch"]) * (p["net"].net.launches + 1) for p in self.passes.values()) \
@@ -367,12 +375,18 @@ class MultiPassOut:
         for s in range(self.s0, self.s1, p["batch"]):
             capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
             p["net"].net.run({"x": p["inbuf"]}, out=rows[s - self.s0], stream=st)
-        par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), 0.0)
+        if self.peer:
+            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), 0.0)
+        else:
+            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), 0.0)
         p = self.passes[2]
         for s in range(self.s0, self.s1, p["batch"]):
             capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
             p["net"].net.run({"x": p["inbuf"], "y": dim[s - self.s0]}, out=rows[s - self.s0], stream=st)
-        par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), self.threshold)
+        if self.peer:
+            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), self.threshold)
+        else:
+            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), self.threshold)
         return dim
 
     def __call__(self, x):
