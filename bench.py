@@ -165,6 +165,8 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference)")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     rank, local, world = par.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -288,12 +290,19 @@ def run_ours(args):
               for k in ("exchange1", "exchange2")}
         bw["algorithmic_bytes_each"] = bts
         bw["peak_GBps"] = peaks["hbm"]
+    elif pass_ms and world > 1:
+        # axis change across ranks: every rank reads its S^3/G slab once and stores (G-1)/G of it into peer slabs
+        remote = (world - 1) / world * S ** 3 / world * 4
+        bw = {k: dict(ms=pass_ms[k], nvlink_GBps_per_rank=remote / (pass_ms[k] * 1e-3) / 1e9,
+                      frac_of_nvlink_900=remote / (pass_ms[k] * 1e-3) / 1e9 / 900.0)
+              for k in ("exchange1", "exchange2")}
+        bw["remote_bytes_per_rank_each"] = remote
     line = dict(
         metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype={"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
         config=dict(workload=workload, L=L, upRes=u, slice_batch=getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())], precision=args.precision,
-                    parallelism="slice-sharded x%d, all-to-all between passes" % world if world > 1 else "single GPU",
+                    parallelism=("slice-sharded x%d, axis change = %s" % (world, "one transpose kernel storing into peer slabs over NVLink (symmetric memory)" if getattr(mp, "peer", None) else "pack + NCCL all-to-all + unpack")) if world > 1 else "single GPU",
                     l2="per-step working set (>= 0.5 GB activations per layer and slice batch) exceeds the 126 MB L2",
                     algorithmic_tflop_per_step=S ** 3 * flop_per_voxel / 1e12),
         algorithmic_tflops=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12,
