@@ -177,3 +177,30 @@ def test_tiles_overlap_cut_and_stitch_roundtrip():
     capi.tiles_stitch_overlap(h, t2, back, n, ty, tx, tile, tile, c, 4, b, 0)
     torch.cuda.synchronize()
     assert np.array_equal(back.cpu().numpy(), x)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("split,perm", [(2, (2, 0, 1)), (2, (2, 1, 0)), (1, (1, 2, 0))])
+def test_reslab_p2p_kernel_matches_numpy(world, split, perm):
+    """mpg_reslab_p2p (fused transpose + stores into the owning rank's slab) with all 'ranks' emulated on one GPU: the
+    peer pointers are G local buffers. Output slab h must be permute(full[:, :, h-range] or full[:, h-range, :], perm),
+    exactly, with the threshold applied (the three (split, perm) pairs are the ones the pipelines use)."""
+    from mpgan_b200 import capi
+    h = capi.default_handle(0)
+    S = 96
+    per = S // world
+    rng = np.random.default_rng(11)
+    full = (rng.random((S, S, S), dtype=np.float32) - 0.2).astype(np.float32)
+    thr = 0.05
+    want_full = np.where(full < thr, 0.0, full).astype(np.float32)
+    outs = [torch.full((per * S * S,), float("nan"), device="cuda") for _ in range(world)]
+    ptrs = [o.data_ptr() for o in outs]
+    for g in range(world):
+        slab = torch.from_numpy(np.ascontiguousarray(full[g * per:(g + 1) * per])).cuda()
+        capi.reslab_p2p(h, slab, ptrs, g, S, split, perm, thr, 0)
+    torch.cuda.synchronize()
+    for r in range(world):
+        blk = want_full[:, :, r * per:(r + 1) * per] if split == 2 else want_full[:, r * per:(r + 1) * per, :]
+        want = np.ascontiguousarray(blk.transpose(perm))
+        got = outs[r].cpu().numpy().reshape(want.shape)
+        assert np.array_equal(got, want), (world, split, perm, r)
