@@ -4,9 +4,11 @@ Within a pass every slice is an independent 2-D inference (GAN/multipassGAN-out.
 owns the contiguous slice range [g*S/G, (g+1)*S/G) of the pass's slice axis.  The only communication is
 the axis change between passes (the `np.array(rows).reshape(S,S,S).transpose(...)` of
 GAN/multipassGAN-out.py:459,521 / GAN/multipassGAN-4x.py:1142): a slab along the old slice axis must
-become a slab along the new one = ONE all-to-all of S^3/G^2-element blocks per rank pair, packed and
-unpacked by the transpose kernel.  NCCL over NVLink 5 / NVSwitch on the GPUs (`torch.distributed`
-backend "nccl"); the same code runs under "gloo" on CPU tensors for the host-logic tests.
+become a slab along the new one = ONE all-to-all of S^3/G^2-element blocks per rank pair.  On the GPUs this
+is a single kernel: `PeerSlab.exchange` transposes the slab and stores every element straight into the output
+slab of the owning rank (symmetric memory mapped over NVLink 5 / NVSwitch, capi.reslab_p2p).  `reslab` /
+`reslab_mid` are the pack -> all_to_all_single -> unpack formulation of the same exchange: NCCL on the GPUs
+when MPG_EXCHANGE=nccl, "gloo" on CPU tensors in the host-logic tests.
 
 `permute3(src, dst, dims, perm, threshold)` is the 3-D axis permutation primitive: on the GPU it is
 capi.transpose3d (mpg_transpose3d), in the CPU tests a torch.permute.
