@@ -8,19 +8,6 @@ namespace mpg {
 
 namespace {
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case MPG_ACT_RELU:
-      return fmaxf(v, 0.0f);
-    case MPG_ACT_LRELU:
-      return 0.6f * v + 0.4f * fabsf(v);  // tools_wscale/GAN.py:733-737 (leak 0.2)
-    case MPG_ACT_TANH:
-      return tanhf(v);
-    default:
-      return v;
-  }
-}
-
 // Branch-free activation: act(v) = ca*v + cb*|v| covers none (1,0), relu (0.5,0.5: exact) and the
 // reference's lrelu 0.6*x + 0.4*|x| (tools_wscale/GAN.py:733-737); tanh is a rare separate pass.
 __device__ __forceinline__ void epi_chunk16(uint32_t taddr, const float* __restrict__ shift16, float ca, float cb,

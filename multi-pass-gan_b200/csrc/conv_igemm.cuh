@@ -1,17 +1,17 @@
 // Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
 //
 // GEMM view: M = output pixels, N = Cout, K = taps x Cin.
-//   - one CTA per SM, persistent over 16x16-pixel output tiles (2 accumulators of M=128:
-//     8 image rows x 16 pixels each), TMEM double buffered (4 accumulators) so the epilogue of
-//     tile i overlaps the MMAs of tile i+1
-//   - A operand: for every (segment, Cin-chunk, dx) ONE TMA box [rows=16+k-1][16 px][CK ch] is
-//     staged in shared memory; the k vertical taps re-use it by advancing the UMMA descriptor
-//     start address by whole image rows (16 px * row_bytes, a multiple of the swizzle atom), so
-//     L2->smem traffic is k x lower than a load per tap. Out-of-image coordinates are zero
-//     filled by TMA, which IS the "SAME" zero padding of tf.nn.conv2d (tools_wscale/GAN.py:691)
-//   - B operand: packed weights [k-tile][Npad][CK], one TMA box per (segment, chunk, dx, dy)
-//   - epilogue: tcgen05.ld -> +shift -> act -> pixel_norm -> bf16/fp32 store (optionally x2
-//     nearest replicated), all fp32
+//   - persistent, warp-specialised CTA (one or two per SM) over 16x16-pixel output tiles = 2 accumulators of M=128
+//     (16 image rows x 8 pixels each); TMEM double buffered (4 accumulators) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1
+//   - A operand: for every (segment, Cin chunk) ONE TMA halo image [16+k-1][16+k-1][CK] lands in swizzled shared
+//     memory; every (dy,dx) tap is the same image addressed through a UMMA descriptor whose start is shifted by whole
+//     pixels and whose 8-row-group stride is the halo pitch. Out-of-image coordinates are zero filled by TMA, which IS
+//     the "SAME" zero padding of tf.nn.conv2d (tools_wscale/GAN.py:691)
+//   - B operand: packed weights [k-tile][Npad][CK]; streamed in stages of k vertical taps, or resident for the CTA's
+//     lifetime when they fit; cta_group::2 CTA pairs hold half of every tile each and issue M=256 MMAs
+//   - epilogue: tcgen05.ld -> +shift -> act -> pixel_norm -> 16-bit / fp32 store (per-warp TMA store for 64-channel
+//     groups, direct 32-byte stores otherwise; optionally x2 nearest replicated), all fp32
 #pragma once
 #include "common.h"
 
@@ -39,11 +39,9 @@ struct IgemmParams {
   int a_stage_bytes, b_stage_bytes;
   int b_tile_bytes;  // one (seg,chunk,dx,dy) weight tile
   int bgroup;        // 1: a B stage holds all ks dy-taps of a (chunk,dx) (same cadence as A); 0: one tap
-  // TMA-store epilogue (16-bit outputs): rows are staged in smem as [box][128 px][box_c ch] (swizzled)
-  int tma_store, box_c, nbox, stage_off, stage_bytes;
-  // halo mode: ONE TMA halo image [16+k-1][16+k-1][CK] per (segment, chunk); every (dy,dx) tap is a
-  // shifted UMMA descriptor into it (accumulator = 16 rows x 8 px). halo_bo: descriptor base_offset rule
-  int halo, halo_bo;
+  // per-warp TMA-store epilogue (16-bit outputs made of 64-channel groups): 4 KB of swizzled staging per epilogue warp
+  // at stage_off; stage_bytes = total staging
+  int tma_store, stage_off, stage_bytes;
   int threads;  // 256 or 384 (launch block size)
   int pair;  // cta_group::2 CTA pairs: each CTA holds half of every weight tile (wide, weight-streaming layers)
   // resident weights: all `ktiles` weight tiles live in smem for the CTA's lifetime (thin layers)

@@ -211,11 +211,9 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.out_dtype = d.out_dtype;
   ip.out_cstride = d.out_cstride;
   // one TMA halo image per (segment, chunk); every (dy,dx) tap is a shifted UMMA descriptor into it. (The earlier
-  // per-dx-image staging and the staged TMA-store epilogue both measured slower on B200 and were removed.)
-  ip.halo = 1;
-  ip.halo_bo = 0;
+  // per-dx-image staging and the block-barrier TMA-store epilogue both measured slower on B200 and were removed.)
   ip.tma_store = 0;
-  ip.a_stage_bytes = (kIgTileH + maxks - 1) * (ip.halo ? (kIgTileW + maxks - 1) : kIgTileW) * rb;
+  ip.a_stage_bytes = (kIgTileH + maxks - 1) * (kIgTileW + maxks - 1) * rb;
   ip.a_stage_bytes = round_up(ip.a_stage_bytes, 1024);
   ip.ktiles = ktiles;
   // CTA pairs (cta_group::2) for the layers that stream their weights: each CTA keeps half of every weight tile
@@ -246,8 +244,6 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   ip.bgroup = (maxks * ip.b_tile_bytes <= 40 * 1024) ? 1 : 0;
   if (const char* e = getenv("MPG_IGEMM_BGROUP")) ip.bgroup = atoi(e) ? 1 : 0;
   ip.b_stage_bytes = ip.b_tile_bytes * (ip.bgroup ? maxks : 1);
-  ip.box_c = (d.out_cstride % 64 == 0) ? 64 : (d.out_cstride % 32 == 0) ? 32 : (d.out_cstride % 16 == 0) ? 16 : 8;
-  ip.nbox = d.out_cstride / ip.box_c;
   ip.stage_bytes = 0;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(4 * npad)) cols <<= 1;
@@ -722,7 +718,7 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
                                 static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
       const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
       const uint32_t box[4] = {static_cast<uint32_t>(p->ck),
-                               static_cast<uint32_t>(mpg::kIgTileW + (p->ip.halo ? d.seg_ksize[s] - 1 : 0)),
+                               static_cast<uint32_t>(mpg::kIgTileW + d.seg_ksize[s] - 1),
                                static_cast<uint32_t>(mpg::kIgTileH + d.seg_ksize[s] - 1), 1u};
       int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
                                box, swizzle_for(p->ck));

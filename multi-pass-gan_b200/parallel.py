@@ -90,6 +90,25 @@ class PeerSlab:
         return self.tensor
 
 
+def make_peer_slab(shape, device, S, world, group=None):
+    """PeerSlab when the fused exchange is usable, else None (-> NCCL all-to-all path). A failing symmetric-memory
+    rendezvous (e.g. no P2P mapping between the visible GPUs) is reported on stderr and ALL ranks fall back together:
+    the rendezvous is collective, and the outcome is agreed on with an all-reduce before anyone proceeds."""
+    if not p2p_usable(S, world):
+        return None
+    import sys
+    slab, ok = None, 1
+    try:
+        slab = PeerSlab(shape, device, group)
+    except Exception as e:  # noqa: BLE001
+        ok = 0
+        sys.stderr.write("mpgan_b200: symmetric-memory exchange unavailable (%s: %s); using the NCCL all-to-all path\n"
+                         % (type(e).__name__, e))
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return slab if int(flag.item()) == 1 else None
+
+
 def p2p_usable(S, world):
     """The fused peer-store exchange needs CUDA, an initialised NCCL group and S/G % 4 == 0 (128-bit stores)."""
     import os

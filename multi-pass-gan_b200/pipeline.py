@@ -165,7 +165,7 @@ class MultiPass4x:
         self.in1 = torch.empty((self.batch, L, L, 4), **f32)
         self.in2 = torch.empty((self.batch, S, S, 4), **f32)
         self.vol_a = torch.empty((self.S_loc, S, S), **f32)
-        self.peer = par.PeerSlab((self.S_loc, S, S), self.device, group) if par.p2p_usable(S, self.world) else None
+        self.peer = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group)
         self.vol_b = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
         if self.world > 1 and self.peer is None:  # NCCL all-to-all path: pack / receive staging
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
@@ -352,7 +352,7 @@ class MultiPassOut:
             self.passes[idx] = dict(net=pn, desc=desc, batch=B, inbuf=torch.empty((B, L, L, cin), **f32))
             self.flops += pn.net.flops / B * self.S_loc  # this rank's share
         self.vol_rows = torch.empty((self.S_loc, S, S), **f32)
-        self.peer = par.PeerSlab((self.S_loc, S, S), self.device, group) if par.p2p_usable(S, self.world) else None
+        self.peer = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group)
         self.vol_dim = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
         if self.world > 1 and self.peer is None:
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
