@@ -305,6 +305,15 @@ def make_weights_out(L, seed, upRes=8, specs=None, nets=(1, 2), **cfg_kw):
     return out
 
 
+def auto_batches(S):
+    """Slices per launch of generators 1, 2, 3 for S x S slices: ~8M / ~4M output pixels per launch (32 / 16 / 16 slices
+    of 512^2, 2 / 1 / 1 of 2048^2); `_pick_batch` later reduces them to divisors of the rank's slice count."""
+    px = int(S) * int(S)
+    b1 = max(2, min(32, (1 << 23) // px))
+    b23 = max(1, min(16, (1 << 22) // px))
+    return (b1, b23, b23)
+
+
 class MultiPassOut:
     """generate3DUniForNewNetwork (GAN/multipassGAN-out.py:390-618) for one frame, on the device."""
 
@@ -323,8 +332,7 @@ class MultiPassOut:
             # 439-447,501-509) because of its GPU memory; slices are independent at inference (no batch statistics), so the
             # batch only sets how many pixels one launch covers. ~8M output pixels per launch keep all 148 SMs busy for
             # many tiles at every stage (32 slices of 512^2, 2 of 2048^2) and bound the activations per layer.
-            px = self.S * self.S
-            batches = (max(2, min(32, (1 << 23) // px)), max(1, min(16, (1 << 22) // px)), max(1, min(16, (1 << 22) // px)))
+            batches = auto_batches(self.S)
         self.cfg = N.config_out(self.L, upRes=self.u, **cfg_kw)
         self.ta = int(transposeAxis)
         self.threshold = float(threshold)

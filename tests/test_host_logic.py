@@ -153,3 +153,28 @@ def test_pick_batch_and_slab_range():
     assert par.slab_range(0, 4, 512) == (0, 128) and par.slab_range(3, 4, 512) == (384, 512)
     with pytest.raises(ValueError):
         par.slab_range(0, 3, 512)
+
+
+def test_auto_batches_and_exchange_selection():
+    """8x pipeline: pixels per launch stay ~constant across slice sizes; the fused peer-store exchange is only selected
+    on CUDA with an initialised NCCL group (CPU / gloo runs use the all_to_all formulation)."""
+    from mpgan_b200 import parallel as par
+    assert P.auto_batches(512) == (32, 16, 16) and P.auto_batches(2048) == (2, 1, 1) and P.auto_batches(128) == (32, 16, 16)
+    assert P.auto_batches(1024) == (8, 4, 4)
+    assert par.p2p_usable(512, 1) is False
+    if not torch.cuda.is_available():
+        assert par.p2p_usable(512, 8) is False
+        assert par.make_peer_slab((64, 512, 512), torch.device("cpu"), 512, 8) is None
+
+
+def test_dry_run_predicts_the_tiny_kernel_for_the_tail_layers():
+    """engine._predict_kind mirrors csrc/conv_plan.cu: ru3 of gen_resnet (8->2, 2(+8)->1) goes to the CUDA-core
+    kernel, the 128->32 layer to the tap-folded tcgen05 kernel, the wide layers to the plain implicit GEMM."""
+    G.reset_default_graph()
+    cfg = N.config_4x(32, upsampling_mode=2)
+    out = N.gen_resnet(G.placeholder([None, 32 * 32 * 4], "x"), cfg)
+    w = W.init_graph_variables(G.get_default_graph(), 1)
+    lab = _labels(engine.CompiledNet(out, w, 8, dry=True))
+    kinds = {l.split()[1]: l.split()[0] for l in lab if l.startswith("conv")}
+    assert kinds["g_cA3"] == "conv[ct]" and kinds["g_cB3+g_s3"] == "conv[ct]"
+    assert kinds["g_cA2"] == "conv[nf]" and kinds["g_cB1+g_s1"] == "conv[tc]" and kinds["g_cA1"] == "conv[tc]"
