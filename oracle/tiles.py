@@ -41,3 +41,33 @@ def concat_tiles(tiles, frame_shape, tile_border=(0, 0, 0, 0)):
             rows.append(np.concatenate(tiles[off:off + frame_shape[2]], axis=2))
         frame.append(np.concatenate(rows, axis=1))
     return np.concatenate(frame, axis=0)
+
+
+def cut_overlap(frames, tile, border):
+    """frames [n, H, W, C] with H = ty*(tile-2*border)+2*border (same for W): overlapped cut with stride tile-2*border,
+    no padding (what mpg_tiles_cut does for the tiled apply). Returns [n*ty*tx, tile, tile, C]."""
+    core = tile - 2 * border
+    n, H, W, _ = frames.shape
+    ty, tx = (H - 2 * border) // core, (W - 2 * border) // core
+    assert ty * core + 2 * border == H and tx * core + 2 * border == W
+    return np.stack([frames[i, y * core:y * core + tile, x * core:x * core + tile] for i in range(n) for y in range(ty)
+                     for x in range(tx)])
+
+
+def stitch_overlap(tiles, n, ty, tx, border):
+    """Restatement of mpg_tiles_stitch_overlap (NOT a reference function: concatTiles drops the frame-edge band, this
+    keeps it): tiles [n*ty*tx, th, tw, C] -> [n, ty*(th-2b)+2b, tx*(tw-2b)+2b, C]. Every tile contributes its centre,
+    tiles on a frame edge also their outer border."""
+    th, tw, c = tiles.shape[1:]
+    ch, cw = th - 2 * border, tw - 2 * border
+    out = np.empty((n, ty * ch + 2 * border, tx * cw + 2 * border, c), tiles.dtype)
+    for i in range(n):
+        for y in range(ty):
+            y0 = 0 if y == 0 else border
+            y1 = th if y == ty - 1 else th - border
+            for x in range(tx):
+                x0 = 0 if x == 0 else border
+                x1 = tw if x == tx - 1 else tw - border
+                t = tiles[(i * ty + y) * tx + x]
+                out[i, y * ch + y0:y * ch + y1, x * cw + x0:x * cw + x1] = t[y0:y1, x0:x1]
+    return out

@@ -126,3 +126,32 @@ def test_two_pass_4x_identity_networks():
     exp = scipy.ndimage.zoom(x[..., 1] * u, [u, u, u], order=1)
     exp[exp < 0.0005] = 0
     assert np.abs(out - exp).max() < 1e-5
+
+
+def test_tiled_apply_needs_exactly_the_receptive_field_halo():
+    """SURVEY App. A.6 on the oracle (fp64): gen_resnet applied to overlapping tiles and stitched with
+    `stitch_overlap` equals the whole-slice apply when the halo is the receptive-field radius (16 output pixels = 4
+    low-res pixels: 8 convs of k=5), and differs when it is one low-res pixel short. This is the property the GPU
+    pipeline's tiled mode (pipeline._TiledPassNet) relies on."""
+    from oracle import tiles as ot_
+    from oracle_nets import oracle_gen_resnet
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import pipeline as P
+    L, u = 24, 4
+    w1, _ = P.make_weights_4x(L, 3, upRes=u, randomize_bn=True)
+    rng = np.random.default_rng(5)
+    x = rng.random((2, L, L, 4))
+    whole = oracle_gen_resnet(w1, L, 2)(x.reshape(2, -1)).reshape(2, L * u, L * u, 1)
+    for halo, exact in ((4, True), (3, False)):
+        core = 8 if halo == 4 else 6           # (L - 2*halo) is a multiple of core in both cases
+        T = core + 2 * halo
+        nt = (L - 2 * halo) // core
+        tiles = ot_.cut_overlap(x, T, halo)
+        assert tiles.shape[0] == 2 * nt * nt
+        yt = oracle_gen_resnet(w1, T, 2)(tiles.reshape(tiles.shape[0], -1)).reshape(-1, T * u, T * u, 1)
+        got = ot_.stitch_overlap(yt, 2, nt, nt, halo * u)
+        err = float(np.abs(got - whole).max())
+        if exact:
+            assert err < 1e-10, err
+        else:
+            assert err > 1e-6, err
