@@ -179,11 +179,11 @@ def test_training_graph_replay_matches_eager():
         a = te.iteration([batches[it]], [batches[it]])
         b = tg.iteration([batches[it]], [batches[it]])
         for k in a:
-            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (it, k, a[k], b[k])
+            assert abs(a[k] - b[k]) <= 3e-4 * max(1.0, abs(a[k])), (it, k, a[k], b[k])
     va, vb = te.values(), tg.values()
     for name in va:
         # biases in front of a batch norm have an exactly-zero gradient; Adam turns their rounding noise into +-lr steps,
         # so only the filter tensors are compared
         if name.endswith("/weight"):
-            assert _rel(vb[name], va[name]) <= 1e-3, (name, _rel(vb[name], va[name]))
+            assert _rel(vb[name], va[name]) <= 3e-3, (name, _rel(vb[name], va[name]))
     assert isinstance(tg._graphs[("d",)], dict)
