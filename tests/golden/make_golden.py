@@ -382,9 +382,69 @@ def make_uni_fixtures():
     print("ref_density.uni / ref_velocity.uni / uni.npz written")
 
 
+def make_sampler_fixtures():
+    """TileCreator.selectRandomTiles without augmentation (the default of GAN/multipassGAN-4x.py: dataAugmentation 0):
+    the reference's own selectRandomTiles / getRandomDatum / getDatum / getRandomTile / cutTile / hasMinDensity /
+    getTileDensity / splitSets, compiled from tools_wscale/tilecreator_t.py and bound to a stub that carries the state
+    __init__ / addData would have set up for 2-D data (dim=2, dim_t=1). `randrange` is Python's random.randrange; the
+    reference passes numpy floats to it (np.floor(bounds)), which Python >= 3.12 rejects, so the shim converts the
+    (integral) bounds with int() -- the documented behaviour of the interpreters the reference ran on."""
+    import random
+    names = ["selectRandomTiles", "getRandomDatum", "getDatum", "getRandomTile", "cutTile", "hasMinDensity",
+             "getTileDensity", "splitSets"]
+    code = ref_methods(os.path.join(REF, "tools_wscale", "tilecreator_t.py"), "TileCreator", names)
+    rnd = random.Random()
+
+    def randrange(a, b):
+        return rnd.randrange(int(a), int(b))
+
+    ns = dict(np=np, randrange=randrange, DATA_KEY_LOW=0, DATA_KEY_HIGH=1, print=lambda *a, **k: None)
+    exec(code, ns)
+
+    class Stub:
+        def TCError(self, msg):
+            raise RuntimeError(msg)
+
+    for name in names:
+        setattr(Stub, name, ns[name])
+    out = {}
+    for tag, (T, L, u, nframes, dmin, part_train, seed) in {"a": (8, 24, 4, 10, 0.02, 0.9, 11), "b": (6, 16, 2, 5, 0.005, 0.6, 5)}.items():
+        rng = np.random.default_rng(seed)
+        S = L * u
+        low = rng.random((nframes, 1, L, L, 4), dtype=np.float32)
+        low[..., 0] *= (rng.random((nframes, 1, L, L)) < 0.15)       # sparse density: many tiles fail densityMinimum
+        low[:, :, : L // 2, :, 0] = 0.0                               # an empty half so that retries really happen
+        high = rng.random((nframes, 1, S, S, 1), dtype=np.float32)
+        st = Stub()
+        st.dim, st.dim_t, st.upres, st.premadeTiles, st.useDataAug = 2, 1, u, False, False
+        st.densityMinimum = dmin
+        st.tile_shape_low = np.array([1, T, T, 4])
+        st.tile_shape_high = np.array([1, T * u, T * u, 1])
+        st.data_flags = {0: dict(channels=4, isLabel=False), 1: dict(channels=1, isLabel=False)}
+        st.data = {0: list(low), 1: list(high)}
+        part_test = {0.9: 0.1, 0.6: 0.4}[part_train]  # TileCreator.__init__: part_x = partX / (partTrain + partTest + partVal)
+        st.part_train, st.part_test = part_train / (part_train + part_test), part_test / (part_train + part_test)
+        st.splitSets()
+        rnd.seed(1000 + seed)
+        xs, ys = [], []
+        for call in range(3):
+            bl, bh = st.selectRandomTiles(5, isTraining=True, augment=False)
+            xs.append(np.asarray(bl, np.float32))
+            ys.append(np.asarray(bh, np.float32))
+        bl, bh = st.selectRandomTiles(4, isTraining=False, augment=False)
+        out.update({tag + "_low": low, tag + "_high": high, tag + "_train_low": np.stack(xs), tag + "_train_high": np.stack(ys),
+                    tag + "_test_low": np.asarray(bl, np.float32), tag + "_test_high": np.asarray(bh, np.float32),
+                    tag + "_cfg": np.array([T, L, u, nframes, dmin, part_train, 1000 + seed], np.float64),
+                    tag + "_borders": np.array(st.setBorders)})
+    np.savez_compressed(os.path.join(HERE, "tilesampler.npz"), **out)
+    print("tilesampler.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
-    which = sys.argv[1:] or ["pipeline", "nets", "tiles", "uni"]
+    which = sys.argv[1:] or ["pipeline", "nets", "tiles", "uni", "sampler"]
+    if "sampler" in which:
+        make_sampler_fixtures()
     if "pipeline" in which:
         make_pipeline_fixtures()
     if "nets" in which:
