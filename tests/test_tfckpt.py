@@ -156,3 +156,24 @@ def test_cli_restores_checkpoints_like_the_reference(tmp_path):
     mp = P.MultiPassOut(L, w, upRes=u, specs=specs, precision="fp32")
     head, vol = uni.read_uni(str(sim / "source_0000.uni"))
     np.testing.assert_array_equal(vol[..., 0], mp(x).cpu().numpy())
+
+
+def test_convert_tool_roundtrip(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ckpt_convert", os.path.join(os.path.dirname(__file__), "..", "tools", "ckpt_convert.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    rng = np.random.default_rng(6)
+    w = {"gen_1/generator/a/weight": rng.standard_normal((3, 3, 4, 8)).astype(np.float32),
+         "gen_1/generator/a/bias": np.full(8, 0.1, np.float32), "gen_2/generator/b/weight": np.ones((1, 1, 2, 2), np.float32)}
+    npz = str(tmp_path / "w.npz")
+    np.savez(npz, **w)
+    prefix = str(tmp_path / "test_0001" / "model_0001.ckpt")
+    assert tool.main(["to-ckpt", npz, prefix, "--strip", "gen_1"]) == 0
+    assert sorted(k for k in tfckpt.list_checkpoint(prefix) if k) == ["generator/a/bias", "generator/a/weight"]
+    back = str(tmp_path / "back.npz")
+    assert tool.main(["to-npz", prefix, back, "--scope", "gen_1"]) == 0
+    got = np.load(back)
+    assert sorted(got.files) == ["gen_1/generator/a/bias", "gen_1/generator/a/weight"]
+    np.testing.assert_array_equal(got["gen_1/generator/a/weight"], w["gen_1/generator/a/weight"])
+    assert tool.main(["list", prefix]) == 0
