@@ -32,13 +32,15 @@ def _all_to_all(recv, send, group):
         recv.view(-1).copy_(send.view(-1))
 
 
-def reslab(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0):
+def reslab(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0, all_to_all=None):
     """Turn this rank's slab along axis 0 into its slab along (old) axis 2, permuted by `final_perm`.
 
     slab      [S/G, S, S]   (a_loc, b, c)  rows of the finished pass, a = old slice axis
     out       the rank's part of the re-sliced volume:  permute(recv[(A), b, c_loc], final_perm)
               where recv is the full-A extent restricted to this rank's c range.
     scratch_* two buffers of S^3/G elements.
+    all_to_all(recv, send, group): the collective (default: torch.distributed all_to_all_single); tests inject an
+              in-process exchange between rank threads.
     Steps: pack [a_loc*b, G, c_loc] -> [G, a_loc*b, c_loc]; all-to-all; the received chunks, ordered by
     source rank, ARE [A, b, c_loc]; one final permutation (with the optional threshold fused).
     """
@@ -47,12 +49,12 @@ def reslab(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_per
         permute3(slab, out, (S, S, S), final_perm, threshold)
         return out
     permute3(slab, scratch_a, (per * S, world, per), (1, 0, 2), 0.0)
-    _all_to_all(scratch_b, scratch_a, group)
+    (all_to_all or _all_to_all)(scratch_b, scratch_a, group)
     permute3(scratch_b, out, (S, S, per), final_perm, threshold)
     return out
 
 
-def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0):
+def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final_perm, threshold=0.0, all_to_all=None):
     """Same as `reslab` but the NEW slab axis is the old axis 1 (b):  [a_loc, B, c] -> perm([A, b_loc, c]).
 
     pack [a_loc, G, b_loc*c] -> [G, a_loc, b_loc*c]; all-to-all -> [A, b_loc, c]; final permutation.
@@ -62,7 +64,7 @@ def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final
         permute3(slab, out, (S, S, S), final_perm, threshold)
         return out
     permute3(slab, scratch_a, (per, world, per * S), (1, 0, 2), 0.0)
-    _all_to_all(scratch_b, scratch_a, group)
+    (all_to_all or _all_to_all)(scratch_b, scratch_a, group)
     permute3(scratch_b, out, (S, per, S), final_perm, threshold)
     return out
 
