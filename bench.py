@@ -93,43 +93,131 @@ class ClockSampler:
 
 
 # ============================================================================ reference / CPU arm
-def cpu_reference_sample(L, u, seed, slices, threads=None):
-    """Time the oracle port of the reference generator on `slices` slices per pass; returns
-    (seconds for the sample, extrapolated voxel/s for the full two-pass frame, cores used)."""
-    import numpy as np
-    import torch
-    import mpgan_b200  # noqa: F401
-    from mpgan_b200 import pipeline as P, synth
-    from oracle import gan as og, networks as on
-
-    if threads:
-        torch.set_num_threads(threads)
-    cores = torch.get_num_threads()
+def job_config(workload, L, u, slice_batch, precision, world, flop_per_voxel):
+    """The `config` object of the JSON line; both arms print the same one (the reference arm is timed on OUR config)."""
     S = L * u
-    w1, w2 = P.make_weights_4x(L, seed, upRes=u)
+    return dict(workload=workload, L=L, upRes=u, slice_batch=slice_batch, precision=precision,
+                parallelism=("slice-sharded x%d" % world) if world > 1 else "single GPU",
+                l2="per-step working set (>= 0.5 GB activations per layer and slice batch) exceeds the 126 MB L2",
+                algorithmic_tflop_per_step=S ** 3 * flop_per_voxel / 1e12)
+
+
+def host_cores():
+    """Host threads this process may use (cgroup / affinity aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def sample_rows(L, u, seed, slices):
+    """The bounded sample of the workload both arms see: `slices` input rows per pass.
+    pass 1: consecutive z-lerped low-res slices (GAN/multipassGAN-4x.py:1103); pass 2: full-res 4-channel slices."""
+    import numpy as np
+    from mpgan_b200 import synth
+    S = L * u
     x = synth.synthetic_volume(L, seed=seed)
     rng = np.random.default_rng(seed)
     z0 = int(rng.integers(0, L - 2))
-    # pass 1 input rows: `slices` consecutive lerped z slices (GAN/multipassGAN-4x.py:1103)
     t = np.linspace(z0, z0 + 1, slices, dtype=np.float32)[:, None, None, None]
-    b1 = (x[z0] * (1 - t) + x[z0 + 1] * t).reshape(slices, -1)
-    b2 = rng.random((slices, S * S * 4), dtype=np.float32)  # pass 2 rows: full-res 4-channel slices
-    t0 = time.perf_counter()
+    b1 = np.ascontiguousarray((x[z0] * (1 - t) + x[z0 + 1] * t).reshape(slices, -1), dtype=np.float32)
+    b2 = rng.random((slices, S * S * 4), dtype=np.float32)
+    return b1, b2
+
+
+def oracle_rows(L, u, seed, b1, b2, dtype):
+    """oracle port of the two 4x generators on the given input rows (pass 1 rows b1, pass 2 rows b2)."""
+    import torch
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import pipeline as P
+    from oracle import gan as og, networks as on
+
+    w1, w2 = P.make_weights_4x(L, seed, upRes=u)
+    outs = []
     with torch.no_grad():
         for rows, w, mode in ((b1, w1, 2), (b2, w2, 1)):
-            ctx = og.Context(og.VarStore(values=w), torch.float32)
-            on.gen_resnet(torch.from_numpy(rows), ctx, on.make_cfg_4x(L, upRes=u, upsampling_mode=mode))
+            ctx = og.Context(og.VarStore(values=w), dtype)
+            y, _ = on.gen_resnet(torch.from_numpy(rows).to(dtype), ctx, on.make_cfg_4x(L, upRes=u, upsampling_mode=mode))
+            outs.append(y.numpy())
+    return outs
+
+
+def cpu_reference_sample(L, u, seed, slices, threads=None, keep=False):
+    """Time the oracle port (fp32, the reference's type) of the reference generator on `slices` slices per pass;
+    returns (seconds for the sample, extrapolated voxel/s for the full two-pass frame, cores used[, outputs])."""
+    import torch
+
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm must use every host core it may run on
+    torch.set_num_threads(threads or host_cores())
+    cores = torch.get_num_threads()
+    S = L * u
+    b1, b2 = sample_rows(L, u, seed, slices)
+    t0 = time.perf_counter()
+    outs = oracle_rows(L, u, seed, b1, b2, torch.float32)
     dt = time.perf_counter() - t0
     frame_s = dt * (S / slices)
+    if keep:
+        return dt, S ** 3 / frame_s, cores, outs
     return dt, S ** 3 / frame_s, cores
+
+
+def err_stats(got, ref):
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = got - ref
+    return dict(rel_l2=float(np.linalg.norm(d) / (np.linalg.norm(ref) + 1e-300)), max_abs=float(np.abs(d).max()),
+                ref_max=float(np.abs(ref).max()))
+
+
+def parity_at_bench_size(mp, L, u, seed, slices, f64_slices, f32_outs, precision, dev):
+    """the parity gate evaluated in the same run at the benchmarked 512x512 slice size.
+    The exact rows the CPU leg times go through the two compiled generators (C ABI, tensor-core path); they are
+    compared with the fp32 oracle outputs of the CPU leg (all rows) and with the fp64 oracle (first `f64_slices` rows:
+    the gate). Tolerances: BASELINE.json north_star (rel-L2 <= 5e-3, max-abs <= 2e-2 x max|ref|; fp32 path 1e-4)."""
+    import numpy as np
+    import torch
+    b1, b2 = sample_rows(L, u, seed, slices)
+    B = mp.batch
+    got = []
+    for rows, net in ((b1, mp.p1.net), (b2, mp.p2.net)):
+        out = []
+        for i in range(0, slices, B):
+            chunk = rows[i:i + B]
+            if chunk.shape[0] < B:  # compiled for a fixed slice batch: pad with repeats of the last row
+                chunk = np.concatenate([chunk, np.repeat(chunk[-1:], B - chunk.shape[0], 0)], 0)
+            y = net.run({"x": torch.from_numpy(chunk).to(dev)})
+            out.append(y.float().cpu().numpy()[:min(B, slices - i)])
+        got.append(np.concatenate(out, 0))
+    torch.cuda.synchronize(dev)
+    k = max(1, min(f64_slices, slices))
+    ref64 = oracle_rows(L, u, seed, b1[:k], b2[:k], torch.float64)
+    rel_tol, abs_tol = (1e-4, 1e-4) if precision == "fp32" else (5e-3, 2e-2)
+    res, gate = {}, True
+    for i, name in enumerate(("pass1", "pass2")):
+        st = err_stats(got[i][:k], ref64[i])
+        st["rows_fp64"] = k
+        if f32_outs is not None:
+            s32 = err_stats(got[i], f32_outs[i])
+            st["vs_fp32_oracle"] = dict(rel_l2=s32["rel_l2"], max_abs=s32["max_abs"], rows=int(got[i].shape[0]))
+            o32 = err_stats(f32_outs[i][:k], ref64[i])
+            st["fp32_oracle_vs_fp64"] = dict(rel_l2=o32["rel_l2"], max_abs=o32["max_abs"])
+        ok = bool(np.isfinite(got[i]).all()) and st["rel_l2"] <= rel_tol and st["max_abs"] <= abs_tol * max(1.0, st["ref_max"])
+        st["ok"] = ok
+        gate = gate and ok
+        res[name] = st
+    res["gate"] = gate
+    res["tolerance"] = dict(rel_l2=rel_tol, max_abs="%g x max(1, max|ref|)" % abs_tol, oracle="fp64 restatement (oracle/)",
+                            size="%dx%d slices, the benchmarked size" % (L * u, L * u))
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return 0  # under torchrun only rank 0 times the CPU path; the other ranks exit without work
     L, u = args.L, 4
-    slices = args.cpu_slices
+    slices = args.ref_slices
     for _ in range(args.warmup):
         cpu_reference_sample(L, u, 1, slices)
     t = []
@@ -146,7 +234,8 @@ def run_reference(args):
     line = dict(impl="reference", metric="output voxels/sec", value=val, unit="voxel/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * sum(t) / len(t), higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=WORKLOAD, L=L, upRes=u, step="bounded CPU sample, see cpu_baseline.sample"),
+                config=job_config(WORKLOAD, L, u, args.batch, args.precision, int(os.environ.get("WORLD_SIZE", "1")),
+                                  FLOP_PER_VOXEL),
                 cpu_baseline=dict(value=val, unit="voxel/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="voxel/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note="TensorFlow 1.x is not installable in this image (no wheel / no network): the reference arm "
@@ -251,7 +340,19 @@ def run_ours(args):
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
-    checksum = float(out_pin.double().sum())
+    # Whole-volume checksum, all-reduced over the ranks so N = 1/2/4/8 print the same numbers when the sharded run
+    # is bit-identical to the single-GPU one: `bits` = sum of the fp32 bit patterns as int64 (wrap-around integer
+    # addition is exact and order independent), plus the double sum / sum of squares for the human reader.
+    res_dev = out_pin.to(dev)
+    chk = torch.stack([res_dev.view(torch.int32).to(torch.int64).sum(),
+                       (res_dev != 0).sum().to(torch.int64)])
+    fsum = torch.stack([res_dev.double().sum(), res_dev.double().square().sum()])
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+    checksum = dict(bits=int(chk[0].item()), nonzero=int(chk[1].item()), sum=float(fsum[0].item()),
+                    sumsq=float(fsum[1].item()), scope="whole volume, all-reduced over ranks")
+    del res_dev
 
     if world > 1:
         dist.barrier()
@@ -264,12 +365,15 @@ def run_ours(args):
     # "sustained" cuBLAS number inside the step, so the stricter (larger) peak is the honest one
     peak = peaks["tflops"]
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline and args.workload == "4x":
-        dt, vox, cores = cpu_reference_sample(L, u, 1, args.cpu_slices)
+        dt, vox, cores, f32_outs = cpu_reference_sample(L, u, 1, args.cpu_slices, keep=True)
         cpu = dict(value=vox, unit="voxel/s", cores=cores, kind="port",
                    sample="oracle port (torch-CPU fp32) of gen_resnet on %d of %d slices per pass at %dx%d (%.1f s), "
                           "extrapolated x%d; host zoom/transposes excluded" % (args.cpu_slices, S, S, S, dt,
                                                                                 S // args.cpu_slices))
+        if getattr(mp, "p2", None) is not None and hasattr(mp.p1, "net") and not args.no_parity:
+            parity = parity_at_bench_size(mp, L, u, 1, args.cpu_slices, args.parity_slices, f32_outs, args.precision, dev)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01b_dominant_kernels.json")
     if os.path.exists(tpath):  # ncu --set full capture of the current build (dram__bytes_read.sum + dram__bytes_write.sum)
@@ -301,10 +405,10 @@ def run_ours(args):
         metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype={"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
-        config=dict(workload=workload, L=L, upRes=u, slice_batch=getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())], precision=args.precision,
-                    parallelism=("slice-sharded x%d, axis change = %s" % (world, "one transpose kernel storing into peer slabs over NVLink (symmetric memory)" if getattr(mp, "peer", None) else "pack + NCCL all-to-all + unpack")) if world > 1 else "single GPU",
-                    l2="per-step working set (>= 0.5 GB activations per layer and slice batch) exceeds the 126 MB L2",
-                    algorithmic_tflop_per_step=S ** 3 * flop_per_voxel / 1e12),
+        config=job_config(workload, L, u, getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())],
+                          args.precision, world, flop_per_voxel),
+        exchange=(("one transpose kernel storing into peer slabs over NVLink (symmetric memory)" if getattr(mp, "peer", None)
+                   else "pack + NCCL all-to-all + unpack") if world > 1 else "transpose3d on the device"),
         algorithmic_tflops=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12,
         frac_of_bf16_peak=dict(burst=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12 / peaks["tflops"] / world,
                                sustained=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"] / world,
@@ -315,6 +419,7 @@ def run_ours(args):
                  h2d_bytes_per_step=int(x_pin.numel() * 4), d2h_bytes_per_step=int(out_pin.numel() * 4),
                  checksum=checksum),
         gpu_launches=int(mp.launches_per_frame * args.steps),
+        checksum=checksum,
         roofline=dict(bound="tensor", kernel="conv_igemm_kernel<64,pair> " + dom_label, achieved=achieved, peak=peak,
                       unit="TFLOP/s", frac=achieved / peak, frac_of_sustained=achieved / peaks["tflops_sustained"],
                       peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops); fp16 operands run at the same kind::f16 rate",
@@ -324,7 +429,12 @@ def run_ours(args):
     )
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity"] = parity
     print(json.dumps(line))
+    if parity is not None and not parity["gate"]:
+        sys.stderr.write("bench.py: PARITY GATE FAILED at the benchmarked size: %s\n" % json.dumps(parity))
+        return 3
     return 0
 
 
@@ -341,7 +451,11 @@ def main():
     ap.add_argument("--batches", default="", help="8x workload: slices per launch of generators 1,2 (e.g. 8,2 = the reference's; default: auto)")
     ap.add_argument("--L", type=int, default=128, help="low-res edge (config 2: 128)")
     ap.add_argument("--cpu-slices", type=int, default=16, help="slices per pass timed on the CPU baseline (~10 s)")
+    ap.add_argument("--ref-slices", type=int, default=4,
+                    help="--impl reference: slices per pass per step (~2-3 s per step, so 25 steps stay under 90 s)")
+    ap.add_argument("--parity-slices", type=int, default=2, help="rows per pass checked against the fp64 oracle (the gate)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

@@ -129,6 +129,14 @@ int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* ou
 int mpg_bicubic_plan_create(mpg_handle h, int in_h, int in_w, int out_h, int out_w, void** plan_out);
 int mpg_bicubic_plan_destroy(void* plan);
 
+/* Standalone tf.image.resize_images(x, [out_h, out_w], mode) of an NHWC tensor with c channels (tools_wscale/GAN.py:541,
+ * GAN.avg_depool): mode 0 = TF1 legacy bilinear (align_corners=False, no half-pixel centres: in = out * in/out,
+ * lerp between floor and min(floor+1, size-1)), mode 2 = TF1 legacy bicubic (needs a plan of mpg_bicubic_plan_create).
+ * Mode 1 (nearest) is mpg_pack_channels. Channels >= c of `out` are written as 0. */
+int mpg_resize_images(mpg_handle h, const void* src, int src_dtype, int src_cstride, int c, int n, int src_h, int src_w,
+                      void* out, int out_dtype, int out_cstride, int out_h, int out_w, int mode, void* bicubic_plan,
+                      void* stream);
+
 /* out[n,y,x] = dens[n,y,x] + R(src[..., src_c])  with R = identity (mode 0, GAN/multipassGAN-out.py:332)
  * or the TF1 bicubic resize (mode 2, GAN/multipassGAN-out.py:330). dens/out fp32 [n,out_h,out_w]. */
 int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_dtype, int src_cstride,

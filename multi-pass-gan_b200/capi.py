@@ -86,6 +86,7 @@ def lib():
     L.mpg_bicubic_plan_create.argtypes = [vp, ip, ip, ip, ip, ctypes.POINTER(vp)]
     L.mpg_bicubic_plan_destroy.argtypes = [vp]
     L.mpg_dens_residual.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
+    L.mpg_resize_images.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
     L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
@@ -281,6 +282,15 @@ def dens_residual(handle, dens, src, src_dtype, src_cstride, src_c, mode, bicubi
                                   int(mode), bicubic_plan.ptr if bicubic_plan is not None else None, int(n),
                                   int(out_h), int(out_w), int(src_h), int(src_w), _ptr(out), stream),
           "mpg_dens_residual")
+
+
+def resize_images(handle, src, src_dtype, src_cstride, c, n, src_h, src_w, out, out_dtype, out_cstride, out_h, out_w, mode,
+                  bicubic_plan=None, stream=0):
+    """tf.image.resize_images(x, [out_h, out_w], mode) with mode 0 (TF1 bilinear) or 2 (TF1 bicubic)."""
+    check(lib().mpg_resize_images(handle.ptr, _ptr(src), int(src_dtype), int(src_cstride), int(c), int(n), int(src_h),
+                                  int(src_w), _ptr(out), int(out_dtype), int(out_cstride), int(out_h), int(out_w),
+                                  int(mode), bicubic_plan.ptr if bicubic_plan is not None else None, stream),
+          "mpg_resize_images")
 
 
 def make_assemble_desc(dims, vol_c, axis_of, zoom, chan_src, chan_scale=None, add_adj=False, out_dtype=BF16,

@@ -75,9 +75,12 @@ def main(argv=None):
     packedSimPath = g("packedSimPath", "../2ddata_sim/")
     fromSim = int(g("fromSim", 1000))
     frame_min = int(g("frame_min", 0))
-    for name in ("genModel", "discModel", "testPathStartNo", "change_velocity", "upsamplingMode", "upsampledData", "gpu",
+    for name in ("genModel", "discModel", "testPathStartNo", "change_velocity", "upsamplingMode", "upsampledData",
                  "useVorticities", "useFlags", "useK_Eps_Turb", "usePixelShuffle", "use_mb_stddev"):
         g(name, 0)  # accepted for compatibility; they do not change the shipped apply path
+    # GAN/multipassGAN-out.py:96-97 exports CUDA_VISIBLE_DEVICES = gpu before TensorFlow starts; CUDA may already be
+    # initialised in this process, so the flag selects the device ordinal instead
+    gpu = int(str(g("gpu", "0")).split(",")[0])
     load_emas = int(g("loadEmas", 0)) != 0  # model_ema_%04d.ckpt instead of model_%04d.ckpt (:156-160)
     batch_norm = int(g("batchNorm", 0)) != 0
     pixel_norm = int(g("pixelNorm", 1)) != 0
@@ -111,6 +114,10 @@ def main(argv=None):
     if not useVelocities:
         raise SystemExit("multipassGAN-out: the shipped generators take (density, vx, vy, vz): useVelocities 1 is required")
     import torch
+    if torch.cuda.is_available():
+        if gpu >= torch.cuda.device_count():
+            raise SystemExit("multipassGAN-out: gpu %d requested, %d visible" % (gpu, torch.cuda.device_count()))
+        torch.cuda.set_device(gpu)
     if weights_npz:
         arch = np.load(weights_npz)
         weights = {i: {k: arch[k] for k in arch.files if k.startswith("gen_%d/" % i)} for i in nets}
@@ -140,7 +147,7 @@ def main(argv=None):
     sim_path = os.path.join(packedSimPath, "sim_%04d" % fromSim)
     mp = P.MultiPassOut(simSizeLow, weights, upRes=upRes, specs=specs, precision=precision, transposeAxis=transposeAxis,
                         threshold=P.THRESHOLD if genUni else 0.0, pixel_norm=pixel_norm, batch_norm=batch_norm,
-                        upsampleMode=upsampleMode, addBicubicUpsample=addBicubic)
+                        upsampleMode=upsampleMode, addBicubicUpsample=addBicubic, device=gpu)
     S = simSizeLow * upRes
     print("*****OUTPUT ONLY*****")
     from . import io_pipeline, uni

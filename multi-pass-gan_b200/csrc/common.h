@@ -76,6 +76,20 @@ inline bool is_dtype(int dtype) { return dtype == MPG_BF16 || dtype == MPG_F16 |
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// Makes `device` current for the scope and restores the caller's device afterwards: every entry point that launches
+// on a handle's device may be called while another device is current (one process can hold handles on several GPUs).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+constexpr int kMaxDevices = 64;
+
 // Encode a tiled tensor map; returns 0 or a CUresult.
 int encode_tmap(mpg_handle h, CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
                 const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,

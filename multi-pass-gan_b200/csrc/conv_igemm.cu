@@ -491,15 +491,18 @@ static IgKernel ig_kernel(int ck, int pair) {
   return ck == 64 ? conv_igemm_kernel<64, false> : (ck == 32 ? conv_igemm_kernel<32, false> : conv_igemm_kernel<16, false>);
 }
 
-// The attribute is per kernel instantiation, not per plan: only ever raise it.
-static size_t g_smem_attr[6] = {0, 0, 0, 0, 0, 0};
+// The attribute is per kernel instantiation AND per device (cudaFuncSetAttribute applies to the current device only):
+// only ever raise it, and remember what each device has.
+static size_t g_smem_attr[kMaxDevices][6] = {};
 
-int igemm_set_smem_attr(int ck, int pair, size_t smem_bytes) {
+int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes) {
   const int slot = (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (pair ? 3 : 0);
-  if (smem_bytes <= g_smem_attr[slot]) return 0;
+  const bool cached = device >= 0 && device < kMaxDevices;
+  if (cached && smem_bytes <= g_smem_attr[device][slot]) return 0;
+  DeviceGuard guard(device);
   cudaError_t e = cudaFuncSetAttribute(ig_kernel(ck, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
-  if (e == cudaSuccess) g_smem_attr[slot] = smem_bytes;
+  if (e == cudaSuccess && cached) g_smem_attr[device][slot] = smem_bytes;
   return static_cast<int>(e);
 }
 

@@ -55,6 +55,6 @@ struct IgemmParams {
 // ck in {16, 32, 64}; returns cudaError_t as int
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
-int igemm_set_smem_attr(int ck, int pair, size_t smem_bytes);
+int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes);
 
 }  // namespace mpg

@@ -394,15 +394,17 @@ static NfKernel nf_kernel(int ck, int ks, int pair) {
   return ck == 64 ? conv_nfold_kernel<64, 3, false> : (ck == 32 ? conv_nfold_kernel<32, 3, false> : conv_nfold_kernel<16, 3, false>);
 }
 
-static size_t g_nf_smem_attr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static size_t g_nf_smem_attr[kMaxDevices][12] = {};  // per device: cudaFuncSetAttribute applies to the current device only
 
-int nfold_set_smem_attr(int ck, int ks, int pair, size_t smem_bytes) {
+int nfold_set_smem_attr(int device, int ck, int ks, int pair, size_t smem_bytes) {
   const int slot = pair ? 8 + (ck == 64 ? 0 : 1) + (ks == 5 ? 0 : 2)
                         : ((ck == 8) ? (ks == 5 ? 6 : 7) : (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (ks == 5 ? 0 : 3));
-  if (smem_bytes <= g_nf_smem_attr[slot]) return 0;
+  const bool cached = device >= 0 && device < kMaxDevices;
+  if (cached && smem_bytes <= g_nf_smem_attr[device][slot]) return 0;
+  DeviceGuard guard(device);
   cudaError_t e = cudaFuncSetAttribute(nf_kernel(ck, ks, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
-  if (e == cudaSuccess) g_nf_smem_attr[slot] = smem_bytes;
+  if (e == cudaSuccess && cached) g_nf_smem_attr[device][slot] = smem_bytes;
   return static_cast<int>(e);
 }
 

@@ -57,6 +57,6 @@ struct NfoldParams {
 
 int nfold_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const NfoldParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
-int nfold_set_smem_attr(int ck, int ks, int pair, size_t smem_bytes);
+int nfold_set_smem_attr(int device, int ck, int ks, int pair, size_t smem_bytes);
 
 }  // namespace mpg

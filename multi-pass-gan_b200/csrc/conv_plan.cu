@@ -311,7 +311,7 @@ int build_igemm(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     if (pairs > pairs_needed) pairs = pairs_needed;
     p->grid = pairs * 2;
   }
-  int r = igemm_set_smem_attr(ck, ip.pair, p->smem_bytes);
+  int r = igemm_set_smem_attr(p->h->device, ck, ip.pair, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes,
               cudaGetErrorString(static_cast<cudaError_t>(r)));
@@ -529,7 +529,7 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     if (pairs > pairs_needed) pairs = pairs_needed;
     p->grid = pairs * 2;
   }
-  int r = nfold_set_smem_attr(ck, ks0, q.pair, p->smem_bytes);
+  int r = nfold_set_smem_attr(p->h->device, ck, ks0, q.pair, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(nfold, max dynamic smem %zu) failed: %s", p->smem_bytes,
               cudaGetErrorString(static_cast<cudaError_t>(r)));
@@ -692,7 +692,7 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     p->flops += 2.0 * d.n * p->oh * p->ow * static_cast<double>(d.seg_ksize[s]) * d.seg_ksize[s] * d.seg_cin[s] * d.cout;
   const float* w[2] = {w_seg0, w_seg1};
   const float* sc[2] = {scale_seg0, scale_seg1};
-  MPG_CUDA(cudaSetDevice(h->device));
+  mpg::DeviceGuard guard(h->device);
   int r = (kind == 1) ? build_igemm(p, w, sc, shift)
           : (kind == 3 ? build_nfold(p, w, sc, shift) : (kind == 4 ? build_tiny(p, w, sc, shift) : build_direct(p, w, sc, shift)));
   if (r) {
@@ -707,6 +707,7 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
   MPG_CHECK_ARG(p && x0 && y, "mpg_conv_plan_run: null argument");
   MPG_CHECK_ARG(p->d.nseg == 1 || x1 != nullptr, "mpg_conv_plan_run: segment 1 input missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mpg::DeviceGuard guard(p->h->device);  // the plan's device, whatever the caller's current device is
   const mpg_conv_desc& d = p->d;
   if (p->kind == 1) {
     const void* xs[2] = {x0, x1};

@@ -287,10 +287,12 @@ int mpg_train_conv_wgrad_tc(mpg_handle h, const void* x, const void* dy, float* 
     if (r) return r;
   }
   const size_t smem_bytes = static_cast<size_t>(p.nstages) * p.stage_bytes + 1024;
-  static size_t attr_set = 0;
-  if (smem_bytes > attr_set) {
+  DeviceGuard guard(h->device);
+  static size_t attr_set[kMaxDevices] = {};  // per device: cudaFuncSetAttribute applies to the current device only
+  const bool cached = h->device >= 0 && h->device < kMaxDevices;
+  if (!cached || smem_bytes > attr_set[h->device]) {
     MPG_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-    attr_set = smem_bytes;
+    if (cached) attr_set[h->device] = smem_bytes;
   }
   conv_wgrad_tc_kernel<<<dim3(static_cast<unsigned>(groups), static_cast<unsigned>(splits)), 256, smem_bytes, st>>>(tm_x, tm_dy, p);
   MPG_CUDA(cudaGetLastError());

@@ -148,6 +148,66 @@ __global__ void __launch_bounds__(256) dens_residual_kernel(const DensParams p) 
   p.out[pix] = p.dens[pix] + add;
 }
 
+// Standalone tf.image.resize_images for any channel count (tools_wscale/GAN.py:541 avg_depool modes 0 / 2 when the
+// result feeds something other than the additive density residual). One thread per (pixel, channel).
+struct ResizeParams {
+  const void* src;  // [n, sh, sw, src_cstride]
+  void* out;        // [n, oh, ow, out_cstride]
+  int src_dtype, src_cstride, out_dtype, out_cstride, c;
+  int mode;  // 0: TF1 legacy bilinear (align_corners=False, no half-pixel centres), 2: TF1 legacy bicubic
+  int n, oh, ow, sh, sw;
+  float scale_y, scale_x;  // in / out, computed in fp32 like CalculateResizeScale
+  const int* iy;
+  const float* wy;
+  const int* ix;
+  const float* wx;
+};
+
+__device__ __forceinline__ float rs_at(const ResizeParams& p, int n, int y, int x, int ch) {
+  const long long o = ((static_cast<long long>(n) * p.sh + y) * p.sw + x) * p.src_cstride + ch;
+  if (p.src_dtype == MPG_F32) return __ldg(reinterpret_cast<const float*>(p.src) + o);
+  return h16_to_float(reinterpret_cast<const uint16_t*>(p.src)[o], p.src_dtype);
+}
+
+__global__ void __launch_bounds__(256) resize_images_kernel(const ResizeParams p) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.n) * p.oh * p.ow * p.out_cstride;
+  if (e >= total) return;
+  const int ch = static_cast<int>(e % p.out_cstride);
+  long long r = e / p.out_cstride;
+  const int x = static_cast<int>(r % p.ow);
+  r /= p.ow;
+  const int y = static_cast<int>(r % p.oh);
+  const int n = static_cast<int>(r / p.oh);
+  float v = 0.0f;
+  if (ch < p.c) {
+    if (p.mode == 0) {
+      // ResizeBilinear: in = out * scale; lower = floor(in), upper = min(lower + 1, size - 1), lerp = in - lower;
+      // top = tl + (tr - tl) * x_lerp; bottom = bl + (br - bl) * x_lerp; out = top + (bottom - top) * y_lerp
+      const float fy = static_cast<float>(y) * p.scale_y, fx = static_cast<float>(x) * p.scale_x;
+      const int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+      const int y1 = min(y0 + 1, p.sh - 1), x1 = min(x0 + 1, p.sw - 1);
+      const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+      const float tl = rs_at(p, n, y0, x0, ch), tr = rs_at(p, n, y0, x1, ch);
+      const float bl = rs_at(p, n, y1, x0, ch), br = rs_at(p, n, y1, x1, ch);
+      const float top = tl + (tr - tl) * lx;
+      const float bot = bl + (br - bl) * lx;
+      v = top + (bot - top) * ly;
+    } else {
+#pragma unroll
+      for (int ty = 0; ty < 4; ++ty) {
+        const int sy = p.iy[y * 4 + ty];
+        float row = 0.0f;
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) row += rs_at(p, n, sy, p.ix[x * 4 + tx], ch) * p.wx[x * 4 + tx];
+        v += row * p.wy[y * 4 + ty];
+      }
+    }
+  }
+  if (p.out_dtype == MPG_F32) reinterpret_cast<float*>(p.out)[e] = v;
+  else reinterpret_cast<uint16_t*>(p.out)[e] = float_to_h16(v, p.out_dtype);
+}
+
 // TF1 bicubic coefficient table (Keys, A = -0.75, 1024 entries), fp32 like resize_bicubic_op.cc
 void bicubic_axis(int in_size, int out_size, std::vector<int>& idx, std::vector<float>& wts) {
   static float tab[1025][2];
@@ -240,6 +300,49 @@ int mpg_bicubic_plan_create(mpg_handle h, int in_h, int in_w, int out_h, int out
 
 int mpg_bicubic_plan_destroy(void* plan) {
   if (plan) cudaFree(plan);
+  return MPG_OK;
+}
+
+int mpg_resize_images(mpg_handle h, const void* src, int src_dtype, int src_cstride, int c, int n, int src_h, int src_w,
+                      void* out, int out_dtype, int out_cstride, int out_h, int out_w, int mode, void* bicubic_plan,
+                      void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && src && out, "mpg_resize_images: null argument");
+  MPG_CHECK_ARG(mode == 0 || mode == 2, "mpg_resize_images: mode must be 0 (bilinear) or 2 (TF1 bicubic); nearest is mpg_pack_channels");
+  MPG_CHECK_ARG(is_dtype(src_dtype) && is_dtype(out_dtype), "mpg_resize_images: bad dtype");
+  MPG_CHECK_ARG(c > 0 && c <= src_cstride && c <= out_cstride && n > 0 && src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0,
+                "mpg_resize_images: bad shape");
+  MPG_CHECK_ARG(mode == 0 || bicubic_plan != nullptr, "mpg_resize_images: bicubic plan missing");
+  ResizeParams p;
+  p.src = src;
+  p.out = out;
+  p.src_dtype = src_dtype;
+  p.src_cstride = src_cstride;
+  p.out_dtype = out_dtype;
+  p.out_cstride = out_cstride;
+  p.c = c;
+  p.mode = mode;
+  p.n = n;
+  p.oh = out_h;
+  p.ow = out_w;
+  p.sh = src_h;
+  p.sw = src_w;
+  p.scale_y = static_cast<float>(src_h) / static_cast<float>(out_h);
+  p.scale_x = static_cast<float>(src_w) / static_cast<float>(out_w);
+  p.iy = p.ix = nullptr;
+  p.wy = p.wx = nullptr;
+  if (mode == 2) {
+    const char* d = static_cast<const char*>(bicubic_plan);
+    const size_t ni = static_cast<size_t>(out_h + out_w) * 4;
+    p.iy = reinterpret_cast<const int*>(d);
+    p.ix = p.iy + static_cast<size_t>(out_h) * 4;
+    p.wy = reinterpret_cast<const float*>(d + ni * 4);
+    p.wx = p.wy + static_cast<size_t>(out_h) * 4;
+  }
+  const long long total = static_cast<long long>(n) * out_h * out_w * out_cstride;
+  DeviceGuard guard(h->device);
+  resize_images_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }
 

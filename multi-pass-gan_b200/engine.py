@@ -43,11 +43,14 @@ class Buf:
 class View:
     """Lazy NHWC tensor: concatenation of channel ranges of buffers, each nearest-replicated."""
 
-    def __init__(self, h, w, sources, bicubic_of=None):
+    def __init__(self, h, w, sources, bicubic_of=None, resize_mode=2):
         self.h, self.w = h, w
         self.sources = sources  # list of (Buf, c0, nch, fh, fw)
         self.c = sum(s[2] for s in sources)
-        self.bicubic_of = bicubic_of  # (View, ) for a TF1-bicubic resize that is not materialisable lazily
+        # source View of a TF1 bilinear (resize_mode 0) / bicubic (2) resize: not expressible as a lazy gather, it is
+        # either fused into the density residual (bicubic) or materialised by mpg_resize_images
+        self.bicubic_of = bicubic_of
+        self.resize_mode = resize_mode
         self._mat = {}
 
     def whole_buf(self):
@@ -106,7 +109,7 @@ class CompiledNet:
     def _materialize(self, view, dtype):
         """Return a Buf holding `view` in `dtype` with a conv-friendly channel stride."""
         if view.bicubic_of is not None:
-            raise NotImplementedError("bicubic resize is only supported as the additive density residual")
+            return self._materialize_resize(view, dtype)
         b = view.whole_buf()
         if b is not None and b.dtype == dtype and (dtype == capi.F32 or b.cstride % 8 == 0):
             return b
@@ -121,6 +124,34 @@ class CompiledNet:
                                out.cstride, out.n, out.h, out.w, stream)
 
         self.steps.append(("pack %dx%dx%d" % (view.h, view.w, view.c), step))
+        view._mat[dtype] = out
+        return out
+
+    def _plain(self, v):
+        """A lazily gatherable View of `v` (a bilinear / bicubic resize is materialised first)."""
+        if v.bicubic_of is None:
+            return v
+        return View(v.h, v.w, [(self._materialize(v, self.act_dtype), 0, v.c, 1, 1)])
+
+    def _materialize_resize(self, view, dtype):
+        """tf.image.resize_images(.., 0 | 2) (tools_wscale/GAN.py:541) as a standalone launch."""
+        if dtype in view._mat:
+            return view._mat[dtype]
+        sv = view.bicubic_of
+        src = self._materialize(sv, capi.F32 if self.precision == "fp32" else dtype)
+        out = self._alloc(view.h, view.w, view.c, dtype)
+        mode = view.resize_mode
+        plan = None
+        if mode == 2 and not self.dry:
+            plan = capi.BicubicPlan(self.h, sv.h, sv.w, view.h, view.w)
+            self.plans.append(plan)
+        handle = self.h
+
+        def step(stream):
+            capi.resize_images(handle, self._p(src), src.dtype, src.cstride, view.c, out.n, sv.h, sv.w, self._p(out),
+                               out.dtype, out.cstride, view.h, view.w, mode, plan, stream)
+
+        self.steps.append(("resize mode %d %dx%d->%dx%dx%d" % (mode, sv.h, sv.w, view.h, view.w, view.c), step))
         view._mat[dtype] = out
         return out
 
@@ -225,9 +256,7 @@ class CompiledNet:
                 vs = [views[t.node.id] for t in n.inputs]
                 srcs = []
                 for v in vs:
-                    if v.bicubic_of is not None:
-                        raise NotImplementedError("concat of a bicubic resize")
-                    srcs.extend(v.sources)
+                    srcs.extend(self._plain(v).sources)
                 views[n.id] = View(n.out.shape[1], n.out.shape[2], srcs)
             elif op == "resize":
                 views[n.id] = self._lower_resize(n, views[n.inputs[0].node.id])
@@ -262,8 +291,7 @@ class CompiledNet:
         return View(h, w, [(alias, 0, c, 1, 1)])
 
     def _lower_slice(self, n, v):
-        if v.bicubic_of is not None:
-            raise NotImplementedError("slice of a bicubic resize")
+        v = self._plain(v)
         c0, c1 = n.attrs["c0"], n.attrs["c1"]
         srcs, pos = [], 0
         for (b, s0, nch, fh, fw) in v.sources:
@@ -280,12 +308,11 @@ class CompiledNet:
             if oh % v.h or ow % v.w:
                 raise NotImplementedError("nearest resize with a non-integer factor")
             fh, fw = oh // v.h, ow // v.w
-            if v.bicubic_of is not None:
-                raise NotImplementedError("nearest resize of a bicubic resize")
+            v = self._plain(v)
             return View(oh, ow, [(b, c0, nch, f0 * fh, f1 * fw) for (b, c0, nch, f0, f1) in v.sources])
-        if m == 2:
-            return View(oh, ow, list(v.sources), bicubic_of=v)
-        raise NotImplementedError("resize method %d (bilinear) is unused by the shipped configurations" % m)
+        if m in (0, 2):  # 0: TF1 bilinear (GAN.avg_depool default mode), 2: TF1 bicubic
+            return View(oh, ow, list(v.sources), bicubic_of=self._plain(v), resize_mode=m)
+        raise NotImplementedError("resize method %d is not a tf.image.ResizeMethod used by tools_wscale/GAN.py" % m)
 
     def _lower_add(self, n, views):
         va, vb = views[n.inputs[0].node.id], views[n.inputs[1].node.id]
@@ -299,6 +326,8 @@ class CompiledNet:
             raise NotImplementedError("density residual: neither operand is a dense fp32 tensor")
         out = self._alloc(dens.h, dens.w, 1, capi.F32)
         handle = self.h
+        if other.bicubic_of is not None and other.resize_mode != 2:
+            other = View(other.h, other.w, [(self._materialize(other, capi.F32), 0, other.c, 1, 1)])
         if other.bicubic_of is not None:
             sv = other.bicubic_of
             (sb, c0, nch, fh, fw), = sv.sources
@@ -350,7 +379,7 @@ class CompiledNet:
         x0 = ins[0]
         x1 = ins[1] if len(ins) > 1 else None
         if self.dry:
-            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride, grp.ups, out.cstride)
+            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride, grp.ups, out.cstride, grp.act)
         else:
             plan = capi.ConvPlan(self.h, self.batch, ih, iw, ws, [b.cstride for b in ins], cout, out.cstride,
                                  act=grp.act, scales=scs if any_scale else None, shift=shift_total,
@@ -376,7 +405,7 @@ class CompiledNet:
         self.steps.append((label, step))
         return View(oh, ow, [(out, 0, cout, 1, 1)])
 
-    def _predict_kind(self, convs, ins, cout, out_dtype, stride, ups=1, out_cstride=None):
+    def _predict_kind(self, convs, ins, cout, out_dtype, stride, ups=1, out_cstride=None, act=None):
         """Mirror of the auto rule in csrc/conv_plan.cu (dry runs only)."""
         if self.act_dtype == capi.F32 or stride != 1 or cout > 128:
             return capi.KIND_DIRECT
@@ -388,7 +417,7 @@ class CompiledNet:
                 and all(c.inputs[0].shape[3] <= 8 for c in convs) and all(b.cstride == 8 for b in ins)
                 and (out_dtype == capi.F32 or out_cstride % 8 == 0)):
             return capi.KIND_TINY
-        if (ups == 1 and cout <= 32 and convs[0].attrs["ksize"] in (3, 5)
+        if (ups == 1 and cout <= 32 and act != "tanh" and convs[0].attrs["ksize"] in (3, 5)
                 and (len(convs) == 1 or convs[1].attrs["ksize"] == 1)
                 and (out_cstride <= 32 if out_dtype == capi.F32 else out_cstride == cp)
                 and (cp * convs[0].attrs["ksize"] <= 64 or sum(c.inputs[0].shape[3] for c in convs) >= 64)):

@@ -488,5 +488,5 @@ def load_generator_weights(prefix, graph_names, scope):
         if not n.startswith(pre):
             raise ValueError("variable '%s' is outside scope '%s'" % (n, scope))
         keys[n] = n[len(pre):]
-    got = read_checkpoint(prefix, names=sorted(set(keys.values())))
+    got = read_checkpoint(prefix, names=sorted(set(keys.values())), verify_data=True)  # CRC32C of every tensor: corrupt .data fails loudly
     return {n: np.asarray(got[k], dtype=np.float32) for n, k in keys.items()}

@@ -258,7 +258,9 @@ class Trainer4x:
 
     # ------------------------------------------------------------------ plumbing
     def bn_decay_for(self, conv):
-        return self.bn_decay  # both GAN(...) instances of the 4x script use bn_decay (:606, GAN.py:19 default 0.999)
+        """gen_resnet builds GAN(_in) with the class default 0.999 (GAN/multipassGAN-4x.py:546, tools_wscale/GAN.py:19);
+        only disc_binclass passes the `bnDecay` flag (:606)."""
+        return self.bn_decay if conv.scope.rsplit("/", 1)[-1].startswith("d_") else 0.999
 
     def buf(self, shape):
         t = torch.empty(shape, dtype=torch.float32, device=self.device)
