@@ -106,6 +106,41 @@ double mpg_conv_plan_flops(mpg_conv_plan p);
 
 
 /* ------------------------------------------------------------------------------------------
+ * Fused THIN residual block = the reference's resBlock (GAN/multipassGAN-4x.py:505-526) in one launch, for the
+ * channel-poor ends of gen_resnet (:560 ru1 4->8->32, :564 ru4 8->2->1):
+ *
+ *   y = act( conv_kxk(act(conv_kxk(x, w_a*scale_a) + shift_a), w_b*scale_b) + conv_1x1(x, w_s*scale_s) + shift_bs )
+ *
+ * x may be the fp32 rows of the slice assembler (<= 4 channels) read through a nearest x`in_upsample` view
+ * (max_depool, GAN/multipassGAN-4x.py:553-554) or a 16-bit NHWC tensor (<= 8 channels, cstride % 8 == 0); the
+ * intermediate never leaves shared memory. Runs on register-level tensor-core MMAs (mma.sync m16n8k16, fp32
+ * accumulate, 16-bit operands of type mma_dtype). Supported: ksize 5, cmid <= 8, and either cout == 32 (16-bit output,
+ * cstride 32) or cout <= 8 (fp32 output with cstride <= 8, or 16-bit output with cstride 8); anything else
+ * returns MPG_ENOSUP and the caller uses separate mpg_conv plans. Weights are HOST fp32 HWIO with the wscale
+ * constant folded; scale_* (inference BN gamma/sqrt(var+eps)) may be NULL (= 1), shift_* NULL (= 0);
+ * shift_bs is the sum of the folded offsets of conv B and of the shortcut.
+ * -----------------------------------------------------------------------------------------*/
+typedef struct mpg_resblock_desc {
+  int n, h, w;        /* spatial size of the block (after in_upsample)                     */
+  int cin, cmid, cout;
+  int ksize;          /* 5                                                                 */
+  int in_upsample;    /* >= 1: x is [n, h/f, w/f, in_cstride], read through a nearest view */
+  int in_dtype;       /* MPG_F32, or the 16-bit mma_dtype                                  */
+  int in_cstride;
+  int mma_dtype;      /* MPG_F16 / MPG_BF16                                                */
+  int out_dtype;      /* mma_dtype or MPG_F32                                              */
+  int out_cstride;
+  int act;            /* MPG_ACT_NONE / RELU / LRELU, after conv A and after the add       */
+} mpg_resblock_desc;
+typedef struct mpg_resblock_plan_s* mpg_resblock_plan;
+int mpg_resblock_plan_create(mpg_handle h, const mpg_resblock_desc* d, const float* w_a, const float* w_b,
+                             const float* w_s, const float* scale_a, const float* scale_b, const float* scale_s,
+                             const float* shift_a, const float* shift_bs, mpg_resblock_plan* out);
+int mpg_resblock_plan_run(mpg_resblock_plan p, const void* x, void* y, void* stream);
+int mpg_resblock_plan_destroy(mpg_resblock_plan p);
+double mpg_resblock_plan_flops(mpg_resblock_plan p);
+
+/* ------------------------------------------------------------------------------------------
  * Tensor plumbing around the convolutions (bandwidth bound)
  * -----------------------------------------------------------------------------------------*/
 typedef struct mpg_chan_src {

@@ -42,6 +42,14 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class ResblockDesc(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int),
+                ("cin", ctypes.c_int), ("cmid", ctypes.c_int), ("cout", ctypes.c_int), ("ksize", ctypes.c_int),
+                ("in_upsample", ctypes.c_int), ("in_dtype", ctypes.c_int), ("in_cstride", ctypes.c_int),
+                ("mma_dtype", ctypes.c_int), ("out_dtype", ctypes.c_int), ("out_cstride", ctypes.c_int),
+                ("act", ctypes.c_int)]
+
+
 class ChanSrc(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int), ("cstride", ctypes.c_int),
                 ("c0", ctypes.c_int), ("nch", ctypes.c_int), ("factor_h", ctypes.c_int),
@@ -82,6 +90,11 @@ def lib():
     L.mpg_conv_plan_kind.argtypes = [vp]
     L.mpg_conv_plan_flops.argtypes = [vp]
     L.mpg_conv_plan_flops.restype = dp
+    L.mpg_resblock_plan_create.argtypes = [vp, ctypes.POINTER(ResblockDesc), fp, fp, fp, fp, fp, fp, fp, fp, ctypes.POINTER(vp)]
+    L.mpg_resblock_plan_run.argtypes = [vp, vp, vp, vp]
+    L.mpg_resblock_plan_destroy.argtypes = [vp]
+    L.mpg_resblock_plan_flops.argtypes = [vp]
+    L.mpg_resblock_plan_flops.restype = dp
     L.mpg_pack_channels.argtypes = [vp, ctypes.POINTER(ChanSrc), ip, vp, ip, ip, ip, ip, ip, vp]
     L.mpg_bicubic_plan_create.argtypes = [vp, ip, ip, ip, ip, ctypes.POINTER(vp)]
     L.mpg_bicubic_plan_destroy.argtypes = [vp]
@@ -228,6 +241,46 @@ class ConvPlan:
     def close(self):
         if self._p:
             lib().mpg_conv_plan_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ResblockPlan:
+    """mpg_resblock_plan: the reference's thin resBlock (GAN/multipassGAN-4x.py:505-526) as one fused launch.
+    w_a [k,k,cin,cmid], w_b [k,k,cmid,cout], w_s [1,1,cin,cout]: HWIO float32, wscale folded; scales = inference-BN
+    factors per conv or None; shift_a / shift_bs = folded offsets (shift_bs = conv B + shortcut)."""
+
+    def __init__(self, handle, n, h, w, w_a, w_b, w_s, in_dtype, in_cstride, mma_dtype, out_dtype, out_cstride, act="relu",
+                 scale_a=None, scale_b=None, scale_s=None, shift_a=None, shift_bs=None, in_upsample=1):
+        self.handle = handle
+        wa, wb, ws = _f32c(w_a), _f32c(w_b), _f32c(w_s)
+        assert wa.ndim == 4 and wb.ndim == 4 and ws.ndim == 4 and ws.shape[0] == 1 and wa.shape[0] == wb.shape[0]
+        assert wa.shape[3] == wb.shape[2] and ws.shape[2] == wa.shape[2] and ws.shape[3] == wb.shape[3]
+        d = ResblockDesc()
+        d.n, d.h, d.w = int(n), int(h), int(w)
+        d.cin, d.cmid, d.cout, d.ksize = wa.shape[2], wa.shape[3], wb.shape[3], wa.shape[0]
+        d.in_upsample, d.in_dtype, d.in_cstride = int(in_upsample), int(in_dtype), int(in_cstride)
+        d.mma_dtype, d.out_dtype, d.out_cstride = int(mma_dtype), int(out_dtype), int(out_cstride)
+        d.act = _ACT_BY_NAME[act] if not isinstance(act, int) else act
+        self.desc = d
+        keep = [_f32c(a) for a in (scale_a, scale_b, scale_s, shift_a, shift_bs)]
+        self._p = ctypes.c_void_p()
+        check(lib().mpg_resblock_plan_create(handle.ptr, ctypes.byref(d), _fptr(wa), _fptr(wb), _fptr(ws), _fptr(keep[0]),
+                                             _fptr(keep[1]), _fptr(keep[2]), _fptr(keep[3]), _fptr(keep[4]),
+                                             ctypes.byref(self._p)), "mpg_resblock_plan_create")
+        self.flops = lib().mpg_resblock_plan_flops(self._p)
+
+    def run(self, x, y, stream=0):
+        check(lib().mpg_resblock_plan_run(self._p, _ptr(x), _ptr(y), stream), "mpg_resblock_plan_run")
+
+    def close(self):
+        if self._p:
+            lib().mpg_resblock_plan_destroy(self._p)
             self._p = ctypes.c_void_p()
 
     def __del__(self):

@@ -10,6 +10,8 @@ GAN/multipassGAN-4x.py:1128) for one fixed slice-batch size.  Fusion rules (SURV
   dens + bicubic(input density) | dens + input density         -> dens_residual (K8)
 Inputs stay on the device; activations are fp16 (default) or bf16 with fp32 accumulation, or fp32 end to end.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -235,10 +237,30 @@ class CompiledNet:
             absorbed[n.id] = grp
             groups_by_out[t.id] = grp
 
+        # ---- thin residual blocks (resBlock of GAN/multipassGAN-4x.py:505-526 with <= 8 input / middle channels):
+        #      conv A + conv B + 1x1 shortcut become ONE launch (csrc/resblock_thin.cu)
+        rb_of_a, rb_of_b = {}, {}
+        if self.precision != "fp32" and os.environ.get("MPG_FUSE_RESBLOCK", "1") != "0":
+            for gb in groups_by_out.values():
+                ga = self._match_thin_resblock(gb, groups_by_out, uses, output)
+                if ga is not None:
+                    rb_of_a[id(ga)] = gb
+                    rb_of_b[id(gb)] = ga
+
         views = {}
         for n in nodes:
             if n.id in groups_by_out:
-                views[n.id] = self._emit_group(groups_by_out[n.id], views)
+                grp = groups_by_out[n.id]
+                if id(grp) in rb_of_a:
+                    xin = views[grp.convs[0].inputs[0].node.id]
+                    if self._thin_resblock_input(xin, grp.convs[0]) is not None:
+                        views[n.id] = None  # produced inside the fused launch of the block, never materialised
+                        continue
+                    del rb_of_b[id(rb_of_a.pop(id(grp)))]  # input layout not supported: separate launches
+                if id(grp) in rb_of_b:
+                    views[n.id] = self._emit_thin_resblock(rb_of_b[id(grp)], grp, views)
+                    continue
+                views[n.id] = self._emit_group(grp, views)
                 continue
             if n.id in absorbed:
                 continue
@@ -404,6 +426,77 @@ class CompiledNet:
         self.step_bufs[len(self.steps)] = out
         self.steps.append((label, step))
         return View(oh, ow, [(out, 0, cout, 1, 1)])
+
+    # ------------------------------------------------------------------ fused thin residual block
+    @staticmethod
+    def _match_thin_resblock(gb, groups_by_out, uses, output):
+        """Group `gb` = act(conv5x5(A_out) + conv1x1(X)); returns the group of A = act(conv5x5(X)) when the three convs
+        form a thin resBlock the fused kernel covers, else None."""
+        if len(gb.convs) != 2 or gb.pn or gb.ups != 1 or gb.act not in (None, "relu", "lrelu"):
+            return None
+        cb, cs = sorted(gb.convs, key=lambda c: -c.attrs["ksize"])
+        if cb.attrs["ksize"] != 5 or cs.attrs["ksize"] != 1 or cb.attrs["stride"] != 1 or cs.attrs["stride"] != 1:
+            return None
+        ta = cb.inputs[0].node
+        ga = groups_by_out.get(ta.id)
+        if ga is None or len(ga.convs) != 1 or ga.pn or ga.ups != 1 or ga.act != gb.act or ta is output.node:
+            return None
+        ca = ga.convs[0]
+        if ca.attrs["ksize"] != 5 or ca.attrs["stride"] != 1 or len(uses[ta.id]) != 1:
+            return None
+        if cs.inputs[0].node is not ca.inputs[0].node:
+            return None
+        cin, cmid, cout = ca.inputs[0].shape[3], ca.out.shape[3], cb.out.shape[3]
+        if cin > 8 or cmid > 8 or not (cout == 32 or cout <= 8):
+            return None
+        return ga
+
+    def _thin_resblock_input(self, v, ca):
+        """(buffer, nearest factor) when the block input view can be read directly by the fused kernel."""
+        if v is None or v.bicubic_of is not None or len(v.sources) != 1:
+            return None
+        b, c0, nch, fh, fw = v.sources[0]
+        cin = ca.inputs[0].shape[3]
+        if c0 != 0 or nch != cin or fh != fw:
+            return None
+        if b.dtype == capi.F32 and cin <= 4 and b.cstride % 4 == 0:
+            return b, fh
+        if b.dtype == self.act_dtype and b.dtype != capi.F32 and b.cstride % 8 == 0:
+            return b, fh
+        return None
+
+    def _emit_thin_resblock(self, ga, gb, views):
+        ca = ga.convs[0]
+        cb, cs = sorted(gb.convs, key=lambda c: -c.attrs["ksize"])
+        xin = views[ca.inputs[0].node.id]
+        src, up = self._thin_resblock_input(xin, ca)
+        (wa, sca, sha), (wb, scb, shb), (ws, scs, shs) = (self._conv_affine(c) for c in (ca, cb, cs))
+        cin, cmid, cout = wa.shape[2], wa.shape[3], wb.shape[3]
+        out_dtype = capi.F32 if cout == 1 else self.act_dtype
+        out = self._alloc(xin.h, xin.w, cout, out_dtype)
+        flops = 2.0 * self.batch * xin.h * xin.w * (25.0 * cin * cmid + 25.0 * cmid * cout + cin * cout)
+        self.flops += flops
+        plan = None
+        if not self.dry:
+            plan = capi.ResblockPlan(self.h, self.batch, xin.h, xin.w, wa, wb, ws, src.dtype, src.cstride, self.act_dtype,
+                                     out_dtype, out.cstride, act=gb.act, scale_a=sca, scale_b=scb, scale_s=scs,
+                                     shift_a=sha, shift_bs=shb + shs, in_upsample=up)
+            self.plans.append(plan)
+            assert abs(plan.flops - flops) < 1e-6 * flops
+
+        def step(stream):
+            plan.run(self._p(src), self._p(out), stream)
+
+        nm = lambda c: c.attrs["weight"]["var"].name.rsplit("/", 2)[-2]
+        label = "resblock[hm] %s>%s+%s k5/5/1 %d->%d->%d %dx%d%s%s" % (
+            nm(ca), nm(cb), nm(cs), cin, cmid, cout, xin.h, xin.w, " " + gb.act if gb.act else "",
+            " in_up%d" % up if up > 1 else "")
+        if self.verbose:
+            print(label)
+        self.step_flops[len(self.steps)] = flops
+        self.step_bufs[len(self.steps)] = out
+        self.steps.append((label, step))
+        return View(xin.h, xin.w, [(out, 0, cout, 1, 1)])
 
     def _predict_kind(self, convs, ins, cout, out_dtype, stride, ups=1, out_cstride=None, act=None):
         """Mirror of the auto rule in csrc/conv_plan.cu (dry runs only)."""
