@@ -132,24 +132,36 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
     const int r = tile - n * per_img;
     const int ty0 = (r / p.tiles_x) * kTH, tx0 = (r % p.tiles_x) * kTW;
 
-    // ---------------- stage 0: input window -> smem (16-bit), zero outside the image
-    for (int i = tid; i < kIH * kIW; i += kThreads) {
-      const int wy = i / kIW, wx = i - wy * kIW;
-      const int gy = ty0 - (kKS - 1) + wy, gx = tx0 - (kKS - 1) + wx;
-      const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-      if (IN_F32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in) v = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.x) +
-                                                           (static_cast<size_t>(n * hs + gy / p.in_up) * ws + gx / p.in_up) * p.in_cstride));
-        uint2 q;
-        q.x = pack_h16x2(v.x, v.y, dt);
-        q.y = pack_h16x2(v.z, v.w, dt);
-        *reinterpret_cast<uint2*>(s_in + i * IN_PX) = q;
-      } else {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (in) v = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.x) +
-                                                          (static_cast<size_t>(n * hs + gy / p.in_up) * ws + gx / p.in_up) * p.in_cstride));
-        *reinterpret_cast<uint4*>(s_in + i * IN_PX) = v;
+    // ---------------- stage 0: input window -> smem (16-bit), zero outside the image. All loads of a thread are issued
+    //                  before the first conversion (a rolled loop exposed one global-memory latency per window row)
+    {
+      constexpr int NLD = (kIH * kIW + kThreads - 1) / kThreads;
+      uint4 raw[NLD];
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int i = tid + j * kThreads;
+        const int wy = i / kIW, wx = i - wy * kIW;
+        const int gy = ty0 - (kKS - 1) + wy, gx = tx0 - (kKS - 1) + wx;
+        const bool in = i < kIH * kIW && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+        raw[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (in) {
+          const size_t spix = static_cast<size_t>(n * hs + gy / p.in_up) * ws + gx / p.in_up;
+          raw[j] = IN_F32 ? __ldg(reinterpret_cast<const uint4*>(static_cast<const float*>(p.x) + spix * p.in_cstride))
+                          : __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.x) + spix * p.in_cstride));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int i = tid + j * kThreads;
+        if (i >= kIH * kIW) break;
+        if (IN_F32) {
+          uint2 q;
+          q.x = pack_h16x2(__uint_as_float(raw[j].x), __uint_as_float(raw[j].y), dt);
+          q.y = pack_h16x2(__uint_as_float(raw[j].z), __uint_as_float(raw[j].w), dt);
+          *reinterpret_cast<uint2*>(s_in + i * IN_PX) = q;
+        } else {
+          *reinterpret_cast<uint4*>(s_in + i * IN_PX) = raw[j];
+        }
       }
     }
     __syncthreads();
@@ -160,46 +172,70 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
 #pragma unroll
       for (int ks = 0; ks < KS1; ++ks) wA[ks] = lds64(a_w + (ks * 32 + lane) * 8);
       const float shA0 = s_shiftA[2 * t], shA1 = s_shiftA[2 * t + 1];
-      for (int mt = warp; mt < (kMH * kMW) / 16; mt += kThreads / 32) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      // two m-tiles (independent accumulator chains) per iteration: a single chain of dependent HMMAs is latency bound
+      constexpr int NMT = (kMH * kMW) / 16;
+      for (int mt0 = warp * 2; mt0 < NMT; mt0 += (kThreads / 32) * 2) {
+        float acc[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+        const int mtu[2] = {mt0, mt0 + 1 < NMT ? mt0 + 1 : mt0};  // an odd tail recomputes the same tile (stored once)
         if (CPP == 8) {
           // ldmatrix: lane l supplies the row address of matrix l/8 = (pixel half l/8 & 1, tap half l/16)
-          const int q = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const uint32_t base = a_in + ((q / kMW) * kIW + q % kMW) * IN_PX;
+          uint32_t base[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int q = mtu[u] * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            base[u] = a_in + ((q / kMW) * kIW + q % kMW) * IN_PX;
+          }
           const bool hi = lane >= 16;
 #pragma unroll
           for (int ks = 0; ks < KS1; ++ks) {
-            uint32_t a[4];
-            ldmatrix_x4(a, base + (hi ? tap_off(2 * ks + 1, kIW) : tap_off(2 * ks, kIW)) * IN_PX);
-            mma16816<BF16>(acc, a, wA[ks].x, wA[ks].y);
+            const uint32_t o = (hi ? tap_off(2 * ks + 1, kIW) : tap_off(2 * ks, kIW)) * IN_PX;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint32_t a[4];
+              ldmatrix_x4(a, base[u] + o);
+              mma16816<BF16>(acc[u], a, wA[ks].x, wA[ks].y);
+            }
           }
         } else {
           // 8-byte pixels: k = tap*4 + ch; a0/a1 = rows g / g+8 at tap 4ks + t/2, a2/a3 two taps further
-          const int q0 = mt * 16 + g, q1 = q0 + 8;
-          const uint32_t b0 = a_in + ((q0 / kMW) * kIW + q0 % kMW) * IN_PX + (t & 1) * 4;
-          const uint32_t b1 = a_in + ((q1 / kMW) * kIW + q1 % kMW) * IN_PX + (t & 1) * 4;
+          uint32_t b0[2], b1[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int q0 = mtu[u] * 16 + g, q1 = q0 + 8;
+            b0[u] = a_in + ((q0 / kMW) * kIW + q0 % kMW) * IN_PX + (t & 1) * 4;
+            b1[u] = a_in + ((q1 / kMW) * kIW + q1 % kMW) * IN_PX + (t & 1) * 4;
+          }
           const bool odd = (t >> 1) != 0;
 #pragma unroll
           for (int ks = 0; ks < KS1; ++ks) {
             const uint32_t o0 = (odd ? tap_off(4 * ks + 1, kIW) : tap_off(4 * ks, kIW)) * IN_PX;
             const uint32_t o1 = (odd ? tap_off(4 * ks + 3, kIW) : tap_off(4 * ks + 2, kIW)) * IN_PX;
-            uint32_t a[4];
-            a[0] = lds32(b0 + o0);
-            a[1] = lds32(b1 + o0);
-            a[2] = lds32(b0 + o1);
-            a[3] = lds32(b1 + o1);
-            mma16816<BF16>(acc, a, wA[ks].x, wA[ks].y);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint32_t a[4];
+              a[0] = lds32(b0[u] + o0);
+              a[1] = lds32(b1[u] + o0);
+              a[2] = lds32(b0[u] + o1);
+              a[3] = lds32(b1[u] + o1);
+              mma16816<BF16>(acc[u], a, wA[ks].x, wA[ks].y);
+            }
           }
         }
 #pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-          const int q = mt * 16 + g + hrow * 8;
-          const int my = q / kMW, mx = q - my * kMW;
-          const int gy = ty0 - (kKS - 1) / 2 + my, gx = tx0 - (kKS - 1) / 2 + mx;
-          const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-          const float v0 = in ? act_apply(acc[2 * hrow] + shA0, ca, cb) : 0.0f;
-          const float v1 = in ? act_apply(acc[2 * hrow + 1] + shA1, ca, cb) : 0.0f;
-          *reinterpret_cast<uint32_t*>(s_mid + q * 16 + t * 4) = pack_h16x2(v0, v1, dt);
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && mt0 + 1 >= NMT) break;
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+            const int q = mtu[u] * 16 + g + hrow * 8;
+            const int my = q / kMW, mx = q - my * kMW;
+            const int gy = ty0 - (kKS - 1) / 2 + my, gx = tx0 - (kKS - 1) / 2 + mx;
+            const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+            const float v0 = in ? act_apply(acc[u][2 * hrow] + shA0, ca, cb) : 0.0f;
+            const float v1 = in ? act_apply(acc[u][2 * hrow + 1] + shA1, ca, cb) : 0.0f;
+            *reinterpret_cast<uint32_t*>(s_mid + q * 16 + t * 4) = pack_h16x2(v0, v1, dt);
+          }
         }
       }
     }

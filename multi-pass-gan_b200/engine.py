@@ -240,10 +240,14 @@ class CompiledNet:
         # ---- thin residual blocks (resBlock of GAN/multipassGAN-4x.py:505-526 with <= 8 input / middle channels):
         #      conv A + conv B + 1x1 shortcut become ONE launch (csrc/resblock_thin.cu)
         rb_of_a, rb_of_b = {}, {}
-        if self.precision != "fp32" and os.environ.get("MPG_FUSE_RESBLOCK", "1") != "0":
+        fuse = int(os.environ.get("MPG_FUSE_RESBLOCK", "1"))
+        if self.precision != "fp32" and fuse:
             for gb in groups_by_out.values():
                 ga = self._match_thin_resblock(gb, groups_by_out, uses, output)
-                if ga is not None:
+                # <= 8 output channels (ru4: 8->2->1): with one 8-column MMA tile per A fragment the fused kernel is bound
+                # by its ldmatrix traffic and measured slower (0.137 ms) than the two CUDA-core conv_tiny launches
+                # (0.096 ms for 8 x 512^2): fused only on request (MPG_FUSE_RESBLOCK=2)
+                if ga is not None and (fuse >= 2 or gb.convs[0].out.shape[3] == 32):
                     rb_of_a[id(ga)] = gb
                     rb_of_b[id(gb)] = ga
 
