@@ -233,6 +233,12 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
  * brackets the launch with cross-rank barriers. */
 int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int world, int rank, int S, int split_axis,
                    const int final_perm[3], float threshold, void* stream);
+/* Same exchange for `count` consecutive rows [a0, a0+count) of the old slice axis only (`part` points at row a0 of the
+ * rank's slab): lets the caller push every finished slice batch to its owners while the pass is still running, so the
+ * axis change leaves the critical path and ONE cross-rank barrier per pass boundary remains (GAN/multipassGAN-out.py:
+ * 443-459: the rows of a slice batch are final when its sess.run returns). */
+int mpg_reslab_p2p_part(mpg_handle h, const float* part, void* const* peer_out, int world, int S, int a0, int count,
+                        int split_axis, const int final_perm[3], float threshold, void* stream);
 int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -104,6 +104,7 @@ def lib():
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
     L.mpg_threshold.argtypes = [vp, vp, ctypes.c_longlong, ctypes.c_float, vp]
     L.mpg_reslab_p2p.argtypes = [vp, vp, ctypes.POINTER(vp), ip, ip, ip, ip, ctypes.POINTER(ip), ctypes.c_float, vp]
+    L.mpg_reslab_p2p_part.argtypes = [vp, vp, ctypes.POINTER(vp), ip, ip, ip, ip, ip, ctypes.POINTER(ip), ctypes.c_float, vp]
     L.mpg_tiles_count.argtypes = [ip, ip, ip]
     L.mpg_tiles_cut.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_tiles_stitch.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
@@ -381,6 +382,15 @@ def reslab_p2p(handle, slab, peer_ptrs, rank, S, split_axis, final_perm, thresho
     pa = (ctypes.c_int * 3)(*[int(x) for x in final_perm])
     check(lib().mpg_reslab_p2p(handle.ptr, _ptr(slab), pp, world, int(rank), int(S), int(split_axis), pa, float(threshold),
                                stream), "mpg_reslab_p2p")
+
+
+def reslab_p2p_part(handle, part, peer_ptrs, S, a0, count, split_axis, final_perm, threshold=0.0, stream=0):
+    """The same exchange for rows [a0, a0+count) of the old slice axis only (`part` = those rows)."""
+    world = len(peer_ptrs)
+    pp = (ctypes.c_void_p * world)(*[int(x) for x in peer_ptrs])
+    pa = (ctypes.c_int * 3)(*[int(x) for x in final_perm])
+    check(lib().mpg_reslab_p2p_part(handle.ptr, _ptr(part), pp, world, int(S), int(a0), int(count), int(split_axis), pa,
+                                    float(threshold), stream), "mpg_reslab_p2p_part")
 
 
 def threshold(handle, vol, count, thr, stream=0):

@@ -185,7 +185,7 @@ struct P2PArgs {
   int d[3];            // input dims
   long long so[3];     // output stride of each INPUT axis (in the destination slab)
   int ay, ab;          // input axes playing y / batch
-  int split, per, rank;
+  int split, per, a0;  // a0: absolute index along axis 0 of the first row of `in` (rank*per for a whole slab)
   float threshold;
 };
 __global__ void __launch_bounds__(256) transpose_p2p_kernel(const float* __restrict__ in, const P2PArgs a) {
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) transpose_p2p_kernel(const float* __restr
       idx[a.ab] = bi;
       const int dst = idx[a.split] / a.per;
       idx[a.split] -= dst * a.per;
-      idx[0] += a.rank * a.per;
+      idx[0] += a.a0;
       float4 v = make_float4(tile[4 * c4 + 0][r + k], tile[4 * c4 + 1][r + k], tile[4 * c4 + 2][r + k], tile[4 * c4 + 3][r + k]);
       v.x = v.x < a.threshold ? 0.0f : v.x;
       v.y = v.y < a.threshold ? 0.0f : v.y;
@@ -354,11 +354,12 @@ int mpg_transpose3d(mpg_handle h, const float* in, float* out, int d0, int d1, i
  * (received block [A, b, c_loc]), 1 = the old axis 1 ([A, b_loc, c]); final_perm: permutation applied to the received
  * block (as in mpg_transpose3d), final_perm[2] must not be 2. Needs S/G % 4 == 0. The caller brackets the launch with
  * cross-rank barriers (all ranks done reading the previous contents / all stores landed). */
-int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int world, int rank, int S, int split_axis,
-                   const int final_perm[3], float threshold, void* stream) {
+int mpg_reslab_p2p_part(mpg_handle h, const float* part, void* const* peer_out, int world, int S, int a0, int count,
+                        int split_axis, const int final_perm[3], float threshold, void* stream) {
   using namespace mpg;
-  MPG_CHECK_ARG(h && slab && peer_out && final_perm, "mpg_reslab_p2p: null argument");
-  MPG_CHECK_ARG(world >= 2 && world <= 16 && rank >= 0 && rank < world && S % world == 0, "mpg_reslab_p2p: world=%d rank=%d S=%d", world, rank, S);
+  MPG_CHECK_ARG(h && part && peer_out && final_perm, "mpg_reslab_p2p: null argument");
+  MPG_CHECK_ARG(world >= 2 && world <= 16 && S % world == 0, "mpg_reslab_p2p: world=%d S=%d", world, S);
+  MPG_CHECK_ARG(a0 >= 0 && count >= 1 && a0 + count <= S, "mpg_reslab_p2p: rows [%d, %d) outside [0, %d)", a0, a0 + count, S);
   MPG_CHECK_ARG(split_axis == 1 || split_axis == 2, "mpg_reslab_p2p: split_axis must be 1 or 2");
   const int per = S / world;
   MPG_CHECK_ARG(per % 4 == 0 && S % 4 == 0, "mpg_reslab_p2p: S/G = %d must be a multiple of 4", per);
@@ -368,12 +369,14 @@ int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int w
     ++seen[final_perm[k]];
   }
   MPG_CHECK_ARG(seen[0] == 1 && seen[1] == 1 && seen[2] == 1 && final_perm[2] != 2, "mpg_reslab_p2p: unsupported permutation");
+  // axis 0 of the part plays the y role when final_perm[2] == 0: its extent must then allow 128-bit stores
+  MPG_CHECK_ARG(final_perm[2] != 0 || (count % 4 == 0 && a0 % 4 == 0), "mpg_reslab_p2p: rows [%d, +%d) must be 4-aligned for this permutation", a0, count);
   P2PArgs a;
   for (int r = 0; r < world; ++r) {
     MPG_CHECK_ARG(peer_out[r] && (reinterpret_cast<uintptr_t>(peer_out[r]) & 15) == 0, "mpg_reslab_p2p: peer pointer %d", r);
     a.peer[r] = static_cast<float*>(peer_out[r]);
   }
-  a.d[0] = per;
+  a.d[0] = count;
   a.d[1] = S;
   a.d[2] = S;
   // received block dims: split 2 -> (S, S, per); split 1 -> (S, per, S); output = permute(received, final_perm)
@@ -385,14 +388,22 @@ int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int w
   a.ab = 3 - 2 - a.ay;
   a.split = split_axis;
   a.per = per;
-  a.rank = rank;
+  a.a0 = a0;
   a.threshold = threshold > 0.0f ? threshold : -INFINITY;
-  MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(slab) & 15) == 0, "mpg_reslab_p2p: slab not 16-byte aligned");
+  MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(part) & 15) == 0, "mpg_reslab_p2p: slab not 16-byte aligned");
   dim3 grid(static_cast<unsigned>(ceil_div(a.d[2], 64)), static_cast<unsigned>(ceil_div(a.d[a.ay], 64)),
             static_cast<unsigned>(a.d[a.ab]));
-  transpose_p2p_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(slab, a);
+  DeviceGuard guard(h->device);
+  transpose_p2p_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(part, a);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
+}
+
+int mpg_reslab_p2p(mpg_handle h, const float* slab, void* const* peer_out, int world, int rank, int S, int split_axis,
+                   const int final_perm[3], float threshold, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(world >= 2 && rank >= 0 && rank < world && S % world == 0, "mpg_reslab_p2p: world=%d rank=%d S=%d", world, rank, S);
+  return mpg_reslab_p2p_part(h, slab, peer_out, world, S, rank * (S / world), S / world, split_axis, final_perm, threshold, stream);
 }
 
 int mpg_threshold(mpg_handle h, float* vol, long long count, float threshold, void* stream) {

@@ -71,10 +71,18 @@ def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final
 
 class PeerSlab:
     """An output slab allocated in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped
-    into every rank of the group over NVLink / NVSwitch), so that the axis change between passes can be ONE kernel that
-    stores straight into the slab of the rank owning each element (capi.reslab_p2p) instead of pack -> all-to-all ->
-    unpack. `exchange(handle, slab, ...)` = barrier (everyone is done reading the previous contents) -> kernel ->
-    barrier (all remote stores have landed), all on the current stream."""
+    into every rank of the group over NVLink / NVSwitch), so that the axis change between passes is a kernel that
+    stores straight into the slab of the rank owning each element (capi.reslab_p2p[_part]) instead of pack ->
+    all-to-all -> unpack.
+
+    Protocol of the pipelines (ONE cross-rank barrier per pass boundary):
+      * `push_part(..)` after every finished slice batch: that batch's rows are transposed and stored into their
+        owners' slabs while the rest of the pass is still running (no barrier before it: see below)
+      * `landed()` at the pass boundary: device-side barrier -- every rank's stores are visible before anyone reads
+      * the two axis changes of a frame target two DIFFERENT symmetric slabs (`PeerSlab` instances), so nobody
+        stores into a slab a peer may still be reading in the current pass; the slab written by the first exchange of
+        frame f+1 was last read before the closing barrier of frame f.
+    `exchange(..)` is the whole-slab form (barrier before only when `wait_readers`)."""
 
     def __init__(self, shape, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -84,9 +92,18 @@ class PeerSlab:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
 
-    def exchange(self, capi, handle, slab, S, split_axis, final_perm, threshold=0.0):
+    def push_part(self, capi, handle, part, S, a0, count, split_axis, final_perm, threshold=0.0):
         st = torch.cuda.current_stream(self.tensor.device).cuda_stream
-        self.hdl.barrier(channel=0)
+        capi.reslab_p2p_part(handle, part, self.ptrs, S, a0, count, split_axis, final_perm, threshold, st)
+
+    def landed(self, channel=0):
+        self.hdl.barrier(channel=channel)
+        return self.tensor
+
+    def exchange(self, capi, handle, slab, S, split_axis, final_perm, threshold=0.0, wait_readers=True):
+        st = torch.cuda.current_stream(self.tensor.device).cuda_stream
+        if wait_readers:
+            self.hdl.barrier(channel=0)
         capi.reslab_p2p(handle, slab, self.ptrs, self.rank, S, split_axis, final_perm, threshold, st)
         self.hdl.barrier(channel=1)
         return self.tensor

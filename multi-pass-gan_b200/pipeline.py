@@ -165,8 +165,14 @@ class MultiPass4x:
         self.in1 = torch.empty((self.batch, L, L, 4), **f32)
         self.in2 = torch.empty((self.batch, S, S, 4), **f32)
         self.vol_a = torch.empty((self.S_loc, S, S), **f32)
+        # vol_b: the first-pass volume re-sliced along x (input of pass 2); vol_c: the finished frame. Two buffers, so the
+        # second axis change never stores into memory a peer (or a pending D2H copy) may still be reading (parallel.PeerSlab)
         self.peer = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group)
+        self.peer_c = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group) if self.peer else None
+        if self.peer is not None and self.peer_c is None:
+            self.peer = None
         self.vol_b = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
+        self.vol_c = self.peer_c.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
         if self.world > 1 and self.peer is None:  # NCCL all-to-all path: pack / receive staging
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
@@ -174,7 +180,7 @@ class MultiPass4x:
             self.scr_a = self.scr_b = None
         nb = self.S_loc // self.batch
         self.flops = (self.p1.net.flops + self.p2.net.flops) / self.batch * self.S_loc  # this rank's share
-        self.launches_per_frame = nb * (self.p1.net.launches + self.p2.net.launches + 2) + (2 if world == 1 else 4)
+        self.launches_per_frame = nb * (self.p1.net.launches + self.p2.net.launches + 2) + (2 if world == 1 else (nb + 1 if self.peer else 4))
         self.events = None
 
     def _permute3(self, src, dst, dims, perm, thr):
@@ -183,28 +189,37 @@ class MultiPass4x:
     def upload(self, x):
         return _dev_f32(x, self.device)
 
-    def __call__(self, x, record=False):
+    def __call__(self, x, record=False, output_free=None):
         """x: [L,L,L,4] float32 (numpy or device tensor, replicated on every rank).
-        Returns the device tensor [S/G,S,S] (z,y,x): this rank's z-slab of the output."""
+        Returns the device tensor [S/G,S,S] (z,y,x): this rank's z-slab of the output (`vol_c`, overwritten by the next
+        call). output_free: optional CUDA event recorded by whoever still reads the previous call's result (e.g. a D2H
+        copy on another stream); nothing stores into it before that event (HostFrameLoop)."""
         S, B = self.S, self.batch
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        st = cur.cuda_stream
         vol = _dev_f32(x, self.device)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
         if ev:
             ev[0].record()
-        # ---- pass 1: xy slices along (interpolated) z; rows land in vol_a[z - s0] = [Zu_loc, Yu, Xu]
+        # ---- pass 1: xy slices along (interpolated) z; rows land in vol_a[z - s0] = [Zu_loc, Yu, Xu]. The .uni
+        #      hand-over between the two processes of the reference = threshold (:1155-1157) + axis change to slices
+        #      along x, [Zu,Yu,Xu] -> [Xu_loc, Zu, Yu]: with peers every finished batch is pushed to its owners at once
         for s in range(self.s0, self.s1, B):
             capi.slice_assemble(self.h, self.asm1, vol, None, s, B, self.in1, st)
             self.p1.net.run({"x": self.in1}, out=self.vol_a[s - self.s0], stream=st)
+            if self.peer:
+                self.peer.push_part(capi, self.h, self.vol_a[s - self.s0], S, s, B, 2, (2, 0, 1), self.threshold)
         if ev:
             ev[1].record()
-        # ---- the .uni hand-over between the two processes: threshold (:1155-1157) + axis change to
-        #      slices along x: [Zu,Yu,Xu] -> [Xu_loc, Zu, Yu]
-        if self.peer:  # one kernel: transpose + stores into the owning rank's slab over NVLink (parallel.PeerSlab)
-            self.peer.exchange(capi, self.h, self.vol_a, S, 2, (2, 0, 1), self.threshold)
-        else:
+        if output_free is not None:
+            cur.wait_event(output_free)
+        if self.peer:
+            self.peer.landed(channel=0)  # the ONE barrier of this pass boundary: all ranks' stores are visible
+        elif self.world > 1:
             par.reslab(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
                        (2, 0, 1), self.threshold)
+        else:
+            self._permute3(self.vol_a, self.vol_b, (S, S, S), (2, 0, 1), self.threshold)
         if ev:
             ev[2].record()
         for s in range(self.s0, self.s1, B):
@@ -212,16 +227,19 @@ class MultiPass4x:
             self.p2.net.run({"x": self.in2}, out=self.vol_a[s - self.s0], stream=st)
         if ev:
             ev[3].record()
-        # rows [Xu_loc, Zu, Yu] -> .transpose(1,2,0) -> [Zu_loc, Yu, Xu] (:1142), threshold (:1155-1157)
+        # rows [Xu_loc, Zu, Yu] -> .transpose(1,2,0) -> [Zu_loc, Yu, Xu] (:1142), threshold (:1155-1157); the target is
+        # vol_c, which no rank reads during pass 2, so no barrier is needed BEFORE the stores
         if self.peer:
-            self.peer.exchange(capi, self.h, self.vol_a, S, 1, (1, 2, 0), self.threshold)
-        else:
-            par.reslab_mid(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_b,
+            self.peer_c.exchange(capi, self.h, self.vol_a, S, 1, (1, 2, 0), self.threshold, wait_readers=False)
+        elif self.world > 1:
+            par.reslab_mid(self.vol_a, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, self.vol_c,
                            (1, 2, 0), self.threshold)
+        else:
+            self._permute3(self.vol_a, self.vol_c, (S, S, S), (1, 2, 0), self.threshold)
         if ev:
             ev[4].record()
             self.events = ev
-        return self.vol_b
+        return self.vol_c
 
     def pass1_only(self, x):
         """First-pass volume [Zu_loc,Yu,Xu] after the threshold (what pass 2 reads from density_low_2x2_*.uni)."""
@@ -238,6 +256,67 @@ class MultiPass4x:
         e = self.events
         return dict(pass1=e[0].elapsed_time(e[1]), exchange1=e[1].elapsed_time(e[2]), pass2=e[2].elapsed_time(e[3]),
                     exchange2=e[3].elapsed_time(e[4]))
+
+
+class HostFrameLoop:
+    """The frame loop of the reference scripts (GAN/multipassGAN-out.py:629-632, GAN/multipassGAN-4x.py:1634-1646) with
+    HOST buffers, the B200 way: the low-res fields of frame i+1 are uploaded and the finished volume of frame i-1 is
+    downloaded on two copy streams while the networks of frame i run (the reference does feed -> run -> fetch serially
+    for every slice batch). `mp` is a MultiPass4x / MultiPassOut; buffers are pre-allocated and pinned, `depth` frames
+    may be in flight.
+
+        loop = HostFrameLoop(mp)
+        for x in frames: k = loop.submit(x)          # x: pinned [L,L,L,4] float32 tensor (or numpy: staged through one)
+        vol = loop.result(k)                          # pinned [S/G,S,S] host tensor, valid until slot k is reused
+    """
+
+    def __init__(self, mp, depth=2):
+        self.mp, self.depth, self.device = mp, int(depth), mp.device
+        L, S = mp.L, mp.S
+        self.up, self.down = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        self.x_dev = [torch.empty((L, L, L, 4), dtype=torch.float32, device=self.device) for _ in range(self.depth)]
+        self.x_pin = [torch.empty((L, L, L, 4), dtype=torch.float32).pin_memory() for _ in range(self.depth)]
+        self.out_pin = [torch.empty((mp.S_loc, S, S), dtype=torch.float32).pin_memory() for _ in range(self.depth)]
+        self.ev_up = [torch.cuda.Event() for _ in range(self.depth)]       # upload of slot k finished
+        self.ev_used = [torch.cuda.Event() for _ in range(self.depth)]     # networks finished reading x_dev[k]
+        self.ev_down = [torch.cuda.Event() for _ in range(self.depth)]     # download into out_pin[k] finished
+        self.count = 0
+        self.h2d_bytes = L * L * L * 4 * 4
+        self.d2h_bytes = mp.S_loc * S * S * 4
+
+    def submit(self, x):
+        k = self.count % self.depth
+        comp = torch.cuda.current_stream(self.device)
+        if not (isinstance(x, torch.Tensor) and x.is_pinned()):
+            if self.count >= self.depth:
+                self.ev_up[k].synchronize()  # the staging buffer is free once its previous upload has finished
+            self.x_pin[k].copy_(torch.as_tensor(x, dtype=torch.float32))
+            x = self.x_pin[k]
+        if self.count >= self.depth:
+            self.up.wait_event(self.ev_used[k])
+        with torch.cuda.stream(self.up):
+            self.x_dev[k].copy_(x, non_blocking=True)
+            self.ev_up[k].record(self.up)
+        comp.wait_event(self.ev_up[k])
+        prev = self.ev_down[(self.count - 1) % self.depth] if self.count > 0 else None
+        res = self.mp(self.x_dev[k], output_free=prev)
+        self.ev_used[k].record(comp)
+        self.down.wait_event(self.ev_used[k])
+        with torch.cuda.stream(self.down):
+            self.out_pin[k].copy_(res, non_blocking=True)
+            self.ev_down[k].record(self.down)
+        self.count += 1
+        return k
+
+    def result(self, k):
+        self.ev_down[k].synchronize()
+        return self.out_pin[k]
+
+    def drain(self):
+        """Make the current stream wait for every pending download (so an event recorded next covers the whole loop)."""
+        comp = torch.cuda.current_stream(self.device)
+        for e in self.ev_down[:min(self.count, self.depth)]:
+            comp.wait_event(e)
 
 
 def make_weights_4x(L, seed, upRes=4, batch_norm=True, randomize_bn=False):
@@ -361,7 +440,11 @@ class MultiPassOut:
             self.flops += pn.net.flops / B * self.S_loc  # this rank's share
         self.vol_rows = torch.empty((self.S_loc, S, S), **f32)
         self.peer = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group)
+        self.peer_c = par.make_peer_slab((self.S_loc, S, S), self.device, S, self.world, group) if self.peer else None
+        if self.peer is not None and self.peer_c is None:
+            self.peer = None
         self.vol_dim = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
+        self.vol_out = self.peer_c.tensor if self.peer else (torch.empty((self.S_loc, S, S), **f32) if self.world > 1 else None)
         if self.world > 1 and self.peer is None:
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
@@ -371,36 +454,48 @@ class MultiPassOut:
     def _permute3(self, src, dst, dims, perm, thr):
         capi.transpose3d(self.h, src, dst, dims, perm, thr, torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _call_sharded(self, x):
+    def _call_sharded(self, x, output_free=None):
         """Generators 1+2 on this rank's slices (App. C): rows [Zu_loc,Yu,Xu] -> all-to-all -> dim_output slab
         [Xu_loc,Yu,Zu] (= the `y` feeds of pass 2, :459) -> rows [Xu_loc,Yu,Zu] -> all-to-all -> [Zu_loc,Yu,Xu]
         (the composition of :521 and :587-590 is .transpose(2,1,0) of the pass-2 rows), threshold fused (:612-615)."""
         S = self.S
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        st = cur.cuda_stream
         vol = _dev_f32(x, self.device)
-        rows, dim = self.vol_rows, self.vol_dim
+        rows, dim, out = self.vol_rows, self.vol_dim, self.vol_out
         p = self.passes[1]
+        # with peers every finished batch is pushed to its owners at once (4-aligned batches: 128-bit stores along z)
+        stream_parts = self.peer is not None and p["batch"] % 4 == 0
         for s in range(self.s0, self.s1, p["batch"]):
             capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
             p["net"].net.run({"x": p["inbuf"]}, out=rows[s - self.s0], stream=st)
-        if self.peer:
-            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), 0.0)
+            if stream_parts:
+                self.peer.push_part(capi, self.h, rows[s - self.s0], S, s, p["batch"], 2, (2, 1, 0), 0.0)
+        if output_free is not None:
+            cur.wait_event(output_free)
+        if stream_parts:
+            self.peer.landed(channel=0)
+        elif self.peer:
+            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), 0.0, wait_readers=False)
         else:
             par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), 0.0)
         p = self.passes[2]
         for s in range(self.s0, self.s1, p["batch"]):
             capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
             p["net"].net.run({"x": p["inbuf"], "y": dim[s - self.s0]}, out=rows[s - self.s0], stream=st)
-        if self.peer:
-            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), self.threshold)
+        if self.peer:  # the target is a second slab nobody reads during pass 2: no barrier before the stores
+            self.peer_c.exchange(capi, self.h, rows, S, 2, (2, 1, 0), self.threshold, wait_readers=False)
         else:
-            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), self.threshold)
-        return dim
+            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, out, (2, 1, 0), self.threshold)
+        return out
 
-    def __call__(self, x):
-        """x: [L,L,L,4] float32, velocities already scaled by velScale (GAN/multipassGAN-out.py:138)."""
+    def __call__(self, x, output_free=None):
+        """x: [L,L,L,4] float32, velocities already scaled by velScale (GAN/multipassGAN-out.py:138).
+        output_free: see MultiPass4x.__call__ (sharded runs; the single-GPU path ping-pongs its two volumes)."""
         if self.world > 1:
-            return self._call_sharded(x)
+            return self._call_sharded(x, output_free)
+        if output_free is not None:
+            torch.cuda.current_stream(self.device).wait_event(output_free)
         S = self.S
         st = torch.cuda.current_stream(self.device).cuda_stream
         vol = _dev_f32(x, self.device)

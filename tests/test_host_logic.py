@@ -34,8 +34,9 @@ def test_gen_resnet_graph_matches_reference_structure():
     w = W.init_graph_variables(g, 1)
     net = engine.CompiledNet(out, w, 8, dry=True)
     lab = _labels(net)
-    assert len(lab) == 9 and lab[0].startswith("pack 128x128x4")
-    assert "g_cB1+g_s1 k5/1 128/32->128" in lab[4] and lab[4].startswith("conv[tc]")
+    # ru1 (pack + conv A + conv B/shortcut) is ONE fused thin-resblock launch reading the fp32 rows through the x4 view
+    assert len(lab) == 7 and lab[0].startswith("resblock[hm] g_cA0>g_cB0+g_s0 k5/5/1 4->8->32 128x128 relu in_up4")
+    assert "g_cB1+g_s1 k5/1 128/32->128" in lab[2] and lab[2].startswith("conv[tc]")
     assert abs(net.flops / (8 * 128 * 128) - 1267412) < 1e-6  # FLOP per output voxel, SURVEY App. A.1
 
 

@@ -204,3 +204,66 @@ def test_reslab_p2p_kernel_matches_numpy(world, split, perm):
         want = np.ascontiguousarray(blk.transpose(perm))
         got = outs[r].cpu().numpy().reshape(want.shape)
         assert np.array_equal(got, want), (world, split, perm, r)
+
+
+@pytest.mark.parametrize("world,split,perm,batch", [(2, 2, (2, 0, 1), 8), (4, 2, (2, 0, 1), 3), (4, 2, (2, 1, 0), 8),
+                                                     (2, 1, (1, 2, 0), 16)])
+def test_reslab_p2p_part_streams_batches(world, split, perm, batch):
+    """mpg_reslab_p2p_part: the axis change issued per finished slice batch (rows [a0, a0+count) of the old slice axis)
+    gives exactly the whole-slab result; ranks emulated on one GPU as in the test above."""
+    from mpgan_b200 import capi
+    h = capi.default_handle(0)
+    S = 96
+    per = S // world
+    rng = np.random.default_rng(12)
+    full = (rng.random((S, S, S), dtype=np.float32) - 0.2).astype(np.float32)
+    thr = 0.05
+    want_full = np.where(full < thr, 0.0, full).astype(np.float32)
+    outs = [torch.full((per * S * S,), float("nan"), device="cuda") for _ in range(world)]
+    ptrs = [o.data_ptr() for o in outs]
+    for g in range(world):
+        slab = torch.from_numpy(np.ascontiguousarray(full[g * per:(g + 1) * per])).cuda()
+        for a in range(0, per, batch):
+            cnt = min(batch, per - a)
+            capi.reslab_p2p_part(h, slab[a], ptrs, S, g * per + a, cnt, split, perm, thr, 0)
+    torch.cuda.synchronize()
+    for r in range(world):
+        blk = want_full[:, :, r * per:(r + 1) * per] if split == 2 else want_full[:, r * per:(r + 1) * per, :]
+        want = np.ascontiguousarray(blk.transpose(perm))
+        got = outs[r].cpu().numpy().reshape(want.shape)
+        assert np.array_equal(got, want), (world, split, perm, r)
+
+
+def test_reslab_p2p_part_rejects_misaligned_rows():
+    """final_perm[2] == 0 stores 4 consecutive rows of the part as one 128-bit word: a0 and count must be 4-aligned."""
+    from mpgan_b200 import capi
+    h = capi.default_handle(0)
+    S, world = 32, 2
+    outs = [torch.zeros((S // world) * S * S, device="cuda") for _ in range(world)]
+    part = torch.zeros((3, S, S), device="cuda")
+    with pytest.raises(capi.MpgError):
+        capi.reslab_p2p_part(h, part, [o.data_ptr() for o in outs], S, 0, 3, 2, (2, 1, 0), 0.0, 0)
+
+
+def test_host_frame_loop_matches_direct_calls():
+    """pipeline.HostFrameLoop (overlapped H2D / D2H on copy streams, two frames in flight) returns, for every frame,
+    exactly what a plain call of the pipeline returns."""
+    from mpgan_b200 import pipeline as P, synth
+    L = 8
+    w1, w2 = P.make_weights_4x(L, 3)
+    mp = P.MultiPass4x(L, w1, w2, precision="fp16", batch=8)
+    frames = [synth.synthetic_volume(L, seed=s) for s in (1, 2, 3, 4, 5)]
+    want = [mp(f).cpu().numpy().copy() for f in frames]
+    loop = P.HostFrameLoop(mp, depth=2)
+    pins = [torch.from_numpy(f).pin_memory() for f in frames]
+    got = []
+    slots = []
+    for i, xp in enumerate(pins):
+        slots.append(loop.submit(xp))
+        if i >= 1:  # consume frame i-1 while frame i is in flight
+            got.append(loop.result(slots[i - 1]).numpy().copy())
+    got.append(loop.result(slots[-1]).numpy().copy())
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    got2 = loop.result(loop.submit(frames[0])).numpy()  # numpy input goes through the pinned staging buffer
+    assert np.array_equal(got2, want[0])
