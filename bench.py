@@ -244,6 +244,83 @@ def run_reference(args):
     return 0
 
 
+# ============================================================================ secondary workloads (BASELINE configs 3-5)
+def secondary_8x(P, synth, par, L, rank, local, world, precision, steps, peaks, barrier, max_over_ranks):
+    """BASELINE.json configs[2] / [4]: multipassGAN-out 8x two-pass (nets 1+2 as shipped, GAN/example_run_output.py:18-48)
+    L^3 -> (8L)^3, slice-sharded over the ranks. Device-timed like the headline; reports its own algorithmic-TFLOP fraction."""
+    import torch
+    u = 8
+    S = L * u
+    mp = P.MultiPassOut(L, P.make_weights_out(L, 1, upRes=u, nets=(1, 2)), upRes=u, precision=precision, device=local,
+                        rank=rank, world=world, group=None)
+    dev = torch.device("cuda", local)
+    x_dev = torch.from_numpy(synth.synthetic_volume(L, seed=1)).to(dev)
+    for _ in range(2 if L >= 256 else 3):
+        res = mp(x_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = mp(x_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    chk = res.view(torch.int32).to(torch.int64).sum().reshape(1)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    flop = S ** 3 * 2067984.0  # SURVEY 8d: net1 521 216 + net2 1 546 768 FLOP per output voxel
+    out = dict(workload="multipassGAN-out 8x two-pass %d^3->%d^3 (BASELINE.json configs[%d])" % (L, S, 2 if L == 64 else 4),
+               ms_per_step=ms, value=S ** 3 / (ms * 1e-3), unit="voxel/s", steps=steps, n_gpus=world,
+               slice_batch=[p_["batch"] for _, p_ in sorted(mp.passes.items())],
+               algorithmic_tflops=flop / (ms * 1e-3) / 1e12,
+               frac_of_bf16_peak=dict(burst=flop / (ms * 1e-3) / 1e12 / peaks["tflops"] / world,
+                                      sustained=flop / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"] / world),
+               checksum_bits=int(chk.item()), gpu_launches=int(mp.launches_per_frame * steps))
+    for p_ in mp.passes.values():
+        p_["net"].net.close()
+    del mp, res, x_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def secondary_train(par, rank, local, world, steps, peaks, barrier, max_over_ranks):
+    """BASELINE.json configs[3]: multipassGAN-4x training loop body (1 D step + 1 G step, GAN/multipassGAN-4x.py:1316-1397)
+    on 16x16 -> 64x64 tile batches of 16 per rank, data parallel (weak scaling); H2D of the batch + loss read-back inside."""
+    import numpy as np
+    import torch
+    from mpgan_b200 import training as T
+    L, u, B = 16, 4, 16
+    S = L * u
+    tr = T.Trainer4x(L, u, B, seed=1, device=local, precision="fp16", graphs=True)
+    rng = np.random.default_rng(100 + rank)
+    xs = torch.from_numpy(rng.random((B, L * L * 4), dtype=np.float32)).pin_memory()
+    ys = torch.from_numpy(rng.random((B, S * S), dtype=np.float32)).pin_memory()
+
+    def body():
+        xd, yd = xs.cuda(non_blocking=True), ys.cuda(non_blocking=True)
+        return tr.iteration([(xd, yd)], [(xd, yd)])
+
+    for _ in range(4):
+        body()
+    barrier()
+    l0 = tr.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses = body()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    g_fwd, d_fwd = 2 * 2.60e9, 2 * 0.0514e9  # SURVEY 8d, per sample
+    flop = B * ((g_fwd + 2 * d_fwd * 3) + (g_fwd * 3 + 2 * d_fwd + 2 * d_fwd))
+    return dict(workload="multipassGAN-4x training loop body, 16 tiles 16x16->64x64 per rank (BASELINE.json configs[3])",
+                ms_per_step=ms, value=world * 1e3 / ms, unit="loop bodies/s", tiles_per_s=world * B * 1e3 / ms, steps=steps,
+                n_gpus=world, scaling="weak", algorithmic_tflops=world * flop / (ms * 1e-3) / 1e12,
+                frac_of_bf16_peak=dict(burst=flop / (ms * 1e-3) / 1e12 / peaks["tflops"]),
+                gpu_launches=int(tr.launches - l0), gen_loss_complete=float(losses.get("gen_loss_complete", float("nan"))))
+
+
 # ============================================================================ our arm
 def run_ours(args):
     import numpy as np
@@ -359,16 +436,8 @@ def run_ours(args):
                     sumsq=float(fsum[1].item()), scope="whole volume, all-reduced over ranks")
     del res_dev
 
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return 0
     peaks = load_peaks()
-    achieved = dom_flops / (kern_avg_ms * 1e-3) / 1e12
-    # denominator: the driver-measured cuBLAS bf16 BURST figure - the kernel sustains more than the 4-s
-    # "sustained" cuBLAS number inside the step, so the stricter (larger) peak is the honest one
-    peak = peaks["tflops"]
+    # ---------------- CPU leg + the parity gate at the benchmarked size (rank 0 of a single-GPU run; uses `mp`)
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline and args.workload == "4x":
@@ -379,6 +448,38 @@ def run_ours(args):
                                                                                 S // args.cpu_slices))
         if getattr(mp, "p2", None) is not None and hasattr(mp.p1, "net") and not args.no_parity:
             parity = parity_at_bench_size(mp, L, u, 1, args.cpu_slices, args.parity_slices, f32_outs, args.precision, dev)
+    # ---------------- secondary workloads: BASELINE.json configs[2] (8x 64^3->512^3), configs[3] (training loop body),
+    #                  configs[4] (8x 256^3->2048^3, 8 GPUs only); timed AFTER the headline, same process group
+    slice_batch = getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())]
+    launches_per_frame, has_peer = mp.launches_per_frame, bool(getattr(mp, "peer", None))
+    secondary = {}
+    if args.workload == "4x" and not args.no_secondary:
+        for pn in nets:
+            pn.close()
+        del mp, loop, x_dev
+        torch.cuda.empty_cache()
+        jobs = [("8x_64_512", lambda: secondary_8x(P, synth, par, 64, rank, local, world, args.precision, 3, peaks, barrier,
+                                                   max_over_ranks)),
+                ("train_4x", lambda: secondary_train(par, rank, local, world, 20, peaks, barrier, max_over_ranks))]
+        if world == 8:
+            jobs.append(("8x_256_2048", lambda: secondary_8x(P, synth, par, 256, rank, local, world, args.precision, 2, peaks,
+                                                            barrier, max_over_ranks)))
+        for name, job in jobs:
+            try:
+                secondary[name] = job()
+            except Exception as e:  # noqa: BLE001 - a secondary workload must never cost the headline line
+                secondary[name] = dict(error="%s: %s" % (type(e).__name__, e))
+                if world > 1:
+                    break  # ranks may have diverged inside a collective: stop here
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    achieved = dom_flops / (kern_avg_ms * 1e-3) / 1e12
+    # denominator: the driver-measured cuBLAS bf16 BURST figure - the kernel sustains more than the 4-s
+    # "sustained" cuBLAS number inside the step, so the stricter (larger) peak is the honest one
+    peak = peaks["tflops"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01b_dominant_kernels.json")
     if os.path.exists(tpath):  # ncu --set full capture of the current build (dram__bytes_read.sum + dram__bytes_write.sum)
@@ -410,10 +511,10 @@ def run_ours(args):
         metric="output voxels/sec", value=value, unit="voxel/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype={"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
-        config=job_config(workload, L, u, getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())],
-                          args.precision, world, flop_per_voxel),
-        exchange=(("one transpose kernel storing into peer slabs over NVLink (symmetric memory)" if getattr(mp, "peer", None)
-                   else "pack + NCCL all-to-all + unpack") if world > 1 else "transpose3d on the device"),
+        config=job_config(workload, L, u, slice_batch, args.precision, world, flop_per_voxel),
+        exchange=(("transpose kernels storing into the owners' slabs over NVLink (symmetric memory): pass-1 rows pushed per finished "
+                   "slice batch, one barrier per pass boundary" if has_peer else "pack + NCCL all-to-all + unpack")
+                  if world > 1 else "transpose3d on the device"),
         algorithmic_tflops=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12,
         frac_of_bf16_peak=dict(burst=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12 / peaks["tflops"] / world,
                                sustained=S ** 3 * flop_per_voxel / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"] / world,
@@ -424,7 +525,7 @@ def run_ours(args):
                  h2d_bytes_per_step=int(loop.h2d_bytes), d2h_bytes_per_step=int(loop.d2h_bytes),
                  how="pipeline.HostFrameLoop: pinned H2D of the frame + D2H of the volume every step, copies of neighbouring frames overlap the networks (2 frames in flight)",
                  checksum=checksum),
-        gpu_launches=int(mp.launches_per_frame * args.steps),
+        gpu_launches=int(launches_per_frame * args.steps),
         checksum=checksum,
         roofline=dict(bound="tensor", kernel="conv_igemm_kernel<64,pair> " + dom_label, achieved=achieved, peak=peak,
                       unit="TFLOP/s", frac=achieved / peak, frac_of_sustained=achieved / peaks["tflops_sustained"],
@@ -433,6 +534,8 @@ def run_ours(args):
                       share_of_step=kern_share, traffic=traffic),
         clocks=clocks,
     )
+    if secondary:
+        line["secondary"] = secondary
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if parity is not None:
@@ -462,6 +565,7 @@ def main():
     ap.add_argument("--parity-slices", type=int, default=2, help="rows per pass checked against the fp64 oracle (the gate)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (BASELINE configs 3-5)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
