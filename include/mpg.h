@@ -137,6 +137,10 @@ int mpg_resblock_plan_create(mpg_handle h, const mpg_resblock_desc* d, const flo
                              const float* w_s, const float* scale_a, const float* scale_b, const float* scale_s,
                              const float* shift_a, const float* shift_bs, mpg_resblock_plan* out);
 int mpg_resblock_plan_run(mpg_resblock_plan p, const void* x, void* y, void* stream);
+/* same, and *sat_counter_dev (may be NULL) += intermediate values that left the 16-bit range (the intermediate never
+ * reaches global memory, so mpg_count_saturated cannot see it) */
+int mpg_resblock_plan_run_checked(mpg_resblock_plan p, const void* x, void* y, unsigned long long* sat_counter_dev,
+                                  void* stream);
 int mpg_resblock_plan_destroy(mpg_resblock_plan p);
 double mpg_resblock_plan_flops(mpg_resblock_plan p);
 
@@ -171,6 +175,14 @@ int mpg_bicubic_plan_destroy(void* plan);
 int mpg_resize_images(mpg_handle h, const void* src, int src_dtype, int src_cstride, int c, int n, int src_h, int src_w,
                       void* out, int out_dtype, int out_cstride, int out_h, int out_w, int mode, void* bicubic_plan,
                       void* stream);
+
+/* Range check (validation mode of the engine): *counter_dev += number of elements of `t` that sit on the 16-bit type's
+ * largest finite value or beyond (+-65504 for MPG_F16: every 16-bit store of the kernels is a SATURATING conversion, so
+ * an out-of-range activation lands exactly there), are infinite or NaN (MPG_F32: non-finite only). The reference
+ * computes in fp32 (tools_wscale/GAN.py:19-35) and cannot overflow this way: a non-zero count means the 16-bit path
+ * has left the reference's result and the caller must fall back to precision fp32. */
+int mpg_count_saturated(mpg_handle h, const void* t, long long count, int dtype, unsigned long long* counter_dev,
+                        void* stream);
 
 /* out[n,y,x] = dens[n,y,x] + R(src[..., src_c])  with R = identity (mode 0, GAN/multipassGAN-out.py:332)
  * or the TF1 bicubic resize (mode 2, GAN/multipassGAN-out.py:330). dens/out fp32 [n,out_h,out_w]. */

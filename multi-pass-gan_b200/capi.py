@@ -22,6 +22,17 @@ class MpgError(RuntimeError):
     """Raised for any non-zero status of the C ABI (mirrors TF's InvalidArgumentError role)."""
 
 
+class MpgRangeError(MpgError):
+    """A 16-bit activation saturated (range_check mode): the fp16 path would silently clip where the fp32 reference
+    does not. `.counts` = {layer label: saturated elements}."""
+
+    def __init__(self, counts):
+        self.counts = dict(counts)
+        worst = sorted(self.counts.items(), key=lambda kv: -kv[1])[:4]
+        super().__init__("16-bit activations saturated (|x| >= max finite) in %d layer(s): %s -- rerun with precision fp32"
+                         % (len(self.counts), "; ".join("%s: %d" % kv for kv in worst)))
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [
         ("n", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int),
@@ -92,6 +103,7 @@ def lib():
     L.mpg_conv_plan_flops.restype = dp
     L.mpg_resblock_plan_create.argtypes = [vp, ctypes.POINTER(ResblockDesc), fp, fp, fp, fp, fp, fp, fp, fp, ctypes.POINTER(vp)]
     L.mpg_resblock_plan_run.argtypes = [vp, vp, vp, vp]
+    L.mpg_resblock_plan_run_checked.argtypes = [vp, vp, vp, vp, vp]
     L.mpg_resblock_plan_destroy.argtypes = [vp]
     L.mpg_resblock_plan_flops.argtypes = [vp]
     L.mpg_resblock_plan_flops.restype = dp
@@ -99,6 +111,7 @@ def lib():
     L.mpg_bicubic_plan_create.argtypes = [vp, ip, ip, ip, ip, ctypes.POINTER(vp)]
     L.mpg_bicubic_plan_destroy.argtypes = [vp]
     L.mpg_dens_residual.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
+    L.mpg_count_saturated.argtypes = [vp, vp, ctypes.c_longlong, ip, vp, vp]
     L.mpg_resize_images.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
     L.mpg_transpose3d.argtypes = [vp, vp, vp, ip, ip, ip, ctypes.POINTER(ctypes.c_int), ctypes.c_float, vp]
@@ -276,8 +289,8 @@ class ResblockPlan:
                                              ctypes.byref(self._p)), "mpg_resblock_plan_create")
         self.flops = lib().mpg_resblock_plan_flops(self._p)
 
-    def run(self, x, y, stream=0):
-        check(lib().mpg_resblock_plan_run(self._p, _ptr(x), _ptr(y), stream), "mpg_resblock_plan_run")
+    def run(self, x, y, stream=0, sat_counter=None):
+        check(lib().mpg_resblock_plan_run_checked(self._p, _ptr(x), _ptr(y), _ptr(sat_counter), stream), "mpg_resblock_plan_run")
 
     def close(self):
         if self._p:
@@ -345,6 +358,11 @@ def resize_images(handle, src, src_dtype, src_cstride, c, n, src_h, src_w, out, 
                                   int(src_w), _ptr(out), int(out_dtype), int(out_cstride), int(out_h), int(out_w),
                                   int(mode), bicubic_plan.ptr if bicubic_plan is not None else None, stream),
           "mpg_resize_images")
+
+
+def count_saturated(handle, t, count, dtype, counter, stream=0):
+    """counter (device int64/uint64 scalar tensor or pointer) += saturated / non-finite elements of t."""
+    check(lib().mpg_count_saturated(handle.ptr, _ptr(t), int(count), int(dtype), _ptr(counter), stream), "mpg_count_saturated")
 
 
 def make_assemble_desc(dims, vol_c, axis_of, zoom, chan_src, chan_scale=None, add_adj=False, out_dtype=BF16,

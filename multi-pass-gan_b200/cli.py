@@ -102,6 +102,7 @@ def main(argv=None):
     weights_npz = g("weightsNpz", None)        # extension
     precision = g("precision", "fp16")         # extension: fp16 | bf16 | fp32
     io_threads = int(g("ioThreads", 4))        # extension: gzip writer threads of the frame pipeline (io_pipeline.py)
+    range_check = int(g("rangeCheck", 0)) != 0  # extension: validation mode, abort on saturated 16-bit activations
     uni_chunk_mb = int(g("uniChunkMB", 0))     # extension: >0 = multi-member gzip output deflated on ioThreads threads
     ph.check_unused()
     if tileSizeLow != simSizeLow:
@@ -147,7 +148,9 @@ def main(argv=None):
     sim_path = os.path.join(packedSimPath, "sim_%04d" % fromSim)
     mp = P.MultiPassOut(simSizeLow, weights, upRes=upRes, specs=specs, precision=precision, transposeAxis=transposeAxis,
                         threshold=P.THRESHOLD if genUni else 0.0, pixel_norm=pixel_norm, batch_norm=batch_norm,
-                        upsampleMode=upsampleMode, addBicubicUpsample=addBicubic, device=gpu)
+                        upsampleMode=upsampleMode, addBicubicUpsample=addBicubic, device=gpu, range_check=range_check)
+    if range_check:
+        print("rangeCheck 1: every 16-bit layer output is scanned for saturated values (validation mode, slower)")
     S = simSizeLow * upRes
     print("*****OUTPUT ONLY*****")
     from . import io_pipeline, uni

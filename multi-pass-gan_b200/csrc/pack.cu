@@ -208,6 +208,26 @@ __global__ void __launch_bounds__(256) resize_images_kernel(const ResizeParams p
   else reinterpret_cast<uint16_t*>(p.out)[e] = float_to_h16(v, p.out_dtype);
 }
 
+// Range check of a stored activation tensor (validation mode): every 16-bit store of the conv kernels is a saturating
+// conversion (cvt.rn.satfinite, common.h), so a value beyond the type's range lands exactly on +-max-finite. Counts the
+// elements that are +-max-finite, +-inf or NaN (fp32: non-finite only).
+__global__ void __launch_bounds__(256) count_saturated_kernel(const void* __restrict__ t, long long count, int dtype,
+                                                              unsigned long long* __restrict__ counter) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  unsigned int local = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    if (dtype == MPG_F32) {
+      const uint32_t u = __float_as_uint(static_cast<const float*>(t)[i]) & 0x7fffffffu;
+      local += u >= 0x7f800000u;
+    } else {
+      const uint32_t u = static_cast<const uint16_t*>(t)[i] & 0x7fffu;
+      local += u >= (dtype == MPG_F16 ? 0x7bffu : 0x7f7fu);  // max finite (65504 / 3.39e38) or above (inf, NaN)
+    }
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, static_cast<unsigned long long>(local));
+}
+
 // TF1 bicubic coefficient table (Keys, A = -0.75, 1024 entries), fp32 like resize_bicubic_op.cc
 void bicubic_axis(int in_size, int out_size, std::vector<int>& idx, std::vector<float>& wts) {
   static float tab[1025][2];
@@ -342,6 +362,20 @@ int mpg_resize_images(mpg_handle h, const void* src, int src_dtype, int src_cstr
   const long long total = static_cast<long long>(n) * out_h * out_w * out_cstride;
   DeviceGuard guard(h->device);
   resize_images_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_count_saturated(mpg_handle h, const void* t, long long count, int dtype, unsigned long long* counter_dev,
+                        void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && t && counter_dev && count >= 0 && is_dtype(dtype), "mpg_count_saturated: bad argument");
+  if (count == 0) return MPG_OK;
+  long long blocks = (count + 255) / 256;
+  const long long cap = static_cast<long long>(h->sm_count) * 16;
+  if (blocks > cap) blocks = cap;
+  DeviceGuard guard(h->device);
+  count_saturated_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, count, dtype, counter_dev);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

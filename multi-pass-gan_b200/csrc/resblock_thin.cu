@@ -60,6 +60,7 @@ struct RbParams {
   int in_up, in_cstride, out_cstride;
   int act;
   int tiles_x, tiles_y, num_tiles;
+  unsigned long long* sat;  // validation mode: counts intermediate values beyond the 16-bit range (null = off)
 };
 
 __host__ __device__ constexpr int tap_off(int tap, int pitch) {
@@ -234,6 +235,11 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
             const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
             const float v0 = in ? act_apply(acc[u][2 * hrow] + shA0, ca, cb) : 0.0f;
             const float v1 = in ? act_apply(acc[u][2 * hrow + 1] + shA1, ca, cb) : 0.0f;
+            if (p.sat != nullptr) {  // the intermediate never reaches global memory: count its saturating stores here
+              const float lim = BF16 ? 3.3895314e38f : 65504.0f;
+              const unsigned c = (fabsf(v0) >= lim || v0 != v0) + (fabsf(v1) >= lim || v1 != v1);
+              if (c) atomicAdd(p.sat, static_cast<unsigned long long>(c));
+            }
             *reinterpret_cast<uint32_t*>(s_mid + q * 16 + t * 4) = pack_h16x2(v0, v1, dt);
           }
         }
@@ -471,6 +477,11 @@ int mpg_resblock_plan_create(mpg_handle h, const mpg_resblock_desc* dsc, const f
 }
 
 int mpg_resblock_plan_run(mpg_resblock_plan p, const void* x, void* y, void* stream) {
+  return mpg_resblock_plan_run_checked(p, x, y, nullptr, stream);
+}
+
+int mpg_resblock_plan_run_checked(mpg_resblock_plan p, const void* x, void* y, unsigned long long* sat_counter_dev,
+                                  void* stream) {
   using namespace mpg;
   MPG_CHECK_ARG(p && x && y, "mpg_resblock_plan_run: null argument");
   MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "resblock: input not 16-byte aligned");
@@ -490,6 +501,7 @@ int mpg_resblock_plan_run(mpg_resblock_plan p, const void* x, void* y, void* str
   q.tiles_x = ceil_div(d.w, kTW);
   q.tiles_y = ceil_div(d.h, kTH);
   q.num_tiles = q.tiles_x * q.tiles_y * d.n;
+  q.sat = sat_counter_dev;
   DeviceGuard guard(p->h->device);
   rb_kernel(p->cpp, p->nt2, d.mma_dtype == MPG_BF16, d.in_dtype == MPG_F32, d.out_dtype == MPG_F32)
       <<<p->grid, kThreads, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(q);

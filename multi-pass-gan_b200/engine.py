@@ -74,8 +74,11 @@ class Group:
 
 
 class CompiledNet:
-    def __init__(self, output, weights, batch, precision="fp16", handle=None, device=0, verbose=False, dry=False):
-        """dry=True records the fused launch list without touching the GPU (host-logic tests)."""
+    def __init__(self, output, weights, batch, precision="fp16", handle=None, device=0, verbose=False, dry=False,
+                 range_check=False):
+        """dry=True records the fused launch list without touching the GPU (host-logic tests).
+        range_check=True (validation mode): every layer output is scanned for saturated 16-bit stores / non-finite values
+        after it is produced (mpg_count_saturated); `run` raises capi.MpgRangeError instead of returning clipped data."""
         assert precision in ("bf16", "fp16", "fp32")
         self.dry = dry
         self.h = None if dry else (handle or capi.default_handle(device))
@@ -95,7 +98,10 @@ class CompiledNet:
         self.verbose = verbose
         self.timed_step = None  # index into self.steps bracketed by CUDA events when set (bench roofline)
         self.timed_events = []
+        self.range_check = bool(range_check) and not dry
         self._lower(output)
+        self.sat_counts = (torch.zeros(len(self.steps) + 1, dtype=torch.int64, device=self.device)
+                           if self.range_check else None)
 
     # ------------------------------------------------------------------ helpers
     def _alloc(self, h, w, c, dtype, cstride=None, name=None):
@@ -125,6 +131,7 @@ class CompiledNet:
             capi.pack_channels(handle, [(self._p(s[0]),) + s[1:] for s in srcs], self._p(out), out.dtype,
                                out.cstride, out.n, out.h, out.w, stream)
 
+        self.step_bufs[len(self.steps)] = out
         self.steps.append(("pack %dx%dx%d" % (view.h, view.w, view.c), step))
         view._mat[dtype] = out
         return out
@@ -153,6 +160,7 @@ class CompiledNet:
             capi.resize_images(handle, self._p(src), src.dtype, src.cstride, view.c, out.n, sv.h, sv.w, self._p(out),
                                out.dtype, out.cstride, view.h, view.w, mode, plan, stream)
 
+        self.step_bufs[len(self.steps)] = out
         self.steps.append(("resize mode %d %dx%d->%dx%dx%d" % (mode, sv.h, sv.w, view.h, view.w, view.c), step))
         view._mat[dtype] = out
         return out
@@ -488,8 +496,11 @@ class CompiledNet:
             self.plans.append(plan)
             assert abs(plan.flops - flops) < 1e-6 * flops
 
+        idx = len(self.steps)
+
         def step(stream):
-            plan.run(self._p(src), self._p(out), stream)
+            plan.run(self._p(src), self._p(out), stream,
+                     sat_counter=self.sat_counts[idx:idx + 1] if self.sat_counts is not None else None)
 
         nm = lambda c: c.attrs["weight"]["var"].name.rsplit("/", 2)[-2]
         label = "resblock[hm] %s>%s+%s k5/5/1 %d->%d->%d %dx%d%s%s" % (
@@ -540,7 +551,14 @@ class CompiledNet:
         if out is not None:
             root.ptr = out.data_ptr() if hasattr(out, "data_ptr") else int(out)
         try:
-            if self.timed_step is None:
+            if self.range_check:
+                for i, (_, step) in enumerate(self.steps):
+                    step(st)
+                    ob_i = self.step_bufs.get(i)
+                    if ob_i is not None:
+                        capi.count_saturated(self.h, self._p(ob_i), ob_i.n * ob_i.h * ob_i.w * ob_i.cstride, ob_i.dtype,
+                                             self.sat_counts[i:i + 1], st)
+            elif self.timed_step is None:
                 for _, step in self.steps:
                     step(st)
             else:
@@ -558,9 +576,25 @@ class CompiledNet:
                         step(st)
         finally:
             root.ptr = saved
+        if self.range_check:
+            self.check_range()
         if out is None:
             return root.tensor.view(self.batch, -1)
         return out
+
+    def saturated(self, reset=True):
+        """{layer label: saturated / non-finite elements} accumulated since the last reset (synchronises)."""
+        if self.sat_counts is None:
+            return {}
+        host = self.sat_counts.cpu().tolist()
+        if reset:
+            self.sat_counts.zero_()
+        return {self.steps[i][0]: int(c) for i, c in enumerate(host[:len(self.steps)]) if c}
+
+    def check_range(self):
+        bad = self.saturated()
+        if bad:
+            raise capi.MpgRangeError(bad)
 
     def dominant_step(self):
         """Index, label and FLOPs of the conv step with the most algorithmic FLOPs."""

@@ -51,11 +51,11 @@ def _pick_batch(n, pref):
 class _PassNet:
     """One generator compiled for a fixed slice batch, fed by the slice assembler."""
 
-    def __init__(self, handle, build_fn, weights, batch, precision):
+    def __init__(self, handle, build_fn, weights, batch, precision, range_check=False):
         G.reset_default_graph()
         self.out_t = build_fn()
         self.graph = G.get_default_graph()
-        self.net = engine.CompiledNet(self.out_t, weights, batch, precision=precision, handle=handle)
+        self.net = engine.CompiledNet(self.out_t, weights, batch, precision=precision, handle=handle, range_check=range_check)
         self.batch = batch
 
 
@@ -112,10 +112,12 @@ class MultiPass4x:
     `__call__` returns this rank's [S/G, S, S] part of the output (rank-major == z order)."""
 
     def __init__(self, L, weights_pass1, weights_pass2, upRes=4, precision="fp16", batch=8, velScale=1.0,
-                 batch_norm=True, device=0, threshold=THRESHOLD, rank=0, world=1, group=None, tile=None):
+                 batch_norm=True, device=0, threshold=THRESHOLD, rank=0, world=1, group=None, tile=None, range_check=False):
         """tile: None = whole slices per launch (the reference's behaviour), or (core1, core2): pass 1 is applied to
         overlapping low-res tiles of core1 + 2*4 pixels, pass 2 to high-res tiles of core2 + 2*16 pixels
-        (_TiledPassNet; (L - 8) % core1 == 0, (S - 32) % core2 == 0, core2 % upRes == 0) -- same result, bounded memory."""
+        (_TiledPassNet; (L - 8) % core1 == 0, (S - 32) % core2 == 0, core2 % upRes == 0) -- same result, bounded memory.
+        range_check: validation mode -- every 16-bit layer output is scanned for saturated stores; a call raises
+        capi.MpgRangeError instead of returning clipped data (engine.CompiledNet)."""
         self.L, self.u, self.S = int(L), int(upRes), int(L) * int(upRes)
         self.h = capi.default_handle(device)
         self.device = torch.device("cuda", device)
@@ -130,9 +132,9 @@ class MultiPass4x:
         cfg1 = N.config_4x(L, upRes=u, upsampling_mode=2, batch_norm=batch_norm)
         cfg2 = N.config_4x(L, upRes=u, upsampling_mode=1, batch_norm=batch_norm)
         self.p1 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg1), weights_pass1,
-                           self.batch, precision)
+                           self.batch, precision, range_check)
         self.p2 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, S * S * 4], "x"), cfg2), weights_pass2,
-                           self.batch, precision) if tile is None else None
+                           self.batch, precision, range_check) if tile is None else None
         if tile is not None:
             core1, core2 = int(tile[0]), int(tile[1])
             halo_hi = 16  # receptive-field radius of gen_resnet: 8 convs of k=5 (App. A.6)
@@ -397,7 +399,7 @@ class MultiPassOut:
     """generate3DUniForNewNetwork (GAN/multipassGAN-out.py:390-618) for one frame, on the device."""
 
     def __init__(self, L, weights, upRes=8, specs=None, precision="fp16", transposeAxis=0, batches=None,
-                 device=0, threshold=THRESHOLD, rank=0, world=1, group=None, **cfg_kw):
+                 device=0, threshold=THRESHOLD, rank=0, world=1, group=None, range_check=False, **cfg_kw):
         """With world > 1 (generators 1+2, transposeAxis 0: the shipped 8x two-pass recipe) the volume is sharded by
         slice: z-slabs in pass 1, x-slabs in pass 2, one all-to-all per axis change; `__call__` then returns this
         rank's canonical z-slab [S/G, S, S]."""
@@ -431,7 +433,7 @@ class MultiPassOut:
             axis_of, chans = _PASS_GEOM[idx][self.ta]
             B = _pick_batch(self.S_loc, batches[idx - 1])
             pn = _PassNet(self.h, lambda idx=idx, spec=spec: build_out_graph(idx, spec, self.cfg), weights[idx], B,
-                          precision)
+                          precision, range_check)
             adj = bool(spec.add_adj_idcs) and idx == 1
             cin = 4 + (2 if adj else 0)
             desc = capi.make_assemble_desc((L, L, L), 4, axis_of, (u, 1, 1), chans, None, add_adj=adj,

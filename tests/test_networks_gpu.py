@@ -85,3 +85,43 @@ def test_growing_gen_plain_chain_net3():
     y = net.run({"x": torch.from_numpy(x).cuda(), "y": torch.from_numpy(yr).cuda()}).cpu().numpy()
     ref = oracle_growing_gen(w, idx, specs[3], L, upRes=u)(x, yr)
     _check("growing_gen net3 chain", y, ref, "fp32")
+
+
+def test_fp16_range_check_raises_instead_of_clipping():
+    """Every 16-bit store saturates silently (cvt.rn.satfinite). In validation mode (range_check=True) a generator whose
+    intermediate activations leave the fp16 range must RAISE, with the offending layers named; the same weights pass in
+    fp32, and sane weights pass the check in fp16."""
+    from mpgan_b200 import capi
+    L, B, u = 8, 2, 4
+    G.reset_default_graph()
+    cfg = N.config_4x(L, upRes=u, upsampling_mode=2)
+    out = N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg)
+    w = W.init_graph_variables(G.get_default_graph(), 3)
+    x = torch.from_numpy(np.random.default_rng(0).random((B, L * L * 4), dtype=np.float32)).cuda()
+    net = engine.CompiledNet(out, w, B, precision="fp16", range_check=True)
+    net.run({"x": x})  # random-init activations peak near 13: no saturation
+    assert net.saturated() == {}
+    net.close()
+    big = dict(w)
+    big["generator/g_cA1/weight"] = w["generator/g_cA1/weight"] * 3e4  # ru2 conv A now produces values beyond 65504
+    net = engine.CompiledNet(out, big, B, precision="fp16", range_check=True)
+    with pytest.raises(capi.MpgRangeError) as ei:
+        net.run({"x": x})
+    assert any("g_cA1" in k for k in ei.value.counts), ei.value.counts
+    net.close()
+    # without the check the same run returns (clipped) finite data: this is the silent behaviour the mode exists for
+    net = engine.CompiledNet(out, big, B, precision="fp16")
+    y = net.run({"x": x})
+    assert torch.isfinite(y).all()
+    net.close()
+    # the fused head keeps its intermediate in shared memory: its in-kernel counter must see a saturating conv A
+    big0 = dict(w)
+    big0["generator/g_cA0/weight"] = w["generator/g_cA0/weight"] * 1e5
+    net = engine.CompiledNet(out, big0, B, precision="fp16", range_check=True)
+    with pytest.raises(capi.MpgRangeError) as ei:
+        net.run({"x": x})
+    assert any("g_cA0" in k for k in ei.value.counts), ei.value.counts
+    net.close()
+    net32 = engine.CompiledNet(out, big, B, precision="fp32", range_check=True)
+    net32.run({"x": x})
+    net32.close()
