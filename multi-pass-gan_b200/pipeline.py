@@ -131,10 +131,14 @@ class MultiPass4x:
         self.batch = _pick_batch(self.S_loc, batch)
         cfg1 = N.config_4x(L, upRes=u, upsampling_mode=2, batch_norm=batch_norm)
         cfg2 = N.config_4x(L, upRes=u, upsampling_mode=1, batch_norm=batch_norm)
+        # either weight set may be None: the reference runs the two passes as two processes that hand the volume over as
+        # a .uni file (GAN/example_run_output.py:6,8); pass1_only / pass2_only are those two runs (cli_4x.py)
+        if tile is not None and (weights_pass1 is None or weights_pass2 is None):
+            raise ValueError("tiled apply needs both generators")
         self.p1 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, L * L * 4], "x"), cfg1), weights_pass1,
-                           self.batch, precision, range_check)
+                           self.batch, precision, range_check) if weights_pass1 is not None else None
         self.p2 = _PassNet(self.h, lambda: N.gen_resnet(G.placeholder([None, S * S * 4], "x"), cfg2), weights_pass2,
-                           self.batch, precision, range_check) if tile is None else None
+                           self.batch, precision, range_check) if (tile is None and weights_pass2 is not None) else None
         if tile is not None:
             core1, core2 = int(tile[0]), int(tile[1])
             halo_hi = 16  # receptive-field radius of gen_resnet: 8 convs of k=5 (App. A.6)
@@ -181,8 +185,9 @@ class MultiPass4x:
         else:
             self.scr_a = self.scr_b = None
         nb = self.S_loc // self.batch
-        self.flops = (self.p1.net.flops + self.p2.net.flops) / self.batch * self.S_loc  # this rank's share
-        self.launches_per_frame = nb * (self.p1.net.launches + self.p2.net.launches + 2) + (2 if world == 1 else (nb + 1 if self.peer else 4))
+        have = [p_ for p_ in (self.p1, self.p2) if p_ is not None]
+        self.flops = sum(p_.net.flops for p_ in have) / self.batch * self.S_loc  # this rank's share
+        self.launches_per_frame = nb * (sum(p_.net.launches for p_ in have) + 2) + (2 if world == 1 else (nb + 1 if self.peer else 4))
         self.events = None
 
     def _permute3(self, src, dst, dims, perm, thr):
@@ -253,6 +258,23 @@ class MultiPass4x:
             self.p1.net.run({"x": self.in1}, out=self.vol_a[s - self.s0], stream=st)
         capi.threshold(self.h, self.vol_a, self.S_loc * S * S, self.threshold, st)
         return self.vol_a
+
+    def pass2_only(self, x, dens):
+        """Second run of the reference recipe (`upsamplingMode 1 upsampledData 1`, GAN/multipassGAN-4x.py:1094-1146):
+        x [L,L,L,4] low-res fields (only the velocities are used), dens [Zu,Yu,Xu] the first-pass volume as read back from
+        density_low_2x2_%04d.uni. Returns the device volume [Zu,Yu,Xu] after the threshold. Single GPU."""
+        if self.world != 1:
+            raise NotImplementedError("pass2_only is the single-process hand-over of the reference; sharded runs use __call__")
+        S, B = self.S, self.batch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        vol = _dev_f32(x, self.device)
+        d = _dev_f32(dens, self.device).reshape(S, S, S)
+        self._permute3(d, self.vol_b, (S, S, S), (2, 0, 1), 0.0)  # [Zu,Yu,Xu] -> slices along x of (z,y) planes
+        for s in range(0, S, B):
+            capi.slice_assemble(self.h, self.asm2, vol, self.vol_b, s, B, self.in2, st)
+            self.p2.net.run({"x": self.in2}, out=self.vol_a[s], stream=st)
+        self._permute3(self.vol_a, self.vol_c, (S, S, S), (1, 2, 0), self.threshold)
+        return self.vol_c
 
     def pass_times_ms(self):
         e = self.events

@@ -77,3 +77,56 @@ def test_cli_end_to_end_writes_source_uni(tmp_path):
         head, vol = uni.read_uni(str(sim / ("source_%04d.uni" % f)))
         assert (head["dimX"], head["dimY"], head["dimZ"]) == (L * u,) * 3
         np.testing.assert_array_equal(vol[..., 0], mp(x).cpu().numpy())
+
+
+def test_cli_4x_flag_handling():
+    """GAN/multipassGAN-4x.py command line: every reference flag is accepted, unknown flags abort, and runs outside the
+    two shipped output-mode calls (GAN/example_run_output.py:6,8) are refused with a message instead of guessed at."""
+    from mpgan_b200 import cli_4x
+    base = ["multipassGAN-4x.py", "useVelocities", "1", "simSize", "8", "tileSize", "8"]
+    with pytest.raises(SystemExit):  # unknown flag
+        cli_4x.main(base + ["out", "1", "noSuchFlag", "3"])
+    with pytest.raises(SystemExit) as e:  # training mode
+        cli_4x.main(base + ["out", "0"])
+    assert "Trainer4x" in str(e.value)
+    with pytest.raises(SystemExit) as e:  # third network
+        cli_4x.main(base + ["out", "1", "upsamplingMode", "3", "upsampledData", "1", "randomInit", "1"])
+    assert "upsamplingMode" in str(e.value)
+    with pytest.raises(SystemExit):  # tiles smaller than the frame
+        cli_4x.main(["multipassGAN-4x.py", "useVelocities", "1", "simSize", "8", "tileSize", "4", "out", "1", "randomInit", "1"])
+
+
+@pytest.mark.gpu
+def test_cli_4x_two_runs_hand_over_uni_like_the_reference_recipe(tmp_path):
+    """The benchmarked recipe through its own entry point: two `multipassGAN-4x.py out 1` runs (upsamplingMode 2, then
+    upsamplingMode 1 upsampledData 1) with the .uni hand-over in between (GAN/example_run_output.py:6,8) must give exactly
+    the volume of the device-resident two-pass pipeline with the same weights."""
+    from mpgan_b200 import cli_4x, pipeline as P, synth, graph as G, networks as N, weights as W
+    L, u = 8, 4
+    S = L * u
+    sim = tmp_path / "sim_1005"
+    sim.mkdir()
+    x = synth.synthetic_volume(L, seed=5)
+    uni.write_uni(str(sim / "density_low_0110.uni"), uni.make_header((L, L, L), 1), x[..., 0:1])
+    uni.write_uni(str(sim / "velocity_low_0110.uni"), uni.make_header((L, L, L), 2), x[..., 1:4])
+    # the shipped command lines (training flags included: they are accepted and ignored in output mode)
+    common = ("randSeed 174213111 upRes 4 startIndex 0 out 1 pretrain 0 pretrainDisc 0 tileSize %d simSize %d lambda 5.0 lambda2 0.00001 "
+              "discRuns 2 genRuns 2 alwaysSave 1 fromSim 1005 toSim 1005 outputInterval 200 genTestImg 1 dropout 0.5 dataDim 2 "
+              "batchSize 16 useVelocities 1 useVorticities 0 useK_Eps_Turb 0 useFlags 0 gif 0 genModel gen_resnet discModel disc_binclass "
+              "packedSimPath %s/ lambda_t 1.0 lambda_t_l2 0.0 frame_min 110 frame_max 111 data_fraction 0.01 adv_flag 1 "
+              "dataAugmentation 1 premadeTiles 0 rot 1 sliceMode 1 genUni 1 interpMode 1 velScale 1.0 precision fp32" % (L, L, tmp_path)).split()
+    assert cli_4x.main(["multipassGAN-4x.py"] + common + "upsamplingMode 2 upsampledData 0 randomInit 31".split()) == 0
+    head, first = uni.read_uni(str(sim / "density_low_2x2_0110.uni"))
+    assert (head["dimX"], head["dimY"], head["dimZ"]) == (S, S, S)
+    assert cli_4x.main(["multipassGAN-4x.py"] + common + "upsamplingMode 1 upsampledData 1 randomInit 32".split()) == 0
+    _, second = uni.read_uni(str(sim / "density_low_1x1_0110.uni"))
+
+    def weights_for(mode, seed):
+        G.reset_default_graph()
+        cfg = N.config_4x(L, upRes=u, upsampling_mode=mode)
+        N.gen_resnet(G.placeholder([None, (L * L if mode == 2 else S * S) * 4], "x"), cfg)
+        return W.init_graph_variables(G.get_default_graph(), seed)
+
+    mp = P.MultiPass4x(L, weights_for(2, 31), weights_for(1, 32), upRes=u, precision="fp32")
+    np.testing.assert_array_equal(first[..., 0], mp.pass1_only(x).cpu().numpy())
+    np.testing.assert_array_equal(second[..., 0], mp(x).cpu().numpy())
