@@ -69,6 +69,25 @@ def reslab_mid(slab, S, world, group, permute3, scratch_a, scratch_b, out, final
     return out
 
 
+def compose_perms(*perms):
+    """x.transpose(p1).transpose(p2)... as ONE numpy-style axis permutation."""
+    cur = (0, 1, 2)
+    for p in perms:
+        cur = tuple(cur[i] for i in p)
+    return cur
+
+
+def reslab_any(slab, S, world, group, permute3, scratch_a, scratch_b, out, perm, threshold=0.0, all_to_all=None):
+    """out = this rank's axis-0 slab of full.transpose(perm), `slab` being its axis-0 slab of `full` [S,S,S].
+    perm[0] == 0: the slab axis stays (local permutation of [S/G,S,S]); 2 -> `reslab`; 1 -> `reslab_mid`."""
+    per = S // world
+    if perm[0] == 0:
+        permute3(slab, out, (per, S, S), perm, threshold)
+        return out
+    fn = reslab if perm[0] == 2 else reslab_mid
+    return fn(slab, S, world, group, permute3, scratch_a, scratch_b, out, perm, threshold, all_to_all)
+
+
 class PeerSlab:
     """An output slab allocated in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped
     into every rank of the group over NVLink / NVSwitch), so that the axis change between passes is a kernel that

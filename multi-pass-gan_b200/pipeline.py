@@ -444,8 +444,6 @@ class MultiPassOut:
         f32 = dict(dtype=torch.float32, device=self.device)
         self.passes = {}
         self.flops = 0.0
-        if self.world > 1 and (self.nets != [1, 2] or self.ta != 0):
-            raise NotImplementedError("slice sharding is implemented for generators 1+2 with transposeAxis 0")
         self.s0, self.s1 = par.slab_range(self.rank, self.world, S)
         self.S_loc = self.s1 - self.s0
         for idx in self.nets:
@@ -469,7 +467,10 @@ class MultiPassOut:
             self.peer = None
         self.vol_dim = self.peer.tensor if self.peer else torch.empty((self.S_loc, S, S), **f32)
         self.vol_out = self.peer_c.tensor if self.peer else (torch.empty((self.S_loc, S, S), **f32) if self.world > 1 else None)
-        if self.world > 1 and self.peer is None:
+        self.scr_a = self.scr_b = None
+        if self.world > 1 and (self.peer is None or 3 in self.nets):
+            # pack / receive staging of the NCCL all-to-all form of an axis change (no peer mapping, or the row-preserving
+            # final permutation of the three-generator recipe, which the transposing peer-store kernel does not cover)
             self.scr_a = torch.empty((self.S_loc, S, S), **f32)
             self.scr_b = torch.empty((self.S_loc, S, S), **f32)
         self.launches_per_frame = sum((self.S_loc // p["batch"]) * (p["net"].net.launches + 1) for p in self.passes.values()) \
@@ -478,40 +479,70 @@ class MultiPassOut:
     def _permute3(self, src, dst, dims, perm, thr):
         capi.transpose3d(self.h, src, dst, dims, perm, thr, torch.cuda.current_stream(self.device).cuda_stream)
 
+    _POST = {1: (2, 1, 0), 2: (1, 2, 0), 3: (0, 1, 2)}  # GAN/multipassGAN-out.py:459, :521, :583
+
+    def _axis_change(self, rows, perm, threshold, k):
+        """k-th axis change of the frame on a slice-sharded volume: returns the buffer holding this rank's axis-0 slab of
+        rows_full.transpose(perm). Targets alternate between two slabs, so nobody stores into memory a peer may still be
+        reading in the current pass (parallel.PeerSlab); a permutation that keeps the slab axis is local."""
+        S = self.S
+        if perm == (0, 1, 2):
+            if threshold > 0:
+                capi.threshold(self.h, rows, self.S_loc * S * S, threshold, torch.cuda.current_stream(self.device).cuda_stream)
+            return rows
+        peer = (self.peer, self.peer_c)[k % 2] if self.peer else None
+        out = peer.tensor if peer else (self.vol_dim, self.vol_out)[k % 2]
+        if perm[0] == 0:
+            self._permute3(rows, out, (self.S_loc, S, S), perm, threshold)
+        elif peer is not None and perm[2] != 2:
+            peer.exchange(capi, self.h, rows, S, perm[0], perm, threshold, wait_readers=False)
+        else:
+            par.reslab_any(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, out, perm, threshold)
+        return out
+
     def _call_sharded(self, x, output_free=None):
-        """Generators 1+2 on this rank's slices (App. C): rows [Zu_loc,Yu,Xu] -> all-to-all -> dim_output slab
-        [Xu_loc,Yu,Zu] (= the `y` feeds of pass 2, :459) -> rows [Xu_loc,Yu,Zu] -> all-to-all -> [Zu_loc,Yu,Xu]
-        (the composition of :521 and :587-590 is .transpose(2,1,0) of the pass-2 rows), threshold fused (:612-615)."""
+        """Any generator chain / transposeAxis on this rank's slices (App. C). After generator i the rows
+        [slice_loc, row, col] are re-sliced into rows_full.transpose(post[i]) along ITS axis 0 (the `y` feed of generator
+        i+1, GAN/multipassGAN-out.py:459,521); after the last one post[i] and the closing transposes (:587-590) are
+        composed into ONE axis change with the threshold (:612-615) fused. Returns this rank's canonical z-slab."""
         S = self.S
         cur = torch.cuda.current_stream(self.device)
         st = cur.cuda_stream
         vol = _dev_f32(x, self.device)
-        rows, dim, out = self.vol_rows, self.vol_dim, self.vol_out
-        p = self.passes[1]
-        # with peers every finished batch is pushed to its owners at once (4-aligned batches: 128-bit stores along z)
-        stream_parts = self.peer is not None and p["batch"] % 4 == 0
-        for s in range(self.s0, self.s1, p["batch"]):
-            capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
-            p["net"].net.run({"x": p["inbuf"]}, out=rows[s - self.s0], stream=st)
+        rows = self.vol_rows
+        dim = None
+        closing = []
+        if 2 in self.nets:
+            closing.append((2, 0, 1))
+        if 1 in self.nets:
+            closing.append((2, 1, 0))
+        if output_free is not None and len(self.nets) != 2:
+            cur.wait_event(output_free)  # the finished frame may live in the slab the first pass already pushes into
+            output_free = None
+        for k, idx in enumerate(self.nets):
+            p = self.passes[idx]
+            B = p["batch"]
+            last = idx == self.nets[-1]
+            perm = par.compose_perms(self._POST[idx], *closing) if last else self._POST[idx]
+            # with peers every finished batch of the FIRST pass is pushed to its owners at once (4-aligned batches when
+            # the part's rows become the contiguous axis: 128-bit stores)
+            stream_parts = (self.peer is not None and k == 0 and not last and perm[2] != 2 and perm[0] != 0
+                            and (perm[2] != 0 or B % 4 == 0))
+            for s in range(self.s0, self.s1, B):
+                capi.slice_assemble(self.h, p["desc"], vol, None, s, B, p["inbuf"], st)
+                feeds = {"x": p["inbuf"]}
+                if idx > 1:
+                    feeds["y"] = dim[s - self.s0]
+                p["net"].net.run(feeds, out=rows[s - self.s0], stream=st)
+                if stream_parts:
+                    self.peer.push_part(capi, self.h, rows[s - self.s0], S, s, B, perm[0], perm, 0.0)
+            if k == 0 and output_free is not None:
+                cur.wait_event(output_free)
             if stream_parts:
-                self.peer.push_part(capi, self.h, rows[s - self.s0], S, s, p["batch"], 2, (2, 1, 0), 0.0)
-        if output_free is not None:
-            cur.wait_event(output_free)
-        if stream_parts:
-            self.peer.landed(channel=0)
-        elif self.peer:
-            self.peer.exchange(capi, self.h, rows, S, 2, (2, 1, 0), 0.0, wait_readers=False)
-        else:
-            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, dim, (2, 1, 0), 0.0)
-        p = self.passes[2]
-        for s in range(self.s0, self.s1, p["batch"]):
-            capi.slice_assemble(self.h, p["desc"], vol, None, s, p["batch"], p["inbuf"], st)
-            p["net"].net.run({"x": p["inbuf"], "y": dim[s - self.s0]}, out=rows[s - self.s0], stream=st)
-        if self.peer:  # the target is a second slab nobody reads during pass 2: no barrier before the stores
-            self.peer_c.exchange(capi, self.h, rows, S, 2, (2, 1, 0), self.threshold, wait_readers=False)
-        else:
-            par.reslab(rows, S, self.world, self.group, self._permute3, self.scr_a, self.scr_b, out, (2, 1, 0), self.threshold)
-        return out
+                dim = self.peer.landed(channel=0)
+            else:
+                dim = self._axis_change(rows, perm, self.threshold if last else 0.0, k)
+        return dim
 
     def __call__(self, x, output_free=None):
         """x: [L,L,L,4] float32, velocities already scaled by velScale (GAN/multipassGAN-out.py:138).

@@ -102,3 +102,49 @@ def test_training_gradient_exchange_is_the_rank_mean(tmp_path):
     want = (base * 1 + base * 2 + 0.25) / 2
     for r in range(world):
         np.testing.assert_allclose(np.load(str(tmp_path / ("g_%d.npy" % r))), want, rtol=1e-6)
+
+
+def _any_worker(rank, world, port, S, ref_path, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import itertools
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import parallel as par
+    full = torch.from_numpy(np.load(ref_path))
+    s0, s1 = par.slab_range(rank, world, S)
+    per = s1 - s0
+    for perm in itertools.permutations(range(3)):
+        out = torch.empty(per, S, S)
+        sa, sb = torch.empty(per, S, S), torch.empty(per, S, S)
+        par.reslab_any(full[s0:s1].clone(), S, world, None, _permute3_cpu, sa, sb, out, perm, 0.0)
+        np.save(os.path.join(out_dir, "any_%d_%d%d%d.npy" % ((rank,) + perm)), out.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reslab_any_covers_every_axis_permutation(tmp_path):
+    """parallel.reslab_any (what the generalized sharded MultiPassOut uses for any generator chain / transposeAxis):
+    for every axis permutation the ranks' outputs concatenate to full.transpose(perm); compose_perms is numpy's rule."""
+    import itertools
+    sys.path.insert(0, ROOT)
+    import mpgan_b200  # noqa: F401
+    from mpgan_b200 import parallel as par
+    S, world = 8, 2
+    full = np.random.default_rng(3).random((S, S, S)).astype(np.float32)
+    for p, q in itertools.product(itertools.permutations(range(3)), repeat=2):
+        assert np.array_equal(full.transpose(p).transpose(q), full.transpose(par.compose_perms(p, q)))
+    # the closing composition of the shipped recipes (GAN/multipassGAN-out.py:521,587-590)
+    assert par.compose_perms((1, 2, 0), (2, 0, 1), (2, 1, 0)) == (2, 1, 0)
+    assert par.compose_perms((0, 1, 2), (2, 0, 1), (2, 1, 0)) == (1, 0, 2)
+    assert par.compose_perms((2, 1, 0), (2, 1, 0)) == (0, 1, 2)
+    ref_path = str(tmp_path / "full.npy")
+    np.save(ref_path, full)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_any_worker, args=(world, port, S, ref_path, str(tmp_path)), nprocs=world, join=True)
+    for perm in itertools.permutations(range(3)):
+        parts = [np.load(str(tmp_path / ("any_%d_%d%d%d.npy" % ((r,) + perm)))) for r in range(world)]
+        assert np.array_equal(np.concatenate(parts, axis=0), full.transpose(perm)), perm

@@ -1,5 +1,5 @@
-"""torchrun --nproc-per-node G tools/check_sharded.py : slice-sharded MultiPass4x (NCCL all-to-all between
-passes) must reproduce the single-GPU volume bit for bit."""
+"""torchrun --nproc-per-node G tools/check_sharded.py [L] [4x|8x|8x3|8x_ta1] : the slice-sharded pipelines (axis changes
+as peer stores over NVLink, or NCCL all-to-all) must reproduce the single-GPU volume bit for bit."""
 import os
 import sys
 
@@ -20,12 +20,17 @@ if which == "4x":
     w1, w2 = P.make_weights_4x(L, 5, randomize_bn=True)
     single = P.MultiPass4x(L, w1, w2, precision="fp16", device=local)(x).clone()
     mp = P.MultiPass4x(L, w1, w2, precision="fp16", device=local, rank=rank, world=world)
-else:  # the shipped 8x two-pass recipe (GAN/example_run_output.py:18-48) with small feature counts
-    specs = {1: P.NetSpec(True, True, 64, 64, 3, True), 2: P.NetSpec(True, False, 48, 48, 5)}
-    w = P.make_weights_out(L, 5, upRes=8, specs=specs, nets=(1, 2))
-    single = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local)(x).clone()
-    mp = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local, rank=rank, world=world)
+else:  # the shipped 8x recipe (GAN/example_run_output.py:18-48) with small feature counts:
+    # "8x" = generators 1+2, "8x3" = all three generators (:39-47), "8x_ta1" = generators 1+2 with transposeAxis 1
+    specs = {1: P.NetSpec(True, True, 64, 64, 3, True), 2: P.NetSpec(True, False, 48, 48, 5),
+             3: P.NetSpec(False, False, 48, 24, 5)}
+    nets = (1, 2, 3) if which == "8x3" else (1, 2)
+    ta = 1 if which == "8x_ta1" else 0
+    w = P.make_weights_out(L, 5, upRes=8, specs=specs, nets=nets)
+    single = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local, transposeAxis=ta)(x).clone()
+    mp = P.MultiPassOut(L, w, upRes=8, specs=specs, precision="fp16", device=local, rank=rank, world=world, transposeAxis=ta)
 part = mp(x)
+part = mp(x)  # a second frame through the same buffers (slab reuse across frames)
 torch.cuda.synchronize()
 ref = single[mp.s0:mp.s1]
 same = bool(torch.equal(part, ref))
