@@ -452,6 +452,7 @@ def run_ours(args):
     #                  configs[4] (8x 256^3->2048^3, 8 GPUs only); timed AFTER the headline, same process group
     slice_batch = getattr(mp, "batch", None) or [p_["batch"] for _, p_ in sorted(mp.passes.items())]
     launches_per_frame, has_peer = mp.launches_per_frame, bool(getattr(mp, "peer", None))
+    h2d_bytes, d2h_bytes = int(loop.h2d_bytes), int(loop.d2h_bytes)
     secondary = {}
     if args.workload == "4x" and not args.no_secondary:
         for pn in nets:
@@ -522,7 +523,7 @@ def run_ours(args):
         pass_ms=pass_ms,
         bandwidth_kernels=bw,
         e2e=dict(value=S ** 3 / (e2e_ms * 1e-3), unit="voxel/s", ms_per_step=e2e_ms,
-                 h2d_bytes_per_step=int(loop.h2d_bytes), d2h_bytes_per_step=int(loop.d2h_bytes),
+                 h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
                  how="pipeline.HostFrameLoop: pinned H2D of the frame + D2H of the volume every step, copies of neighbouring frames overlap the networks (2 frames in flight)",
                  checksum=checksum),
         gpu_launches=int(launches_per_frame * args.steps),
