@@ -8,7 +8,15 @@ the same `random.randrange` call sequence (frame, then up to 19 offset tries of 
 degenerate `randrange(0, 1)` of the z axis, which consumes generator state) and the same float64 density test on the
 low-res tile -- and one gather per batch builds `[n, T*T*C]` / `[n, (T*u)^2]` rows directly in device memory.
 Pinned against the reference's own methods: tests/golden/tilesampler.npz (tests/golden/make_golden.py sampler).
-Augmentation (scipy rotations / scaling, `generateTile`) is not ported.
+
+Data augmentation (`selectRandomTiles(augment=True)` -> `generateTile`, :491-546) as the shipped 4x command line uses it
+(GAN/example_run_output.py:6: `dataAugmentation 1 rot 1`; defaults minScale 0.85, maxScale 1.15, flip 1): random scaling
+(scipy.ndimage.zoom order 1 = align-corners bilinear), a second random cut, a random 90-degree rotation and a random flip
+with the velocity channels fixed up (:755-879). Same split: the host replays the decisions (Python `random.randrange` for
+frame / offsets, numpy's legacy `RandomState` for the scale factor, rotation and flip -- the reference calls the global
+`np.random.uniform` / `np.random.choice`), the device does the data movement and interpolation. Pinned by
+tests/golden/tileaugment.npz (the reference's own generateTile, tests/golden/make_golden.py augment).
+The free-angle rotation (`rot 2`: scipy affine_transform) is not ported.
 """
 import random
 
@@ -35,6 +43,22 @@ class TileSampler:
         self.high = None    # [N, S, S, Ch]
         self._dens = None   # host copy of the low-res density channel, float32 [N, L, L] (density test)
         self.set_borders = [0, 0, 0]
+        self.use_data_aug = False
+
+    def init_data_augmentation(self, rot=2, minScale=0.85, maxScale=1.15, flip=True, np_rng=None):
+        """TileCreator.initDataAugmentation (:227-317). rot: 1 = 90-degree rotations, 2 = free rotation (not ported),
+        else none; minScale == maxScale == 1 disables scaling. np_rng: a numpy RandomState (the reference draws from the
+        global one; `np.random.RandomState(seed)` reproduces `np.random.seed(seed)`)."""
+        if rot == 2:
+            raise NotImplementedError("free-angle rotation (rot 2, scipy affine_transform) is not ported; the shipped 4x "
+                                      "recipe trains with rot 1 (GAN/example_run_output.py:6)")
+        self.use_data_aug = True
+        self.do_rot90 = rot == 1
+        self.scale_factor = (float(minScale), float(maxScale))
+        self.do_scaling = not (minScale == 1 and maxScale == 1)
+        self.do_flip = bool(flip)
+        self.np_rng = np_rng if np_rng is not None else np.random
+        return self
 
     # ------------------------------------------------------------------ data
     def add_data(self, low, high):
@@ -109,13 +133,87 @@ class TileSampler:
         high = self.high[f[:, None, None], (oy[:, None] * u + aru)[:, :, None], (ox[:, None] * u + aru)[:, None, :]]
         return low.unsqueeze(1), high.unsqueeze(1)
 
-    def select_random_tiles(self, selection_size, is_training=True):
-        """selectRandomTiles(selectionSize, isTraining, augment=False): (batch_low, batch_high)."""
+    def select_random_tiles(self, selection_size, is_training=True, augment=False):
+        """selectRandomTiles(selectionSize, isTraining, augment): (batch_low, batch_high)."""
+        if augment and self.use_data_aug:
+            return self.generate_tiles(selection_size, is_training)
         return self.gather(self.select_offsets(selection_size, is_training))
 
-    def batch_rows(self, batch_size, is_training=True):
+    # ------------------------------------------------------------------ augmentation (generateTile :491-546)
+    def _random_offset(self, f, frame_h, tile, dens_of):
+        """getRandomTile (:574-640) on a square 2-D frame: up to 19 tries of (z, y, x) offsets, density test on the cut."""
+        end = frame_h - tile + 1
+        if end < 1:
+            raise TileSamplerError("Can't cut tile %d from frame %d." % (tile, frame_h))
+        need = self.density_minimum * 1 * tile * tile
+        rr = self.rng.randrange
+        i, ok = 1, False
+        oy = ox = 0
+        while (not ok) and i < 20:
+            rr(0, 1)
+            oy = rr(0, end)
+            ox = rr(0, end)
+            ok = dens_of(oy, ox, tile) >= need
+            i += 1
+        return oy, ox
+
+    def generate_tiles(self, selection_size, is_training=True):
+        """`selection_size` augmented (low, high) tile pairs: [n, 1, T, T, C] / [n, 1, T*u, T*u, Ch] on self.device."""
+        import torch.nn.functional as F
+        T, u = self.T, self.u
+        L = self._dens.shape[1]
+        rr = self.rng.randrange
+        lows, highs = [], []
+        for _ in range(int(selection_size)):
+            f = rr(0, self.set_borders[0]) if is_training else rr(self.set_borders[0], self.set_borders[1])
+            low, high = self.low[f], self.high[f]  # [L,L,C], [S,S,Ch] views on the device
+            dens = self._dens[f]
+            if self.do_scaling:
+                sf = float(self.np_rng.uniform(self.scale_factor[0], self.scale_factor[1]))
+                tb = int(np.ceil(T * (1.0 / sf)))  # tile cut "for faster transformation" (:503-512)
+                oy, ox = self._random_offset(f, L, tb, lambda y, x, t: float(dens[y:y + t, x:x + t].sum(dtype=np.float64)))
+                low = low[oy:oy + tb, ox:ox + tb]
+                high = high[oy * u:(oy + tb) * u, ox * u:(ox + tb) * u]
+                # scale (:818-851): zoom factors round(shape_low * f) / shape_low for BOTH tensors, order-1 zoom
+                ts = int(np.round(tb * sf))
+                zf = ts / tb
+                hs = int(round(tb * u * zf))
+                low = F.interpolate(low.permute(2, 0, 1)[None], size=(ts, ts), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
+                high = F.interpolate(high.permute(2, 0, 1)[None], size=(hs, hs), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
+                low = torch.cat([low[..., :1], low[..., 1:4] * np.float32(sf), low[..., 4:]], dim=-1)  # scaleVelocities :853-862
+                dens_t = low[..., 0].double().cpu().numpy()  # the density test of the second cut sees the scaled tile
+                oy, ox = self._random_offset(f, ts, T, lambda y, x, t: float(dens_t[y:y + t, x:x + t].sum(dtype=np.float64)))
+            else:
+                oy, ox = self._random_offset(f, L, T, lambda y, x, t: float(dens[y:y + t, x:x + t].sum(dtype=np.float64)))
+            low = low[oy:oy + T, ox:ox + T]
+            high = high[oy * u:(oy + T) * u, ox * u:(ox + T) * u]
+            if self.do_rot90:  # cube_rot[2] = [[], [z], [z, z], [nz]], z = (2, 1), nz = (1, 2) (:292-300)
+                k = int(self.np_rng.randint(0, 4))
+                for axes in ([], [(2, 1)], [(2, 1), (2, 1)], [(1, 2)])[k]:
+                    # np.rot90(data[1,y,x,c], axes=(a0,a1)) on the tile without its unit z axis: axes (1,2) -> (0,1)
+                    dims = (axes[0] - 1, axes[1] - 1)
+                    low, high = torch.rot90(low, 1, dims), torch.rot90(high, 1, dims)
+                    # Reference quirk (reproduced, not fixed): rotate90Velocities (:755-763) swaps entries of a LIST of
+                    # channel views and returns a new array, and special_aug (:648-663) only writes an op's result back
+                    # for tile_t > 1 -- so with single frames the velocity vectors are NOT rotated with the tile
+                    # (flipVelocities / scaleVelocities modify their views in place and do take effect).
+            if self.do_flip:
+                axis = int(self.np_rng.randint(0, 4))
+                if axis < 3:
+                    if axis > 0:
+                        low, high = torch.flip(low, (axis - 1,)), torch.flip(high, (axis - 1,))
+                    ch = list(low.unbind(-1))  # flipVelocities (:797-813): axis 2 -> vx, 1 -> vy, 0 -> vz
+                    ch[3 - axis] = -ch[3 - axis]
+                    low = torch.stack(ch, dim=-1)
+            if tuple(low.shape[:2]) != (T, T) or tuple(high.shape[:2]) != (T * u, T * u):
+                raise TileSamplerError("Wrong tile shape after data augmentation. is: %s,%s." % (tuple(low.shape), tuple(high.shape)))
+            lows.append(low)
+            highs.append(high)
+        return torch.stack(lows).unsqueeze(1).contiguous(), torch.stack(highs).unsqueeze(1).contiguous()
+
+    def batch_rows(self, batch_size, is_training=True, augment=False):
         """getinput (GAN/multipassGAN-4x.py:1017-1047) with useVelocities and no vorticity / velocity modification:
         (batch_xs [n, T*T*C], batch_ys [n, (T*u)^2 * Ch]) in device memory, ready for Trainer4x.iteration."""
-        low, high = self.select_random_tiles(batch_size, is_training)
+        low, high = self.select_random_tiles(batch_size, is_training, augment)
         n = low.shape[0]
         return low.reshape(n, -1), high.reshape(n, -1)

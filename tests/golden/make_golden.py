@@ -440,9 +440,162 @@ def make_sampler_fixtures():
     print("tilesampler.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_augment_fixtures():
+    """TileCreator.selectRandomTiles(augment=True) -> generateTile (tools_wscale/tilecreator_t.py:491-546) with the data
+    augmentation of the shipped 4x command line (GAN/example_run_output.py:6: `dataAugmentation 1 rot 1`, default
+    minScale 0.85 / maxScale 1.15 / flip 1, GAN/multipassGAN-4x.py:95-102,263-264): random scaling (scipy.ndimage.zoom,
+    order 1), a second random tile cut, a random 90-degree rotation and a random flip, with the velocity channels fixed up
+    (scaleVelocities / rotate90Velocities / flipVelocities). The reference's own methods are compiled from the source
+    and bound to a stub carrying the state __init__ / initDataAugmentation set up for 2-D data with channel layout
+    'd,vx,vy,vz'. Two shims for today's interpreters, both documented behaviour of the versions the reference ran on:
+    `randrange` gets int() bounds (numpy floats are rejected by Python >= 3.12) and `np.random.choice` of the ragged
+    rotation list picks `lst[np.random.randint(0, len(lst))]` (numpy < 1.24 built a 1-D object array and drew one index)."""
+    import random
+    import types
+    import scipy.ndimage
+    names = ["selectRandomTiles", "generateTile", "getRandomDatum", "getDatum", "getRandomTile", "cutTile", "hasMinDensity",
+             "getTileDensity", "splitSets", "special_aug", "scale", "scaleVelocities", "rotate90", "rotate90Velocities", "flip",
+             "flipVelocities"]
+    code = ref_methods(os.path.join(REF, "tools_wscale", "tilecreator_t.py"), "TileCreator", names)
+    rnd = random.Random()
+
+    def randrange(a, b):
+        return rnd.randrange(int(a), int(b))
+
+    class _Rand:  # np.random with the legacy ragged-list behaviour of choice()
+        def __getattr__(self, k):
+            return getattr(np.random, k)
+
+        @staticmethod
+        def choice(a):
+            if isinstance(a, (int, np.integer)):
+                return np.random.randint(0, a)
+            return a[np.random.randint(0, len(a))]
+
+    np_shim = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    np_shim.random = _Rand()
+    ns = dict(np=np_shim, scipy=scipy, randrange=randrange, DATA_KEY_LOW=0, DATA_KEY_HIGH=1, AOPS_KEY_ROTATE="rot",
+              AOPS_KEY_SCALE="scale", AOPS_KEY_ROT90="rot90", AOPS_KEY_FLIP="flip", print=lambda *a, **k: None)
+    exec(code, ns)
+
+    class Stub:
+        def TCError(self, msg):
+            raise RuntimeError(msg)
+
+    for name in names:
+        setattr(Stub, name, ns[name])
+    out = {}
+    cfgs = {"a": (8, 24, 4, 4, 0.02, 0.85, 1.15, 1, 1, 21), "b": (6, 20, 2, 5, 0.005, 1.0, 1.0, 1, 0, 22),
+            "c": (8, 24, 2, 4, 0.02, 0.7, 1.3, 0, 1, 23)}
+    for tag, (T, L, u, nframes, dmin, smin, smax, rot, flip, seed) in cfgs.items():
+        rng = np.random.default_rng(seed)
+        S = L * u
+        low = rng.random((nframes, 1, L, L, 4), dtype=np.float32)
+        low[..., 1:4] -= 0.5
+        low[..., 0] *= (rng.random((nframes, 1, L, L)) < 0.3)
+        high = rng.random((nframes, 1, S, S, 1), dtype=np.float32)
+        st = Stub()
+        st.dim, st.dim_t, st.upres, st.premadeTiles, st.useDataAug = 2, 1, u, False, True
+        st.densityMinimum = dmin
+        st.tile_shape_low = np.array([1, T, T, 4])
+        st.tile_shape_high = np.array([1, T * u, T * u, 1])
+        vel = {"d": [0], "v": [[1, 2, 3]], "x": [], "o": [], "f": [], "k": [], "e": []}
+        none = {"d": [0], "v": [], "x": [], "o": [], "f": [], "k": [], "e": []}
+        st.c_lists = {0: vel, 1: none}
+        st.data_flags = {0: dict(channels=4, isLabel=False, d=True, v=True, x=False), 1: dict(channels=1, isLabel=False, d=True, v=False, x=False)}
+        st.aops = {k: {"rot": {}, "scale": {"v": st.scaleVelocities, "x": st.scaleVelocities},
+                       "rot90": {"v": st.rotate90Velocities, "x": st.rotate90Velocities},
+                       "flip": {"v": st.flipVelocities, "x": st.flipVelocities}} for k in (0, 1)}
+        # initDataAugmentation(rot, minScale, maxScale, flip) :227-317
+        st.do_rotation, st.do_rot90 = False, rot == 1
+        z, nz = (2, 1), (1, 2)
+        st.cube_rot = {2: [[], [z], [z, z], [nz]]}
+        st.scaleFactor = [smin, smax]
+        st.do_scaling = not (smin == 1 and smax == 1)
+        st.do_flip = flip
+        st.interpolation_order, st.fill_mode = 1, "constant"
+        st.data = {0: list(low), 1: list(high)}
+        st.part_train, st.part_test = 0.9, 0.1
+        st.splitSets()
+        rnd.seed(2000 + seed)
+        np.random.seed(3000 + seed)
+        xs, ys = [], []
+        for call in range(3):
+            bl, bh = st.selectRandomTiles(6, isTraining=True, augment=True)
+            xs.append(np.asarray(bl, np.float32))
+            ys.append(np.asarray(bh, np.float32))
+        out.update({tag + "_low": low, tag + "_high": high, tag + "_aug_low": np.stack(xs), tag + "_aug_high": np.stack(ys),
+                    tag + "_cfg": np.array([T, L, u, nframes, dmin, smin, smax, rot, flip, 2000 + seed, 3000 + seed], np.float64)})
+    np.savez_compressed(os.path.join(HERE, "tileaugment.npz"), **out)
+    print("tileaugment.npz:", {k: v.shape for k, v in out.items()})
+
+
+def make_slice_fixtures():
+    """The conv_slices path of FluidDataLoader.loadFiles (tools_wscale/fluiddataloader.py): the two `if self.conv_slices:`
+    statements of loadFiles are lifted out of the method body by line number (:414-431 axis conversion / channel swap for
+    x, :511-524 zoom + addAdjSlices + removeSlices + selectRandomSamples) and executed with the class's own helper methods
+    on a stub `self`; the y branch of the axis conversion (:451-467) is the same code on fy."""
+    import scipy.ndimage
+    path = os.path.join(REF, "tools_wscale", "fluiddataloader.py")
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "FluidDataLoader"][0]
+    load = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "loadFiles"][0]
+    ifs = [n for n in ast.walk(load) if isinstance(n, ast.If) and isinstance(n.test, ast.Attribute) and n.test.attr == "conv_slices"]
+    conv_x = [n for n in ifs if n.lineno in range(410, 420)][0]
+    post = [n for n in ifs if n.lineno in range(508, 514)][0]
+
+    def as_fn(name, args, stmt, ret):
+        fn = ast.FunctionDef(name=name, args=ast.arguments(posonlyargs=[], args=[ast.arg(arg=a) for a in args], kwonlyargs=[],
+                                                           kw_defaults=[], defaults=[]),
+                             body=[stmt, ast.parse("return " + ret).body[0]], decorator_list=[], type_params=[])
+        return fn
+
+    helpers = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("removeSlices", "addAdjSlices", "selectRandomSamples")]
+    mod = ast.Module(body=helpers + [as_fn("conv_x", ["self", "fx"], conv_x, "fx"), as_fn("post", ["self", "fx", "fy"], post, "(fx, fy)")],
+                     type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = dict(np=np, scipy=scipy, FDG_DTYPE=np.float32)
+    exec(compile(mod, path, "exec"), ns)
+
+    class Stub:
+        pass
+
+    for k in ("removeSlices", "addAdjSlices", "selectRandomSamples", "conv_x", "post"):
+        setattr(Stub, k, ns[k])
+    out = {}
+    rng = np.random.default_rng(31)
+    L, u = 6, 4
+    cases = {"mode2": (0, [1, 1, 1, 1], [0.25, 1, 1, 1], 4, False), "mode3": (1, [1, 1, 1, 1], [1, 1, 1, 1], 4, False),
+             "mode1_tempo": (2, [1, 1, 1, 1], [1, 1, 1, 1], 12, False), "adj": (0, [1, 1, 1, 1], [0.25, 1, 1, 1], 12, True)}
+    for tag, (axis, sc, scy, C, adj) in cases.items():
+        same = axis != 0  # refinement modes: x is already at the high resolution
+        shp = (L * u,) * 3 if same else (L,) * 3
+        fx = rng.random(shp + (C,), dtype=np.float32)
+        fx[..., 0] *= (rng.random(shp) < 0.03) * 1.0
+        fx[: shp[0] // 3, ..., 0] = 0.0
+        fy = rng.random((L * u,) * 3 + (1,), dtype=np.float32)
+        st = Stub()
+        st.conv_slices, st.conv_axis, st.have_y_npz = True, axis, True
+        st.axis_scaling, st.axis_scaling_y, st.add_adj_idcs = sc, scy, adj
+        st.density_threshold, st.select_random = 0.002, 0.5
+        x1 = st.conv_x(np.copy(fx))
+        y1 = st.conv_x(np.copy(fy))
+        np.random.seed(7)
+        x2, y2 = st.post(np.copy(x1), np.copy(y1))
+        out.update({tag + "_fx": fx, tag + "_fy": fy, tag + "_x": np.asarray(x2, np.float32), tag + "_y": np.asarray(y2, np.float32),
+                    tag + "_cfg": np.array([axis, C, int(adj)] + sc + scy, np.float64)})
+    np.savez_compressed(os.path.join(HERE, "slicedata.npz"), **out)
+    print("slicedata.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
-    which = sys.argv[1:] or ["pipeline", "nets", "tiles", "uni", "sampler"]
+    if "slices" in (sys.argv[1:] or ["slices"]):
+        make_slice_fixtures()
+    which = sys.argv[1:] or ["pipeline", "nets", "tiles", "uni", "sampler", "augment"]
+    if "augment" in which:
+        make_augment_fixtures()
     if "sampler" in which:
         make_sampler_fixtures()
     if "pipeline" in which:

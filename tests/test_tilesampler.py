@@ -90,3 +90,33 @@ def test_device_resident_sampler_feeds_the_trainer():
     tr = T_.Trainer4x(8, 4, 4, seed=2)
     out = tr.iteration([(xg, yg)], [(xg, yg)])
     assert np.isfinite(out["gen_loss_complete"]) and np.isfinite(out["disc_loss"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_augmented_tiles_match_reference_generate_tile(tag):
+    """selectRandomTiles(augment=True) -> generateTile (scaling, second cut, rot90, flip, velocity fix-ups) against the
+    reference's own methods (tests/golden/tileaugment.npz): identical decisions (Python random + numpy RandomState call
+    sequences), data movement exact, the order-1 zoom within fp32 rounding of scipy's double-precision interpolation."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tileaugment.npz"))
+    T, L, u, nframes, dmin, smin, smax, rot, flip, seed_py, seed_np = gold[tag + "_cfg"]
+    s = ts.TileSampler(int(T), int(u), densityMinimum=float(dmin), rng=random.Random(int(seed_py)))
+    s.add_data(gold[tag + "_low"], gold[tag + "_high"])
+    s.init_data_augmentation(rot=int(rot), minScale=float(smin), maxScale=float(smax), flip=bool(flip),
+                             np_rng=np.random.RandomState(int(seed_np)))
+    exact = float(smin) == 1.0 and float(smax) == 1.0
+    for call in range(3):
+        low, high = s.select_random_tiles(6, is_training=True, augment=True)
+        wl, wh = gold[tag + "_aug_low"][call], gold[tag + "_aug_high"][call]
+        assert tuple(low.shape) == wl.shape and tuple(high.shape) == wh.shape
+        if exact:  # no interpolation: cut + rot90 + flip + sign changes are pure data movement
+            np.testing.assert_array_equal(low.numpy(), wl)
+            np.testing.assert_array_equal(high.numpy(), wh)
+        else:
+            np.testing.assert_allclose(low.numpy(), wl, rtol=0, atol=3e-6)
+            np.testing.assert_allclose(high.numpy(), wh, rtol=0, atol=3e-6)
+
+
+def test_augmentation_free_rotation_is_refused():
+    s = ts.TileSampler(8, 4)
+    with pytest.raises(NotImplementedError):
+        s.init_data_augmentation(rot=2)
