@@ -406,7 +406,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             fence_proxy_async();
             __syncwarp();
             if (lane == 0 && t < p.num_tiles && !(p.dbg & 1)) {
-              tma_store_4d(&tm_y, stg, cg, tc.x0 + acc * 8, tc.y0 + ew * 4, tc.n);
+              if (ups == 1) {
+                tma_store_4d(&tm_y, stg, cg, tc.x0 + acc * 8, tc.y0 + ew * 4, tc.n);
+              } else {  // nearest x2: the four replicas of the block, map dims (c, ux, x, uy, n*h + y)
+                const int row = tc.n * p.h + tc.y0 + ew * 4;
+                tma_store_5d(&tm_y, stg, cg, 0, tc.x0 + acc * 8, 0, row);
+                tma_store_5d(&tm_y, stg, cg, 1, tc.x0 + acc * 8, 0, row);
+                tma_store_5d(&tm_y, stg, cg, 0, tc.x0 + acc * 8, 1, row);
+                tma_store_5d(&tm_y, stg, cg, 1, tc.x0 + acc * 8, 1, row);
+              }
               tma_store_commit();
             }
           }

@@ -17,6 +17,10 @@ CASES = {
     "2seg_128k5_32k1": dict(n=1, h=64, w=64, cins=[128, 32], ks=[5, 1], cout=128, act="relu"),
     "2seg_32k5_128k1_to8": dict(n=1, h=64, w=64, cins=[32, 128], ks=[5, 1], cout=8, act="relu"),
     "k3_pn_up2": dict(n=1, h=32, w=32, cins=[128], ks=[3], cout=128, act="relu", pixel_norm=True, upsample=2),
+    # nearest x2 store: bulk tensor stores through the 5-D map (whole tiles per image, several images) / per-lane fallback
+    "k3_up2_tma_n3": dict(n=3, h=32, w=48, cins=[128, 64], ks=[3, 1], cout=128, act="relu", pixel_norm=True, upsample=2),
+    "k3_up2_ragged_h24": dict(n=2, h=24, w=40, cins=[128], ks=[3], cout=128, act="relu", pixel_norm=True, upsample=2),
+    "k3_up2_64ch": dict(n=2, h=32, w=32, cins=[64, 64], ks=[3, 1], cout=64, act="relu", pixel_norm=True, upsample=2),
     "ragged_37x45": dict(n=3, h=37, w=45, cins=[64], ks=[5], cout=48, act="lrelu"),
     "tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="tanh"),
     "nf_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=3),
