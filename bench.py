@@ -333,6 +333,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference)")
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL still logs goes to stderr, never into the JSON stream
     rank, local, world = par.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
