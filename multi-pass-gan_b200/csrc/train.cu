@@ -297,6 +297,91 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradArgs a, int 
 __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const float* dz, const float* mean,
                                                         const float* invstd, double* out, long long rows, int c,
                                                         int mode) {
+  // Vector path (c % 4 == 0, c <= 1024): a thread owns 4 adjacent channels (one 128-bit load per row) and walks the rows
+  // with 4 independent loads in flight; the block combines its row groups in shared memory, so every block issues ONE
+  // double atomic per channel and statistic. (The scalar version below kept 4 x 4 bytes per thread in flight and was
+  // latency bound at ~30 % of the HBM rate: 34 us for a 33 MB layer, 68 launches per loop body.)
+  if ((c & 3) == 0 && c <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (mode != 1 || (reinterpret_cast<uintptr_t>(dz) & 15) == 0)) {
+    __shared__ double red[2][256][4];
+    const int groups = c >> 2;                       // float4 groups per row
+    const int lanes = groups < 256 ? groups : 256;   // threads per row
+    const int rows_per_iter = 256 / lanes;
+    const int gl = threadIdx.x % lanes, r_l = threadIdx.x / lanes;
+    const bool active = r_l < rows_per_iter;
+    const long long rstep = static_cast<long long>(gridDim.x) * rows_per_iter;
+    for (int g0 = 0; g0 < groups; g0 += lanes) {
+      const int g = g0 + gl;
+      double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+      if (active && g < groups) {
+        const float4* xp = reinterpret_cast<const float4*>(x) + g;
+        const float4* dp = reinterpret_cast<const float4*>(dz) + g;
+        float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
+        if (mode == 1) {
+          mu = reinterpret_cast<const float4*>(mean)[g];
+          is = reinterpret_cast<const float4*>(invstd)[g];
+        }
+        long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + r_l;
+        for (; r < rows; r += 4 * rstep) {
+          float4 v[4], d[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const long long rr = r + j * rstep;
+            v[j] = rr < rows ? __ldg(xp + rr * groups) : make_float4(0, 0, 0, 0);
+            if (mode == 1) d[j] = rr < rows ? __ldg(dp + rr * groups) : make_float4(0, 0, 0, 0);
+          }
+          // fp32 partial sums over the 4 rows in flight, accumulated in double across iterations
+          float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            if (mode == 1) {
+              const float dv[4] = {d[j].x, d[j].y, d[j].z, d[j].w};
+              const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, i4[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                a0[q] += dv[q];
+                a1[q] = fmaf(dv[q], (xv[q] - m4[q]) * i4[q], a1[q]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                a0[q] += xv[q];
+                if (mode == 0) a1[q] = fmaf(xv[q], xv[q], a1[q]);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            s0[q] += a0[q];
+            s1[q] += a1[q];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        red[0][threadIdx.x][q] = s0[q];
+        red[1][threadIdx.x][q] = s1[q];
+      }
+      __syncthreads();
+      // threads of row group 0 fold the other row groups of their channel quad
+      if (r_l == 0 && g < groups) {
+        for (int o = 1; o < rows_per_iter; ++o)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            s0[q] += red[0][o * lanes + gl][q];
+            s1[q] += red[1][o * lanes + gl][q];
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          atomicAdd(&out[4 * g + q], s0[q]);
+          if (mode != 2) atomicAdd(&out[c + 4 * g + q], s1[q]);
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
   // thread -> channel (tid % c) when c <= 256, rows strided
   const int lanes_per_row = c < 256 ? c : 256;
   const int rows_per_iter = 256 / lanes_per_row;
@@ -307,15 +392,6 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
     double s0 = 0.0, s1 = 0.0;
     const long long rstep = static_cast<long long>(gridDim.x) * rows_per_iter;
     long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + r_l;
-    if (mode != 1) {
-      // four independent loads in flight (the plain loop is bound by one load latency per row and thread)
-      for (; r + 3 * rstep < rows; r += 4 * rstep) {
-        const float x0 = x[r * c + ch], x1 = x[(r + rstep) * c + ch], x2 = x[(r + 2 * rstep) * c + ch], x3 = x[(r + 3 * rstep) * c + ch];
-        s0 += (static_cast<double>(x0) + x1) + (static_cast<double>(x2) + x3);
-        if (mode == 0)
-          s1 += (static_cast<double>(x0) * x0 + static_cast<double>(x1) * x1) + (static_cast<double>(x2) * x2 + static_cast<double>(x3) * x3);
-      }
-    }
     for (; r < rows; r += rstep) {
       const float xv = x[r * c + ch];
       if (mode == 0) {
