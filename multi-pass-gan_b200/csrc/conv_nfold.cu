@@ -77,7 +77,8 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     tma_prefetch_desc(&tm_x0);
     if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
     for (int i = 0; i < p.na; ++i) {
-      mbar_init(&full_a[i], 1);
+      // cp.async staging: one arrival per producer lane (2 warps), plus the peer CTA's relay in PAIR mode (leader only)
+      mbar_init(&full_a[i], p.a_cpasync ? 64u + ((PAIR && rank == 0) ? 1u : 0u) : 1u);
       mbar_init(&empty_a[i], 1);
     }
     for (int i = 0; i < kNfMaxStagesB; ++i) {
@@ -106,7 +107,89 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
+  // ===================== A producer, cp.async form (p.a_cpasync; swizzled layouts, resident weights) ================
+  // Tiled TMA costs ~5.5 cycles per box row (one pixel of one K-chunk, <= 128 B) per SM whatever its size (measured:
+  // the load-only skeleton of the 5x5 128->32 layer took 0.198 ms with 128-byte rows and 0.358 ms with 64-byte rows),
+  // which bounded that layer below its MMA time. Here warps 0 and 3 copy the window with 16-byte cp.async (LDGSTS,
+  // 512 B per warp instruction) straight into the 128B/64B/32B-swizzled image the UMMA descriptors expect; out-of-image
+  // pixels and channels beyond the tensor are zero-filled (= SAME padding / TMA out-of-bounds fill). Every lane's copies
+  // arrive on the stage's mbarrier asynchronously (cp.async.mbarrier.arrive.noinc); in PAIR mode the peer CTA collects
+  // its own lanes on its local barrier and warp 2 relays one cluster-scope arrival to the leader.
+  if (p.a_cpasync && !NS8 && (warp == 0 || warp == 3)) {
+    if (warp == 3 && lane == 0) {  // resident weights first (same as the TMA form below)
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
+      const uint32_t tile_bytes = static_cast<uint32_t>(p.b_tile_bytes);
+      if (PAIR) {
+        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+        for (int kt = 0; kt < p.ktiles; ++kt)
+          bulk_load_1d(smB + static_cast<size_t>(kt) * tile_bytes, wsrc + (static_cast<size_t>(kt) * 2 + rank) * tile_bytes,
+                       tile_bytes, &full_b[0]);
+        mbar_wait(&full_b[0], 0);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready), 0));
+      } else {
+        mbar_arrive_expect_tx(&full_b[0], tile_bytes * static_cast<uint32_t>(p.ktiles));
+        bulk_load_1d(smB, wsrc, tile_bytes * static_cast<uint32_t>(p.ktiles), &full_b[0]);
+      }
+    }
+    __syncwarp();
+    constexpr int CPR = RB / 16;    // 16-byte chunks per pixel row of a K-chunk
+    constexpr int PPI = 32 / CPR;   // pixels per warp instruction
+    const int pw = warp == 0 ? 0 : 1;
+    const int j = lane % CPR, q = lane / CPR;
+    const uint32_t smA_u32 = smem_u32(smA);
+    int st = 0;
+    uint32_t ph = 0;
+    NF_TILE_LOOP(t) {
+      const NfTile tc = nf_decode(NF_TILE_CLAMP(t), p);
+      for (int s = 0; s < p.nseg; ++s) {
+        const int ks = p.seg_ks[s];
+        const int wy0 = tc.y0 - (ks >> 1);
+        const int npx = (p.rows + ks - 1) * kNfWin;
+        const int cin = p.seg_cin[s];
+        const size_t cs2 = static_cast<size_t>(p.seg_cstride[s]) * 2;
+        const uint8_t* img = static_cast<const uint8_t*>(p.x[s]) + static_cast<size_t>(tc.n) * p.h * p.w * cs2;
+        for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+          if (lane == 0) mbar_wait(&empty_a[st], ph ^ 1u);
+          __syncwarp();
+          const uint32_t stage = smA_u32 + static_cast<uint32_t>(st) * static_cast<uint32_t>(p.a_stage_bytes);
+          const int c0 = ch * CK + j * 8;  // first channel of this lane's 16 bytes
+          const int cbytes = c0 >= cin ? 0 : ((cin - c0) >= 8 ? 16 : (cin - c0) * 2);
+          for (int px = pw * PPI + q; px < npx; px += 2 * PPI) {
+            const int wy = px >> 5, wx = px & (kNfWin - 1);
+            const int gy = wy0 + wy, gx = tc.gx0 + wx;
+            const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+            const uint32_t sw = RB == 128 ? (px & 7) : (RB == 64 ? ((px >> 1) & 3) : ((px >> 2) & 1));
+            const uint8_t* src = in ? img + (static_cast<size_t>(gy) * p.w + gx) * cs2 + static_cast<size_t>(c0 < cin ? c0 : 0) * 2 : img;
+            cp_async_16_zfill(stage + static_cast<uint32_t>(px) * RB + ((static_cast<uint32_t>(j) ^ sw) << 4), src,
+                              in ? static_cast<uint32_t>(cbytes) : 0u);
+          }
+          cp_async_mbar_arrive_noinc(&full_a[st]);
+          if (++st == p.na) {
+            st = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (p.a_cpasync && !NS8 && PAIR && rank != 0 && warp == 2) {
+    // peer CTA: relay "this CTA's window has landed" to the leader's stage barrier
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      NF_TILE_LOOP(t) {
+        for (int s = 0; s < p.nseg; ++s)
+          for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
+            mbar_wait(&full_a[st], ph);
+            fence_proxy_async_all();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&full_a[st]), 0));
+            if (++st == p.na) {
+              st = 0;
+              ph ^= 1u;
+            }
+          }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== A producer: one window image per (segment, chunk) =====================
     if (lane == 0) {
       int st = 0;
@@ -214,7 +297,9 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const int ks = p.seg_ks[s];
         const int nchunk = p.seg_nchunk[s];
         for (int ch = 0; ch < nchunk; ++ch) {
-          mbar_wait(&full_a[sa], pa);
+          if (PAIR) mbar_wait_cluster(&full_a[sa], pa);  // (the peer's relay arrives with release.cluster)
+          else mbar_wait(&full_a[sa], pa);
+          if (p.a_cpasync) fence_proxy_async_all();  // cp.async wrote through the generic proxy, the MMA reads through the async one
           tc_fence_after();
           uint32_t a_row = smA_lo + static_cast<uint32_t>(sa) * a_stage16;  // image row dy of the window
           for (int dy = 0; dy < ks; dy += (NS8 ? 2 : 1)) {

@@ -25,7 +25,7 @@ constexpr int kNfWin = 32;      // pixels per image row held by an accumulator
 constexpr int kNfRowsAcc = 4;   // image rows per accumulator (4 * 32 = 128 MMA rows)
 constexpr int kNfThreads = 256;     // 4 role warps + 4 epilogue warps (two CTAs per SM)
 constexpr int kNfMaxThreads = 384;  // + 8 epilogue warps (one CTA per SM)
-constexpr int kNfMaxStagesA = 4;
+constexpr int kNfMaxStagesA = 8;
 constexpr int kNfMaxStagesB = 8;
 constexpr int kNfMaxBufs = 10;  // TMEM accumulator buffers (tiles in flight between the MMA and epilogue warps)
 
@@ -46,6 +46,9 @@ struct NfoldParams {
   int na, nb;
   int a_stage_bytes, b_tile_bytes;
   int bres, ktiles;
+  int a_cpasync;  // window images staged by two producer warps with cp.async instead of tiled TMA (conv_nfold.cu)
+  int seg_cin[2], seg_cstride[2];  // for the cp.async producer: real channels / channel stride of each input
+  const void* x[2];                // ... and the input tensors themselves
   int pair;  // cta_group::2 CTA pairs with resident half weight tiles, one accumulator per tile (conv_nfold.cu)
   int threads;  // launch block size: 256 or 384
   int dbg;  // profiling only (env MPG_NFOLD_DBG): bit0 skip stores, bit1 skip the whole epilogue body, bit2 skip MMAs

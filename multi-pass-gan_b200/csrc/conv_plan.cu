@@ -495,6 +495,14 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     q.b_tile_bytes = (npad / 2) * rb;  // this CTA's half of a k-tile
     q.bres = 1;
   }
+  // window images by cp.async instead of tiled TMA (conv_nfold.cu): swizzled layouts with resident weights (warp 3 is then
+  // free to be the second producer warp)
+  q.a_cpasync = (!ns8 && q.bres) ? 1 : 0;
+  if (const char* e = getenv("MPG_NFOLD_CPASYNC")) q.a_cpasync = (q.a_cpasync && atoi(e) != 0) ? 1 : 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    q.seg_cin[s] = d.seg_cin[s];
+    q.seg_cstride[s] = d.seg_cstride[s];
+  }
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(q.nbuf * q.naccs * npad)) cols <<= 1;
   q.tmem_cols = cols;
@@ -793,6 +801,8 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
     mpg::NfoldParams q = p->np;
     q.out = y;
+    q.x[0] = x0;
+    q.x[1] = x1;
     int r = mpg::nfold_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w, q, p->grid,
                               p->smem_bytes, st);
     if (r) {

@@ -133,6 +133,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 
 // 64-thread barrier of the two epilogue warps that share TMEM lane quarter `q` (ids 1..4, immediate operands so the
 // kernel reserves 5 hardware barriers instead of all 16)
+// ---------------------------------------------------------------- cp.async (LDGSTS) with zero fill
+// 16-byte global -> shared copy; only `src_bytes` (0..16) are read, the rest of the 16 bytes is written as zeros
+// (src_bytes = 0 = a zero fill: SAME padding / channels beyond the tensor)
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all of its prior cp.async copies have landed; .noinc: the
+// arrival is part of the barrier's expected count
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy writes (cp.async, st.shared) -> async-proxy reads (tcgen05.mma operands), any state space
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 __device__ __forceinline__ void quarter_pair_sync(int q) {
   switch (q) {
     case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
