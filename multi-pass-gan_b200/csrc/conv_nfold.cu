@@ -153,15 +153,35 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           __syncwarp();
           const uint32_t stage = smA_u32 + static_cast<uint32_t>(st) * static_cast<uint32_t>(p.a_stage_bytes);
           const int c0 = ch * CK + j * 8;  // first channel of this lane's 16 bytes
-          const int cbytes = c0 >= cin ? 0 : ((cin - c0) >= 8 ? 16 : (cin - c0) * 2);
-          for (int px = pw * PPI + q; px < npx; px += 2 * PPI) {
-            const int wy = px >> 5, wx = px & (kNfWin - 1);
-            const int gy = wy0 + wy, gx = tc.gx0 + wx;
-            const bool in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-            const uint32_t sw = RB == 128 ? (px & 7) : (RB == 64 ? ((px >> 1) & 3) : ((px >> 2) & 1));
-            const uint8_t* src = in ? img + (static_cast<size_t>(gy) * p.w + gx) * cs2 + static_cast<size_t>(c0 < cin ? c0 : 0) * 2 : img;
-            cp_async_16_zfill(stage + static_cast<uint32_t>(px) * RB + ((static_cast<uint32_t>(j) ^ sw) << 4), src,
-                              in ? static_cast<uint32_t>(cbytes) : 0u);
+          const uint32_t cbytes = c0 >= cin ? 0u : ((cin - c0) >= 8 ? 16u : static_cast<uint32_t>((cin - c0) * 2));
+          // a lane owns NCOL fixed window columns (wx = pw*PPI + q + 2*PPI*k): per image row ONE 64-bit address, then NCOL
+          // copies at constant offsets (a per-pixel recomputation made every copy a ~150-cycle dependent chain)
+          constexpr int NCOL = kNfWin / (2 * PPI);
+          const int wx0 = pw * PPI + q;
+          uint32_t dst_col[NCOL];
+          uint32_t ok_col = 0;
+#pragma unroll
+          for (int k = 0; k < NCOL; ++k) {
+            const int wx = wx0 + 2 * PPI * k;
+            const uint32_t sw = RB == 128 ? (wx & 7) : (RB == 64 ? ((wx >> 1) & 3) : ((wx >> 2) & 1));
+            dst_col[k] = stage + static_cast<uint32_t>(wx) * RB + ((static_cast<uint32_t>(j) ^ sw) << 4);
+            const int gx = tc.gx0 + wx;
+            ok_col |= (gx >= 0 && gx < p.w && cbytes != 0u) ? (1u << k) : 0u;
+          }
+          const uint8_t* col0 = img + (static_cast<long long>(tc.gx0) + wx0) * static_cast<long long>(cs2) +
+                                static_cast<size_t>(c0 < cin ? c0 : 0) * 2;
+          const int nrows = p.rows + ks - 1;
+#pragma unroll 2
+          for (int wy = 0; wy < nrows; ++wy) {
+            const int gy = wy0 + wy;
+            const bool row_ok = gy >= 0 && gy < p.h;
+            const uint8_t* rowp = col0 + static_cast<long long>(row_ok ? gy : 0) * p.w * static_cast<long long>(cs2);
+            const uint32_t drow = static_cast<uint32_t>(wy) * (kNfWin * RB);
+#pragma unroll
+            for (int k = 0; k < NCOL; ++k) {
+              const bool ok = row_ok && ((ok_col >> k) & 1u);
+              cp_async_16_zfill(dst_col[k] + drow, ok ? rowp + static_cast<size_t>(2 * PPI * k) * cs2 : img, ok ? cbytes : 0u);
+            }
           }
           cp_async_mbar_arrive_noinc(&full_a[st]);
           if (++st == p.na) {

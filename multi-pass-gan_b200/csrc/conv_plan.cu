@@ -495,10 +495,13 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
     q.b_tile_bytes = (npad / 2) * rb;  // this CTA's half of a k-tile
     q.bres = 1;
   }
-  // window images by cp.async instead of tiled TMA (conv_nfold.cu): swizzled layouts with resident weights (warp 3 is then
-  // free to be the second producer warp)
-  q.a_cpasync = (!ns8 && q.bres) ? 1 : 0;
-  if (const char* e = getenv("MPG_NFOLD_CPASYNC")) q.a_cpasync = (q.a_cpasync && atoi(e) != 0) ? 1 : 0;
+  // Window images by cp.async producer warps instead of tiled TMA (conv_nfold.cu). OFF by default: measured on B200 the
+  // two-warp LDGSTS producer is 3.4x SLOWER than tiled TMA (load-only skeleton of the 5x5 128->32 layer 0.684 ms vs
+  // 0.198 ms; ~157 cycles per 512-byte warp copy whatever the address arithmetic costs), so the TMA row rate
+  // (~5.5 cycles per <=128-byte box row per SM) stays the bound of that layer. Kept behind MPG_NFOLD_CPASYNC=1 (parity
+  // tested) for swizzled layouts with resident weights, where warp 3 is free to be the second producer warp.
+  q.a_cpasync = 0;
+  if (const char* e = getenv("MPG_NFOLD_CPASYNC")) q.a_cpasync = (!ns8 && q.bres && atoi(e) != 0) ? 1 : 0;
   for (int s = 0; s < d.nseg; ++s) {
     q.seg_cin[s] = d.seg_cin[s];
     q.seg_cstride[s] = d.seg_cstride[s];

@@ -84,3 +84,17 @@ def test_flagship_shape_one_slice():
     """ru2_B + shortcut at 512x512 (config 2 resolution), one slice."""
     r = run_case(n=1, h=512, w=512, cins=[128, 32], ks=[5, 1], cout=128, act="relu")
     assert r["kind"] == 1 and r["rel_l2"] < 6e-3, r
+
+
+@pytest.mark.parametrize("name", ["nfp_k5_128to32_ragged", "nf_k3_64to32_s", "2seg_32k5_128k1_to8"])
+def test_nfold_cp_async_producer_variant(name, monkeypatch):
+    """The cp.async (LDGSTS) window producer of the tap-folded kernel (off by default: slower than tiled TMA on B200, see
+    conv_plan.cu) gives the same results: swizzled destinations, zero fill = SAME padding, CTA-pair relay."""
+    monkeypatch.setenv("MPG_NFOLD_CPASYNC", "1")
+    kw = dict(CASES[name])
+    for key in ("in_dtype", "out_dtype"):
+        if kw.get(key, "bf16") == "bf16":
+            kw[key] = "f16"
+    r = run_case(**kw)
+    assert r["finite"] and r["pad_ok"] and r["kind"] == 3, r
+    assert r["rel_l2"] < 8e-4, (name, r)
