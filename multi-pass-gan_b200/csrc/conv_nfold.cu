@@ -144,7 +144,6 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       for (int s = 0; s < p.nseg; ++s) {
         const int ks = p.seg_ks[s];
         const int wy0 = tc.y0 - (ks >> 1);
-        const int npx = (p.rows + ks - 1) * kNfWin;
         const int cin = p.seg_cin[s];
         const size_t cs2 = static_cast<size_t>(p.seg_cstride[s]) * 2;
         const uint8_t* img = static_cast<const uint8_t*>(p.x[s]) + static_cast<size_t>(tc.n) * p.h * p.w * cs2;
@@ -156,7 +155,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           const uint32_t cbytes = c0 >= cin ? 0u : ((cin - c0) >= 8 ? 16u : static_cast<uint32_t>((cin - c0) * 2));
           // a lane owns NCOL fixed window columns (wx = pw*PPI + q + 2*PPI*k): per image row ONE 64-bit address, then NCOL
           // copies at constant offsets (a per-pixel recomputation made every copy a ~150-cycle dependent chain)
-          constexpr int NCOL = kNfWin / (2 * PPI);
+          constexpr int NCOL = kNfWin / (2 * PPI) > 0 ? kNfWin / (2 * PPI) : 1;  // (>= 1 only to let the unused NS8 instance compile)
           const int wx0 = pw * PPI + q;
           uint32_t dst_col[NCOL];
           uint32_t ok_col = 0;
