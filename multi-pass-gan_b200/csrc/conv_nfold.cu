@@ -71,14 +71,17 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   if (threadIdx.x < 32) s_shift[threadIdx.x] = threadIdx.x < p.cp ? p.shift[threadIdx.x] : 0.0f;
   // 4 epilogue warps (256-thread launch, two CTAs per SM) or 8 (384 threads: two warps per TMEM lane quarter take
   // the even / odd 8-channel chunks; for pixel_norm they exchange their partial sums of squares through s_pn)
-  const int epi_active = ((blockDim.x >> 5) - 4 == 8 && p.cp > 8) ? 8 : 4;
+  const int n_extra = p.a_cpasync ? p.nprod - 2 : 0;  // extra cp.async producer warps sit after the epilogue warps
+  const int n_epi_launched = static_cast<int>(blockDim.x >> 5) - 4 - n_extra;
+  const int epi_active = (n_epi_launched == 8 && p.cp > 8) ? 8 : 4;
+  const int first_extra = 4 + n_epi_launched;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x0);
     if (p.nseg > 1) tma_prefetch_desc(&tm_x1);
     for (int i = 0; i < p.na; ++i) {
       // cp.async staging: one arrival per producer lane (2 warps), plus the peer CTA's relay in PAIR mode (leader only)
-      mbar_init(&full_a[i], p.a_cpasync ? 64u + ((PAIR && rank == 0) ? 1u : 0u) : 1u);
+      mbar_init(&full_a[i], p.a_cpasync ? 32u * static_cast<uint32_t>(p.nprod) + ((PAIR && rank == 0) ? 1u : 0u) : 1u);
       mbar_init(&empty_a[i], 1);
     }
     for (int i = 0; i < kNfMaxStagesB; ++i) {
@@ -115,7 +118,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   // pixels and channels beyond the tensor are zero-filled (= SAME padding / TMA out-of-bounds fill). Every lane's copies
   // arrive on the stage's mbarrier asynchronously (cp.async.mbarrier.arrive.noinc); in PAIR mode the peer CTA collects
   // its own lanes on its local barrier and warp 2 relays one cluster-scope arrival to the leader.
-  if (p.a_cpasync && !NS8 && (warp == 0 || warp == 3)) {
+  if (p.a_cpasync && !NS8 && (warp == 0 || warp == 3 || warp >= first_extra)) {
     if (warp == 3 && lane == 0) {  // resident weights first (same as the TMA form below)
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
       const uint32_t tile_bytes = static_cast<uint32_t>(p.b_tile_bytes);
@@ -134,7 +137,10 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     __syncwarp();
     constexpr int CPR = RB / 16;    // 16-byte chunks per pixel row of a K-chunk
     constexpr int PPI = 32 / CPR;   // pixels per warp instruction
-    const int pw = warp == 0 ? 0 : 1;
+    // producer warp index -> (column group cgp in {0,1}, row group rg): a warp copies its column group of every
+    // (nprod/2)-th window row
+    const int pidx = warp == 0 ? 0 : (warp == 3 ? 1 : 2 + (warp - first_extra));
+    const int pw = pidx & 1, rg = pidx >> 1, nrg = p.nprod >> 1;
     const int j = lane % CPR, q = lane / CPR;
     const uint32_t smA_u32 = smem_u32(smA);
     int st = 0;
@@ -171,7 +177,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                                 static_cast<size_t>(c0 < cin ? c0 : 0) * 2;
           const int nrows = p.rows + ks - 1;
 #pragma unroll 2
-          for (int wy = 0; wy < nrows; ++wy) {
+          for (int wy = rg; wy < nrows; wy += nrg) {
             const int gy = wy0 + wy;
             const bool row_ok = gy >= 0 && gy < p.h;
             const uint8_t* rowp = col0 + static_cast<long long>(row_ok ? gy : 0) * p.w * static_cast<long long>(cs2);

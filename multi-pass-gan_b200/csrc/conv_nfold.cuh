@@ -46,7 +46,8 @@ struct NfoldParams {
   int na, nb;
   int a_stage_bytes, b_tile_bytes;
   int bres, ktiles;
-  int a_cpasync;  // window images staged by two producer warps with cp.async instead of tiled TMA (conv_nfold.cu)
+  int a_cpasync;  // window images staged by producer warps with cp.async instead of tiled TMA (conv_nfold.cu)
+  int nprod;      // ... number of producer warps: warps 0 and 3 plus (nprod - 2) extra warps after the epilogue warps
   int seg_cin[2], seg_cstride[2];  // for the cp.async producer: real channels / channel stride of each input
   const void* x[2];                // ... and the input tensors themselves
   int pair;  // cta_group::2 CTA pairs with resident half weight tiles, one accumulator per tile (conv_nfold.cu)

@@ -501,7 +501,11 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   // (~5.5 cycles per <=128-byte box row per SM) stays the bound of that layer. Kept behind MPG_NFOLD_CPASYNC=1 (parity
   // tested) for swizzled layouts with resident weights, where warp 3 is free to be the second producer warp.
   q.a_cpasync = 0;
-  if (const char* e = getenv("MPG_NFOLD_CPASYNC")) q.a_cpasync = (!ns8 && q.bres && atoi(e) != 0) ? 1 : 0;
+  q.nprod = 2;
+  if (const char* e = getenv("MPG_NFOLD_CPASYNC")) {
+    q.a_cpasync = (!ns8 && q.bres && atoi(e) != 0) ? 1 : 0;
+    if (atoi(e) >= 4 && atoi(e) <= 8 && atoi(e) % 2 == 0) q.nprod = atoi(e);  // 4 / 6 / 8 producer warps
+  }
   for (int s = 0; s < d.nseg; ++s) {
     q.seg_cin[s] = d.seg_cin[s];
     q.seg_cstride[s] = d.seg_cstride[s];
@@ -515,6 +519,10 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   if (q.pair) occ = 1;
   q.threads = (occ == 1) ? kNfMaxThreads : kNfThreads;
   if (const char* e = getenv("MPG_NFOLD_THREADS")) q.threads = atoi(e) == 384 ? 384 : 256;
+  if (q.a_cpasync && q.nprod > 2) {
+    if (occ != 1) q.nprod = 2;  // the extra producer warps need the registers of a one-CTA-per-SM launch
+    else q.threads += 32 * (q.nprod - 2);
+  }
   const int budget = (210 * 1024) / occ - (occ > 1 ? 2048 : 0);
   int nb;
   if (q.bres) {
