@@ -48,7 +48,8 @@ def build(force=False, verbose=False):
             if fh.read().strip() == dig:
                 return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
+    extra = os.environ.get("MPG_NVCC_EXTRA", "").split()  # experiments only (e.g. -DMPG_RB_MT2=2); not part of the stamp
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -51,6 +51,14 @@ constexpr int kIH = kTH + 2 * (kKS - 1);
 constexpr int kMW = kTW + (kKS - 1);      // 36: window of the intermediate
 constexpr int kMH = kTH + (kKS - 1);
 constexpr int kThreads = 256;
+#ifndef MPG_RB_MT2
+#define MPG_RB_MT2 4
+#endif
+#ifndef MPG_RB_OCC
+#define MPG_RB_OCC 2
+#endif
+constexpr int kRbMT2 = MPG_RB_MT2;  // 4: two image rows per pass (64 accumulator registers), 2: one row (32)
+constexpr int kRbOcc = MPG_RB_OCC;  // CTAs per SM the register budget is sized for
 
 struct RbParams {
   const void* x;
@@ -101,7 +109,8 @@ __device__ __forceinline__ float act_apply(float x, float ca, float cb) { return
 // CPP: 16-bit channels per pixel of the staged input (4: <= 4 input channels, fp32 source; 8: <= 8, 16-bit source)
 // NT2: 8-column MMA tiles of the block output (4: 32 channels, 16-bit output; 1: <= 8 channels)
 template <int CPP, int NT2, bool BF16, bool IN_F32, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbParams p) {
+__global__ void __launch_bounds__(kThreads, kRbOcc) resblock_thin_kernel(const RbParams p) {
+  constexpr int MT2 = kRbMT2;  // m-tiles (16 pixels each) a warp accumulates at once in stage 2
   constexpr int KS1 = (kTaps * CPP + 15) / 16;  // K steps of convA: 7 (4 taps per step) or 13 (2 taps per step)
   constexpr int KS2 = (kTaps + 1) / 2;          // 13: two taps x 8 channels per step
   constexpr int IN_PX = CPP * 2;                // bytes per staged input pixel
@@ -249,11 +258,11 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
 
     // ---------------- stage 2: convB + 1x1 shortcut; warp = 4 image rows, two passes of 2 rows x 2 halves (4 m-tiles)
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int y0 = warp * 4 + pass * 2;  // first of the two tile rows of this pass
-      float acc[4][NT2][4];
+    for (int pass = 0; pass < 8 / MT2; ++pass) {
+      const int y0 = warp * 4 + pass * (MT2 / 2);  // first tile row of this pass (MT2/2 rows x 2 halves)
+      float acc[MT2][NT2][4];
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < MT2; ++m)
 #pragma unroll
         for (int nt = 0; nt < NT2; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
       // ldmatrix row address of this lane inside m-tile 0 of the pass: pixel x = (l & 7) + 8 * ((l >> 3) & 1)
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
         for (int nt = 0; nt < NT2; ++nt) bf[nt] = lds64(a_w + WA_BYTES + ((ks * NT2 + nt) * 32 + lane) * 8);
         const uint32_t toff = (hi ? tap_off(2 * ks + 1, kMW) : tap_off(2 * ks, kMW)) * 16;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < MT2; ++m) {
           uint32_t a[4];
           ldmatrix_x4(a, lbase + toff + ((m >> 1) * kMW + (m & 1) * 16) * 16);
 #pragma unroll
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
 #pragma unroll
         for (int nt = 0; nt < NT2; ++nt) bf[nt] = lds64(a_w + WA_BYTES + WB_BYTES + (nt * 32 + lane) * 8);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
+        for (int m = 0; m < MT2; ++m) {
           const int yy = y0 + (m >> 1) + (kKS - 1), xx = (m & 1) * 16 + (kKS - 1);
           uint32_t a[4] = {0u, 0u, 0u, 0u};
           if (CPP == 8 || t < 2) {
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 2) resblock_thin_kernel(const RbPara
       }
       // epilogue: lane (g, t) holds GEMM columns (nt, 2t + e) of rows g and g+8 = channels 8t + 2nt + e (NT2 == 4)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
+      for (int m = 0; m < MT2; ++m) {
         const int gy = ty0 + y0 + (m >> 1);
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -463,7 +472,7 @@ int mpg_resblock_plan_create(mpg_handle h, const mpg_resblock_desc* dsc, const f
   }
   p->smem_bytes = static_cast<size_t>(kIH) * kIW * cpp * 2 + static_cast<size_t>(kMH) * kMW * 16 + blob.size();
   const int tiles = ceil_div(d.w, kTW) * ceil_div(d.h, kTH) * d.n;
-  p->grid = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
+  p->grid = tiles < kRbOcc * h->sm_count ? tiles : kRbOcc * h->sm_count;
   e = cudaFuncSetAttribute(rb_kernel(cpp, nt2, bf16, in_f32, out_f32), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(p->smem_bytes));  // per device and per instance; plan creation is not a hot path
   if (e != cudaSuccess) {
