@@ -482,17 +482,16 @@ def run_ours(args):
     # denominator: the driver-measured cuBLAS bf16 BURST figure - the kernel sustains more than the 4-s
     # "sustained" cuBLAS number inside the step, so the stricter (larger) peak is the honest one
     peak = peaks["tflops"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01b_dominant_kernels.json")
-    if os.path.exists(tpath):  # ncu --set full capture of the current build (dram__bytes_read.sum + dram__bytes_write.sum)
-        with open(tpath) as fh:
-            k0 = json.load(fh)["kernels"][0]
-            traffic = int(k0["dram_bytes_read"] + k0["dram_bytes_write"])
-    else:
-        tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic_pair.json")
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the latest committed `ncu --set full` capture
+    # of this build (it cannot be measured inside an un-profiled run); the source file is named in the line
+    traffic, traffic_src = None, None
+    for name in ("r02_dominant_kernels.json", "r01b_dominant_kernels.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+                k0 = json.load(fh)["kernels"][0]
+            traffic, traffic_src = int(k0["dram_bytes_read"] + k0["dram_bytes_write"]), "profiles/" + name
+            break
     # the bandwidth-bound kernels of the step: the two axis changes (transpose3d + fused threshold), 2 * S^3 * 4 B each
     bw = None
     if pass_ms and world == 1:
@@ -533,7 +532,7 @@ def run_ours(args):
                       unit="TFLOP/s", frac=achieved / peak, frac_of_sustained=achieved / peaks["tflops_sustained"],
                       peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops); fp16 operands run at the same kind::f16 rate",
                       flops_per_launch=dom_flops, avg_launch_ms=kern_avg_ms, launches_timed=len(kern_ms),
-                      share_of_step=kern_share, traffic=traffic),
+                      share_of_step=kern_share, traffic=traffic, traffic_source=traffic_src),
         clocks=clocks,
     )
     if secondary:
