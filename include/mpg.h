@@ -92,6 +92,16 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* d, const float* w_se
                          const float* shift, mpg_conv_plan* out);
 int mpg_conv_plan_run(mpg_conv_plan p, const void* x_seg0, const void* x_seg1, void* y,
                       void* stream);
+/* Cross-launch shortcut fusion (the 1x1 shortcut conv of the NEXT residual block reads this conv's whole output: for ru3 of
+ * gen_resnet, GAN/multipassGAN-4x.py:521,563, that is a 537 MB re-read of the 128-channel tensor per slice batch):
+ * mpg_conv_plan_set_side gives a 128-channel tcgen05 plan a SIDE output y_side[n,h,w,8] (fp32) = y x w_side, computed in the
+ * epilogue from the fp32 values while they are in registers (w_side: HOST fp32 [128][side_cout], the shortcut's weight with
+ * wscale / BN scale folded; side_cout <= 8); the consumer (a tap-folded plan with <= 8 output channels, built WITHOUT the
+ * shortcut segment) adds it through `residual` before its activation. MPG_ENOSUP when the plan cannot carry a side output
+ * (the caller keeps the two-segment form). */
+int mpg_conv_plan_set_side(mpg_conv_plan p, const float* w_side, int side_cout);
+int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x_seg0, const void* x_seg1, void* y, float* y_side,
+                         const float* residual, void* stream);
 int mpg_conv_plan_destroy(mpg_conv_plan p);
 /* Training: refresh the packed weights / shift of a tcgen05 plan (force_kind 1) from DEVICE fp32 HWIO tensors,
  * stream ordered. mode 0: w_seg is this conv's weight; mode 1: w_seg is the weight of the FORWARD conv whose

@@ -96,6 +96,8 @@ def lib():
     L.mpg_sm_count.argtypes = [vp]
     L.mpg_conv_plan_create.argtypes = [vp, ctypes.POINTER(ConvDesc), fp, fp, fp, fp, fp, ctypes.POINTER(vp)]
     L.mpg_conv_plan_run.argtypes = [vp, vp, vp, vp, vp]
+    L.mpg_conv_plan_set_side.argtypes = [vp, fp, ip]
+    L.mpg_conv_plan_run_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.mpg_conv_plan_destroy.argtypes = [vp]
     L.mpg_conv_plan_update.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     L.mpg_conv_plan_kind.argtypes = [vp]
@@ -246,6 +248,16 @@ class ConvPlan:
         p1 = None if x1 is None else (x1.data_ptr() if hasattr(x1, "data_ptr") else int(x1))
         py = y.data_ptr() if hasattr(y, "data_ptr") else int(y)
         check(lib().mpg_conv_plan_run(self._p, p0, p1, py, stream), "mpg_conv_plan_run")
+
+    def set_side(self, w_side):
+        """Give the plan a side output y_side = y x w_side (w_side: float32 [cout, side_cout], scales folded)."""
+        w = _f32c(w_side)
+        check(lib().mpg_conv_plan_set_side(self._p, _fptr(w), int(w.shape[1])), "mpg_conv_plan_set_side")
+        self.has_side = True
+
+    def run_ex(self, x0, x1, y, y_side=None, residual=None, stream=0):
+        check(lib().mpg_conv_plan_run_ex(self._p, _ptr(x0), _ptr(x1), _ptr(y), _ptr(y_side), _ptr(residual), stream),
+              "mpg_conv_plan_run_ex")
 
     def update(self, w0, w1=None, mode0=0, mode1=0, shift=None, stream=0):
         """Refresh the packed weights from device fp32 HWIO tensors (training; tcgen05 plans only)."""

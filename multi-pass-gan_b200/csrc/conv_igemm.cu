@@ -52,7 +52,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const IgemmParams& p) {
 // accumulators, epilogue) but holds only HALF of every weight tile; the leader issues M=256 MMAs that read both
 // halves, so the L2->SM weight traffic per SM halves (measured: an SM ingests ~27 B/clk from L2, which bounds
 // the single-CTA kernel at 970 KB per tile vs 26 K MMA cycles).
-template <int CK, bool PAIR>
+template <int CK, bool PAIR, bool SIDE>
 __global__ void __launch_bounds__(kIgMaxThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
@@ -340,6 +340,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const int cend = (warp >= 8) ? p.npad : csplit;
     const bool st32 = (p.out_cstride % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) && !(p.dbg & 8);
     uint8_t* stg = smem + p.stage_off + static_cast<size_t>(warp - 4) * 4096;  // TMA-store staging of this warp
+    // side output: weights [128][8] and the partial-sum exchange between the two warps of a lane quarter
+    const float4* s_sw = reinterpret_cast<const float4*>(smem + p.side_off);
+    float4* s_sx = reinterpret_cast<float4*>(smem + p.side_off + 4096);
+    if (SIDE && p.side) {
+      for (int i = threadIdx.x - 128; i < 256; i += static_cast<int>(blockDim.x) - 128)
+        reinterpret_cast<float4*>(smem + p.side_off)[i] = reinterpret_cast<const float4*>(p.side_w)[i];
+      asm volatile("bar.sync 5, 256;" ::: "memory");  // the 8 epilogue warps
+    }
     int it = 0;
     for (int t = tfirst; t - static_cast<int>(rank) < p.num_tiles; t += tstep, ++it) {
       const int buf = it & 1;
@@ -377,6 +385,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           // store instruction (the 32->128 layer was bound by those: epilogue alone 0.28 ms vs 0.24 ms of MMAs).
           // No block barrier is involved (the earlier staged variant needed two per tile and lost).
           const int od = p.out_dtype;
+          float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           for (int cg = cbeg; cg < cend; cg += 64) {
             if (lane == 0) tma_store_wait_read();  // the previous store of this warp has finished reading the staging
             __syncwarp();
@@ -389,6 +398,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
               if (p.pixel_norm) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] *= rn;
+              }
+              if (SIDE && p.side) {  // 1x1 shortcut of the next block: 16 channels x 8 outputs from registers, weights broadcast
+                const float4* wq = s_sw + (cg + q4 * 16) * 2;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float4 w0 = wq[2 * j], w1 = wq[2 * j + 1];
+                  sacc[0] = fmaf(v[j], w0.x, sacc[0]);
+                  sacc[1] = fmaf(v[j], w0.y, sacc[1]);
+                  sacc[2] = fmaf(v[j], w0.z, sacc[2]);
+                  sacc[3] = fmaf(v[j], w0.w, sacc[3]);
+                  sacc[4] = fmaf(v[j], w1.x, sacc[4]);
+                  sacc[5] = fmaf(v[j], w1.y, sacc[5]);
+                  sacc[6] = fmaf(v[j], w1.z, sacc[6]);
+                  sacc[7] = fmaf(v[j], w1.w, sacc[7]);
+                }
               }
               uint4 lo, hi;
               lo.x = pack_h16x2(v[0], v[1], od);
@@ -405,6 +429,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
+            if (SIDE && p.side && cg + 64 >= cend) {
+              // fold the two column halves (warps w and w+4 of this lane quarter) and store 8 fp32 per pixel
+              if (epi_active == 8) {
+                if (warp >= 8) {
+                  s_sx[2 * m] = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+                  s_sx[2 * m + 1] = make_float4(sacc[4], sacc[5], sacc[6], sacc[7]);
+                }
+                quarter_pair_sync(ew);
+                if (warp < 8) {
+                  const float4 a = s_sx[2 * m], b = s_sx[2 * m + 1];
+                  sacc[0] += a.x; sacc[1] += a.y; sacc[2] += a.z; sacc[3] += a.w;
+                  sacc[4] += b.x; sacc[5] += b.y; sacc[6] += b.z; sacc[7] += b.w;
+                }
+                quarter_pair_sync(ew);  // the exchange buffer is free for the next accumulator
+              }
+              if (warp < 8 && valid) {
+                float4* so = reinterpret_cast<float4*>(p.side_out + ((static_cast<size_t>(tc.n) * p.h + y) * p.w + x) * 8);
+                so[0] = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+                so[1] = make_float4(sacc[4], sacc[5], sacc[6], sacc[7]);
+              }
+            }
             if (lane == 0 && t < p.num_tiles && !(p.dbg & 1)) {
               if (ups == 1) {
                 tma_store_4d(&tm_y, stg, cg, tc.x0 + acc * 8, tc.y0 + ew * 4, tc.n);
@@ -494,21 +539,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
 typedef void (*IgKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams);
 
-static IgKernel ig_kernel(int ck, int pair) {
-  if (pair) return ck == 64 ? conv_igemm_kernel<64, true> : (ck == 32 ? conv_igemm_kernel<32, true> : conv_igemm_kernel<16, true>);
-  return ck == 64 ? conv_igemm_kernel<64, false> : (ck == 32 ? conv_igemm_kernel<32, false> : conv_igemm_kernel<16, false>);
+static IgKernel ig_kernel(int ck, int pair, int side = 0) {
+  // SIDE (epilogue side output, mpg_conv_plan_set_side) is its own instantiation: its 8 extra accumulators and weight
+  // registers must not cost the two-CTAs-per-SM layers their occupancy
+  if (side) return conv_igemm_kernel<64, true, true>;
+  if (pair) return ck == 64 ? conv_igemm_kernel<64, true, false> : (ck == 32 ? conv_igemm_kernel<32, true, false> : conv_igemm_kernel<16, true, false>);
+  return ck == 64 ? conv_igemm_kernel<64, false, false> : (ck == 32 ? conv_igemm_kernel<32, false, false> : conv_igemm_kernel<16, false, false>);
 }
 
 // The attribute is per kernel instantiation AND per device (cudaFuncSetAttribute applies to the current device only):
 // only ever raise it, and remember what each device has.
-static size_t g_smem_attr[kMaxDevices][6] = {};
+static size_t g_smem_attr[kMaxDevices][7] = {};
 
-int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes) {
-  const int slot = (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (pair ? 3 : 0);
+int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes, int side) {
+  const int slot = side ? 6 : (ck == 64 ? 0 : (ck == 32 ? 1 : 2)) + (pair ? 3 : 0);
   const bool cached = device >= 0 && device < kMaxDevices;
   if (cached && smem_bytes <= g_smem_attr[device][slot]) return 0;
   DeviceGuard guard(device);
-  cudaError_t e = cudaFuncSetAttribute(ig_kernel(ck, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(ig_kernel(ck, pair, side), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
   if (e == cudaSuccess && cached) g_smem_attr[device][slot] = smem_bytes;
   return static_cast<int>(e);
@@ -533,7 +581,7 @@ int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, ig_kernel(ck, 1), tm_x0, tm_x1, tm_w, tm_y, p));
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, ig_kernel(ck, 1, p.side), tm_x0, tm_x1, tm_w, tm_y, p));
 }
 
 }  // namespace mpg

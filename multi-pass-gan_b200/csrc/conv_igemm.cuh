@@ -50,11 +50,17 @@ struct IgemmParams {
   uint32_t tmem_cols;
   const float* shift;  // [npad] device
   void* out;
+  // side output (mpg_conv_plan_set_side): side_out[pix][0..7] = sum_c y[pix][c] * side_w[c][0..7], the 1x1 shortcut of the NEXT
+  // residual block computed from the fp32 epilogue values while they are in registers (TMA-store epilogue, 8 epilogue warps).
+  // side_off: dynamic smem offset of 4 KB weights [128][8] + 4 KB partial-sum exchange
+  int side, side_off;
+  const float* side_w;  // device [128][8] fp32
+  float* side_out;      // [n,h,w,8] fp32
 };
 
 // ck in {16, 32, 64}; returns cudaError_t as int
 int igemm_launch(int ck, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const CUtensorMap& tm_w,
                  const CUtensorMap& tm_y, const IgemmParams& p, int grid, size_t smem_bytes, cudaStream_t stream);
-int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes);
+int igemm_set_smem_attr(int device, int ck, int pair, size_t smem_bytes, int side = 0);
 
 }  // namespace mpg

@@ -413,6 +413,13 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                                static_cast<uint32_t>((buf * p.naccs + acc) * p.npad);
         float o[32];
         float ssq = 0.0f;
+        float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (p.resid != nullptr && valid) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + ((static_cast<size_t>(tc.n) * p.h + y) * p.w + gx) * 8);
+          const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          rs[0] = r0.x; rs[1] = r0.y; rs[2] = r0.z; rs[3] = r0.w;
+          rs[4] = r1.x; rs[5] = r1.y; rs[6] = r1.z; rs[7] = r1.w;
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunks && (all_chunks || (c & 1) == cgrp)) {
@@ -429,7 +436,7 @@ conv_nfold_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
               float a = t[0];
 #pragma unroll
               for (int dx = 1; dx < KS; ++dx) a += t[dx];
-              const float x = a + s_shift[c * 8 + j];
+              const float x = a + s_shift[c * 8 + j] + (c == 0 ? rs[j] : 0.0f);
               const float v = is_relu ? fmaxf(x, 0.0f) : fmaf(act_b, fabsf(x), act_a * x);
               o[c * 8 + j] = v;
               ssq = fmaf(v, v, ssq);

@@ -50,6 +50,8 @@ struct NfoldParams {
   int nprod;      // ... number of producer warps: warps 0 and 3 plus (nprod - 2) extra warps after the epilogue warps
   int seg_cin[2], seg_cstride[2];  // for the cp.async producer: real channels / channel stride of each input
   const void* x[2];                // ... and the input tensors themselves
+  const float* resid;  // optional fp32 [n,h,w,8] tensor added before the activation (cout <= 8): the block's 1x1 shortcut
+                       // computed by the producer of its input (mpg_conv_plan_set_side)
   int pair;  // cta_group::2 CTA pairs with resident half weight tiles, one accumulator per tile (conv_nfold.cu)
   int threads;  // launch block size: 256 or 384
   int dbg;  // profiling only (env MPG_NFOLD_DBG): bit0 skip stores, bit1 skip the whole epilogue body, bit2 skip MMAs

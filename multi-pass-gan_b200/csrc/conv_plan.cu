@@ -31,6 +31,7 @@ struct mpg_conv_plan_s {
   mpg::IgemmParams ip;
   size_t smem_bytes;
   int grid;
+  float* d_side_w;  // igemm side output (mpg_conv_plan_set_side): [128][8] fp32
   // ---- direct
   float* d_wdirect;
   mpg::DirectParams dp;
@@ -726,8 +727,51 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   return MPG_OK;
 }
 
+int mpg_conv_plan_set_side(mpg_conv_plan p, const float* w_side, int side_cout) {
+  MPG_CHECK_ARG(p && w_side && side_cout >= 1, "mpg_conv_plan_set_side: bad argument");
+  const mpg::IgemmParams& ip = p->ip;
+  if (p->kind != 1 || !ip.tma_store || !ip.pair || p->ck != 64 || ip.threads != mpg::kIgMaxThreads || ip.npad != 128 || p->d.cout != 128 || ip.pixel_norm ||
+      ip.upsample != 1 || side_cout > 8) {
+    mpg::set_error("conv: a side output needs a 128-channel tcgen05 plan with the per-warp TMA-store epilogue (8 epilogue warps, no "
+                   "pixel_norm / upsample) and <= 8 side channels");
+    return MPG_ENOSUP;
+  }
+  const size_t need = static_cast<size_t>(ip.stage_off) + static_cast<size_t>(ip.stage_bytes) + 8192 + 1024;
+  if (need > 227 * 1024) {
+    mpg::set_error("conv: no shared memory left for the side output (%zu B)", need);
+    return MPG_ENOSUP;
+  }
+  mpg::DeviceGuard guard(p->h->device);
+  std::vector<float> w(128 * 8, 0.0f);
+  for (int c = 0; c < 128; ++c)
+    for (int k = 0; k < side_cout; ++k) w[c * 8 + k] = w_side[static_cast<size_t>(c) * side_cout + k];
+  if (!p->d_side_w) MPG_CUDA(cudaMalloc(&p->d_side_w, w.size() * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_side_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->ip.side = 1;
+  p->ip.side_off = ip.stage_off + ip.stage_bytes;
+  p->ip.side_w = p->d_side_w;
+  p->smem_bytes = need;
+  int r = mpg::igemm_set_smem_attr(p->h->device, p->ck, ip.pair, p->smem_bytes, 1);
+  if (r) {
+    mpg::set_error("cudaFuncSetAttribute(max dynamic smem %zu) failed: %s", p->smem_bytes, cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  return MPG_OK;
+}
+
 int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, void* stream) {
+  return mpg_conv_plan_run_ex(p, x0, x1, y, nullptr, nullptr, stream);
+}
+
+int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* y, float* y_side, const float* residual,
+                         void* stream) {
   MPG_CHECK_ARG(p && x0 && y, "mpg_conv_plan_run: null argument");
+  MPG_CHECK_ARG((y_side != nullptr) == (p->kind == 1 && p->ip.side != 0), "conv: y_side must be given exactly when the plan has a side output");
+  MPG_CHECK_ARG(y_side == nullptr || (reinterpret_cast<uintptr_t>(y_side) & 15) == 0, "conv: y_side not 16-byte aligned");
+  if (residual != nullptr) {
+    MPG_CHECK_ARG(p->kind == 3 && p->d.cout <= 8 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                  "conv: an fp32 residual input needs a tap-folded plan with <= 8 output channels and a 16-byte aligned tensor");
+  }
   MPG_CHECK_ARG(p->d.nseg == 1 || x1 != nullptr, "mpg_conv_plan_run: segment 1 input missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mpg::DeviceGuard guard(p->h->device);  // the plan's device, whatever the caller's current device is
@@ -753,6 +797,7 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
     mpg::IgemmParams ip = p->ip;
     ip.out = y;
+    ip.side_out = y_side;
     if (ip.tma_store && p->tm_y_ptr != y) {
       // per-warp store box: 64 channels x 8 px x 4 image rows, 128B-swizzled staging
       const CUtensorMapDataType dt = d.out_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -814,6 +859,7 @@ int mpg_conv_plan_run(mpg_conv_plan p, const void* x0, const void* x1, void* y, 
     q.out = y;
     q.x[0] = x0;
     q.x[1] = x1;
+    q.resid = residual;
     int r = mpg::nfold_launch(p->ck, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], p->tm_w, q, p->grid,
                               p->smem_bytes, st);
     if (r) {
@@ -893,6 +939,7 @@ int mpg_conv_plan_destroy(mpg_conv_plan p) {
   if (p->d_wpacked) cudaFree(p->d_wpacked);
   if (p->d_shift) cudaFree(p->d_shift);
   if (p->d_wdirect) cudaFree(p->d_wdirect);
+  if (p->d_side_w) cudaFree(p->d_side_w);
   delete p;
   return MPG_OK;
 }

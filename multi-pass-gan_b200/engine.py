@@ -259,6 +259,24 @@ class CompiledNet:
                     rb_of_a[id(ga)] = gb
                     rb_of_b[id(gb)] = ga
 
+        # ---- the 1x1 shortcut of a block whose input is a 128-channel tcgen05 conv output is computed in THAT conv's epilogue
+        #      (mpg_conv_plan_set_side) and added by the consumer as an fp32 residual: removes the re-read of the 128-channel
+        #      tensor (537 MB per slice batch for ru3 of gen_resnet, GAN/multipassGAN-4x.py:521,563)
+        self._side_of = {}   # id(producer group) -> (consumer group, shortcut conv)
+        self._side_buf = {}  # id(consumer group) -> fp32 [n,h,w,8] side tensor, once the producer was emitted with it
+        if self.precision != "fp32" and int(os.environ.get("MPG_FUSE_SHORTCUT", "1")):
+            for gx in groups_by_out.values():
+                if len(gx.convs) != 2 or gx.pn or gx.ups != 1 or id(gx) in rb_of_b:
+                    continue
+                c5, cs = sorted(gx.convs, key=lambda c: -c.attrs["ksize"])
+                if c5.attrs["ksize"] not in (3, 5) or cs.attrs["ksize"] != 1 or cs.out.shape[3] > 8:
+                    continue
+                gp = groups_by_out.get(cs.inputs[0].node.id)
+                if (gp is None or gp.pn or gp.ups != 1 or gp.convs[0].out.shape[3] != 128 or id(gp) in self._side_of
+                        or id(gp) in rb_of_b or id(gp) in rb_of_a):
+                    continue
+                self._side_of[id(gp)] = (gx, cs)
+
         views = {}
         for n in nodes:
             if n.id in groups_by_out:
@@ -392,14 +410,17 @@ class CompiledNet:
     def _emit_group(self, grp, views):
         convs = sorted(grp.convs, key=lambda c: -c.attrs["ksize"])
         first = convs[0]
+        resid = self._side_buf.get(id(grp))  # the shortcut of this block was computed by the producer of its input
         ws, scs, shift_total, ins = [], [], None, []
         any_scale = False
         for c in convs:
             w_eff, sc, sh = self._conv_affine(c)
+            shift_total = sh if shift_total is None else shift_total + sh
+            if resid is not None and c is not first:
+                continue  # its weights live in the producer's epilogue; only the folded offset stays here
             ws.append(w_eff)
             scs.append(sc)
             any_scale = any_scale or sc is not None
-            shift_total = sh if shift_total is None else shift_total + sh
             ins.append(self._materialize(views[c.inputs[0].node.id], self.act_dtype))
         cout = first.out.shape[3]
         ih, iw = first.inputs[0].shape[1], first.inputs[0].shape[2]
@@ -412,26 +433,60 @@ class CompiledNet:
         self.flops += flops
         x0 = ins[0]
         x1 = ins[1] if len(ins) > 1 else None
+        side = None
         if self.dry:
-            plan, kind = None, self._predict_kind(convs, ins, cout, out_dtype, stride, grp.ups, out.cstride, grp.act)
+            plan, kind = None, self._predict_kind(convs if resid is None else convs[:1], ins, cout, out_dtype, stride, grp.ups,
+                                                  out.cstride, grp.act)
         else:
-            plan = capi.ConvPlan(self.h, self.batch, ih, iw, ws, [b.cstride for b in ins], cout, out.cstride,
-                                 act=grp.act, scales=scs if any_scale else None, shift=shift_total,
-                                 pixel_norm=grp.pn, upsample=grp.ups, stride=stride, in_dtype=self.act_dtype,
-                                 out_dtype=out_dtype)
+            def make(ws_, scs_, ins_):
+                return capi.ConvPlan(self.h, self.batch, ih, iw, ws_, [b.cstride for b in ins_], cout, out.cstride,
+                                     act=grp.act, scales=scs_ if any(sc_ is not None for sc_ in scs_) else None,
+                                     shift=shift_total, pixel_norm=grp.pn, upsample=grp.ups, stride=stride,
+                                     in_dtype=self.act_dtype, out_dtype=out_dtype)
+
+            plan = make(ws, scs, ins)
+            if resid is not None and not (plan.kind == capi.KIND_NFOLD and cout <= 8):
+                # the consumer kernel cannot add a residual: back to the two-segment form (the side tensor stays unused)
+                plan.close()
+                resid = None
+                ws, scs, ins = [], [], []
+                for c in convs:
+                    w_eff, sc, _ = self._conv_affine(c)
+                    ws.append(w_eff)
+                    scs.append(sc)
+                    ins.append(self._materialize(views[c.inputs[0].node.id], self.act_dtype))
+                x0, x1 = ins[0], (ins[1] if len(ins) > 1 else None)
+                plan = make(ws, scs, ins)
             self.plans.append(plan)
             kind = plan.kind
-            assert abs(plan.flops - flops) < 1e-6 * flops
+            if id(grp) in self._side_of:
+                gx, cs = self._side_of[id(grp)]
+                w_s, sc_s, _ = self._conv_affine(cs)  # [1,1,128,k]; its offset is added by the consumer
+                w_side = w_s[0, 0] * (sc_s[None, :] if sc_s is not None else 1.0)
+                try:
+                    plan.set_side(w_side.astype(np.float32))
+                    side = self._alloc(oh, ow, 8, capi.F32, cstride=8)
+                    self._side_buf[id(gx)] = side
+                except capi.MpgError:
+                    side = None  # this plan cannot carry a side output: the consumer keeps its shortcut segment
 
         def step(stream):
-            plan.run(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out), stream)
+            if side is None and resid is None:
+                plan.run(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out), stream)
+            else:
+                plan.run_ex(self._p(x0), self._p(x1) if x1 is not None else None, self._p(out),
+                            y_side=self._p(side) if side is not None else None,
+                            residual=self._p(resid) if resid is not None else None, stream=stream)
 
-        label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s" % (
+        if x1 is not None and resid is not None:
+            x1 = None
+        label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s%s%s" % (
             {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf", capi.KIND_TINY: "ct"}.get(kind, "cc"),
             "+".join(c.attrs["weight"]["var"].name.rsplit("/", 2)[-2] for c in convs),
             "/".join(str(c.attrs["ksize"]) for c in convs),
             "/".join(str(c.inputs[0].shape[3]) for c in convs), cout, ih, iw,
-            " " + grp.act if grp.act else "", " pn" if grp.pn else "", " up2" if grp.ups == 2 else "")
+            " " + grp.act if grp.act else "", " pn" if grp.pn else "", " up2" if grp.ups == 2 else "",
+            " +side8" if side is not None else "", " (shortcut via residual)" if resid is not None else "")
         if self.verbose:
             print(label)
         self.step_flops[len(self.steps)] = flops

@@ -98,3 +98,61 @@ def test_nfold_cp_async_producer_variant(name, monkeypatch):
     r = run_case(**kw)
     assert r["finite"] and r["pad_ok"] and r["kind"] == 3, r
     assert r["rel_l2"] < 8e-4, (name, r)
+
+
+def test_side_output_and_residual_equal_the_two_segment_form():
+    """Cross-launch shortcut fusion (mpg_conv_plan_set_side / mpg_conv_plan_run_ex): a 128-channel tcgen05 conv also emits
+    y_side = y x W_s (fp32, 8 channels) from its epilogue, and the next block's tap-folded conv adds it as a residual instead
+    of re-reading the 128-channel tensor through a 1x1 shortcut segment. Checked against fp64 math on the same operands and
+    against the unfused two-segment plan (the results agree to the rounding of the 16-bit intermediate)."""
+    import numpy as np
+    import torch
+    from mpgan_b200 import capi
+    from convref import ref_conv
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 2, 48, 80
+    hd = capi.default_handle(0)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(n, h, w, 128, generator=g).to(torch.float16).to(dev)
+    xs = torch.randn(n, h, w, 32, generator=g).to(torch.float16).to(dev)
+    wp = (torch.randn(5, 5, 128, 128, generator=g) * (np.sqrt(2.0) / np.sqrt(3200))).numpy()
+    wps = (torch.randn(1, 1, 32, 128, generator=g) * (np.sqrt(2.0) / np.sqrt(32))).numpy()
+    shp = (torch.randn(128, generator=g) * 0.1).numpy()
+    ws_next = (torch.randn(1, 1, 128, 8, generator=g) * (np.sqrt(2.0) / np.sqrt(128))).numpy()
+    producer = capi.ConvPlan(hd, n, h, w, [wp, wps], [128, 32], 128, 128, act="relu", shift=shp, in_dtype=capi.F16, out_dtype=capi.F16)
+    assert producer.kind == capi.KIND_TCGEN05
+    producer.set_side(ws_next[0, 0])
+    y = torch.empty(n, h, w, 128, dtype=torch.float16, device=dev)
+    side = torch.full((n, h, w, 8), float("nan"), dtype=torch.float32, device=dev)
+    producer.run_ex(x, xs, y, y_side=side, stream=st)
+    with pytest.raises(capi.MpgError):
+        producer.run(x, xs, y, st)  # a plan with a side output must be given the side tensor
+    torch.cuda.synchronize()
+    yref = ref_conv([x.float(), xs.float()], [wp, wps], [None, None], shp, "relu", False, 1, round_w=torch.float16)
+    assert float(torch.linalg.norm(y.double() - yref) / torch.linalg.norm(yref)) < 8e-4
+    side_ref = torch.einsum("nhwc,ck->nhwk", yref, torch.from_numpy(ws_next[0, 0]).double().to(dev))
+    rel = float(torch.linalg.norm(side.double() - side_ref) / torch.linalg.norm(side_ref))
+    assert torch.isfinite(side).all() and rel < 2e-5, rel  # fp32 values straight from the accumulators
+    # consumer: 5x5 32->8 (+ the 1x1 128->8 shortcut): residual form vs two-segment form
+    x32 = torch.randn(n, h, w, 32, generator=g).to(torch.float16).to(dev)
+    w5 = (torch.randn(5, 5, 32, 8, generator=g) * (np.sqrt(2.0) / np.sqrt(800))).numpy()
+    shc = (torch.randn(8, generator=g) * 0.1).numpy()
+    fused = capi.ConvPlan(hd, n, h, w, [w5], [32], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16)
+    assert fused.kind == capi.KIND_NFOLD
+    o1 = torch.empty(n, h, w, 8, dtype=torch.float16, device=dev)
+    fused.run_ex(x32, None, o1, residual=side, stream=st)
+    two = capi.ConvPlan(hd, n, h, w, [w5, ws_next], [32, 128], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16)
+    o2 = torch.empty(n, h, w, 8, dtype=torch.float16, device=dev)
+    two.run(x32, y, o2, st)
+    torch.cuda.synchronize()
+    want = torch.relu(ref_conv([x32.float()], [w5], [None], shc, None, False, 1, round_w=torch.float16) + side_ref)
+    for got in (o1, o2):
+        assert float(torch.linalg.norm(got.double() - want) / torch.linalg.norm(want)) < 1.5e-3
+    for pl in (producer, fused, two):
+        pl.close()
+    # plans that cannot carry a side output say so
+    small = capi.ConvPlan(hd, 1, 32, 32, [np.zeros((3, 3, 64, 64), np.float32)], [64], 64, 64, in_dtype=capi.F16, out_dtype=capi.F16)
+    with pytest.raises(capi.MpgError):
+        small.set_side(np.zeros((64, 8), np.float32))
+    small.close()
