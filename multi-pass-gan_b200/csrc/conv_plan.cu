@@ -10,12 +10,16 @@
 #include "conv_igemm.cuh"
 #include "conv_nfold.cuh"
 #include "conv_tiny.cuh"
+#include "conv_vfold.cuh"
 
 struct mpg_conv_plan_s {
   mpg_handle h;
   mpg_conv_desc d;
-  int kind;  // 1 igemm, 2 direct, 3 tap-folded igemm (narrow Cout), 4 CUDA-core tiny (Cout <= 2, Cin <= 8)
+  int kind;  // 1 igemm, 2 direct, 3 tap-folded igemm (narrow Cout), 4 CUDA-core tiny (Cout <= 2, Cin <= 8),
+             // 5 row-streaming igemm with the vertical taps folded into N (conv_vfold.cu)
   mpg::NfoldParams np;
+  mpg::VfoldParams vp;
+  int vf_nchw;
   double flops;
   int oh, ow;
   // ---- igemm
@@ -563,6 +567,194 @@ int build_nfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   return 0;
 }
 
+// ---- row-streaming kernel with the vertical taps folded into N (conv_vfold.cu) ----
+struct VfGeom {
+  int ck, cp, npad, nchunks, groups, nchw, n_sc, sc_col;
+  int seg_nchunk[2], seg_klast[2];
+  int b_tile_bytes, b_sc_tile_bytes, b_bytes, a_stage_bytes, na, nbuf;
+};
+
+bool vfold_geometry(const mpg_conv_desc& d, VfGeom* g) {
+  if (!igemm_eligible(d) || d.upsample != 1) return false;
+  const int ks = d.seg_ksize[0];
+  if (ks != 3 && ks != 5) return false;
+  if (d.nseg == 2 && d.seg_ksize[1] != 1) return false;
+  const int cp = round_up(d.cout, 8);
+  if (ks * cp > 256 || cp / 8 > (ks == 5 ? 6 : 8)) return false;
+  if (d.out_dtype == MPG_F32 ? d.out_cstride > cp : d.out_cstride != cp) return false;
+  g->cp = cp;
+  g->npad = round_up(ks * cp, 16);
+  g->nchunks = cp / 8;
+  // epilogue warp groups x chunks per warp (the epilogue is TMEM-read bound: as many warps in flight as registers allow)
+  static const int cfg[9][2] = {{0, 0}, {1, 1}, {2, 1}, {3, 1}, {2, 2}, {3, 2}, {2, 3}, {4, 2}, {4, 2}};
+  g->groups = cfg[g->nchunks][0];
+  g->nchw = cfg[g->nchunks][1];
+  if (const char* e = getenv("MPG_VFOLD_GROUPS")) {
+    const int gg = atoi(e);
+    if (gg >= 1 && gg <= 4 && ceil_div(g->nchunks, gg) <= (gg == 2 ? 3 : 2)) {
+      g->groups = gg;
+      g->nchw = ceil_div(g->nchunks, gg);
+    }
+  }
+  const int pad = ks / 2;
+  if ((pad * cp) % 16 == 0) {
+    g->n_sc = round_up(cp, 16);
+    g->sc_col = pad * cp;
+  } else {  // a narrow MMA would start at a column that is no multiple of 16: use the whole accumulator width
+    g->n_sc = g->npad;
+    g->sc_col = 0;
+  }
+  int maxcin = 0;
+  for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
+  const int budget = 212 * 1024;
+  const int first_ck = maxcin > 32 ? 64 : 32;
+  for (int ck = first_ck; ck >= 32; ck /= 2) {
+    const int rb = ck * 2;
+    g->ck = ck;
+    g->b_tile_bytes = round_up(g->npad / 2 * rb, 1024);
+    g->b_sc_tile_bytes = round_up(g->n_sc / 2 * rb, 1024);
+    g->a_stage_bytes = round_up((kVfStrip + ks - 1) * rb, 1024);
+    int stages_per_row = 0;
+    g->b_bytes = 0;
+    for (int s = 0; s < d.nseg; ++s) {
+      g->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
+      g->seg_klast[s] = ceil_div(d.seg_cin[s] - (g->seg_nchunk[s] - 1) * ck, 16);
+      stages_per_row += g->seg_nchunk[s];
+      g->b_bytes += s == 0 ? g->seg_nchunk[s] * ks * g->b_tile_bytes : g->seg_nchunk[s] * g->b_sc_tile_bytes;
+    }
+    if (d.nseg == 1) g->seg_nchunk[1] = g->seg_klast[1] = 0;
+    int na = (budget - g->b_bytes) / g->a_stage_bytes;
+    na = na > kVfMaxStagesA ? kVfMaxStagesA : na;
+    g->na = na;
+    if (na >= stages_per_row + 1 && na >= 2) break;
+    if (ck == 32) return false;
+  }
+  g->nbuf = 512 / g->npad > kVfMaxBufs ? kVfMaxBufs : 512 / g->npad;
+  return g->nbuf >= 2;
+}
+
+int build_vfold(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  VfGeom g;
+  if (!vfold_geometry(d, &g)) {
+    set_error("conv(vfold): layer does not fit the row-streaming kernel");
+    return MPG_ENOSUP;
+  }
+  const int ks = d.seg_ksize[0], pad = ks / 2, ck = g.ck, cp = g.cp;
+  p->ck = ck;
+  p->npad = g.npad;
+  p->vf_nchw = g.nchw;
+  for (int s = 0; s < 2; ++s) p->seg_nchunk[s] = g.seg_nchunk[s];
+  // resident image per CTA rank: main tiles (chunk, dx) then shortcut tiles (chunk); a tile = this rank's half of the
+  // N rows (row n = dy*cp + co) in the swizzled K-major layout
+  std::vector<uint16_t> wp(static_cast<size_t>(g.b_bytes), 0);  // 2 ranks x b_bytes / 2 elements
+  auto cvt = [&](float v) { return d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v); };
+  for (int r = 0; r < 2; ++r) {
+    size_t off = static_cast<size_t>(r) * g.b_bytes / 2;  // in elements
+    for (int ch = 0; ch < g.seg_nchunk[0]; ++ch)
+      for (int dx = 0; dx < ks; ++dx, off += g.b_tile_bytes / 2)
+        for (int nr = 0; nr < g.npad / 2; ++nr) {
+          const int col = r * (g.npad / 2) + nr;
+          const int dy = col / cp, co = col % cp;
+          if (dy >= ks || co >= d.cout) continue;
+          const float sc = scale[0] ? scale[0][co] : 1.0f;
+          for (int c = 0; c < ck; ++c) {
+            const int ci = ch * ck + c;
+            if (ci >= d.seg_cin[0]) break;
+            wp[off + swz_elem(nr, c, ck)] = cvt(w[0][((static_cast<size_t>(dy) * ks + dx) * d.seg_cin[0] + ci) * d.cout + co] * sc);
+          }
+        }
+    for (int ch = 0; d.nseg > 1 && ch < g.seg_nchunk[1]; ++ch, off += g.b_sc_tile_bytes / 2)
+      for (int nr = 0; nr < g.n_sc / 2; ++nr) {
+        const int col = g.sc_col + r * (g.n_sc / 2) + nr;
+        const int dy = col / cp, co = col % cp;
+        if (dy != pad || co >= d.cout) continue;
+        const float sc = scale[1] ? scale[1][co] : 1.0f;
+        for (int c = 0; c < ck; ++c) {
+          const int ci = ch * ck + c;
+          if (ci >= d.seg_cin[1]) break;
+          wp[off + swz_elem(nr, c, ck)] = cvt(w[1][static_cast<size_t>(ci) * d.cout + co] * sc);
+        }
+      }
+  }
+  MPG_CUDA(cudaMalloc(&p->d_wpacked, wp.size() * 2));
+  MPG_CUDA(cudaMemcpy(p->d_wpacked, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> sh(64, 0.0f);
+  if (shift)
+    for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
+  MPG_CUDA(cudaMalloc(&p->d_shift, 64 * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+  VfoldParams& q = p->vp;
+  memset(&q, 0, sizeof(q));
+  q.n = d.n;
+  q.h = d.h;
+  q.w = d.w;
+  q.strips2 = ceil_div(ceil_div(d.w, kVfStrip), 2);
+  q.total_rows = d.n * q.strips2 * d.h;
+  int npairs = p->h->sm_count / 2;
+  if (const char* e = getenv("MPG_VFOLD_PAIRS")) npairs = atoi(e) > 0 ? atoi(e) : npairs;
+  q.rows_per_pair = ceil_div(q.total_rows, npairs);
+  if (q.rows_per_pair < 1) q.rows_per_pair = 1;
+  p->grid = 2 * ceil_div(q.total_rows, q.rows_per_pair);
+  q.ks = ks;
+  q.nseg = d.nseg;
+  for (int s = 0; s < 2; ++s) {
+    q.seg_nchunk[s] = g.seg_nchunk[s];
+    q.seg_klast[s] = g.seg_klast[s];
+  }
+  q.npad = g.npad;
+  q.cp = cp;
+  q.cout = d.cout;
+  q.n_sc = g.n_sc;
+  q.sc_col = g.sc_col;
+  q.act = d.act;
+  q.pixel_norm = d.pixel_norm;
+  q.in_dtype = d.in_dtype;
+  q.out_dtype = d.out_dtype;
+  q.out_cstride = d.out_cstride;
+  q.na = g.na;
+  if (const char* e = getenv("MPG_VFOLD_NA")) q.na = (atoi(e) >= 2 && atoi(e) <= g.na) ? atoi(e) : g.na;
+  q.a_stage_bytes = g.a_stage_bytes;
+  q.b_tile_bytes = g.b_tile_bytes;
+  q.b_sc_tile_bytes = g.b_sc_tile_bytes;
+  q.b_bytes = g.b_bytes;
+  q.nbuf = g.nbuf;
+  if (const char* e = getenv("MPG_VFOLD_NBUF")) q.nbuf = (atoi(e) >= 1 && atoi(e) <= g.nbuf) ? atoi(e) : g.nbuf;
+  q.epi_groups = g.groups;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(q.nbuf * q.npad)) cols <<= 1;
+  q.tmem_cols = cols;
+  q.shift = p->d_shift;
+  q.wpacked = p->d_wpacked;
+  if (const char* e = getenv("MPG_VFOLD_DBG")) q.dbg = atoi(e);
+  p->smem_bytes = static_cast<size_t>(q.b_bytes) + static_cast<size_t>(q.na) * q.a_stage_bytes + 1024;
+  int r = vfold_set_smem_attr(p->h->device, ck, ks, g.nchw, g.groups, p->smem_bytes);
+  if (r) {
+    set_error("cudaFuncSetAttribute(vfold, max dynamic smem %zu) failed: %s", p->smem_bytes,
+              cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
+  return 0;
+}
+
+// The row-streaming kernel pays off when a strip pair is mostly real pixels and every CTA pair gets a long row range.
+bool vfold_preferred(const mpg_conv_desc& d, int sm_count) {
+  VfGeom g;
+  if (!vfold_geometry(d, &g)) return false;
+  // The epilogue reads k*cp accumulator columns per output pixel and TMEM reads run at ~40-64 B/clk/SM (measured: the
+  // epilogue alone costs ~12.7 cycles per column and image row), so the fold only pays when the MMAs of a row take longer:
+  // k * (Cin/16) K-steps of max(64, N/2) cycles, i.e. 5x5 layers with >= 48 input channels.
+  int min_cin = 48;
+  if (const char* e = getenv("MPG_VFOLD_MINCIN")) min_cin = atoi(e);
+  if (d.seg_ksize[0] != 5 || d.seg_cin[0] < min_cin) return false;
+  const int strips = ceil_div(d.w, kVfStrip);
+  if (d.w < 2 * kVfStrip || (strips % 2 != 0 && strips < 5)) return false;
+  const long long total = static_cast<long long>(d.n) * ceil_div(strips, 2) * d.h;
+  if (total < 16LL * (sm_count / 2)) return false;
+  return true;
+}
+
 int build_direct(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
   const mpg_conv_desc& d = p->d;
   DirectParams& dp = p->dp;
@@ -685,6 +877,15 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     bool nf = nfold_eligible(d) && (round_up(d.cout, 8) * d.seg_ksize[0] <= 64 || cin_total >= 64);
     if (const char* e = getenv("MPG_CONV_NFOLD")) nf = (atoi(e) == 2) ? nfold_eligible(d) : (nf && atoi(e) != 0);
     if (kind == 1 && nf) kind = 3;
+    // medium / narrow Cout on wide images: stream image rows, fold the VERTICAL taps into N (conv_vfold.cu)
+    if (kind == 1 || kind == 3) {
+      bool vf = vfold_preferred(d, h->sm_count);
+      if (const char* e = getenv("MPG_CONV_VFOLD")) {
+        VfGeom g;
+        vf = (atoi(e) == 2) ? vfold_geometry(d, &g) : (vf && atoi(e) != 0);
+      }
+      if (vf) kind = 5;
+    }
     // Cout <= 2 from <= 8 channels: a bandwidth kernel on CUDA cores beats the per-tile hand-overs of the tensor path
     bool tiny = tiny_eligible(d);
     if (const char* e = getenv("MPG_CONV_TINY")) tiny = tiny && atoi(e) != 0;
@@ -702,7 +903,14 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
     mpg::set_error("conv: tcgen05 path needs bf16/f16 input (same 16-bit output type or f32), stride 1, k in {1,3,5}, cstride %% 8 == 0, cout <= 128");
     return MPG_ENOSUP;
   }
-  MPG_CHECK_ARG(kind >= 1 && kind <= 4, "conv: bad force_kind %d", d.force_kind);
+  if (kind == 5) {
+    VfGeom g;
+    if (!vfold_geometry(d, &g)) {
+      mpg::set_error("conv: row-streaming path needs the tcgen05 constraints plus k0 in {3,5}, k0 * round_up(cout, 8) <= 256, 1x1 shortcut, no upsample");
+      return MPG_ENOSUP;
+    }
+  }
+  MPG_CHECK_ARG(kind >= 1 && kind <= 5, "conv: bad force_kind %d", d.force_kind);
 
   mpg_conv_plan p = new mpg_conv_plan_s();
   memset(p, 0, sizeof(*p));
@@ -718,7 +926,8 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   const float* sc[2] = {scale_seg0, scale_seg1};
   mpg::DeviceGuard guard(h->device);
   int r = (kind == 1) ? build_igemm(p, w, sc, shift)
-          : (kind == 3 ? build_nfold(p, w, sc, shift) : (kind == 4 ? build_tiny(p, w, sc, shift) : build_direct(p, w, sc, shift)));
+          : (kind == 3 ? build_nfold(p, w, sc, shift)
+                       : (kind == 4 ? build_tiny(p, w, sc, shift) : (kind == 5 ? build_vfold(p, w, sc, shift) : build_direct(p, w, sc, shift))));
   if (r) {
     mpg_conv_plan_destroy(p);
     return r;
@@ -769,7 +978,7 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
   MPG_CHECK_ARG((y_side != nullptr) == (p->kind == 1 && p->ip.side != 0), "conv: y_side must be given exactly when the plan has a side output");
   MPG_CHECK_ARG(y_side == nullptr || (reinterpret_cast<uintptr_t>(y_side) & 15) == 0, "conv: y_side not 16-byte aligned");
   if (residual != nullptr) {
-    MPG_CHECK_ARG(p->kind == 3 && p->d.cout <= 8 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+    MPG_CHECK_ARG((p->kind == 3 || p->kind == 5) && p->d.cout <= 8 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                   "conv: an fp32 residual input needs a tap-folded plan with <= 8 output channels and a 16-byte aligned tensor");
   }
   MPG_CHECK_ARG(p->d.nseg == 1 || x1 != nullptr, "mpg_conv_plan_run: segment 1 input missing");
@@ -864,6 +1073,34 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
                               p->smem_bytes, st);
     if (r) {
       mpg::set_error("conv nfold launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+      return r;
+    }
+    return MPG_OK;
+  }
+  if (p->kind == 5) {
+    const void* xs[2] = {x0, x1};
+    for (int s = 0; s < d.nseg; ++s) {
+      if (p->tm_x_ptr[s] == xs[s]) continue;
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(xs[s]) & 15) == 0, "conv: input %d not 16-byte aligned", s);
+      const uint64_t cs = static_cast<uint64_t>(d.seg_cstride[s]) * 2;
+      const uint64_t dims[4] = {static_cast<uint64_t>(d.seg_cin[s]), static_cast<uint64_t>(d.w),
+                                static_cast<uint64_t>(d.h), static_cast<uint64_t>(d.n)};
+      const uint64_t strides[3] = {cs, cs * d.w, cs * d.w * d.h};
+      // one staged image row of the strip (the shortcut input uses the same window, centre pixel shift)
+      const uint32_t box[4] = {static_cast<uint32_t>(p->ck), static_cast<uint32_t>(mpg::kVfStrip + d.seg_ksize[0] - 1), 1u, 1u};
+      int r = mpg::encode_tmap(p->h, &p->tm_x[s], d.in_dtype == MPG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, xs[s], dims, strides,
+                               box, swizzle_for(p->ck));
+      if (r) return r;
+      p->tm_x_ptr[s] = xs[s];
+    }
+    if (d.out_dtype != MPG_F32)
+      MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
+    mpg::VfoldParams q = p->vp;
+    q.out = y;
+    q.resid = residual;
+    int r = mpg::vfold_launch(p->ck, p->vf_nchw, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], q, p->grid, p->smem_bytes, st);
+    if (r) {
+      mpg::set_error("conv vfold launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
       return r;
     }
     return MPG_OK;

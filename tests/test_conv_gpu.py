@@ -56,6 +56,22 @@ CASES = {
     "ct_ragged_37x45_k3_4to2": dict(n=3, h=37, w=45, cins=[4, 5], ks=[3, 1], cout=2, act="lrelu", with_scale=True, force_kind=4),
     "ct_k5_3to1_16bit_out": dict(n=1, h=19, w=130, cins=[3], ks=[5], cout=1, act="tanh", force_kind=4),
     "ct_k3_8to1_f32_cs4": dict(n=1, h=16, w=64, cins=[8], ks=[3], cout=1, out_dtype="f32", out_cstride=4, force_kind=4),
+    # row-streaming tcgen05 path (conv_vfold.cu): vertical taps folded into N, CTA pairs on adjacent 128-pixel strips
+    "vf_k5_128to32": dict(n=2, h=40, w=300, cins=[128], ks=[5], cout=32, act="relu", force_kind=5),
+    "vf_k5_48to48_pn": dict(n=1, h=33, w=256, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k5_48and96_to48_pn": dict(n=2, h=24, w=140, cins=[48, 96], ks=[5, 1], cout=48, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k5_96to48_ck32": dict(n=1, h=20, w=260, cins=[96], ks=[5], cout=48, act="lrelu", force_kind=5),
+    "vf_k5_24and48_to24_pn": dict(n=1, h=30, w=130, cins=[24, 48], ks=[5, 1], cout=24, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k5_24to12_pn": dict(n=3, h=17, w=64, cins=[24], ks=[5], cout=12, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k5_32to8": dict(n=2, h=37, w=45, cins=[32], ks=[5], cout=8, act="relu", force_kind=5),
+    "vf_k5_32and128_to8": dict(n=1, h=21, w=129, cins=[32, 128], ks=[5, 1], cout=8, act="relu", force_kind=5),
+    "vf_k3_64to64_pn": dict(n=2, h=32, w=200, cins=[64], ks=[3], cout=64, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k3_64and64_to32_pn": dict(n=1, h=48, w=256, cins=[64, 64], ks=[3, 1], cout=32, act="relu", pixel_norm=True, force_kind=5),
+    "vf_k3_32and32_to24_tanh": dict(n=1, h=19, w=77, cins=[32, 32], ks=[3, 1], cout=24, act="tanh", force_kind=5),
+    "vf_k5_128to24_f32": dict(n=1, h=16, w=131, cins=[128], ks=[5], cout=24, out_dtype="f32", act="relu", force_kind=5),
+    "vf_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", with_scale=True, force_kind=5),
+    "vf_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=5),
+    "vf_k5_128to32_512": dict(n=2, h=128, w=512, cins=[128], ks=[5], cout=32, act="relu", force_kind=5),
     "forced_direct_16bit": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64, force_kind=2, act="relu"),
 }
 
@@ -76,8 +92,34 @@ def test_conv_case(name, half):
     assert r["rel_l2"] < tol, (name, r)
     if name.startswith("nf_"):
         assert r["kind"] == 3, r
+    if name.startswith("vf_"):
+        assert r["kind"] == 5, r
     if name.startswith("ct_") or name in ("direct_k5_8to2", "direct_2seg_to1_f32"):
         assert r["kind"] == 4, r
+
+
+@pytest.mark.parametrize("pairs", ["1", "3", "7"])
+@pytest.mark.parametrize("name", ["vf_k5_48and96_to48_pn", "vf_ragged_37x45", "vf_k3_64to64_pn"])
+def test_vfold_row_ranges_crossing_images(name, pairs, monkeypatch):
+    """Few CTA pairs = long contiguous row ranges that cross strip and image boundaries (the running sums restart)."""
+    monkeypatch.setenv("MPG_VFOLD_PAIRS", pairs)
+    kw = dict(CASES[name])
+    for key in ("in_dtype", "out_dtype"):
+        if kw.get(key, "bf16") == "bf16":
+            kw[key] = "f16"
+    r = run_case(**kw)
+    assert r["finite"] and r["pad_ok"] and r["kind"] == 5, r
+    assert r["rel_l2"] < 8e-4, (name, r)
+
+
+def test_vfold_auto_rule_picks_wide_images():
+    """Auto kind: the row-streaming kernel takes medium / narrow Cout layers on wide images, nothing else."""
+    r = run_case(n=4, h=256, w=512, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 5 and r["rel_l2"] < 8e-4, r
+    r = run_case(n=1, h=64, w=64, cins=[48], ks=[5], cout=48, act="relu", in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 1, r
+    r = run_case(n=1, h=128, w=512, cins=[128], ks=[5], cout=128, act="relu", in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 1, r
 
 
 def test_flagship_shape_one_slice():
@@ -138,18 +180,22 @@ def test_side_output_and_residual_equal_the_two_segment_form():
     x32 = torch.randn(n, h, w, 32, generator=g).to(torch.float16).to(dev)
     w5 = (torch.randn(5, 5, 32, 8, generator=g) * (np.sqrt(2.0) / np.sqrt(800))).numpy()
     shc = (torch.randn(8, generator=g) * 0.1).numpy()
-    fused = capi.ConvPlan(hd, n, h, w, [w5], [32], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16)
+    fused = capi.ConvPlan(hd, n, h, w, [w5], [32], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16, force_kind=3)
     assert fused.kind == capi.KIND_NFOLD
     o1 = torch.empty(n, h, w, 8, dtype=torch.float16, device=dev)
     fused.run_ex(x32, None, o1, residual=side, stream=st)
+    fused_vf = capi.ConvPlan(hd, n, h, w, [w5], [32], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16, force_kind=5)
+    assert fused_vf.kind == capi.KIND_VFOLD
+    o3 = torch.empty(n, h, w, 8, dtype=torch.float16, device=dev)
+    fused_vf.run_ex(x32, None, o3, residual=side, stream=st)
     two = capi.ConvPlan(hd, n, h, w, [w5, ws_next], [32, 128], 8, 8, act="relu", shift=shc, in_dtype=capi.F16, out_dtype=capi.F16)
     o2 = torch.empty(n, h, w, 8, dtype=torch.float16, device=dev)
     two.run(x32, y, o2, st)
     torch.cuda.synchronize()
     want = torch.relu(ref_conv([x32.float()], [w5], [None], shc, None, False, 1, round_w=torch.float16) + side_ref)
-    for got in (o1, o2):
+    for got in (o1, o2, o3):
         assert float(torch.linalg.norm(got.double() - want) / torch.linalg.norm(want)) < 1.5e-3
-    for pl in (producer, fused, two):
+    for pl in (producer, fused, two, fused_vf):
         pl.close()
     # plans that cannot carry a side output say so
     small = capi.ConvPlan(hd, 1, 32, 32, [np.zeros((3, 3, 64, 64), np.float32)], [64], 64, 64, in_dtype=capi.F16, out_dtype=capi.F16)

@@ -31,6 +31,9 @@ SHAPES_8X = [
     ("n2 24/12->48", dict(cins=[24, 12], ks=[5, 1], cout=48, pn=True)),
     ("n1 64->64k3", dict(cins=[64], ks=[3], cout=64, pn=True)),
     ("n1 32->32k3", dict(cins=[32], ks=[3], cout=32, pn=True)),
+    ("n2 48->24", dict(cins=[48], ks=[5], cout=24, pn=True)),
+    ("n2 24->24", dict(cins=[24], ks=[5], cout=24, pn=True)),
+    ("n2 5->16", dict(cins=[5], ks=[5], cout=16, pn=True)),
 ]
 if os.environ.get("PROBE_8X"):
     SHAPES = SHAPES_8X
@@ -50,6 +53,16 @@ CONFIGS = {
     "ck64": {"MPG_IGEMM_CK": "64"},
     "ck32": {"MPG_IGEMM_CK": "32"},
     "nfck32": {"MPG_NFOLD_CK": "32"},
+    # row-streaming kernel (conv_vfold.cu)
+    "vf_off": {"MPG_CONV_VFOLD": "0"},
+    "vf_nostore": {"MPG_VFOLD_DBG": "1"},
+    "vf_noepi": {"MPG_VFOLD_DBG": "2"},
+    "vf_nomma": {"MPG_VFOLD_DBG": "4"},
+    "vf_skel": {"MPG_VFOLD_DBG": "6"},
+    "vf_na2": {"MPG_VFOLD_NA": "2"},
+    "vf_g2": {"MPG_VFOLD_GROUPS": "2"},
+    "vf_g2_nomma": {"MPG_VFOLD_GROUPS": "2", "MPG_VFOLD_DBG": "4"},
+    "vf_nbuf1": {"MPG_VFOLD_NBUF": "1"},
     "nfck32_skel": {"MPG_NFOLD_CK": "32", "MPG_NFOLD_DBG": "6", "MPG_IGEMM_DBG": "6"},
 }
 KEYS = sorted({k for c in CONFIGS.values() for k in c})
