@@ -78,7 +78,7 @@ typedef struct mpg_conv_desc {
   int upsample;       /* 1, or 2 = nearest x2 replicated store                             */
   int in_upsample;    /* >=1: the conv reads a nearest-upsampled view of x (CUDA-core path) */
   int stride;         /* 1 (tensor-core path) or 2 (CUDA-core path, discriminator)         */
-  int force_kind;     /* 0 auto, 1 tcgen05 implicit GEMM, 2 CUDA-core direct, 3 tap-folded, 4 tiny, 5 row-streaming */
+  int force_kind;     /* 0 auto, 1 tcgen05 implicit GEMM, 2 CUDA-core direct, 3 tap-folded, 4 tiny, 5 / 6 row-streaming */
   int in_dtype;       /* MPG_BF16 / MPG_F16 (tensor-core path) or MPG_F32 (CUDA-core path) */
   int out_dtype;      /* MPG_BF16 / MPG_F16 (same 16-bit type as in_dtype) or MPG_F32      */
   int out_cstride;    /* channel stride (elements) of y; channels >= cout are written as 0 */
@@ -110,7 +110,8 @@ int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* 
                          const float* shift_dev, void* stream);
 /* which kernel the plan dispatches to: 1 = tcgen05 implicit GEMM, 2 = CUDA-core direct, 3 = tcgen05 with the
  * horizontal taps folded into N (narrow Cout), 4 = CUDA-core kernel for cout <= 2 from <= 8 channels,
- * 5 = row-streaming tcgen05 kernel with the vertical taps folded into N (k * round_up(cout, 8) <= 256, wide images) */
+ * 5 = row-streaming tcgen05 kernel with the vertical taps folded into N (k * round_up(cout, 8) <= 256, wide images),
+ * 6 = row-streaming tcgen05 kernel that accumulates the vertical-tap sum in a TMEM ring (cout <= 64) */
 int mpg_conv_plan_kind(mpg_conv_plan p);
 /* algorithmic FLOPs of one run (2*MAC, un-padded channels) */
 double mpg_conv_plan_flops(mpg_conv_plan p);

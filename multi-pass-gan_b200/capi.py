@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmpg_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 BF16, F32, F16 = 0, 1, 2
+KIND_VRING = 6  # tcgen05, row streaming, vertical-tap sum accumulated in a TMEM ring of output rows
 KIND_VFOLD = 5  # tcgen05, image rows streamed through 128-pixel strips, vertical taps folded into N
 KIND_TCGEN05, KIND_DIRECT, KIND_NFOLD, KIND_TINY = 1, 2, 3, 4  # NFOLD: tcgen05 with the horizontal taps folded into N; TINY: CUDA-core kernel for cout <= 2 / cin <= 8
 

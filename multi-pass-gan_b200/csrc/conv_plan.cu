@@ -11,6 +11,7 @@
 #include "conv_nfold.cuh"
 #include "conv_tiny.cuh"
 #include "conv_vfold.cuh"
+#include "conv_vring.cuh"
 
 struct mpg_conv_plan_s {
   mpg_handle h;
@@ -20,6 +21,7 @@ struct mpg_conv_plan_s {
   mpg::NfoldParams np;
   mpg::VfoldParams vp;
   int vf_nchw;
+  mpg::VringParams rp;
   double flops;
   int oh, ow;
   // ---- igemm
@@ -755,6 +757,161 @@ bool vfold_preferred(const mpg_conv_desc& d, int sm_count) {
   return true;
 }
 
+// ---- row-streaming kernel with the vertical-tap sum accumulated in a TMEM ring (conv_vring.cu) ----
+struct VrGeom {
+  int ck, cp, cs, nslots, nchunks, groups, nchw;
+  int seg_nchunk[2], seg_klast[2], seg_ksteps[2];
+  int b_tile_bytes, b_sc_tile_bytes, b_bytes, a_stage_bytes, na;
+};
+
+bool vring_geometry(const mpg_conv_desc& d, VrGeom* g) {
+  if (!igemm_eligible(d) || d.upsample != 1) return false;
+  const int ks = d.seg_ksize[0];
+  if (ks != 3 && ks != 5) return false;
+  if (d.nseg == 2 && d.seg_ksize[1] != 1) return false;
+  const int cp = round_up(d.cout, 8), cs = round_up(d.cout, 16);
+  if (ks * cs > 256 || cp > 64) return false;
+  if (d.out_dtype == MPG_F32 ? d.out_cstride > cp : d.out_cstride != cp) return false;
+  g->cp = cp;
+  g->cs = cs;
+  g->nslots = 512 / cs > kVrMaxSlots ? kVrMaxSlots : 512 / cs;
+  if (g->nslots < ks + 1) return false;
+  g->nchunks = cp / 8;
+  g->groups = g->nchunks > 1 ? 2 : 1;
+  g->nchw = ceil_div(g->nchunks, g->groups);
+  int maxcin = 0;
+  for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
+  const int ck = maxcin > 32 ? 64 : 32, rb = ck * 2;
+  g->ck = ck;
+  g->b_tile_bytes = ks * cs * 32;
+  g->b_sc_tile_bytes = cs * 32;
+  g->a_stage_bytes = round_up((kVrStrip + ks - 1) * rb, 1024);
+  int stages_per_row = 0;
+  g->b_bytes = 0;
+  g->seg_nchunk[1] = g->seg_klast[1] = g->seg_ksteps[1] = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    g->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
+    g->seg_klast[s] = ceil_div(d.seg_cin[s] - (g->seg_nchunk[s] - 1) * ck, 16);
+    g->seg_ksteps[s] = (g->seg_nchunk[s] - 1) * (ck / 16) + g->seg_klast[s];
+    stages_per_row += g->seg_nchunk[s];
+    g->b_bytes += s == 0 ? g->seg_ksteps[s] * ks * g->b_tile_bytes : g->seg_ksteps[s] * g->b_sc_tile_bytes;
+  }
+  g->b_bytes = round_up(g->b_bytes, 1024);
+  const int budget = 212 * 1024;
+  int na = (budget - g->b_bytes) / g->a_stage_bytes;
+  na = na > kVrMaxStagesA ? kVrMaxStagesA : na;
+  g->na = na;
+  return na >= stages_per_row + 1 && na >= 2;
+}
+
+int build_vring(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
+  const mpg_conv_desc& d = p->d;
+  VrGeom g;
+  if (!vring_geometry(d, &g)) {
+    set_error("conv(vring): layer does not fit the TMEM-ring row-streaming kernel");
+    return MPG_ENOSUP;
+  }
+  const int ks = d.seg_ksize[0], cs = g.cs;
+  p->ck = g.ck;
+  p->npad = ks * cs;
+  p->vf_nchw = g.nchw;
+  for (int s = 0; s < 2; ++s) p->seg_nchunk[s] = g.seg_nchunk[s];
+  // resident image: main tiles [K-step][dx] of ks*cs rows (row = (ks-1-dy)*cs + co) x 16 channels, then shortcut tiles
+  // [K-step] of cs rows; 32-byte rows in the SWIZZLE_32B K-major layout
+  std::vector<uint16_t> wp(static_cast<size_t>(g.b_bytes) / 2, 0);
+  auto cvt = [&](float v) { return d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v); };
+  size_t off = 0;
+  for (int kk = 0; kk < g.seg_ksteps[0]; ++kk)
+    for (int dx = 0; dx < ks; ++dx, off += g.b_tile_bytes / 2)
+      for (int dy = 0; dy < ks; ++dy)
+        for (int co = 0; co < d.cout; ++co) {
+          const float sc = scale[0] ? scale[0][co] : 1.0f;
+          const int row = (ks - 1 - dy) * cs + co;
+          for (int c = 0; c < 16; ++c) {
+            const int ci = kk * 16 + c;
+            if (ci >= d.seg_cin[0]) break;
+            wp[off + swz_elem(row, c, 16)] = cvt(w[0][((static_cast<size_t>(dy) * ks + dx) * d.seg_cin[0] + ci) * d.cout + co] * sc);
+          }
+        }
+  for (int kk = 0; d.nseg > 1 && kk < g.seg_ksteps[1]; ++kk, off += g.b_sc_tile_bytes / 2)
+    for (int co = 0; co < d.cout; ++co) {
+      const float sc = scale[1] ? scale[1][co] : 1.0f;
+      for (int c = 0; c < 16; ++c) {
+        const int ci = kk * 16 + c;
+        if (ci >= d.seg_cin[1]) break;
+        wp[off + swz_elem(co, c, 16)] = cvt(w[1][static_cast<size_t>(ci) * d.cout + co] * sc);
+      }
+    }
+  MPG_CUDA(cudaMalloc(&p->d_wpacked, wp.size() * 2));
+  MPG_CUDA(cudaMemcpy(p->d_wpacked, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> sh(64, 0.0f);
+  if (shift)
+    for (int n = 0; n < d.cout; ++n) sh[n] = shift[n];
+  MPG_CUDA(cudaMalloc(&p->d_shift, 64 * sizeof(float)));
+  MPG_CUDA(cudaMemcpy(p->d_shift, sh.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+  VringParams& q = p->rp;
+  memset(&q, 0, sizeof(q));
+  q.n = d.n;
+  q.h = d.h;
+  q.w = d.w;
+  q.strips = ceil_div(d.w, kVrStrip);
+  q.total_rows = d.n * q.strips * d.h;
+  int nctas = p->h->sm_count;
+  if (const char* e = getenv("MPG_VRING_CTAS")) nctas = atoi(e) > 0 ? atoi(e) : nctas;
+  q.rows_per_cta = ceil_div(q.total_rows, nctas);
+  if (q.rows_per_cta < 1) q.rows_per_cta = 1;
+  p->grid = ceil_div(q.total_rows, q.rows_per_cta);
+  q.ks = ks;
+  q.nseg = d.nseg;
+  for (int s = 0; s < 2; ++s) {
+    q.seg_nchunk[s] = g.seg_nchunk[s];
+    q.seg_klast[s] = g.seg_klast[s];
+  }
+  q.cs = cs;
+  q.nslots = g.nslots;
+  if (const char* e = getenv("MPG_VRING_SLOTS")) q.nslots = (atoi(e) >= ks + 1 && atoi(e) <= g.nslots) ? atoi(e) : g.nslots;
+  q.cp = g.cp;
+  q.cout = d.cout;
+  q.act = d.act;
+  q.pixel_norm = d.pixel_norm;
+  q.in_dtype = d.in_dtype;
+  q.out_dtype = d.out_dtype;
+  q.out_cstride = d.out_cstride;
+  q.na = g.na;
+  q.a_stage_bytes = g.a_stage_bytes;
+  q.b_tile_bytes = g.b_tile_bytes;
+  q.b_sc_tile_bytes = g.b_sc_tile_bytes;
+  q.b_bytes = g.b_bytes;
+  q.epi_groups = g.groups;
+  q.shift = p->d_shift;
+  q.wpacked = p->d_wpacked;
+  if (const char* e = getenv("MPG_VRING_DBG")) q.dbg = atoi(e);
+  p->smem_bytes = static_cast<size_t>(q.b_bytes) + static_cast<size_t>(q.na) * q.a_stage_bytes + 1024;
+  int r = vring_set_smem_attr(p->h->device, g.ck, ks, g.nchw, g.groups, p->smem_bytes);
+  if (r) {
+    set_error("cudaFuncSetAttribute(vring, max dynamic smem %zu) failed: %s", p->smem_bytes,
+              cudaGetErrorString(static_cast<cudaError_t>(r)));
+    return r;
+  }
+  p->tm_x_ptr[0] = p->tm_x_ptr[1] = nullptr;
+  return 0;
+}
+
+// Measured per layer (tools/thin_probe.py, tools/step_times*.py): the ring beats the tap-by-tap kernel, both folds and the
+// CUDA-core paths on every eligible layer except <= 8 output channels (the horizontal fold is as fast there).
+bool vring_preferred(const mpg_conv_desc& d, int sm_count) {
+  VrGeom g;
+  if (!vring_geometry(d, &g)) return false;
+  if (const char* e = getenv("MPG_CONV_VRING")) {
+    if (atoi(e) == 0) return false;
+    if (atoi(e) == 2) return true;
+  }
+  if (g.cp <= 8) return false;
+  const int strips = ceil_div(d.w, kVrStrip);
+  if (strips * kVrStrip * 4 > d.w * 5) return false;  // > 25 % of a strip row would be padding
+  return static_cast<long long>(d.n) * strips * d.h >= 8LL * sm_count;
+}
+
 int build_direct(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
   const mpg_conv_desc& d = p->d;
   DirectParams& dp = p->dp;
@@ -884,7 +1041,9 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
         VfGeom g;
         vf = (atoi(e) == 2) ? vfold_geometry(d, &g) : (vf && atoi(e) != 0);
       }
-      if (vf) kind = 5;
+      // the TMEM-ring variant first: it beats the fold on every layer whose weights fit one CTA (measured, thin_probe.py)
+      if (vring_preferred(d, h->sm_count)) kind = 6;
+      else if (vf) kind = 5;
     }
     // Cout <= 2 from <= 8 channels: a bandwidth kernel on CUDA cores beats the per-tile hand-overs of the tensor path
     bool tiny = tiny_eligible(d);
@@ -910,7 +1069,14 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
       return MPG_ENOSUP;
     }
   }
-  MPG_CHECK_ARG(kind >= 1 && kind <= 5, "conv: bad force_kind %d", d.force_kind);
+  if (kind == 6) {
+    VrGeom g;
+    if (!vring_geometry(d, &g)) {
+      mpg::set_error("conv: TMEM-ring path needs the tcgen05 constraints plus k0 in {3,5}, k0 * round_up(cout, 16) <= 256, cout <= 64, 1x1 shortcut, no upsample, weights <= ~150 KB");
+      return MPG_ENOSUP;
+    }
+  }
+  MPG_CHECK_ARG(kind >= 1 && kind <= 6, "conv: bad force_kind %d", d.force_kind);
 
   mpg_conv_plan p = new mpg_conv_plan_s();
   memset(p, 0, sizeof(*p));
@@ -927,7 +1093,7 @@ int mpg_conv_plan_create(mpg_handle h, const mpg_conv_desc* dsc, const float* w_
   mpg::DeviceGuard guard(h->device);
   int r = (kind == 1) ? build_igemm(p, w, sc, shift)
           : (kind == 3 ? build_nfold(p, w, sc, shift)
-                       : (kind == 4 ? build_tiny(p, w, sc, shift) : (kind == 5 ? build_vfold(p, w, sc, shift) : build_direct(p, w, sc, shift))));
+                       : (kind == 4 ? build_tiny(p, w, sc, shift) : (kind == 5 ? build_vfold(p, w, sc, shift) : (kind == 6 ? build_vring(p, w, sc, shift) : build_direct(p, w, sc, shift)))));
   if (r) {
     mpg_conv_plan_destroy(p);
     return r;
@@ -978,7 +1144,7 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
   MPG_CHECK_ARG((y_side != nullptr) == (p->kind == 1 && p->ip.side != 0), "conv: y_side must be given exactly when the plan has a side output");
   MPG_CHECK_ARG(y_side == nullptr || (reinterpret_cast<uintptr_t>(y_side) & 15) == 0, "conv: y_side not 16-byte aligned");
   if (residual != nullptr) {
-    MPG_CHECK_ARG((p->kind == 3 || p->kind == 5) && p->d.cout <= 8 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+    MPG_CHECK_ARG((p->kind == 3 || p->kind == 5 || p->kind == 6) && p->d.cout <= 8 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                   "conv: an fp32 residual input needs a tap-folded plan with <= 8 output channels and a 16-byte aligned tensor");
   }
   MPG_CHECK_ARG(p->d.nseg == 1 || x1 != nullptr, "mpg_conv_plan_run: segment 1 input missing");
@@ -1077,7 +1243,7 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
     }
     return MPG_OK;
   }
-  if (p->kind == 5) {
+  if (p->kind == 5 || p->kind == 6) {
     const void* xs[2] = {x0, x1};
     for (int s = 0; s < d.nseg; ++s) {
       if (p->tm_x_ptr[s] == xs[s]) continue;
@@ -1095,6 +1261,17 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
     }
     if (d.out_dtype != MPG_F32)
       MPG_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv: output not 16-byte aligned");
+    if (p->kind == 6) {
+      mpg::VringParams q = p->rp;
+      q.out = y;
+      q.resid = residual;
+      int r = mpg::vring_launch(p->ck, p->vf_nchw, p->tm_x[0], d.nseg > 1 ? p->tm_x[1] : p->tm_x[0], q, p->grid, p->smem_bytes, st);
+      if (r) {
+        mpg::set_error("conv vring launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+        return r;
+      }
+      return MPG_OK;
+    }
     mpg::VfoldParams q = p->vp;
     q.out = y;
     q.resid = residual;

@@ -445,7 +445,7 @@ class CompiledNet:
                                      in_dtype=self.act_dtype, out_dtype=out_dtype)
 
             plan = make(ws, scs, ins)
-            if resid is not None and not (plan.kind in (capi.KIND_NFOLD, capi.KIND_VFOLD) and cout <= 8):
+            if resid is not None and not (plan.kind in (capi.KIND_NFOLD, capi.KIND_VFOLD, capi.KIND_VRING) and cout <= 8):
                 # the consumer kernel cannot add a residual: back to the two-segment form (the side tensor stays unused)
                 plan.close()
                 resid = None
@@ -481,7 +481,7 @@ class CompiledNet:
         if x1 is not None and resid is not None:
             x1 = None
         label = "conv[%s] %s k%s %s->%d %dx%d%s%s%s%s%s" % (
-            {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf", capi.KIND_TINY: "ct", capi.KIND_VFOLD: "vf"}.get(kind, "cc"),
+            {capi.KIND_TCGEN05: "tc", capi.KIND_NFOLD: "nf", capi.KIND_TINY: "ct", capi.KIND_VFOLD: "vf", capi.KIND_VRING: "vr"}.get(kind, "cc"),
             "+".join(c.attrs["weight"]["var"].name.rsplit("/", 2)[-2] for c in convs),
             "/".join(str(c.attrs["ksize"]) for c in convs),
             "/".join(str(c.inputs[0].shape[3]) for c in convs), cout, ih, iw,

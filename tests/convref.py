@@ -89,7 +89,7 @@ def run_case(n, h, w, cins, ks, cout, act=None, pixel_norm=False, upsample=1, in
     plan.run(xs_dev[0], xs_dev[1] if nseg > 1 else None, y, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     ref = ref_conv(xs_val, ws, scs, shift, act, pixel_norm, upsample, in_upsample, stride,
-                   round_w=_TDT[in_dtype] if plan.kind in (capi.KIND_TCGEN05, capi.KIND_NFOLD, capi.KIND_VFOLD) else None)
+                   round_w=_TDT[in_dtype] if plan.kind in (capi.KIND_TCGEN05, capi.KIND_NFOLD, capi.KIND_VFOLD, capi.KIND_VRING) else None)
     got = y.double()
     pad_ok = True
     if out_cstride > cout:

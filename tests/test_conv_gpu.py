@@ -72,6 +72,21 @@ CASES = {
     "vf_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", with_scale=True, force_kind=5),
     "vf_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=5),
     "vf_k5_128to32_512": dict(n=2, h=128, w=512, cins=[128], ks=[5], cout=32, act="relu", force_kind=5),
+    # row-streaming tcgen05 path with the vertical-tap sum accumulated in a TMEM ring (conv_vring.cu)
+    "vr_k5_48to48_pn": dict(n=1, h=33, w=256, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k5_48and96_to48_pn": dict(n=2, h=24, w=140, cins=[48, 96], ks=[5, 1], cout=48, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k5_24and48_to24_pn": dict(n=1, h=30, w=130, cins=[24, 48], ks=[5, 1], cout=24, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k5_24to12_pn": dict(n=3, h=17, w=64, cins=[24], ks=[5], cout=12, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k5_5to16_pn": dict(n=2, h=40, w=200, cins=[5], ks=[5], cout=16, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k5_32to8": dict(n=2, h=37, w=45, cins=[32], ks=[5], cout=8, act="relu", force_kind=6),
+    "vr_k5_32and128_to8": dict(n=1, h=21, w=129, cins=[32, 128], ks=[5, 1], cout=8, act="relu", force_kind=6),
+    "vr_k3_64to64_pn": dict(n=2, h=32, w=200, cins=[64], ks=[3], cout=64, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k3_64and64_to32_pn": dict(n=1, h=48, w=256, cins=[64, 64], ks=[3, 1], cout=32, act="relu", pixel_norm=True, force_kind=6),
+    "vr_k3_32and32_to24_tanh": dict(n=1, h=19, w=77, cins=[32, 32], ks=[3, 1], cout=24, act="tanh", force_kind=6),
+    "vr_k5_64to24_f32": dict(n=1, h=16, w=131, cins=[64], ks=[5], cout=24, out_dtype="f32", act="relu", force_kind=6),
+    "vr_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", with_scale=True, force_kind=6),
+    "vr_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=6),
+    "vr_k5_48to48_512": dict(n=2, h=128, w=512, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, force_kind=6),
     "forced_direct_16bit": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64, force_kind=2, act="relu"),
 }
 
@@ -94,6 +109,8 @@ def test_conv_case(name, half):
         assert r["kind"] == 3, r
     if name.startswith("vf_"):
         assert r["kind"] == 5, r
+    if name.startswith("vr_"):
+        assert r["kind"] == 6, r
     if name.startswith("ct_") or name in ("direct_k5_8to2", "direct_2seg_to1_f32"):
         assert r["kind"] == 4, r
 
@@ -112,10 +129,29 @@ def test_vfold_row_ranges_crossing_images(name, pairs, monkeypatch):
     assert r["rel_l2"] < 8e-4, (name, r)
 
 
-def test_vfold_auto_rule_picks_wide_images():
+@pytest.mark.parametrize("ctas", ["1", "3", "7"])
+@pytest.mark.parametrize("name", ["vr_k5_48and96_to48_pn", "vr_ragged_37x45", "vr_k3_64to64_pn", "vr_k5_24to12_pn"])
+def test_vring_row_ranges_crossing_images(name, ctas, monkeypatch):
+    """Few CTAs = long contiguous row ranges: the TMEM ring wraps many times and crosses strip / image boundaries (the
+    first image row of every new range overwrites the partial sums the previous one left in the ring)."""
+    monkeypatch.setenv("MPG_VRING_CTAS", ctas)
+    kw = dict(CASES[name])
+    for key in ("in_dtype", "out_dtype"):
+        if kw.get(key, "bf16") == "bf16":
+            kw[key] = "f16"
+    r = run_case(**kw)
+    assert r["finite"] and r["pad_ok"] and r["kind"] == 6, r
+    assert r["rel_l2"] < 8e-4, (name, r)
+
+
+def test_row_streaming_auto_rule_picks_wide_images():
     """Auto kind: the row-streaming kernel takes medium / narrow Cout layers on wide images, nothing else."""
+    r = run_case(n=4, h=256, w=512, cins=[128], ks=[5], cout=32, act="relu", in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 5 and r["rel_l2"] < 8e-4, r  # weights too large for one CTA: the fold with CTA pairs
     r = run_case(n=4, h=256, w=512, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, in_dtype="f16", out_dtype="f16")
-    assert r["kind"] == 5 and r["rel_l2"] < 8e-4, r
+    assert r["kind"] == 6 and r["rel_l2"] < 8e-4, r  # the TMEM-ring variant
+    r = run_case(n=4, h=256, w=512, cins=[32], ks=[5], cout=8, act="relu", in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 3, r
     r = run_case(n=1, h=64, w=64, cins=[48], ks=[5], cout=48, act="relu", in_dtype="f16", out_dtype="f16")
     assert r["kind"] == 1, r
     r = run_case(n=1, h=128, w=512, cins=[128], ks=[5], cout=128, act="relu", in_dtype="f16", out_dtype="f16")

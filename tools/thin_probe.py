@@ -60,6 +60,11 @@ CONFIGS = {
     "vf_nomma": {"MPG_VFOLD_DBG": "4"},
     "vf_skel": {"MPG_VFOLD_DBG": "6"},
     "vf_na2": {"MPG_VFOLD_NA": "2"},
+    "vr": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0"},
+    "vr_nostore": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "1"},
+    "vr_noepi": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "2"},
+    "vr_nomma": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "4"},
+    "vr_skel": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "6"},
     "vf_g2": {"MPG_VFOLD_GROUPS": "2"},
     "vf_g2_nomma": {"MPG_VFOLD_GROUPS": "2", "MPG_VFOLD_DBG": "4"},
     "vf_nbuf1": {"MPG_VFOLD_NBUF": "1"},
