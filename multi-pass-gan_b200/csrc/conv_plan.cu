@@ -759,12 +759,13 @@ bool vfold_preferred(const mpg_conv_desc& d, int sm_count) {
 
 // ---- row-streaming kernel with the vertical-tap sum accumulated in a TMEM ring (conv_vring.cu) ----
 struct VrGeom {
-  int ck, cp, cs, nslots, nchunks, groups, nchw;
+  int ck, cp, cs, nslots, nchunks, groups, nchw, pair;
   int seg_nchunk[2], seg_klast[2], seg_ksteps[2];
   int b_tile_bytes, b_sc_tile_bytes, b_bytes, a_stage_bytes, na;
 };
 
-bool vring_geometry(const mpg_conv_desc& d, VrGeom* g) {
+// pair: -1 = choose, 0 = single CTA, 1 = CTA pairs
+bool vring_geometry(const mpg_conv_desc& d, VrGeom* g, int pair = -1) {
   if (!igemm_eligible(d) || d.upsample != 1) return false;
   const int ks = d.seg_ksize[0];
   if (ks != 3 && ks != 5) return false;
@@ -774,7 +775,8 @@ bool vring_geometry(const mpg_conv_desc& d, VrGeom* g) {
   if (d.out_dtype == MPG_F32 ? d.out_cstride > cp : d.out_cstride != cp) return false;
   g->cp = cp;
   g->cs = cs;
-  g->nslots = 512 / cs > kVrMaxSlots ? kVrMaxSlots : 512 / cs;
+  g->nslots = 512 / cs - (ks - 1);  // ring slots; the k-1 overflow slots follow
+  if (g->nslots > kVrMaxSlots) g->nslots = kVrMaxSlots;
   if (g->nslots < ks + 1) return false;
   g->nchunks = cp / 8;
   g->groups = g->nchunks > 1 ? 2 : 1;
@@ -783,65 +785,83 @@ bool vring_geometry(const mpg_conv_desc& d, VrGeom* g) {
   for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
   const int ck = maxcin > 32 ? 64 : 32, rb = ck * 2;
   g->ck = ck;
-  g->b_tile_bytes = ks * cs * 32;
-  g->b_sc_tile_bytes = cs * 32;
   g->a_stage_bytes = round_up((kVrStrip + ks - 1) * rb, 1024);
-  int stages_per_row = 0;
-  g->b_bytes = 0;
+  int stages_per_row = 0, tiles0 = 0, tiles1 = 0;
   g->seg_nchunk[1] = g->seg_klast[1] = g->seg_ksteps[1] = 0;
   for (int s = 0; s < d.nseg; ++s) {
     g->seg_nchunk[s] = ceil_div(d.seg_cin[s], ck);
     g->seg_klast[s] = ceil_div(d.seg_cin[s] - (g->seg_nchunk[s] - 1) * ck, 16);
     g->seg_ksteps[s] = (g->seg_nchunk[s] - 1) * (ck / 16) + g->seg_klast[s];
     stages_per_row += g->seg_nchunk[s];
-    g->b_bytes += s == 0 ? g->seg_ksteps[s] * ks * g->b_tile_bytes : g->seg_ksteps[s] * g->b_sc_tile_bytes;
+    (s == 0 ? tiles0 : tiles1) = s == 0 ? g->seg_ksteps[s] * ks : g->seg_ksteps[s];
   }
-  g->b_bytes = round_up(g->b_bytes, 1024);
   const int budget = 212 * 1024;
-  int na = (budget - g->b_bytes) / g->a_stage_bytes;
-  na = na > kVrMaxStagesA ? kVrMaxStagesA : na;
-  g->na = na;
-  return na >= stages_per_row + 1 && na >= 2;
+  const int strips = ceil_div(d.w, kVrStrip);
+  for (int pr = (pair < 0 ? 0 : pair); pr <= (pair < 0 ? 1 : pair); ++pr) {
+    g->pair = pr;
+    g->b_tile_bytes = ks * cs * 32 / (pr ? 2 : 1);
+    g->b_sc_tile_bytes = cs * 32 / (pr ? 2 : 1);
+    g->b_bytes = round_up(tiles0 * g->b_tile_bytes + tiles1 * g->b_sc_tile_bytes, 1024);
+    int na = (budget - g->b_bytes) / g->a_stage_bytes;
+    na = na > kVrMaxStagesA ? kVrMaxStagesA : na;
+    g->na = na;
+    const bool fits = na >= stages_per_row + 1 && na >= 2;
+    if (pair >= 0) return fits && (!pr || strips >= 2);
+    // choose: a single CTA whenever the weights fit it. Pairs halve the per-CTA weight fetch of every MMA, but their ring is
+    // handed over across two SMs and (for wide slots) only k+1 slots deep: measured slower on every layer that fits one CTA
+    // (5x5 48->48: 0.179 ms single, 0.266 ms pairs), faster than the fold where only the halves fit (5x5 96->48: 0.314 vs 0.408)
+    if (pr == 0 && fits) return true;
+    if (pr == 1 && fits && strips >= 2) return true;
+  }
+  return false;
 }
 
 int build_vring(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {
   const mpg_conv_desc& d = p->d;
   VrGeom g;
-  if (!vring_geometry(d, &g)) {
+  int want = -1;
+  if (const char* e = getenv("MPG_VRING_PAIR")) want = atoi(e) != 0 ? 1 : 0;
+  if (!vring_geometry(d, &g, want) && !(want >= 0 && vring_geometry(d, &g, -1))) {
     set_error("conv(vring): layer does not fit the TMEM-ring row-streaming kernel");
     return MPG_ENOSUP;
   }
-  const int ks = d.seg_ksize[0], cs = g.cs;
+  const int ks = d.seg_ksize[0], cs = g.cs, nr = g.pair ? 2 : 1;
   p->ck = g.ck;
   p->npad = ks * cs;
   p->vf_nchw = g.nchw;
   for (int s = 0; s < 2; ++s) p->seg_nchunk[s] = g.seg_nchunk[s];
-  // resident image: main tiles [K-step][dx] of ks*cs rows (row = (ks-1-dy)*cs + co) x 16 channels, then shortcut tiles
-  // [K-step] of cs rows; 32-byte rows in the SWIZZLE_32B K-major layout
-  std::vector<uint16_t> wp(static_cast<size_t>(g.b_bytes) / 2, 0);
+  // resident image (per CTA rank): main tiles [K-step][dx] of ks*cs rows (row = (ks-1-dy)*cs + co) x 16 channels, then
+  // shortcut tiles [K-step] of cs rows; 32-byte rows in the SWIZZLE_32B K-major layout. A pair splits every tile's rows.
+  std::vector<uint16_t> wp(static_cast<size_t>(g.b_bytes) / 2 * nr, 0);
   auto cvt = [&](float v) { return d.in_dtype == MPG_F16 ? f32_to_f16_rn(v) : f32_to_bf16_rn(v); };
-  size_t off = 0;
-  for (int kk = 0; kk < g.seg_ksteps[0]; ++kk)
-    for (int dx = 0; dx < ks; ++dx, off += g.b_tile_bytes / 2)
-      for (int dy = 0; dy < ks; ++dy)
-        for (int co = 0; co < d.cout; ++co) {
-          const float sc = scale[0] ? scale[0][co] : 1.0f;
-          const int row = (ks - 1 - dy) * cs + co;
-          for (int c = 0; c < 16; ++c) {
-            const int ci = kk * 16 + c;
-            if (ci >= d.seg_cin[0]) break;
-            wp[off + swz_elem(row, c, 16)] = cvt(w[0][((static_cast<size_t>(dy) * ks + dx) * d.seg_cin[0] + ci) * d.cout + co] * sc);
+  const int half0 = ks * cs / nr, half1 = cs / nr;
+  for (int r = 0; r < nr; ++r) {
+    size_t off = static_cast<size_t>(r) * g.b_bytes / 2;
+    for (int kk = 0; kk < g.seg_ksteps[0]; ++kk)
+      for (int dx = 0; dx < ks; ++dx, off += g.b_tile_bytes / 2)
+        for (int dy = 0; dy < ks; ++dy)
+          for (int co = 0; co < d.cout; ++co) {
+            const int row = (ks - 1 - dy) * cs + co - r * half0;
+            if (row < 0 || row >= half0) continue;
+            const float sc = scale[0] ? scale[0][co] : 1.0f;
+            for (int c = 0; c < 16; ++c) {
+              const int ci = kk * 16 + c;
+              if (ci >= d.seg_cin[0]) break;
+              wp[off + swz_elem(row, c, 16)] = cvt(w[0][((static_cast<size_t>(dy) * ks + dx) * d.seg_cin[0] + ci) * d.cout + co] * sc);
+            }
           }
+    for (int kk = 0; d.nseg > 1 && kk < g.seg_ksteps[1]; ++kk, off += g.b_sc_tile_bytes / 2)
+      for (int co = 0; co < d.cout; ++co) {
+        const int row = co - r * half1;
+        if (row < 0 || row >= half1) continue;
+        const float sc = scale[1] ? scale[1][co] : 1.0f;
+        for (int c = 0; c < 16; ++c) {
+          const int ci = kk * 16 + c;
+          if (ci >= d.seg_cin[1]) break;
+          wp[off + swz_elem(row, c, 16)] = cvt(w[1][static_cast<size_t>(ci) * d.cout + co] * sc);
         }
-  for (int kk = 0; d.nseg > 1 && kk < g.seg_ksteps[1]; ++kk, off += g.b_sc_tile_bytes / 2)
-    for (int co = 0; co < d.cout; ++co) {
-      const float sc = scale[1] ? scale[1][co] : 1.0f;
-      for (int c = 0; c < 16; ++c) {
-        const int ci = kk * 16 + c;
-        if (ci >= d.seg_cin[1]) break;
-        wp[off + swz_elem(co, c, 16)] = cvt(w[1][static_cast<size_t>(ci) * d.cout + co] * sc);
       }
-    }
+  }
   MPG_CUDA(cudaMalloc(&p->d_wpacked, wp.size() * 2));
   MPG_CUDA(cudaMemcpy(p->d_wpacked, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   std::vector<float> sh(64, 0.0f);
@@ -854,13 +874,14 @@ int build_vring(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   q.n = d.n;
   q.h = d.h;
   q.w = d.w;
-  q.strips = ceil_div(d.w, kVrStrip);
-  q.total_rows = d.n * q.strips * d.h;
-  int nctas = p->h->sm_count;
+  q.pair = g.pair;
+  q.units_x = ceil_div(ceil_div(d.w, kVrStrip), nr);
+  q.total_rows = d.n * q.units_x * d.h;
+  int nctas = p->h->sm_count / nr;
   if (const char* e = getenv("MPG_VRING_CTAS")) nctas = atoi(e) > 0 ? atoi(e) : nctas;
   q.rows_per_cta = ceil_div(q.total_rows, nctas);
   if (q.rows_per_cta < 1) q.rows_per_cta = 1;
-  p->grid = ceil_div(q.total_rows, q.rows_per_cta);
+  p->grid = nr * ceil_div(q.total_rows, q.rows_per_cta);
   q.ks = ks;
   q.nseg = d.nseg;
   for (int s = 0; s < 2; ++s) {
@@ -887,7 +908,7 @@ int build_vring(mpg_conv_plan p, const float* w[2], const float* scale[2], const
   q.wpacked = p->d_wpacked;
   if (const char* e = getenv("MPG_VRING_DBG")) q.dbg = atoi(e);
   p->smem_bytes = static_cast<size_t>(q.b_bytes) + static_cast<size_t>(q.na) * q.a_stage_bytes + 1024;
-  int r = vring_set_smem_attr(p->h->device, g.ck, ks, g.nchw, g.groups, p->smem_bytes);
+  int r = vring_set_smem_attr(p->h->device, g.ck, ks, g.nchw, g.groups, g.pair, p->smem_bytes);
   if (r) {
     set_error("cudaFuncSetAttribute(vring, max dynamic smem %zu) failed: %s", p->smem_bytes,
               cudaGetErrorString(static_cast<cudaError_t>(r)));
@@ -907,8 +928,16 @@ bool vring_preferred(const mpg_conv_desc& d, int sm_count) {
     if (atoi(e) == 2) return true;
   }
   if (g.cp <= 8) return false;
+  if (g.pair) {
+    // pairs pay off on deep-K 5x5 layers only (5x5 96->48: 0.59 ms vs 0.88 with the fold; 3x3 128/128->64 at 256^2: 0.43 vs
+    // 0.35 on the tap-by-tap kernel)
+    if (d.seg_ksize[0] != 5 || d.seg_cin[0] < 64) return false;
+    if (const char* e = getenv("MPG_CONV_VRING_PAIRS"))
+      if (atoi(e) == 0) return false;
+  }
   const int strips = ceil_div(d.w, kVrStrip);
   if (strips * kVrStrip * 4 > d.w * 5) return false;  // > 25 % of a strip row would be padding
+  if (g.pair && strips % 2 != 0 && strips < 5) return false;
   return static_cast<long long>(d.n) * strips * d.h >= 8LL * sm_count;
 }
 

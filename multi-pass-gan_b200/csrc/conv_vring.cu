@@ -13,20 +13,22 @@ namespace {
 struct VrIter {
   int cur, end;
   int n, x0, y0, len;
-  __device__ __forceinline__ bool next(const VringParams& p) {
+  // units_x: strips (single CTA) or strip pairs (CTA pair: the CTA of cluster rank r takes strip 2*unit + r) per image row
+  __device__ __forceinline__ bool next(const VringParams& p, int per_unit, int rank) {
     if (cur >= end) return false;
     const int u = cur / p.h;
     y0 = cur - u * p.h;
     len = min(p.h - y0, end - cur);
-    n = u / p.strips;
-    x0 = (u - n * p.strips) * kVrStrip;
+    n = u / p.units_x;
+    x0 = ((u - n * p.units_x) * per_unit + rank) * kVrStrip;
     cur += len;
     return true;
   }
 };
 
-// NCHW: 8-column chunks of a slot an epilogue warp owns; G: epilogue warps per TMEM lane quarter.
-template <int CK, int KS, int NCHW, int G>
+// NCHW: 8-column chunks of a slot an epilogue warp owns; G: epilogue warps per TMEM lane quarter; PAIR: cta_group::2 pairs
+// (adjacent strips, HALF of every weight tile resident per CTA, M = 256 MMAs issued by the leader).
+template <int CK, int KS, int NCHW, int G, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
                   const VringParams p) {
@@ -43,7 +45,7 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_a[kVrMaxStagesA], empty_a[kVrMaxStagesA];
   __shared__ __align__(8) uint64_t slot_full[kVrMaxSlots], slot_free[kVrMaxSlots];
-  __shared__ __align__(8) uint64_t full_b;
+  __shared__ __align__(8) uint64_t full_b, b_ready;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[64];
   __shared__ float s_pn[2][G][128];
@@ -55,7 +57,10 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int row_begin = static_cast<int>(blockIdx.x) * p.rows_per_cta;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int PER_UNIT = PAIR ? 2 : 1;
+  const int irank = static_cast<int>(rank);
+  const int row_begin = static_cast<int>(PAIR ? blockIdx.x >> 1 : blockIdx.x) * p.rows_per_cta;
   const int row_end = min(row_begin + p.rows_per_cta, p.total_rows);
   const int R = p.nslots;
   const int cs = p.cs;
@@ -70,27 +75,34 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
-      mbar_init(&slot_free[i], 4 * G);  // one arrive per epilogue warp
+      mbar_init(&slot_free[i], (PAIR ? 2 : 1) * 4 * G);  // one arrive per epilogue warp (of both CTAs)
     }
     mbar_init(&full_b, 1);
+    mbar_init(&b_ready, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(&tmem_base_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&tmem_base_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  // tensor memory is undefined after allocation and every MMA except a range's first image row accumulates: clear the ring
+  // tensor memory is undefined after allocation and every MMA accumulates: clear it once
   if (warp >= 4 && warp < 8) {
     const uint32_t la = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     for (uint32_t c = 0; c < TMEM_COLS; c += 8) tmem_st8_fill(la + c, 0u);
     tmem_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // (also: the peer's barriers must be initialised before anything signals them)
+  else __syncthreads();
   tc_fence_after();
 
   if (warp == 0) {
@@ -100,7 +112,7 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       int st = 0;
       uint32_t ph = 0;
       VrIter it{row_begin, row_end, 0, 0, 0, 0};
-      while (it.next(p)) {
+      while (it.next(p, PER_UNIT, irank)) {
         const int nrows = it.len + KS - 1;
         for (int wr = 0; wr < nrows; ++wr) {
           const int gy = it.y0 - PAD + wr;
@@ -108,8 +120,14 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             const CUtensorMap* tm = (s == 0) ? &tm_x0 : &tm_x1;
             for (int ch = 0; ch < p.seg_nchunk[s]; ++ch) {
               mbar_wait(&empty_a[st], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_a[st], bytes);
-              tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, it.x0 - PAD, gy, it.n);
+              if (PAIR) {  // both CTAs' rows complete on the LEADER's barrier, which expects the bytes of both
+                if (rank == 0) mbar_arrive_expect_tx(&full_a[st], 2u * bytes);
+                tma_load_4d_2cta(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, mapa_u32(smem_u32(&full_a[st]), 0),
+                                 ch * CK, it.x0 - PAD, gy, it.n);
+              } else {
+                mbar_arrive_expect_tx(&full_a[st], bytes);
+                tma_load_4d(smA + static_cast<size_t>(st) * p.a_stage_bytes, tm, &full_a[st], ch * CK, it.x0 - PAD, gy, it.n);
+              }
               if (++st == p.na) {
                 st = 0;
                 ph ^= 1u;
@@ -122,25 +140,27 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   } else if (warp == 3) {
     // ===================== resident weights, loaded once =====================
     if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(rank) * p.b_bytes;
       mbar_arrive_expect_tx(&full_b, static_cast<uint32_t>(p.b_bytes));
       for (int off = 0; off < p.b_bytes; off += 32768) {
         const int nb = min(32768, p.b_bytes - off);
         bulk_load_1d(smB + off, wsrc + off, static_cast<uint32_t>(nb), &full_b);
       }
+      if (PAIR) {
+        mbar_wait(&full_b, 0);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&b_ready), 0));
+      }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues; PAIR: leader CTA only) ===========
     const uint32_t fmt = p.in_dtype == MPG_F16 ? 0u : 1u;
-    uint32_t idesc_m[6];  // N = m column blocks
-#pragma unroll
-    for (int m = 1; m <= KS; ++m) idesc_m[m] = umma_idesc_f16kind(128, m * cs, fmt);
+    const uint32_t idesc = umma_idesc_f16kind(PAIR ? 256 : 128, KS * cs, fmt);
+    const uint32_t idesc_sc = umma_idesc_f16kind(PAIR ? 256 : 128, cs, fmt);
     const uint32_t smA_lo = ((smem_u32(smA) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t smB_lo = ((smem_u32(smB) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
     const uint32_t b_tile16 = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
     const uint32_t b_sc_tile16 = static_cast<uint32_t>(p.b_sc_tile_bytes) >> 4;
-    const uint32_t blk16 = (static_cast<uint32_t>(cs) * 32u) >> 4;  // one column block of a weight tile
     const int na = p.na, nseg = p.nseg;
     const int nch0 = p.seg_nchunk[0], kl0 = p.seg_klast[0];
     const int nch1 = p.seg_nchunk[1], kl1 = p.seg_klast[1];
@@ -151,24 +171,25 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     int b0 = 0;        // slot of this image row's first column block = (image-row counter) mod R
     int sn = KS - 1;   // slot newly touched by this image row = (counter + KS - 1) mod R ...
     int un = 0;        // ... and how often it has been used before
-    mbar_wait(&full_b, 0);
+    if (PAIR) mbar_wait_cluster(&b_ready, 0);
+    else mbar_wait(&full_b, 0);
     tc_fence_after();
     VrIter it{row_begin, row_end, 0, 0, 0, 0};
-    while (it.next(p)) {
+    while (it.next(p, PER_UNIT, irank)) {
       const int nrows = it.len + KS - 1;
       for (int wr = 0; wr < nrows; ++wr) {
-        if (un > 0) {  // the epilogue has read and cleared the slot's previous output row
-          mbar_wait(&slot_free[sn], static_cast<uint32_t>(un - 1) & 1u);
+        if (un > 0) {  // the epilogue has read and cleared the slot's previous output row (both of its columns ranges)
+          if (PAIR) mbar_wait_cluster(&slot_free[sn], static_cast<uint32_t>(un - 1) & 1u);
+          else mbar_wait(&slot_free[sn], static_cast<uint32_t>(un - 1) & 1u);
           tc_fence_after();
         }
-        const int n1 = min(KS, R - b0);  // column blocks before the ring wraps
-        const uint32_t d1 = tmem_base + static_cast<uint32_t>(b0 * cs);
-        const uint32_t i1 = idesc_m[n1], i2 = idesc_m[KS - n1 > 0 ? KS - n1 : 1];
-        const uint32_t b_wrap = static_cast<uint32_t>(n1) * blk16;
+        // the k column blocks go to the PHYSICAL slots b0 .. b0+k-1: past the end of the ring they land in the k-1
+        // overflow slots, which alias ring slots 0 .. k-2 (the epilogue adds the two halves), so an MMA never splits
+        const uint32_t d = tmem_base + static_cast<uint32_t>(b0 * cs);
         uint32_t b_cur = smB_lo;
-        uint32_t accumulate = wr == 0 ? 0u : 1u;  // a range's first image row overwrites (and discards older partial sums)
         for (int ch = 0; ch < nch0; ++ch) {
-          mbar_wait(&full_a[sa], pa);
+          if (PAIR) mbar_wait_cluster(&full_a[sa], pa);
+          else mbar_wait(&full_a[sa], pa);
           tc_fence_after();
           const uint32_t a_row = smA_lo + static_cast<uint32_t>(sa) * a_stage16;
           const int nk = (ch == nch0 - 1) ? kl0 : KSTEPS;
@@ -179,17 +200,18 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 #pragma unroll
                 for (int dx = 0; dx < KS; ++dx) {
                   const uint64_t ad = (static_cast<uint64_t>(A_HI) << 32) | (a_row + static_cast<uint32_t>(dx) * PX16 + k * 2);
-                  const uint32_t bt = b_cur + static_cast<uint32_t>(k * KS + dx) * b_tile16;
-                  const uint32_t acc = (dx > 0 || k > 0) ? 1u : accumulate;
-                  umma_bf16_ss(d1, ad, (static_cast<uint64_t>(B_HI) << 32) | bt, i1, acc);
-                  if (n1 < KS) umma_bf16_ss(tmem_base, ad, (static_cast<uint64_t>(B_HI) << 32) | (bt + b_wrap), i2, acc);
+                  const uint64_t bd = (static_cast<uint64_t>(B_HI) << 32) | (b_cur + static_cast<uint32_t>(k * KS + dx) * b_tile16);
+                  if (PAIR) umma_bf16_ss_2cta(d, ad, bd, idesc, 1u);
+                  else umma_bf16_ss(d, ad, bd, idesc, 1u);
                 }
               }
             }
           }
           b_cur += static_cast<uint32_t>(nk * KS) * b_tile16;
-          accumulate = 1;
-          if (leader) umma_commit(&empty_a[sa]);
+          if (leader) {
+            if (PAIR) umma_commit_2cta(&empty_a[sa], 3);
+            else umma_commit(&empty_a[sa]);
+          }
           __syncwarp();
           if (++sa == na) {
             sa = 0;
@@ -198,11 +220,10 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         }
         if (nseg > 1) {
           // 1x1 shortcut: centre pixel shift, onto the slot of the output row at this image row (column block PAD)
-          int sc_slot = b0 + PAD;
-          if (sc_slot >= R) sc_slot -= R;
-          const uint32_t ds = tmem_base + static_cast<uint32_t>(sc_slot * cs);
+          const uint32_t ds = d + static_cast<uint32_t>(PAD * cs);
           for (int ch = 0; ch < nch1; ++ch) {
-            mbar_wait(&full_a[sa], pa);
+            if (PAIR) mbar_wait_cluster(&full_a[sa], pa);
+            else mbar_wait(&full_a[sa], pa);
             tc_fence_after();
             const uint32_t a_tap = smA_lo + static_cast<uint32_t>(sa) * a_stage16 + static_cast<uint32_t>(PAD) * PX16;
             const int nk = (ch == nch1 - 1) ? kl1 : KSTEPS;
@@ -211,12 +232,17 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
               for (int k = 0; k < KSTEPS; ++k) {
                 if (k < nk) {
                   const uint64_t ad = (static_cast<uint64_t>(A_HI) << 32) | (a_tap + k * 2);
-                  umma_bf16_ss(ds, ad, (static_cast<uint64_t>(B_HI) << 32) | (b_cur + static_cast<uint32_t>(k) * b_sc_tile16), idesc_m[1], 1u);
+                  const uint64_t bd = (static_cast<uint64_t>(B_HI) << 32) | (b_cur + static_cast<uint32_t>(k) * b_sc_tile16);
+                  if (PAIR) umma_bf16_ss_2cta(ds, ad, bd, idesc_sc, 1u);
+                  else umma_bf16_ss(ds, ad, bd, idesc_sc, 1u);
                 }
               }
             }
             b_cur += static_cast<uint32_t>(nk) * b_sc_tile16;
-            if (leader) umma_commit(&empty_a[sa]);
+            if (leader) {
+              if (PAIR) umma_commit_2cta(&empty_a[sa], 3);
+              else umma_commit(&empty_a[sa]);
+            }
             __syncwarp();
             if (++sa == na) {
               sa = 0;
@@ -224,7 +250,10 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             }
           }
         }
-        if (leader) umma_commit(&slot_full[b0]);  // slot b0 has received its last tap
+        if (leader) {  // slot b0 has received its last tap
+          if (PAIR) umma_commit_2cta(&slot_full[b0], 3);
+          else umma_commit(&slot_full[b0]);
+        }
         __syncwarp();
         if (++b0 == R) b0 = 0;
         if (++sn == R) {
@@ -248,7 +277,7 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     int slot = 0;
     uint32_t use = 0;
     VrIter it{row_begin, row_end, 0, 0, 0, 0};
-    while (it.next(p)) {
+    while (it.next(p, PER_UNIT, irank)) {
       const int gx = it.x0 + ew * 32 + lane;
       const bool col_ok = gx < p.w && !(p.dbg & 1);
       const int nrows = it.len + KS - 1;
@@ -257,27 +286,36 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         mbar_wait(&slot_full[slot], use & 1u);
         tc_fence_after();
         const uint32_t taddr = lane_addr + static_cast<uint32_t>(slot * cs + grp * NCHW * 8);
+        const uint32_t talias = taddr + static_cast<uint32_t>(R * cs);  // overflow slot R + slot (exists for slot < KS-1)
+        const bool alias = slot < KS - 1;
         const int orow = wr - (KS - 1);  // output row (relative to y0) held by this slot; < 0: rows above the range
         float o[NCHW * 8];
         if (orow >= 0) {
 #pragma unroll
           for (int c = 0; c < NCHW; ++c) {
             if (grp * NCHW + c < nchunks) {
-              uint32_t r[8];
+              uint32_t r[8], r2[8];
               tmem_ld8(taddr + static_cast<uint32_t>(c * 8), r);
+              if (alias) tmem_ld8(talias + static_cast<uint32_t>(c * 8), r2);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[c * 8 + j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 8; ++j) o[c * 8 + j] = __uint_as_float(r[j]) + (alias ? __uint_as_float(r2[j]) : 0.0f);
             }
           }
         }
 #pragma unroll
         for (int c = 0; c < NCHW; ++c)
-          if (grp * NCHW + c < nchunks) tmem_st8_fill(taddr + static_cast<uint32_t>(c * 8), 0u);
+          if (grp * NCHW + c < nchunks) {
+            tmem_st8_fill(taddr + static_cast<uint32_t>(c * 8), 0u);
+            if (alias) tmem_st8_fill(talias + static_cast<uint32_t>(c * 8), 0u);
+          }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[slot]);
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&slot_free[slot]), 0));
+          else mbar_arrive(&slot_free[slot]);
+        }
         if (++slot == R) {
           slot = 0;
           ++use;
@@ -350,46 +388,52 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 typedef void (*VrKernel)(const CUtensorMap, const CUtensorMap, const VringParams);
 
-template <int CK, int KS>
+template <int CK, int KS, bool PAIR>
 VrKernel vr_kernel_cfg(int nchw, int g) {
   if (g == 1) {
     switch (nchw) {
-      case 1: return conv_vring_kernel<CK, KS, 1, 1>;
-      default: return conv_vring_kernel<CK, KS, 2, 1>;
+      case 1: return conv_vring_kernel<CK, KS, 1, 1, PAIR>;
+      default: return conv_vring_kernel<CK, KS, 2, 1, PAIR>;
     }
   }
   switch (nchw) {
-    case 1: return conv_vring_kernel<CK, KS, 1, 2>;
-    case 2: return conv_vring_kernel<CK, KS, 2, 2>;
-    case 3: return conv_vring_kernel<CK, KS, 3, 2>;
-    default: return conv_vring_kernel<CK, KS, 4, 2>;
+    case 1: return conv_vring_kernel<CK, KS, 1, 2, PAIR>;
+    case 2: return conv_vring_kernel<CK, KS, 2, 2, PAIR>;
+    case 3: return conv_vring_kernel<CK, KS, 3, 2, PAIR>;
+    default: return conv_vring_kernel<CK, KS, 4, 2, PAIR>;
   }
 }
 
-VrKernel vr_kernel(int ck, int ks, int nchw, int g) {
-  if (ck == 64) return ks == 5 ? vr_kernel_cfg<64, 5>(nchw, g) : vr_kernel_cfg<64, 3>(nchw, g);
-  return ks == 5 ? vr_kernel_cfg<32, 5>(nchw, g) : vr_kernel_cfg<32, 3>(nchw, g);
+VrKernel vr_kernel(int ck, int ks, int nchw, int g, int pair) {
+  if (pair) {
+    if (ck == 64) return ks == 5 ? vr_kernel_cfg<64, 5, true>(nchw, g) : vr_kernel_cfg<64, 3, true>(nchw, g);
+    return ks == 5 ? vr_kernel_cfg<32, 5, true>(nchw, g) : vr_kernel_cfg<32, 3, true>(nchw, g);
+  }
+  if (ck == 64) return ks == 5 ? vr_kernel_cfg<64, 5, false>(nchw, g) : vr_kernel_cfg<64, 3, false>(nchw, g);
+  return ks == 5 ? vr_kernel_cfg<32, 5, false>(nchw, g) : vr_kernel_cfg<32, 3, false>(nchw, g);
 }
 
 }  // namespace
 
-static size_t g_vr_smem_attr[kMaxDevices][32] = {};  // per device: cudaFuncSetAttribute applies to the current device only
+static size_t g_vr_smem_attr[kMaxDevices][64] = {};  // per device: cudaFuncSetAttribute applies to the current device only
 
-int vring_set_smem_attr(int device, int ck, int ks, int nchw, int g, size_t smem_bytes) {
-  const int slot = (ck == 64 ? 0 : 16) + (ks == 5 ? 0 : 8) + (g - 1) * 4 + (nchw - 1);
+int vring_set_smem_attr(int device, int ck, int ks, int nchw, int g, int pair, size_t smem_bytes) {
+  const int slot = (pair ? 32 : 0) + (ck == 64 ? 0 : 16) + (ks == 5 ? 0 : 8) + (g - 1) * 4 + (nchw - 1);
   const bool cached = device >= 0 && device < kMaxDevices;
   if (cached && smem_bytes <= g_vr_smem_attr[device][slot]) return 0;
   DeviceGuard guard(device);
-  cudaError_t e = cudaFuncSetAttribute(vr_kernel(ck, ks, nchw, g), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(vr_kernel(ck, ks, nchw, g, pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes));
   if (e == cudaSuccess && cached) g_vr_smem_attr[device][slot] = smem_bytes;
   return static_cast<int>(e);
@@ -397,8 +441,25 @@ int vring_set_smem_attr(int device, int ck, int ks, int nchw, int g, size_t smem
 
 int vring_launch(int ck, int nchw, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const VringParams& p, int grid,
                  size_t smem_bytes, cudaStream_t stream) {
-  vr_kernel(ck, p.ks, nchw, p.epi_groups)<<<grid, 128 + 128 * p.epi_groups, smem_bytes, stream>>>(tm_x0, tm_x1, p);
-  return static_cast<int>(cudaGetLastError());
+  const unsigned threads = 128u + 128u * static_cast<unsigned>(p.epi_groups);
+  if (!p.pair) {
+    vr_kernel(ck, p.ks, nchw, p.epi_groups, 0)<<<grid, threads, smem_bytes, stream>>>(tm_x0, tm_x1, p);
+    return static_cast<int>(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, vr_kernel(ck, p.ks, nchw, p.epi_groups, 1), tm_x0, tm_x1, p));
 }
 
 }  // namespace mpg

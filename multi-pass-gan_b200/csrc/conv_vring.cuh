@@ -7,14 +7,18 @@
 //   * TMEM holds a RING of R = 512 / cs output-row accumulators ("slots": 128 pixels x cs columns, cs = round_up(Cout, 16));
 //     output row o lives in slot (o + k - 1) mod R;
 //   * image row r (N = k * cs columns, column block j <-> vertical tap dy = k-1-j) is accumulated straight onto the k
-//     consecutive slots r .. r+k-1: ONE MMA per (dx, K-step) of N = k*cs columns, or two narrower ones when the k slots wrap
-//     around the end of the ring (B descriptor advanced by whole column blocks);
-//   * a slot is complete once the image row with its last tap has been issued; the epilogue reads just those cs columns
-//     (k times less TMEM traffic, no adds), writes zeros back (tcgen05.st) and hands the slot to the MMA warp again. Every MMA
-//     accumulates; only the first image row of a row range overwrites (accumulate = 0), which also discards the partial sums a
-//     previous range left in the ring;
-//   * single CTA per SM (cta_group::1): the narrow wrap MMAs need the whole B tile, which a CTA pair splits in halves. The
-//     weights stay resident as [dx][K-step] tiles of N x 16 channels (32-byte rows, SWIZZLE_32B), <= ~150 KB.
+//     consecutive slots r .. r+k-1 by ONE MMA per (dx, K-step). The ring is followed by k-1 OVERFLOW slots: when the k slots
+//     would wrap around the end of the ring the MMA simply runs on into them (overflow slot R+i aliases ring slot i), so an
+//     MMA never has to be split -- which is what lets CTA pairs, whose B halves fit exactly one N, use the scheme;
+//   * a slot is complete once the image row with its last tap has been issued; the epilogue reads just those cs columns (plus
+//     the alias for the first k-1 slots: k times less TMEM traffic than the fold), writes zeros back (tcgen05.st) and hands
+//     the slot to the MMA warp again. Every MMA accumulates. The partial sums a row range leaves behind in the ring sit in
+//     slots whose outputs the next range discards (the k-1 rows above its first output row) and are cleared with them;
+//   * single CTA per SM for the thin layers (no cross-CTA hand-overs: a row is only a few hundred MMA cycles), CTA pairs
+//     (cta_group::2, adjacent strips, HALF of every weight tile per CTA) for wide N: an SS-mode MMA fetches its operands at
+//     ~64 B/clk per SM, so a single CTA needs (4 KB + N * 32 B) / 64 cycles per MMA -- 184 for N = 240 against 120 tensor
+//     cycles -- while a pair fetches only N/2 weight rows per CTA. Weights stay resident as [K-step][dx] tiles of N x 16
+//     channels (32-byte rows, SWIZZLE_32B).
 // A operand, strips, flattened (image, strip, row) work ranges and SAME padding by TMA zero fill are as in conv_vfold.cuh.
 #pragma once
 #include "common.h"
@@ -27,15 +31,16 @@ constexpr int kVrMaxSlots = 32;
 
 struct VringParams {
   int n, h, w;
-  int strips;        // 128-pixel strips per image row
-  int total_rows;    // n * strips * h
-  int rows_per_cta;  // contiguous (image, strip, row) units per CTA
+  int pair;          // cta_group::2 CTA pairs on adjacent strips, half of every weight tile per CTA
+  int units_x;       // 128-pixel strips (or strip pairs) per image row
+  int total_rows;    // n * units_x * h
+  int rows_per_cta;  // contiguous (image, strip [pair], row) units per CTA (pair)
   int ks;
   int nseg;
   int seg_nchunk[2];  // Cin chunks of CK channels (one TMA box each)
   int seg_klast[2];   // K=16 steps of the last chunk
   int cs;             // slot width in columns = round_up(cout, 16)
-  int nslots;         // R
+  int nslots;         // R ring slots; k-1 overflow slots follow them in tensor memory ((R + k - 1) * cs <= 512)
   int cp, cout;
   int act, pixel_norm;
   int in_dtype, out_dtype, out_cstride;
@@ -53,6 +58,6 @@ struct VringParams {
 
 int vring_launch(int ck, int nchw, const CUtensorMap& tm_x0, const CUtensorMap& tm_x1, const VringParams& p, int grid,
                  size_t smem_bytes, cudaStream_t stream);
-int vring_set_smem_attr(int device, int ck, int ks, int nchw, int groups, size_t smem_bytes);
+int vring_set_smem_attr(int device, int ck, int ks, int nchw, int groups, int pair, size_t smem_bytes);
 
 }  // namespace mpg

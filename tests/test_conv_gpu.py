@@ -86,6 +86,8 @@ CASES = {
     "vr_k5_64to24_f32": dict(n=1, h=16, w=131, cins=[64], ks=[5], cout=24, out_dtype="f32", act="relu", force_kind=6),
     "vr_ragged_37x45": dict(n=3, h=37, w=45, cins=[48], ks=[5], cout=24, act="lrelu", with_scale=True, force_kind=6),
     "vr_tiny_3x5": dict(n=1, h=3, w=5, cins=[16], ks=[3], cout=16, act="relu", force_kind=6),
+    "vr_k5_96to48_pair_only": dict(n=1, h=20, w=260, cins=[96], ks=[5], cout=48, act="lrelu", force_kind=6),
+    "vr_k5_128to32_pair_only": dict(n=2, h=40, w=300, cins=[128], ks=[5], cout=32, act="relu", force_kind=6),
     "vr_k5_48to48_512": dict(n=2, h=128, w=512, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, force_kind=6),
     "forced_direct_16bit": dict(n=1, h=32, w=32, cins=[64], ks=[3], cout=64, force_kind=2, act="relu"),
 }
@@ -129,12 +131,29 @@ def test_vfold_row_ranges_crossing_images(name, pairs, monkeypatch):
     assert r["rel_l2"] < 8e-4, (name, r)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("name", sorted(k for k in CASES if k.startswith("vr_") and "pair_only" not in k))
+def test_vring_single_cta_and_cta_pairs(name, pair, monkeypatch):
+    """Every TMEM-ring case in both launch forms: one CTA per strip, and cta_group::2 pairs on adjacent strips with half of
+    every weight tile per CTA (odd strip counts leave the second CTA of the last pair without pixels)."""
+    monkeypatch.setenv("MPG_VRING_PAIR", pair)
+    kw = dict(CASES[name])
+    for key in ("in_dtype", "out_dtype"):
+        if kw.get(key, "bf16") == "bf16":
+            kw[key] = "f16"
+    r = run_case(**kw)
+    assert r["finite"] and r["pad_ok"] and r["kind"] == 6, r
+    assert r["rel_l2"] < (8e-4 if kw["out_dtype"] != "f32" else 2e-5), (name, r)
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
 @pytest.mark.parametrize("ctas", ["1", "3", "7"])
 @pytest.mark.parametrize("name", ["vr_k5_48and96_to48_pn", "vr_ragged_37x45", "vr_k3_64to64_pn", "vr_k5_24to12_pn"])
-def test_vring_row_ranges_crossing_images(name, ctas, monkeypatch):
+def test_vring_row_ranges_crossing_images(name, ctas, pair, monkeypatch):
     """Few CTAs = long contiguous row ranges: the TMEM ring wraps many times and crosses strip / image boundaries (the
-    first image row of every new range overwrites the partial sums the previous one left in the ring)."""
+    partial sums a range leaves in the ring land in slots whose outputs the next range discards)."""
     monkeypatch.setenv("MPG_VRING_CTAS", ctas)
+    monkeypatch.setenv("MPG_VRING_PAIR", pair)
     kw = dict(CASES[name])
     for key in ("in_dtype", "out_dtype"):
         if kw.get(key, "bf16") == "bf16":
@@ -147,11 +166,17 @@ def test_vring_row_ranges_crossing_images(name, ctas, monkeypatch):
 def test_row_streaming_auto_rule_picks_wide_images():
     """Auto kind: the row-streaming kernel takes medium / narrow Cout layers on wide images, nothing else."""
     r = run_case(n=4, h=256, w=512, cins=[128], ks=[5], cout=32, act="relu", in_dtype="f16", out_dtype="f16")
-    assert r["kind"] == 5 and r["rel_l2"] < 8e-4, r  # weights too large for one CTA: the fold with CTA pairs
+    assert r["kind"] == 6 and r["rel_l2"] < 8e-4, r  # weights too large for one CTA: the ring with CTA pairs
     r = run_case(n=4, h=256, w=512, cins=[48], ks=[5], cout=48, act="relu", pixel_norm=True, in_dtype="f16", out_dtype="f16")
     assert r["kind"] == 6 and r["rel_l2"] < 8e-4, r  # the TMEM-ring variant
     r = run_case(n=4, h=256, w=512, cins=[32], ks=[5], cout=8, act="relu", in_dtype="f16", out_dtype="f16")
     assert r["kind"] == 3, r
+
+
+def test_vfold_is_the_fallback_when_the_ring_is_off(monkeypatch):
+    monkeypatch.setenv("MPG_CONV_VRING", "0")
+    r = run_case(n=4, h=256, w=512, cins=[128], ks=[5], cout=32, act="relu", in_dtype="f16", out_dtype="f16")
+    assert r["kind"] == 5 and r["rel_l2"] < 8e-4, r
     r = run_case(n=1, h=64, w=64, cins=[48], ks=[5], cout=48, act="relu", in_dtype="f16", out_dtype="f16")
     assert r["kind"] == 1, r
     r = run_case(n=1, h=128, w=512, cins=[128], ks=[5], cout=128, act="relu", in_dtype="f16", out_dtype="f16")

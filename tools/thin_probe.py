@@ -61,6 +61,9 @@ CONFIGS = {
     "vf_skel": {"MPG_VFOLD_DBG": "6"},
     "vf_na2": {"MPG_VFOLD_NA": "2"},
     "vr": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0"},
+    "vr_single": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_PAIR": "0"},
+    "vr_pair": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_PAIR": "1"},
+    "vr_pair_noepi": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_PAIR": "1", "MPG_VRING_DBG": "2"},
     "vr_nostore": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "1"},
     "vr_noepi": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "2"},
     "vr_nomma": {"MPG_CONV_VRING": "1", "MPG_CONV_VFOLD": "0", "MPG_VRING_DBG": "4"},
