@@ -202,6 +202,14 @@ int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_
                       int src_c, int mode, void* bicubic_plan, int n, int out_h, int out_w, int src_h,
                       int src_w, float* out, void* stream);
 
+/* Density output of the out.py generators in one pass: out[n,y,x] = sum_c x[n,y,x,c] * w[c] + bias + R(src[..., src_c]),
+ * i.e. the 1x1 conv g_cdensOut (gain 1, no activation, GAN/multipassGAN-out.py:282) fused with the additive residual of
+ * mpg_dens_residual (:327-332). x: NHWC features (MPG_F32, or 16-bit at a channel stride that is a multiple of 8);
+ * w_host: HOST fp32 [cin] (wscale folded), cin <= 64; mode -1 = no residual, 0 / 2 as mpg_dens_residual. */
+int mpg_dens_out(mpg_handle h, const void* x, int x_dtype, int x_cstride, int cin, const float* w_host, float bias,
+                 const void* src, int src_dtype, int src_cstride, int src_c, int mode, void* bicubic_plan, int n,
+                 int out_h, int out_w, int src_h, int src_w, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Volume pipeline (replaces the host numpy/scipy code of generate3DUniForNewNetwork,
  * GAN/multipassGAN-out.py:390-618 and GAN/multipassGAN-4x.py:1090-1169)

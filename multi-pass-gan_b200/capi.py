@@ -115,6 +115,7 @@ def lib():
     L.mpg_bicubic_plan_create.argtypes = [vp, ip, ip, ip, ip, ctypes.POINTER(vp)]
     L.mpg_bicubic_plan_destroy.argtypes = [vp]
     L.mpg_dens_residual.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
+    L.mpg_dens_out.argtypes = [vp, vp, ip, ip, ip, fp, ctypes.c_float, vp, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
     L.mpg_count_saturated.argtypes = [vp, vp, ctypes.c_longlong, ip, vp, vp]
     L.mpg_resize_images.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, vp]
     L.mpg_slice_assemble.argtypes = [vp, ctypes.POINTER(AssembleDesc), vp, vp, ip, ip, vp, vp]
@@ -363,6 +364,17 @@ def dens_residual(handle, dens, src, src_dtype, src_cstride, src_c, mode, bicubi
                                   int(mode), bicubic_plan.ptr if bicubic_plan is not None else None, int(n),
                                   int(out_h), int(out_w), int(src_h), int(src_w), _ptr(out), stream),
           "mpg_dens_residual")
+
+
+def dens_out(handle, x, x_dtype, x_cstride, cin, w, bias, src, src_dtype, src_cstride, src_c, mode, bicubic_plan, n, out_h,
+             out_w, src_h, src_w, out, stream=0):
+    """g_cdensOut (1x1 conv to one channel) + the additive density residual in one launch (mpg_dens_out)."""
+    wv = np.ascontiguousarray(w, dtype=np.float32).reshape(-1)
+    check(lib().mpg_dens_out(handle.ptr, _ptr(x), int(x_dtype), int(x_cstride), int(cin),
+                             wv.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.c_float(float(bias)),
+                             _ptr(src) if src is not None else None, int(src_dtype), int(src_cstride), int(src_c), int(mode),
+                             bicubic_plan.ptr if bicubic_plan is not None else None, int(n), int(out_h), int(out_w),
+                             int(src_h), int(src_w), _ptr(out), stream), "mpg_dens_out")
 
 
 def resize_images(handle, src, src_dtype, src_cstride, c, n, src_h, src_w, out, out_dtype, out_cstride, out_h, out_w, mode,

@@ -4,6 +4,8 @@
 //                        tf.concat / tf.slice GAN/multipassGAN-out.py:330-332,357)
 //   mpg_dens_residual   out = dens + {channel | TF1 legacy bicubic resize of channel} of the network input
 //                       (addBicubicUpsample, GAN/multipassGAN-out.py:327-332 -> tools_wscale/GAN.py:541 mode 2)
+#include <string.h>
+
 #include <vector>
 
 #include "common.h"
@@ -17,7 +19,10 @@ constexpr int kPackRows = 8;
 struct PackSrc {
   const void* ptr;
   int dtype, cstride, c0, nch, fh, fw;
+  int sh, sw;    // source image size = out size / factor (host-computed: integer divisions bounded this kernel)
+  int lfh, lfw;  // log2 of the factors when they are powers of two, else -1
 };
+__device__ __forceinline__ int pack_div(int v, int f, int lf) { return lf >= 0 ? (v >> lf) : v / f; }
 struct PackParams {
   PackSrc src[kMaxSrc];
   int nsrc;
@@ -32,11 +37,16 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
   if (x >= p.ow) return;
   // kPackRows image rows per block: one-row blocks finish in well under a microsecond and the kernel was bound by the
   // block launch rate (8192 blocks for 8 x 512^2), not by memory
+  const int row0 = static_cast<int>(blockIdx.y) * kPackRows;
+  int n = row0 / p.oh;
+  int y = row0 - n * p.oh - 1;
   for (int rr = 0; rr < kPackRows; ++rr) {
-  const int row = static_cast<int>(blockIdx.y) * kPackRows + rr;
+  const int row = row0 + rr;
   if (row >= p.n * p.oh) return;
-  const int n = row / p.oh;
-  const int y = row - n * p.oh;
+  if (++y == p.oh) {
+    y = 0;
+    ++n;
+  }
   const long long pix = static_cast<long long>(row) * p.ow + x;
   int oc = 0;
   if (p.out_dtype != MPG_F32 && (p.out_cstride & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
@@ -46,8 +56,7 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
     unsigned long long lo = 0ull, hi = 0ull;  // dynamic shifts instead of a dynamically indexed array (stays in registers)
     for (int s = 0; s < p.nsrc; ++s) {
       const PackSrc& q = p.src[s];
-      const int sh = p.oh / q.fh, sw = p.ow / q.fw;
-      const long long spix = (static_cast<long long>(n) * sh + y / q.fh) * sw + x / q.fw;
+      const long long spix = (static_cast<long long>(n) * q.sh + pack_div(y, q.fh, q.lfh)) * q.sw + pack_div(x, q.fw, q.lfw);
       const bool vec4 = q.dtype == MPG_F32 && q.nch == 4 && ((spix * q.cstride + q.c0) & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0;
       float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -80,8 +89,7 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
   }
   for (int s = 0; s < p.nsrc; ++s) {
     const PackSrc& q = p.src[s];
-    const int sh = p.oh / q.fh, sw = p.ow / q.fw;
-    const long long spix = (static_cast<long long>(n) * sh + y / q.fh) * sw + x / q.fw;
+    const long long spix = (static_cast<long long>(n) * q.sh + pack_div(y, q.fh, q.lfh)) * q.sw + pack_div(x, q.fw, q.lfw);
     for (int c = 0; c < q.nch; ++c, ++oc) {
       float v;
       if (q.dtype == MPG_F32)
@@ -146,6 +154,71 @@ __global__ void __launch_bounds__(256) dens_residual_kernel(const DensParams p) 
     }
   }
   p.out[pix] = p.dens[pix] + add;
+}
+
+// Density output of the out.py generators in ONE pass: the 1x1 conv to a single channel (g_cdensOut, gain 1, no activation,
+// GAN/multipassGAN-out.py:282) plus the additive residual (:327-332) -- the conv as its own launch re-read the whole
+// feature tensor through the tensor-core path (N padded to 16) and the residual made another pass over the fp32 image.
+struct DensOutParams {
+  DensParams d;      // d.dens unused; d.mode: -1 no residual, 0 channel add, 2 TF1 bicubic
+  const void* x;     // [n, oh, ow, x_cstride] features
+  int x_dtype, x_cstride, cin;
+  float bias;
+  float w[64];
+};
+
+// One thread per output pixel, grid = (ceil(ow / 256), n * oh): 32-bit index arithmetic, the weights are uniform constant-bank
+// operands, and the bicubic tables are read as ONE 16-byte vector each -- the kernel is bound by its load instructions
+// (L1 hits), not by HBM: a lanes-per-pixel variant with shuffles issued 2-4x more of them and measured 1.5-2x slower.
+__global__ void __launch_bounds__(256) dens_out_kernel(const __grid_constant__ DensOutParams q) {
+  const DensParams& p = q.d;
+  const int x = static_cast<int>(blockIdx.x) * 256 + static_cast<int>(threadIdx.x);
+  if (x >= p.ow) return;
+  const int rowi = static_cast<int>(blockIdx.y);
+  const int n = rowi / p.oh;
+  const int y = rowi - n * p.oh;
+  const long long pix = static_cast<long long>(rowi) * p.ow + x;
+  float acc = q.bias;
+  if (q.x_dtype == MPG_F32) {
+    const float* xp = reinterpret_cast<const float*>(q.x) + pix * q.x_cstride;
+    for (int c = 0; c < q.cin; ++c) acc = fmaf(__ldg(xp + c), q.w[c], acc);
+  } else {
+    const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(q.x) + pix * q.x_cstride);
+    const int nv = (q.cin + 7) >> 3;
+#pragma unroll 4
+    for (int v = 0; v < nv; ++v) {
+      const uint4 u = __ldg(xp + v);
+      const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = v * 8 + j * 2;  // (channels beyond cin are zero in the tensor and have zero weights here)
+        acc = fmaf(h16_to_float(static_cast<uint16_t>(wd[j] & 0xFFFFu), q.x_dtype), q.w[c], acc);
+        acc = fmaf(h16_to_float(static_cast<uint16_t>(wd[j] >> 16), q.x_dtype), q.w[c + 1], acc);
+      }
+    }
+  }
+  if (p.mode == 0) {
+    acc += src_at(p, n, y, x);
+  } else if (p.mode == 2) {
+    // TF1 ResizeBicubic: interpolate along x for each of the 4 rows, then along y (fp32); tables are [size][4]
+    const int4 ix = __ldg(reinterpret_cast<const int4*>(p.ix) + x);
+    const float4 wx = __ldg(reinterpret_cast<const float4*>(p.wx) + x);
+    const int4 iy = __ldg(reinterpret_cast<const int4*>(p.iy) + y);
+    const float4 wy = __ldg(reinterpret_cast<const float4*>(p.wy) + y);
+    const int sy[4] = {iy.x, iy.y, iy.z, iy.w};
+    const float wyv[4] = {wy.x, wy.y, wy.z, wy.w};
+    float add = 0.0f;
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+      float row = src_at(p, n, sy[ty], ix.x) * wx.x;
+      row += src_at(p, n, sy[ty], ix.y) * wx.y;
+      row += src_at(p, n, sy[ty], ix.z) * wx.z;
+      row += src_at(p, n, sy[ty], ix.w) * wx.w;
+      add += row * wyv[ty];
+    }
+    acc += add;
+  }
+  p.out[pix] = acc;
 }
 
 // Standalone tf.image.resize_images for any channel count (tools_wscale/GAN.py:541 avg_depool modes 0 / 2 when the
@@ -280,8 +353,13 @@ int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* ou
     MPG_CHECK_ARG(oh % srcs[s].factor_h == 0 && ow % srcs[s].factor_w == 0, "pack: size not divisible by factor");
     MPG_CHECK_ARG(srcs[s].c0 >= 0 && srcs[s].nch > 0 && srcs[s].c0 + srcs[s].nch <= srcs[s].cstride,
                   "pack: channel range of source %d", s);
+    auto lg2 = [](int f) {
+      int l = 0;
+      while ((1 << l) < f) ++l;
+      return (1 << l) == f ? l : -1;
+    };
     p.src[s] = {srcs[s].ptr, srcs[s].dtype, srcs[s].cstride, srcs[s].c0, srcs[s].nch, srcs[s].factor_h,
-                srcs[s].factor_w};
+                srcs[s].factor_w, oh / srcs[s].factor_h, ow / srcs[s].factor_w, lg2(srcs[s].factor_h), lg2(srcs[s].factor_w)};
     total += srcs[s].nch;
   }
   MPG_CHECK_ARG(total <= out_cstride, "pack: %d channels do not fit out_cstride %d", total, out_cstride);
@@ -414,6 +492,57 @@ int mpg_dens_residual(mpg_handle h, const float* dens, const void* src, int src_
   p.out = out;
   const long long npix = static_cast<long long>(n) * out_h * out_w;
   dens_residual_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+int mpg_dens_out(mpg_handle h, const void* x, int x_dtype, int x_cstride, int cin, const float* w_host, float bias,
+                 const void* src, int src_dtype, int src_cstride, int src_c, int mode, void* bicubic_plan, int n, int out_h,
+                 int out_w, int src_h, int src_w, float* out, void* stream) {
+  using namespace mpg;
+  MPG_CHECK_ARG(h && x && w_host && out, "mpg_dens_out: null argument");
+  MPG_CHECK_ARG(cin >= 1 && cin <= 64 && x_cstride >= cin, "mpg_dens_out: cin=%d (1..64) x_cstride=%d", cin, x_cstride);
+  MPG_CHECK_ARG(is_dtype(x_dtype), "mpg_dens_out: bad x_dtype %d", x_dtype);
+  MPG_CHECK_ARG(x_dtype == MPG_F32 || (x_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0),
+                "mpg_dens_out: 16-bit features need a channel stride that is a multiple of 8 and a 16-byte aligned tensor");
+  MPG_CHECK_ARG(mode == -1 || mode == 0 || mode == 2, "mpg_dens_out: mode must be -1 (no residual), 0 (channel add) or 2 (TF1 bicubic)");
+  MPG_CHECK_ARG(mode == -1 || src != nullptr, "mpg_dens_out: residual source missing");
+  MPG_CHECK_ARG(mode != 0 || (src_h == out_h && src_w == out_w), "mpg_dens_out: mode 0 needs equal sizes");
+  MPG_CHECK_ARG(mode != 2 || bicubic_plan != nullptr, "mpg_dens_out: bicubic plan missing");
+  DensOutParams q;
+  memset(&q, 0, sizeof(q));
+  DensParams& p = q.d;
+  p.src = src;
+  p.src_dtype = src_dtype;
+  p.src_cstride = src_cstride;
+  p.src_c = src_c;
+  p.mode = mode;
+  p.n = n;
+  p.oh = out_h;
+  p.ow = out_w;
+  p.sh = src_h;
+  p.sw = src_w;
+  if (mode == 2) {
+    const char* d = static_cast<const char*>(bicubic_plan);
+    const size_t ni = static_cast<size_t>(out_h + out_w) * 4;
+    p.iy = reinterpret_cast<const int*>(d);
+    p.ix = p.iy + static_cast<size_t>(out_h) * 4;
+    p.wy = reinterpret_cast<const float*>(d + ni * 4);
+    p.wx = p.wy + static_cast<size_t>(out_h) * 4;
+  }
+  p.out = out;
+  q.x = x;
+  q.x_dtype = x_dtype;
+  q.x_cstride = x_cstride;
+  q.cin = cin;
+  q.bias = bias;
+  for (int c = 0; c < cin; ++c) q.w[c] = w_host[c];
+  DeviceGuard guard(h->device);
+  const long long npix = static_cast<long long>(n) * out_h * out_w;
+  (void)npix;
+  MPG_CHECK_ARG(static_cast<long long>(n) * out_h <= 65535, "mpg_dens_out: n*out_h = %lld rows exceed the grid limit", static_cast<long long>(n) * out_h);
+  const dim3 blocks(static_cast<unsigned>((out_w + 255) / 256), static_cast<unsigned>(n * out_h));
+  dens_out_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

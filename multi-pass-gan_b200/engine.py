@@ -73,6 +73,13 @@ class Group:
         self.out_node = conv
 
 
+class _PendingDens:
+    """Placeholder view of a 1x1 density-output conv whose launch is fused with the residual add that consumes it."""
+
+    def __init__(self, grp):
+        self.grp = grp
+
+
 class CompiledNet:
     def __init__(self, output, weights, batch, precision="fp16", handle=None, device=0, verbose=False, dry=False,
                  range_check=False):
@@ -277,10 +284,26 @@ class CompiledNet:
                     continue
                 self._side_of[id(gp)] = (gx, cs)
 
+        # ---- density output (g_cdensOut: 1x1 conv to ONE channel, no activation, GAN/multipassGAN-out.py:282) whose only
+        #      consumer is the additive residual (:327-332): one bandwidth-bound launch (mpg_dens_out) instead of a padded
+        #      tensor-core conv plus a second pass over the fp32 image
+        dens_fused = set()
+        if int(os.environ.get("MPG_FUSE_DENSOUT", "1")):
+            for gd in groups_by_out.values():
+                c = gd.convs[0]
+                if (len(gd.convs) == 1 and c.attrs["ksize"] == 1 and c.attrs["stride"] == 1 and c.out.shape[3] == 1
+                        and gd.act is None and not gd.pn and gd.ups == 1 and gd.out_node is c and c is not output.node
+                        and c.attrs["bn"] is None and c.inputs[0].shape[3] <= 64
+                        and len(uses[c.id]) == 1 and uses[c.id][0].op == "add" and uses[c.id][0].out.shape[3] == 1):
+                    dens_fused.add(id(gd))
+
         views = {}
         for n in nodes:
             if n.id in groups_by_out:
                 grp = groups_by_out[n.id]
+                if id(grp) in dens_fused:
+                    views[n.id] = _PendingDens(grp)
+                    continue
                 if id(grp) in rb_of_a:
                     xin = views[grp.convs[0].inputs[0].node.id]
                     if self._thin_resblock_input(xin, grp.convs[0]) is not None:
@@ -370,13 +393,22 @@ class CompiledNet:
         va, vb = views[n.inputs[0].node.id], views[n.inputs[1].node.id]
         if n.out.shape[3] != 1:
             raise NotImplementedError("standalone add is only implemented for the 1-channel density residual")
-        dens = va.whole_buf()
-        other = vb
-        if dens is None or dens.dtype != capi.F32:
-            dens, other = vb.whole_buf(), va
-        if dens is None or dens.dtype != capi.F32:
-            raise NotImplementedError("density residual: neither operand is a dense fp32 tensor")
-        out = self._alloc(dens.h, dens.w, 1, capi.F32)
+        pend = va if isinstance(va, _PendingDens) else (vb if isinstance(vb, _PendingDens) else None)
+        feat = None
+        if pend is not None:
+            conv = pend.grp.convs[0]
+            other = vb if pend is va else va
+            feat = self._materialize(views[conv.inputs[0].node.id], self.act_dtype)
+            oh, ow = feat.h, feat.w
+        else:
+            dens = va.whole_buf()
+            other = vb
+            if dens is None or dens.dtype != capi.F32:
+                dens, other = vb.whole_buf(), va
+            if dens is None or dens.dtype != capi.F32:
+                raise NotImplementedError("density residual: neither operand is a dense fp32 tensor")
+            oh, ow = dens.h, dens.w
+        out = self._alloc(oh, ow, 1, capi.F32)
         handle = self.h
         if other.bicubic_of is not None and other.resize_mode != 2:
             other = View(other.h, other.w, [(self._materialize(other, capi.F32), 0, other.c, 1, 1)])
@@ -386,7 +418,7 @@ class CompiledNet:
             assert nch == 1 and fh == 1 and fw == 1
             plan = None
             if not self.dry:
-                plan = capi.BicubicPlan(handle, sv.h, sv.w, dens.h, dens.w)
+                plan = capi.BicubicPlan(handle, sv.h, sv.w, oh, ow)
                 self.plans.append(plan)
             mode, sh, sw = 2, sv.h, sv.w
         else:
@@ -394,7 +426,27 @@ class CompiledNet:
             if fh != 1 or fw != 1:
                 sb = self._materialize(other, capi.F32)
                 c0 = 0
-            plan, mode, sh, sw = None, 0, dens.h, dens.w
+            plan, mode, sh, sw = None, 0, oh, ow
+
+        if feat is not None:
+            w_eff, sc, shift = self._conv_affine(conv)
+            cin = w_eff.shape[2]
+            wvec = (w_eff[0, 0, :, 0] * (sc[0] if sc is not None else 1.0)).astype(np.float32)
+            bias = float(shift[0])
+            flops = 2.0 * self.batch * oh * ow * cin
+            self.flops += flops
+
+            def step(stream):
+                capi.dens_out(handle, self._p(feat), feat.dtype, feat.cstride, cin, wvec, bias, self._p(sb), sb.dtype, sb.cstride,
+                              c0, mode, plan, out.n, oh, ow, sh, sw, self._p(out), stream)
+
+            label = "dens_out %s k1 %d->1 + residual mode %d %dx%d" % (
+                conv.attrs["weight"]["var"].name.rsplit("/", 2)[-2], cin, mode, oh, ow)
+            if self.verbose:
+                print(label)
+            self.step_flops[len(self.steps)] = flops
+            self.steps.append((label, step))
+            return View(out.h, out.w, [(out, 0, 1, 1, 1)])
 
         def step(stream):
             capi.dens_residual(handle, self._p(dens), self._p(sb), sb.dtype, sb.cstride, c0, mode, plan, out.n, dens.h,

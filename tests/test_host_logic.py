@@ -50,14 +50,15 @@ def test_growing_gen_graphs_and_fusion():
     lab = _labels(net)
     assert sum("up2" in l for l in lab) == 2  # genBlock2->4 and 4->8 nearest x2 fused into the producer epilogue
     assert all(" pn" in l for l in lab if l.startswith("conv") and "cdensOut" not in l)
-    assert lab[-1] == "dens_residual mode 2" and "g_cdensOut8" in lab[-2]
+    # g_cdensOut8 (1x1 -> one channel) and the bicubic residual are ONE launch (mpg_dens_out)
+    assert lab[-1].startswith("dens_out g_cdensOut8 k1 32->1 + residual mode 2")
     assert abs(net.flops / (8 * 128 * 128) - 521216) < 1e-6
     G.reset_default_graph()
     out2 = P.build_out_graph(2, P.SHIPPED_8X[2], cfg)
     w2 = W.init_graph_variables(G.get_default_graph(), 1)
     assert sum(v.size for v in w2.values()) == 774301
     net2 = engine.CompiledNet(out2, w2, 2, dry=True)
-    assert _labels(net2)[-1] == "dens_residual mode 0" and _labels(net2)[0] == "pack 128x128x5"
+    assert _labels(net2)[-1].startswith("dens_out g_cdensOut8 k1 12->1 + residual mode 0") and _labels(net2)[0] == "pack 128x128x5"
     assert abs(net2.flops / (2 * 128 * 128) - 1546768) < 1e-6
     assert set(net2.placeholders) == {"x", "y"}
 

@@ -109,3 +109,41 @@ def test_resize_images_kernel(mode, factor):
     ref = fn(torch.from_numpy(x).double(), oh, ow).numpy()
     assert np.abs(got[..., :c] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
     assert (got[..., c:] == 0).all()  # padded channels are written as zeros
+
+
+@pytest.mark.parametrize("mode", [-1, 0, 2])
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
+def test_dens_out_fused_density_output(mode, dt):
+    """mpg_dens_out = g_cdensOut (1x1 conv to one channel, GAN/multipassGAN-out.py:282) + the additive residual (:327-332)
+    in one launch, against the separate oracle ops."""
+    import numpy as np
+    from mpgan_b200 import capi
+    from oracle import tf_ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    n, h, w, cin, cs = 2, 40, 48, 12, 16
+    tdt = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[dt]
+    code = {"f16": capi.F16, "bf16": capi.BF16, "f32": capi.F32}[dt]
+    x = torch.zeros(n, h, w, cs)
+    x[..., :cin] = torch.randn(n, h, w, cin, generator=g)
+    xd = x.to(tdt).to(dev)
+    wv = torch.randn(cin, generator=g).numpy().astype(np.float32)
+    bias = 0.1
+    want = torch.einsum("nhwc,c->nhw", xd.double()[..., :cin].cpu(), torch.from_numpy(wv).double()) + bias
+    hd = capi.default_handle(0)
+    plan, src, sh, sw = None, None, h, w
+    if mode == 0:
+        src = torch.randn(n, h, w, 5, generator=g).to(dev)
+        want = want + src.double().cpu()[..., 2]
+    elif mode == 2:
+        sh, sw = h // 8, w // 8
+        src = torch.randn(n, sh, sw, 5, generator=g).to(dev)
+        up = tf_ops.resize_bicubic_tf1(src.cpu().double()[..., 2:3], h, w)
+        want = want + up[..., 0]
+        plan = capi.BicubicPlan(hd, sh, sw, h, w)
+    out = torch.full((n, h, w), float("nan"), device=dev)
+    capi.dens_out(hd, xd, code, cs, cin, wv, bias, src, capi.F32, 5, 2, mode, plan, n, h, w, sh, sw, out,
+                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    err = float((out.double().cpu() - want).abs().max())
+    assert err < 2e-5 * max(1.0, float(want.abs().max())), err
