@@ -779,8 +779,15 @@ bool vring_geometry(const mpg_conv_desc& d, VrGeom* g, int pair = -1) {
   if (g->nslots > kVrMaxSlots) g->nslots = kVrMaxSlots;
   if (g->nslots < ks + 1) return false;
   g->nchunks = cp / 8;
-  g->groups = g->nchunks > 1 ? 2 : 1;
+  // epilogue warp groups per TMEM lane quarter x 8-column chunks per warp (measured: 48 columns 3 x 2, 64 columns 4 x 2
+  // are 4-6 % faster than 2 x 3 / 2 x 4)
+  g->groups = g->nchunks > 6 ? 4 : (g->nchunks > 4 ? 3 : (g->nchunks > 1 ? 2 : 1));
   g->nchw = ceil_div(g->nchunks, g->groups);
+  if (const char* e = getenv("MPG_VRING_GROUPS")) {
+    const int gg = atoi(e);
+    if (gg == 2 && g->nchunks > 1) g->groups = 2, g->nchw = ceil_div(g->nchunks, 2);
+    if (gg == 4 && g->nchunks >= 3) g->groups = 4, g->nchw = ceil_div(g->nchunks, 4);
+  }
   int maxcin = 0;
   for (int s = 0; s < d.nseg; ++s) maxcin = d.seg_cin[s] > maxcin ? d.seg_cin[s] : maxcin;
   const int ck = maxcin > 32 ? 64 : 32, rb = ck * 2;

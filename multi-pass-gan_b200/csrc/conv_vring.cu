@@ -291,15 +291,21 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const int orow = wr - (KS - 1);  // output row (relative to y0) held by this slot; < 0: rows above the range
         float o[NCHW * 8];
         if (orow >= 0) {
+          // all loads of the row in flight at once, ONE wait (a wait per chunk serialised NCHW TMEM round trips per row)
+          uint32_t r[NCHW][8], r2[NCHW][8];
 #pragma unroll
           for (int c = 0; c < NCHW; ++c) {
             if (grp * NCHW + c < nchunks) {
-              uint32_t r[8], r2[8];
-              tmem_ld8(taddr + static_cast<uint32_t>(c * 8), r);
-              if (alias) tmem_ld8(talias + static_cast<uint32_t>(c * 8), r2);
-              tmem_ld_wait();
+              tmem_ld8(taddr + static_cast<uint32_t>(c * 8), r[c]);
+              if (alias) tmem_ld8(talias + static_cast<uint32_t>(c * 8), r2[c]);
+            }
+          }
+          tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[c * 8 + j] = __uint_as_float(r[j]) + (alias ? __uint_as_float(r2[j]) : 0.0f);
+          for (int c = 0; c < NCHW; ++c) {
+            if (grp * NCHW + c < nchunks) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[c * 8 + j] = __uint_as_float(r[c][j]) + (alias ? __uint_as_float(r2[c][j]) : 0.0f);
             }
           }
         }
@@ -407,6 +413,13 @@ VrKernel vr_kernel_cfg(int nchw, int g) {
       default: return conv_vring_kernel<CK, KS, 2, 1, PAIR>;
     }
   }
+  if (g == 3) return conv_vring_kernel<CK, KS, 2, 3, PAIR>;
+  if (g == 4) {
+    switch (nchw) {
+      case 1: return conv_vring_kernel<CK, KS, 1, 4, PAIR>;
+      default: return conv_vring_kernel<CK, KS, 2, 4, PAIR>;
+    }
+  }
   switch (nchw) {
     case 1: return conv_vring_kernel<CK, KS, 1, 2, PAIR>;
     case 2: return conv_vring_kernel<CK, KS, 2, 2, PAIR>;
@@ -426,10 +439,10 @@ VrKernel vr_kernel(int ck, int ks, int nchw, int g, int pair) {
 
 }  // namespace
 
-static size_t g_vr_smem_attr[kMaxDevices][64] = {};  // per device: cudaFuncSetAttribute applies to the current device only
+static size_t g_vr_smem_attr[kMaxDevices][128] = {};  // per device: cudaFuncSetAttribute applies to the current device only
 
 int vring_set_smem_attr(int device, int ck, int ks, int nchw, int g, int pair, size_t smem_bytes) {
-  const int slot = (pair ? 32 : 0) + (ck == 64 ? 0 : 16) + (ks == 5 ? 0 : 8) + (g - 1) * 4 + (nchw - 1);
+  const int slot = (pair ? 64 : 0) + (ck == 64 ? 0 : 32) + (ks == 5 ? 0 : 16) + (g - 1) * 4 + (nchw - 1);
   const bool cached = device >= 0 && device < kMaxDevices;
   if (cached && smem_bytes <= g_vr_smem_attr[device][slot]) return 0;
   DeviceGuard guard(device);

@@ -1,4 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/s5f_bench.json 2> gpurun_out/s5f_bench.err; echo rc=$?
-python -c "
-import json;d=json.load(open('gpurun_out/s5f_bench.json'));print({k:d[k] for k in ('value','ms_per_step','frac_of_bf16_peak','clocks')});print(d['parity']['gate'], d['checksum']['bits']);print({k:(v['ms_per_step'],v.get('frac_of_bf16_peak'),v.get('checksum_bits')) for k,v in d['secondary'].items()})"
+for g in 2 3 4; do echo "== groups $g"; MPG_VRING_GROUPS=$g python tools/prof_conv.py n2_48to48,n2_48_96to48,n1_64to64k3 4; done
+MPG_VRING_GROUPS=4 timeout 600 python -m pytest tests/test_conv_gpu.py -x -q -k "vr_ or vring" 2>&1 | tail -2
