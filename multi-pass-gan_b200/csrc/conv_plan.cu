@@ -752,9 +752,10 @@ bool vfold_preferred(const mpg_conv_desc& d, int sm_count) {
   if (d.seg_ksize[0] != 5 || d.seg_cin[0] < min_cin) return false;
   const int strips = ceil_div(d.w, kVfStrip);
   if (d.w < 2 * kVfStrip || (strips % 2 != 0 && strips < 5)) return false;
-  const long long total = static_cast<long long>(d.n) * ceil_div(strips, 2) * d.h;
-  if (total < 16LL * (sm_count / 2)) return false;
-  return true;
+  // (independent of the batch size on purpose: the same layer must pick the same kernel in a 1-GPU and an N-GPU run, which
+  //  process different numbers of slices per launch, for the sharded volume to stay bit-identical)
+  (void)sm_count;
+  return d.h >= 64;
 }
 
 // ---- row-streaming kernel with the vertical-tap sum accumulated in a TMEM ring (conv_vring.cu) ----
@@ -945,7 +946,9 @@ bool vring_preferred(const mpg_conv_desc& d, int sm_count) {
   const int strips = ceil_div(d.w, kVrStrip);
   if (strips * kVrStrip * 4 > d.w * 5) return false;  // > 25 % of a strip row would be padding
   if (g.pair && strips % 2 != 0 && strips < 5) return false;
-  return static_cast<long long>(d.n) * strips * d.h >= 8LL * sm_count;
+  // (independent of the batch size on purpose, see vfold_preferred)
+  (void)sm_count;
+  return d.h >= 64;
 }
 
 int build_direct(mpg_conv_plan p, const float* w[2], const float* scale[2], const float* shift) {

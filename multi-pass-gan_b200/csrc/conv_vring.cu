@@ -45,7 +45,7 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_a[kVrMaxStagesA], empty_a[kVrMaxStagesA];
   __shared__ __align__(8) uint64_t slot_full[kVrMaxSlots], slot_free[kVrMaxSlots];
-  __shared__ __align__(8) uint64_t full_b, b_ready;
+  __shared__ __align__(8) uint64_t full_b, b_ready, seg_flushed;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_shift[64];
   __shared__ float s_pn[2][G][128];
@@ -79,6 +79,7 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     }
     mbar_init(&full_b, 1);
     mbar_init(&b_ready, 2);
+    mbar_init(&seg_flushed, (PAIR ? 2 : 1) * 4 * G);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -168,9 +169,16 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const bool leader = elect_one() != 0;
     int sa = 0;
     uint32_t pa = 0;
-    int b0 = 0;        // slot of this image row's first column block = (image-row counter) mod R
-    int sn = KS - 1;   // slot newly touched by this image row = (counter + KS - 1) mod R ...
-    int un = 0;        // ... and how often it has been used before
+    // Ring positions are a function of the IMAGE ROW (slot of a row's first column block = row mod R), not of a running
+    // counter: which contributions of an output row land in an overflow slot -- i.e. the order its fp32 partial sums are
+    // added in -- then depends on the row alone, and the result is bit-identical however the rows are cut into ranges
+    // (batch size, number of GPUs). The price: a range leaves k-1 partially written slots at positions unrelated to the
+    // next range, so the epilogue clears them and the next range waits for that (seg_flushed).
+    int b0 = 0;
+    uint32_t need_wait = 0;  // bit s: slot s was handed to the MMAs and its output row is (or will be) read by the epilogue
+    uint32_t free_par = 0;   // bit s: parity of the next completion of slot_free[s] to wait for
+    uint32_t garbage = 0;    // slots the previous range left partially written (cleared by the epilogue's flush)
+    int seg = 0;
     if (PAIR) mbar_wait_cluster(&b_ready, 0);
     else mbar_wait(&full_b, 0);
     tc_fence_after();
@@ -178,11 +186,30 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     while (it.next(p, PER_UNIT, irank)) {
       const int nrows = it.len + KS - 1;
       for (int wr = 0; wr < nrows; ++wr) {
-        if (un > 0) {  // the epilogue has read and cleared the slot's previous output row (both of its columns ranges)
-          if (PAIR) mbar_wait_cluster(&slot_free[sn], static_cast<uint32_t>(un - 1) & 1u);
-          else mbar_wait(&slot_free[sn], static_cast<uint32_t>(un - 1) & 1u);
-          tc_fence_after();
+        int first_new = KS - 1;  // column blocks [first_new, KS) touch slots this row is the first to use
+        if (wr == 0) {
+          if (seg > 0) {
+            if (PAIR) mbar_wait_cluster(&seg_flushed, static_cast<uint32_t>(seg - 1) & 1u);
+            else mbar_wait(&seg_flushed, static_cast<uint32_t>(seg - 1) & 1u);
+            tc_fence_after();
+            need_wait &= ~garbage;
+          }
+          ++seg;
+          b0 = it.y0 % R;
+          first_new = 0;
         }
+        for (int j = first_new; j < KS; ++j) {
+          int sn = b0 + j;
+          if (sn >= R) sn -= R;
+          const uint32_t bit = 1u << sn;
+          if (need_wait & bit) {  // the epilogue has read and cleared the slot's previous output row
+            if (PAIR) mbar_wait_cluster(&slot_free[sn], (free_par >> sn) & 1u);
+            else mbar_wait(&slot_free[sn], (free_par >> sn) & 1u);
+            free_par ^= bit;
+          }
+          need_wait |= bit;
+        }
+        tc_fence_after();
         // the k column blocks go to the PHYSICAL slots b0 .. b0+k-1: past the end of the ring they land in the k-1
         // overflow slots, which alias ring slots 0 .. k-2 (the epilogue adds the two halves), so an MMA never splits
         const uint32_t d = tmem_base + static_cast<uint32_t>(b0 * cs);
@@ -256,10 +283,12 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         }
         __syncwarp();
         if (++b0 == R) b0 = 0;
-        if (++sn == R) {
-          sn = 0;
-          ++un;
-        }
+      }
+      garbage = 0;  // slots b0 .. b0+k-2 (b0 already advanced) hold partial sums of rows below the range
+      for (int j = 0; j < KS - 1; ++j) {
+        int sg = b0 + j;
+        if (sg >= R) sg -= R;
+        garbage |= 1u << sg;
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * G) {
@@ -275,15 +304,17 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     int pn_slot = 0;
     int slot = 0;
-    uint32_t use = 0;
+    uint32_t full_par = 0;  // bit s: parity of the next completion of slot_full[s]
     VrIter it{row_begin, row_end, 0, 0, 0, 0};
     while (it.next(p, PER_UNIT, irank)) {
       const int gx = it.x0 + ew * 32 + lane;
       const bool col_ok = gx < p.w && !(p.dbg & 1);
       const int nrows = it.len + KS - 1;
+      slot = it.y0 % R;  // ring position = image row mod R (see the MMA warp)
 #pragma unroll 1
       for (int wr = 0; wr < nrows; ++wr) {
-        mbar_wait(&slot_full[slot], use & 1u);
+        mbar_wait(&slot_full[slot], (full_par >> slot) & 1u);
+        full_par ^= 1u << slot;
         tc_fence_after();
         const uint32_t taddr = lane_addr + static_cast<uint32_t>(slot * cs + grp * NCHW * 8);
         const uint32_t talias = taddr + static_cast<uint32_t>(R * cs);  // overflow slot R + slot (exists for slot < KS-1)
@@ -322,9 +353,29 @@ conv_vring_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&slot_free[slot]), 0));
           else mbar_arrive(&slot_free[slot]);
         }
-        if (++slot == R) {
-          slot = 0;
-          ++use;
+        const bool last_row = wr == nrows - 1;
+        if (++slot == R) slot = 0;
+        if (last_row) {
+          // the k-1 slots after the last output row hold partial sums of rows below the range: clear them (the MMAs that
+          // wrote them completed before slot_full of this row) and tell the MMA warp the ring is clean
+          for (int j = 0; j < KS - 1; ++j) {
+            int sg = slot + j;
+            if (sg >= R) sg -= R;
+            const uint32_t tg = lane_addr + static_cast<uint32_t>(sg * cs + grp * NCHW * 8);
+#pragma unroll
+            for (int c = 0; c < NCHW; ++c)
+              if (grp * NCHW + c < nchunks) {
+                tmem_st8_fill(tg + static_cast<uint32_t>(c * 8), 0u);
+                if (sg < KS - 1) tmem_st8_fill(tg + static_cast<uint32_t>(R * cs + c * 8), 0u);
+              }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&seg_flushed), 0));
+            else mbar_arrive(&seg_flushed);
+          }
         }
         if (orow < 0 || (p.dbg & 2)) continue;
         const int y = it.y0 + orow;

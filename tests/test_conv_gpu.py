@@ -163,6 +163,43 @@ def test_vring_row_ranges_crossing_images(name, ctas, pair, monkeypatch):
     assert r["rel_l2"] < 8e-4, (name, r)
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_vring_is_bit_identical_for_any_row_partition(pair, monkeypatch):
+    """Ring positions are a function of the image row, so the order an output's fp32 partial sums are added in does not
+    depend on how the rows are cut into per-CTA ranges: the same slices give the same bits whatever the CTA count or the
+    number of slices per launch (what keeps a slice-sharded N-GPU volume identical to the single-GPU one)."""
+    import numpy as np
+    import torch
+    from mpgan_b200 import capi
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    n, h, w, cin, cout = 6, 70, 300, 48, 48
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.float16).to(dev)
+    xs = torch.randn(n, h, w, 96, generator=g).to(torch.float16).to(dev)
+    w5 = (torch.randn(5, 5, cin, cout, generator=g) * (np.sqrt(2.0) / np.sqrt(25 * cin))).numpy()
+    w1 = (torch.randn(1, 1, 96, cout, generator=g) * (np.sqrt(2.0) / np.sqrt(96))).numpy()
+    hd = capi.default_handle(0)
+    st = torch.cuda.current_stream().cuda_stream
+    monkeypatch.setenv("MPG_VRING_PAIR", pair)
+
+    def run(ctas, n_run):
+        monkeypatch.setenv("MPG_VRING_CTAS", ctas)
+        plan = capi.ConvPlan(hd, n_run, h, w, [w5, w1], [cin, 96], cout, cout, act="relu", pixel_norm=True, in_dtype=capi.F16,
+                             out_dtype=capi.F16, force_kind=6)
+        assert plan.kind == capi.KIND_VRING
+        y = torch.empty(n_run, h, w, cout, dtype=torch.float16, device=dev)
+        plan.run(x[:n_run].contiguous(), xs[:n_run].contiguous(), y, st)
+        torch.cuda.synchronize()
+        plan.close()
+        return y
+
+    ref = run("148", n)
+    for ctas in ("1", "5", "37"):
+        assert torch.equal(run(ctas, n), ref), ctas
+    assert torch.equal(run("148", 2), ref[:2])  # fewer slices per launch: other ranges, same bits
+    assert torch.equal(run("3", 1), ref[:1])
+
+
 def test_row_streaming_auto_rule_picks_wide_images():
     """Auto kind: the row-streaming kernel takes medium / narrow Cout layers on wide images, nothing else."""
     r = run_case(n=4, h=256, w=512, cins=[128], ks=[5], cout=32, act="relu", in_dtype="f16", out_dtype="f16")

@@ -1,1 +1,2 @@
-python bench.py --steps 2 --warmup 3 > gpurun_out/s5g_plain.json 2> gpurun_out/s5g_plain.err && ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 --csv --log-file gpurun_out/r02b_launches_bench_default.csv python bench.py --steps 2 --warmup 3 > gpurun_out/s5g_ncu.log 2>&1; echo rc=$?; tail -2 gpurun_out/s5g_ncu.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/r02e_bench_n1.json 2> gpurun_out/r02e_bench_n1.err; echo rc=$?
