@@ -1,0 +1,144 @@
+"""ORACLE (test infrastructure only): pieces of the 8x progressive-growing trainer on CPU, torch fp64.
+
+Restates GAN/multipassGAN-8x.py for the configuration the shipped training command uses for the first network
+(GAN/example_run_training.py:4: `firstNNArch 1 upsamplingMode 2 use_wgan_gp 1 batchNorm 0 gDrop 0 use_mb_stddev 0`):
+  lerp :596-597, growBlockDisc :752-780, growing_disc :782-866 (spatial discriminator grown stage by stage, every stage
+  blended in with lerp(old, new, percentage - (j-1))), the WGAN-GP discriminator / generator losses :1101-1143
+  (tf.gradients of the critic w.r.t. the interpolated sample: a double backward here), the per-stage variable selection of
+  the optimizers :1304-1362 ("%i" % 2**i in var.name), TF1 Adam (oracle.training.Adam) and the generator weight averaging
+  of tf.contrib.opt.MovingAverageOptimizer(…, 0.999) :1356-1361.
+Pinned by golden vectors produced by executing the reference's own growing_disc / growBlockDisc / lerp on the numpy TF1
+shim (tests/golden/make_golden.py growdisc -> tests/golden/growdisc.npz); gradients are torch autograd in fp64.
+Out of scope: temporal discriminator / advection (:868-923, lambda_t), loss scaling (numerically the identity), gDrop noise.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import gan as og
+from . import tf_ops
+
+
+def lerp(x, y, t):
+    """GAN/multipassGAN-8x.py:596-597."""
+    return x + (y - x) * torch.clamp(torch.as_tensor(t, dtype=x.dtype), 0.0, 1.0)
+
+
+def avg_pool2(x):
+    """GAN.avg_pool default (tools_wscale/GAN.py:162-169): tf.nn.avg_pool 2x2 stride 2 VALID, NHWC."""
+    return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+
+
+class Cfg8x:
+    """Flags of GAN/multipassGAN-8x.py that shape growing_disc (defaults of the shipped first-network command)."""
+
+    def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3,
+                 first_nn_arch=True, upsampleMode=1):
+        self.tileSizeLow, self.upRes = int(tileSizeLow), int(upRes)
+        self.tileSizeHigh = self.tileSizeLow * self.upRes
+        self.n_inputChannels = int(n_inputChannels)
+        self.start_fms, self.max_fms, self.filterSize = int(start_fms), int(max_fms), int(filterSize)
+        self.first_nn_arch = bool(first_nn_arch)
+        self.upsampleMode = int(upsampleMode)
+        self.stages = int(round(math.log(self.upRes, 2)))
+
+
+def grow_block_disc(gan, inp, upres, fms, cfg, name="d"):
+    """growBlockDisc :752-780 (upsampling_mode 2, no batch norm, no gDrop). Returns (pooled x2, x1, x2)."""
+    with gan.ctx.variable_scope(name + "Block%d" % upres):
+        filt = [4, 4] if cfg.first_nn_arch else [cfg.filterSize, cfg.filterSize]
+        out2 = min(min(fms * 2, cfg.max_fms), cfg.start_fms // 2)
+        if cfg.first_nn_arch:
+            c1 = fms * 3 if upres == 2 else fms * 2
+            x1, _ = gan.convolutional_layer(c1, filt, og.lrelu, stride=[1], name="%s_cA%d" % (name, upres), in_layer=inp,
+                                            in_channels=fms)
+            x2, _ = gan.convolutional_layer(out2, filt, og.lrelu, stride=[1], name="%s_cB%d" % (name, upres), in_layer=x1)
+        else:
+            x1, _ = gan.convolutional_layer(fms, filt, og.lrelu, stride=[1], name="%s_cA%d" % (name, upres), in_layer=inp,
+                                            in_channels=fms)
+            x2, _ = gan.convolutional_layer(out2, filt, og.lrelu, stride=[1], name="%s_cB%d" % (name, upres), in_layer=x1,
+                                            in_channels=fms)
+        gan.layer = avg_pool2(gan.layer)  # outp = gan.avg_pool() :771-772
+        return gan.layer, x1, x2
+
+
+def growing_disc(in_high, in_low, percentage, ctx, cfg):
+    """growing_disc :782-866. in_high [B, S*S], in_low [B, L*L*C] flat rows -> (logits [B,1], feature layers)."""
+    L, S, C, u = cfg.tileSizeLow, cfg.tileSizeHigh, cfg.n_inputChannels, cfg.upRes
+    with ctx.variable_scope("spatial-disc"):
+        hi = in_high.reshape(-1, S, S, 1)
+        lo = in_low.reshape(-1, L, L, C)[..., 0:1]                                     # :796
+        lo = og.GAN(lo, ctx).avg_depool(scale=[u], mode=cfg.upsampleMode)              # :797
+        hi = torch.cat([lo, hi], dim=3)                                                # :813
+        feats = []
+        gan = og.GAN(hi, ctx)
+        x_, _ = gan.convolutional_layer(int(cfg.start_fms / u), [1, 1], None, in_layer=hi, stride=[1],
+                                        name="d_cfromDensity%d" % u)                   # :818
+        feats.append(lerp(torch.zeros_like(x_), x_, percentage - (cfg.stages - 1)))
+        in_high_ = hi
+        gan2 = og.GAN(in_high_, ctx)
+        for j in range(cfg.stages, 0, -1):
+            num_fms = int(min(cfg.start_fms / (2 ** j), cfg.max_fms))
+            in_high_ = avg_pool2(in_high_)                                             # :828-829
+            x_, x1, x2 = grow_block_disc(gan, x_, int(2 ** j), num_fms, cfg)           # :833
+            from_dens = min(min(num_fms * 2, cfg.max_fms), cfg.start_fms // 2)
+            old, _ = gan2.convolutional_layer(from_dens, [1, 1], None, stride=[1], name="d_cfromDensity%d" % (2 ** (j - 1)),
+                                              in_layer=in_high_)                       # :836
+            with ctx.variable_scope("blend%i" % j):
+                x_ = lerp(old, x_, percentage - (j - 1))                               # :838-839
+            feats.append(lerp(torch.zeros_like(x1), x1, percentage - (j - 1)))
+            feats.append(lerp(torch.zeros_like(x2), x2, percentage - (j - 1)))
+        if not cfg.first_nn_arch:
+            f = [cfg.filterSize, cfg.filterSize]
+            x1, _ = gan.convolutional_layer(32, f, og.lrelu, stride=[1], name="d_cA1", in_layer=x_)
+            gan.convolutional_layer(4, f, None, stride=[1], name="d_cB1", in_layer=x1)
+        else:
+            # quirk reproduced: nothing moves the GAN cursor here, so flatten() below acts on gan.layer = the pooled output of
+            # the LAST growBlockDisc -- the blend with d_cfromDensity1 only reaches the feature list, not the logits
+            x1 = x_
+        feats.append(lerp(torch.zeros_like(x1), x1, percentage))
+        gan.flatten()
+        gan.fully_connected_layer(1, None, name="d_l61", gain=1)                        # :862
+        return gan.y(), feats
+
+
+def wgan_gp_losses(disc, gen, d_out_fn, y_in, gen_y, lerp_factor, wgan_lambda=10.0, wgan_target=1.0, wgan_epsilon=0.001,
+                   weight_dld=1.0):
+    """Discriminator / generator critic losses with use_wgan_gp (:1101-1143). d_out_fn(y) -> critic logits.
+    lerp_factor: the tf.random_uniform([B, 1]) sample of :1120 (fed in, so that both sides use the same numbers)."""
+    d_loss = (-disc).mean() * weight_dld + gen.mean()
+    y_gp = (lerp_factor * y_in + (1 - lerp_factor) * gen_y).detach().requires_grad_(True)
+    d_out_loss = d_out_fn(y_gp).mean()
+    grads = torch.autograd.grad(d_out_loss, y_gp, create_graph=True)[0]
+    norms = torch.sqrt(((grads + 1e-4) ** 2).sum(dim=1))                               # :1130
+    gp = (wgan_lambda * (norms - wgan_target) ** 2).mean()
+    eps_pen = (disc ** 2).mean()
+    return dict(disc_loss=d_loss + eps_pen * wgan_epsilon + gp, grad_penalty=gp, epsilon_penalty=eps_pen,
+                g_loss_d=(-gen).mean(), grad_norms=norms.detach())
+
+
+def stage_variables(names, z, n_stages=3):
+    """Variable subset optimizer z updates (:1332-1338 / :1349-1355): all of them at the last stage, else those whose name
+    contains "%i" % 2**i for an i in [0, z+1] -- a SUBSTRING test, so "1" also selects every name with a 1 in it
+    (d_cfromDensity16 would match, d_l61 does; reproduced as is)."""
+    if z == n_stages - 1:
+        return list(names)
+    out = []
+    for i in range(0, z + 2):
+        out.extend(n for n in names if ("%i" % (2 ** i)) in n and n not in out)
+    return out
+
+
+def ema_init(values):
+    """ExponentialMovingAverage shadows start at the variables' initial values."""
+    return {k: np.array(v, dtype=np.float64) for k, v in values.items()}
+
+
+def ema_update(shadow, values, decay=0.999):
+    """tf.contrib.opt.MovingAverageOptimizer(opt, 0.999) = ExponentialMovingAverage without num_updates, applied after every
+    optimizer step to the variables that step updates: s -= (1 - decay) * (s - v)."""
+    for k, v in values.items():
+        shadow[k] = shadow[k] - (1.0 - decay) * (shadow[k] - np.asarray(v, np.float64))
+    return shadow

@@ -317,6 +317,52 @@ def make_net_fixtures():
     print("nets.npz written:", len(fixtures), "arrays")
 
 
+# =============================================================================== 8x trainer: growing discriminator
+def make_growdisc_fixtures():
+    """growing_disc / growBlockDisc / lerp of GAN/multipassGAN-8x.py (:596-597, 752-866) executed on the numpy TF1 shim with
+    the module-level flags of the shipped first-network training command (GAN/example_run_training.py:4) at small sizes."""
+    ref_gan = load_ref_gan()
+    code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["lerp", "growBlockDisc", "growing_disc"])
+    fixtures = {}
+    rng = np.random.default_rng(8)
+
+    def run(tag, seed, L, u, C, start_fms, max_fms, first_nn_arch, percentages, filterSize=3):
+        S = L * u
+        store, getv = _provide(seed)
+        tfs.reset({})
+        tfs.get_variable = getv
+        ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, tileSizeLow=L, tileSizeHigh=S, upRes=u,
+                  n_inputChannels=C, upsampling_mode=2, upsampleMode=1, start_fms=start_fms, max_fms=max_fms,
+                  filterSize=filterSize, first_nn_arch=first_nn_arch, useVelInTDisc=False, bn_decay=0.999,
+                  use_mb_stddev=False, gn=lambda x, gstr: x, print=lambda *a, **k: None)
+        exec(code, ns)
+        B = 2
+        x_rows = rng.random((B, L * L * C), dtype=np.float32)
+        y_rows = rng.random((B, S * S), dtype=np.float32)
+        fixtures[tag + "_x"], fixtures[tag + "_y"] = x_rows, y_rows
+        for k, pct in enumerate(percentages):
+            tfs.STATE.requested = {}
+            logits, feats = ns["growing_disc"](tfs.T(y_rows), tfs.T(x_rows), tfs.T(np.float32(pct)), reuse=tfs.AUTO_REUSE,
+                                               use_batch_norm=False, train=False, currentUpres=int(round(math.log(u, 2))))
+            fixtures["%s_p%d_logits" % (tag, k)] = logits.a
+            for i, f in enumerate(feats):  # feature layers: full tensors for one percentage, (sum, sum |.|) for the others
+                if k == 1:
+                    fixtures["%s_p%d_feat%d" % (tag, k, i)] = f.a
+                else:
+                    fixtures["%s_p%d_feat%d_sums" % (tag, k, i)] = np.array([f.a.sum(dtype=np.float64), np.abs(f.a).sum(dtype=np.float64)])
+            print(tag, pct, logits.a.ravel(), len(feats), "feature layers")
+        fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
+        fixtures[tag + "_wsum"] = _wsum(store)
+        fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, C=C, start_fms=start_fms, max_fms=max_fms,
+                                                 first_nn_arch=first_nn_arch, percentages=list(percentages),
+                                                 filterSize=filterSize))
+
+    run("gd_first", 81, 4, 8, 6, 32, 32, True, (0.4, 1.3, 2.75, 3.0))
+    run("gd_plain", 82, 4, 4, 4, 32, 16, False, (0.5, 1.6, 2.0))
+    np.savez_compressed(os.path.join(HERE, "growdisc.npz"), **fixtures)
+    print("growdisc.npz written:", len(fixtures), "arrays")
+
+
 def ref_methods(path, cls, names):
     """The named methods of a reference class, compiled as plain functions."""
     with open(path) as fh:
@@ -602,6 +648,8 @@ if __name__ == "__main__":
         make_pipeline_fixtures()
     if "nets" in which:
         make_net_fixtures()
+    if "growdisc" in which:
+        make_growdisc_fixtures()
     if "tiles" in which:
         make_tile_fixtures()
     if "uni" in which:

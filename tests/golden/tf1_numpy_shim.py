@@ -286,3 +286,24 @@ def kb_resize_images(x, height_factor, width_factor, data_format, interpolation=
 
 
 keras_backend = types.SimpleNamespace(resize_images=kb_resize_images)
+
+
+# ---- ops used by the 8x trainer's growing_disc (GAN/multipassGAN-8x.py:596-597, 752-866; tools_wscale/GAN.py:162-169)
+def zeros_like(x):
+    return T(np.zeros_like(_v(x)))
+
+
+def clip_by_value(x, lo, hi):
+    return T(np.clip(_v(x), lo, hi))
+
+
+def _avg_pool(x, ksize, strides, padding):
+    assert padding == "VALID" and list(ksize) == list(strides) and ksize[0] == 1 and ksize[3] == 1
+    a = _v(x)
+    kh, kw = int(ksize[1]), int(ksize[2])
+    n, h, w, c = a.shape
+    a = a[:, :h // kh * kh, :w // kw * kw]
+    return T(a.reshape(n, h // kh, kh, w // kw, kw, c).mean(axis=(2, 4)))
+
+
+nn.avg_pool = _avg_pool
