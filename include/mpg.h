@@ -357,6 +357,20 @@ int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* 
 int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long npix, int cstride, int c,
                            int accumulate, void* stream);
 
+/* Pieces of the 8x progressive-growing trainer (GAN/multipassGAN-8x.py): 2x2 average pooling of growBlockDisc
+ * (:771-772 -> tools_wscale/GAN.py:162-169; hh, ww = INPUT size), lerp blending of the growing stages (:596-597, t already
+ * clipped), y = alpha x, the WGAN-GP gradient penalty (:1130-1133: g [rows, n] -> *loss += mean_b lambda (|g_b + 1e-4| -
+ * target)^2, v = d penalty / d g, optional per-sample norms) and the critic terms scale * mean(x^power) (:1111-1112, 1140). */
+int mpg_train_avgpool2_fwd(mpg_handle h, const float* x, float* y, int n, int hh, int ww, int c, void* stream);
+int mpg_train_avgpool2_bwd(mpg_handle h, const float* dy, float* dx, int n, int hh, int ww, int c, int accumulate,
+                           void* stream);
+int mpg_train_lerp(mpg_handle h, float* out, const float* a, const float* b, float t, long long count, void* stream);
+int mpg_train_scale(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream);
+int mpg_train_gp_penalty(mpg_handle h, const float* g, float* v, double* loss, float* norms, int rows, long long n,
+                         float lambda, float target, void* stream);
+int mpg_train_mean_pow(mpg_handle h, const float* x, float scale, int power, double* loss, float* dx, long long count,
+                       int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,6 +148,12 @@ def lib():
     L.mpg_train_fc_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_fc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_take_channel.argtypes = [vp, vp, vp, ll, ip, ip, ip, vp]
+    L.mpg_train_avgpool2_fwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp]
+    L.mpg_train_avgpool2_bwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_lerp.argtypes = [vp, vp, vp, vp, fl, ll, vp]
+    L.mpg_train_scale.argtypes = [vp, vp, vp, fl, ll, vp]
+    L.mpg_train_gp_penalty.argtypes = [vp, vp, vp, vp, vp, ip, ll, fl, fl, vp]
+    L.mpg_train_mean_pow.argtypes = [vp, vp, fl, ip, vp, vp, ll, ip, vp]
     _lib = L
     return L
 

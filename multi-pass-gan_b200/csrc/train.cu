@@ -491,6 +491,92 @@ __global__ void __launch_bounds__(256) mul_kernel(float* out, const float* a, co
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     out[e] = a[e] * b[e];
 }
+// ---- pieces of the 8x progressive-growing trainer (GAN/multipassGAN-8x.py:596-597 lerp, tools_wscale/GAN.py:162-169
+//      avg_pool, :1101-1143 WGAN-GP terms)
+__global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const float* x, float* y, int n, int oh, int ow, int c) {
+  const long long total = static_cast<long long>(n) * oh * ow * c;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % c);
+    long long r = e / c;
+    const int ox = static_cast<int>(r % ow);
+    r /= ow;
+    const int oy = static_cast<int>(r % oh);
+    const long long img = r / oh;
+    const long long row = static_cast<long long>(2 * ow) * c;
+    const float* p = x + ((img * (2 * oh) + 2 * oy) * (2 * ow) + 2 * ox) * c + ch;
+    y[e] = 0.25f * ((p[0] + p[c]) + (p[row] + p[row + c]));
+  }
+}
+__global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const float* dy, float* dx, int n, int oh, int ow, int c,
+                                                            int accumulate) {
+  const long long total = static_cast<long long>(n) * (2 * oh) * (2 * ow) * c;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % c);
+    long long r = e / c;
+    const int x = static_cast<int>(r % (2 * ow));
+    r /= 2 * ow;
+    const int y = static_cast<int>(r % (2 * oh));
+    const long long img = r / (2 * oh);
+    const float g = 0.25f * dy[((img * oh + (y >> 1)) * ow + (x >> 1)) * c + ch];
+    dx[e] = accumulate ? dx[e] + g : g;
+  }
+}
+__global__ void __launch_bounds__(256) lerp_kernel(float* out, const float* a, const float* b, float t, long long total) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    out[e] = a[e] + (b[e] - a[e]) * t;
+}
+__global__ void __launch_bounds__(256) scale_kernel(float* y, const float* x, float alpha, long long total) {
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
+    y[e] = alpha * x[e];
+}
+// one block per sample: norm = sqrt(sum (g + 1e-4)^2); loss += lambda * (norm - target)^2 / rows;
+// v = d loss / d g = (2 * lambda / rows) * (norm - target) * (g + 1e-4) / norm      (GAN/multipassGAN-8x.py:1130-1133)
+__global__ void __launch_bounds__(256) gp_penalty_kernel(const float* g, float* v, double* loss, float* norms, int rows,
+                                                          long long n, float lambda, float target) {
+  __shared__ double red[256];
+  const int b = blockIdx.x;
+  const float* gb = g + static_cast<long long>(b) * n;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const double t = static_cast<double>(gb[i]) + 1e-4;
+    s += t * t;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double norm = sqrt(red[0]);
+  const double coef = 2.0 * lambda / rows * (norm - target) / norm;
+  for (long long i = threadIdx.x; i < n; i += 256)
+    v[static_cast<long long>(b) * n + i] = static_cast<float>(coef * (static_cast<double>(gb[i]) + 1e-4));
+  if (threadIdx.x == 0) {
+    atomicAdd(loss, static_cast<double>(lambda) * (norm - target) * (norm - target) / rows);
+    if (norms) norms[b] = static_cast<float>(norm);
+  }
+}
+// loss += scale * mean(x^power) (power 1 or 2), dx (+)= its gradient: the WGAN critic terms mean(-disc), mean(gen),
+// wgan_epsilon * mean(disc^2) (:1111-1112, 1140-1141)
+__global__ void __launch_bounds__(256) mean_pow_kernel(const float* x, float scale, int power, double* loss, float* dx,
+                                                        long long total, int accumulate) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (long long e = threadIdx.x; e < total; e += 256) {
+    const float v = x[e];
+    s += power == 2 ? static_cast<double>(v) * v : static_cast<double>(v);
+    const float g = scale / static_cast<float>(total) * (power == 2 ? 2.0f * v : 1.0f);
+    if (dx) dx[e] = accumulate ? dx[e] + g : g;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(loss, static_cast<double>(scale) * red[0] / static_cast<double>(total));
+}
+
 __global__ void __launch_bounds__(256) dsum_to_f32_kernel(const double* s, float* out, int c, int accumulate) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < c) out[i] = (accumulate ? out[i] : 0.0f) + static_cast<float>(s[i]);
@@ -839,6 +925,56 @@ int mpg_train_act_bwd(mpg_handle h, const float* y, const float* dy, float* dz, 
 int mpg_train_axpy(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream) {
   MPG_CHECK_ARG(h && x && y, "mpg_train_axpy: bad argument");
   axpy_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, alpha, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* 2x2 average pooling, stride 2, VALID (tools_wscale/GAN.py:162-169 avg_pool defaults); hh, ww: INPUT size (even) */
+int mpg_train_avgpool2_fwd(mpg_handle h, const float* x, float* y, int n, int hh, int ww, int c, void* stream) {
+  MPG_CHECK_ARG(h && x && y && hh % 2 == 0 && ww % 2 == 0, "mpg_train_avgpool2_fwd: bad argument");
+  const long long total = static_cast<long long>(n) * (hh / 2) * (ww / 2) * c;
+  avgpool2_fwd_kernel<<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, hh / 2, ww / 2, c);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_avgpool2_bwd(mpg_handle h, const float* dy, float* dx, int n, int hh, int ww, int c, int accumulate,
+                           void* stream) {
+  MPG_CHECK_ARG(h && dy && dx && hh % 2 == 0 && ww % 2 == 0, "mpg_train_avgpool2_bwd: bad argument");
+  const long long total = static_cast<long long>(n) * hh * ww * c;
+  avgpool2_bwd_kernel<<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dx, n, hh / 2, ww / 2, c,
+                                                                                                  accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* out = a + (b - a) * t with t already clipped to [0,1] (lerp, GAN/multipassGAN-8x.py:596-597) */
+int mpg_train_lerp(mpg_handle h, float* out, const float* a, const float* b, float t, long long count, void* stream) {
+  MPG_CHECK_ARG(h && out && a && b, "mpg_train_lerp: bad argument");
+  lerp_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, a, b, t, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* y = alpha * x */
+int mpg_train_scale(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream) {
+  MPG_CHECK_ARG(h && x && y, "mpg_train_scale: bad argument");
+  scale_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, alpha, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* WGAN-GP gradient penalty (GAN/multipassGAN-8x.py:1130-1133): g [rows, n] = gradient of mean(critic) w.r.t. the
+ * interpolated samples; *loss += mean_b lambda (||g_b + 1e-4|| - target)^2, v [rows, n] = d penalty / d g, norms [rows]
+ * (may be NULL) = the per-sample norms */
+int mpg_train_gp_penalty(mpg_handle h, const float* g, float* v, double* loss, float* norms, int rows, long long n,
+                         float lambda, float target, void* stream) {
+  MPG_CHECK_ARG(h && g && v && loss && rows > 0 && n > 0, "mpg_train_gp_penalty: bad argument");
+  gp_penalty_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, v, loss, norms, rows, n, lambda, target);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* *loss += scale * mean(x^power), power 1 or 2; dx (may be NULL) (+)= the gradient (WGAN critic terms :1111-1112, 1140) */
+int mpg_train_mean_pow(mpg_handle h, const float* x, float scale, int power, double* loss, float* dx, long long count,
+                       int accumulate, void* stream) {
+  MPG_CHECK_ARG(h && x && loss && (power == 1 || power == 2) && count > 0, "mpg_train_mean_pow: bad argument");
+  mean_pow_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, scale, power, loss, dx, count, accumulate);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }
