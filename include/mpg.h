@@ -370,6 +370,9 @@ int mpg_train_gp_penalty(mpg_handle h, const float* g, float* v, double* loss, f
                          float lambda, float target, void* stream);
 int mpg_train_mean_pow(mpg_handle h, const float* x, float scale, int power, double* loss, float* dx, long long count,
                        int accumulate, void* stream);
+/* pixel_norm (tools_wscale/GAN.py:472-474) of the growing generator in training mode, x [rows, c], and its backward */
+int mpg_train_pixel_norm_fwd(mpg_handle h, const float* x, float* y, long long rows, int c, void* stream);
+int mpg_train_pixel_norm_bwd(mpg_handle h, const float* x, const float* dy, float* dx, long long rows, int c, void* stream);
 
 #ifdef __cplusplus
 }

@@ -154,6 +154,8 @@ def lib():
     L.mpg_train_scale.argtypes = [vp, vp, vp, fl, ll, vp]
     L.mpg_train_gp_penalty.argtypes = [vp, vp, vp, vp, vp, ip, ll, fl, fl, vp]
     L.mpg_train_mean_pow.argtypes = [vp, vp, fl, ip, vp, vp, ll, ip, vp]
+    L.mpg_train_pixel_norm_fwd.argtypes = [vp, vp, vp, ll, ip, vp]
+    L.mpg_train_pixel_norm_bwd.argtypes = [vp, vp, vp, vp, ll, ip, vp]
     _lib = L
     return L
 

@@ -529,6 +529,31 @@ __global__ void __launch_bounds__(256) scale_kernel(float* y, const float* x, fl
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     y[e] = alpha * x[e];
 }
+// pixel_norm (tools_wscale/GAN.py:472-474): y = x * rsqrt(mean_c x^2 + 1e-8), one thread per pixel; backward:
+// dx = r dy - x r^3 mean_c(dy x)
+__global__ void __launch_bounds__(256) pixel_norm_fwd_kernel(const float* x, float* y, long long rows, int c) {
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < rows; p += static_cast<long long>(gridDim.x) * 256) {
+    const float* xp = x + p * c;
+    float s = 0.0f;
+    for (int i = 0; i < c; ++i) s = fmaf(xp[i], xp[i], s);
+    const float r = rsqrtf(s / static_cast<float>(c) + 1e-8f);
+    for (int i = 0; i < c; ++i) y[p * c + i] = xp[i] * r;
+  }
+}
+__global__ void __launch_bounds__(256) pixel_norm_bwd_kernel(const float* x, const float* dy, float* dx, long long rows, int c) {
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < rows; p += static_cast<long long>(gridDim.x) * 256) {
+    const float* xp = x + p * c;
+    const float* gp = dy + p * c;
+    float s = 0.0f, d = 0.0f;
+    for (int i = 0; i < c; ++i) {
+      s = fmaf(xp[i], xp[i], s);
+      d = fmaf(gp[i], xp[i], d);
+    }
+    const float r = rsqrtf(s / static_cast<float>(c) + 1e-8f);
+    const float k = r * r * r * d / static_cast<float>(c);
+    for (int i = 0; i < c; ++i) dx[p * c + i] = r * gp[i] - xp[i] * k;
+  }
+}
 // one block per sample: norm = sqrt(sum (g + 1e-4)^2); loss += lambda * (norm - target)^2 / rows;
 // v = d loss / d g = (2 * lambda / rows) * (norm - target) * (g + 1e-4) / norm      (GAN/multipassGAN-8x.py:1130-1133)
 __global__ void __launch_bounds__(256) gp_penalty_kernel(const float* g, float* v, double* loss, float* norms, int rows,
@@ -957,6 +982,19 @@ int mpg_train_lerp(mpg_handle h, float* out, const float* a, const float* b, flo
 int mpg_train_scale(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream) {
   MPG_CHECK_ARG(h && x && y, "mpg_train_scale: bad argument");
   scale_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, alpha, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* pixel_norm of the growing generator in training mode (tools_wscale/GAN.py:472-474) and its backward; x [rows, c] */
+int mpg_train_pixel_norm_fwd(mpg_handle h, const float* x, float* y, long long rows, int c, void* stream) {
+  MPG_CHECK_ARG(h && x && y && rows > 0 && c > 0, "mpg_train_pixel_norm_fwd: bad argument");
+  pixel_norm_fwd_kernel<<<grid_for(rows, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, c);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_pixel_norm_bwd(mpg_handle h, const float* x, const float* dy, float* dx, long long rows, int c, void* stream) {
+  MPG_CHECK_ARG(h && x && dy && dx && rows > 0 && c > 0, "mpg_train_pixel_norm_bwd: bad argument");
+  pixel_norm_bwd_kernel<<<grid_for(rows, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, rows, c);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

@@ -14,9 +14,14 @@ no batch norm / gDrop / minibatch stddev in the discriminator):
 * `stage_mask` / `StagedAdam` -- the per-stage optimizers (:1304-1362: optimizer z only updates the variables whose name
   contains "%i" % 2**i, i <= z+1 -- a substring rule, reproduced), TF1 Adam over the flat buffer with a 0/1 mask.
 * `WeightEMA` -- tf.contrib.opt.MovingAverageOptimizer(…, 0.999) (:1356-1361): shadow -= (1 - decay) (shadow - value).
+* `GrowingGen` -- growing_gen in TRAINING mode (:626-750, output=False): per-stage density outputs blended with lerp, nearest
+  x2 between stages, resBlocks with pixel_norm (forward + backward kernels), the TF1-bicubic residual of the input density.
+* `Trainer8x` -- the loop body of :1898-2075 without the temporal terms: critic step, generator step (g_loss_d + lambda l1)
+  through the critic's input gradient, the optimizers of growing stage z, the generator EMA.
 Everything that computes runs in the fp32 training kernels behind the C ABI (mpg_train_*), PyTorch owns the buffers.
 Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned by executing the reference's own functions.
-Not built: the growing generator's training graph, the temporal discriminator, loss scaling, the training loop / CLI.
+Not built: the temporal discriminator / advection (lambda_t), loss scaling (numerically the identity), the feature-layer loss
+(lambda2, 0 in the shipped command), the percentage / learning-rate schedules, data loading and the command line.
 """
 import math
 
@@ -103,8 +108,8 @@ class GrowingDisc:
     """growing_disc (GAN/multipassGAN-8x.py:782-866), upsampling_mode 2."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3,
-                 first_nn_arch=True, batch=16, values=None, seed=1, device=0):
-        self.cx = _Ctx(device)
+                 first_nn_arch=True, batch=16, values=None, seed=1, device=0, cx=None):
+        self.cx = cx if cx is not None else _Ctx(device)
         self.L, self.u, self.S, self.C, self.B = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(n_inputChannels), int(batch)
         self.stages = int(round(math.log(self.u, 2)))
         self.first = bool(first_nn_arch)
@@ -365,3 +370,200 @@ class WeightEMA:
     def export(self):
         host = self.shadow.cpu().numpy()
         return {name: host[off:off + n].reshape(shape).copy() for name, shape, off, n, _ in self.ps.specs}
+
+
+class GrowingGen:
+    """growing_gen in TRAINING mode (GAN/multipassGAN-8x.py:626-750, output=False; firstNNArch, upsampling_mode 2, pixel_norm,
+    no batch norm): nearest x2 per stage, resBlocks  A(k, relu) -> pixel_norm -> B(k) ; s(1x1) ; pixel_norm(relu(B + s)),
+    a density output per stage (1x1, gain 1) [+ the TF1-bicubic upsample of the input density], blended with the
+    nearest-upsampled density of the previous stage by lerp(old, new, percentage - (j-1)). Forward and backward."""
+
+    def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
+                 addBicubicUpsample=True, values=None, seed=1, device=0, cx=None):
+        self.cx = cx if cx is not None else _Ctx(device)
+        self.L, self.u, self.S, self.C = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(n_inputChannels)
+        self.stages = int(round(math.log(self.u, 2)))
+        self.bicubic = bool(addBicubicUpsample)
+        self.ps = ps = ParamSet(self.cx.device)
+        cx, k = self.cx, int(filterSize)
+        sc = "generator/"
+        self.c_dens = {1: _Conv8(cx, ps, sc + "g_cdensOut1", 1, self.C, 1, None, gain=1.0)}
+        self.blocks = {}
+        cin = self.C
+        for j in range(1, self.stages + 1):
+            fms = min(int(start_fms / (2 ** j)), max_fms)
+            up = 2 ** j
+            if up == 2:
+                plan = [(fms, fms, n) for n in ("first", "second", "third", "fourth", "fifth")]
+            elif up == 4:
+                plan = [(fms * 2, fms, "first"), (fms, fms, "second"), (fms, fms, "third")]
+            else:
+                plan = [(fms * 2, fms, "first"), (fms, fms, "second")]
+            rbs = []
+            for s1, s2, name in plan:
+                pre = sc + "genBlock%d/" % up
+                rbs.append((_Conv8(cx, ps, pre + "g_cA_" + name, k, cin, s1, "relu"),
+                            _Conv8(cx, ps, pre + "g_cB_" + name, k, s1, s2, None),
+                            _Conv8(cx, ps, pre + "g_s_" + name, 1, cin, s2, None)))
+                cin = s2
+            self.blocks[j] = rbs
+            self.c_dens[up] = _Conv8(cx, ps, sc + "genBlock%d/g_cdensOut%d" % (up, up), 1, cin, 1, None, gain=1.0)
+        vals = dict(values) if values else {}
+        for name, shape, _, _, _ in ps.specs:
+            if name not in vals:
+                vals[name] = W.init_variable(seed, name, shape, "normal" if name.endswith("/weight") else ("const", 0.1))
+        ps.finalize(vals)
+        self.bic_plans = {}
+
+    def refresh(self):
+        ps = self.ps
+        self.cx.call("mul", ps.w, ps.v, ps.scale, ps.total, self.cx.st)
+
+    def _up2(self, x, B, h, w, c):
+        y = self.cx.buf((B, 2 * h, 2 * w, c))
+        capi.pack_channels(self.cx.h, [(x, capi.F32, c, 0, c, 2, 2)], y, capi.F32, c, B, 2 * h, 2 * w, self.cx.st)
+        return y
+
+    def _up2_bwd(self, dy, B, h, w, c):
+        """backward of the nearest x2: sum over the 2x2 replicas."""
+        cx = self.cx
+        t = cx.buf((B, h, w, c))
+        cx.call("avgpool2_fwd", dy, t, B, 2 * h, 2 * w, c, cx.st)
+        cx.call("scale", t, t, 4.0, t.numel(), cx.st)
+        return t
+
+    def _pn(self, x):
+        y = self.cx.buf(x.shape)
+        self.cx.call("pixel_norm_fwd", x, y, x.numel() // x.shape[-1], x.shape[-1], self.cx.st)
+        return y
+
+    def forward(self, x_rows, percentage):
+        """x_rows [B, L*L*C] device fp32 -> (gen rows [B, S*S], saved)."""
+        cx, B, L, C = self.cx, x_rows.shape[0], self.L, self.C
+        x0 = x_rows.view(B, L, L, C)
+        sv = dict(B=B, lvl={}, pct=float(percentage))
+        old, sv["d1"] = self.c_dens[1].forward(x0, B, L, L)
+        cur, res, ch = x0, L, C
+        for j in range(1, self.stages + 1):
+            up = self._up2(cur, B, res, res, ch)
+            res *= 2
+            inp, rbs_sv = up, []
+            for a, b, s in self.blocks[j]:
+                ya, sa = a.forward(inp, B, res, res)
+                yap = self._pn(ya)
+                yb, sb = b.forward(yap, B, res, res)
+                ys, ss = s.forward(inp, B, res, res)
+                r = cx.buf(yb.shape)
+                cx.call("add_act_fwd", yb, ys, r, r.numel(), capi.ACT_RELU, cx.st)
+                rp = self._pn(r)
+                rbs_sv.append(dict(sa=sa, sb=sb, ss=ss, ya=ya, r=r))
+                inp = rp
+            cur, ch = inp, inp.shape[-1]
+            dens, sd = self.c_dens[2 ** j].forward(cur, B, res, res)
+            if self.bicubic:
+                key = (L, res)
+                if key not in self.bic_plans:
+                    self.bic_plans[key] = capi.BicubicPlan(cx.h, L, L, res, res)
+                out = cx.buf(dens.shape)
+                capi.dens_residual(cx.h, dens, x0, capi.F32, C, 0, 2, self.bic_plans[key], B, res, res, L, L, out, cx.st)
+                dens = out
+            oldu = self._up2(old, B, res // 2, res // 2, 1)
+            t = float(min(max(percentage - (j - 1), 0.0), 1.0))
+            blend = cx.buf(dens.shape)
+            cx.call("lerp", blend, oldu, dens, t, blend.numel(), cx.st)
+            sv["lvl"][j] = dict(rbs=rbs_sv, sd=sd, t=t, res=res)
+            old = blend
+        return old.view(B, self.S * self.S), sv
+
+    def backward(self, sv, dout):
+        """dout [B, S*S]: gradient w.r.t. the generated rows. Accumulates the parameter gradients into ps.gw."""
+        cx, B = self.cx, sv["B"]
+        d_old = dout.reshape(B, self.S, self.S, 1)
+        d_up_next = None  # gradient w.r.t. the (upsampled) input of the next finer stage
+        for j in range(self.stages, 0, -1):
+            lv = sv["lvl"][j]
+            res, t = lv["res"], lv["t"]
+            d_dens = cx.buf(d_old.shape)
+            cx.call("scale", d_dens, d_old, t, d_dens.numel(), cx.st)
+            d_oldu = cx.buf(d_old.shape)
+            cx.call("scale", d_oldu, d_old, 1.0 - t, d_oldu.numel(), cx.st)
+            ch = lv["sd"]["x"].shape[-1]
+            d_cur = cx.buf(lv["sd"]["x"].shape)
+            self.c_dens[2 ** j].backward(lv["sd"], d_dens, dx=d_cur)
+            if d_up_next is not None:
+                cx.call("axpy", d_cur, self._up2_bwd(d_up_next, B, res, res, ch), 1.0, d_cur.numel(), cx.st)
+            d = d_cur
+            rbs = self.blocks[j]
+            for i in range(len(rbs) - 1, -1, -1):
+                a, b, s = rbs[i]
+                q = lv["rbs"][i]
+                first_of_net = (j == 1 and i == 0)  # its input is the upsampled DATA: no input gradient needed
+                d_r = cx.buf(q["r"].shape)
+                cx.call("pixel_norm_bwd", q["r"], d, d_r, q["r"].numel() // q["r"].shape[-1], q["r"].shape[-1], cx.st)
+                d_sum = cx.buf(q["r"].shape)
+                cx.call("act_bwd", q["r"], d_r, d_sum, d_sum.numel(), capi.ACT_RELU, cx.st)
+                d_yap = cx.buf(q["ya"].shape)
+                b.backward(q["sb"], d_sum, dx=d_yap)
+                d_inp = None if first_of_net else cx.buf(q["sa"]["x"].shape)
+                s.backward(q["ss"], d_sum, dx=d_inp)
+                d_ya = cx.buf(q["ya"].shape)
+                cx.call("pixel_norm_bwd", q["ya"], d_yap, d_ya, q["ya"].numel() // q["ya"].shape[-1], q["ya"].shape[-1], cx.st)
+                a.backward(q["sa"], d_ya, dx=d_inp, accumulate=True)
+                d = d_inp
+            d_up_next = d
+            d_old = self._up2_bwd(d_oldu, B, res // 2, res // 2, 1)
+        self.c_dens[1].backward(sv["d1"], d_old)
+
+    def grads(self):
+        ps = self.ps
+        host = ps.g.cpu().numpy()
+        return {name: host[off:off + n].reshape(shape).copy() for name, shape, off, n, _ in ps.specs}
+
+
+class Trainer8x:
+    """Loop body of the 8x progressive-growing training (GAN/multipassGAN-8x.py:1898-2075, spatial part): one critic step
+    (WGAN-GP, :1111-1143) and one generator step (g_loss_d + lambda * l1, :1117,1145) with the optimizers of growing stage z
+    (:1304-1362) and the generator weight EMA. Temporal discriminator terms (lambda_t) and loss scaling are not built."""
+
+    def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
+                 learning_rate=1e-4, adam_beta1=0.0, adam_beta2=0.99, lambda_l1=1.0, values=None, seed=1, device=0):
+        self.cx = cx = _Ctx(device)
+        self.gen = GrowingGen(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, batch, True, values, seed, device, cx=cx)
+        self.disc = GrowingDisc(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, True, batch, values, seed, device,
+                                cx=cx)
+        n = self.gen.stages
+        self.opt_g = StagedAdam(cx, self.gen.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
+        self.opt_d = StagedAdam(cx, self.disc.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
+        self.ema = WeightEMA(self.gen.ps, 0.999)
+        self.k_l1 = float(lambda_l1)
+        self.losses = torch.zeros(4, dtype=torch.float64, device=cx.device)
+
+    def disc_step(self, x_rows, y_rows, percentage, z, lerp_factor):
+        cx = self.cx
+        cx.st = torch.cuda.current_stream(cx.device).cuda_stream
+        self.gen.refresh()
+        gen_y, _ = self.gen.forward(x_rows, percentage)
+        out = self.disc.critic_step(x_rows, y_rows, gen_y, percentage, lerp_factor)
+        self.opt_d.step(z)
+        return out
+
+    def gen_step(self, x_rows, y_rows, percentage, z):
+        cx, g, d = self.cx, self.gen, self.disc
+        cx.st = torch.cuda.current_stream(cx.device).cuda_stream
+        g.refresh()
+        d.refresh()
+        g.ps.gw.zero_()
+        self.losses.zero_()
+        gen_y, gsv = g.forward(x_rows, percentage)
+        logits, dsv = d.forward(x_rows, gen_y, percentage)
+        dl = cx.buf(logits.shape)
+        cx.call("mean_pow", logits, -1.0, 1, self.losses[0:1], dl, logits.numel(), 0, cx.st)      # g_loss_d = mean(-gen) :1117
+        dxin = d.backward(dsv, dl, need_input_grad=True, param_grads=False)
+        dgen = cx.buf(gen_y.shape)
+        cx.call("l1_mean", y_rows, gen_y, self.k_l1, self.losses[1:2], dgen, gen_y.numel(), 0, cx.st)  # lambda * mean|y - G| :1099,1145
+        cx.call("take_channel", dxin, dgen, gen_y.numel(), 2, 1, 1, cx.st)
+        g.backward(gsv, dgen)
+        cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
+        self.opt_g.step(z)
+        self.ema.update(self.opt_g.state[z]["mask"])
+        return self.losses

@@ -18,6 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import gan as og
+from . import networks as on
 from . import tf_ops
 
 
@@ -102,6 +103,30 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
         gan.flatten()
         gan.fully_connected_layer(1, None, name="d_l61", gain=1)                        # :862
         return gan.y(), feats
+
+
+def growing_gen_train(x_rows, percentage, ctx, cfg, pixel_norm=True, addBicubicUpsample=True):
+    """growing_gen with output=False (GAN/multipassGAN-8x.py:700-750), firstNNArch / upsampling_mode 2: every stage emits a
+    density (1x1 conv, gain 1) [+ the bicubic upsample of the input density], blended with the nearest-upsampled density of
+    the previous stage by lerp(old, new, percentage - (j-1)).  Returns the flat rows [B, S*S]."""
+    ocfg = on.make_cfg_out(cfg.tileSizeLow, cfg.upRes, cfg.n_inputChannels, pixel_norm=pixel_norm,
+                           addBicubicUpsample=addBicubicUpsample, upsampleMode=cfg.upsampleMode)
+    L, C = cfg.tileSizeLow, cfg.n_inputChannels
+    with ctx.variable_scope("generator"):
+        _in = x_rows.reshape(-1, L, L, C)
+        gan = og.GAN(_in, ctx)
+        x_g = _in                                                                       # first_nn_arch :712-713
+        old, _ = og.GAN(x_g, ctx).convolutional_layer(1, [1, 1], None, stride=[1], name="g_cdensOut1", in_layer=x_g, gain=1)
+        for j in range(1, cfg.stages + 1):
+            num_fms = min(int(cfg.start_fms / (2 ** j)), cfg.max_fms)
+            x_g, dens = on._grow_block_gen(gan, ctx, ocfg, x_g, int(2 ** j), num_fms, False, False, False, True,
+                                           cfg.filterSize, True, True)
+            if addBicubicUpsample:                                                      # :735-737
+                dens = dens + og.GAN(_in[..., 0:1], ctx).avg_depool(mode=2, scale=[int(2 ** j)])
+            with ctx.variable_scope("growingPart%i" % j):
+                old = og.GAN(old, ctx).avg_depool(mode=1)                               # :744
+                old = lerp(old, dens, percentage - (j - 1))                             # :748
+        return old.reshape(-1, cfg.tileSizeHigh * cfg.tileSizeHigh)
 
 
 def wgan_gp_losses(disc, gen, d_out_fn, y_in, gen_y, lerp_factor, wgan_lambda=10.0, wgan_target=1.0, wgan_epsilon=0.001,

@@ -357,6 +357,33 @@ def make_growdisc_fixtures():
                                                  first_nn_arch=first_nn_arch, percentages=list(percentages),
                                                  filterSize=filterSize))
 
+    gen_code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["lerp", "resBlock", "growBlockGen", "growing_gen"])
+
+    def run_gen(tag, seed, L, u, C, start_fms, max_fms, percentages):
+        """growing_gen in TRAINING mode (output=False: per-stage density outputs blended with lerp, :700-750)."""
+        S = L * u
+        store, getv = _provide(seed)
+        tfs.reset({})
+        tfs.get_variable = getv
+        ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, tileSizeLow=L, tileSizeHigh=S, upRes=u,
+                  n_inputChannels=C, n_output=S * S, upsampling_mode=2, upsampleMode=1, start_fms=start_fms, max_fms=max_fms,
+                  filterSize=3, first_nn_arch=True, use_res_net=True, pixel_norm=True, usePixelShuffle=False,
+                  addBicubicUpsample=True, dataDimension=2, bn_decay=0.999, train=False, rbId=0, print=lambda *a, **k: None)
+        exec(gen_code, ns)
+        x_rows = rng.random((2, L * L * C), dtype=np.float32)
+        fixtures[tag + "_x"] = x_rows
+        for k, pct in enumerate(percentages):
+            tfs.STATE.requested = {}
+            res = ns["growing_gen"](tfs.T(x_rows), tfs.T(np.float32(pct)), reuse=tfs.AUTO_REUSE, use_batch_norm=False, train=False,
+                                    currentUpres=int(round(math.log(u, 2))), output=False)
+            fixtures["%s_p%d_out" % (tag, k)] = res.a
+            print(tag, pct, res.a.shape, float(np.abs(res.a).max()))
+        fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
+        fixtures[tag + "_wsum"] = _wsum(store)
+        fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, C=C, start_fms=start_fms, max_fms=max_fms,
+                                                 percentages=list(percentages)))
+
+    run_gen("gg_first", 83, 4, 8, 6, 32, 32, (0.4, 1.3, 2.75, 3.0))
     run("gd_first", 81, 4, 8, 6, 32, 32, True, (0.4, 1.3, 2.75, 3.0))
     run("gd_plain", 82, 4, 4, 4, 32, 16, False, (0.5, 1.6, 2.0))
     np.savez_compressed(os.path.join(HERE, "growdisc.npz"), **fixtures)

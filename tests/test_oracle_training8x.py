@@ -84,3 +84,17 @@ def test_wgan_gp_gradient_penalty_is_differentiable_wrt_the_critic():
     k = "spatial-disc/d_cfromDensity1/weight"
     assert k not in got or float(got[k].abs().max()) == 0.0
     assert L["grad_norms"].shape == (2,) and float(L["grad_penalty"]) > 0
+
+
+def test_growing_gen_training_graph_reproduces_the_reference_code():
+    """growing_gen with output=False (per-stage density outputs blended with lerp, GAN/multipassGAN-8x.py:700-750)."""
+    c = json.loads(str(GOLD["gg_first_cfg"]))
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+    store = og.VarStore(seed=c["seed"])
+    x = torch.from_numpy(GOLD["gg_first_x"]).double()
+    for k, pct in enumerate(c["percentages"]):
+        out = o8.growing_gen_train(x, pct, og.Context(store, torch.float64), cfg)
+        ref = GOLD["gg_first_p%d_out" % k]
+        assert out.shape == ref.shape and np.abs(out.numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), pct
+    want = {k: tuple(v) for k, v in json.loads(str(GOLD["gg_first_vars"]))}
+    assert {k: tuple(v.shape) for k, v in store.values.items()} == want

@@ -136,3 +136,124 @@ def test_staged_adam_and_weight_ema():
         assert np.abs(got_ema[n] - shadow[n]).max() < 1e-5, n
     # stage 0 / 1 never touched the first blocks: those variables are still at their initial values after the z<2 steps
     # (checked implicitly above: the oracle only updated `sel`)
+
+
+def _gen_setup():
+    c = json.loads(str(GOLD["gg_first_cfg"]))
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+    store = og.VarStore(seed=c["seed"])
+    x = torch.from_numpy(GOLD["gg_first_x"]).double()
+    o8.growing_gen_train(x, 1.0, og.Context(store, torch.float64), cfg)
+    g = t8.GrowingGen(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, batch=2, values=store.values)
+    assert {n for n, *_ in g.ps.specs} == set(store.values)
+    return c, cfg, store, x, g
+
+
+def test_growing_gen_training_forward_matches_the_reference_vectors():
+    c, cfg, store, x, g = _gen_setup()
+    dev = g.cx.device
+    g.cx.st = torch.cuda.current_stream(dev).cuda_stream
+    g.refresh()
+    for k, pct in enumerate(c["percentages"]):
+        out, _ = g.forward(x.float().to(dev), pct)
+        ref = GOLD["gg_first_p%d_out" % k]
+        assert np.abs(out.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), pct
+
+
+def _gen_autograd(store, x, pct, cfg, dtype):
+    ctx = ot.TrainContext(store, dtype)
+    out = o8.growing_gen_train(x.to(dtype), pct, ctx, cfg)
+    wgt = torch.cos(torch.arange(out.numel(), dtype=torch.float64) * 0.37).view_as(out)
+    names = [n for n, t in ctx.leaves.items() if t.requires_grad]
+    grads = torch.autograd.grad((out * wgt.to(dtype)).sum(), [ctx.leaves[n] for n in names], allow_unused=True)
+    return names, wgt, {n: (gr.double().numpy() if gr is not None else np.zeros(tuple(ctx.leaves[n].shape)))
+                        for n, gr in zip(names, grads)}
+
+
+@pytest.mark.parametrize("pct", [0.6, 1.7, 2.5])
+def test_growing_gen_backward_matches_autograd(pct):
+    """Parameter gradients of the training-mode generator (30 convs, 20 pixel norms, ReLU kinks) against fp64 autograd. The
+    earliest layers see the rounding of everything above them (a ReLU input near zero may change sign between fp32 and fp64),
+    so each variable is held to 3e-3 or to 4x the distance of torch's OWN fp32 autograd from the fp64 result."""
+    c, cfg, store, x, g = _gen_setup()
+    dev = g.cx.device
+    names, wgt, want = _gen_autograd(store, x, pct, cfg, torch.float64)
+    _, _, want32 = _gen_autograd(store, x, pct, cfg, torch.float32)
+    g.cx.st = torch.cuda.current_stream(dev).cuda_stream
+    g.refresh()
+    g.ps.gw.zero_()
+    gen, sv = g.forward(x.float().to(dev), pct)
+    g.backward(sv, wgt.float().to(dev).contiguous())
+    g.cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, g.cx.st)
+    got = g.grads()
+    tight = easy = live = 0
+    for n in names:
+        if np.abs(want[n]).max() < 1e-12:  # stages that are not blended in yet receive no gradient
+            assert np.abs(got[n]).max() < 1e-5, n
+            continue
+        live += 1
+        r32 = _rel(want32[n], want[n])
+        tol = max(3e-3, 4.0 * r32)
+        assert _rel(got[n], want[n]) < tol, (n, _rel(got[n], want[n]), tol)
+        easy += r32 < 7.5e-4             # variables torch's fp32 autograd itself resolves well ...
+        tight += r32 < 7.5e-4 and _rel(got[n], want[n]) < 3e-3   # ... must be within 3e-3 here
+    assert live > 0 and tight == easy, (tight, easy, live)
+
+
+def test_trainer8x_critic_and_generator_steps_track_the_oracle():
+    """Two loop bodies (critic step then generator step, GAN/multipassGAN-8x.py:1898-2075 without the temporal terms) at two
+    growing stages: losses and every updated variable against the fp64 oracle with the same staged Adam."""
+    c = json.loads(str(GOLD["gg_first_cfg"]))
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(GOLD["gg_first_x"]).double()
+    y = torch.from_numpy(rng.random((2, cfg.tileSizeHigh ** 2))).double()
+    store = og.VarStore(seed=7)
+    o8.growing_gen_train(x, 1.0, og.Context(store, torch.float64), cfg)
+    o8.growing_disc(y, x, 1.0, og.Context(store, torch.float64), cfg)
+    tr = t8.Trainer8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, batch=2, learning_rate=1e-3, values=store.values)
+    dev = tr.cx.device
+    ref_vals = {k: np.array(v, np.float64) for k, v in store.values.items()}
+    g_names = sorted(k for k in ref_vals if k.startswith("generator/"))
+    d_names = sorted(k for k in ref_vals if k.startswith("spatial-disc/"))
+    og_opt = [ot.Adam(1e-3, 0.0, 0.99) for _ in range(3)]
+    od_opt = [ot.Adam(1e-3, 0.0, 0.99) for _ in range(3)]
+    lf = torch.tensor([[0.35], [0.6]], dtype=torch.float64)
+    xf, yf = x.float().to(dev), y.float().to(dev)
+
+    def oracle_ctx():
+        st = og.VarStore(seed=7)
+        st.values = {k: v.astype(np.float32) for k, v in ref_vals.items()}
+        return ot.TrainContext(st, torch.float64)
+
+    def apply(opt, sel, loss, ctx):
+        grads = torch.autograd.grad(loss, [ctx.leaves[n] for n in sel], allow_unused=True)
+        gd = {n: (gr.numpy() if gr is not None else np.zeros(tuple(ctx.leaves[n].shape))) for n, gr in zip(sel, grads)}
+        v32 = {n: ref_vals[n].astype(np.float32) for n in sel}
+        opt.step(v32, gd)
+        for n in sel:
+            ref_vals[n] = v32[n].astype(np.float64)
+
+    for z, pct in ((0, 0.7), (1, 1.4)):
+        # critic step
+        ctx = oracle_ctx()
+        gen_y = o8.growing_gen_train(x, pct, ctx, cfg).detach()
+        disc, _ = o8.growing_disc(y, x, pct, ctx, cfg)
+        gen, _ = o8.growing_disc(gen_y, x, pct, ctx, cfg)
+        L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, pct, ctx, cfg)[0], y, gen_y, lf)
+        got = tr.disc_step(xf, yf, pct, z, lf).cpu().numpy()
+        assert abs(got[0] - float(L["disc_loss"].detach())) < 5e-4 * max(1.0, abs(float(L["disc_loss"].detach())))
+        apply(od_opt[z], o8.stage_variables(d_names, z), L["disc_loss"], ctx)
+        # generator step
+        ctx = oracle_ctx()
+        gen_y = o8.growing_gen_train(x, pct, ctx, cfg)
+        gen, _ = o8.growing_disc(gen_y, x, pct, ctx, cfg)
+        g_loss = (-gen).mean() + 1.0 * (y - gen_y).abs().mean()
+        gl = tr.gen_step(xf, yf, pct, z).cpu().numpy()
+        assert abs(gl[0] + gl[1] - float(g_loss.detach())) < 5e-4 * max(1.0, abs(float(g_loss.detach())))
+        apply(og_opt[z], o8.stage_variables(g_names, z), g_loss, ctx)
+    got_g, got_d = tr.gen.ps.export(), tr.disc.ps.export()
+    for n in g_names:
+        assert np.abs(got_g[n] - ref_vals[n]).max() < 5e-4, (n, float(np.abs(got_g[n] - ref_vals[n]).max()))
+    for n in d_names:
+        assert np.abs(got_d[n] - ref_vals[n]).max() < 5e-4, (n, float(np.abs(got_d[n] - ref_vals[n]).max()))
