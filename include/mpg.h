@@ -108,6 +108,12 @@ int mpg_conv_plan_destroy(mpg_conv_plan p);
  * input gradient this plan computes (taps flipped, channels swapped = Conv2DBackpropInput). */
 int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
                          const float* shift_dev, void* stream);
+/* ... with segment 0 read from a smaller and / or wider source tensor: src_k x src_k taps embedded in the plan's k x k kernel at
+ * offset k - src_k (TF's SAME window of a 4x4 conv = taps -1..+2 of a 5x5 one: the k = 4 convs of disc_binclass,
+ * GAN/multipassGAN-4x.py:593-614, on the tensor cores) and, in mode 0, output channels [cout_off, cout_off + cout) of a source
+ * with src_cout channels (cout > 128 split over several plans). 0 = same as the plan. */
+int mpg_conv_plan_update_ex(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
+                            const float* shift_dev, int src_k, int src_cout, int cout_off, void* stream);
 /* which kernel the plan dispatches to: 1 = tcgen05 implicit GEMM, 2 = CUDA-core direct, 3 = tcgen05 with the
  * horizontal taps folded into N (narrow Cout), 4 = CUDA-core kernel for cout <= 2 from <= 8 channels,
  * 5 = row-streaming tcgen05 kernel with the vertical taps folded into N (k * round_up(cout, 8) <= 256, wide images),
@@ -370,6 +376,13 @@ int mpg_train_gp_penalty(mpg_handle h, const float* g, float* v, double* loss, f
                          float lambda, float target, void* stream);
 int mpg_train_mean_pow(mpg_handle h, const float* x, float scale, int power, double* loss, float* dx, long long count,
                        int accumulate, void* stream);
+/* Strided convs through a stride-1 tensor-core plan: out[n,oy,ox,out_c0 + c] = in[n, oy*stride, ox*stride, c] (pick), and its
+ * adjoint for the input gradient: a 16-bit full-resolution tensor that holds dy at the sampled positions and zeros elsewhere
+ * (channels >= c of the cstride are zero too) */
+int mpg_train_pick(mpg_handle h, const float* in, float* out, int n, int oh, int ow, int c, int stride, int in_cstride,
+                   int out_cstride, int out_c0, void* stream);
+int mpg_train_stuff16(mpg_handle h, const float* dy, void* out16, int out_dtype, int n, int oh, int ow, int c, int stride,
+                      int out_cstride, void* stream);
 /* pixel_norm (tools_wscale/GAN.py:472-474) of the growing generator in training mode, x [rows, c], and its backward */
 int mpg_train_pixel_norm_fwd(mpg_handle h, const float* x, float* y, long long rows, int c, void* stream);
 int mpg_train_pixel_norm_bwd(mpg_handle h, const float* x, const float* dy, float* dx, long long rows, int c, void* stream);

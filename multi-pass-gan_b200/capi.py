@@ -102,6 +102,7 @@ def lib():
     L.mpg_conv_plan_run_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.mpg_conv_plan_destroy.argtypes = [vp]
     L.mpg_conv_plan_update.argtypes = [vp, vp, vp, ip, ip, vp, vp]
+    L.mpg_conv_plan_update_ex.argtypes = [vp, vp, vp, ip, ip, vp, ip, ip, ip, vp]
     L.mpg_conv_plan_kind.argtypes = [vp]
     L.mpg_conv_plan_flops.argtypes = [vp]
     L.mpg_conv_plan_flops.restype = dp
@@ -155,6 +156,8 @@ def lib():
     L.mpg_train_gp_penalty.argtypes = [vp, vp, vp, vp, vp, ip, ll, fl, fl, vp]
     L.mpg_train_mean_pow.argtypes = [vp, vp, fl, ip, vp, vp, ll, ip, vp]
     L.mpg_train_pixel_norm_fwd.argtypes = [vp, vp, vp, ll, ip, vp]
+    L.mpg_train_pick.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, ip, vp]
+    L.mpg_train_stuff16.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, ip, ip, vp]
     L.mpg_train_pixel_norm_bwd.argtypes = [vp, vp, vp, vp, ll, ip, vp]
     _lib = L
     return L
@@ -270,10 +273,11 @@ class ConvPlan:
         check(lib().mpg_conv_plan_run_ex(self._p, _ptr(x0), _ptr(x1), _ptr(y), _ptr(y_side), _ptr(residual), stream),
               "mpg_conv_plan_run_ex")
 
-    def update(self, w0, w1=None, mode0=0, mode1=0, shift=None, stream=0):
-        """Refresh the packed weights from device fp32 HWIO tensors (training; tcgen05 plans only)."""
-        check(lib().mpg_conv_plan_update(self._p, _ptr(w0), _ptr(w1), int(mode0), int(mode1), _ptr(shift), stream),
-              "mpg_conv_plan_update")
+    def update(self, w0, w1=None, mode0=0, mode1=0, shift=None, stream=0, src_k=0, src_cout=0, cout_off=0):
+        """Refresh the packed weights from device fp32 HWIO tensors (training; tcgen05 plans only). src_k / src_cout /
+        cout_off: segment 0 comes from a smaller (embedded) and / or wider source tensor (mpg_conv_plan_update_ex)."""
+        check(lib().mpg_conv_plan_update_ex(self._p, _ptr(w0), _ptr(w1), int(mode0), int(mode1), _ptr(shift), int(src_k),
+                                            int(src_cout), int(cout_off), stream), "mpg_conv_plan_update_ex")
 
     def close(self):
         if self._p:

@@ -88,6 +88,9 @@ struct RepackArgs {
   const float* w[2];
   int mode[2];
   int ks[2], cin[2], nchunk[2], kt0[2];
+  int src_k;     // segment 0: kernel size of the SOURCE tensor (== ks[0], or smaller: embedded at offset ks[0] - src_k, zero taps before)
+  int src_cout;  // segment 0, mode 0: cout of the source tensor (this plan covers its channels [cout_off, cout_off + cout))
+  int cout_off;
   int nseg, ck, npad, cout, f16;
   uint16_t* out;
   long long total;
@@ -108,10 +111,16 @@ __global__ void __launch_bounds__(256) repack_igemm_kernel(const RepackArgs a) {
     const int ci = ch * a.ck + c;
     float v = 0.0f;
     if (ci < a.cin[s] && n < a.cout) {
-      if (a.mode[s] == 0)
-        v = a.w[s][((static_cast<size_t>(dy) * ks + dx) * a.cin[s] + ci) * a.cout + n];
-      else
-        v = a.w[s][((static_cast<size_t>(ks - 1 - dy) * ks + (ks - 1 - dx)) * a.cout + n) * a.cin[s] + ci];
+      // source taps: a k' x k' tensor embedded in the k x k kernel at offset o = k - k' (the TF SAME window of an even kernel,
+      // e.g. 4x4 -> taps -1..+2 of a 5x5); segment 1 is never embedded
+      const int kf = s == 0 ? a.src_k : ks, o = ks - kf;
+      const int sc = (s == 0 && a.mode[s] == 0) ? a.src_cout : a.cout, co = (s == 0 && a.mode[s] == 0) ? a.cout_off : 0;
+      if (a.mode[s] == 0) {
+        if (dy >= o && dx >= o) v = a.w[s][((static_cast<size_t>(dy - o) * kf + (dx - o)) * a.cin[s] + ci) * sc + co + n];
+      } else {
+        const int fy = ks - 1 - dy - o, fx = ks - 1 - dx - o;
+        if (fy >= 0 && fx >= 0) v = a.w[s][((static_cast<size_t>(fy) * kf + fx) * a.cout + n) * a.cin[s] + ci];
+      }
     }
     a.out[e] = a.f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
@@ -1354,7 +1363,18 @@ int mpg_conv_plan_run_ex(mpg_conv_plan p, const void* x0, const void* x1, void* 
  * gradient this plan computes (flipped taps, swapped channels). shift_dev may be NULL (= keep). */
 int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
                          const float* shift_dev, void* stream) {
+  return mpg_conv_plan_update_ex(p, w_seg0_dev, w_seg1_dev, mode0, mode1, shift_dev, 0, 0, 0, stream);
+}
+
+/* ... with segment 0 read from a SMALLER and / or WIDER source tensor: src_k x src_k taps embedded in the plan's k x k kernel
+ * at offset k - src_k (a 4x4 TF-SAME conv is taps -1..+2 of a 5x5 one: the discriminator's k = 4 convs on the tensor cores),
+ * and, in mode 0, a plan that covers output channels [cout_off, cout_off + cout) of a source with src_cout channels (cout >
+ * 128 split over several plans). 0 = same as the plan. */
+int mpg_conv_plan_update_ex(mpg_conv_plan p, const float* w_seg0_dev, const float* w_seg1_dev, int mode0, int mode1,
+                            const float* shift_dev, int src_k, int src_cout, int cout_off, void* stream) {
   MPG_CHECK_ARG(p && w_seg0_dev, "mpg_conv_plan_update: null argument");
+  MPG_CHECK_ARG(src_k >= 0 && src_k <= p->d.seg_ksize[0] && cout_off >= 0 && (src_cout == 0 || src_cout >= cout_off + p->d.cout),
+                "mpg_conv_plan_update_ex: src_k=%d src_cout=%d cout_off=%d do not fit the plan", src_k, src_cout, cout_off);
   MPG_CHECK_ARG(p->kind == 1, "mpg_conv_plan_update: only tcgen05 igemm plans (force_kind 1) can be refreshed on the device");
   MPG_CHECK_ARG(p->d.nseg == 1 || w_seg1_dev, "mpg_conv_plan_update: segment 1 weights missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1372,6 +1392,9 @@ int mpg_conv_plan_update(mpg_conv_plan p, const float* w_seg0_dev, const float* 
     a.kt0[s] = kt;
     kt += p->seg_nchunk[s] * a.ks[s] * a.ks[s];
   }
+  a.src_k = src_k > 0 ? src_k : p->d.seg_ksize[0];
+  a.src_cout = src_cout > 0 ? src_cout : p->d.cout;
+  a.cout_off = cout_off;
   a.nseg = p->d.nseg;
   a.ck = p->ck;
   a.npad = p->npad;

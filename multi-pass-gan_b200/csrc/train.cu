@@ -529,6 +529,38 @@ __global__ void __launch_bounds__(256) scale_kernel(float* y, const float* x, fl
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     y[e] = alpha * x[e];
 }
+// strided pick / zero-stuffed 16-bit scatter: a stride-2 conv = the stride-1 conv sampled at even positions, its input gradient
+// = the stride-1 dgrad of dy scattered onto those positions (mpg_conv_plan_update_ex)
+__global__ void __launch_bounds__(256) pick_kernel(const float* in, float* out, int n, int oh, int ow, int c, int stride,
+                                                    int in_cstride, int out_cstride, int out_c0) {
+  const long long total = static_cast<long long>(n) * oh * ow * c;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % c);
+    long long r = e / c;
+    const int ox = static_cast<int>(r % ow);
+    r /= ow;
+    const int oy = static_cast<int>(r % oh);
+    const long long img = r / oh;
+    const long long src = ((img * (oh * stride) + static_cast<long long>(oy) * stride) * (ow * stride) + static_cast<long long>(ox) * stride) * in_cstride + ch;
+    out[((img * oh + oy) * ow + ox) * out_cstride + out_c0 + ch] = in[src];
+  }
+}
+__global__ void __launch_bounds__(256) stuff16_kernel(const float* dy, uint16_t* out, int dtype, int n, int oh, int ow, int c,
+                                                       int stride, int cs) {
+  const int h = oh * stride, w = ow * stride;
+  const long long total = static_cast<long long>(n) * h * w * cs;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(e % cs);
+    long long r = e / cs;
+    const int x = static_cast<int>(r % w);
+    r /= w;
+    const int y = static_cast<int>(r % h);
+    const long long img = r / h;
+    float v = 0.0f;
+    if (ch < c && y % stride == 0 && x % stride == 0) v = dy[((img * oh + y / stride) * ow + x / stride) * c + ch];
+    out[e] = float_to_h16(v, dtype);
+  }
+}
 // pixel_norm (tools_wscale/GAN.py:472-474): y = x * rsqrt(mean_c x^2 + 1e-8), one thread per pixel; backward:
 // dx = r dy - x r^3 mean_c(dy x)
 __global__ void __launch_bounds__(256) pixel_norm_fwd_kernel(const float* x, float* y, long long rows, int c) {
@@ -982,6 +1014,24 @@ int mpg_train_lerp(mpg_handle h, float* out, const float* a, const float* b, flo
 int mpg_train_scale(mpg_handle h, float* y, const float* x, float alpha, long long count, void* stream) {
   MPG_CHECK_ARG(h && x && y, "mpg_train_scale: bad argument");
   scale_kernel<<<grid_for(count, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, alpha, count);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_pick(mpg_handle h, const float* in, float* out, int n, int oh, int ow, int c, int stride, int in_cstride,
+                   int out_cstride, int out_c0, void* stream) {
+  MPG_CHECK_ARG(h && in && out && stride >= 1 && c <= in_cstride && out_c0 + c <= out_cstride, "mpg_train_pick: bad argument");
+  const long long total = static_cast<long long>(n) * oh * ow * c;
+  pick_kernel<<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, oh, ow, c, stride, in_cstride,
+                                                                                          out_cstride, out_c0);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+int mpg_train_stuff16(mpg_handle h, const float* dy, void* out16, int out_dtype, int n, int oh, int ow, int c, int stride,
+                      int out_cstride, void* stream) {
+  MPG_CHECK_ARG(h && dy && out16 && stride >= 1 && c <= out_cstride && mpg::is_h16(out_dtype), "mpg_train_stuff16: bad argument");
+  const long long total = static_cast<long long>(n) * oh * stride * ow * stride * out_cstride;
+  stuff16_kernel<<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, static_cast<uint16_t*>(out16),
+                                                                                             out_dtype, n, oh, ow, c, stride, out_cstride);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

@@ -86,8 +86,26 @@ class _Conv:
         self.fast_w = (tr.precision == "fp16" and k in (1, 3, 5) and stride == 1 and in_up == 1
                        and ((cin == 128 and cout in (32, 64, 128)) or (cout == 128 and cin in (32, 64))))
         self.plan_f = self.plan_d = None
+        # discriminator convs (k = 4, stride 2 / 1; GAN/multipassGAN-4x.py:593-614) on the tensor cores too: TF's SAME window
+        # of a 4x4 kernel is taps -1..+2 of a 5x5 one, so the conv runs as a stride-1 5x5 plan at the INPUT resolution with the
+        # weights embedded (mpg_conv_plan_update_ex) and a stride-2 layer keeps every other output pixel (4x the MACs, on a
+        # pipe that is ~50x faster than the fp32 CUDA-core kernel these layers used: 42 % of the serialized loop body);
+        # the input gradient is the same plan's dgrad of dy scattered onto the sampled positions. cout > 128 = several plans.
+        self.emb = tr.precision == "fp16" and k == 4 and in_up == 1 and stride in (1, 2)
+        self.plans_f = []
 
     def build_plans(self, n, h, w):
+        if self.emb and not self.plans_f:
+            tr = self.tr
+            for c0 in range(0, self.cout, 128):
+                cc = min(128, self.cout - c0)
+                self.plans_f.append((c0, cc, capi.ConvPlan(tr.h, n, h, w, [np.zeros((5, 5, self.cin, cc), np.float32)], [self.cpi], cc, cc,
+                                                           act=None, shift=np.zeros(cc, np.float32), in_dtype=capi.F16,
+                                                           out_dtype=capi.F32, force_kind=1)))
+            self.plan_d = capi.ConvPlan(tr.h, n, h, w, [np.zeros((5, 5, self.cout, self.cin), np.float32)], [self.cpo], self.cin,
+                                        self.cin, act=None, shift=np.zeros(self.cin, np.float32), in_dtype=capi.BF16,
+                                        out_dtype=capi.F32, force_kind=1)
+            return
         if not self.fast or self.plan_f is not None:
             return
         tr = self.tr
@@ -100,6 +118,15 @@ class _Conv:
                                         shift=np.zeros(self.cin, np.float32), in_dtype=capi.BF16, out_dtype=capi.F32, force_kind=1)
 
     def refresh(self):
+        if self.emb and self.plans_f:
+            ps, tr = self.ps, self.tr
+            bias = ps.view(ps.w, self.bn_)
+            for c0, cc, pl in self.plans_f:
+                pl.update(ps.view(ps.w, self.wn), mode0=0, shift=bias[c0:c0 + cc], stream=tr.st, src_k=4, src_cout=self.cout,
+                          cout_off=c0)
+            self.plan_d.update(ps.view(ps.w, self.wn), mode0=1, stream=tr.st, src_k=4)
+            tr.launches += len(self.plans_f) + 1
+            return
         if self.plan_f is None:
             return
         ps, tr = self.ps, self.tr
@@ -114,7 +141,16 @@ class _Conv:
         tr, ps = self.tr, self.ps
         oh, ow = -(-h // self.stride), -(-w // self.stride)
         lin = tr.buf((n, oh, ow, self.cout))
-        if self.fast:
+        if self.emb and self.plans_f:
+            x16 = tr.buf16((n, h, w, self.cpi), torch.float16)
+            capi.pack_channels(tr.h, [(x, capi.F32, self.cin, 0, self.cin, 1, 1)], x16, capi.F16, self.cpi, n, h, w, tr.st)
+            tr.launches += 1
+            for c0, cc, pl in self.plans_f:
+                full = tr.buf((n, h, w, cc))
+                pl.run(x16, None, full, tr.st)
+                tr.call("pick", full, lin, n, oh, ow, cc, self.stride, cc, self.cout, c0, tr.st)
+                tr.launches += 1
+        elif self.fast:
             x16 = tr.buf16((n, h, w, self.cpi), torch.float16)
             capi.pack_channels(tr.h, [(x, capi.F32, self.cin, 0, self.cin, self.in_up, self.in_up)], x16, capi.F16, self.cpi, n, h,
                                w, tr.st)
@@ -153,6 +189,20 @@ class _Conv:
             tr.call("act_bwd", sv["y"], dy, dlin, rows * self.cout, self.act, tr.st)
         else:
             dlin = dy
+        if self.emb and self.plans_f:
+            if param_grads:
+                tr.call("conv_wgrad", sv["x"], dlin, ps.view(ps.gw, self.wn), ps.view(ps.gw, self.bn_), tr.scratch, sv["n"],
+                        sv["h"], sv["w"], self.cin, self.cout, self.k, self.stride, self.in_up, tr.st)
+            if dx is not None:
+                oh, ow = dlin.shape[1], dlin.shape[2]
+                g16 = tr.buf16((sv["n"], sv["h"], sv["w"], self.cpo), torch.bfloat16)
+                tr.call("stuff16", dlin, g16, capi.BF16, sv["n"], oh, ow, self.cout, self.stride, self.cpo, tr.st)
+                tgt = tr.buf(tuple(dx.shape)) if accumulate else dx
+                self.plan_d.run(g16, None, tgt, tr.st)
+                tr.launches += 1
+                if accumulate:
+                    tr.call("axpy", dx, tgt, 1.0, dx.numel(), tr.st)
+            return
         g16 = None
         use_wtc = param_grads and self.fast_w and sv["w"] % 16 == 0
         if use_wtc or (dx is not None and self.fast):
@@ -250,6 +300,10 @@ class Trainer4x:
         for a, b, sc in self.rbs:
             for c in (a, b, sc):
                 c.build_plans(self.B, self.S, self.S)
+        hh = self.S
+        for c in self.dcs:
+            c.build_plans(self.B, hh, hh)
+            hh = -(-hh // c.stride)
         self.scratch = torch.zeros(4096, dtype=torch.float64, device=self.device)
         self.losses = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.st = 0
@@ -287,6 +341,8 @@ class Trainer4x:
         for a, b, sc in self.rbs:
             for c in (a, b, sc):
                 c.refresh()
+        for c in self.dcs:
+            c.refresh()
 
     # ------------------------------------------------------------------ networks
     def gen_forward(self, x):

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_training8x_gpu.py -x -q 2>&1 | grep -E "Error|assert |passed|failed" | head -12
+timeout 900 python -m pytest tests/test_training_gpu.py -x -q 2>&1 | tail -15
+python tools/bench_train.py 2>&1 | tail -3
