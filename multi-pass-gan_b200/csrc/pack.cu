@@ -111,6 +111,35 @@ __global__ void __launch_bounds__(256) pack_channels_kernel(const PackParams p) 
   }
 }
 
+// Dense fp32 -> 16-bit cast with channel padding (one source, no resize, all of its channels): the common case of the training
+// step (every tensor-core conv gets a 16-bit copy of its fp32 input / output gradient). One thread per 8-channel chunk of the
+// OUTPUT (one 16-byte store; consecutive threads = consecutive chunks = coalesced on both sides). The generic kernel below
+// gives a thread a whole pixel: with 128 channels that is 512 contiguous bytes per lane, 512 bytes apart -- measured 83 us
+// per call on [16,64,64,128] (36 % of the training loop body) against ~8 us for the bytes moved.
+__global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ in, uint4* __restrict__ out, long long npix,
+                                                        int cin, int cs8, int dtype) {
+  const long long total = npix * cs8;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const long long pix = e / cs8;
+    const int c0 = static_cast<int>(e - pix * cs8) * 8;
+    const float* p = in + pix * cin + c0;
+    float v[8];
+    if (c0 + 8 <= cin && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cin) ? __ldg(p + j) : 0.0f;
+    }
+    uint4 q;
+    q.x = pack_h16x2(v[0], v[1], dtype);
+    q.y = pack_h16x2(v[2], v[3], dtype);
+    q.z = pack_h16x2(v[4], v[5], dtype);
+    q.w = pack_h16x2(v[6], v[7], dtype);
+    out[e] = q;
+  }
+}
+
 struct DensParams {
   const float* dens;  // [n, oh, ow]
   const void* src;    // [n, sh, sw, cstride]
@@ -370,6 +399,18 @@ int mpg_pack_channels(mpg_handle h, const mpg_chan_src* srcs, int nsrc, void* ou
   p.out_dtype = out_dtype;
   p.out_cstride = out_cstride;
   p.out = out;
+  if (nsrc == 1 && srcs[0].factor_h == 1 && srcs[0].factor_w == 1 && srcs[0].dtype == MPG_F32 && is_h16(out_dtype) &&
+      srcs[0].c0 == 0 && srcs[0].nch == srcs[0].cstride && out_cstride % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(srcs[0].ptr) & 3) == 0) {
+    const long long npix = static_cast<long long>(n) * oh * ow;
+    const long long total = npix * (out_cstride / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > h->sm_count * 16LL) blocks = h->sm_count * 16LL;
+    cast_pad_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(srcs[0].ptr), static_cast<uint4*>(out), npix, srcs[0].nch, out_cstride / 8, out_dtype);
+    MPG_CUDA(cudaGetLastError());
+    return MPG_OK;
+  }
   MPG_CHECK_ARG((static_cast<long long>(n) * oh + kPackRows - 1) / kPackRows <= 65535, "pack: n*oh = %lld rows exceed the grid limit", static_cast<long long>(n) * oh);
   pack_channels_kernel<<<dim3(static_cast<unsigned>((ow + 255) / 256), static_cast<unsigned>((n * oh + kPackRows - 1) / kPackRows)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   MPG_CUDA(cudaGetLastError());
