@@ -304,6 +304,7 @@ class Trainer4x:
         for c in self.dcs:
             c.build_plans(self.B, hh, hh)
             hh = -(-hh // c.stride)
+        self.dirty = {"g": True, "d": True}  # variable sets whose effective / packed weights are stale
         self.scratch = torch.zeros(4096, dtype=torch.float64, device=self.device)
         self.losses = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.st = 0
@@ -336,13 +337,18 @@ class Trainer4x:
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
 
     def _refresh_weights(self):
-        for ps in (self.pg, self.pd):
-            self.call("mul", ps.w, ps.v, ps.scale, ps.total, self.st)  # W_eff = v * wscale (tools_wscale/GAN.py:668)
-        for a, b, sc in self.rbs:
-            for c in (a, b, sc):
+        """Effective weights and packed tensor-core copies -- only of the variable set an optimizer has changed since the last
+        refresh (a generator step leaves the discriminator's copies valid and vice versa: half of the re-packing launches)."""
+        if self.dirty["g"]:
+            self.call("mul", self.pg.w, self.pg.v, self.pg.scale, self.pg.total, self.st)  # W_eff = v * wscale (GAN.py:668)
+            for a, b, sc in self.rbs:
+                for c in (a, b, sc):
+                    c.refresh()
+        if self.dirty["d"]:
+            self.call("mul", self.pd.w, self.pd.v, self.pd.scale, self.pd.total, self.st)
+            for c in self.dcs:
                 c.refresh()
-        for c in self.dcs:
-            c.refresh()
+        self.dirty["g"] = self.dirty["d"] = False
 
     # ------------------------------------------------------------------ networks
     def gen_forward(self, x):
@@ -457,11 +463,14 @@ class Trainer4x:
         """Run one optimizer step eagerly, or (graphs=True) capture it on its second call and replay it afterwards."""
         x, y = self._dev(x_rows), self._dev(y_rows)
         self._prep_adam(ps)
+        which = "g" if ps is self.pg else "d"
         if not self.use_graphs:
             self._bufs = []
             self.st = torch.cuda.current_stream(self.device).cuda_stream
             body(x, y)
+            self.dirty[which] = True
             return self.losses
+        key = key + (self.dirty["g"], self.dirty["d"])  # the captured body refreshes exactly the stale sets
         ent = self._graphs.get(key)
         if ent is None:  # warm-up: plans, shared-memory attributes and allocator pools settle outside any capture
             self._bufs = []
@@ -469,15 +478,18 @@ class Trainer4x:
             body(x, y)
             self._after_graph(ps)
             self._graphs[key] = "warm"
+            self.dirty[which] = True
             return self.losses
         if ent == "warm":
             sx, sy = x.clone(), y.clone()
             launches = self.launches
             torch.cuda.synchronize(self.device)
+            stale = dict(self.dirty)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._bufs = []
                 self.st = torch.cuda.current_stream(self.device).cuda_stream
+                self.dirty.update(stale)
                 body(sx, sy)
             ent = dict(graph=g, bufs=self._bufs, x=sx, y=sy, launches=self.launches - launches)
             self._graphs[key] = ent
@@ -488,6 +500,8 @@ class Trainer4x:
             self.launches += ent["launches"]
         ent["graph"].replay()
         self._after_graph(ps)
+        self.dirty["g"] = self.dirty["d"] = False  # the replayed body refreshed what was stale ...
+        self.dirty[which] = True                   # ... and its optimizer changed this set
         return self.losses
 
     def _after_graph(self, ps):

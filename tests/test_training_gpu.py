@@ -186,4 +186,6 @@ def test_training_graph_replay_matches_eager():
         # so only the filter tensors are compared
         if name.endswith("/weight"):
             assert _rel(vb[name], va[name]) <= 3e-3, (name, _rel(vb[name], va[name]))
-    assert isinstance(tg._graphs[("d",)], dict)
+    # (graph keys carry which weight sets the captured body re-packs: the steady-state D and G bodies are captured)
+    assert any(isinstance(v, dict) for k, v in tg._graphs.items() if k[0] == "d")
+    assert any(isinstance(v, dict) for k, v in tg._graphs.items() if k[0] == "g")
