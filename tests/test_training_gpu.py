@@ -189,3 +189,59 @@ def test_training_graph_replay_matches_eager():
     # (graph keys carry which weight sets the captured body re-packs: the steady-state D and G bodies are captured)
     assert any(isinstance(v, dict) for k, v in tg._graphs.items() if k[0] == "d")
     assert any(isinstance(v, dict) for k, v in tg._graphs.items() if k[0] == "g")
+
+
+@pytest.mark.parametrize("stride,cin,cout", [(2, 2, 32), (2, 32, 64), (1, 128, 256)])
+def test_k4_conv_through_embedded_5x5_tensor_core_plan(stride, cin, cout):
+    """disc_binclass convs (k = 4, stride 2 / 1, GAN/multipassGAN-4x.py:593-614) on the tcgen05 kernel: TF's SAME window of a
+    4x4 kernel = taps -1..+2 of a 5x5 one (mpg_conv_plan_update_ex embeds the weights), a stride-2 layer = the stride-1 plan
+    sampled at even positions (mpg_train_pick), its input gradient = the plan's dgrad of dy scattered onto those positions
+    (mpg_train_stuff16). Against torch conv2d / its autograd on the same 16-bit-rounded operands."""
+    import torch.nn.functional as F
+    from mpgan_b200 import capi
+    from convref import tf_same_pad
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    n, h, w = 3, 16, 16
+    hd = capi.default_handle(0)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = (torch.randn(4, 4, cin, cout, generator=g) * (np.sqrt(2.0) / np.sqrt(16 * cin))).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    cpi, cpo = -(-cin // 8) * 8, -(-cout // 8) * 8
+    x16 = torch.zeros(n, h, w, cpi, dtype=torch.float16, device=dev)
+    x16[..., :cin] = x.to(torch.float16).to(dev)
+    oh, ow = -(-h // stride), -(-w // stride)
+    lin = torch.full((n, oh, ow, cout), float("nan"), device=dev)
+    for c0 in range(0, cout, 128):
+        cc = min(128, cout - c0)
+        pl = capi.ConvPlan(hd, n, h, w, [np.zeros((5, 5, cin, cc), np.float32)], [cpi], cc, cc, act=None,
+                           shift=np.zeros(cc, np.float32), in_dtype=capi.F16, out_dtype=capi.F32, force_kind=1)
+        pl.update(wt, mode0=0, shift=bias[c0:c0 + cc], stream=st, src_k=4, src_cout=cout, cout_off=c0)
+        full = torch.empty(n, h, w, cc, device=dev)
+        pl.run(x16, None, full, st)
+        capi.train_call("pick", hd, full, lin, n, oh, ow, cc, stride, cc, cout, c0, st)
+        pl.close()
+    torch.cuda.synchronize()
+    xr = x16[..., :cin].double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.to(torch.float16).double().permute(3, 2, 0, 1)
+    pt, pb = tf_same_pad(h, 4, stride)
+    plft, prt = tf_same_pad(w, 4, stride)
+    ref = F.conv2d(F.pad(xr, (plft, prt, pt, pb)), wr, bias.double(), stride=stride)
+    assert float(torch.linalg.norm(lin.double() - ref.permute(0, 2, 3, 1)) / torch.linalg.norm(ref)) < 1e-3
+    # input gradient
+    dy = torch.randn(n, oh, ow, cout, generator=g).to(dev)
+    g16 = torch.empty(n, h, w, cpo, dtype=torch.bfloat16, device=dev)
+    capi.train_call("stuff16", hd, dy, g16, capi.BF16, n, oh, ow, cout, stride, cpo, st)
+    pd = capi.ConvPlan(hd, n, h, w, [np.zeros((5, 5, cout, cin), np.float32)], [cpo], cin, cin, act=None,
+                       shift=np.zeros(cin, np.float32), in_dtype=capi.BF16, out_dtype=capi.F32, force_kind=1)
+    pd.update(wt, mode0=1, stream=st, src_k=4)
+    dx = torch.empty(n, h, w, cin, device=dev)
+    pd.run(g16, None, dx, st)
+    torch.cuda.synchronize()
+    pd.close()
+    dyr = dy.to(torch.bfloat16).double().permute(0, 3, 1, 2)
+    wr_b = wt.to(torch.bfloat16).double().permute(3, 2, 0, 1)
+    ref2 = F.conv2d(F.pad(xr, (plft, prt, pt, pb)), wr_b, None, stride=stride)
+    (gx,) = torch.autograd.grad(ref2, xr, dyr)
+    assert float(torch.linalg.norm(dx.double() - gx.permute(0, 2, 3, 1)) / torch.linalg.norm(gx)) < 2e-3
