@@ -444,6 +444,25 @@ __global__ void bn_finalize_kernel(const double* sums, float* mean, float* var, 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const float* gamma, const float* beta,
                                                         const float* mean, const float* invstd, float* y,
                                                         long long total, int c, int act) {
+  // 128-bit path: c % 4 == 0 keeps a float4 inside one pixel, the channel index is 32-bit arithmetic (the scalar form did one
+  // 64-bit modulo and one 4-byte load per element: these element-wise passes were a third of the training loop body)
+  if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && total < (1LL << 33)) {
+    const unsigned c4 = static_cast<unsigned>(c) >> 2;
+    const long long t4 = total >> 2;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+      const int ch = static_cast<int>(static_cast<unsigned>(e % c4)) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + e);
+      const float4 m = *reinterpret_cast<const float4*>(mean + ch), is = *reinterpret_cast<const float4*>(invstd + ch);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + ch), b = *reinterpret_cast<const float4*>(beta + ch);
+      float4 o;
+      o.x = act_fwd((v.x - m.x) * is.x * g.x + b.x, act);
+      o.y = act_fwd((v.y - m.y) * is.y * g.y + b.y, act);
+      o.z = act_fwd((v.z - m.z) * is.z * g.z + b.z, act);
+      o.w = act_fwd((v.w - m.w) * is.w * g.w + b.w, act);
+      reinterpret_cast<float4*>(y)[e] = o;
+    }
+    return;
+  }
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
     const int ch = static_cast<int>(e % c);
     const float z = (x[e] - mean[ch]) * invstd[ch] * gamma[ch] + beta[ch];
@@ -453,6 +472,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const flo
 
 // dz = dy * act'(y)   (in place allowed)
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* y, const float* dy, float* dz, long long total, int act) {
+  if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0) {
+    const long long t4 = total >> 2;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+      const float4 a = reinterpret_cast<const float4*>(y)[e], d = reinterpret_cast<const float4*>(dy)[e];
+      float4 o;
+      o.x = d.x * act_grad_from_out(a.x, act);
+      o.y = d.y * act_grad_from_out(a.y, act);
+      o.z = d.z * act_grad_from_out(a.z, act);
+      o.w = d.w * act_grad_from_out(a.w, act);
+      reinterpret_cast<float4*>(dz)[e] = o;
+    }
+    return;
+  }
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     dz[e] = dy[e] * act_grad_from_out(y[e], act);
 }
@@ -463,6 +495,31 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* x, const float
                                                       float* dx, float* dgamma, float* dbeta, long long rows, int c) {
   const long long total = rows * c;
   const float inv_n = 1.0f / static_cast<float>(rows);
+  if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    const unsigned c4 = static_cast<unsigned>(c) >> 2;
+    const long long t4 = total >> 2;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+      const int ch = static_cast<int>(static_cast<unsigned>(e % c4)) * 4;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e), dv = reinterpret_cast<const float4*>(dz)[e];
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float db = static_cast<float>(sums[ch + j]), dg = static_cast<float>(sums[c + ch + j]);
+        const float xh = (xa[j] - mean[ch + j]) * invstd[ch + j];
+        o[j] = gamma[ch + j] * invstd[ch + j] * (da[j] - inv_n * (db + xh * dg));
+      }
+      reinterpret_cast<float4*>(dx)[e] = make_float4(o[0], o[1], o[2], o[3]);
+      if (e * 4 < c) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dgamma[e * 4 + j] += static_cast<float>(sums[c + e * 4 + j]);
+          dbeta[e * 4 + j] += static_cast<float>(sums[e * 4 + j]);
+        }
+      }
+    }
+    return;
+  }
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
     const int ch = static_cast<int>(e % c);
     const float db = static_cast<float>(sums[ch]), dg = static_cast<float>(sums[c + ch]);
@@ -476,10 +533,27 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* x, const float
 }
 
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* x, float* y, long long total, int act) {
+  if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const long long t4 = total >> 2;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+      const float4 p = reinterpret_cast<const float4*>(x)[e];
+      reinterpret_cast<float4*>(y)[e] = make_float4(act_fwd(p.x, act), act_fwd(p.y, act), act_fwd(p.z, act), act_fwd(p.w, act));
+    }
+    return;
+  }
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     y[e] = act_fwd(x[e], act);
 }
 __global__ void __launch_bounds__(256) add_act_kernel(const float* a, const float* b, float* y, long long total, int act) {
+  if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const long long t4 = total >> 2;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+      const float4 p = reinterpret_cast<const float4*>(a)[e], q = reinterpret_cast<const float4*>(b)[e];
+      reinterpret_cast<float4*>(y)[e] = make_float4(act_fwd(p.x + q.x, act), act_fwd(p.y + q.y, act), act_fwd(p.z + q.z, act),
+                                                    act_fwd(p.w + q.w, act));
+    }
+    return;
+  }
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256)
     y[e] = act_fwd(a[e] + b[e], act);
 }
