@@ -41,7 +41,10 @@ def tc(name, *a):
 
 def pk(*a, **k):
     hist["pack_channels"] += 1
-    return timed("pack_channels", lambda: orig_pack(*a, **k))
+    srcs = a[1]
+    key = "pack %dsrc f%d %s -> %s cs%d @%dx%dx%d" % (len(srcs), srcs[0][5], "+".join(str(t[4]) for t in srcs),
+                                                    {0: "bf16", 1: "f16", 2: "f32"}.get(a[3], a[3]), a[4], a[5], a[6], a[7])
+    return timed(key, lambda: orig_pack(*a, **k))
 
 
 def run(self, *a, **k):
@@ -71,5 +74,5 @@ for k, v in hist.most_common():
     print("%6d %5.1f%%  %s" % (v, 100.0 * v / tot, k))
 tt = sum(tms.values())
 print("device time per loop body (events around every call, synchronised): %.3f ms" % tt)
-for k, v in tms.most_common(25):
+for k, v in tms.most_common(40):
     print("%8.3f ms %5.1f%%  %s" % (v, 100.0 * v / tt, k))
