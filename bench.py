@@ -245,6 +245,58 @@ def run_reference(args):
 
 
 # ============================================================================ secondary workloads (BASELINE configs 3-5)
+def parity_8x(mp, P, L, u, dev):
+    """The parity gate at the benchmarked 512x512 size for the 8x recipe as well: ONE input row per generator (the first slice
+    of the frame for generator 1; the same slice geometry plus a random first-pass density row for generator 2) goes through the
+    compiled nets (C ABI, tensor cores: the row-streaming kernels carry most of this recipe) and through the fp64 oracle.
+    Rank 0 only; a few seconds of CPU time (one row of net 2 is 0.2 TMAC)."""
+    import numpy as np
+    import torch
+    from mpgan_b200 import capi
+    from oracle import gan as og, networks as on
+    torch.set_num_threads(host_cores())
+    S = L * u
+    weights = P.make_weights_out(L, 1, upRes=u, nets=(1, 2))
+    cfg = on.make_cfg_out(L, upRes=u)
+    cu = on.log2i(u)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    vol = torch.from_numpy(__import__("mpgan_b200").synth.synthetic_volume(L, seed=1)).to(dev)
+    rng = np.random.default_rng(11)
+    res, gate = {}, True
+    for idx in (1, 2):
+        p_ = mp.passes[idx]
+        B, spec = p_["batch"], mp.specs[idx]
+        capi.slice_assemble(mp.h, p_["desc"], vol, None, mp.s0 + S // 3, B, p_["inbuf"], st)
+        feeds = {"x": p_["inbuf"]}
+        yrow = None
+        if idx > 1:
+            yrow = torch.from_numpy(rng.random((B, S * S), dtype=np.float32)).to(dev)
+            feeds["y"] = yrow
+        got = p_["net"].net.run(feeds, stream=st)[0].float().cpu().numpy()
+        torch.cuda.synchronize(dev)
+        x0 = p_["inbuf"][0:1].reshape(1, -1).cpu().double()
+        with torch.no_grad():
+            ctx = og.Context(og.VarStore(values=weights[idx]), torch.float64)
+            with ctx.variable_scope("gen_%d" % idx):
+                if idx == 1:
+                    ref, _ = on.growing_gen(x0, ctx, cfg, currentUpres=cu, output=True, firstGen=True, filterSize=spec.filterSize,
+                                            startFms=spec.startFms, maxFms=spec.maxFms, add_adj_idcs=spec.add_adj_idcs,
+                                            first_nn_arch=spec.first_nn_arch, use_res_net=spec.use_res_net)
+                else:
+                    xin = on.sampler_input_2(x0, yrow[0:1].cpu().double(), cfg)
+                    ref, _ = on.growing_gen(xin, ctx, cfg, currentUpres=cu, output=True, firstGen=False, filterSize=spec.filterSize,
+                                            startFms=spec.startFms, maxFms=spec.maxFms, add_adj_idcs=False, first_nn_arch=False,
+                                            use_res_net=spec.use_res_net)
+        stt = err_stats(got, ref.numpy()[0])
+        stt["ok"] = bool(stt["rel_l2"] <= 5e-3 and stt["max_abs"] <= 2e-2 * max(1.0, stt["ref_max"]))
+        gate = gate and stt["ok"]
+        res["net%d" % idx] = stt
+    res["gate"] = gate
+    res["tolerance"] = {"rel_l2": 5e-3, "max_abs": "0.02 x max(1, max|ref|)", "oracle": "fp64 restatement (oracle/)",
+                        "size": "%dx%d slices, one row per generator" % (S, S)}
+    return res
+
+
 def secondary_8x(P, synth, par, L, rank, local, world, precision, steps, peaks, barrier, max_over_ranks):
     """BASELINE.json configs[2] / [4]: multipassGAN-out 8x two-pass (nets 1+2 as shipped, GAN/example_run_output.py:18-48)
     L^3 -> (8L)^3, slice-sharded over the ranks. Device-timed like the headline; reports its own algorithmic-TFLOP fraction."""
@@ -277,6 +329,10 @@ def secondary_8x(P, synth, par, L, rank, local, world, precision, steps, peaks, 
                frac_of_bf16_peak=dict(burst=flop / (ms * 1e-3) / 1e12 / peaks["tflops"] / world,
                                       sustained=flop / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"] / world),
                checksum_bits=int(chk.item()), gpu_launches=int(mp.launches_per_frame * steps))
+    if L == 64 and precision != "fp32":
+        if rank == 0:
+            out["parity"] = parity_8x(mp, P, L, u, dev)
+        barrier()
     for p_ in mp.passes.values():
         p_["net"].net.close()
     del mp, res, x_dev
@@ -544,6 +600,10 @@ def run_ours(args):
     print(json.dumps(line))
     if parity is not None and not parity["gate"]:
         sys.stderr.write("bench.py: PARITY GATE FAILED at the benchmarked size: %s\n" % json.dumps(parity))
+        return 3
+    p8 = (secondary or {}).get("8x_64_512", {}).get("parity") if rank == 0 else None
+    if p8 is not None and not p8["gate"]:
+        sys.stderr.write("bench.py: PARITY GATE FAILED for the 8x recipe at the benchmarked size: %s\n" % json.dumps(p8))
         return 3
     return 0
 
