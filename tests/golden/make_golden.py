@@ -662,6 +662,82 @@ def make_slice_fixtures():
     print("slicedata.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_schedule_fixtures():
+    """The growing / blending / learning-rate-step schedule of the 8x trainer, traced by EXECUTING the reference's own
+    statements: the initialisation block in front of the training loop (GAN/multipassGAN-8x.py:1884-1896), the initial
+    `currentUpres` (:211-218) and, from the body of `for it in range(startingIter, trainingIterations)` (:1898), every
+    statement that drives the schedule (:1905-1916 without the data re-loading, :1966-1982); copyAdamVariables / saveModel
+    are recording stubs.  Output: one row (it, currentUpres, index, currBlendPer, lrgs, grew) per iteration."""
+    path = os.path.join(REF, "GAN", "multipassGAN-8x.py")
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    loop = [n for n in ast.walk(tree) if isinstance(n, ast.For) and isinstance(n.target, ast.Name) and n.target.id == "it"
+            and "trainingIterations" in ast.unparse(n.iter)][0]
+    parent = [n for n in ast.walk(tree) if isinstance(n, ast.Try) and loop in n.body][0]
+    sched_names = {"currBlendPer", "interpolate_Perc", "start_interpol", "interpol_c", "lrgs"}
+
+    def assigns(n):
+        return isinstance(n, ast.Assign) and all(isinstance(t, ast.Name) and t.id in sched_names for t in n.targets)
+
+    init = [n for n in parent.body[:parent.body.index(loop)]
+            if assigns(n) or (isinstance(n, ast.If) and "startingIter" in ast.unparse(n.test))]
+    up0 = [n for n in tree.body if isinstance(n, ast.If) and ast.unparse(n.test) == "outputOnly"
+           and "currentUpres" in ast.unparse(n)][0]
+    keys = ("start_interpol", "interpolate_Perc", "currBlendPer", "decayLR")
+    body = []
+    for n in loop.body:
+        if isinstance(n, ast.If) and any(k in ast.unparse(n.test) for k in keys) and not ast.unparse(n.test).startswith("0 and"):
+            if "currentUpres < upRes" in ast.unparse(n.test):  # the growing event: drop the data re-loading and the print
+                n.body = [m for m in n.body if not (isinstance(m, ast.If) and "upsampling_mode" in ast.unparse(m.test))
+                          and not (isinstance(m, ast.Expr) and "print" in ast.unparse(m))]
+            body.append(n)
+        elif isinstance(n, ast.Assign) and ast.unparse(n.targets[0]) == "index":
+            body.append(n)
+    assert len(init) >= 6 and len(body) == 7, (len(init), len(body))
+    body.append(ast.parse("trace.append((it, currentUpres, index, currBlendPer, lrgs, len(events)))").body[0])
+    loop.body = body
+    mod = ast.Module(body=[up0] + init + [loop], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    code = compile(mod, path, "exec")
+    out = {}
+    cases = {"m2_s5": dict(upsampling_mode=2, stageIter=5, decayIter=7, startingIter=0, upRes=8, decayLR=True),
+             "m2_s4_resume9": dict(upsampling_mode=2, stageIter=4, decayIter=3, startingIter=9, upRes=8, decayLR=True),
+             "m2_s4_resume12": dict(upsampling_mode=2, stageIter=4, decayIter=3, startingIter=12, upRes=8, decayLR=False),
+             "m2_s3_resume17": dict(upsampling_mode=2, stageIter=3, decayIter=4, startingIter=17, upRes=8, decayLR=True),
+             "m1_s1": dict(upsampling_mode=1, stageIter=1, decayIter=9, startingIter=0, upRes=8, decayLR=True),
+             "m1_s3": dict(upsampling_mode=1, stageIter=3, decayIter=5, startingIter=0, upRes=8, decayLR=True),
+             "m2_u4_s3": dict(upsampling_mode=2, stageIter=3, decayIter=2, startingIter=0, upRes=4, decayLR=True)}
+    import time as _time
+    for tag, c in cases.items():
+        events, trace = [], []
+        ns = dict(math=math, time=_time, outputOnly=False, trace=trace, events=events,
+                  trainingIterations=c["stageIter"] * 6 + c["decayIter"],                    # :166
+                  copyAdamVariables=lambda u: events.append(("copy", u)), saveModel=lambda c_: events.append(("save", c_)), **c)
+        exec(code, ns)
+        out[tag] = np.array(trace, np.float64)
+        out[tag + "_cfg"] = json.dumps(c)
+        print(tag, len(trace), "iterations; growing events", events)
+    # the 1-in-20 empty-density batches of getinput (:1527-1533): that one statement, executed on seeded numpy state
+    gi = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "getinput"][0]
+    stmt = [n for n in gi.body if isinstance(n, ast.If) and "randint" in ast.unparse(n.test)][0]
+    zcode = compile(ast.fix_missing_locations(ast.Module(body=[stmt], type_ignores=[])), path, "exec")
+    rng = np.random.default_rng(77)
+    xs0 = rng.random((3, 1, 4, 4, 6), dtype=np.float32)
+    ys0 = rng.random((3, 1, 8, 8, 1), dtype=np.float32)
+    hits = []
+    for seed in range(60):
+        np.random.seed(seed)
+        ns = dict(np=np, batch_xs=xs0.copy(), batch_ys=ys0.copy(), add_adj_idcs=1)
+        exec(zcode, ns)
+        if not np.array_equal(ns["batch_xs"], xs0):
+            hits.append(seed)
+            if len(hits) == 1:
+                out["zero_seed"], out["zero_xs"], out["zero_ys"] = np.array(seed), ns["batch_xs"], ns["batch_ys"]
+    out["zero_xs0"], out["zero_ys0"], out["zero_hits"] = xs0, ys0, np.array(hits)
+    print("empty-density batches at seeds", hits)
+    np.savez_compressed(os.path.join(HERE, "schedule8x.npz"), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
     if "slices" in (sys.argv[1:] or ["slices"]):
@@ -677,6 +753,8 @@ if __name__ == "__main__":
         make_net_fixtures()
     if "growdisc" in which:
         make_growdisc_fixtures()
+    if "schedule" in which:
+        make_schedule_fixtures()
     if "tiles" in which:
         make_tile_fixtures()
     if "uni" in which:
