@@ -20,8 +20,13 @@ no batch norm / gDrop / minibatch stddev in the discriminator):
   through the critic's input gradient, the optimizers of growing stage z, the generator EMA.
 Everything that computes runs in the fp32 training kernels behind the C ABI (mpg_train_*), PyTorch owns the buffers.
 Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned by executing the reference's own functions.
+* `Trainer8x.train` -- the training loop around it (:1898-2089): the growing / blending / learning-rate schedules
+  (schedule8x.GrowthSchedule, pinned by traces of the reference's own loop statements), discRuns / genRuns, the nearest resize
+  of the stage's target tiles to the full tile size (:1057-1058), the 1-in-20 empty-density batches of getinput (:1527-1533),
+  growing events, the save rule (:2076-2084) and `save` / `load` of `model_%04d.ckpt` + `model_ema_%04d.ckpt` (:1804-1807)
+  as TF checkpoint-V2 bundles that multipassGAN-out.py restores.
 Not built: the temporal discriminator / advection (lambda_t), loss scaling (numerically the identity), the feature-layer loss
-(lambda2, 0 in the shipped command), the percentage / learning-rate schedules, data loading and the command line.
+(lambda2, 0 in the shipped command), the .uni data loading of the three-frame sequences and the command line.
 """
 import math
 
@@ -29,6 +34,7 @@ import numpy as np
 import torch
 
 from . import capi
+from . import schedule8x
 from . import weights as W
 from .training import ParamSet
 
@@ -536,7 +542,9 @@ class Trainer8x:
         self.opt_d = StagedAdam(cx, self.disc.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
         self.ema = WeightEMA(self.gen.ps, 0.999)
         self.k_l1 = float(lambda_l1)
+        self.learning_rate = float(learning_rate)
         self.losses = torch.zeros(4, dtype=torch.float64, device=cx.device)
+        self.save_no = 0
 
     def disc_step(self, x_rows, y_rows, percentage, z, lerp_factor):
         cx = self.cx
@@ -567,3 +575,154 @@ class Trainer8x:
         self.opt_g.step(z)
         self.ema.update(self.opt_g.state[z]["mask"])
         return self.losses
+
+    # ------------------------------------------------------------------ the loop around the two steps
+    def target_rows(self, y_rows):
+        """y_in of :1057-1058: the stage's target tiles [B, (L * currentUpres)^2] nearest-resized to the full tile size S.
+        (The reference takes the stage's tile size from 2 ** ceil(percentage); its schedule runs one stage ahead of its data
+        (schedule8x doc), so the size is taken from the rows themselves here.)"""
+        cx, S, B = self.cx, self.gen.S, y_rows.shape[0]
+        cur = int(round(math.sqrt(y_rows.shape[1])))
+        if cur * cur != y_rows.shape[1] or S % cur:
+            raise ValueError("target rows of %d values are not square tiles dividing %d" % (y_rows.shape[1], S))
+        if cur == S:
+            return y_rows
+        out = cx.buf((B, S * S))
+        capi.pack_channels(cx.h, [(y_rows, capi.F32, 1, 0, 1, S // cur, S // cur)], out, capi.F32, 1, B, S, S, cx.st)
+        return out
+
+    def train(self, batches, schedule, discRuns=1, genRuns=1, lambda_f=1.0, add_adj_idcs=True, zero_density=True, save_dir=None,
+              saveInterval=200, alwaysSave=True, on_grow=None, log=None, log_interval=0, lerp_seed=0, max_iters=None):
+        """The training loop of GAN/multipassGAN-8x.py:1898-2089 (spatial part). `batches(currentUpres)` returns one batch
+        (x_rows [B, L*L*C], y_rows [B, (L*currentUpres)^2]) of device fp32 rows (getinput, :1497); `schedule` is a
+        schedule8x.GrowthSchedule. Per iteration: discRuns critic steps, genRuns generator steps (each on a fresh batch) with
+        the optimizers of the stage's index, blend value and decayed learning rate; at a growing event the model is saved and
+        `on_grow(new_upres)` is called (the reference re-loads its data there, :1916-1963); the model is saved when
+        `(disc_cost + gen_cost < lastCost or alwaysSave) and lastSave >= saveInterval` (:2076-2084).  The critic's
+        interpolation factors are torch's uniform numbers (TF's random stream is not reproducible).  Returns a list of
+        (it, disc_loss, g_loss_d, l1) at the logged iterations (log_interval 0: only the last iteration is read back)."""
+        cx = self.cx
+        gen_rng = torch.Generator(device=cx.device)
+        gen_rng.manual_seed(int(lerp_seed))
+        last_save, last_cost = 1, 1e10
+        kkin = self.k_l1
+        history, done = [], 0
+        d_loss = g_loss = None
+        n_total = len(schedule) if max_iters is None else min(len(schedule), int(max_iters))
+
+        def batch(upres):
+            xs, ys = batches(upres)
+            if zero_density and not min(np.random.randint(0, 20), 1):            # :1527-1533 on the device rows
+                C, scale = self.gen.C, 1.0 + np.random.rand() * 1.5
+                xs = xs.clone()
+                xv = xs.view(xs.shape[0], -1, C)
+                xv[..., 0:1] = 0
+                if add_adj_idcs and C >= 6:
+                    xv[..., 4:6] = 0
+                xv[..., 1:4] *= scale
+                ys = torch.zeros_like(ys)
+            return xs, self.target_rows(ys)
+
+        for st in schedule:
+            if done >= n_total:
+                break
+            if st.grew:
+                if save_dir is not None:
+                    self.save(save_dir)                                             # saveModel(0.0) :1913
+                if on_grow is not None:
+                    on_grow(st.currentUpres)
+            lrs_g, lrs_d = schedule8x.learning_rates(self.learning_rate, st.lrgs, schedule.decayIter, schedule.decayLR,
+                                                     self.gen.stages)
+            self.opt_g.lrs, self.opt_d.lrs = lrs_g, lrs_d
+            for _ in range(discRuns):
+                xs, ys = batch(st.currentUpres)
+                lf = torch.rand((xs.shape[0], 1), generator=gen_rng, device=cx.device)
+                d_loss = self.disc_step(xs, ys, st.percentage, st.index, lf)
+            for _ in range(genRuns):
+                xs, ys = batch(st.currentUpres)
+                kkin = lambda_f * kkin                                              # :2019
+                self.k_l1 = kkin
+                g_loss = self.gen_step(xs, ys, st.percentage, st.index).clone()
+            done += 1
+            read = (log_interval and (st.it + 1) % log_interval == 0) or done == n_total or not alwaysSave
+            if read:
+                dl = float(d_loss[0]) if d_loss is not None else 0.0
+                gl = g_loss.cpu().numpy() if g_loss is not None else np.zeros(4)
+                history.append((st.it, dl, float(gl[0]), float(gl[1])))
+                if log is not None:
+                    log("it %d upres %d stage %d blend %.4f lr %.3e: disc %.5f gen %.5f l1 %.5f" %
+                        (st.it, st.currentUpres, st.index, st.percentage, lrs_g[0], dl, gl[0], gl[1]))
+            cost = (history[-1][1] + history[-1][2]) if (read and history) else 0.0
+            if ((not alwaysSave and cost < last_cost) or alwaysSave) and last_save >= saveInterval:
+                last_save = 1
+                last_cost = cost
+                if save_dir is not None:
+                    self.save(save_dir)
+            else:
+                last_save += 1
+        return history
+
+    # ------------------------------------------------------------------ checkpoints
+    def values(self):
+        out = self.gen.ps.export()
+        out.update(self.disc.ps.export())
+        return out
+
+    def save(self, test_path):
+        """saveModel (:1804-1807): `model_%04d.ckpt` = the variables, `model_ema_%04d.ckpt` = the same names with the generator's
+        moving averages swapped in (MovingAverageOptimizer.swapping_saver), both as TF checkpoint-V2 bundles (tfckpt.py) under
+        the reference's variable names, which is what multipassGAN-out.py restores (:367-386).  The optimizer moments travel
+        in the first file under TF's slot names (`<var>/<g|d>_adam_<2**(z+1)>[_1]`) for resumed runs."""
+        import os
+        from . import tfckpt
+        vals = self.values()
+        ema = dict(vals)
+        ema.update(self.ema.export())
+        full = dict(vals)
+        for tag, opt, ps in (("g", self.opt_g, self.gen.ps), ("d", self.opt_d, self.disc.ps)):
+            for z, st in enumerate(opt.state):
+                if st["t"] == 0:
+                    continue
+                m, v, mask = st["m"].cpu().numpy(), st["v"].cpu().numpy(), st["mask"].cpu().numpy()
+                for name, shape, off, n, _ in ps.specs:
+                    if mask[off] != 0:
+                        full["%s/%s_adam_%d" % (name, tag, 2 ** (z + 1))] = m[off:off + n].reshape(shape).copy()
+                        full["%s/%s_adam_%d_1" % (name, tag, 2 ** (z + 1))] = v[off:off + n].reshape(shape).copy()
+                full["mpg_b200/%s_adam_%d/steps" % (tag, 2 ** (z + 1))] = np.array([st["t"]], np.float32)
+        os.makedirs(test_path, exist_ok=True)
+        no = self.save_no
+        tfckpt.write_checkpoint(os.path.join(test_path, "model_%04d.ckpt" % no), full)
+        tfckpt.write_checkpoint(os.path.join(test_path, "model_ema_%04d.ckpt" % no), ema)
+        self.save_no += 1
+        return no
+
+    def load(self, test_path, no):
+        """saver.restore + saver_2.restore of :1373-1377: variables, optimizer moments and the generator's moving averages."""
+        import os
+        from . import tfckpt
+        full = tfckpt.read_checkpoint(os.path.join(test_path, "model_%04d.ckpt" % no), verify_data=True)
+        ema = tfckpt.read_checkpoint(os.path.join(test_path, "model_ema_%04d.ckpt" % no), verify_data=True)
+        for tag, opt, ps in (("g", self.opt_g, self.gen.ps), ("d", self.opt_d, self.disc.ps)):
+            host = ps.v.cpu().numpy()
+            for name, shape, off, n, _ in ps.specs:
+                host[off:off + n] = np.asarray(full[name], np.float32).reshape(-1)
+            ps.v.copy_(torch.from_numpy(host))
+            for z, st in enumerate(opt.state):
+                key = "mpg_b200/%s_adam_%d/steps" % (tag, 2 ** (z + 1))
+                if key not in full:
+                    continue
+                st["t"] = int(full[key][0])
+                m, v = st["m"].cpu().numpy(), st["v"].cpu().numpy()
+                for name, shape, off, n, _ in ps.specs:
+                    k = "%s/%s_adam_%d" % (name, tag, 2 ** (z + 1))
+                    if k in full:
+                        m[off:off + n] = np.asarray(full[k], np.float32).reshape(-1)
+                        v[off:off + n] = np.asarray(full[k + "_1"], np.float32).reshape(-1)
+                st["m"].copy_(torch.from_numpy(m))
+                st["v"].copy_(torch.from_numpy(v))
+        ps = self.gen.ps
+        host = self.ema.shadow.cpu().numpy()
+        for name, shape, off, n, _ in ps.specs:
+            host[off:off + n] = np.asarray(ema[name], np.float32).reshape(-1)
+        self.ema.shadow.copy_(torch.from_numpy(host))
+        self.save_no = int(no) + 1

@@ -257,3 +257,80 @@ def test_trainer8x_critic_and_generator_steps_track_the_oracle():
         assert np.abs(got_g[n] - ref_vals[n]).max() < 5e-4, (n, float(np.abs(got_g[n] - ref_vals[n]).max()))
     for n in d_names:
         assert np.abs(got_d[n] - ref_vals[n]).max() < 5e-4, (n, float(np.abs(got_d[n] - ref_vals[n]).max()))
+
+
+def _loop_trainer(seed=7, values=None):
+    return t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2, learning_rate=1e-3, values=values, seed=seed)
+
+
+def _batches(dev, L=4, C=6, B=2, seed=5):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    seen = []
+
+    def batches(upres):
+        seen.append(upres)
+        return (torch.rand((B, L * L * C), generator=g).to(dev), torch.rand((B, (L * upres) ** 2), generator=g).to(dev))
+    return batches, seen
+
+
+def test_trainer8x_training_loop_grows_saves_and_resumes(tmp_path):
+    """Trainer8x.train over a whole (tiny) schedule: the stage's data resolution reaches `batches`, growing events save the
+    model, the per-stage optimizers leave later stages untouched, the learning rate decays, and a run resumed from the saved
+    checkpoint continues identically (variables, optimizer moments, moving averages)."""
+    from mpgan_b200 import schedule8x as S8, tfckpt
+    np.random.seed(3)
+    tr = _loop_trainer()
+    dev = tr.cx.device
+    v0 = tr.values()
+    sch = S8.GrowthSchedule(stageIter=2, decayIter=2, upRes=8, upsampling_mode=2)
+    batches, seen = _batches(dev)
+    grown, logs = [], []
+    # stage 1 only (4 iterations, optimizers of index 0): genBlock8 / dBlock8 stay at their initial values
+    hist = tr.train(batches, sch, zero_density=False, max_iters=4, log=logs.append, log_interval=1)
+    assert seen == [2] * 8 and len(hist) == 4 and all(np.isfinite(h[1:]).all() for h in hist)
+    v1 = tr.values()
+    moved = {n for n in v0 if not np.array_equal(v0[n], v1[n])}
+    assert moved and not any(("genBlock8/" in n or "dBlock8/" in n or "dBlock4/" in n or "genBlock4/g_c" in n) for n in moved), sorted(moved)
+    assert any("genBlock2/" in n for n in moved) and any("dBlock2/" in n for n in moved)
+    # the whole schedule on a fresh trainer: 14 iterations, two growing events
+    np.random.seed(3)
+    tr = _loop_trainer()
+    batches, seen = _batches(dev)
+    d = str(tmp_path / "test_0000")
+    hist = tr.train(batches, sch, save_dir=d, saveInterval=5, on_grow=grown.append, zero_density=True, log_interval=1)
+    assert grown == [4, 8] and len(hist) == 14 and seen[0] == 2 and seen[-1] == 8 and sorted(set(seen)) == [2, 4, 8]
+    assert tr.opt_g.lrs[0] == pytest.approx(S8.polynomial_decay(1e-3, 2, 2, 5e-5, 1.1))
+    assert [st["t"] for st in tr.opt_g.state] == [4, 4, 6]
+    saved = sorted(f for f in os.listdir(d) if f.endswith(".index"))
+    assert saved[:2] == ["model_0000.ckpt.index", "model_0001.ckpt.index"] and len(saved) == 2 * tr.save_no and tr.save_no >= 4
+    # the moving-average file carries the generator's shadow values under the variable names multipassGAN-out.py restores
+    last = tr.save(d)
+    ema = tfckpt.read_checkpoint(os.path.join(d, "model_ema_%04d.ckpt" % last), verify_data=True)
+    sh = tr.ema.export()
+    assert all(np.array_equal(ema[n], sh[n]) for n in sh) and any(not np.array_equal(sh[n], tr.values()[n]) for n in sh)
+    # resume: a fresh trainer restored from the files continues exactly like the original
+    tr2 = _loop_trainer(seed=99)
+    tr2.load(d, last)
+    xs, ys = torch.rand((2, 96), device=dev), torch.rand((2, 1024), device=dev)
+    lf = torch.tensor([[0.25], [0.5]])
+    for t in (tr, tr2):
+        t.opt_g.lrs = t.opt_d.lrs = [1e-3] * 3
+        t.disc_step(xs, ys, 2.5, 2, lf)
+        t.gen_step(xs, ys, 2.5, 2)
+    a, b = tr.values(), tr2.values()   # (filter gradients are summed with atomics: equal up to the summation order)
+    assert max(float(np.abs(a[n] - b[n]).max()) for n in a) < 2e-6
+    assert float((tr.ema.shadow - tr2.ema.shadow).abs().max()) < 1e-7
+
+
+def test_trainer8x_target_rows_are_the_nearest_resize():
+    tr = _loop_trainer()
+    dev = tr.cx.device
+    tr.cx.st = torch.cuda.current_stream(dev).cuda_stream
+    y = torch.rand((2, 64), device=dev)                       # 8x8 tiles (currentUpres 2 at L = 4) -> 32x32
+    got = tr.target_rows(y).view(2, 32, 32)
+    want = y.view(2, 8, 8).repeat_interleave(4, 1).repeat_interleave(4, 2)
+    assert torch.equal(got, want)
+    full = torch.rand((2, 1024), device=dev)
+    assert tr.target_rows(full) is full
+    with pytest.raises(ValueError):
+        tr.target_rows(torch.rand((2, 60), device=dev))
