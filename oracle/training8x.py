@@ -36,7 +36,9 @@ class Cfg8x:
     """Flags of GAN/multipassGAN-8x.py that shape growing_disc (defaults of the shipped first-network command)."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3,
-                 first_nn_arch=True, upsampleMode=1):
+                 first_nn_arch=True, upsampleMode=1, upsampling_mode=2):
+        self.upsampling_mode = int(upsampling_mode)  # 2: first network (grows in resolution); 1 / 3: refinement networks
+        assert self.upsampling_mode in (1, 2, 3)
         self.tileSizeLow, self.upRes = int(tileSizeLow), int(upRes)
         self.tileSizeHigh = self.tileSizeLow * self.upRes
         self.n_inputChannels = int(n_inputChannels)
@@ -47,7 +49,7 @@ class Cfg8x:
 
 
 def grow_block_disc(gan, inp, upres, fms, cfg, name="d"):
-    """growBlockDisc :752-780 (upsampling_mode 2, no batch norm, no gDrop). Returns (pooled x2, x1, x2)."""
+    """growBlockDisc :752-780 (no batch norm, no gDrop). Returns (pooled x2 [upsampling_mode 2] or x2 [1 / 3], x1, x2)."""
     with gan.ctx.variable_scope(name + "Block%d" % upres):
         filt = [4, 4] if cfg.first_nn_arch else [cfg.filterSize, cfg.filterSize]
         out2 = min(min(fms * 2, cfg.max_fms), cfg.start_fms // 2)
@@ -61,8 +63,10 @@ def grow_block_disc(gan, inp, upres, fms, cfg, name="d"):
                                             in_channels=fms)
             x2, _ = gan.convolutional_layer(out2, filt, og.lrelu, stride=[1], name="%s_cB%d" % (name, upres), in_layer=x1,
                                             in_channels=fms)
-        gan.layer = avg_pool2(gan.layer)  # outp = gan.avg_pool() :771-772
-        return gan.layer, x1, x2
+        if cfg.upsampling_mode == 2:
+            gan.layer = avg_pool2(gan.layer)  # outp = gan.avg_pool() :771-772
+            return gan.layer, x1, x2
+        return x2, x1, x2                     # :773-774
 
 
 def growing_disc(in_high, in_low, percentage, ctx, cfg):
@@ -82,7 +86,8 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
         gan2 = og.GAN(in_high_, ctx)
         for j in range(cfg.stages, 0, -1):
             num_fms = int(min(cfg.start_fms / (2 ** j), cfg.max_fms))
-            in_high_ = avg_pool2(in_high_)                                             # :828-829
+            if cfg.upsampling_mode == 2:
+                in_high_ = avg_pool2(in_high_)                                         # :828-829
             x_, x1, x2 = grow_block_disc(gan, x_, int(2 ** j), num_fms, cfg)           # :833
             from_dens = min(min(num_fms * 2, cfg.max_fms), cfg.start_fms // 2)
             old, _ = gan2.convolutional_layer(from_dens, [1, 1], None, stride=[1], name="d_cfromDensity%d" % (2 ** (j - 1)),
@@ -106,38 +111,68 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
 
 
 def growing_gen_train(x_rows, percentage, ctx, cfg, pixel_norm=True, addBicubicUpsample=True):
-    """growing_gen with output=False (GAN/multipassGAN-8x.py:700-750), firstNNArch / upsampling_mode 2: every stage emits a
-    density (1x1 conv, gain 1) [+ the bicubic upsample of the input density], blended with the nearest-upsampled density of
-    the previous stage by lerp(old, new, percentage - (j-1)).  Returns the flat rows [B, S*S]."""
+    """growing_gen with output=False (GAN/multipassGAN-8x.py:700-750): every stage emits a density (1x1 conv, gain 1) plus the
+    residual input density, blended with the density of the previous stage by lerp(old, new, percentage - (j-1)).
+    upsampling_mode 2 (firstNNArch): x_rows [B, L*L*C], nearest x2 per stage, bicubic residual; upsampling_mode 1 / 3
+    (refinement networks): x_rows [B, S*S*(C+1)] = concat(first-pass density, resized low-res fields), two head resBlocks,
+    no resampling, the residual is channel 0 of the input.  Returns the flat rows [B, S*S]."""
     ocfg = on.make_cfg_out(cfg.tileSizeLow, cfg.upRes, cfg.n_inputChannels, pixel_norm=pixel_norm,
                            addBicubicUpsample=addBicubicUpsample, upsampleMode=cfg.upsampleMode)
-    L, C = cfg.tileSizeLow, cfg.n_inputChannels
+    L, S, C = cfg.tileSizeLow, cfg.tileSizeHigh, cfg.n_inputChannels
+    first = cfg.upsampling_mode == 2
+    assert first == cfg.first_nn_arch, "built: firstNNArch with upsampling_mode 2, the plain res-net with modes 1 / 3"
     with ctx.variable_scope("generator"):
-        _in = x_rows.reshape(-1, L, L, C)
+        _in = x_rows.reshape(-1, L, L, C) if first else x_rows.reshape(-1, S, S, C + 1)   # :702-705
         gan = og.GAN(_in, ctx)
-        x_g = _in                                                                       # first_nn_arch :712-713
+        if first:
+            x_g = _in                                                                   # first_nn_arch :712-713
+        else:
+            m = min(cfg.max_fms, cfg.start_fms // 2)
+            x_g = on._resblock_out(gan, ocfg, _in, 16, m // 8, False, "1", cfg.filterSize, False)        # :715
+            x_g = on._resblock_out(gan, ocfg, x_g, m // 4, m // 2, False, "2", cfg.filterSize, False)    # :716
         old, _ = og.GAN(x_g, ctx).convolutional_layer(1, [1, 1], None, stride=[1], name="g_cdensOut1", in_layer=x_g, gain=1)
         for j in range(1, cfg.stages + 1):
             num_fms = min(int(cfg.start_fms / (2 ** j)), cfg.max_fms)
-            x_g, dens = on._grow_block_gen(gan, ctx, ocfg, x_g, int(2 ** j), num_fms, False, False, False, True,
-                                           cfg.filterSize, True, True)
-            if addBicubicUpsample:                                                      # :735-737
-                dens = dens + og.GAN(_in[..., 0:1], ctx).avg_depool(mode=2, scale=[int(2 ** j)])
+            x_g, dens = on._grow_block_gen(gan, ctx, ocfg, x_g, int(2 ** j), num_fms, False, False, False, first,
+                                           cfg.filterSize, first, True)
+            if addBicubicUpsample:                                                      # :735-739
+                if first:
+                    dens = dens + og.GAN(_in[..., 0:1], ctx).avg_depool(mode=2, scale=[int(2 ** j)])
+                else:
+                    dens = dens + _in[..., 0:1]
             with ctx.variable_scope("growingPart%i" % j):
-                old = og.GAN(old, ctx).avg_depool(mode=1)                               # :744
-                old = lerp(old, dens, percentage - (j - 1))                             # :748
-        return old.reshape(-1, cfg.tileSizeHigh * cfg.tileSizeHigh)
+                if first:
+                    old = og.GAN(old, ctx).avg_depool(mode=1)                           # :744
+                old = lerp(old, dens, percentage - (j - 1))                             # :748-750
+        return old.reshape(-1, S * S)
+
+
+def refine_input(x_rows, y_rows, cfg):
+    """x_in / y_in of the refinement networks' training graph (:1042-1044, 1061-1062): the target rows carry two channels,
+    y[..., 0] = the high-res density to learn, y[..., 1] = the first-pass density; the network input is
+    concat(y[..., 1], nearest resize of the low-res fields).  Returns (x_in rows [B, S*S*(C+1)], y_in [B, S*S])."""
+    L, S, C = cfg.tileSizeLow, cfg.tileSizeHigh, cfg.n_inputChannels
+    y2 = y_rows.reshape(-1, S, S, 2)
+    lo = tf_ops.resize_nearest(x_rows.reshape(-1, L, L, C), S, S)
+    x_in = torch.cat([y2[..., 1:2], lo], dim=3)
+    return x_in.reshape(-1, S * S * (C + 1)), y2[..., 0].reshape(-1, S * S)
 
 
 def wgan_gp_losses(disc, gen, d_out_fn, y_in, gen_y, lerp_factor, wgan_lambda=10.0, wgan_target=1.0, wgan_epsilon=0.001,
-                   weight_dld=1.0):
+                   weight_dld=1.0, image_side=None):
     """Discriminator / generator critic losses with use_wgan_gp (:1101-1143). d_out_fn(y) -> critic logits.
-    lerp_factor: the tf.random_uniform([B, 1]) sample of :1120 (fed in, so that both sides use the same numbers)."""
+    lerp_factor: the tf.random_uniform([B, 1]) sample of :1120 (fed in, so that both sides use the same numbers).
+    image_side: upsampling_mode 1 / 3 keeps the samples as [B, S, S, 1] images there (:1047, 1062), so the reference's
+    `reduce_sum(..., axis=1)` (:1130) sums over the image ROWS only: one gradient norm per (sample, column).  Reproduced:
+    pass S to get that reduction on the flat rows."""
     d_loss = (-disc).mean() * weight_dld + gen.mean()
     y_gp = (lerp_factor * y_in + (1 - lerp_factor) * gen_y).detach().requires_grad_(True)
     d_out_loss = d_out_fn(y_gp).mean()
     grads = torch.autograd.grad(d_out_loss, y_gp, create_graph=True)[0]
-    norms = torch.sqrt(((grads + 1e-4) ** 2).sum(dim=1))                               # :1130
+    if image_side is None:
+        norms = torch.sqrt(((grads + 1e-4) ** 2).sum(dim=1))                           # :1130
+    else:
+        norms = torch.sqrt(((grads.reshape(-1, image_side, image_side) + 1e-4) ** 2).sum(dim=1))
     gp = (wgan_lambda * (norms - wgan_target) ** 2).mean()
     eps_pen = (disc ** 2).mean()
     return dict(disc_loss=d_loss + eps_pen * wgan_epsilon + gp, grad_penalty=gp, epsilon_penalty=eps_pen,

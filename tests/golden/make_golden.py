@@ -326,13 +326,13 @@ def make_growdisc_fixtures():
     fixtures = {}
     rng = np.random.default_rng(8)
 
-    def run(tag, seed, L, u, C, start_fms, max_fms, first_nn_arch, percentages, filterSize=3):
+    def run(tag, seed, L, u, C, start_fms, max_fms, first_nn_arch, percentages, filterSize=3, upsampling_mode=2):
         S = L * u
         store, getv = _provide(seed)
         tfs.reset({})
         tfs.get_variable = getv
         ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, tileSizeLow=L, tileSizeHigh=S, upRes=u,
-                  n_inputChannels=C, upsampling_mode=2, upsampleMode=1, start_fms=start_fms, max_fms=max_fms,
+                  n_inputChannels=C, upsampling_mode=upsampling_mode, upsampleMode=1, start_fms=start_fms, max_fms=max_fms,
                   filterSize=filterSize, first_nn_arch=first_nn_arch, useVelInTDisc=False, bn_decay=0.999,
                   use_mb_stddev=False, gn=lambda x, gstr: x, print=lambda *a, **k: None)
         exec(code, ns)
@@ -355,22 +355,24 @@ def make_growdisc_fixtures():
         fixtures[tag + "_wsum"] = _wsum(store)
         fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, C=C, start_fms=start_fms, max_fms=max_fms,
                                                  first_nn_arch=first_nn_arch, percentages=list(percentages),
-                                                 filterSize=filterSize))
+                                                 filterSize=filterSize, upsampling_mode=upsampling_mode))
 
     gen_code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["lerp", "resBlock", "growBlockGen", "growing_gen"])
 
-    def run_gen(tag, seed, L, u, C, start_fms, max_fms, percentages):
+    def run_gen(tag, seed, L, u, C, start_fms, max_fms, percentages, first_nn_arch=True, upsampling_mode=2, filterSize=3):
         """growing_gen in TRAINING mode (output=False: per-stage density outputs blended with lerp, :700-750)."""
         S = L * u
         store, getv = _provide(seed)
         tfs.reset({})
         tfs.get_variable = getv
         ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, tileSizeLow=L, tileSizeHigh=S, upRes=u,
-                  n_inputChannels=C, n_output=S * S, upsampling_mode=2, upsampleMode=1, start_fms=start_fms, max_fms=max_fms,
-                  filterSize=3, first_nn_arch=True, use_res_net=True, pixel_norm=True, usePixelShuffle=False,
+                  n_inputChannels=C, n_output=S * S, upsampling_mode=upsampling_mode, upsampleMode=1, start_fms=start_fms,
+                  max_fms=max_fms, filterSize=filterSize, first_nn_arch=first_nn_arch, use_res_net=True, pixel_norm=True,
+                  usePixelShuffle=False,
                   addBicubicUpsample=True, dataDimension=2, bn_decay=0.999, train=False, rbId=0, print=lambda *a, **k: None)
         exec(gen_code, ns)
-        x_rows = rng.random((2, L * L * C), dtype=np.float32)
+        # upsampling_mode 1 / 3: the network input is the high-res concat(first-pass density, resized low-res fields) :684
+        x_rows = rng.random((2, L * L * C) if upsampling_mode == 2 else (2, S * S * (C + 1)), dtype=np.float32)
         fixtures[tag + "_x"] = x_rows
         for k, pct in enumerate(percentages):
             tfs.STATE.requested = {}
@@ -381,11 +383,15 @@ def make_growdisc_fixtures():
         fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
         fixtures[tag + "_wsum"] = _wsum(store)
         fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, C=C, start_fms=start_fms, max_fms=max_fms,
-                                                 percentages=list(percentages)))
+                                                 percentages=list(percentages), first_nn_arch=first_nn_arch,
+                                                 upsampling_mode=upsampling_mode, filterSize=filterSize))
 
     run_gen("gg_first", 83, 4, 8, 6, 32, 32, (0.4, 1.3, 2.75, 3.0))
     run("gd_first", 81, 4, 8, 6, 32, 32, True, (0.4, 1.3, 2.75, 3.0))
     run("gd_plain", 82, 4, 4, 4, 32, 16, False, (0.5, 1.6, 2.0))
+    # the second (refinement) network's training graph: upsampling_mode 1, firstNNArch 0 (GAN/example_run_training.py:7)
+    run_gen("gg_second", 84, 2, 8, 4, 32, 32, (0.4, 1.3, 2.75, 3.0), first_nn_arch=False, upsampling_mode=1, filterSize=5)
+    run("gd_second", 85, 2, 8, 4, 32, 32, False, (0.4, 1.3, 2.75, 3.0), filterSize=5, upsampling_mode=1)
     np.savez_compressed(os.path.join(HERE, "growdisc.npz"), **fixtures)
     print("growdisc.npz written:", len(fixtures), "arrays")
 

@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import gan as og
@@ -16,11 +17,12 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "growdisc.npz")
 
 def _cfg(tag):
     c = json.loads(str(GOLD[tag + "_cfg"]))
-    return c, o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], c["filterSize"], c["first_nn_arch"])
+    return c, o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], c["filterSize"], c["first_nn_arch"],
+                       upsampling_mode=c.get("upsampling_mode", 2))
 
 
 def test_growing_disc_oracle_reproduces_the_reference_code():
-    for tag in ("gd_first", "gd_plain"):
+    for tag in ("gd_first", "gd_plain", "gd_second"):   # gd_second: upsampling_mode 1 (no pooling anywhere)
         c, cfg = _cfg(tag)
         store = og.VarStore(seed=c["seed"])
         x = torch.from_numpy(GOLD[tag + "_x"]).double()
@@ -86,15 +88,40 @@ def test_wgan_gp_gradient_penalty_is_differentiable_wrt_the_critic():
     assert L["grad_norms"].shape == (2,) and float(L["grad_penalty"]) > 0
 
 
-def test_growing_gen_training_graph_reproduces_the_reference_code():
-    """growing_gen with output=False (per-stage density outputs blended with lerp, GAN/multipassGAN-8x.py:700-750)."""
-    c = json.loads(str(GOLD["gg_first_cfg"]))
-    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+@pytest.mark.parametrize("tag", ["gg_first", "gg_second"])
+def test_growing_gen_training_graph_reproduces_the_reference_code(tag):
+    """growing_gen with output=False (per-stage density outputs blended with lerp, GAN/multipassGAN-8x.py:700-750): the first
+    network (firstNNArch, upsampling_mode 2) and the refinement network (upsampling_mode 1, two head resBlocks, no resampling)."""
+    c, cfg = _cfg(tag)
     store = og.VarStore(seed=c["seed"])
-    x = torch.from_numpy(GOLD["gg_first_x"]).double()
+    x = torch.from_numpy(GOLD[tag + "_x"]).double()
     for k, pct in enumerate(c["percentages"]):
         out = o8.growing_gen_train(x, pct, og.Context(store, torch.float64), cfg)
-        ref = GOLD["gg_first_p%d_out" % k]
+        ref = GOLD["%s_p%d_out" % (tag, k)]
         assert out.shape == ref.shape and np.abs(out.numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), pct
-    want = {k: tuple(v) for k, v in json.loads(str(GOLD["gg_first_vars"]))}
+    want = {k: tuple(v) for k, v in json.loads(str(GOLD[tag + "_vars"]))}
     assert {k: tuple(v.shape) for k, v in store.values.items()} == want
+
+
+def test_refinement_gradient_penalty_reduces_over_image_rows():
+    """upsampling_mode 1 / 3: the reference's reduce_sum(axis=1) acts on [B, S, S, 1] gradients (:1130), so there is one norm
+    per (sample, column); refine_input builds x_in / y_in of :1042-1044, 1061-1062."""
+    c, cfg = _cfg("gd_second")
+    S = cfg.tileSizeHigh
+    store = og.VarStore(seed=c["seed"])
+    ctx = ot.TrainContext(store, torch.float64)
+    x = torch.from_numpy(GOLD["gd_second_x"]).double()
+    y = torch.from_numpy(GOLD["gd_second_y"]).double()
+    g = y * 0.5 + 0.1
+    disc, _ = o8.growing_disc(y, x, 2.4, ctx, cfg)
+    gen, _ = o8.growing_disc(g, x, 2.4, ctx, cfg)
+    lf = torch.tensor([[0.3], [0.8]], dtype=torch.float64)
+    L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, 2.4, ctx, cfg)[0], y, g, lf, image_side=S)
+    assert L["grad_norms"].shape == (2, S) and float(L["grad_penalty"]) > 0
+    y2 = torch.stack([y, g], dim=2).reshape(2, S * S * 2)
+    x_in, y_in = o8.refine_input(x, y2, cfg)
+    assert torch.equal(y_in, y) and x_in.shape == (2, S * S * (cfg.n_inputChannels + 1))
+    xi = x_in.reshape(2, S, S, -1)
+    assert torch.equal(xi[..., 0], g.reshape(2, S, S))
+    lo = x.reshape(2, cfg.tileSizeLow, cfg.tileSizeLow, -1)
+    assert torch.equal(xi[:, 5, 9, 1:], lo[:, 5 * cfg.tileSizeLow // S, 9 * cfg.tileSizeLow // S, :])
