@@ -111,11 +111,18 @@ class _Conv8:
 
 
 class GrowingDisc:
-    """growing_disc (GAN/multipassGAN-8x.py:782-866), upsampling_mode 2."""
+    """growing_disc (GAN/multipassGAN-8x.py:782-866). upsampling_mode 2 (first network): every growBlockDisc ends in a 2x2
+    average pooling and the image is pooled along (:771-772, 828-829); upsampling_mode 1 / 3 (refinement networks): no
+    pooling anywhere, every stage works at the full tile size (:773-774)."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3,
-                 first_nn_arch=True, batch=16, values=None, seed=1, device=0, cx=None):
+                 first_nn_arch=True, batch=16, values=None, seed=1, device=0, cx=None, upsampling_mode=2):
         self.cx = cx if cx is not None else _Ctx(device)
+        if int(upsampling_mode) not in (1, 2, 3):
+            raise ValueError("upsampling_mode %r: built are 2 (first network) and 1 / 3 (refinement networks)" % (upsampling_mode,))
+        self.pool = int(upsampling_mode) == 2
+        if not self.pool and first_nn_arch:
+            raise ValueError("firstNNArch is the first network's architecture (upsampling_mode 2)")
         self.L, self.u, self.S, self.C, self.B = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(n_inputChannels), int(batch)
         self.stages = int(round(math.log(self.u, 2)))
         self.first = bool(first_nn_arch)
@@ -140,7 +147,7 @@ class GrowingDisc:
             self.tail = (_Conv8(cx, ps, sc + "d_cA1", int(filterSize), last, 32, "lrelu"),
                          _Conv8(cx, ps, sc + "d_cB1", int(filterSize), 32, 4, None))
             last = 4
-        self.fc_in = self.L * self.L * last
+        self.fc_in = (self.L * self.L if self.pool else self.S * self.S) * last
         self.fc_w = ps.add(sc + "d_l61/weight", (self.fc_in, 1), np.float32(1.0 / np.sqrt(self.fc_in)))  # gain 1 (:862)
         self.fc_b = ps.add(sc + "d_l61/bias", (1,))
         vals = dict(values) if values else {}
@@ -180,16 +187,18 @@ class GrowingDisc:
         inH, res = xin, S
         for j in range(self.stages, 0, -1):
             a, b, out2 = self.blocks[j]
-            inH = self._pool(inH, B, res, res, 2)
+            ro = res // 2 if self.pool else res
+            if self.pool:
+                inH = self._pool(inH, B, res, res, 2)
             x1, sa = a.forward(x_, B, res, res)
             x2, sb = b.forward(x1, B, res, res)
-            pooled = self._pool(x2, B, res, res, out2)
-            old, so = self.c_from[2 ** (j - 1)].forward(inH, B, res // 2, res // 2)
+            pooled = self._pool(x2, B, res, res, out2) if self.pool else x2
+            old, so = self.c_from[2 ** (j - 1)].forward(inH, B, ro, ro)
             t = self._t(percentage, j)
             blend = cx.buf(pooled.shape)
             cx.call("lerp", blend, old, pooled, t, blend.numel(), cx.st)
             sv["lvl"][j] = dict(sa=sa, sb=sb, so=so, res=res, t=t, inH=inH, pooled=pooled)
-            x_, res = blend, res // 2
+            x_, res = blend, ro
         if self.first:
             flat = sv["lvl"][1]["pooled"]  # cursor quirk: flatten() sees the pooled block output, not the last blend
         else:
@@ -220,6 +229,8 @@ class GrowingDisc:
             dblend = cx.buf(sv["t1"]["x"].shape)
             self.tail[0].backward(sv["t1"], d1, dx=dblend, param_grads=param_grads)
         dH = None  # gradient w.r.t. the pooled input image of the level being processed
+        # without pooling every d_cfromDensity conv reads the SAME image: their input gradients add up in place
+        dxin_np = cx.zeros(sv["xin"].shape) if (need_input_grad and not self.pool) else None
         for j in range(1, self.stages + 1):
             a, b, out2 = self.blocks[j]
             lv = sv["lvl"][j]
@@ -229,26 +240,35 @@ class GrowingDisc:
                 cx.call("scale", dpool, dblend, t, dpool.numel(), cx.st)
                 dold = cx.buf(dblend.shape)
                 cx.call("scale", dold, dblend, 1.0 - t, dold.numel(), cx.st)
-                dHj = cx.buf(lv["inH"].shape) if need_input_grad else None
-                self.c_from[2 ** (j - 1)].backward(lv["so"], dold, dx=dHj, param_grads=param_grads)
+                if self.pool:
+                    dHj = cx.buf(lv["inH"].shape) if need_input_grad else None
+                    self.c_from[2 ** (j - 1)].backward(lv["so"], dold, dx=dHj, param_grads=param_grads)
+                else:
+                    self.c_from[2 ** (j - 1)].backward(lv["so"], dold, dx=dxin_np, accumulate=True, param_grads=param_grads)
             else:
                 dHj = cx.zeros(lv["inH"].shape) if need_input_grad else None
             if j == 1 and self.first:
                 cx.call("axpy", dpool, dflat, 1.0, dpool.numel(), cx.st)
-            if need_input_grad:
+            if need_input_grad and self.pool:
                 if dH is not None:  # the deeper level's image gradient comes up through this level's pooling
                     cx.call("avgpool2_bwd", dH, dHj, B, res // 2, res // 2, 2, 1, cx.st)
                 dH = dHj
-            dx2 = cx.buf(lv["sb"]["y"].shape)
-            cx.call("avgpool2_bwd", dpool, dx2, B, res, res, out2, 0, cx.st)
+            if self.pool:
+                dx2 = cx.buf(lv["sb"]["y"].shape)
+                cx.call("avgpool2_bwd", dpool, dx2, B, res, res, out2, 0, cx.st)
+            else:
+                dx2 = dpool
             dx1 = cx.buf(lv["sa"]["y"].shape)
             b.backward(lv["sb"], dx2, dx=dx1, param_grads=param_grads)
             dblend = cx.buf(lv["sa"]["x"].shape)
             a.backward(lv["sa"], dx1, dx=dblend, param_grads=param_grads)
         dxin = None
         if need_input_grad:
-            dxin = cx.buf(sv["xin"].shape)
-            cx.call("avgpool2_bwd", dH, dxin, B, self.S, self.S, 2, 0, cx.st)
+            if self.pool:
+                dxin = cx.buf(sv["xin"].shape)
+                cx.call("avgpool2_bwd", dH, dxin, B, self.S, self.S, 2, 0, cx.st)
+            else:
+                dxin = dxin_np
             self.c_from[self.u].backward(sv["from_u"], dblend, dx=dxin, accumulate=True, param_grads=param_grads)
         else:
             self.c_from[self.u].backward(sv["from_u"], dblend, param_grads=param_grads)
@@ -267,8 +287,16 @@ class GrowingDisc:
         g = cx.buf((B, S * S))
         cx.call("take_channel", dxin, g, B * S * S, 2, 1, 0, cx.st)  # tf.gradients(..., [y_gp_d, x_disc])[0]
         v = cx.buf((B, S * S))
-        norms = cx.buf((B,))
-        cx.call("gp_penalty", g, v, loss, norms, B, S * S, float(lam), float(target), cx.st)
+        if self.pool:
+            norms = cx.buf((B,))
+            cx.call("gp_penalty", g, v, loss, norms, B, S * S, float(lam), float(target), cx.st)
+        else:
+            # upsampling_mode 1 / 3 keep the samples as [B, S, S, 1] images, so the reference's reduce_sum(axis=1) (:1130) sums
+            # over the image rows only: one norm per (sample, column). Columns become rows for the kernel and back.
+            gT, vT, norms = cx.buf((B, S, S)), cx.buf((B, S, S)), cx.buf((B * S,))
+            capi.transpose3d(cx.h, g, gT, (B, S, S), (0, 2, 1), 0.0, cx.st)
+            cx.call("gp_penalty", gT, vT, loss, norms, B * S, S, float(lam), float(target), cx.st)
+            capi.transpose3d(cx.h, vT, v, (B, S, S), (0, 2, 1), 0.0, cx.st)
         # tangent pass of (0, v) through the linearised critic; every layer adds wgrad(tangent input, primal delta)
         txin = cx.zeros((B, S, S, 2))
         capi.pack_channels(cx.h, [(cx.zeros((B, S * S)), capi.F32, 1, 0, 1, 1, 1), (v, capi.F32, 1, 0, 1, 1, 1)], txin, capi.F32,
@@ -278,10 +306,11 @@ class GrowingDisc:
         for j in range(self.stages, 0, -1):
             a, b, out2 = self.blocks[j]
             lv = sv["lvl"][j]
-            tH = self._pool(tH, B, res, res, 2)
+            if self.pool:
+                tH = self._pool(tH, B, res, res, 2)
             t1 = a.tangent(t_x, lv["sa"])
             t2 = b.tangent(t1, lv["sb"])
-            tp = self._pool(t2, B, res, res, out2)
+            tp = self._pool(t2, B, res, res, out2) if self.pool else t2
             if "dlin" in lv["so"]:
                 told = self.c_from[2 ** (j - 1)].tangent(tH, lv["so"])
                 t_x = cx.buf(tp.shape)
@@ -290,7 +319,8 @@ class GrowingDisc:
                 t_x = tp
             if j == 1 and self.first:
                 t_flat = tp
-            res //= 2
+            if self.pool:
+                res //= 2
         if not self.first:
             y1 = self.tail[0].tangent(t_x, sv["t1"])
             t_flat = self.tail[1].tangent(y1, sv["t2"])
@@ -379,27 +409,48 @@ class WeightEMA:
 
 
 class GrowingGen:
-    """growing_gen in TRAINING mode (GAN/multipassGAN-8x.py:626-750, output=False; firstNNArch, upsampling_mode 2, pixel_norm,
-    no batch norm): nearest x2 per stage, resBlocks  A(k, relu) -> pixel_norm -> B(k) ; s(1x1) ; pixel_norm(relu(B + s)),
-    a density output per stage (1x1, gain 1) [+ the TF1-bicubic upsample of the input density], blended with the
-    nearest-upsampled density of the previous stage by lerp(old, new, percentage - (j-1)). Forward and backward."""
+    """growing_gen in TRAINING mode (GAN/multipassGAN-8x.py:626-750, output=False; pixel_norm, no batch norm): resBlocks
+    A(k, relu) -> pixel_norm -> B(k) ; s(1x1) ; pixel_norm(relu(B + s)), a density output per stage (1x1, gain 1) plus the
+    residual input density, blended with the density of the previous stage by lerp(old, new, percentage - (j-1)).
+    Forward and backward.
+    * upsampling_mode 2 / firstNNArch (first network): input rows [B, L*L*C], nearest x2 per stage, 5 / 3 / 2 resBlocks,
+      TF1-bicubic residual of input channel 0, the previous stage's density nearest-upsampled before the blend.
+    * upsampling_mode 1 / 3 (refinement networks, use_res_net): input rows [B, S*S*(C+1)] (concat(first-pass density, resized
+      low-res fields), :1042-1044), two head resBlocks (:715-716), two resBlocks per stage, no resampling anywhere, the
+      residual is input channel 0 itself (:738-739)."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
-                 addBicubicUpsample=True, values=None, seed=1, device=0, cx=None):
+                 addBicubicUpsample=True, values=None, seed=1, device=0, cx=None, upsampling_mode=2):
         self.cx = cx if cx is not None else _Ctx(device)
+        if int(upsampling_mode) not in (1, 2, 3):
+            raise ValueError("upsampling_mode %r: built are 2 (first network) and 1 / 3 (refinement networks)" % (upsampling_mode,))
+        self.up = int(upsampling_mode) == 2
         self.L, self.u, self.S, self.C = int(tileSizeLow), int(upRes), int(tileSizeLow) * int(upRes), int(n_inputChannels)
         self.stages = int(round(math.log(self.u, 2)))
         self.bicubic = bool(addBicubicUpsample)
         self.ps = ps = ParamSet(self.cx.device)
         cx, k = self.cx, int(filterSize)
         sc = "generator/"
-        self.c_dens = {1: _Conv8(cx, ps, sc + "g_cdensOut1", 1, self.C, 1, None, gain=1.0)}
+
+        def rb(pre, name, cin, s1, s2):
+            return (_Conv8(cx, ps, pre + "g_cA_" + name, k, cin, s1, "relu"), _Conv8(cx, ps, pre + "g_cB_" + name, k, s1, s2, None),
+                    _Conv8(cx, ps, pre + "g_s_" + name, 1, cin, s2, None))
+
+        self.cin0 = cin = self.C if self.up else self.C + 1
+        self.head = []
+        if not self.up:
+            m = min(int(max_fms), int(start_fms) // 2)
+            for s1, s2, name in ((16, m // 8, "1"), (m // 4, m // 2, "2")):
+                self.head.append(rb(sc, name, cin, s1, s2))
+                cin = s2
+        self.c_dens = {1: _Conv8(cx, ps, sc + "g_cdensOut1", 1, cin, 1, None, gain=1.0)}
         self.blocks = {}
-        cin = self.C
         for j in range(1, self.stages + 1):
             fms = min(int(start_fms / (2 ** j)), max_fms)
             up = 2 ** j
-            if up == 2:
+            if not self.up:
+                plan = [(fms, fms, "first"), (fms // 2, fms // 2, "second")]
+            elif up == 2:
                 plan = [(fms, fms, n) for n in ("first", "second", "third", "fourth", "fifth")]
             elif up == 4:
                 plan = [(fms * 2, fms, "first"), (fms, fms, "second"), (fms, fms, "third")]
@@ -407,10 +458,7 @@ class GrowingGen:
                 plan = [(fms * 2, fms, "first"), (fms, fms, "second")]
             rbs = []
             for s1, s2, name in plan:
-                pre = sc + "genBlock%d/" % up
-                rbs.append((_Conv8(cx, ps, pre + "g_cA_" + name, k, cin, s1, "relu"),
-                            _Conv8(cx, ps, pre + "g_cB_" + name, k, s1, s2, None),
-                            _Conv8(cx, ps, pre + "g_s_" + name, 1, cin, s2, None)))
+                rbs.append(rb(sc + "genBlock%d/" % up, name, cin, s1, s2))
                 cin = s2
             self.blocks[j] = rbs
             self.c_dens[up] = _Conv8(cx, ps, sc + "genBlock%d/g_cdensOut%d" % (up, up), 1, cin, 1, None, gain=1.0)
@@ -443,37 +491,69 @@ class GrowingGen:
         self.cx.call("pixel_norm_fwd", x, y, x.numel() // x.shape[-1], x.shape[-1], self.cx.st)
         return y
 
+    def _rb_fwd(self, rb, inp, B, res):
+        cx = self.cx
+        a, b, s = rb
+        ya, sa = a.forward(inp, B, res, res)
+        yap = self._pn(ya)
+        yb, sb = b.forward(yap, B, res, res)
+        ys, ss = s.forward(inp, B, res, res)
+        r = cx.buf(yb.shape)
+        cx.call("add_act_fwd", yb, ys, r, r.numel(), capi.ACT_RELU, cx.st)
+        return self._pn(r), dict(sa=sa, sb=sb, ss=ss, ya=ya, r=r)
+
+    def _rb_bwd(self, rb, q, d, need_input_grad):
+        """d: gradient w.r.t. the block's (pixel-normed) output; returns the gradient w.r.t. its input (None for data)."""
+        cx = self.cx
+        a, b, s = rb
+        d_r = cx.buf(q["r"].shape)
+        cx.call("pixel_norm_bwd", q["r"], d, d_r, q["r"].numel() // q["r"].shape[-1], q["r"].shape[-1], cx.st)
+        d_sum = cx.buf(q["r"].shape)
+        cx.call("act_bwd", q["r"], d_r, d_sum, d_sum.numel(), capi.ACT_RELU, cx.st)
+        d_yap = cx.buf(q["ya"].shape)
+        b.backward(q["sb"], d_sum, dx=d_yap)
+        d_inp = cx.buf(q["sa"]["x"].shape) if need_input_grad else None
+        s.backward(q["ss"], d_sum, dx=d_inp)
+        d_ya = cx.buf(q["ya"].shape)
+        cx.call("pixel_norm_bwd", q["ya"], d_yap, d_ya, q["ya"].numel() // q["ya"].shape[-1], q["ya"].shape[-1], cx.st)
+        a.backward(q["sa"], d_ya, dx=d_inp, accumulate=True)
+        return d_inp
+
     def forward(self, x_rows, percentage):
-        """x_rows [B, L*L*C] device fp32 -> (gen rows [B, S*S], saved)."""
+        """x_rows: device fp32 [B, L*L*C] (upsampling_mode 2) or [B, S*S*(C+1)] (1 / 3) -> (gen rows [B, S*S], saved)."""
         cx, B, L, C = self.cx, x_rows.shape[0], self.L, self.C
-        x0 = x_rows.view(B, L, L, C)
-        sv = dict(B=B, lvl={}, pct=float(percentage))
-        old, sv["d1"] = self.c_dens[1].forward(x0, B, L, L)
-        cur, res, ch = x0, L, C
+        res = L if self.up else self.S
+        x0 = x_rows.view(B, res, res, self.cin0)
+        sv = dict(B=B, lvl={}, pct=float(percentage), head=[])
+        cur, ch = x0, self.cin0
+        for rb in self.head:
+            cur, q = self._rb_fwd(rb, cur, B, res)
+            sv["head"].append(q)
+            ch = cur.shape[-1]
+        old, sv["d1"] = self.c_dens[1].forward(cur, B, res, res)
         for j in range(1, self.stages + 1):
-            up = self._up2(cur, B, res, res, ch)
-            res *= 2
-            inp, rbs_sv = up, []
-            for a, b, s in self.blocks[j]:
-                ya, sa = a.forward(inp, B, res, res)
-                yap = self._pn(ya)
-                yb, sb = b.forward(yap, B, res, res)
-                ys, ss = s.forward(inp, B, res, res)
-                r = cx.buf(yb.shape)
-                cx.call("add_act_fwd", yb, ys, r, r.numel(), capi.ACT_RELU, cx.st)
-                rp = self._pn(r)
-                rbs_sv.append(dict(sa=sa, sb=sb, ss=ss, ya=ya, r=r))
-                inp = rp
+            if self.up:
+                inp = self._up2(cur, B, res, res, ch)
+                res *= 2
+            else:
+                inp = cur
+            rbs_sv = []
+            for rb in self.blocks[j]:
+                inp, q = self._rb_fwd(rb, inp, B, res)
+                rbs_sv.append(q)
             cur, ch = inp, inp.shape[-1]
             dens, sd = self.c_dens[2 ** j].forward(cur, B, res, res)
             if self.bicubic:
-                key = (L, res)
-                if key not in self.bic_plans:
-                    self.bic_plans[key] = capi.BicubicPlan(cx.h, L, L, res, res)
                 out = cx.buf(dens.shape)
-                capi.dens_residual(cx.h, dens, x0, capi.F32, C, 0, 2, self.bic_plans[key], B, res, res, L, L, out, cx.st)
+                if self.up:
+                    key = (L, res)
+                    if key not in self.bic_plans:
+                        self.bic_plans[key] = capi.BicubicPlan(cx.h, L, L, res, res)
+                    capi.dens_residual(cx.h, dens, x0, capi.F32, C, 0, 2, self.bic_plans[key], B, res, res, L, L, out, cx.st)
+                else:
+                    capi.dens_residual(cx.h, dens, x0, capi.F32, self.cin0, 0, 0, None, B, res, res, res, res, out, cx.st)
                 dens = out
-            oldu = self._up2(old, B, res // 2, res // 2, 1)
+            oldu = self._up2(old, B, res // 2, res // 2, 1) if self.up else old
             t = float(min(max(percentage - (j - 1), 0.0), 1.0))
             blend = cx.buf(dens.shape)
             cx.call("lerp", blend, oldu, dens, t, blend.numel(), cx.st)
@@ -497,28 +577,23 @@ class GrowingGen:
             d_cur = cx.buf(lv["sd"]["x"].shape)
             self.c_dens[2 ** j].backward(lv["sd"], d_dens, dx=d_cur)
             if d_up_next is not None:
-                cx.call("axpy", d_cur, self._up2_bwd(d_up_next, B, res, res, ch), 1.0, d_cur.numel(), cx.st)
+                cx.call("axpy", d_cur, self._up2_bwd(d_up_next, B, res, res, ch) if self.up else d_up_next, 1.0, d_cur.numel(),
+                        cx.st)
             d = d_cur
             rbs = self.blocks[j]
             for i in range(len(rbs) - 1, -1, -1):
-                a, b, s = rbs[i]
-                q = lv["rbs"][i]
-                first_of_net = (j == 1 and i == 0)  # its input is the upsampled DATA: no input gradient needed
-                d_r = cx.buf(q["r"].shape)
-                cx.call("pixel_norm_bwd", q["r"], d, d_r, q["r"].numel() // q["r"].shape[-1], q["r"].shape[-1], cx.st)
-                d_sum = cx.buf(q["r"].shape)
-                cx.call("act_bwd", q["r"], d_r, d_sum, d_sum.numel(), capi.ACT_RELU, cx.st)
-                d_yap = cx.buf(q["ya"].shape)
-                b.backward(q["sb"], d_sum, dx=d_yap)
-                d_inp = None if first_of_net else cx.buf(q["sa"]["x"].shape)
-                s.backward(q["ss"], d_sum, dx=d_inp)
-                d_ya = cx.buf(q["ya"].shape)
-                cx.call("pixel_norm_bwd", q["ya"], d_yap, d_ya, q["ya"].numel() // q["ya"].shape[-1], q["ya"].shape[-1], cx.st)
-                a.backward(q["sa"], d_ya, dx=d_inp, accumulate=True)
-                d = d_inp
+                # the first block of the first network reads the upsampled DATA: no input gradient needed
+                d = self._rb_bwd(rbs[i], lv["rbs"][i], d, not (self.up and j == 1 and i == 0))
             d_up_next = d
-            d_old = self._up2_bwd(d_oldu, B, res // 2, res // 2, 1)
-        self.c_dens[1].backward(sv["d1"], d_old)
+            d_old = self._up2_bwd(d_oldu, B, res // 2, res // 2, 1) if self.up else d_oldu
+        if not self.head:
+            self.c_dens[1].backward(sv["d1"], d_old)
+            return
+        d = cx.buf(sv["d1"]["x"].shape)
+        self.c_dens[1].backward(sv["d1"], d_old, dx=d)
+        cx.call("axpy", d, d_up_next, 1.0, d.numel(), cx.st)
+        for i in range(len(self.head) - 1, -1, -1):
+            d = self._rb_bwd(self.head[i], sv["head"][i], d, i > 0)
 
     def grads(self):
         ps = self.ps
@@ -529,14 +604,24 @@ class GrowingGen:
 class Trainer8x:
     """Loop body of the 8x progressive-growing training (GAN/multipassGAN-8x.py:1898-2075, spatial part): one critic step
     (WGAN-GP, :1111-1143) and one generator step (g_loss_d + lambda * l1, :1117,1145) with the optimizers of growing stage z
-    (:1304-1362) and the generator weight EMA. Temporal discriminator terms (lambda_t) and loss scaling are not built."""
+    (:1304-1362) and the generator weight EMA. Temporal discriminator terms (lambda_t) and loss scaling are not built.
+    upsampling_mode 2 + firstNNArch = the first network (GAN/example_run_training.py:4): x rows [B, L*L*C], y rows
+    [B, S*S].  upsampling_mode 1 / 3 = the refinement networks (:7): y rows [B, S*S*2] carry (target density, first-pass
+    density) per pixel; the generator input is concat(first-pass density, nearest-resized low-res fields) (:1042-1044), the
+    target is channel 0 (:1061-1062) and the critic's gradient penalty reduces over image rows (GrowingDisc)."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
-                 learning_rate=1e-4, adam_beta1=0.0, adam_beta2=0.99, lambda_l1=1.0, values=None, seed=1, device=0):
+                 learning_rate=1e-4, adam_beta1=0.0, adam_beta2=0.99, lambda_l1=1.0, values=None, seed=1, device=0,
+                 upsampling_mode=2, first_nn_arch=None):
         self.cx = cx = _Ctx(device)
-        self.gen = GrowingGen(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, batch, True, values, seed, device, cx=cx)
-        self.disc = GrowingDisc(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, True, batch, values, seed, device,
-                                cx=cx)
+        self.refine = int(upsampling_mode) != 2
+        first = (not self.refine) if first_nn_arch is None else bool(first_nn_arch)
+        if first == self.refine:
+            raise ValueError("built: firstNNArch 1 with upsamplingMode 2, firstNNArch 0 with upsamplingMode 1 / 3")
+        self.gen = GrowingGen(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, batch, True, values, seed, device,
+                              cx=cx, upsampling_mode=upsampling_mode)
+        self.disc = GrowingDisc(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, first, batch, values, seed,
+                                device, cx=cx, upsampling_mode=upsampling_mode)
         n = self.gen.stages
         self.opt_g = StagedAdam(cx, self.gen.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
         self.opt_d = StagedAdam(cx, self.disc.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
@@ -546,12 +631,28 @@ class Trainer8x:
         self.losses = torch.zeros(4, dtype=torch.float64, device=cx.device)
         self.save_no = 0
 
+    def _inputs(self, x_rows, y_rows):
+        """(generator input rows, target rows) of the training graph (:1040-1062)."""
+        if not self.refine:
+            return x_rows, y_rows
+        cx, g = self.cx, self.gen
+        B, S, L, C = x_rows.shape[0], g.S, g.L, g.C
+        if y_rows.shape[1] != S * S * 2:
+            raise ValueError("refinement networks train on target rows of S*S*2 values (target, first-pass density)")
+        x_in = cx.buf((B, S * S * (C + 1)))
+        capi.pack_channels(cx.h, [(y_rows, capi.F32, 2, 1, 1, 1, 1), (x_rows, capi.F32, C, 0, C, g.u, g.u)], x_in, capi.F32, C + 1,
+                           B, S, S, cx.st)
+        y_in = cx.buf((B, S * S))
+        cx.call("take_channel", y_rows, y_in, B * S * S, 2, 0, 0, cx.st)
+        return x_in, y_in
+
     def disc_step(self, x_rows, y_rows, percentage, z, lerp_factor):
         cx = self.cx
         cx.st = torch.cuda.current_stream(cx.device).cuda_stream
         self.gen.refresh()
-        gen_y, _ = self.gen.forward(x_rows, percentage)
-        out = self.disc.critic_step(x_rows, y_rows, gen_y, percentage, lerp_factor)
+        x_in, y_in = self._inputs(x_rows, y_rows)
+        gen_y, _ = self.gen.forward(x_in, percentage)
+        out = self.disc.critic_step(x_rows, y_in, gen_y, percentage, lerp_factor)
         self.opt_d.step(z)
         return out
 
@@ -562,13 +663,14 @@ class Trainer8x:
         d.refresh()
         g.ps.gw.zero_()
         self.losses.zero_()
-        gen_y, gsv = g.forward(x_rows, percentage)
+        x_in, y_in = self._inputs(x_rows, y_rows)
+        gen_y, gsv = g.forward(x_in, percentage)
         logits, dsv = d.forward(x_rows, gen_y, percentage)
         dl = cx.buf(logits.shape)
         cx.call("mean_pow", logits, -1.0, 1, self.losses[0:1], dl, logits.numel(), 0, cx.st)      # g_loss_d = mean(-gen) :1117
         dxin = d.backward(dsv, dl, need_input_grad=True, param_grads=False)
         dgen = cx.buf(gen_y.shape)
-        cx.call("l1_mean", y_rows, gen_y, self.k_l1, self.losses[1:2], dgen, gen_y.numel(), 0, cx.st)  # lambda * mean|y - G| :1099,1145
+        cx.call("l1_mean", y_in, gen_y, self.k_l1, self.losses[1:2], dgen, gen_y.numel(), 0, cx.st)  # lambda * mean|y - G| :1099,1145
         cx.call("take_channel", dxin, dgen, gen_y.numel(), 2, 1, 1, cx.st)
         g.backward(gsv, dgen)
         cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
@@ -582,6 +684,8 @@ class Trainer8x:
         (The reference takes the stage's tile size from 2 ** ceil(percentage); its schedule runs one stage ahead of its data
         (schedule8x doc), so the size is taken from the rows themselves here.)"""
         cx, S, B = self.cx, self.gen.S, y_rows.shape[0]
+        if self.refine:
+            return y_rows                 # upsampling_mode 1 / 3: the data is at the full resolution from the start (:1061)
         cur = int(round(math.sqrt(y_rows.shape[1])))
         if cur * cur != y_rows.shape[1] or S % cur:
             raise ValueError("target rows of %d values are not square tiles dividing %d" % (y_rows.shape[1], S))

@@ -22,13 +22,14 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "growdisc.npz")
 
 def _setup(tag, batch=2):
     c = json.loads(str(GOLD[tag + "_cfg"]))
-    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], c["filterSize"], c["first_nn_arch"])
+    mode = c.get("upsampling_mode", 2)
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], c["filterSize"], c["first_nn_arch"], upsampling_mode=mode)
     store = og.VarStore(seed=c["seed"])
     x = torch.from_numpy(GOLD[tag + "_x"]).double()
     y = torch.from_numpy(GOLD[tag + "_y"]).double()
     o8.growing_disc(y, x, 1.0, og.Context(store, torch.float64), cfg)  # creates every variable
     d = t8.GrowingDisc(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], c["filterSize"], c["first_nn_arch"], batch=batch,
-                       values=store.values)
+                       values=store.values, upsampling_mode=mode)
     assert {n for n, *_ in d.ps.specs} == set(store.values)
     return c, cfg, store, x, y, d
 
@@ -38,7 +39,7 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
 
 
-@pytest.mark.parametrize("tag", ["gd_first", "gd_plain"])
+@pytest.mark.parametrize("tag", ["gd_first", "gd_plain", "gd_second"])
 def test_growing_disc_forward_matches_the_reference_vectors(tag):
     c, cfg, store, x, y, d = _setup(tag)
     dev = d.cx.device
@@ -50,7 +51,8 @@ def test_growing_disc_forward_matches_the_reference_vectors(tag):
         assert np.abs(logits.cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (tag, pct)
 
 
-@pytest.mark.parametrize("tag,pct", [("gd_first", 2.4), ("gd_first", 0.7), ("gd_plain", 1.5), ("gd_plain", 2.0)])
+@pytest.mark.parametrize("tag,pct", [("gd_first", 2.4), ("gd_first", 0.7), ("gd_plain", 1.5), ("gd_plain", 2.0),
+                                     ("gd_second", 2.4), ("gd_second", 0.7)])
 def test_wgan_gp_critic_loss_and_gradients_match_double_backward(tag, pct):
     c, cfg, store, x, y, d = _setup(tag)
     dev = d.cx.device
@@ -60,7 +62,9 @@ def test_wgan_gp_critic_loss_and_gradients_match_double_backward(tag, pct):
     ctx = ot.TrainContext(store, torch.float64)
     disc, _ = o8.growing_disc(y, x, pct, ctx, cfg)
     gen, _ = o8.growing_disc(g, x, pct, ctx, cfg)
-    L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, pct, ctx, cfg)[0], y, g, lf)
+    # refinement networks (gd_second): one gradient norm per (sample, image column), see oracle.wgan_gp_losses
+    L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, pct, ctx, cfg)[0], y, g, lf,
+                          image_side=None if cfg.upsampling_mode == 2 else cfg.tileSizeHigh)
     names = [n for n, t in ctx.leaves.items() if t.requires_grad]
     grads = torch.autograd.grad(L["disc_loss"], [ctx.leaves[n] for n in names], allow_unused=True)
     want = {n: (gr.numpy() if gr is not None else np.zeros(tuple(ctx.leaves[n].shape))) for n, gr in zip(names, grads)}
@@ -80,9 +84,10 @@ def test_wgan_gp_critic_loss_and_gradients_match_double_backward(tag, pct):
     assert worst > 0.0
 
 
-def test_critic_input_gradient_for_the_generator_step():
+@pytest.mark.parametrize("tag", ["gd_first", "gd_second"])
+def test_critic_input_gradient_for_the_generator_step(tag):
     """g_loss_d = mean(-D(G(x))) (:1117): the gradient the generator receives through the critic."""
-    c, cfg, store, x, y, d = _setup("gd_first")
+    c, cfg, store, x, y, d = _setup(tag)
     dev = d.cx.device
     pct = 1.6
     yy = y.clone().requires_grad_(True)
@@ -138,25 +143,27 @@ def test_staged_adam_and_weight_ema():
     # (checked implicitly above: the oracle only updated `sel`)
 
 
-def _gen_setup():
-    c = json.loads(str(GOLD["gg_first_cfg"]))
-    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+def _gen_setup(tag="gg_first"):
+    c = json.loads(str(GOLD[tag + "_cfg"]))
+    mode, fs = c.get("upsampling_mode", 2), c.get("filterSize", 3)
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], fs, c.get("first_nn_arch", True), upsampling_mode=mode)
     store = og.VarStore(seed=c["seed"])
-    x = torch.from_numpy(GOLD["gg_first_x"]).double()
+    x = torch.from_numpy(GOLD[tag + "_x"]).double()
     o8.growing_gen_train(x, 1.0, og.Context(store, torch.float64), cfg)
-    g = t8.GrowingGen(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, batch=2, values=store.values)
+    g = t8.GrowingGen(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], fs, batch=2, values=store.values, upsampling_mode=mode)
     assert {n for n, *_ in g.ps.specs} == set(store.values)
     return c, cfg, store, x, g
 
 
-def test_growing_gen_training_forward_matches_the_reference_vectors():
-    c, cfg, store, x, g = _gen_setup()
+@pytest.mark.parametrize("tag", ["gg_first", "gg_second"])
+def test_growing_gen_training_forward_matches_the_reference_vectors(tag):
+    c, cfg, store, x, g = _gen_setup(tag)
     dev = g.cx.device
     g.cx.st = torch.cuda.current_stream(dev).cuda_stream
     g.refresh()
     for k, pct in enumerate(c["percentages"]):
         out, _ = g.forward(x.float().to(dev), pct)
-        ref = GOLD["gg_first_p%d_out" % k]
+        ref = GOLD["%s_p%d_out" % (tag, k)]
         assert np.abs(out.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), pct
 
 
@@ -170,12 +177,12 @@ def _gen_autograd(store, x, pct, cfg, dtype):
                         for n, gr in zip(names, grads)}
 
 
-@pytest.mark.parametrize("pct", [0.6, 1.7, 2.5])
-def test_growing_gen_backward_matches_autograd(pct):
+@pytest.mark.parametrize("tag,pct", [("gg_first", 0.6), ("gg_first", 1.7), ("gg_first", 2.5), ("gg_second", 0.6), ("gg_second", 2.5)])
+def test_growing_gen_backward_matches_autograd(tag, pct):
     """Parameter gradients of the training-mode generator (30 convs, 20 pixel norms, ReLU kinks) against fp64 autograd. The
     earliest layers see the rounding of everything above them (a ReLU input near zero may change sign between fp32 and fp64),
     so each variable is held to 3e-3 or to 4x the distance of torch's OWN fp32 autograd from the fp64 result."""
-    c, cfg, store, x, g = _gen_setup()
+    c, cfg, store, x, g = _gen_setup(tag)
     dev = g.cx.device
     names, wgt, want = _gen_autograd(store, x, pct, cfg, torch.float64)
     _, _, want32 = _gen_autograd(store, x, pct, cfg, torch.float32)
@@ -200,22 +207,31 @@ def test_growing_gen_backward_matches_autograd(pct):
     assert live > 0 and tight == easy, (tight, easy, live)
 
 
-def test_trainer8x_critic_and_generator_steps_track_the_oracle():
+@pytest.mark.parametrize("tag", ["gg_first", "gg_second"])
+def test_trainer8x_critic_and_generator_steps_track_the_oracle(tag):
     """Two loop bodies (critic step then generator step, GAN/multipassGAN-8x.py:1898-2075 without the temporal terms) at two
-    growing stages: losses and every updated variable against the fp64 oracle with the same staged Adam."""
-    c = json.loads(str(GOLD["gg_first_cfg"]))
-    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, True)
+    growing stages: losses and every updated variable against the fp64 oracle with the same staged Adam.  gg_first = the first
+    network's graph, gg_second = the refinement network's (x_in / y_in wiring, no resampling, row-wise gradient penalty)."""
+    c = json.loads(str(GOLD[tag + "_cfg"]))
+    mode, fs = c.get("upsampling_mode", 2), c.get("filterSize", 3)
+    first = c.get("first_nn_arch", True)
+    cfg = o8.Cfg8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], fs, first, upsampling_mode=mode)
+    S = cfg.tileSizeHigh
     rng = np.random.default_rng(3)
-    x = torch.from_numpy(GOLD["gg_first_x"]).double()
-    y = torch.from_numpy(rng.random((2, cfg.tileSizeHigh ** 2))).double()
+    x = torch.from_numpy(rng.random((2, cfg.tileSizeLow ** 2 * cfg.n_inputChannels))).double()
+    y = torch.from_numpy(rng.random((2, S * S * (1 if mode == 2 else 2)))).double()
+    x_in, y_in = (x, y) if mode == 2 else o8.refine_input(x, y, cfg)
+    side = None if mode == 2 else S
     store = og.VarStore(seed=7)
-    o8.growing_gen_train(x, 1.0, og.Context(store, torch.float64), cfg)
-    o8.growing_disc(y, x, 1.0, og.Context(store, torch.float64), cfg)
-    tr = t8.Trainer8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], 3, batch=2, learning_rate=1e-3, values=store.values)
+    o8.growing_gen_train(x_in, 1.0, og.Context(store, torch.float64), cfg)
+    o8.growing_disc(y_in, x, 1.0, og.Context(store, torch.float64), cfg)
+    tr = t8.Trainer8x(c["L"], c["u"], c["C"], c["start_fms"], c["max_fms"], fs, batch=2, learning_rate=1e-3, values=store.values,
+                      upsampling_mode=mode)
     dev = tr.cx.device
     ref_vals = {k: np.array(v, np.float64) for k, v in store.values.items()}
     g_names = sorted(k for k in ref_vals if k.startswith("generator/"))
     d_names = sorted(k for k in ref_vals if k.startswith("spatial-disc/"))
+    assert {n for n, *_ in tr.gen.ps.specs} == set(g_names) and {n for n, *_ in tr.disc.ps.specs} == set(d_names)
     og_opt = [ot.Adam(1e-3, 0.0, 0.99) for _ in range(3)]
     od_opt = [ot.Adam(1e-3, 0.0, 0.99) for _ in range(3)]
     lf = torch.tensor([[0.35], [0.6]], dtype=torch.float64)
@@ -237,18 +253,18 @@ def test_trainer8x_critic_and_generator_steps_track_the_oracle():
     for z, pct in ((0, 0.7), (1, 1.4)):
         # critic step
         ctx = oracle_ctx()
-        gen_y = o8.growing_gen_train(x, pct, ctx, cfg).detach()
-        disc, _ = o8.growing_disc(y, x, pct, ctx, cfg)
+        gen_y = o8.growing_gen_train(x_in, pct, ctx, cfg).detach()
+        disc, _ = o8.growing_disc(y_in, x, pct, ctx, cfg)
         gen, _ = o8.growing_disc(gen_y, x, pct, ctx, cfg)
-        L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, pct, ctx, cfg)[0], y, gen_y, lf)
+        L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc(t, x, pct, ctx, cfg)[0], y_in, gen_y, lf, image_side=side)
         got = tr.disc_step(xf, yf, pct, z, lf).cpu().numpy()
         assert abs(got[0] - float(L["disc_loss"].detach())) < 5e-4 * max(1.0, abs(float(L["disc_loss"].detach())))
         apply(od_opt[z], o8.stage_variables(d_names, z), L["disc_loss"], ctx)
         # generator step
         ctx = oracle_ctx()
-        gen_y = o8.growing_gen_train(x, pct, ctx, cfg)
+        gen_y = o8.growing_gen_train(x_in, pct, ctx, cfg)
         gen, _ = o8.growing_disc(gen_y, x, pct, ctx, cfg)
-        g_loss = (-gen).mean() + 1.0 * (y - gen_y).abs().mean()
+        g_loss = (-gen).mean() + 1.0 * (y_in - gen_y).abs().mean()
         gl = tr.gen_step(xf, yf, pct, z).cpu().numpy()
         assert abs(gl[0] + gl[1] - float(g_loss.detach())) < 5e-4 * max(1.0, abs(float(g_loss.detach())))
         apply(og_opt[z], o8.stage_variables(g_names, z), g_loss, ctx)
@@ -334,3 +350,28 @@ def test_trainer8x_target_rows_are_the_nearest_resize():
     assert tr.target_rows(full) is full
     with pytest.raises(ValueError):
         tr.target_rows(torch.rand((2, 60), device=dev))
+
+
+def test_trainer8x_refinement_network_training_loop():
+    """The second network's shipped schedule (GAN/example_run_training.py:7: upsamplingMode 1, stageIter 1): the data is at 8x
+    from the first iteration, every iteration uses the last stage's optimizers, the blend reaches 2 after the first one."""
+    from mpgan_b200 import schedule8x as S8
+    np.random.seed(11)
+    tr = t8.Trainer8x(2, 8, 4, 32, 32, 5, batch=2, learning_rate=1e-3, upsampling_mode=1)
+    dev = tr.cx.device
+    g = torch.Generator(device="cpu").manual_seed(2)
+    seen = []
+
+    def batches(upres):
+        seen.append(upres)
+        return torch.rand((2, 2 * 2 * 4), generator=g).to(dev), torch.rand((2, 16 * 16 * 2), generator=g).to(dev)
+
+    v0 = tr.values()
+    sch = S8.GrowthSchedule(stageIter=1, decayIter=2, upRes=8, upsampling_mode=1)
+    hist = tr.train(batches, sch, add_adj_idcs=False, log_interval=1)
+    assert len(hist) == 8 and seen == [8] * 16 and all(np.isfinite(h[1:]).all() for h in hist)
+    assert [st["t"] for st in tr.opt_g.state] == [0, 0, 8] and [st["t"] for st in tr.opt_d.state] == [0, 0, 8]
+    v1 = tr.values()
+    assert all(not np.array_equal(v0[n], v1[n]) for n in v0 if n.endswith("/weight") and "d_cfromDensity1" not in n)
+    with pytest.raises(ValueError):
+        tr.disc_step(torch.rand((2, 16), device=dev), torch.rand((2, 256), device=dev), 2.0, 2, torch.rand(2, 1))
