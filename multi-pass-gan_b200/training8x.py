@@ -601,6 +601,21 @@ class GrowingGen:
         return {name: host[off:off + n].reshape(shape).copy() for name, shape, off, n, _ in ps.specs}
 
 
+class StageBatches:
+    """`batches(currentUpres)` for Trainer8x.train out of one tilesampler.TileSampler per data resolution. The reference
+    builds a new TileCreator with `upres=currentUpres` and re-loads `density_low_<currentUpres>_%04d.uni` as the targets at
+    every growing event (GAN/multipassGAN-8x.py:1916-1960); here the frames of every stage stay resident on the device and
+    the growing event only switches the sampler. getinput (:1497-1536) = selectRandomTiles + the reshape to rows."""
+
+    def __init__(self, samplers, batch_size, augment=False):
+        self.samplers, self.batch_size, self.augment = dict(samplers), int(batch_size), bool(augment)
+
+    def __call__(self, currentUpres):
+        if currentUpres not in self.samplers:
+            raise KeyError("no training data at %dx (have %s)" % (currentUpres, sorted(self.samplers)))
+        return self.samplers[currentUpres].batch_rows(self.batch_size, augment=self.augment)
+
+
 class Trainer8x:
     """Loop body of the 8x progressive-growing training (GAN/multipassGAN-8x.py:1898-2075, spatial part): one critic step
     (WGAN-GP, :1111-1143) and one generator step (g_loss_d + lambda * l1, :1117,1145) with the optimizers of growing stage z

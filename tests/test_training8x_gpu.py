@@ -377,3 +377,27 @@ def test_trainer8x_refinement_network_training_loop():
         assert not np.array_equal(v0[n], v1[n]), n
     with pytest.raises(ValueError):
         tr.disc_step(torch.rand((2, 16), device=dev), torch.rand((2, 256), device=dev), 2.0, 2, torch.rand(2, 1))
+
+
+def test_stage_batches_feed_the_loop_from_device_resident_tile_samplers():
+    """StageBatches: one TileSampler per data resolution (the reference re-creates its TileCreator at every growing event,
+    :1916-1960), tiles gathered on the device, target tiles nearest-resized to the full size inside the loop."""
+    import random
+    from mpgan_b200 import schedule8x as S8
+    from mpgan_b200.tilesampler import TileSampler
+    np.random.seed(5)
+    tr = _loop_trainer()
+    dev = tr.cx.device
+    rng = np.random.default_rng(9)
+    low = rng.random((6, 1, 8, 8, 6), dtype=np.float32) + 0.1
+    samplers = {}
+    for u in (2, 4, 8):
+        samplers[u] = TileSampler(4, u, densityMinimum=0.02, device=dev, rng=random.Random(u))
+        samplers[u].add_data(low, rng.random((6, 1, 8 * u, 8 * u, 1), dtype=np.float32))
+    sb = t8.StageBatches(samplers, 2)
+    xs, ys = sb(4)
+    assert xs.shape == (2, 4 * 4 * 6) and ys.shape == (2, 16 * 16) and xs.device == dev
+    hist = tr.train(sb, S8.GrowthSchedule(stageIter=1, decayIter=1), log_interval=1)
+    assert len(hist) == 7 and all(np.isfinite(h[1:]).all() for h in hist)
+    with pytest.raises(KeyError):
+        t8.StageBatches({2: samplers[2]}, 2)(4)
