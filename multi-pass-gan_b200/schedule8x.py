@@ -12,6 +12,8 @@
 Reference behaviour kept as is (it looks unintended, the trainer reproduces it instead of repairing it):
 the blend counter starts one stage ahead (`interpol_c += stageIter`, :1893), so `percentage` already runs from 1 to 2
 while the data of the first stage (currentUpres 2) is trained and ends at 3 one stage before the data reaches 8x.
+For the refinement networks (upsampling_mode 1 / 3) there are no growing events, so the counter stops after the first blend
+phase and `percentage` stays at 2: under the reference's own schedule their 8x stage is never blended in.
 """
 import math
 from collections import namedtuple
