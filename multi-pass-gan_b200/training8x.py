@@ -731,15 +731,10 @@ class Trainer8x:
 
         def batch(upres):
             xs, ys = batches(upres)
-            if zero_density and not min(np.random.randint(0, 20), 1):            # :1527-1533 on the device rows
-                C, scale = self.gen.C, 1.0 + np.random.rand() * 1.5
-                xs = xs.clone()
-                xv = xs.view(xs.shape[0], -1, C)
-                xv[..., 0:1] = 0
-                if add_adj_idcs and C >= 6:
-                    xv[..., 4:6] = 0
-                xv[..., 1:4] *= scale
-                ys = torch.zeros_like(ys)
+            if zero_density:                                                      # :1527-1533 on (copies of) the device rows
+                xz, yz = xs.clone(), ys.clone()
+                if schedule8x.zero_density_batch(xz.view(xz.shape[0], -1, self.gen.C), yz, add_adj_idcs and self.gen.C >= 6):
+                    xs, ys = xz, yz
             return xs, self.target_rows(ys)
 
         for st in schedule:
