@@ -406,3 +406,37 @@ def test_stage_batches_feed_the_loop_from_device_resident_tile_samplers():
     assert len(hist) == 7 and all(np.isfinite(h[1:]).all() for h in hist)
     with pytest.raises(KeyError):
         t8.StageBatches({2: samplers[2]}, 2)(4)
+
+
+def test_trained_checkpoint_applies_through_the_out_pipeline_graph(tmp_path):
+    """train -> model_ema_%04d.ckpt -> the restore rule of multipassGAN-out.py (:367-386, tfckpt.load_generator_weights) -> the
+    apply engine: at percentage 3 every stage is fully blended in, so the training-mode generator (per-stage density outputs,
+    lerp) and the apply graph (`output=True`, last stage only) are the same function of the same moving-average weights."""
+    from mpgan_b200 import engine, graph as G, networks as N, pipeline as P, schedule8x as S8, tfckpt
+    np.random.seed(1)
+    tr = _loop_trainer()
+    dev = tr.cx.device
+    batches, _ = _batches(dev)
+    d = str(tmp_path / "test_0003")
+    tr.train(batches, S8.GrowthSchedule(stageIter=1, decayIter=1), save_dir=d, saveInterval=7, zero_density=False)
+    no = tr.save(d)
+    spec = P.NetSpec(use_res_net=True, add_adj_idcs=True, startFms=32, maxFms=32, filterSize=3, first_nn_arch=True)
+    G.reset_default_graph()
+    out = P.build_out_graph(1, spec, N.config_out(4, upRes=8))
+    names = list(G.get_default_graph().variables)           # gen_1/generator/... : the names the graph built from the flags needs
+    w = tfckpt.load_generator_weights(os.path.join(d, "model_ema_%04d.ckpt" % no), sorted(names), "gen_1")
+    sh = tr.ema.export()
+    assert all(np.array_equal(w[n], sh[n[len("gen_1/"):]]) for n in w) and len(w) >= 60
+    x = torch.rand((2, 4 * 4 * 6), device=dev)
+    net = engine.CompiledNet(out, w, 2, precision="fp32")
+    applied = net.run({"x": x}).float().cpu().numpy()
+    net.close()
+    # the trainer's own forward on the moving averages
+    keep = tr.gen.ps.v.clone()
+    tr.gen.ps.v.copy_(tr.ema.shadow)
+    tr.cx.st = torch.cuda.current_stream(dev).cuda_stream
+    tr.gen.refresh()
+    trained, _ = tr.gen.forward(x, 3.0)
+    tr.gen.ps.v.copy_(keep)
+    ref = trained.cpu().numpy()
+    assert np.abs(applied - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
