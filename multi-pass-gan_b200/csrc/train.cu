@@ -146,10 +146,23 @@ struct WgradArgs {
   float* dw;
   int n, h, w_, cin, cout, k, stride, pad, oh, ow, in_up, px_per_split;
 };
+// TCI = input channels per thread (1, 2, 4): block tile 32*TCI ci x 64 co, thread tile TCI ci x 8 co. The first version
+// (1 x 8 with the 8 output channels contiguous) was shared-memory bound: 8 FMAs per 36 bytes of LDS and a 2-way bank
+// conflict on both 128-bit loads (ncu: 16.8 M conflicts, 26 % issue utilisation, 177 us for 128->256 on 8x8 maps). Now a
+// thread's channels are {4 cg .. 4 cg + 3} and {32 + 4 cg ..}: a quarter warp reads 128 contiguous bytes, and the wide layers
+// do 32 FMAs per three 128-bit loads.
+// PH = pixel phases (narrow inputs, cin <= 16): the 32 thread rows hold 32/PH channels x PH interleaved pixel subsets instead
+// of 32 channels (the 2-channel first layer of the discriminator used 2 of 32 rows); the phases are summed through shared
+// memory before the atomics.
+template <int TCI, int PH>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
-  __shared__ float xs[32][33];
+  static_assert(PH == 1 || TCI == 1, "pixel phases only with one channel per thread");
+  constexpr int CIB = 32 * TCI / PH;  // input channels per block tile
+  constexpr int XST = CIB + 4;        // row stride of xs: keeps 128-bit rows aligned
+  __shared__ __align__(16) float xs[32 * XST];
   __shared__ __align__(16) float ys[32][64];
-  const int ci_tiles = (a.cin + 31) / 32, co_tiles = (a.cout + 63) / 64;
+  __shared__ long long xbase[32];  // element offset of the tap's input pixel for each of the 32 staged output pixels, -1 = zero
+  const int ci_tiles = (a.cin + CIB - 1) / CIB, co_tiles = (a.cout + 63) / 64;
   int b = blockIdx.x;
   const int cot = b % co_tiles;
   b /= co_tiles;
@@ -157,29 +170,42 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
   const int tap = b / ci_tiles;
   const int ky = tap / a.k, kx = tap % a.k;
   const int tid = threadIdx.x;
-  const int ci_l = tid >> 3, cg = tid & 7;
+  const int row = tid >> 3, cg = tid & 7;
+  const int ci0 = PH == 1 ? row * TCI : row % CIB;  // first channel of this thread inside the block tile
+  const int phase = PH == 1 ? 0 : row / CIB;
   const long long npix = static_cast<long long>(a.n) * a.oh * a.ow;
   const long long p_begin = static_cast<long long>(blockIdx.y) * a.px_per_split;
   long long p_end = p_begin + a.px_per_split;
   if (p_end > npix) p_end = npix;
   const int sh = a.h / a.in_up, sw = a.w_ / a.in_up;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[TCI][8];
+#pragma unroll
+  for (int t = 0; t < TCI; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.0f;
   for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
     __syncthreads();
-    for (int e = tid; e < 32 * 32; e += 256) {
-      const int pl = e >> 5, c = e & 31;
-      const long long p = p0 + pl;
-      float v = 0.0f;
-      if (p < p_end && cit * 32 + c < a.cin) {
-        const int ox = static_cast<int>(p % a.ow);
-        const long long r = p / a.ow;
-        const int oy = static_cast<int>(r % a.oh);
-        const int n = static_cast<int>(r / a.oh);
+    // the pixel -> (n, oy, ox) decomposition once per staged pixel (32 threads), not once per element
+    if (tid < 32) {
+      const long long p = p0 + tid;
+      long long base = -1;
+      if (p < p_end) {
+        const unsigned pu = static_cast<unsigned>(p);  // n * oh * ow < 2^31 (checked by the host wrapper)
+        const int ox = static_cast<int>(pu % static_cast<unsigned>(a.ow));
+        const unsigned r = pu / static_cast<unsigned>(a.ow);
+        const int oy = static_cast<int>(r % static_cast<unsigned>(a.oh));
+        const int n = static_cast<int>(r / static_cast<unsigned>(a.oh));
         const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
         if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w_)
-          v = a.in[((static_cast<size_t>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + cit * 32 + c];
+          base = ((static_cast<long long>(n) * sh + iy / a.in_up) * sw + ix / a.in_up) * a.cin + cit * CIB;
       }
-      xs[pl][c] = v;
+      xbase[tid] = base;
+    }
+    __syncthreads();
+    for (int e = tid; e < 32 * CIB; e += 256) {
+      const int pl = e / CIB, c = e % CIB;
+      const long long base = xbase[pl];
+      xs[pl * XST + c] = (base >= 0 && cit * CIB + c < a.cin) ? a.in[base + c] : 0.0f;
     }
     for (int e = tid; e < 32 * 64; e += 256) {
       const int pl = e >> 6, o = e & 63;
@@ -190,28 +216,74 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     }
     __syncthreads();
 #pragma unroll 8
-    for (int pl = 0; pl < 32; ++pl) {
-      const float xv = xs[pl][ci_l];
-      const float4 y0 = *reinterpret_cast<const float4*>(&ys[pl][cg * 8]);
-      const float4 y1 = *reinterpret_cast<const float4*>(&ys[pl][cg * 8 + 4]);
-      acc[0] = fmaf(xv, y0.x, acc[0]);
-      acc[1] = fmaf(xv, y0.y, acc[1]);
-      acc[2] = fmaf(xv, y0.z, acc[2]);
-      acc[3] = fmaf(xv, y0.w, acc[3]);
-      acc[4] = fmaf(xv, y1.x, acc[4]);
-      acc[5] = fmaf(xv, y1.y, acc[5]);
-      acc[6] = fmaf(xv, y1.z, acc[6]);
-      acc[7] = fmaf(xv, y1.w, acc[7]);
-    }
-  }
-  const int ci = cit * 32 + ci_l;
-  if (ci < a.cin) {
+    for (int pl = phase; pl < 32; pl += PH) {
+      float xv[TCI];
+      if (TCI == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&xs[pl * XST + ci0]);
+        xv[0] = q.x, xv[1 % TCI] = q.y, xv[2 % TCI] = q.z, xv[3 % TCI] = q.w;
+      } else if (TCI == 2) {
+        const float2 q = *reinterpret_cast<const float2*>(&xs[pl * XST + ci0]);
+        xv[0] = q.x, xv[1 % TCI] = q.y;
+      } else {
+        xv[0] = xs[pl * XST + ci0];
+      }
+      const float4 y0 = *reinterpret_cast<const float4*>(&ys[pl][cg * 4]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&ys[pl][32 + cg * 4]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = cot * 64 + cg * 8 + j;
-      if (co < a.cout) atomicAdd(&a.dw[(static_cast<size_t>(tap) * a.cin + ci) * a.cout + co], acc[j]);
+      for (int t = 0; t < TCI; ++t) {
+        acc[t][0] = fmaf(xv[t], y0.x, acc[t][0]);
+        acc[t][1] = fmaf(xv[t], y0.y, acc[t][1]);
+        acc[t][2] = fmaf(xv[t], y0.z, acc[t][2]);
+        acc[t][3] = fmaf(xv[t], y0.w, acc[t][3]);
+        acc[t][4] = fmaf(xv[t], y1.x, acc[t][4]);
+        acc[t][5] = fmaf(xv[t], y1.y, acc[t][5]);
+        acc[t][6] = fmaf(xv[t], y1.z, acc[t][6]);
+        acc[t][7] = fmaf(xv[t], y1.w, acc[t][7]);
+      }
     }
   }
+  if (PH == 1) {
+#pragma unroll
+    for (int t = 0; t < TCI; ++t) {
+      const int ci = cit * CIB + ci0 + t;
+      if (ci >= a.cin) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int co = cot * 64 + (j < 4 ? cg * 4 + j : 32 + cg * 4 + (j - 4));
+        if (co < a.cout) atomicAdd(&a.dw[(static_cast<size_t>(tap) * a.cin + ci) * a.cout + co], acc[t][j]);
+      }
+    }
+  } else {
+    // sum the pixel phases: row = phase * CIB + channel
+    __syncthreads();
+    float* red = &ys[0][0];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[row * 64 + (j < 4 ? cg * 4 + j : 32 + cg * 4 + (j - 4))] = acc[0][j];
+    __syncthreads();
+    for (int e = tid; e < CIB * 64; e += 256) {
+      const int c = e >> 6, o = e & 63;
+      const int ci = cit * CIB + c, co = cot * 64 + o;
+      if (ci >= a.cin || co >= a.cout) continue;
+      float sum = 0.0f;
+#pragma unroll
+      for (int ph = 0; ph < PH; ++ph) sum += red[(ph * CIB + c) * 64 + o];
+      atomicAdd(&a.dw[(static_cast<size_t>(tap) * a.cin + ci) * a.cout + co], sum);
+    }
+  }
+}
+
+template <int TCI, int PH>
+static void launch_wgrad(mpg_handle h, WgradArgs& a, long long npix, cudaStream_t st) {
+  constexpr int CIB = 32 * TCI / PH;
+  const int tiles = a.k * a.k * ((a.cin + CIB - 1) / CIB) * ((a.cout + 63) / 64);
+  int splits = (h->sm_count * 4 + tiles - 1) / tiles;
+  if (splits < 1) splits = 1;
+  long long per = (npix + splits - 1) / splits;
+  per = (per + 31) / 32 * 32;
+  if (per < 32) per = 32;
+  splits = static_cast<int>((npix + per - 1) / per);
+  a.px_per_split = static_cast<int>(per);
+  wgrad_kernel<TCI, PH><<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits)), 256, 0, st>>>(a);
 }
 
 // Filter gradient of the THIN stride-1 convolutions (cout <= 32, any cin; generator layers 4->8, 8->32, 32->8, 8->2,
@@ -958,6 +1030,7 @@ int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* d
   a.ow = (ww + stride - 1) / stride;
   a.in_up = in_up;
   const long long npix = static_cast<long long>(n) * a.oh * a.ow;
+  MPG_CHECK_ARG(npix < (1ll << 31), "mpg_train_conv_wgrad: %lld output pixels exceed 2^31", npix);
   if (stride == 1 && (k == 1 || k == 3 || k == 5) && cout <= 32) {
     // thin layers: (tap, ci)-per-thread kernel, persistent over 8x16-pixel tiles
     int ci_chunk = k == 5 ? 8 : (k == 3 ? 24 : 32);
@@ -970,16 +1043,14 @@ int mpg_train_conv_wgrad(mpg_handle h, const float* x, const float* dy, float* d
     else wgrad_thin_kernel<32><<<grid, 256, 0, st>>>(a, ci_chunk);
     MPG_CUDA(cudaGetLastError());
   } else {
-  const int tiles = k * k * ((cin + 31) / 32) * ((cout + 63) / 64);
-  int splits = (h->sm_count * 4 + tiles - 1) / tiles;
-  if (splits < 1) splits = 1;
-  long long per = (npix + splits - 1) / splits;
-  per = (per + 31) / 32 * 32;
-  if (per < 32) per = 32;
-  splits = static_cast<int>((npix + per - 1) / per);
-  a.px_per_split = static_cast<int>(per);
-  wgrad_kernel<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits)), 256, 0, st>>>(a);
-  MPG_CUDA(cudaGetLastError());
+    if (cin <= 2) launch_wgrad<1, 16>(h, a, npix, st);
+    else if (cin <= 4) launch_wgrad<1, 8>(h, a, npix, st);
+    else if (cin <= 8) launch_wgrad<1, 4>(h, a, npix, st);
+    else if (cin <= 16) launch_wgrad<1, 2>(h, a, npix, st);
+    else if (cin >= 128) launch_wgrad<4, 1>(h, a, npix, st);
+    else if (cin >= 64) launch_wgrad<2, 1>(h, a, npix, st);
+    else launch_wgrad<1, 1>(h, a, npix, st);
+    MPG_CUDA(cudaGetLastError());
   }
   if (dbias) {
     MPG_CHECK_ARG(scratch != nullptr, "mpg_train_conv_wgrad: scratch missing");
