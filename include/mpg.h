@@ -331,6 +331,8 @@ int mpg_train_bias_grad(mpg_handle h, const float* dy, float* dbias, double* scr
 int mpg_train_bn_fwd(mpg_handle h, const float* x, const float* gamma, const float* beta, float* y, float* mean,
                      float* var, float* invstd, float* moving_mean, float* moving_var, double* scratch,
                      long long rows, int c, float eps, float decay, int act, void* stream);
+/* backward: dy = gradient w.r.t. the activated output y; dx = gradient w.r.t. x; dgamma / dbeta accumulate. `dz` is
+ * unused (kept for ABI stability, may be NULL): dy * act'(y) is formed inside the statistics and the dx pass */
 int mpg_train_bn_bwd(mpg_handle h, const float* x, const float* y, const float* dy, const float* gamma,
                      const float* mean, const float* invstd, float* dz, float* dx, float* dgamma, float* dbeta,
                      double* scratch, long long rows, int c, int act, void* stream);

@@ -363,18 +363,33 @@ __global__ void __launch_bounds__(256) wgrad_thin_kernel(const WgradArgs a, int 
 }
 
 // per-channel double-precision sums over `rows` rows of a [rows, c] matrix: out[0..c) += sum a*b?, out[c..2c) ...
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == MPG_ACT_RELU) return fmaxf(z, 0.0f);
+  if (act == MPG_ACT_LRELU) return 0.6f * z + 0.4f * fabsf(z);  // tools_wscale/GAN.py:733-737
+  if (act == MPG_ACT_TANH) return tanhf(z);
+  return z;
+}
+// derivative expressed through the OUTPUT y = act(z) (relu / lrelu keep the sign of z)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  if (act == MPG_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  if (act == MPG_ACT_LRELU) return y > 0.0f ? 1.0f : (y < 0.0f ? 0.2f : 0.6f);  // d/dz (0.6 z + 0.4 |z|), 0.6 at z = 0
+  if (act == MPG_ACT_TANH) return 1.0f - y * y;
+  return 1.0f;
+}
+
 // mode 0: s0 = sum x, s1 = sum x^2          (BN statistics)
-// mode 1: s0 = sum dz, s1 = sum dz * xhat    (BN backward; xhat = (x - mean) * invstd)
+// mode 1: s0 = sum dz, s1 = sum dz * xhat    (BN backward; xhat = (x - mean) * invstd); with yact != NULL the `dz`
+//         argument is dy, the gradient w.r.t. the ACTIVATED output, and dz = dy * act'(yact) is formed on the fly
 // mode 2: s0 = sum x                         (bias gradient)
 __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const float* dz, const float* mean,
                                                         const float* invstd, double* out, long long rows, int c,
-                                                        int mode) {
+                                                        int mode, const float* yact = nullptr, int act = 0) {
   // Vector path (c % 4 == 0, c <= 1024): a thread owns 4 adjacent channels (one 128-bit load per row) and walks the rows
   // with 4 independent loads in flight; the block combines its row groups in shared memory, so every block issues ONE
   // double atomic per channel and statistic. (The scalar version below kept 4 x 4 bytes per thread in flight and was
   // latency bound at ~30 % of the HBM rate: 34 us for a 33 MB layer, 68 launches per loop body.)
   if ((c & 3) == 0 && c <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (mode != 1 || (reinterpret_cast<uintptr_t>(dz) & 15) == 0)) {
+      (mode != 1 || ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(yact)) & 15) == 0)) {
     __shared__ double red[2][256][4];
     const int groups = c >> 2;                       // float4 groups per row
     const int lanes = groups < 256 ? groups : 256;   // threads per row
@@ -388,6 +403,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
       if (active && g < groups) {
         const float4* xp = reinterpret_cast<const float4*>(x) + g;
         const float4* dp = reinterpret_cast<const float4*>(dz) + g;
+        const float4* yp = reinterpret_cast<const float4*>(yact) + g;
         float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
         if (mode == 1) {
           mu = reinterpret_cast<const float4*>(mean)[g];
@@ -400,7 +416,16 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
           for (int j = 0; j < 4; ++j) {
             const long long rr = r + j * rstep;
             v[j] = rr < rows ? __ldg(xp + rr * groups) : make_float4(0, 0, 0, 0);
-            if (mode == 1) d[j] = rr < rows ? __ldg(dp + rr * groups) : make_float4(0, 0, 0, 0);
+            if (mode == 1) {
+              d[j] = rr < rows ? __ldg(dp + rr * groups) : make_float4(0, 0, 0, 0);
+              if (yact != nullptr && rr < rows) {
+                const float4 ya = __ldg(yp + rr * groups);
+                d[j].x *= act_grad_from_out(ya.x, act);
+                d[j].y *= act_grad_from_out(ya.y, act);
+                d[j].z *= act_grad_from_out(ya.z, act);
+                d[j].w *= act_grad_from_out(ya.w, act);
+              }
+            }
           }
           // fp32 partial sums over the 4 rows in flight, accumulated in double across iterations
           float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
@@ -470,7 +495,8 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
         s0 += xv;
         s1 += static_cast<double>(xv) * xv;
       } else if (mode == 1) {
-        const float d = dz[r * c + ch];
+        float d = dz[r * c + ch];
+        if (yact != nullptr) d *= act_grad_from_out(yact[r * c + ch], act);
         s0 += d;
         s1 += static_cast<double>(d) * ((xv - mean[ch]) * invstd[ch]);
       } else {
@@ -480,20 +506,6 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* x, const flo
     atomicAdd(&out[ch], s0);
     if (mode != 2) atomicAdd(&out[c + ch], s1);
   }
-}
-
-__device__ __forceinline__ float act_fwd(float z, int act) {
-  if (act == MPG_ACT_RELU) return fmaxf(z, 0.0f);
-  if (act == MPG_ACT_LRELU) return 0.6f * z + 0.4f * fabsf(z);  // tools_wscale/GAN.py:733-737
-  if (act == MPG_ACT_TANH) return tanhf(z);
-  return z;
-}
-// derivative expressed through the OUTPUT y = act(z) (relu / lrelu keep the sign of z)
-__device__ __forceinline__ float act_grad_from_out(float y, int act) {
-  if (act == MPG_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
-  if (act == MPG_ACT_LRELU) return y > 0.0f ? 1.0f : (y < 0.0f ? 0.2f : 0.6f);  // d/dz (0.6 z + 0.4 |z|), 0.6 at z = 0
-  if (act == MPG_ACT_TANH) return 1.0f - y * y;
-  return 1.0f;
 }
 
 // finalize BN statistics: mean, biased variance, invstd; EMA of the moving statistics (tf.contrib batch_norm)
@@ -542,6 +554,49 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const flo
   }
 }
 
+// bn_finalize_kernel + bn_apply_kernel in one launch (c % 4 == 0, c <= 1024): every block derives mean / invstd of all channels
+// from the double sums (same arithmetic as bn_finalize_kernel) into shared memory, block 0 also publishes them and updates the
+// moving statistics; the element pass is bn_apply_kernel's 128-bit path.
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const float* x, const float* gamma, const float* beta,
+                                                                 const double* sums, float* mean, float* var, float* invstd,
+                                                                 float* moving_mean, float* moving_var, float* y,
+                                                                 long long rows, int c, float eps, float decay, int act) {
+  __shared__ __align__(16) float s_mean[1024];
+  __shared__ __align__(16) float s_inv[1024];
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    const double m = sums[ch] / static_cast<double>(rows);
+    double v = sums[c + ch] / static_cast<double>(rows) - m * m;
+    if (v < 0.0) v = 0.0;
+    const float is = static_cast<float>(1.0 / sqrt(v + static_cast<double>(eps)));
+    s_mean[ch] = static_cast<float>(m);
+    s_inv[ch] = is;
+    if (blockIdx.x == 0) {
+      mean[ch] = static_cast<float>(m);
+      var[ch] = static_cast<float>(v);
+      invstd[ch] = is;
+      if (moving_mean) {  // moving = moving * decay + batch * (1 - decay)
+        moving_mean[ch] = moving_mean[ch] * decay + static_cast<float>(m) * (1.0f - decay);
+        moving_var[ch] = moving_var[ch] * decay + static_cast<float>(v) * (1.0f - decay);
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned c4 = static_cast<unsigned>(c) >> 2;
+  const long long t4 = (rows * c) >> 2;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
+    const int ch = static_cast<int>(static_cast<unsigned>(e % c4)) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + e);
+    const float4 m = *reinterpret_cast<const float4*>(s_mean + ch), is = *reinterpret_cast<const float4*>(s_inv + ch);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + ch), b = *reinterpret_cast<const float4*>(beta + ch);
+    float4 o;
+    o.x = act_fwd((v.x - m.x) * is.x * g.x + b.x, act);
+    o.y = act_fwd((v.y - m.y) * is.y * g.y + b.y, act);
+    o.z = act_fwd((v.z - m.z) * is.z * g.z + b.z, act);
+    o.w = act_fwd((v.w - m.w) * is.w * g.w + b.w, act);
+    reinterpret_cast<float4*>(y)[e] = o;
+  }
+}
+
 // dz = dy * act'(y)   (in place allowed)
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* y, const float* dy, float* dz, long long total, int act) {
   if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0) {
@@ -562,17 +617,28 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* y, const floa
 }
 
 // dx = gamma * invstd / N * (N * dz - dbeta - xhat * dgamma);  dgamma/dbeta are read from `sums` (double)
+// `dz` is dy (gradient w.r.t. the activated output) and dz = dy * act'(y) is formed here when y != NULL
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* x, const float* dz, const float* gamma,
                                                       const float* mean, const float* invstd, const double* sums,
-                                                      float* dx, float* dgamma, float* dbeta, long long rows, int c) {
+                                                      float* dx, float* dgamma, float* dbeta, long long rows, int c,
+                                                      const float* y, int act) {
   const long long total = rows * c;
   const float inv_n = 1.0f / static_cast<float>(rows);
-  if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+  if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dx) |
+                        reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     const unsigned c4 = static_cast<unsigned>(c) >> 2;
     const long long t4 = total >> 2;
     for (long long e = blockIdx.x * 256LL + threadIdx.x; e < t4; e += static_cast<long long>(gridDim.x) * 256) {
       const int ch = static_cast<int>(static_cast<unsigned>(e % c4)) * 4;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e), dv = reinterpret_cast<const float4*>(dz)[e];
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e);
+      float4 dv = reinterpret_cast<const float4*>(dz)[e];
+      if (y != nullptr) {
+        const float4 ya = __ldg(reinterpret_cast<const float4*>(y) + e);
+        dv.x *= act_grad_from_out(ya.x, act);
+        dv.y *= act_grad_from_out(ya.y, act);
+        dv.z *= act_grad_from_out(ya.z, act);
+        dv.w *= act_grad_from_out(ya.w, act);
+      }
       const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
       float o[4];
 #pragma unroll
@@ -596,7 +662,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* x, const float
     const int ch = static_cast<int>(e % c);
     const float db = static_cast<float>(sums[ch]), dg = static_cast<float>(sums[c + ch]);
     const float xh = (x[e] - mean[ch]) * invstd[ch];
-    dx[e] = gamma[ch] * invstd[ch] * (dz[e] - inv_n * (db + xh * dg));
+    const float d = y != nullptr ? dz[e] * act_grad_from_out(y[e], act) : dz[e];
+    dx[e] = gamma[ch] * invstd[ch] * (d - inv_n * (db + xh * dg));
     if (e < c) {
       dgamma[e] += static_cast<float>(sums[c + e]);
       dbeta[e] += static_cast<float>(sums[e]);
@@ -1084,23 +1151,32 @@ int mpg_train_bn_fwd(mpg_handle h, const float* x, const float* gamma, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * c, st));
   colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(x, nullptr, nullptr, nullptr, scratch, rows, c, 0);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, mean, var, invstd, moving_mean, moving_var, rows, c, eps, decay);
-  bn_apply_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, gamma, beta, mean, invstd, y, rows * c, c, act);
+  if ((c & 3) == 0 && c <= 1024 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+      rows * c < (1LL << 33)) {
+    bn_finalize_apply_kernel<<<grid_for(rows * c / 4, h->sm_count), 256, 0, st>>>(x, gamma, beta, scratch, mean, var, invstd,
+                                                                                   moving_mean, moving_var, y, rows, c, eps, decay,
+                                                                                   act);
+  } else {
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, mean, var, invstd, moving_mean, moving_var, rows, c, eps, decay);
+    bn_apply_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, gamma, beta, mean, invstd, y, rows * c, c, act);
+  }
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }
 
 /* backward of mpg_train_bn_fwd: dy is the gradient w.r.t. the activated output y; dgamma/dbeta accumulate.
- * dz (scratch, rows*c floats, may alias dy) receives dy * act'(y). scratch: 2*c doubles. */
+ * dz: unused since round 2 (dy * act'(y) is formed inside the statistics and the dx pass instead of a pass of its own);
+ * may be NULL. scratch: 2*c doubles. */
 int mpg_train_bn_bwd(mpg_handle h, const float* x, const float* y, const float* dy, const float* gamma, const float* mean,
                      const float* invstd, float* dz, float* dx, float* dgamma, float* dbeta, double* scratch, long long rows,
                      int c, int act, void* stream) {
-  MPG_CHECK_ARG(h && x && y && dy && gamma && mean && invstd && dz && dx && dgamma && dbeta && scratch, "mpg_train_bn_bwd: bad argument");
+  MPG_CHECK_ARG(h && x && y && dy && gamma && mean && invstd && dx && dgamma && dbeta && scratch, "mpg_train_bn_bwd: bad argument");
+  (void)dz;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  act_bwd_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(y, dy, dz, rows * c, act);
   MPG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * c, st));
-  colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(x, dz, mean, invstd, scratch, rows, c, 1);
-  bn_bwd_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, dz, gamma, mean, invstd, scratch, dx, dgamma, dbeta, rows, c);
+  colstats_kernel<<<h->sm_count * 2, 256, 0, st>>>(x, dy, mean, invstd, scratch, rows, c, 1, y, act);
+  bn_bwd_kernel<<<grid_for(rows * c, h->sm_count), 256, 0, st>>>(x, dy, gamma, mean, invstd, scratch, dx, dgamma, dbeta, rows, c, y,
+                                                                  act);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

@@ -181,8 +181,7 @@ class _Conv:
         rows = sv["rows"]
         if self.bn:
             dlin = tr.buf(sv["lin"].shape)
-            dz = tr.buf(sv["lin"].shape)
-            tr.call("bn_bwd", sv["lin"], sv["y"], dy, ps.view(ps.w, self.gamma), sv["mean"], sv["invstd"], dz, dlin,
+            tr.call("bn_bwd", sv["lin"], sv["y"], dy, ps.view(ps.w, self.gamma), sv["mean"], sv["invstd"], None, dlin,
                     ps.view(ps.gw, self.gamma), ps.view(ps.gw, self.beta), tr.scratch, rows, self.cout, self.act, tr.st)
         elif self.act != capi.ACT_NONE:
             dlin = tr.buf(sv["lin"].shape)
