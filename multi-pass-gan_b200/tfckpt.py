@@ -18,7 +18,9 @@ string table whose values are BundleEntryProto messages):
 PARITY UNPINNED: no TensorFlow-written checkpoint exists in the reference tree or in this image, so the reader is
 tested against this module's own writer plus known-answer vectors of the primitives (CRC32C, masking, varints,
 footer magic). `read_checkpoint` verifies block checksums, so a format misunderstanding fails loudly instead of
-yielding wrong weights.
+yielding wrong weights. Pinned by a third party where one exists in the image: the snappy decoder (compression type 1 of
+the table format) decodes streams produced by Google's snappy library through pyarrow, also as the compressor of whole
+index blocks (tests/test_tfckpt.py); multi-shard bundles (`num_shards` > 1, `shard_id`) round-trip through the writer.
 """
 import os
 import struct
@@ -420,13 +422,22 @@ def _build_block(items, restart_interval=16):
     return bytes(out)
 
 
-def write_checkpoint(prefix, tensors, block_size=4096):
-    """Write {name: array} as a single-shard V2 checkpoint (`prefix`.index + `prefix`.data-00000-of-00001), readable by
-    tf.train.Saver / tf.train.load_checkpoint. Uncompressed blocks, CRCs on every block and tensor."""
+def write_checkpoint(prefix, tensors, block_size=4096, compressor=None, num_shards=1):
+    """Write {name: array} as a V2 checkpoint (`prefix`.index + `prefix`.data-0000k-of-0000N) in the layout of
+    tf.train.Saver. CRCs on every block and tensor. Defaults: one data shard, uncompressed index blocks (what TF writes).
+    compressor: callable bytes -> raw snappy stream; index blocks are then stored with compression type 1 (the LevelDB table
+    format's kSnappyCompression) -- used by the tests with a third-party snappy implementation to pin the reader's decoder.
+    num_shards > 1: tensors are dealt round-robin over that many data files (shard_id / per-shard offsets in the entries),
+    the layout a sharded Saver merges its bundles into."""
     names = sorted(tensors, key=lambda s: s.encode("utf-8"))
     if "" in tensors:
         raise ValueError("the empty name is reserved for the bundle header")
+    num_shards = int(num_shards)
+    if num_shards < 1:
+        raise ValueError("num_shards must be >= 1")
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    if num_shards > 1:
+        return _write_sharded(prefix, tensors, names, block_size, compressor, num_shards)
     entries = []
     offset = 0
     with open(prefix + ".data-00000-of-00001", "wb") as fh:
@@ -444,7 +455,42 @@ def write_checkpoint(prefix, tensors, block_size=4096):
             msg += _pb_varint_field(5, len(raw)) + put_varint((6 << 3) | 5) + struct.pack("<I", mask_crc(crc32c(raw)))
             entries.append((name.encode("utf-8"), msg))
             offset += len(raw)
-    header = _pb_varint_field(1, 1) + _pb_bytes_field(3, _pb_varint_field(1, 1))  # num_shards=1, little endian, producer 1
+    _write_index(prefix, entries, 1, block_size, compressor)
+
+
+def _entry_message(a, dt, raw, offset, shard_id):
+    shape = b"".join(_pb_bytes_field(2, _pb_varint_field(1, int(d))) for d in a.shape)
+    msg = _pb_varint_field(1, _DTYPE_CODE[np.dtype(dt)]) + _pb_bytes_field(2, shape)
+    if shard_id:
+        msg += _pb_varint_field(3, shard_id)
+    if offset:
+        msg += _pb_varint_field(4, offset)
+    return msg + _pb_varint_field(5, len(raw)) + put_varint((6 << 3) | 5) + struct.pack("<I", mask_crc(crc32c(raw)))
+
+
+def _write_sharded(prefix, tensors, names, block_size, compressor, num_shards):
+    files = [open("%s.data-%05d-of-%05d" % (prefix, k, num_shards), "wb") for k in range(num_shards)]
+    offsets = [0] * num_shards
+    entries = []
+    try:
+        for i, name in enumerate(names):
+            a = np.asarray(tensors[name])
+            dt = a.dtype.newbyteorder("<") if a.dtype.byteorder == ">" else a.dtype
+            if np.dtype(dt) not in _DTYPE_CODE:
+                raise ValueError("dtype %s of '%s' is not supported" % (a.dtype, name))
+            raw = a.astype(dt, copy=False).tobytes(order="C")
+            k = i % num_shards
+            files[k].write(raw)
+            entries.append((name.encode("utf-8"), _entry_message(a, dt, raw, offsets[k], k)))
+            offsets[k] += len(raw)
+    finally:
+        for fh in files:
+            fh.close()
+    _write_index(prefix, entries, num_shards, block_size, compressor)
+
+
+def _write_index(prefix, entries, num_shards, block_size, compressor):
+    header = _pb_varint_field(1, num_shards) + _pb_bytes_field(3, _pb_varint_field(1, 1))  # num_shards, little endian, producer 1
     items = [(b"", header)] + entries
     blocks = []
     cur, cur_bytes = [], 0
@@ -460,9 +506,12 @@ def write_checkpoint(prefix, tensors, block_size=4096):
 
     def emit(block_bytes):
         off = len(out)
+        ctype = b"\x00"  # kNoCompression
+        if compressor is not None:
+            block_bytes, ctype = bytes(compressor(block_bytes)), b"\x01"  # kSnappyCompression
         out.extend(block_bytes)
-        out.append(0)  # kNoCompression
-        out.extend(struct.pack("<I", mask_crc(crc32c(block_bytes + b"\x00"))))
+        out.extend(ctype)
+        out.extend(struct.pack("<I", mask_crc(crc32c(block_bytes + ctype))))
         return put_varint(off) + put_varint(len(block_bytes))
 
     index_items = []

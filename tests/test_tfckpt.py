@@ -177,3 +177,72 @@ def test_convert_tool_roundtrip(tmp_path):
     assert sorted(got.files) == ["gen_1/generator/a/bias", "gen_1/generator/a/weight"]
     np.testing.assert_array_equal(got["gen_1/generator/a/weight"], w["gen_1/generator/a/weight"])
     assert tool.main(["list", prefix]) == 0
+
+
+def _pa_snappy():
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("snappy"):
+        pytest.skip("pyarrow built without snappy")
+    return lambda b: pa.compress(bytes(b), codec="snappy", asbytes=True)
+
+
+def test_snappy_decoder_against_a_third_party_compressor():
+    """Streams produced by Google's snappy library (through pyarrow) -- literals of every length class, copies with 1-, 2-
+    and 4-byte offsets, overlapping copies -- decode to the original bytes."""
+    comp = _pa_snappy()
+    rng = np.random.default_rng(12)
+    cases = [b"", b"a", b"abcd" * 5, bytes(range(256)) * 3, rng.integers(0, 256, 70000, dtype=np.uint8).tobytes(),
+             (b"the quick brown fox " * 40 + rng.integers(0, 4, 3000, dtype=np.uint8).tobytes()) * 30,
+             b"\x00" * 200000, rng.integers(0, 2, 150000, dtype=np.uint8).tobytes()]
+    big = rng.integers(0, 256, 90000, dtype=np.uint8).tobytes()
+    cases.append(big + b"x" * 10 + big)            # a copy further back than 64 KiB
+    for raw in cases:
+        enc = comp(raw)
+        assert tfckpt.snappy_decompress(enc) == raw
+    assert sum(len(comp(c)) for c in cases) < sum(len(c) for c in cases) // 2   # the streams really are compressed
+
+
+def test_index_blocks_compressed_by_a_third_party_snappy(tmp_path):
+    """A bundle whose index blocks carry LevelDB's kSnappyCompression, compressed by Google's snappy (pyarrow)."""
+    comp = _pa_snappy()
+    rng = np.random.default_rng(13)
+    tensors = _tensors(rng, 120)
+    prefix = str(tmp_path / "model_0001.ckpt")
+    tfckpt.write_checkpoint(prefix, tensors, block_size=1024, compressor=comp)
+    plain = str(tmp_path / "plain.ckpt")
+    tfckpt.write_checkpoint(plain, tensors, block_size=1024)
+    assert os.path.getsize(prefix + ".index") < os.path.getsize(plain + ".index")
+    got = tfckpt.read_checkpoint(prefix, verify_data=True)
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    # a flipped byte inside a compressed block fails the block checksum
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[40] ^= 0x10
+    open(prefix + ".index", "wb").write(bytes(raw))
+    with pytest.raises(tfckpt.CheckpointError):
+        tfckpt.read_checkpoint(prefix)
+
+
+def test_multi_shard_bundle(tmp_path):
+    """num_shards = 3: .data-0000k-of-00003 files, shard_id / per-shard offsets in the entries (the layout a sharded Saver
+    merges into); a missing shard and a corrupted one fail loudly."""
+    rng = np.random.default_rng(14)
+    tensors = _tensors(rng, 40)
+    prefix = str(tmp_path / "model_0002.ckpt")
+    tfckpt.write_checkpoint(prefix, tensors, num_shards=3)
+    assert sorted(f for f in os.listdir(tmp_path) if ".data-" in f) == ["model_0002.ckpt.data-%05d-of-00003" % k for k in range(3)]
+    got = tfckpt.read_checkpoint(prefix, verify_data=True)
+    for k, v in tensors.items():
+        assert np.array_equal(got[k], v) and got[k].dtype == v.dtype, k
+    some = sorted(tensors)[4]
+    assert np.array_equal(tfckpt.read_checkpoint(prefix, names=[some])[some], tensors[some])
+    shard1 = prefix + ".data-00001-of-00003"
+    data = bytearray(open(shard1, "rb").read())
+    data[7] ^= 1
+    open(shard1, "wb").write(bytes(data))
+    with pytest.raises(tfckpt.CheckpointError):
+        tfckpt.read_checkpoint(prefix, verify_data=True)
+    os.remove(shard1)
+    with pytest.raises((tfckpt.CheckpointError, OSError)):
+        tfckpt.read_checkpoint(prefix, verify_data=True)
