@@ -9,7 +9,9 @@ Restates GAN/multipassGAN-8x.py for the configuration the shipped training comma
   of tf.contrib.opt.MovingAverageOptimizer(…, 0.999) :1356-1361.
 Pinned by golden vectors produced by executing the reference's own growing_disc / growBlockDisc / lerp on the numpy TF1
 shim (tests/golden/make_golden.py growdisc -> tests/golden/growdisc.npz); gradients are torch autograd in fp64.
-Out of scope: temporal discriminator / advection (:868-923, lambda_t), loss scaling (numerically the identity), gDrop noise.
+Also growing_disc_tempo :868-923 (the temporal critic of three aligned frames) with its WGAN-GP loss :1262-1289, pinned the same
+way (gt_first / gt_second vectors).  Out of scope: the frame alignment in front of it (advection / tensorResample, adv_flag),
+loss scaling (numerically the identity), gDrop noise.
 """
 import math
 
@@ -110,6 +112,38 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
         return gan.y(), feats
 
 
+def growing_disc_tempo(frames, percentage, ctx, cfg):
+    """growing_disc_tempo :868-923 (useVelInTDisc 0, no batch norm / gDrop / minibatch stddev): the unconditional critic of
+    three aligned frames. frames [B, S*S, 3] (what `tf.transpose(reshape(., [-1, 3, n_output]), [0, 2, 1])` of :1213-1214
+    hands over) -> logits [B, 1].  Same growing structure as growing_disc with the name prefix "t" and a 3-channel image."""
+    S, u = cfg.tileSizeHigh, cfg.upRes
+    with ctx.variable_scope("tempo-disc"):
+        img = frames.reshape(-1, S, S, 3)                                              # :879
+        gan = og.GAN(img, ctx)
+        x, _ = gan.convolutional_layer(int(cfg.start_fms / u), [1, 1], None, in_layer=img, stride=[1],
+                                       name="t_cfromDensity%d" % u)                    # :882
+        in_high = img
+        gan2 = og.GAN(in_high, ctx)
+        for j in range(cfg.stages, 0, -1):
+            num_fms = int(min(cfg.start_fms / (2 ** j), cfg.max_fms))
+            if cfg.upsampling_mode == 2:
+                in_high = avg_pool2(in_high)                                           # :889-890
+            x, _, _ = grow_block_disc(gan, x, int(2 ** j), num_fms, cfg, name="t")     # :894
+            from_dens = min(min(num_fms * 2, cfg.max_fms), cfg.start_fms // 2)
+            old, _ = gan2.convolutional_layer(from_dens, [1, 1], None, stride=[1], name="t_cfromDensity%d" % (2 ** (j - 1)),
+                                              in_layer=in_high)                        # :896
+            with ctx.variable_scope("blend%i" % j):
+                x = lerp(old, x, percentage - (j - 1))                                 # :899-904
+        if not cfg.first_nn_arch:
+            f = [cfg.filterSize, cfg.filterSize]
+            x1, _ = gan.convolutional_layer(32, f, og.lrelu, stride=[1], name="t_cA1", in_layer=x)
+            gan.convolutional_layer(4, f, None, stride=[1], name="t_cB1", in_layer=x1)
+        # (firstNNArch: same cursor quirk as growing_disc -- flatten() sees the pooled output of the last growBlockDisc)
+        gan.flatten()
+        gan.fully_connected_layer(1, None, name="t_l61", gain=1)                        # :919
+        return gan.y()
+
+
 def growing_gen_train(x_rows, percentage, ctx, cfg, pixel_norm=True, addBicubicUpsample=True):
     """growing_gen with output=False (GAN/multipassGAN-8x.py:700-750): every stage emits a density (1x1 conv, gain 1) plus the
     residual input density, blended with the density of the previous stage by lerp(old, new, percentage - (j-1)).
@@ -159,17 +193,21 @@ def refine_input(x_rows, y_rows, cfg):
 
 
 def wgan_gp_losses(disc, gen, d_out_fn, y_in, gen_y, lerp_factor, wgan_lambda=10.0, wgan_target=1.0, wgan_epsilon=0.001,
-                   weight_dld=1.0, image_side=None):
+                   weight_dld=1.0, image_side=None, frames=None):
     """Discriminator / generator critic losses with use_wgan_gp (:1101-1143). d_out_fn(y) -> critic logits.
     lerp_factor: the tf.random_uniform([B, 1]) sample of :1120 (fed in, so that both sides use the same numbers).
     image_side: upsampling_mode 1 / 3 keeps the samples as [B, S, S, 1] images there (:1047, 1062), so the reference's
     `reduce_sum(..., axis=1)` (:1130) sums over the image ROWS only: one gradient norm per (sample, column).  Reproduced:
-    pass S to get that reduction on the flat rows."""
+    pass S to get that reduction on the flat rows.
+    frames: the temporal critic's samples are [B, S*S, frames] (:1213-1214, 1279-1285), so the same reduce_sum(axis=1) gives
+    one norm per (sample, frame): pass 3 with rows of S*S*3 values."""
     d_loss = (-disc).mean() * weight_dld + gen.mean()
     y_gp = (lerp_factor * y_in + (1 - lerp_factor) * gen_y).detach().requires_grad_(True)
     d_out_loss = d_out_fn(y_gp).mean()
     grads = torch.autograd.grad(d_out_loss, y_gp, create_graph=True)[0]
-    if image_side is None:
+    if frames is not None:
+        norms = torch.sqrt(((grads.reshape(grads.shape[0], -1, frames) + 1e-4) ** 2).sum(dim=1))   # :1284
+    elif image_side is None:
         norms = torch.sqrt(((grads + 1e-4) ** 2).sum(dim=1))                           # :1130
     else:
         norms = torch.sqrt(((grads.reshape(-1, image_side, image_side) + 1e-4) ** 2).sum(dim=1))

@@ -357,6 +357,33 @@ def make_growdisc_fixtures():
                                                  first_nn_arch=first_nn_arch, percentages=list(percentages),
                                                  filterSize=filterSize, upsampling_mode=upsampling_mode))
 
+    tcode = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["lerp", "growBlockDisc", "growing_disc_tempo"])
+
+    def run_tempo(tag, seed, L, u, start_fms, max_fms, first_nn_arch, percentages, filterSize=3, upsampling_mode=2):
+        """growing_disc_tempo (:868-923): the unconditional critic of three aligned frames, input [B, S*S, 3]."""
+        S = L * u
+        store, getv = _provide(seed)
+        tfs.reset({})
+        tfs.get_variable = getv
+        ns = dict(tf=tfs, GAN=ref_gan.GAN, lrelu=ref_gan.lrelu, np=np, math=math, tileSizeLow=L, tileSizeHigh=S, upRes=u,
+                  upsampling_mode=upsampling_mode, upsampleMode=1, start_fms=start_fms, max_fms=max_fms, filterSize=filterSize,
+                  first_nn_arch=first_nn_arch, useVelInTDisc=False, bn_decay=0.999, use_mb_stddev=False, gn=lambda x, gstr: x,
+                  print=lambda *a, **k: None)
+        exec(tcode, ns)
+        frames = rng.random((2, S * S, 3), dtype=np.float32)
+        fixtures[tag + "_frames"] = frames
+        for k, pct in enumerate(percentages):
+            tfs.STATE.requested = {}
+            logits = ns["growing_disc_tempo"](tfs.T(frames), tfs.T(np.float32(pct)), reuse=tfs.AUTO_REUSE, use_batch_norm=False,
+                                              train=False, currentUpres=int(round(math.log(u, 2))))
+            fixtures["%s_p%d_logits" % (tag, k)] = logits.a
+            print(tag, pct, logits.a.ravel())
+        fixtures[tag + "_vars"] = _names_blob(tfs.STATE.requested)
+        fixtures[tag + "_wsum"] = _wsum(store)
+        fixtures[tag + "_cfg"] = json.dumps(dict(seed=seed, L=L, u=u, C=0, start_fms=start_fms, max_fms=max_fms,
+                                                 first_nn_arch=first_nn_arch, percentages=list(percentages),
+                                                 filterSize=filterSize, upsampling_mode=upsampling_mode))
+
     gen_code = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["lerp", "resBlock", "growBlockGen", "growing_gen"])
 
     def run_gen(tag, seed, L, u, C, start_fms, max_fms, percentages, first_nn_arch=True, upsampling_mode=2, filterSize=3):
@@ -392,6 +419,9 @@ def make_growdisc_fixtures():
     # the second (refinement) network's training graph: upsampling_mode 1, firstNNArch 0 (GAN/example_run_training.py:7)
     run_gen("gg_second", 84, 2, 8, 4, 32, 32, (0.4, 1.3, 2.75, 3.0), first_nn_arch=False, upsampling_mode=1, filterSize=5)
     run("gd_second", 85, 2, 8, 4, 32, 32, False, (0.4, 1.3, 2.75, 3.0), filterSize=5, upsampling_mode=1)
+    # the temporal critic of both shipped training commands (lambda_t 1.0): first network / refinement network
+    run_tempo("gt_first", 86, 4, 8, 32, 32, True, (0.4, 1.3, 2.75, 3.0))
+    run_tempo("gt_second", 87, 2, 8, 32, 32, False, (0.4, 1.3, 2.75, 3.0), filterSize=5, upsampling_mode=1)
     np.savez_compressed(os.path.join(HERE, "growdisc.npz"), **fixtures)
     print("growdisc.npz written:", len(fixtures), "arrays")
 

@@ -125,3 +125,26 @@ def test_refinement_gradient_penalty_reduces_over_image_rows():
     assert torch.equal(xi[..., 0], g.reshape(2, S, S))
     lo = x.reshape(2, cfg.tileSizeLow, cfg.tileSizeLow, -1)
     assert torch.equal(xi[:, 5, 9, 1:], lo[:, 5 * cfg.tileSizeLow // S, 9 * cfg.tileSizeLow // S, :])
+
+
+@pytest.mark.parametrize("tag", ["gt_first", "gt_second"])
+def test_temporal_critic_oracle_reproduces_the_reference_code(tag):
+    """growing_disc_tempo (:868-923) on three-frame samples [B, S*S, 3]: logits and requested variables against the
+    reference's own function on the TF1 shim; its gradient penalty has one norm per (sample, frame) (:1284)."""
+    c, cfg = _cfg(tag)
+    store = og.VarStore(seed=c["seed"])
+    fr = torch.from_numpy(GOLD[tag + "_frames"]).double()
+    for k, pct in enumerate(c["percentages"]):
+        logits = o8.growing_disc_tempo(fr, pct, og.Context(store, torch.float64), cfg)
+        ref = GOLD["%s_p%d_logits" % (tag, k)]
+        assert np.abs(logits.numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), (tag, pct)
+    want = {k: tuple(v) for k, v in json.loads(str(GOLD[tag + "_vars"]))}
+    assert {k: tuple(v.shape) for k, v in store.values.items()} == want
+    ctx = ot.TrainContext(store, torch.float64)
+    rows = fr.reshape(2, -1)
+    fake = rows * 0.5 + 0.1
+    disc = o8.growing_disc_tempo(rows, 2.4, ctx, cfg)
+    gen = o8.growing_disc_tempo(fake, 2.4, ctx, cfg)
+    lf = torch.tensor([[0.3], [0.8]], dtype=torch.float64)
+    L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc_tempo(t, 2.4, ctx, cfg), rows, fake, lf, frames=3)
+    assert L["grad_norms"].shape == (2, 3) and float(L["grad_penalty"]) > 0
