@@ -25,8 +25,13 @@ Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned
   of the stage's target tiles to the full tile size (:1057-1058), the 1-in-20 empty-density batches of getinput (:1527-1533),
   growing events, the save rule (:2076-2084) and `save` / `load` of `model_%04d.ckpt` + `model_ema_%04d.ckpt` (:1804-1807)
   as TF checkpoint-V2 bundles that multipassGAN-out.py restores.
-Not built: the temporal discriminator / advection (lambda_t), loss scaling (numerically the identity), the feature-layer loss
-(lambda2, 0 in the shipped command), the .uni data loading of the three-frame sequences and the command line.
+* the temporal critic (lambda_t, both shipped commands): `GrowingDisc(kind="tempo")` = growing_disc_tempo (:868-923) on three
+  aligned frames per pixel, its WGAN-GP loss with one gradient norm per (sample, frame) (:1262-1289), the t_adam_* staged
+  optimizers and the generator term kkt * mean(-T(G frames)) (`Trainer8x(lambda_t=...)`, `t_disc_step`, `gen_step(..., x_t, y_t)`).
+Not built: the frame ALIGNMENT in front of the temporal critic (adv_flag 1: advection / tensorResample of the previous and next
+frame with CPU-advected positions, :1178-1210; the steps here take triplets that are already aligned = adv_flag 0), loss scaling
+(numerically the identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni data loading of the three-frame
+sequences and the command line.
 """
 import math
 
@@ -116,8 +121,15 @@ class GrowingDisc:
     pooling anywhere, every stage works at the full tile size (:773-774)."""
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3,
-                 first_nn_arch=True, batch=16, values=None, seed=1, device=0, cx=None, upsampling_mode=2):
+                 first_nn_arch=True, batch=16, values=None, seed=1, device=0, cx=None, upsampling_mode=2, kind="spatial"):
+        """kind "spatial": growing_disc, the conditional critic of (nearest-upsampled low-res density, high-res sample);
+        kind "tempo": growing_disc_tempo (:868-923), the unconditional critic of three aligned frames [B, S*S, 3] -- the same
+        growing structure with the name prefix "t" in scope "tempo-disc" and a 3-channel image."""
         self.cx = cx if cx is not None else _Ctx(device)
+        if kind not in ("spatial", "tempo"):
+            raise ValueError("kind must be 'spatial' or 'tempo'")
+        self.kind = kind
+        self.cimg = 2 if kind == "spatial" else 3   # channels of the image the critic looks at
         if int(upsampling_mode) not in (1, 2, 3):
             raise ValueError("upsampling_mode %r: built are 2 (first network) and 1 / 3 (refinement networks)" % (upsampling_mode,))
         self.pool = int(upsampling_mode) == 2
@@ -128,9 +140,9 @@ class GrowingDisc:
         self.first = bool(first_nn_arch)
         self.ps = ps = ParamSet(self.cx.device)
         cx = self.cx
-        sc = "spatial-disc/"
+        sc, p = ("spatial-disc/", "d") if kind == "spatial" else ("tempo-disc/", "t")
         k = 4 if self.first else int(filterSize)
-        self.c_from = {self.u: _Conv8(cx, ps, sc + "d_cfromDensity%d" % self.u, 1, 2, int(start_fms / self.u), None)}
+        self.c_from = {self.u: _Conv8(cx, ps, sc + "%s_cfromDensity%d" % (p, self.u), 1, self.cimg, int(start_fms / self.u), None)}
         self.blocks = {}
         for j in range(self.stages, 0, -1):
             fms = int(min(start_fms / (2 ** j), max_fms))
@@ -138,18 +150,18 @@ class GrowingDisc:
             up = 2 ** j
             c1 = (fms * 3 if up == 2 else fms * 2) if self.first else fms
             # (firstNNArch 0 declares in_channels = fms for cB although its input has c1 = fms channels: same thing)
-            a = _Conv8(cx, ps, sc + "dBlock%d/d_cA%d" % (up, up), k, fms, c1, "lrelu")
-            b = _Conv8(cx, ps, sc + "dBlock%d/d_cB%d" % (up, up), k, c1, out2, "lrelu")
+            a = _Conv8(cx, ps, sc + "%sBlock%d/%s_cA%d" % (p, up, p, up), k, fms, c1, "lrelu")
+            b = _Conv8(cx, ps, sc + "%sBlock%d/%s_cB%d" % (p, up, p, up), k, c1, out2, "lrelu")
             self.blocks[j] = (a, b, out2)
-            self.c_from[2 ** (j - 1)] = _Conv8(cx, ps, sc + "d_cfromDensity%d" % (2 ** (j - 1)), 1, 2, out2, None)
+            self.c_from[2 ** (j - 1)] = _Conv8(cx, ps, sc + "%s_cfromDensity%d" % (p, 2 ** (j - 1)), 1, self.cimg, out2, None)
         last = self.blocks[1][2]
         if not self.first:
-            self.tail = (_Conv8(cx, ps, sc + "d_cA1", int(filterSize), last, 32, "lrelu"),
-                         _Conv8(cx, ps, sc + "d_cB1", int(filterSize), 32, 4, None))
+            self.tail = (_Conv8(cx, ps, sc + "%s_cA1" % p, int(filterSize), last, 32, "lrelu"),
+                         _Conv8(cx, ps, sc + "%s_cB1" % p, int(filterSize), 32, 4, None))
             last = 4
         self.fc_in = (self.L * self.L if self.pool else self.S * self.S) * last
-        self.fc_w = ps.add(sc + "d_l61/weight", (self.fc_in, 1), np.float32(1.0 / np.sqrt(self.fc_in)))  # gain 1 (:862)
-        self.fc_b = ps.add(sc + "d_l61/bias", (1,))
+        self.fc_w = ps.add(sc + "%s_l61/weight" % p, (self.fc_in, 1), np.float32(1.0 / np.sqrt(self.fc_in)))  # gain 1 (:862)
+        self.fc_b = ps.add(sc + "%s_l61/bias" % p, (1,))
         vals = dict(values) if values else {}
         for name, shape, _, _, _ in ps.specs:
             if name not in vals:
@@ -189,7 +201,7 @@ class GrowingDisc:
             a, b, out2 = self.blocks[j]
             ro = res // 2 if self.pool else res
             if self.pool:
-                inH = self._pool(inH, B, res, res, 2)
+                inH = self._pool(inH, B, res, res, self.cimg)
             x1, sa = a.forward(x_, B, res, res)
             x2, sb = b.forward(x1, B, res, res)
             pooled = self._pool(x2, B, res, res, out2) if self.pool else x2
@@ -251,7 +263,7 @@ class GrowingDisc:
                 cx.call("axpy", dpool, dflat, 1.0, dpool.numel(), cx.st)
             if need_input_grad and self.pool:
                 if dH is not None:  # the deeper level's image gradient comes up through this level's pooling
-                    cx.call("avgpool2_bwd", dH, dHj, B, res // 2, res // 2, 2, 1, cx.st)
+                    cx.call("avgpool2_bwd", dH, dHj, B, res // 2, res // 2, self.cimg, 1, cx.st)
                 dH = dHj
             if self.pool:
                 dx2 = cx.buf(lv["sb"]["y"].shape)
@@ -266,7 +278,7 @@ class GrowingDisc:
         if need_input_grad:
             if self.pool:
                 dxin = cx.buf(sv["xin"].shape)
-                cx.call("avgpool2_bwd", dH, dxin, B, self.S, self.S, 2, 0, cx.st)
+                cx.call("avgpool2_bwd", dH, dxin, B, self.S, self.S, self.cimg, 0, cx.st)
             else:
                 dxin = dxin_np
             self.c_from[self.u].backward(sv["from_u"], dblend, dx=dxin, accumulate=True, param_grads=param_grads)
@@ -276,38 +288,51 @@ class GrowingDisc:
 
     # ------------------------------------------------------------------ gradient penalty
     def gradient_penalty(self, in_low, y_gp, percentage, lam=10.0, target=1.0, loss=None):
-        """WGAN-GP term of :1120-1138 for the interpolated samples y_gp [B, S*S]: adds the penalty to `loss` (device double)
-        and its parameter gradient to ps.gw. Returns the per-sample gradient norms."""
-        cx, ps, B, S = self.cx, self.ps, y_gp.shape[0], self.S
+        """WGAN-GP term of :1120-1138 for the interpolated samples y_gp [B, S*S] of the spatial critic: adds the penalty to
+        `loss` (device double) and its parameter gradient to ps.gw. Returns the gradient norms."""
+        return self._gp(self._input(in_low, y_gp), percentage, lam, target, loss)
+
+    def _gp(self, xin, percentage, lam=10.0, target=1.0, loss=None):
+        """Gradient penalty at the critic input image xin [B,S,S,cimg]. Spatial critic: the gradient w.r.t. channel 1 (the
+        sample; `tf.gradients(d_out_loss, [y_gp_d, x_disc])[0]`). Temporal critic (:1279-1285): the samples are
+        [B, S*S, 3], so reduce_sum(axis=1) gives one norm per (sample, frame)."""
+        cx, ps, B, S = self.cx, self.ps, xin.shape[0], self.S
         loss = self.losses[1:2] if loss is None else loss
-        logits, sv = self.forward(in_low, y_gp, percentage)
+        logits, sv = self.forward_from_input(xin, percentage)
         dl = cx.buf((B, 1))
         dl.fill_(1.0 / B)  # d_out_loss = reduce_mean(d_out)
         dxin = self.backward(sv, dl, need_input_grad=True, param_grads=False)
-        g = cx.buf((B, S * S))
-        cx.call("take_channel", dxin, g, B * S * S, 2, 1, 0, cx.st)  # tf.gradients(..., [y_gp_d, x_disc])[0]
-        v = cx.buf((B, S * S))
-        if self.pool:
-            norms = cx.buf((B,))
-            cx.call("gp_penalty", g, v, loss, norms, B, S * S, float(lam), float(target), cx.st)
+        if self.kind == "tempo":
+            gT, vT, norms = cx.buf((B, 3, S * S)), cx.buf((B, 3, S * S)), cx.buf((B * 3,))
+            capi.transpose3d(cx.h, dxin, gT, (B, S * S, 3), (0, 2, 1), 0.0, cx.st)
+            cx.call("gp_penalty", gT, vT, loss, norms, B * 3, S * S, float(lam), float(target), cx.st)
+            txin = cx.buf((B, S, S, 3))
+            capi.transpose3d(cx.h, vT, txin, (B, 3, S * S), (0, 2, 1), 0.0, cx.st)
         else:
-            # upsampling_mode 1 / 3 keep the samples as [B, S, S, 1] images, so the reference's reduce_sum(axis=1) (:1130) sums
-            # over the image rows only: one norm per (sample, column). Columns become rows for the kernel and back.
-            gT, vT, norms = cx.buf((B, S, S)), cx.buf((B, S, S)), cx.buf((B * S,))
-            capi.transpose3d(cx.h, g, gT, (B, S, S), (0, 2, 1), 0.0, cx.st)
-            cx.call("gp_penalty", gT, vT, loss, norms, B * S, S, float(lam), float(target), cx.st)
-            capi.transpose3d(cx.h, vT, v, (B, S, S), (0, 2, 1), 0.0, cx.st)
-        # tangent pass of (0, v) through the linearised critic; every layer adds wgrad(tangent input, primal delta)
-        txin = cx.zeros((B, S, S, 2))
-        capi.pack_channels(cx.h, [(cx.zeros((B, S * S)), capi.F32, 1, 0, 1, 1, 1), (v, capi.F32, 1, 0, 1, 1, 1)], txin, capi.F32,
-                           2, B, S, S, cx.st)
+            g = cx.buf((B, S * S))
+            cx.call("take_channel", dxin, g, B * S * S, 2, 1, 0, cx.st)  # tf.gradients(..., [y_gp_d, x_disc])[0]
+            v = cx.buf((B, S * S))
+            if self.pool:
+                norms = cx.buf((B,))
+                cx.call("gp_penalty", g, v, loss, norms, B, S * S, float(lam), float(target), cx.st)
+            else:
+                # upsampling_mode 1 / 3 keep the samples as [B, S, S, 1] images, so the reference's reduce_sum(axis=1) (:1130)
+                # sums over the image rows only: one norm per (sample, column). Columns become rows for the kernel and back.
+                gT, vT, norms = cx.buf((B, S, S)), cx.buf((B, S, S)), cx.buf((B * S,))
+                capi.transpose3d(cx.h, g, gT, (B, S, S), (0, 2, 1), 0.0, cx.st)
+                cx.call("gp_penalty", gT, vT, loss, norms, B * S, S, float(lam), float(target), cx.st)
+                capi.transpose3d(cx.h, vT, v, (B, S, S), (0, 2, 1), 0.0, cx.st)
+            # tangent pass of (0, v) through the linearised critic; every layer adds wgrad(tangent input, primal delta)
+            txin = cx.zeros((B, S, S, 2))
+            capi.pack_channels(cx.h, [(cx.zeros((B, S * S)), capi.F32, 1, 0, 1, 1, 1), (v, capi.F32, 1, 0, 1, 1, 1)], txin,
+                               capi.F32, 2, B, S, S, cx.st)
         t_x = self.c_from[self.u].tangent(txin, sv["from_u"])
         tH, res = txin, S
         for j in range(self.stages, 0, -1):
             a, b, out2 = self.blocks[j]
             lv = sv["lvl"][j]
             if self.pool:
-                tH = self._pool(tH, B, res, res, 2)
+                tH = self._pool(tH, B, res, res, self.cimg)
             t1 = a.tangent(t_x, lv["sa"])
             t2 = b.tangent(t1, lv["sb"])
             tp = self._pool(t2, B, res, res, out2) if self.pool else t2
@@ -334,22 +359,40 @@ class GrowingDisc:
         """disc_loss of :1111-1143 (use_wgan_gp, not LSGAN): mean(-D(y)) * weight_dld + mean(D(G)) + eps * mean(D(y)^2) +
         gradient penalty at lerp_factor * y + (1 - lerp_factor) * G. Leaves d loss / d variables in ps.g; returns the loss
         tensor [total, penalty] (device doubles)."""
-        cx, ps = self.cx, self.ps
+        cx = self.cx
         cx.st = torch.cuda.current_stream(cx.device).cuda_stream
+        lf = lerp_factor.to(device=cx.device, dtype=torch.float32).view(-1, 1)
+        y_gp = (lf * y_real + (1.0 - lf) * y_fake).contiguous()
+        return self._critic(self._input(in_low, y_real), self._input(in_low, y_fake), self._input(in_low, y_gp), percentage,
+                            weight_dld, lam, target, eps)
+
+    def critic_step_frames(self, real, fake, percentage, lerp_factor, weight_dld=1.0, lam=10.0, target=1.0, eps=0.001):
+        """t_disc_loss of :1262-1289 for the temporal critic: real / fake [B, S*S*3] rows of three aligned frames per pixel
+        (y_resampled / g_resampled of :1213-1214, 1232-1233), lerp_factor [B, 1] (tf.random_uniform([B, 1, 1]))."""
+        cx, S = self.cx, self.S
+        if self.kind != "tempo":
+            raise ValueError("critic_step_frames is the temporal critic's step")
+        cx.st = torch.cuda.current_stream(cx.device).cuda_stream
+        B = real.shape[0]
+        lf = lerp_factor.to(device=cx.device, dtype=torch.float32).view(-1, 1)
+        gp = (lf * real + (1.0 - lf) * fake).contiguous()
+        return self._critic(real.view(B, S, S, 3), fake.view(B, S, S, 3), gp.view(B, S, S, 3), percentage, weight_dld, lam, target,
+                            eps)
+
+    def _critic(self, x_real, x_fake, x_gp, percentage, weight_dld, lam, target, eps):
+        cx, ps = self.cx, self.ps
         self.refresh()
         ps.gw.zero_()
         self.losses.zero_()
-        disc, sv_r = self.forward(in_low, y_real, percentage)
-        gen, sv_f = self.forward(in_low, y_fake, percentage)
+        disc, sv_r = self.forward_from_input(x_real, percentage)
+        gen, sv_f = self.forward_from_input(x_fake, percentage)
         dl_r, dl_f = cx.buf(disc.shape), cx.buf(gen.shape)
         cx.call("mean_pow", disc, -float(weight_dld), 1, self.losses[0:1], dl_r, disc.numel(), 0, cx.st)
         cx.call("mean_pow", disc, float(eps), 2, self.losses[0:1], dl_r, disc.numel(), 1, cx.st)
         cx.call("mean_pow", gen, 1.0, 1, self.losses[0:1], dl_f, gen.numel(), 0, cx.st)
         self.backward(sv_r, dl_r)
         self.backward(sv_f, dl_f)
-        lf = lerp_factor.to(device=cx.device, dtype=torch.float32).view(-1, 1)
-        y_gp = (lf * y_real + (1.0 - lf) * y_fake).contiguous()
-        self.gradient_penalty(in_low, y_gp, percentage, lam, target, loss=self.losses[1:2])
+        self._gp(x_gp, percentage, lam, target, loss=self.losses[1:2])
         cx.call("mul", ps.g, ps.gw, ps.scale, ps.total, cx.st)  # d/dv = d/dW_eff * wscale
         total = self.losses[0:1] + self.losses[1:2]
         return torch.cat([total, self.losses[1:2]])
@@ -627,7 +670,7 @@ class Trainer8x:
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
                  learning_rate=1e-4, adam_beta1=0.0, adam_beta2=0.99, lambda_l1=1.0, values=None, seed=1, device=0,
-                 upsampling_mode=2, first_nn_arch=None):
+                 upsampling_mode=2, first_nn_arch=None, lambda_t=0.0):
         self.cx = cx = _Ctx(device)
         self.refine = int(upsampling_mode) != 2
         first = (not self.refine) if first_nn_arch is None else bool(first_nn_arch)
@@ -641,6 +684,14 @@ class Trainer8x:
         self.opt_g = StagedAdam(cx, self.gen.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
         self.opt_d = StagedAdam(cx, self.disc.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
         self.ema = WeightEMA(self.gen.ps, 0.999)
+        # temporal critic (lambda_t > 1e-6 = useTempoD, :196-201): growing_disc_tempo on three aligned frames, its own staged
+        # optimizers (t_adam_*, :1318-1330) and the generator term kkt * mean(-T(G frames)) (:1296-1302)
+        self.k_t = float(lambda_t)
+        self.tdisc = self.opt_t = None
+        if self.k_t > 1e-6:
+            self.tdisc = GrowingDisc(tileSizeLow, upRes, n_inputChannels, start_fms, max_fms, filterSize, first, batch, values, seed,
+                                     device, cx=cx, upsampling_mode=upsampling_mode, kind="tempo")
+            self.opt_t = StagedAdam(cx, self.tdisc.ps, [learning_rate] * n, adam_beta1, adam_beta2, n_stages=n)
         self.k_l1 = float(lambda_l1)
         self.learning_rate = float(learning_rate)
         self.losses = torch.zeros(4, dtype=torch.float64, device=cx.device)
@@ -671,7 +722,35 @@ class Trainer8x:
         self.opt_d.step(z)
         return out
 
-    def gen_step(self, x_rows, y_rows, percentage, z):
+    def _frames(self, rows):
+        """[B*3, S*S] rows ordered (sample, frame) -> [B, S*S*3]: `transpose(reshape(., [-1, 3, n_output]), [0, 2, 1])` of
+        :1213-1214 / :1232-1233 (three aligned frames per pixel, the temporal critic's channel axis)."""
+        cx, n = self.cx, self.gen.S * self.gen.S
+        if rows.shape[0] % 3 or rows.shape[1] != n:
+            raise ValueError("temporal batches are 3 consecutive frames per sample: [B*3, S*S] rows")
+        B = rows.shape[0] // 3
+        out = cx.buf((B, n * 3))
+        capi.transpose3d(cx.h, rows, out, (B, 3, n), (0, 2, 1), 0.0, cx.st)
+        return out
+
+    def t_disc_step(self, x_t_rows, y_t_rows, percentage, z, lerp_factor):
+        """One step of t_disc_optimizer[z] (:2001-2013) on frame triplets that are ALREADY aligned (adv_flag 0, :1229-1231: the
+        advection / tensorResample in front of the critic is not built): x_t_rows [B*3, L*L*C], y_t_rows [B*3, S*S(*2)] ordered
+        (sample, frame)."""
+        if self.tdisc is None:
+            raise ValueError("lambda_t is 0: no temporal critic")
+        cx = self.cx
+        cx.st = torch.cuda.current_stream(cx.device).cuda_stream
+        self.gen.refresh()
+        x_in, y_in = self._inputs(x_t_rows, y_t_rows)
+        gen_ts, _ = self.gen.forward(x_in, percentage)
+        out = self.tdisc.critic_step_frames(self._frames(y_in), self._frames(gen_ts), percentage, lerp_factor)
+        self.opt_t.step(z)
+        return out
+
+    def gen_step(self, x_rows, y_rows, percentage, z, x_t_rows=None, y_t_rows=None):
+        """gen_optimizer[z] (:2015-2043) on gen_loss_complete = g_loss_d + kk * l1 [+ kkt * g_loss_t on the temporal batch].
+        Returns the device doubles [g_loss_d, kk * l1, kkt * g_loss_t, 0]."""
         cx, g, d = self.cx, self.gen, self.disc
         cx.st = torch.cuda.current_stream(cx.device).cuda_stream
         g.refresh()
@@ -688,6 +767,21 @@ class Trainer8x:
         cx.call("l1_mean", y_in, gen_y, self.k_l1, self.losses[1:2], dgen, gen_y.numel(), 0, cx.st)  # lambda * mean|y - G| :1099,1145
         cx.call("take_channel", dxin, dgen, gen_y.numel(), 2, 1, 1, cx.st)
         g.backward(gsv, dgen)
+        if self.tdisc is not None and x_t_rows is not None:
+            # + kkt * mean(-T(G(x_t))) (:1296-1302): a second pass of the same generator on the frame triplets; its parameter
+            # gradients accumulate onto those of the spatial terms
+            t = self.tdisc
+            t.refresh()
+            x_in_t, _ = self._inputs(x_t_rows, y_t_rows)
+            gen_ts, gsv_t = g.forward(x_in_t, percentage)
+            B, S = gen_ts.shape[0] // 3, g.S
+            logits_t, tsv = t.forward_from_input(self._frames(gen_ts).view(B, S, S, 3), percentage)
+            dl_t = cx.buf(logits_t.shape)
+            cx.call("mean_pow", logits_t, -self.k_t, 1, self.losses[2:3], dl_t, logits_t.numel(), 0, cx.st)
+            dx_t = t.backward(tsv, dl_t, need_input_grad=True, param_grads=False)
+            dgen_t = cx.buf(gen_ts.shape)
+            capi.transpose3d(cx.h, dx_t, dgen_t, (B, S * S, 3), (0, 2, 1), 0.0, cx.st)
+            g.backward(gsv_t, dgen_t)
         cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
         self.opt_g.step(z)
         self.ema.update(self.opt_g.state[z]["mask"])
@@ -711,14 +805,18 @@ class Trainer8x:
         return out
 
     def train(self, batches, schedule, discRuns=1, genRuns=1, lambda_f=1.0, add_adj_idcs=True, zero_density=True, save_dir=None,
-              saveInterval=200, alwaysSave=True, on_grow=None, log=None, log_interval=0, lerp_seed=0, max_iters=None):
+              saveInterval=200, alwaysSave=True, on_grow=None, log=None, log_interval=0, lerp_seed=0, max_iters=None,
+              tempo_batches=None):
         """The training loop of GAN/multipassGAN-8x.py:1898-2089 (spatial part). `batches(currentUpres)` returns one batch
         (x_rows [B, L*L*C], y_rows [B, (L*currentUpres)^2]) of device fp32 rows (getinput, :1497); `schedule` is a
         schedule8x.GrowthSchedule. Per iteration: discRuns critic steps, genRuns generator steps (each on a fresh batch) with
         the optimizers of the stage's index, blend value and decayed learning rate; at a growing event the model is saved and
         `on_grow(new_upres)` is called (the reference re-loads its data there, :1916-1963); the model is saved when
         `(disc_cost + gen_cost < lastCost or alwaysSave) and lastSave >= saveInterval` (:2076-2084).  The critic's
-        interpolation factors are torch's uniform numbers (TF's random stream is not reproducible).  Returns a list of
+        interpolation factors are torch's uniform numbers (TF's random stream is not reproducible).  With lambda_t > 0 and
+        `tempo_batches(currentUpres)` -> (x_t rows [B*3, ...], y_t rows [B*3, ...]) of ALIGNED frame triplets (getTempoinput
+        with adv_flag 0), every iteration also runs discRuns temporal-critic steps (:2001-2013) and the generator step carries
+        the temporal term.  Returns a list of
         (it, disc_loss, g_loss_d, l1) at the logged iterations (log_interval 0: only the last iteration is read back)."""
         cx = self.cx
         gen_rng = torch.Generator(device=cx.device)
@@ -748,15 +846,27 @@ class Trainer8x:
             lrs_g, lrs_d = schedule8x.learning_rates(self.learning_rate, st.lrgs, schedule.decayIter, schedule.decayLR,
                                                      self.gen.stages)
             self.opt_g.lrs, self.opt_d.lrs = lrs_g, lrs_d
+            if self.opt_t is not None:
+                self.opt_t.lrs = list(lrs_d)                                        # learning_rates_t = the same decay (:1005-1006)
             for _ in range(discRuns):
                 xs, ys = batch(st.currentUpres)
                 lf = torch.rand((xs.shape[0], 1), generator=gen_rng, device=cx.device)
                 d_loss = self.disc_step(xs, ys, st.percentage, st.index, lf)
+            tempo = self.tdisc is not None and tempo_batches is not None
+            if tempo:
+                for _ in range(discRuns):
+                    xt, yt = tempo_batches(st.currentUpres)
+                    lf = torch.rand((xt.shape[0] // 3, 1), generator=gen_rng, device=cx.device)
+                    self.t_disc_step(xt, self._tempo_targets(yt), st.percentage, st.index, lf)
             for _ in range(genRuns):
                 xs, ys = batch(st.currentUpres)
                 kkin = lambda_f * kkin                                              # :2019
                 self.k_l1 = kkin
-                g_loss = self.gen_step(xs, ys, st.percentage, st.index).clone()
+                xt = yt = None
+                if tempo:
+                    xt, yt = tempo_batches(st.currentUpres)
+                    yt = self._tempo_targets(yt)
+                g_loss = self.gen_step(xs, ys, st.percentage, st.index, xt, yt).clone()
             done += 1
             read = (log_interval and (st.it + 1) % log_interval == 0) or done == n_total or not alwaysSave
             if read:
@@ -776,10 +886,21 @@ class Trainer8x:
                 last_save += 1
         return history
 
+    def _tempo_targets(self, y_t_rows):
+        return self.target_rows(y_t_rows)
+
+    def _optimizers(self):
+        out = [("g", self.opt_g, self.gen.ps), ("d", self.opt_d, self.disc.ps)]
+        if self.tdisc is not None:
+            out.append(("t", self.opt_t, self.tdisc.ps))
+        return out
+
     # ------------------------------------------------------------------ checkpoints
     def values(self):
         out = self.gen.ps.export()
         out.update(self.disc.ps.export())
+        if self.tdisc is not None:
+            out.update(self.tdisc.ps.export())
         return out
 
     def save(self, test_path):
@@ -793,7 +914,7 @@ class Trainer8x:
         ema = dict(vals)
         ema.update(self.ema.export())
         full = dict(vals)
-        for tag, opt, ps in (("g", self.opt_g, self.gen.ps), ("d", self.opt_d, self.disc.ps)):
+        for tag, opt, ps in self._optimizers():
             for z, st in enumerate(opt.state):
                 if st["t"] == 0:
                     continue
@@ -816,7 +937,7 @@ class Trainer8x:
         from . import tfckpt
         full = tfckpt.read_checkpoint(os.path.join(test_path, "model_%04d.ckpt" % no), verify_data=True)
         ema = tfckpt.read_checkpoint(os.path.join(test_path, "model_ema_%04d.ckpt" % no), verify_data=True)
-        for tag, opt, ps in (("g", self.opt_g, self.gen.ps), ("d", self.opt_d, self.disc.ps)):
+        for tag, opt, ps in self._optimizers():
             host = ps.v.cpu().numpy()
             for name, shape, off, n, _ in ps.specs:
                 host[off:off + n] = np.asarray(full[name], np.float32).reshape(-1)
