@@ -613,3 +613,43 @@ def test_trainer8x_temporal_steps_track_the_oracle(tag):
             assert diff.max() < 2.1e-3, n                      # a flipped sign is 2 * lr, never more
             checked, total = checked + int(m.sum()), total + m.size
     assert checked > 0.5 * total, (checked, total)
+
+
+def test_training_loop_with_the_temporal_critic_and_checkpoints(tmp_path):
+    """Trainer8x.train with lambda_t > 0 and aligned frame triplets: the temporal critic trains with its own staged
+    optimizers, its variables and moments travel in the checkpoint, a restored trainer continues like the original."""
+    from mpgan_b200 import schedule8x as S8
+    np.random.seed(2)
+    tr = t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2, learning_rate=1e-3, seed=7, lambda_t=1.0)
+    dev = tr.cx.device
+    batches, seen = _batches(dev)
+    g = torch.Generator(device="cpu").manual_seed(8)
+    tseen = []
+
+    def tempo_batches(upres):
+        tseen.append(upres)
+        return torch.rand((6, 4 * 4 * 6), generator=g).to(dev), torch.rand((6, (4 * upres) ** 2), generator=g).to(dev)
+
+    t0 = tr.tdisc.ps.export()
+    d = str(tmp_path / "test_0007")
+    hist = tr.train(batches, S8.GrowthSchedule(stageIter=1, decayIter=1), tempo_batches=tempo_batches, save_dir=d, saveInterval=100,
+                    log_interval=1)
+    assert len(hist) == 7 and all(np.isfinite(h[1:]).all() for h in hist)
+    assert tseen == [2, 2, 2, 2, 4, 4, 4, 4, 8, 8, 8, 8, 8, 8] and [st["t"] for st in tr.opt_t.state] == [2, 2, 3]
+    t1 = tr.tdisc.ps.export()
+    assert any(not np.array_equal(t0[n], t1[n]) for n in t0)
+    no = tr.save(d)
+    tr2 = t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2, learning_rate=1e-3, seed=99, lambda_t=1.0)
+    tr2.load(d, no)
+    xs, ys = torch.rand((2, 96), device=dev), torch.rand((2, 1024), device=dev)
+    xt, yt = torch.rand((6, 96), device=dev), torch.rand((6, 1024), device=dev)
+    lf = torch.tensor([[0.25], [0.5]])
+    for t in (tr, tr2):
+        t.opt_g.lrs = t.opt_d.lrs = t.opt_t.lrs = [1e-3] * 3
+        t.t_disc_step(xt, yt, 2.5, 2, lf)
+        t.gen_step(xs, ys, 2.5, 2, xt, yt)
+    a, b = tr.values(), tr2.values()
+    assert any(n.startswith("tempo-disc/") for n in a)
+    assert max(float(np.abs(a[n] - b[n]).max()) for n in a) < 2e-6
+    with pytest.raises(ValueError):
+        t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2).t_disc_step(xt, yt, 2.5, 2, lf)
