@@ -112,6 +112,25 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
         return gan.y(), feats
 
 
+def tensor_resample(value, pos):
+    """tensorResample :545-594 for 2-D data: value [B, H, W, C] sampled at pos [B, H, W, 2] (pos[..., 0] along H, pos[..., 1]
+    along W, cell centres at i + 0.5): bilinear weights 1 - |pos - 0.5 - index| over floor / floor + 1, indices are NOT clamped
+    (the `if 0:` block), out-of-range corners contribute 0 (what tf.gather_nd does on the GPU).  Differentiable in `value`."""
+    B, H, W, C = value.shape
+    q = pos - 0.5
+    f = torch.floor(q).long()
+    out = torch.zeros(pos.shape[:-1] + (C,), dtype=value.dtype)
+    bidx = torch.arange(B).view(B, 1, 1).expand(pos.shape[:-1])
+    for c0 in (0, 1):
+        for c1 in (0, 1):
+            i0, i1 = f[..., 0] + c0, f[..., 1] + c1
+            w = (1.0 - (q[..., 0] - i0.to(q.dtype)).abs()) * (1.0 - (q[..., 1] - i1.to(q.dtype)).abs())
+            ok = (i0 >= 0) & (i0 < H) & (i1 >= 0) & (i1 < W)
+            v = value[bidx, i0.clamp(0, H - 1), i1.clamp(0, W - 1)]
+            out = out + v * (w * ok.to(q.dtype)).unsqueeze(-1)
+    return out
+
+
 def growing_disc_tempo(frames, percentage, ctx, cfg):
     """growing_disc_tempo :868-923 (useVelInTDisc 0, no batch norm / gDrop / minibatch stddev): the unconditional critic of
     three aligned frames. frames [B, S*S, 3] (what `tf.transpose(reshape(., [-1, 3, n_output]), [0, 2, 1])` of :1213-1214

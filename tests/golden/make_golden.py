@@ -422,6 +422,19 @@ def make_growdisc_fixtures():
     # the temporal critic of both shipped training commands (lambda_t 1.0): first network / refinement network
     run_tempo("gt_first", 86, 4, 8, 32, 32, True, (0.4, 1.3, 2.75, 3.0))
     run_tempo("gt_second", 87, 2, 8, 32, 32, False, (0.4, 1.3, 2.75, 3.0), filterSize=5, upsampling_mode=1)
+    # tensorResample (:545-594): the bilinear re-sampling of a frame at CPU-advected positions in front of the temporal critic
+    rcode = ref_functions(os.path.join(REF, "GAN", "multipassGAN-8x.py"), ["tensorResample"])
+    rns = dict(tf=tfs, np=np, pow=pow, int=int, bool=bool, range=range, len=len)
+    exec(rcode, rns)
+    Bn, Hn = 3, 8
+    val = rng.random((Bn, Hn, Hn, 2), dtype=np.float32)
+    base = np.stack(np.meshgrid(np.arange(Hn) + 0.5, np.arange(Hn) + 0.5, indexing="ij"), axis=-1)[None]
+    posn = (base + rng.normal(0.0, 1.2, (Bn, Hn, Hn, 2))).astype(np.float32)      # some positions leave the tile
+    fixtures["resample_value"], fixtures["resample_pos"] = val, posn
+    fixtures["resample_out"] = rns["tensorResample"](tfs.T(val), tfs.T(posn)).a
+    ident = rns["tensorResample"](tfs.T(val), tfs.T(np.broadcast_to(base, (Bn, Hn, Hn, 2)).copy())).a
+    assert np.abs(ident - val).max() < 1e-12            # cell centres reproduce the values
+    print("resample:", fixtures["resample_out"].shape, float(np.abs(fixtures["resample_out"]).max()))
     np.savez_compressed(os.path.join(HERE, "growdisc.npz"), **fixtures)
     print("growdisc.npz written:", len(fixtures), "arrays")
 

@@ -307,3 +307,65 @@ def _avg_pool(x, ksize, strides, padding):
 
 
 nn.avg_pool = _avg_pool
+
+
+# ---- ops used by tensorResample (GAN/multipassGAN-8x.py:545-594): index arithmetic + tf.gather_nd
+int32 = "int32"
+float32 = "float32"
+
+
+def _cmp(self, o):
+    return T(self.a > _v(o))
+
+
+def _and(self, o):
+    return T(np.logical_and(self.a != 0, np.asarray(_v(o)) != 0))
+
+
+T.__gt__ = _cmp
+T.__and__ = _and
+T.__rsub__ = lambda self, o: T(_v(o) - self.a)
+
+
+@contextlib.contextmanager
+def name_scope(name):
+    yield name
+
+
+def floor(x):
+    return T(np.floor(_v(x)))
+
+
+def ones_like(x, dtype=None):
+    return T(np.ones_like(_v(x)))
+
+
+def where(cond, a, b):
+    return T(np.where(_v(cond) != 0, _v(a), _v(b)))
+
+
+def abs(x):  # noqa: A001
+    return T(np.abs(_v(x)))
+
+
+def reduce_prod(x, axis=None, keep_dims=False, keepdims=False):
+    return T(np.prod(_v(x), axis=axis, keepdims=keep_dims or keepdims))
+
+
+def cumsum(x, axis=0, exclusive=False):
+    a = _v(x)
+    c = np.cumsum(a, axis=axis)
+    return T(c - a if exclusive else c)
+
+
+def gather_nd(params, indices):
+    """tf.gather_nd with full-rank-minus-channels indices [..., k]: params[idx[..., 0], ..., idx[..., k-1]] (trailing params
+    axes are kept). Out-of-range indices yield 0, which is what the TensorFlow GPU kernel does (the CPU kernel raises)."""
+    p, idx = _v(params), np.asarray(_v(indices)).astype(np.int64)
+    k = idx.shape[-1]
+    ok = np.ones(idx.shape[:-1], bool)
+    for d in range(k):
+        ok &= (idx[..., d] >= 0) & (idx[..., d] < p.shape[d])
+    safe = np.where(ok[..., None], idx, 0)
+    out = p[tuple(safe[..., d] for d in range(k))]
+    return T(out * ok.reshape(ok.shape + (1,) * (out.ndim - ok.ndim)))

@@ -148,3 +148,13 @@ def test_temporal_critic_oracle_reproduces_the_reference_code(tag):
     lf = torch.tensor([[0.3], [0.8]], dtype=torch.float64)
     L = o8.wgan_gp_losses(disc, gen, lambda t: o8.growing_disc_tempo(t, 2.4, ctx, cfg), rows, fake, lf, frames=3)
     assert L["grad_norms"].shape == (2, 3) and float(L["grad_penalty"]) > 0
+
+
+def test_tensor_resample_oracle_reproduces_the_reference_code():
+    """tensorResample (:545-594) executed on the shim vs the torch restatement, incl. positions that leave the tile."""
+    val = torch.from_numpy(GOLD["resample_value"]).double()
+    pos = torch.from_numpy(GOLD["resample_pos"]).double()
+    out = o8.tensor_resample(val, pos)
+    assert np.abs(out.numpy() - GOLD["resample_out"]).max() < 1e-12
+    q = (pos - 0.5).floor()
+    assert bool(((q < 0) | (q + 1 > 7)).any())          # the vectors do exercise out-of-range corners
