@@ -362,6 +362,13 @@ int mpg_train_fc_fwd(mpg_handle h, const float* x, const float* w, const float* 
                      void* stream);
 int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* dy, float* dx, float* dw,
                      float* dbias, int rows, int nin, void* stream);
+/* tensorResample of the 8x trainer (GAN/multipassGAN-8x.py:545-594; used on the frame triplets in front of the temporal
+ * critic, :1195-1197, 1241-1242): out[n,hh,ww,c] = value re-sampled bilinearly at pos[n,hh,ww,2] - 0.5 (pos[...,0] along hh),
+ * no index clamping, out-of-range cells contribute 0; _bwd scatter-adds dout into dvalue (zero it first) */
+int mpg_train_resample_fwd(mpg_handle h, const float* value, const float* pos, float* out, int n, int hh, int ww, int c,
+                           void* stream);
+int mpg_train_resample_bwd(mpg_handle h, const float* dout, const float* pos, float* dvalue, int n, int hh, int ww, int c,
+                           void* stream);
 int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long npix, int cstride, int c,
                            int accumulate, void* stream);
 

@@ -149,6 +149,8 @@ def lib():
     L.mpg_train_fc_fwd.argtypes = [vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_fc_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip, vp]
     L.mpg_train_take_channel.argtypes = [vp, vp, vp, ll, ip, ip, ip, vp]
+    L.mpg_train_resample_fwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.mpg_train_resample_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp]
     L.mpg_train_avgpool2_fwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp]
     L.mpg_train_avgpool2_bwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
     L.mpg_train_lerp.argtypes = [vp, vp, vp, vp, fl, ll, vp]

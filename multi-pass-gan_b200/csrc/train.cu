@@ -969,6 +969,37 @@ __global__ void __launch_bounds__(256) take_channel_kernel(const float* in, floa
     out[e] = (accumulate ? out[e] : 0.0f) + in[e * cstride + c];
 }
 
+// tensorResample (GAN/multipassGAN-8x.py:545-594) for 2-D frames: out[b,y,x,:] = sum over the 4 cells around pos - 0.5 of
+// (1 - |dy|)(1 - |dx|) * value[b, iy, ix, :]; pos[..., 0] runs along H, pos[..., 1] along W; indices are not clamped and
+// out-of-range cells contribute nothing (tf.gather_nd on the GPU). BWD = 1: dvalue[b, iy, ix, :] += w * dout[b, y, x, :].
+template <int BWD>
+__global__ void __launch_bounds__(256) resample_kernel(const float* value, const float* pos, float* out, float* dvalue,
+                                                        const float* dout, int n, int hh, int ww, int c) {
+  const long long total = static_cast<long long>(n) * hh * ww;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const long long b = e / (static_cast<long long>(hh) * ww);
+    const float q0 = pos[2 * e] - 0.5f, q1 = pos[2 * e + 1] - 0.5f;
+    const float f0 = floorf(q0), f1 = floorf(q1);
+    const int i0 = static_cast<int>(f0), i1 = static_cast<int>(f1);
+    for (int ch = 0; ch < c; ++ch) {
+      float acc = 0.0f;
+      const float g = BWD ? dout[e * c + ch] : 0.0f;
+#pragma unroll
+      for (int c0 = 0; c0 < 2; ++c0)
+#pragma unroll
+        for (int c1 = 0; c1 < 2; ++c1) {
+          const int y = i0 + c0, x = i1 + c1;
+          if (y < 0 || y >= hh || x < 0 || x >= ww) continue;
+          const float w = (1.0f - fabsf(q0 - static_cast<float>(y))) * (1.0f - fabsf(q1 - static_cast<float>(x)));
+          const long long src = ((b * hh + y) * ww + x) * c + ch;
+          if (BWD) atomicAdd(&dvalue[src], w * g);
+          else acc = fmaf(w, value[src], acc);
+        }
+      if (!BWD) out[e * c + ch] = acc;
+    }
+  }
+}
+
 inline int grid_for(long long total, int sm) {
   long long b = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm) * 8;
@@ -1354,6 +1385,28 @@ int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long 
                            void* stream) {
   MPG_CHECK_ARG(h && in && out && npix > 0 && c >= 0 && c < cstride, "mpg_train_take_channel: bad argument");
   take_channel_kernel<<<grid_for(npix, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, npix, cstride, c, accumulate);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+
+/* tensorResample (GAN/multipassGAN-8x.py:545-594, 2-D): out[n,hh,ww,c] = value re-sampled at pos[n,hh,ww,2] (bilinear around
+ * pos - 0.5, no clamping, out-of-range cells contribute 0) */
+int mpg_train_resample_fwd(mpg_handle h, const float* value, const float* pos, float* out, int n, int hh, int ww, int c,
+                           void* stream) {
+  MPG_CHECK_ARG(h && value && pos && out && n > 0 && hh > 0 && ww > 0 && c > 0, "mpg_train_resample_fwd: bad argument");
+  const long long total = static_cast<long long>(n) * hh * ww;
+  resample_kernel<0><<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(value, pos, out, nullptr, nullptr,
+                                                                                              n, hh, ww, c);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
+/* dvalue[n,hh,ww,c] += gradient of mpg_train_resample_fwd w.r.t. value given dout (scatter-add; zero dvalue first) */
+int mpg_train_resample_bwd(mpg_handle h, const float* dout, const float* pos, float* dvalue, int n, int hh, int ww, int c,
+                           void* stream) {
+  MPG_CHECK_ARG(h && dout && pos && dvalue && n > 0 && hh > 0 && ww > 0 && c > 0, "mpg_train_resample_bwd: bad argument");
+  const long long total = static_cast<long long>(n) * hh * ww;
+  resample_kernel<1><<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(nullptr, pos, nullptr, dvalue, dout,
+                                                                                              n, hh, ww, c);
   MPG_CUDA(cudaGetLastError());
   return MPG_OK;
 }

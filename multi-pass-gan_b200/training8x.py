@@ -28,10 +28,11 @@ Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned
 * the temporal critic (lambda_t, both shipped commands): `GrowingDisc(kind="tempo")` = growing_disc_tempo (:868-923) on three
   aligned frames per pixel, its WGAN-GP loss with one gradient norm per (sample, frame) (:1262-1289), the t_adam_* staged
   optimizers and the generator term kkt * mean(-T(G frames)) (`Trainer8x(lambda_t=...)`, `t_disc_step`, `gen_step(..., x_t, y_t)`).
-Not built: the frame ALIGNMENT in front of the temporal critic (adv_flag 1: advection / tensorResample of the previous and next
-frame with CPU-advected positions, :1178-1210; the steps here take triplets that are already aligned = adv_flag 0), loss scaling
-(numerically the identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni data loading of the three-frame
-sequences and the command line.
+  Frame alignment of the shipped commands (adv_flag 1, adv_mode 0): `tensorResample` (:545-594) of the generated and the target
+  frames at given positions (`y_pos`; kernels mpg_train_resample_fwd/_bwd), at the full tile size.
+Not built: getTempoinput (the CPU advection that PRODUCES those positions, tilecreator_t.py) and the in-graph advection of
+adv_mode 1 / 2, loss scaling (numerically the identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni
+data loading of the three-frame sequences and the command line.
 """
 import math
 
@@ -733,10 +734,23 @@ class Trainer8x:
         capi.transpose3d(cx.h, rows, out, (B, 3, n), (0, 2, 1), 0.0, cx.st)
         return out
 
-    def t_disc_step(self, x_t_rows, y_t_rows, percentage, z, lerp_factor):
-        """One step of t_disc_optimizer[z] (:2001-2013) on frame triplets that are ALREADY aligned (adv_flag 0, :1229-1231: the
-        advection / tensorResample in front of the critic is not built): x_t_rows [B*3, L*L*C], y_t_rows [B*3, S*S(*2)] ordered
-        (sample, frame)."""
+    def _align(self, rows, y_pos):
+        """tensorResample (:545-594) of the frames [B*3, S*S] at the advected positions y_pos [B*3, S*S*2] (adv_flag 1,
+        adv_mode 0: :1195-1197 for the generated frames, :1241-1242 for the targets). y_pos None = frames already aligned
+        (adv_flag 0). Positions are taken at the full tile size: the reference re-samples at `2 ** ceil(percentage) * tileSize`
+        and resizes back (:1192-1204), which is the full size for the refinement networks and the first network's last stage."""
+        if y_pos is None:
+            return rows
+        cx, S, n = self.cx, self.gen.S, rows.shape[0]
+        if tuple(y_pos.shape) != (n, S * S * 2):
+            raise ValueError("y_pos must be [B*3, S*S*2] positions at the full tile size (got %s)" % (tuple(y_pos.shape),))
+        out = cx.buf(rows.shape)
+        cx.call("resample_fwd", rows, y_pos, out, n, S, S, 1, cx.st)
+        return out
+
+    def t_disc_step(self, x_t_rows, y_t_rows, percentage, z, lerp_factor, y_pos=None):
+        """One step of t_disc_optimizer[z] (:2001-2013) on frame triplets: x_t_rows [B*3, L*L*C], y_t_rows [B*3, S*S(*2)]
+        ordered (sample, frame); y_pos: see _align (None = the triplets are already aligned, adv_flag 0 :1229-1231)."""
         if self.tdisc is None:
             raise ValueError("lambda_t is 0: no temporal critic")
         cx = self.cx
@@ -744,11 +758,12 @@ class Trainer8x:
         self.gen.refresh()
         x_in, y_in = self._inputs(x_t_rows, y_t_rows)
         gen_ts, _ = self.gen.forward(x_in, percentage)
-        out = self.tdisc.critic_step_frames(self._frames(y_in), self._frames(gen_ts), percentage, lerp_factor)
+        out = self.tdisc.critic_step_frames(self._frames(self._align(y_in.contiguous(), y_pos)),
+                                            self._frames(self._align(gen_ts, y_pos)), percentage, lerp_factor)
         self.opt_t.step(z)
         return out
 
-    def gen_step(self, x_rows, y_rows, percentage, z, x_t_rows=None, y_t_rows=None):
+    def gen_step(self, x_rows, y_rows, percentage, z, x_t_rows=None, y_t_rows=None, y_pos=None):
         """gen_optimizer[z] (:2015-2043) on gen_loss_complete = g_loss_d + kk * l1 [+ kkt * g_loss_t on the temporal batch].
         Returns the device doubles [g_loss_d, kk * l1, kkt * g_loss_t, 0]."""
         cx, g, d = self.cx, self.gen, self.disc
@@ -775,12 +790,16 @@ class Trainer8x:
             x_in_t, _ = self._inputs(x_t_rows, y_t_rows)
             gen_ts, gsv_t = g.forward(x_in_t, percentage)
             B, S = gen_ts.shape[0] // 3, g.S
-            logits_t, tsv = t.forward_from_input(self._frames(gen_ts).view(B, S, S, 3), percentage)
+            logits_t, tsv = t.forward_from_input(self._frames(self._align(gen_ts, y_pos)).view(B, S, S, 3), percentage)
             dl_t = cx.buf(logits_t.shape)
             cx.call("mean_pow", logits_t, -self.k_t, 1, self.losses[2:3], dl_t, logits_t.numel(), 0, cx.st)
             dx_t = t.backward(tsv, dl_t, need_input_grad=True, param_grads=False)
             dgen_t = cx.buf(gen_ts.shape)
             capi.transpose3d(cx.h, dx_t, dgen_t, (B, S * S, 3), (0, 2, 1), 0.0, cx.st)
+            if y_pos is not None:  # back through tensorResample: scatter-add onto the un-aligned frames
+                d_un = cx.zeros(gen_ts.shape)
+                cx.call("resample_bwd", dgen_t, y_pos, d_un, gen_ts.shape[0], S, S, 1, cx.st)
+                dgen_t = d_un
             g.backward(gsv_t, dgen_t)
         cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
         self.opt_g.step(z)
@@ -814,8 +833,8 @@ class Trainer8x:
         `on_grow(new_upres)` is called (the reference re-loads its data there, :1916-1963); the model is saved when
         `(disc_cost + gen_cost < lastCost or alwaysSave) and lastSave >= saveInterval` (:2076-2084).  The critic's
         interpolation factors are torch's uniform numbers (TF's random stream is not reproducible).  With lambda_t > 0 and
-        `tempo_batches(currentUpres)` -> (x_t rows [B*3, ...], y_t rows [B*3, ...]) of ALIGNED frame triplets (getTempoinput
-        with adv_flag 0), every iteration also runs discRuns temporal-critic steps (:2001-2013) and the generator step carries
+        `tempo_batches(currentUpres)` -> (x_t rows [B*3, ...], y_t rows [B*3, ...][, y_pos [B*3, S*S*2]]) frame triplets
+        (getTempoinput; without y_pos they are taken as aligned, adv_flag 0), every iteration also runs discRuns temporal-critic steps (:2001-2013) and the generator step carries
         the temporal term.  Returns a list of
         (it, disc_loss, g_loss_d, l1) at the logged iterations (log_interval 0: only the last iteration is read back)."""
         cx = self.cx
@@ -855,18 +874,18 @@ class Trainer8x:
             tempo = self.tdisc is not None and tempo_batches is not None
             if tempo:
                 for _ in range(discRuns):
-                    xt, yt = tempo_batches(st.currentUpres)
+                    xt, yt, pos = (tuple(tempo_batches(st.currentUpres)) + (None,))[:3]
                     lf = torch.rand((xt.shape[0] // 3, 1), generator=gen_rng, device=cx.device)
-                    self.t_disc_step(xt, self._tempo_targets(yt), st.percentage, st.index, lf)
+                    self.t_disc_step(xt, self._tempo_targets(yt), st.percentage, st.index, lf, pos)
             for _ in range(genRuns):
                 xs, ys = batch(st.currentUpres)
                 kkin = lambda_f * kkin                                              # :2019
                 self.k_l1 = kkin
-                xt = yt = None
+                xt = yt = pos = None
                 if tempo:
-                    xt, yt = tempo_batches(st.currentUpres)
+                    xt, yt, pos = (tuple(tempo_batches(st.currentUpres)) + (None,))[:3]
                     yt = self._tempo_targets(yt)
-                g_loss = self.gen_step(xs, ys, st.percentage, st.index, xt, yt).clone()
+                g_loss = self.gen_step(xs, ys, st.percentage, st.index, xt, yt, pos).clone()
             done += 1
             read = (log_interval and (st.it + 1) % log_interval == 0) or done == n_total or not alwaysSave
             if read:

@@ -497,8 +497,27 @@ def test_temporal_critic_wgan_gp_loss_and_gradients_match_double_backward(tag, p
     assert worst > 0.0
 
 
-@pytest.mark.parametrize("tag", ["gg_first", "gg_second"])
-def test_trainer8x_temporal_steps_track_the_oracle(tag):
+def test_tensor_resample_kernels_match_the_reference_vectors_and_autograd():
+    """mpg_train_resample_fwd against the reference's own tensorResample (vectors incl. out-of-range positions), _bwd against
+    autograd of the torch restatement."""
+    from mpgan_b200 import capi
+    val, pos = GOLD["resample_value"], GOLD["resample_pos"]
+    n, hh, ww, c = val.shape
+    h = capi.default_handle(0)
+    v, p = torch.from_numpy(val).cuda(), torch.from_numpy(pos).cuda()
+    out = torch.empty_like(v)
+    capi.train_call("resample_fwd", h, v, p, out, n, hh, ww, c, 0)
+    assert np.abs(out.cpu().numpy() - GOLD["resample_out"]).max() < 1e-5
+    vv = torch.from_numpy(val).double().requires_grad_(True)
+    wgt = torch.cos(torch.arange(val.size, dtype=torch.float64) * 0.61).view(val.shape)
+    (o8.tensor_resample(vv, torch.from_numpy(pos).double()) * wgt).sum().backward()
+    dv = torch.zeros_like(v)
+    capi.train_call("resample_bwd", h, wgt.float().cuda().contiguous(), p, dv, n, hh, ww, c, 0)
+    assert np.abs(dv.cpu().numpy() - vv.grad.numpy()).max() < 1e-5
+
+
+@pytest.mark.parametrize("tag,advected", [("gg_first", False), ("gg_second", False), ("gg_first", True)])
+def test_trainer8x_temporal_steps_track_the_oracle(tag, advected):
     """lambda_t 1.0 as in both shipped commands (aligned triplets, adv_flag 0): one temporal-critic step (:2001-2013) and one
     generator step whose loss carries kkt * mean(-T(G(x_t))) next to the spatial terms (:2015-2043), against the fp64 oracle
     with the same staged Adam: losses and every variable of the three networks."""
@@ -520,7 +539,16 @@ def test_trainer8x_temporal_steps_track_the_oracle(tag):
     xt_in, yt_in = conv(xt, yt)
     side = None if mode == 2 else S
 
+    # advected: adv_flag 1 / adv_mode 0 of the shipped commands -- both the generated and the target frames are re-sampled at
+    # given positions (tensorResample, :1195-1197, 1241-1242) before they become the critic's three channels
+    pos = None
+    if advected:
+        base = np.stack(np.meshgrid(np.arange(S) + 0.5, np.arange(S) + 0.5, indexing="ij"), axis=-1)[None]
+        pos = torch.from_numpy((base + rng.normal(0.0, 0.8, (6, S, S, 2))).reshape(6, -1)).double()
+
     def frames(rows):                                                    # :1213-1214
+        if pos is not None:
+            rows = o8.tensor_resample(rows.reshape(-1, S, S, 1), pos.to(rows.dtype).reshape(-1, S, S, 2)).reshape(-1, S * S)
         return rows.reshape(-1, 3, S * S).permute(0, 2, 1).reshape(-1, S * S * 3)
 
     store = og.VarStore(seed=7)
@@ -563,7 +591,8 @@ def test_trainer8x_temporal_steps_track_the_oracle(tag):
     disc_s = o8.growing_disc_tempo(real, pct, ctx, cfg)
     gen_s = o8.growing_disc_tempo(fake, pct, ctx, cfg)
     Lt = o8.wgan_gp_losses(disc_s, gen_s, lambda t: o8.growing_disc_tempo(t, pct, ctx, cfg), real, fake, lf, frames=3)
-    got = tr.t_disc_step(xt.float().to(dev), yt.float().to(dev), pct, z, lf).cpu().numpy()
+    pos_d = pos.float().to(dev).contiguous() if pos is not None else None
+    got = tr.t_disc_step(xt.float().to(dev), yt.float().to(dev), pct, z, lf, pos_d).cpu().numpy()
     assert abs(got[0] - float(Lt["disc_loss"].detach())) < 5e-4 * max(1.0, abs(float(Lt["disc_loss"].detach())))
     apply(o8.stage_variables(t_names, z), Lt["disc_loss"], ctx)
     # generator step: g_loss_d + l1 + kkt * g_loss_t
@@ -574,7 +603,7 @@ def test_trainer8x_temporal_steps_track_the_oracle(tag):
     gen_ts = o8.growing_gen_train(xt_in, pct, ctx, cfg)
     g_loss_t = (-o8.growing_disc_tempo(frames(gen_ts), pct, ctx, cfg)).mean()
     g_loss = (-gen).mean() + 1.0 * (y_in - gen_y).abs().mean() + 1.0 * g_loss_t
-    gl = tr.gen_step(x.float().to(dev), y.float().to(dev), pct, z, xt.float().to(dev), yt.float().to(dev)).cpu().numpy()
+    gl = tr.gen_step(x.float().to(dev), y.float().to(dev), pct, z, xt.float().to(dev), yt.float().to(dev), pos_d).cpu().numpy()
     assert abs(gl[2] - float(g_loss_t.detach())) < 5e-4 * max(1.0, abs(float(g_loss_t.detach())))
     assert abs(gl[0] + gl[1] + gl[2] - float(g_loss.detach())) < 5e-4 * max(1.0, abs(float(g_loss.detach())))
     apply(o8.stage_variables(g_names, z), g_loss, ctx)
