@@ -112,6 +112,49 @@ def growing_disc(in_high, in_low, percentage, ctx, cfg):
         return gan.y(), feats
 
 
+def semi_lagr_positions(vel, dt, out_side):
+    """getSemiLagrPosBatch (tools_wscale/tilecreator_t.py:1341-1378) for 2-D tiles: vel [n, L, L, 3] (vx, vy, vz per low-res
+    cell), dt [n] -> positions [n, S, S, 2] (y, x; cell centres at i + 0.5) = centre - centred velocity * dt, where the
+    velocity is first interpolated to the S x S grid (gridInterpolBatch :1291-1314: scipy map_coordinates order 1, mode
+    'nearest', at index (i + 0.5) * L / S), then centred like a MAC grid (getMACGridCenteredBatch :1319-1338: the mean of a
+    component and its +1 neighbour along its own axis, the last cell repeated) and scaled by S / L."""
+    vel = np.asarray(vel, np.float64)
+    n, L = vel.shape[0], vel.shape[1]
+    S = int(out_side)
+    dt = np.asarray(dt, np.float64).reshape(n, 1, 1)
+    if S == L:
+        vy, vx, scale = vel[..., 1], vel[..., 0], 1.0
+    else:
+        c = np.clip((np.arange(S) + 0.5) * (L / S), 0.0, L - 1.0)
+        lo = np.minimum(np.floor(c).astype(int), L - 1)
+        hi = np.minimum(lo + 1, L - 1)
+        t = c - lo
+
+        def up(a):
+            rows = a[:, lo] * (1 - t)[None, :, None] + a[:, hi] * t[None, :, None]
+            return rows[:, :, lo] * (1 - t)[None, None, :] + rows[:, :, hi] * t[None, None, :]
+        vy, vx, scale = up(vel[..., 1]), up(vel[..., 0]), S / L
+    nxt = np.minimum(np.arange(S) + 1, S - 1)
+    cy = 0.5 * (vy + vy[:, nxt, :]) * scale
+    cx = 0.5 * (vx + vx[:, :, nxt]) * scale
+    yy, xx = np.meshgrid(np.arange(S) + 0.5, np.arange(S) + 0.5, indexing="ij")
+    return np.stack([yy[None] - cy * dt, xx[None] - cx * dt], axis=-1)
+
+
+def tempo_tiles(low, high, n_t=3, dt=0.5, vel_channels=(1, 2, 3)):
+    """selectRandomTempoTiles (tilecreator_t.py:1382-1413) after the tile selection: low [B, 1, T, T, C*n_t], high
+    [B, 1, S, S, n_t] three-frame tiles (frames stored as channel groups) -> rows ordered (sample, frame):
+    x_t [B*n_t, T*T*C], y_t [B*n_t, S*S], positions [B*n_t, S*S*2] with dt * (n_t//2, ..., -(n_t//2)) per frame."""
+    low, high = np.asarray(low), np.asarray(high)
+    B, _, T, _, cc = low.shape
+    S, C = high.shape[2], cc // n_t
+    x = low.reshape(B, 1, T, T, n_t, C).transpose(0, 4, 1, 2, 3, 5).reshape(B * n_t, T, T, C)
+    y = high.reshape(B, 1, S, S, n_t, -1).transpose(0, 4, 1, 2, 3, 5).reshape(B * n_t, -1)
+    dts = np.array([i * dt for i in range(n_t // 2, -n_t // 2, -1)] * B, np.float32)
+    pos = semi_lagr_positions(x[..., list(vel_channels)], dts, S)
+    return x.reshape(B * n_t, -1), y, pos.reshape(B * n_t, -1)
+
+
 def tensor_resample(value, pos):
     """tensorResample :545-594 for 2-D data: value [B, H, W, C] sampled at pos [B, H, W, 2] (pos[..., 0] along H, pos[..., 1]
     along W, cell centres at i + 0.5): bilinear weights 1 - |pos - 0.5 - index| over floor / floor + 1, indices are NOT clamped

@@ -787,6 +787,43 @@ def make_schedule_fixtures():
     np.savez_compressed(os.path.join(HERE, "schedule8x.npz"), **out)
 
 
+def make_tempo_fixtures():
+    """getTempoinput's data side (tools_wscale/tilecreator_t.py): selectRandomTempoTiles (:1382-1413, the (sample, frame)
+    re-ordering of three-frame tiles and the per-frame dt) and getSemiLagrPosBatch / gridInterpolBatch /
+    getMACGridCenteredBatch (:1291-1378, the semi-Lagrangian re-sampling positions), executed as they are on a stub `self`
+    whose selectRandomTiles hands back prepared three-frame tiles."""
+    import scipy.ndimage
+    path = os.path.join(REF, "tools_wscale", "tilecreator_t.py")
+    code = ref_functions(path, ["gridInterpolBatch", "getMACGridCenteredBatch", "getSemiLagrPosBatch", "selectRandomTempoTiles"])
+    ns = dict(np=np, scipy=scipy, DATA_KEY_LOW=0, DATA_KEY_HIGH=1, C_KEY_VELOCITY="v")
+    exec(code, ns)
+    rng = np.random.default_rng(41)
+    T, u, C, B, n_t = 4, 4, 6, 2, 3
+    S = T * u
+    low = rng.standard_normal((B, 1, T, T, C * n_t)).astype(np.float32)
+    high = rng.random((B, 1, S, S, n_t), dtype=np.float32)
+
+    class Stub:
+        tileSizeLow, tileSizeHigh, dim = [1, T, T], [1, S, S], 2
+        c_lists = {0: {"v": [[1, 2, 3]]}}
+
+        def selectRandomTiles(self, n, isTraining, augment, tile_t=1):
+            assert n == B and tile_t == n_t
+            return low.copy(), high.copy()
+
+    xt, yt, pos = ns["selectRandomTempoTiles"](Stub(), B * n_t, True, False, n_t, 0.5)
+    out = dict(low=low, high=high, xt=np.asarray(xt, np.float32), yt=np.asarray(yt, np.float32), pos=np.asarray(pos, np.float64),
+               cfg=np.array([T, u, C, B, n_t, 0.5]))
+    # positions alone, other sizes (incl. the no-interpolation branch cube_len_output == tile size)
+    vel = rng.standard_normal((5, 1, 3, 3, 3)).astype(np.float32)
+    dta = np.array([0.5, 0.0, -0.5, 0.25, -1.0], np.float32).reshape(-1, 1, 1, 1)
+    out["vel"], out["dt"] = vel, dta.ravel()
+    out["pos_up8"] = np.asarray(ns["getSemiLagrPosBatch"](vel, dta, 24), np.float64)
+    out["pos_same"] = np.asarray(ns["getSemiLagrPosBatch"](vel, dta, 3), np.float64)
+    np.savez_compressed(os.path.join(HERE, "tempotiles.npz"), **out)
+    print("tempotiles.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the authoring container (needs /root/reference)"
     if "slices" in (sys.argv[1:] or ["slices"]):
@@ -804,6 +841,8 @@ if __name__ == "__main__":
         make_growdisc_fixtures()
     if "schedule" in which:
         make_schedule_fixtures()
+    if "tempo" in which:
+        make_tempo_fixtures()
     if "tiles" in which:
         make_tile_fixtures()
     if "uni" in which:

@@ -158,3 +158,14 @@ def test_tensor_resample_oracle_reproduces_the_reference_code():
     assert np.abs(out.numpy() - GOLD["resample_out"]).max() < 1e-12
     q = (pos - 0.5).floor()
     assert bool(((q < 0) | (q + 1 > 7)).any())          # the vectors do exercise out-of-range corners
+
+
+def test_tempo_tiles_and_semi_lagrangian_positions_reproduce_the_reference_code():
+    """getTempoinput's data side: selectRandomTempoTiles / getSemiLagrPosBatch (tools_wscale/tilecreator_t.py:1291-1413)."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tempotiles.npz"))
+    xt, yt, pos = o8.tempo_tiles(G["low"], G["high"], 3, 0.5)
+    assert np.array_equal(xt, G["xt"]) and np.array_equal(yt, G["yt"])
+    # (the reference interpolates float32 velocities in float32 -- scipy keeps the input type -- the restatement in float64)
+    assert np.abs(pos - G["pos"]).max() < 5e-6
+    assert np.abs(o8.semi_lagr_positions(G["vel"][:, 0], G["dt"], 24) - G["pos_up8"]).max() < 5e-6
+    assert np.abs(o8.semi_lagr_positions(G["vel"][:, 0], G["dt"], 3) - G["pos_same"]).max() < 5e-6
