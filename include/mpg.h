@@ -367,6 +367,12 @@ int mpg_train_fc_bwd(mpg_handle h, const float* x, const float* w, const float* 
  * no index clamping, out-of-range cells contribute 0; _bwd scatter-adds dout into dvalue (zero it first) */
 int mpg_train_resample_fwd(mpg_handle h, const float* value, const float* pos, float* out, int n, int hh, int ww, int c,
                            void* stream);
+/* the positions it reads: getSemiLagrPosBatch of getTempoinput (tools_wscale/tilecreator_t.py:1341-1378, called from
+ * selectRandomTempoTiles :1382-1413) for 2-D tiles. x [n, L, L, cstride] low-res tile rows ordered (sample, frame), (vx, vy) at
+ * channels c0, c0 + 1; pos [n, S, S, 2] (y, x) = cell centre - (velocity interpolated to S x S, MAC-centred, * S / L) * dt,
+ * dt of row r = dt0 * (n_t / 2 - r % n_t) */
+int mpg_train_semilagr_pos(mpg_handle h, const float* x, float* pos, int n, int L, int S, int cstride, int c0, float dt0,
+                           int n_t, void* stream);
 int mpg_train_resample_bwd(mpg_handle h, const float* dout, const float* pos, float* dvalue, int n, int hh, int ww, int c,
                            void* stream);
 int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long npix, int cstride, int c,

@@ -151,6 +151,7 @@ def lib():
     L.mpg_train_take_channel.argtypes = [vp, vp, vp, ll, ip, ip, ip, vp]
     L.mpg_train_resample_fwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp]
     L.mpg_train_resample_bwd.argtypes = [vp, vp, vp, vp, ip, ip, ip, ip, vp]
+    L.mpg_train_semilagr_pos.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, fl, ip, vp]
     L.mpg_train_avgpool2_fwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp]
     L.mpg_train_avgpool2_bwd.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip, vp]
     L.mpg_train_lerp.argtypes = [vp, vp, vp, vp, fl, ll, vp]

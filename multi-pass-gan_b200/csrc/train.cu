@@ -1000,6 +1000,38 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* value, const
   }
 }
 
+// getSemiLagrPosBatch (tools_wscale/tilecreator_t.py:1341-1378) for 2-D tiles, one thread per high-res cell: the MAC velocity
+// (vx, vy at channel c0, c0 + 1 of the low-res tile rows) is interpolated to the S x S grid (order-1 map_coordinates at index
+// (i + 0.5) * L / S, mode 'nearest'), centred (mean with the +1 neighbour along its own axis, last cell repeated), scaled by
+// S / L, and pos = cell centre - centred velocity * dt with dt = dt0 * (n_t / 2 - frame), frame = row % n_t.
+__global__ void __launch_bounds__(256) semilagr_pos_kernel(const float* x, float* pos, int n, int L, int S, int cstride, int c0,
+                                                            float dt0, int n_t) {
+  const long long total = static_cast<long long>(n) * S * S;
+  const float f = static_cast<float>(L) / static_cast<float>(S), scale = static_cast<float>(S) / static_cast<float>(L);
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256) {
+    const int X = static_cast<int>(e % S), Y = static_cast<int>((e / S) % S);
+    const long long b = e / (static_cast<long long>(S) * S);
+    const float dt = dt0 * static_cast<float>(n_t / 2 - static_cast<int>(b % n_t));
+    const float* tile = x + b * L * L * cstride;
+    auto up = [&](int ch, int yy, int xx) {  // interpolated component at high-res cell (yy, xx)
+      if (S == L) return tile[(yy * L + xx) * cstride + ch];
+      float cy = (static_cast<float>(yy) + 0.5f) * f, cx = (static_cast<float>(xx) + 0.5f) * f;
+      cy = fminf(fmaxf(cy, 0.0f), static_cast<float>(L - 1));
+      cx = fminf(fmaxf(cx, 0.0f), static_cast<float>(L - 1));
+      const int y0 = min(static_cast<int>(floorf(cy)), L - 1), x0 = min(static_cast<int>(floorf(cx)), L - 1);
+      const int y1 = min(y0 + 1, L - 1), x1 = min(x0 + 1, L - 1);
+      const float ty = cy - static_cast<float>(y0), tx = cx - static_cast<float>(x0);
+      const float a = tile[(y0 * L + x0) * cstride + ch] * (1.0f - ty) + tile[(y1 * L + x0) * cstride + ch] * ty;
+      const float c = tile[(y0 * L + x1) * cstride + ch] * (1.0f - ty) + tile[(y1 * L + x1) * cstride + ch] * ty;
+      return a * (1.0f - tx) + c * tx;
+    };
+    const float vy = 0.5f * (up(c0 + 1, Y, X) + up(c0 + 1, min(Y + 1, S - 1), X)) * scale;
+    const float vx = 0.5f * (up(c0, Y, X) + up(c0, Y, min(X + 1, S - 1))) * scale;
+    pos[2 * e] = static_cast<float>(Y) + 0.5f - vy * dt;
+    pos[2 * e + 1] = static_cast<float>(X) + 0.5f - vx * dt;
+  }
+}
+
 inline int grid_for(long long total, int sm) {
   long long b = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm) * 8;
@@ -1389,6 +1421,19 @@ int mpg_train_take_channel(mpg_handle h, const float* in, float* out, long long 
   return MPG_OK;
 }
 
+/* getSemiLagrPosBatch (tools_wscale/tilecreator_t.py:1341-1378, 2-D): x [n, L, L, cstride] low-res tile rows ordered
+ * (sample, frame) with (vx, vy) at channels c0, c0 + 1; pos [n, S, S, 2] (y, x) = the positions tensorResample reads,
+ * dt of row r = dt0 * (n_t / 2 - r % n_t) */
+int mpg_train_semilagr_pos(mpg_handle h, const float* x, float* pos, int n, int L, int S, int cstride, int c0, float dt0,
+                           int n_t, void* stream) {
+  MPG_CHECK_ARG(h && x && pos && n > 0 && L > 0 && S >= L && cstride >= c0 + 2 && c0 >= 0 && n_t >= 1,
+                "mpg_train_semilagr_pos: bad argument");
+  const long long total = static_cast<long long>(n) * S * S;
+  semilagr_pos_kernel<<<grid_for(total, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, pos, n, L, S, cstride, c0,
+                                                                                                dt0, n_t);
+  MPG_CUDA(cudaGetLastError());
+  return MPG_OK;
+}
 /* tensorResample (GAN/multipassGAN-8x.py:545-594, 2-D): out[n,hh,ww,c] = value re-sampled at pos[n,hh,ww,2] (bilinear around
  * pos - 0.5, no clamping, out-of-range cells contribute 0) */
 int mpg_train_resample_fwd(mpg_handle h, const float* value, const float* pos, float* out, int n, int hh, int ww, int c,

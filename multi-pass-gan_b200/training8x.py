@@ -30,9 +30,10 @@ Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned
   optimizers and the generator term kkt * mean(-T(G frames)) (`Trainer8x(lambda_t=...)`, `t_disc_step`, `gen_step(..., x_t, y_t)`).
   Frame alignment of the shipped commands (adv_flag 1, adv_mode 0): `tensorResample` (:545-594) of the generated and the target
   frames at given positions (`y_pos`; kernels mpg_train_resample_fwd/_bwd), at the full tile size.
-Not built: getTempoinput (the CPU advection that PRODUCES those positions, tilecreator_t.py) and the in-graph advection of
-adv_mode 1 / 2, loss scaling (numerically the identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni
-data loading of the three-frame sequences and the command line.
+  `TempoBatches` = getTempoinput / TileCreator.selectRandomTempoTiles: three-frame tiles from device-resident sequences, rows
+  (sample, frame), and the semi-Lagrangian positions of every frame (getSemiLagrPosBatch, kernel mpg_train_semilagr_pos).
+Not built: data augmentation of three-frame tiles, the in-graph advection of adv_mode 1 / 2, loss scaling (numerically the
+identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni loading of the sequences and the command line.
 """
 import math
 
@@ -660,6 +661,36 @@ class StageBatches:
         return self.samplers[currentUpres].batch_rows(self.batch_size, augment=self.augment)
 
 
+class TempoBatches:
+    """`tempo_batches(currentUpres)` for Trainer8x.train: getTempoinput (GAN/multipassGAN-8x.py:1475-1495) =
+    TileCreator.selectRandomTempoTiles (tools_wscale/tilecreator_t.py:1382-1413) without augmentation. The samplers hold
+    THREE-frame data (TileCreator(dim_t=3): the frames of a sequence stored as channel groups, low [N,1,L,L,C*3], high
+    [N,1,S,S,3]); a batch is `batch_size // 3` random three-frame tiles (same random decisions as selectRandomTiles), re-ordered
+    to rows (sample, frame), plus the semi-Lagrangian re-sampling positions of every frame (getSemiLagrPosBatch :1341-1378,
+    kernel mpg_train_semilagr_pos) with dt * (+1, 0, -1): the neighbouring frames are pulled onto the middle one."""
+
+    def __init__(self, samplers, batch_size, n_t=3, dt=0.5, vel_channel=1, device=0):
+        self.samplers, self.batch_size, self.n_t, self.dt = dict(samplers), int(batch_size), int(n_t), float(dt)
+        self.c0, self.h = int(vel_channel), capi.default_handle(device)
+
+    def __call__(self, currentUpres):
+        if currentUpres not in self.samplers:
+            raise KeyError("no three-frame training data at %dx (have %s)" % (currentUpres, sorted(self.samplers)))
+        s, n_t = self.samplers[currentUpres], self.n_t
+        B = max(1, self.batch_size // n_t)
+        low, high = s.select_random_tiles(B, True, False)              # [B,1,T,T,C*n_t], [B,1,Su,Su,n_t]
+        T, Su = low.shape[2], high.shape[2]
+        C = low.shape[-1] // n_t
+        if low.shape[-1] != C * n_t or high.shape[-1] != n_t:
+            raise ValueError("TempoBatches needs %d-frame data: low channels C*%d, high channels %d" % (n_t, n_t, n_t))
+        x = low.reshape(B, T, T, n_t, C).permute(0, 3, 1, 2, 4).contiguous().view(B * n_t, T * T * C)
+        y = high.reshape(B, Su, Su, n_t).permute(0, 3, 1, 2).contiguous().view(B * n_t, Su * Su)
+        pos = torch.empty((B * n_t, Su * Su * 2), dtype=torch.float32, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        capi.train_call("semilagr_pos", self.h, x, pos, B * n_t, T, Su, C, self.c0, self.dt, n_t, st)
+        return x, y, pos
+
+
 class Trainer8x:
     """Loop body of the 8x progressive-growing training (GAN/multipassGAN-8x.py:1898-2075, spatial part): one critic step
     (WGAN-GP, :1111-1143) and one generator step (g_loss_d + lambda * l1, :1117,1145) with the optimizers of growing stage z
@@ -735,18 +766,48 @@ class Trainer8x:
         return out
 
     def _align(self, rows, y_pos):
-        """tensorResample (:545-594) of the frames [B*3, S*S] at the advected positions y_pos [B*3, S*S*2] (adv_flag 1,
+        """tensorResample (:545-594) of the frames [n, S*S] at the advected positions y_pos [n, cur*cur*2] (adv_flag 1,
         adv_mode 0: :1195-1197 for the generated frames, :1241-1242 for the targets). y_pos None = frames already aligned
-        (adv_flag 0). Positions are taken at the full tile size: the reference re-samples at `2 ** ceil(percentage) * tileSize`
-        and resizes back (:1192-1204), which is the full size for the refinement networks and the first network's last stage."""
+        (adv_flag 0). Positions live on the grid of the stage's tiles (cur = tileSize * currentUpres): as in :1192-1204 the
+        frames are nearest-resized to that grid (a strided pick), re-sampled, and nearest-resized back to the full tile."""
         if y_pos is None:
             return rows
         cx, S, n = self.cx, self.gen.S, rows.shape[0]
-        if tuple(y_pos.shape) != (n, S * S * 2):
-            raise ValueError("y_pos must be [B*3, S*S*2] positions at the full tile size (got %s)" % (tuple(y_pos.shape),))
-        out = cx.buf(rows.shape)
-        cx.call("resample_fwd", rows, y_pos, out, n, S, S, 1, cx.st)
+        cur = int(round(math.sqrt(y_pos.shape[1] // 2)))
+        if y_pos.shape[0] != n or cur * cur * 2 != y_pos.shape[1] or S % cur:
+            raise ValueError("y_pos must be [B*3, cur*cur*2] positions on a grid dividing the tile (got %s)" % (tuple(y_pos.shape),))
+        f = S // cur
+        src = rows
+        if f > 1:
+            src = cx.buf((n, cur * cur))
+            cx.call("pick", rows, src, n, cur, cur, 1, f, 1, 1, 0, cx.st)
+        out = cx.buf((n, cur * cur))
+        cx.call("resample_fwd", src, y_pos, out, n, cur, cur, 1, cx.st)
+        if f > 1:
+            up = cx.buf((n, S * S))
+            capi.pack_channels(cx.h, [(out, capi.F32, 1, 0, 1, f, f)], up, capi.F32, 1, n, S, S, cx.st)
+            out = up
         return out
+
+    def _align_bwd(self, d_rows, y_pos):
+        """Adjoint of _align: gradient w.r.t. the un-aligned frames [n, S*S]."""
+        cx, S, n = self.cx, self.gen.S, d_rows.shape[0]
+        cur = int(round(math.sqrt(y_pos.shape[1] // 2)))
+        f = S // cur
+        d = d_rows
+        res = S
+        while res > cur:                     # adjoint of the nearest resize up: sum over the replicas, a factor 2 at a time
+            t = cx.buf((n, (res // 2) ** 2))
+            cx.call("avgpool2_fwd", d, t, n, res, res, 1, cx.st)
+            cx.call("scale", t, t, 4.0, t.numel(), cx.st)
+            d, res = t, res // 2
+        d_src = cx.zeros((n, cur * cur))
+        cx.call("resample_bwd", d, y_pos, d_src, n, cur, cur, 1, cx.st)
+        if f == 1:
+            return d_src
+        out = cx.zeros((n, S, S))            # adjoint of the strided pick: the gradient lands on the sampled positions
+        out[:, ::f, ::f] = d_src.view(n, cur, cur)
+        return out.view(n, S * S)
 
     def t_disc_step(self, x_t_rows, y_t_rows, percentage, z, lerp_factor, y_pos=None):
         """One step of t_disc_optimizer[z] (:2001-2013) on frame triplets: x_t_rows [B*3, L*L*C], y_t_rows [B*3, S*S(*2)]
@@ -797,9 +858,7 @@ class Trainer8x:
             dgen_t = cx.buf(gen_ts.shape)
             capi.transpose3d(cx.h, dx_t, dgen_t, (B, S * S, 3), (0, 2, 1), 0.0, cx.st)
             if y_pos is not None:  # back through tensorResample: scatter-add onto the un-aligned frames
-                d_un = cx.zeros(gen_ts.shape)
-                cx.call("resample_bwd", dgen_t, y_pos, d_un, gen_ts.shape[0], S, S, 1, cx.st)
-                dgen_t = d_un
+                dgen_t = self._align_bwd(dgen_t, y_pos)
             g.backward(gsv_t, dgen_t)
         cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
         self.opt_g.step(z)

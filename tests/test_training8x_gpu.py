@@ -682,3 +682,90 @@ def test_training_loop_with_the_temporal_critic_and_checkpoints(tmp_path):
     assert max(float(np.abs(a[n] - b[n]).max()) for n in a) < 2e-6
     with pytest.raises(ValueError):
         t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2).t_disc_step(xt, yt, 2.5, 2, lf)
+
+
+# ------------------------------------------------------------------ getTempoinput: three-frame tiles + advected positions
+TEMPO = np.load(os.path.join(os.path.dirname(__file__), "golden", "tempotiles.npz"))
+
+
+def test_semi_lagrangian_positions_kernel_matches_the_reference_vectors():
+    """mpg_train_semilagr_pos against getSemiLagrPosBatch / selectRandomTempoTiles executed from the reference
+    (tools_wscale/tilecreator_t.py:1341-1413): interpolating (x4, x8) and same-size grids, dt = 0.5 * (+1, 0, -1)."""
+    from mpgan_b200 import capi
+    h = capi.default_handle(0)
+    T, u, C = (int(v) for v in TEMPO["cfg"][:3])
+    S = T * u
+    xt = torch.from_numpy(TEMPO["xt"]).cuda()
+    pos = torch.empty((6, S * S * 2), device="cuda")
+    capi.train_call("semilagr_pos", h, xt, pos, 6, T, S, C, 1, 0.5, 3, 0)
+    assert np.abs(pos.cpu().numpy() - TEMPO["pos"]).max() < 2e-5
+    vel = torch.from_numpy(np.ascontiguousarray(TEMPO["vel"][:3, 0])).cuda()      # rows 0..2 carry dt = 0.5, 0, -0.5
+    for side, key in ((24, "pos_up8"), (3, "pos_same")):
+        p = torch.empty((3, side, side, 2), device="cuda")
+        capi.train_call("semilagr_pos", h, vel, p, 3, 3, side, 3, 0, 0.5, 3, 0)
+        assert np.abs(p.cpu().numpy() - TEMPO[key][:3]).max() < 2e-5, key
+
+
+def _tempo_sampler(dev, u, seed, rng_data):
+    import random
+    from mpgan_b200.tilesampler import TileSampler
+    s = TileSampler(4, u, densityMinimum=0.02, device=dev, rng=random.Random(seed))
+    low = rng_data.random((5, 1, 8, 8, 18), dtype=np.float32) + 0.05            # 3 frames x (d, vx, vy, vz, d-, d+)
+    low[..., 1:4] -= 0.5
+    high = rng_data.random((5, 1, 8 * u, 8 * u, 3), dtype=np.float32)
+    s.add_data(low, high)
+    return s
+
+
+def test_tempo_batches_reproduce_select_random_tempo_tiles():
+    dev = torch.device("cuda", 0)
+    a = _tempo_sampler(dev, 4, 21, np.random.default_rng(50))
+    b = _tempo_sampler(dev, 4, 21, np.random.default_rng(50))
+    x, y, pos = t8.TempoBatches({4: a}, 6)(4)
+    low, high = b.select_random_tiles(2, True, False)
+    wx, wy, wpos = o8.tempo_tiles(low.cpu().numpy(), high.cpu().numpy(), 3, 0.5)
+    assert x.shape == (6, 4 * 4 * 6) and y.shape == (6, 16 * 16) and pos.shape == (6, 16 * 16 * 2)
+    assert np.array_equal(x.cpu().numpy(), wx) and np.array_equal(y.cpu().numpy(), wy)
+    assert np.abs(pos.cpu().numpy() - wpos).max() < 2e-5
+    with pytest.raises(KeyError):
+        t8.TempoBatches({4: a}, 6)(8)
+
+
+def test_frame_alignment_on_a_coarser_grid_and_its_adjoint():
+    """_align for positions on the stage's grid (cur = S / 2): strided pick -> tensorResample -> nearest resize (:1192-1204),
+    against the oracle, and _align_bwd is its adjoint (<align(a), b> = <a, align_bwd(b)>)."""
+    tr = _loop_trainer()
+    dev, S = tr.cx.device, tr.gen.S
+    tr.cx.st = torch.cuda.current_stream(dev).cuda_stream
+    cur = S // 2
+    rng = np.random.default_rng(60)
+    a = torch.from_numpy(rng.random((6, S * S), dtype=np.float32)).to(dev)
+    base = np.stack(np.meshgrid(np.arange(cur) + 0.5, np.arange(cur) + 0.5, indexing="ij"), axis=-1)[None]
+    pos = torch.from_numpy((base + rng.normal(0, 0.9, (6, cur, cur, 2))).astype(np.float32).reshape(6, -1)).to(dev)
+    got = tr._align(a, pos)
+    picked = a.view(6, S, S)[:, ::2, ::2].double().cpu().unsqueeze(-1)
+    want = o8.tensor_resample(picked, pos.double().cpu().view(6, cur, cur, 2))[..., 0]
+    want = want.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(6, -1)
+    assert float((got.double().cpu() - want).abs().max()) < 1e-5
+    bvec = torch.from_numpy(rng.standard_normal((6, S * S)).astype(np.float32)).to(dev)
+    lhs = float((got.double() * bvec.double()).sum())
+    rhs = float((a.double() * tr._align_bwd(bvec, pos).double()).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    assert tr._align(a, None) is a
+
+
+def test_training_loop_on_three_frame_tiles_with_advected_positions():
+    """The temporal path end to end: TempoBatches (three-frame tiles + semi-Lagrangian positions at the stage's resolution) ->
+    tensorResample alignment -> temporal critic and generator steps, over a growing schedule."""
+    from mpgan_b200 import schedule8x as S8
+    np.random.seed(4)
+    tr = t8.Trainer8x(4, 8, 6, 32, 32, 3, batch=2, learning_rate=1e-3, seed=7, lambda_t=1.0)
+    dev = tr.cx.device
+    rng = np.random.default_rng(70)
+    tb = t8.TempoBatches({u: _tempo_sampler(dev, u, 30 + u, rng) for u in (2, 4, 8)}, 6)
+    batches, _ = _batches(dev)
+    g0 = tr.gen.ps.export()
+    hist = tr.train(batches, S8.GrowthSchedule(stageIter=1, decayIter=1), tempo_batches=tb, log_interval=1)
+    assert len(hist) == 7 and all(np.isfinite(h[1:]).all() for h in hist)
+    g1 = tr.gen.ps.export()
+    assert any(not np.array_equal(g0[n], g1[n]) for n in g0) and [st["t"] for st in tr.opt_t.state] == [2, 2, 3]
