@@ -41,6 +41,7 @@ import numpy as np
 import torch
 
 from . import capi
+from . import parallel as par
 from . import schedule8x
 from . import weights as W
 from .training import ParamSet
@@ -702,8 +703,12 @@ class Trainer8x:
 
     def __init__(self, tileSizeLow=16, upRes=8, n_inputChannels=6, start_fms=256, max_fms=256, filterSize=3, batch=16,
                  learning_rate=1e-4, adam_beta1=0.0, adam_beta2=0.99, lambda_l1=1.0, values=None, seed=1, device=0,
-                 upsampling_mode=2, first_nn_arch=None, lambda_t=0.0):
+                 upsampling_mode=2, first_nn_arch=None, lambda_t=0.0, group=None):
+        """group: torch.distributed process group for data-parallel training (one process per GPU, every rank draws its own
+        batches): the flat gradient of each optimizer step is averaged over the ranks with ONE all-reduce
+        (parallel.allreduce_mean, as in Trainer4x); None with an initialised default group = all ranks."""
         self.cx = cx = _Ctx(device)
+        self.group = group
         self.refine = int(upsampling_mode) != 2
         first = (not self.refine) if first_nn_arch is None else bool(first_nn_arch)
         if first == self.refine:
@@ -751,6 +756,7 @@ class Trainer8x:
         x_in, y_in = self._inputs(x_rows, y_rows)
         gen_y, _ = self.gen.forward(x_in, percentage)
         out = self.disc.critic_step(x_rows, y_in, gen_y, percentage, lerp_factor)
+        par.allreduce_mean(self.disc.ps.g, self.group)
         self.opt_d.step(z)
         return out
 
@@ -821,6 +827,7 @@ class Trainer8x:
         gen_ts, _ = self.gen.forward(x_in, percentage)
         out = self.tdisc.critic_step_frames(self._frames(self._align(y_in.contiguous(), y_pos)),
                                             self._frames(self._align(gen_ts, y_pos)), percentage, lerp_factor)
+        par.allreduce_mean(self.tdisc.ps.g, self.group)
         self.opt_t.step(z)
         return out
 
@@ -861,6 +868,7 @@ class Trainer8x:
                 dgen_t = self._align_bwd(dgen_t, y_pos)
             g.backward(gsv_t, dgen_t)
         cx.call("mul", g.ps.g, g.ps.gw, g.ps.scale, g.ps.total, cx.st)
+        par.allreduce_mean(g.ps.g, self.group)
         self.opt_g.step(z)
         self.ema.update(self.opt_g.state[z]["mask"])
         return self.losses
