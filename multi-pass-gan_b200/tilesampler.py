@@ -30,10 +30,14 @@ class TileSamplerError(Exception):
 
 class TileSampler:
     def __init__(self, tileSizeLow, upres, densityMinimum=0.02, partTrain=0.9, partTest=0.1, partVal=0, device=None,
-                 rng=None):
+                 rng=None, dim_t=1):
         """rng: an object with `randrange(a, b)` (default: the `random` module, like the reference's
-        `from random import randrange`); pass `random.Random(seed)` for reproducible batches."""
+        `from random import randrange`); pass `random.Random(seed)` for reproducible batches.
+        dim_t: frames per datum (TileCreator(dim_t=3) of the 8x trainer: the frames of a sequence are channel groups,
+        low [N,1,L,L,C*dim_t], high [N,1,S,S,Ch*dim_t]); tiles then carry all dim_t frames (`tile_t = dim_t`, as
+        selectRandomTempoTiles asks for, :1391) and the augmentation's velocity fix-ups act on every frame's group."""
         self.T, self.u = int(tileSizeLow), int(upres)
+        self.dim_t = int(dim_t)
         self.density_minimum = float(densityMinimum)
         total = partTrain + partTest + partVal
         self.part_train, self.part_test = partTrain / total, partTest / total  # :222-225
@@ -180,7 +184,7 @@ class TileSampler:
                 hs = int(round(tb * u * zf))
                 low = F.interpolate(low.permute(2, 0, 1)[None], size=(ts, ts), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
                 high = F.interpolate(high.permute(2, 0, 1)[None], size=(hs, hs), mode="bilinear", align_corners=True)[0].permute(1, 2, 0)
-                low = torch.cat([low[..., :1], low[..., 1:4] * np.float32(sf), low[..., 4:]], dim=-1)  # scaleVelocities :853-862
+                low = self._vel_map(low, lambda v: [c * np.float32(sf) for c in v])  # scaleVelocities :853-862
                 dens_t = low[..., 0].double().cpu().numpy()  # the density test of the second cut sees the scaled tile
                 oy, ox = self._random_offset(f, ts, T, lambda y, x, t: float(dens_t[y:y + t, x:x + t].sum(dtype=np.float64)))
             else:
@@ -197,19 +201,39 @@ class TileSampler:
                     # channel views and returns a new array, and special_aug (:648-663) only writes an op's result back
                     # for tile_t > 1 -- so with single frames the velocity vectors are NOT rotated with the tile
                     # (flipVelocities / scaleVelocities modify their views in place and do take effect).
+                    if self.dim_t > 1:  # multi-frame tiles: the result IS written back, every frame's vectors rotate
+                        a0, a1 = 2 - axes[0], 2 - axes[1]  # axes z,y,x = 0,1,2 -> velocity components x,y,z = 0,1,2
+
+                        def rot(v, a0=a0, a1=a1):
+                            v = list(v)
+                            v[a0], v[a1] = -v[a1], v[a0]
+                            return v
+                        low = self._vel_map(low, rot)
             if self.do_flip:
                 axis = int(self.np_rng.randint(0, 4))
                 if axis < 3:
                     if axis > 0:
                         low, high = torch.flip(low, (axis - 1,)), torch.flip(high, (axis - 1,))
-                    ch = list(low.unbind(-1))  # flipVelocities (:797-813): axis 2 -> vx, 1 -> vy, 0 -> vz
-                    ch[3 - axis] = -ch[3 - axis]
-                    low = torch.stack(ch, dim=-1)
+                    def flip_v(v, k=2 - axis):  # flipVelocities (:797-813): axis 2 -> vx, 1 -> vy, 0 -> vz
+                        v = list(v)
+                        v[k] = -v[k]
+                        return v
+                    low = self._vel_map(low, flip_v)
             if tuple(low.shape[:2]) != (T, T) or tuple(high.shape[:2]) != (T * u, T * u):
                 raise TileSamplerError("Wrong tile shape after data augmentation. is: %s,%s." % (tuple(low.shape), tuple(high.shape)))
             lows.append(low)
             highs.append(high)
         return torch.stack(lows).unsqueeze(1).contiguous(), torch.stack(highs).unsqueeze(1).contiguous()
+
+    def _vel_map(self, low, fn):
+        """Apply fn([vx, vy, vz]) -> [vx', vy', vz'] to the velocity channels (1, 2, 3) of every frame's channel group
+        (special_aug :648-663 reshapes multi-frame data to [-1, tile_t, channels] before it calls the op)."""
+        ch = list(low.unbind(-1))
+        C = len(ch) // self.dim_t
+        for k in range(self.dim_t):
+            b = k * C
+            ch[b + 1], ch[b + 2], ch[b + 3] = fn([ch[b + 1], ch[b + 2], ch[b + 3]])
+        return torch.stack(ch, dim=-1)
 
     def batch_rows(self, batch_size, is_training=True, augment=False):
         """getinput (GAN/multipassGAN-4x.py:1017-1047) with useVelocities and no vorticity / velocity modification:

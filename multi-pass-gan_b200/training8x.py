@@ -32,8 +32,8 @@ Checked against the fp64 autograd oracle (oracle/training8x.py), which is pinned
   frames at given positions (`y_pos`; kernels mpg_train_resample_fwd/_bwd), at the full tile size.
   `TempoBatches` = getTempoinput / TileCreator.selectRandomTempoTiles: three-frame tiles from device-resident sequences, rows
   (sample, frame), and the semi-Lagrangian positions of every frame (getSemiLagrPosBatch, kernel mpg_train_semilagr_pos).
-Not built: data augmentation of three-frame tiles, the in-graph advection of adv_mode 1 / 2, loss scaling (numerically the
-identity), the feature-layer loss (lambda2, 0 in the shipped commands), the .uni loading of the sequences and the command line.
+Not built: the in-graph advection of adv_mode 1 / 2, loss scaling (numerically the identity), the feature-layer loss (lambda2,
+0 in the shipped commands), the .uni loading of the sequences and the command line.
 """
 import math
 
@@ -664,22 +664,24 @@ class StageBatches:
 
 class TempoBatches:
     """`tempo_batches(currentUpres)` for Trainer8x.train: getTempoinput (GAN/multipassGAN-8x.py:1475-1495) =
-    TileCreator.selectRandomTempoTiles (tools_wscale/tilecreator_t.py:1382-1413) without augmentation. The samplers hold
+    TileCreator.selectRandomTempoTiles (tools_wscale/tilecreator_t.py:1382-1413). The samplers hold
     THREE-frame data (TileCreator(dim_t=3): the frames of a sequence stored as channel groups, low [N,1,L,L,C*3], high
     [N,1,S,S,3]); a batch is `batch_size // 3` random three-frame tiles (same random decisions as selectRandomTiles), re-ordered
     to rows (sample, frame), plus the semi-Lagrangian re-sampling positions of every frame (getSemiLagrPosBatch :1341-1378,
     kernel mpg_train_semilagr_pos) with dt * (+1, 0, -1): the neighbouring frames are pulled onto the middle one."""
 
-    def __init__(self, samplers, batch_size, n_t=3, dt=0.5, vel_channel=1, device=0):
+    def __init__(self, samplers, batch_size, n_t=3, dt=0.5, vel_channel=1, device=0, augment=False):
+        """augment: selectRandomTiles(..., augment=True) -> generateTile on the three-frame tiles (samplers built with
+        dim_t=3 and init_data_augmentation: scaling / rot90 / flip with every frame's velocity vectors fixed up)."""
         self.samplers, self.batch_size, self.n_t, self.dt = dict(samplers), int(batch_size), int(n_t), float(dt)
-        self.c0, self.h = int(vel_channel), capi.default_handle(device)
+        self.c0, self.h, self.augment = int(vel_channel), capi.default_handle(device), bool(augment)
 
     def __call__(self, currentUpres):
         if currentUpres not in self.samplers:
             raise KeyError("no three-frame training data at %dx (have %s)" % (currentUpres, sorted(self.samplers)))
         s, n_t = self.samplers[currentUpres], self.n_t
         B = max(1, self.batch_size // n_t)
-        low, high = s.select_random_tiles(B, True, False)              # [B,1,T,T,C*n_t], [B,1,Su,Su,n_t]
+        low, high = s.select_random_tiles(B, True, self.augment)       # [B,1,T,T,C*n_t], [B,1,Su,Su,n_t]
         T, Su = low.shape[2], high.shape[2]
         C = low.shape[-1] // n_t
         if low.shape[-1] != C * n_t or high.shape[-1] != n_t:

@@ -607,17 +607,21 @@ def make_augment_fixtures():
     for name in names:
         setattr(Stub, name, ns[name])
     out = {}
+    # "t3": THREE-frame tiles (TileCreator(dim_t=3), selectRandomTiles(..., tile_t=3) as selectRandomTempoTiles calls it,
+    # :1391): the frames of a sequence are channel groups and special_aug applies the velocity fix-ups per frame
     cfgs = {"a": (8, 24, 4, 4, 0.02, 0.85, 1.15, 1, 1, 21), "b": (6, 20, 2, 5, 0.005, 1.0, 1.0, 1, 0, 22),
-            "c": (8, 24, 2, 4, 0.02, 0.7, 1.3, 0, 1, 23)}
+            "c": (8, 24, 2, 4, 0.02, 0.7, 1.3, 0, 1, 23), "t3": (6, 18, 2, 4, 0.02, 0.85, 1.15, 1, 1, 24)}
     for tag, (T, L, u, nframes, dmin, smin, smax, rot, flip, seed) in cfgs.items():
+        dim_t = 3 if tag == "t3" else 1
         rng = np.random.default_rng(seed)
         S = L * u
-        low = rng.random((nframes, 1, L, L, 4), dtype=np.float32)
-        low[..., 1:4] -= 0.5
+        low = rng.random((nframes, 1, L, L, 4 * dim_t), dtype=np.float32)
+        for k in range(dim_t):
+            low[..., 4 * k + 1:4 * k + 4] -= 0.5
         low[..., 0] *= (rng.random((nframes, 1, L, L)) < 0.3)
-        high = rng.random((nframes, 1, S, S, 1), dtype=np.float32)
+        high = rng.random((nframes, 1, S, S, dim_t), dtype=np.float32)
         st = Stub()
-        st.dim, st.dim_t, st.upres, st.premadeTiles, st.useDataAug = 2, 1, u, False, True
+        st.dim, st.dim_t, st.upres, st.premadeTiles, st.useDataAug = 2, dim_t, u, False, True
         st.densityMinimum = dmin
         st.tile_shape_low = np.array([1, T, T, 4])
         st.tile_shape_high = np.array([1, T * u, T * u, 1])
@@ -643,7 +647,7 @@ def make_augment_fixtures():
         np.random.seed(3000 + seed)
         xs, ys = [], []
         for call in range(3):
-            bl, bh = st.selectRandomTiles(6, isTraining=True, augment=True)
+            bl, bh = st.selectRandomTiles(6, isTraining=True, augment=True, tile_t=dim_t)
             xs.append(np.asarray(bl, np.float32))
             ys.append(np.asarray(bh, np.float32))
         out.update({tag + "_low": low, tag + "_high": high, tag + "_aug_low": np.stack(xs), tag + "_aug_high": np.stack(ys),

@@ -92,14 +92,15 @@ def test_device_resident_sampler_feeds_the_trainer():
     assert np.isfinite(out["gen_loss_complete"]) and np.isfinite(out["disc_loss"])
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "t3"])
 def test_augmented_tiles_match_reference_generate_tile(tag):
     """selectRandomTiles(augment=True) -> generateTile (scaling, second cut, rot90, flip, velocity fix-ups) against the
     reference's own methods (tests/golden/tileaugment.npz): identical decisions (Python random + numpy RandomState call
     sequences), data movement exact, the order-1 zoom within fp32 rounding of scipy's double-precision interpolation."""
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tileaugment.npz"))
     T, L, u, nframes, dmin, smin, smax, rot, flip, seed_py, seed_np = gold[tag + "_cfg"]
-    s = ts.TileSampler(int(T), int(u), densityMinimum=float(dmin), rng=random.Random(int(seed_py)))
+    # "t3": three-frame tiles (TileCreator(dim_t=3), tile_t=3): per-frame velocity fix-ups, rot90 DOES rotate the vectors there
+    s = ts.TileSampler(int(T), int(u), densityMinimum=float(dmin), rng=random.Random(int(seed_py)), dim_t=3 if tag == "t3" else 1)
     s.add_data(gold[tag + "_low"], gold[tag + "_high"])
     s.init_data_augmentation(rot=int(rot), minScale=float(smin), maxScale=float(smax), flip=bool(flip),
                              np_rng=np.random.RandomState(int(seed_np)))
