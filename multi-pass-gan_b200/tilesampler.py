@@ -45,7 +45,7 @@ class TileSampler:
         self.rng = rng if rng is not None else random
         self.low = None     # [N, L, L, C]  on self.device
         self.high = None    # [N, S, S, Ch]
-        self._dens = None   # host copy of the low-res density channel, float32 [N, L, L] (density test)
+        self._dens = None   # host copy of the low-res density channel of every frame, float32 [N, dim_t, L, L] (density test)
         self.set_borders = [0, 0, 0]
         self.use_data_aug = False
 
@@ -85,7 +85,12 @@ class TileSampler:
             raise TileSamplerError("Can't cut tile %d from frame %d." % (self.T, L))
         lo = torch.from_numpy(np.ascontiguousarray(low[:, 0])).to(self.device)
         hi = torch.from_numpy(np.ascontiguousarray(high[:, 0])).to(self.device)
-        dens = np.ascontiguousarray(low[:, 0, :, :, 0])
+        if low.shape[-1] % self.dim_t or high.shape[-1] % self.dim_t:
+            raise TileSamplerError("channel counts %d / %d are not multiples of dim_t %d" % (low.shape[-1], high.shape[-1], self.dim_t))
+        C = low.shape[-1] // self.dim_t
+        # density channel of every frame of the datum, [N, dim_t, L, L] (the density test sees channel 0 of the CUT tile, i.e.
+        # of the first frame the tile carries)
+        dens = np.ascontiguousarray(np.stack([low[:, 0, :, :, k * C] for k in range(self.dim_t)], axis=1))
         if self.low is None:
             self.low, self.high, self._dens = lo, hi, dens
         else:
@@ -98,36 +103,54 @@ class TileSampler:
         self.set_borders = [end_train, end_train + int(n * self.part_test), n]
 
     # ------------------------------------------------------------------ the reference's decisions
-    def select_offsets(self, selection_size, is_training=True):
-        """[(frame, oy, ox)] * selection_size, consuming the generator exactly like selectRandomTiles (:457-489)."""
+    def _tile_t(self, tile_t):
+        """Frames per tile: None = the whole sequence (tile_t = dim_t, selectRandomTempoTiles :1391); 1 = the reference's
+        default for getinput, which on dim_t > 1 data also draws WHICH frame (getRandomDatum :548-560)."""
+        t = self.dim_t if tile_t is None else int(tile_t)
+        if t > self.dim_t:
+            raise TileSamplerError("not enough coherent frames. Requested %d, given %d" % (t, self.dim_t))
+        return t
+
+    def _rand_frame(self, tile_t):
+        """getRandomDatum :555-560: `randrange(0, dim_t - tile_t)` when tile_t < dim_t (so the last frame is never the first of
+        a tile), no draw otherwise."""
+        return self.rng.randrange(0, self.dim_t - tile_t) if tile_t < self.dim_t else 0
+
+    def select_offsets(self, selection_size, is_training=True, tile_t=None):
+        """[(frame, oy, ox, first frame of the sequence)] * selection_size, consuming the generator exactly like
+        selectRandomTiles (:457-489)."""
         if is_training:
             if self.set_borders[0] < 1:
                 raise TileSamplerError("no training data.")
         elif self.set_borders[1] - self.set_borders[0] < 1:
             raise TileSamplerError("no test data.")
-        L, T = self._dens.shape[1], self.T
+        L, T = self._dens.shape[2], self.T
+        tile_t = self._tile_t(tile_t)
         end = L - T + 1
         need = self.density_minimum * 1 * T * T  # hasMinDensity :920-921
         rr = self.rng.randrange
         picks = []
         for _ in range(int(selection_size)):
             f = rr(0, self.set_borders[0]) if is_training else rr(self.set_borders[0], self.set_borders[1])  # :548-553
+            fr = self._rand_frame(tile_t)
             i, ok = 1, False
             oy = ox = 0
             while (not ok) and i < 20:  # getRandomTile :622-640
                 rr(0, 1)  # the z offset of 2-D data: always 0, but the call advances the generator
                 oy = rr(0, end)
                 ox = rr(0, end)
-                ok = float(self._dens[f, oy:oy + T, ox:ox + T].sum(dtype=np.float64)) >= need  # getTileDensity :923-926
+                ok = float(self._dens[f, fr, oy:oy + T, ox:ox + T].sum(dtype=np.float64)) >= need  # getTileDensity :923-926
                 i += 1
-            picks.append((f, oy, ox))
+            picks.append((f, oy, ox, fr))
         return picks
 
     # ------------------------------------------------------------------ gather
-    def gather(self, picks):
-        """-> (low [n, 1, T, T, C], high [n, 1, T*u, T*u, Ch]) tensors on self.device (one advanced-indexing gather each)."""
+    def gather(self, picks, tile_t=None):
+        """-> (low [n, 1, T, T, C*tile_t], high [n, 1, T*u, T*u, Ch*tile_t]) tensors on self.device (one advanced-indexing
+        gather each, then the channel groups of the picked frames)."""
         T, u = self.T, self.u
         dev = self.device
+        tile_t = self._tile_t(tile_t)
         f = torch.tensor([p[0] for p in picks], device=dev, dtype=torch.long)
         oy = torch.tensor([p[1] for p in picks], device=dev, dtype=torch.long)
         ox = torch.tensor([p[2] for p in picks], device=dev, dtype=torch.long)
@@ -135,13 +158,19 @@ class TileSampler:
         low = self.low[f[:, None, None], (oy[:, None] + ar)[:, :, None], (ox[:, None] + ar)[:, None, :]]
         aru = torch.arange(T * u, device=dev)
         high = self.high[f[:, None, None], (oy[:, None] * u + aru)[:, :, None], (ox[:, None] * u + aru)[:, None, :]]
+        if tile_t < self.dim_t:  # getDatum :562-573: the channel groups of frames [fr, fr + tile_t)
+            C, Ch = low.shape[-1] // self.dim_t, high.shape[-1] // self.dim_t
+            fr = torch.tensor([p[3] for p in picks], device=dev, dtype=torch.long)
+            low = torch.gather(low, 3, (fr[:, None] * C + torch.arange(C * tile_t, device=dev))[:, None, None, :].expand(-1, T, T, -1))
+            high = torch.gather(high, 3, (fr[:, None] * Ch + torch.arange(Ch * tile_t, device=dev))[:, None, None, :].expand(-1, T * u, T * u, -1))
         return low.unsqueeze(1), high.unsqueeze(1)
 
-    def select_random_tiles(self, selection_size, is_training=True, augment=False):
-        """selectRandomTiles(selectionSize, isTraining, augment): (batch_low, batch_high)."""
+    def select_random_tiles(self, selection_size, is_training=True, augment=False, tile_t=None):
+        """selectRandomTiles(selectionSize, isTraining, augment, tile_t): (batch_low, batch_high). tile_t: see _tile_t (None =
+        every frame of the datum; the reference's own default is 1)."""
         if augment and self.use_data_aug:
-            return self.generate_tiles(selection_size, is_training)
-        return self.gather(self.select_offsets(selection_size, is_training))
+            return self.generate_tiles(selection_size, is_training, tile_t)
+        return self.gather(self.select_offsets(selection_size, is_training, tile_t), tile_t)
 
     # ------------------------------------------------------------------ augmentation (generateTile :491-546)
     def _random_offset(self, f, frame_h, tile, dens_of):
@@ -161,17 +190,22 @@ class TileSampler:
             i += 1
         return oy, ox
 
-    def generate_tiles(self, selection_size, is_training=True):
+    def generate_tiles(self, selection_size, is_training=True, tile_t=None):
         """`selection_size` augmented (low, high) tile pairs: [n, 1, T, T, C] / [n, 1, T*u, T*u, Ch] on self.device."""
         import torch.nn.functional as F
         T, u = self.T, self.u
-        L = self._dens.shape[1]
+        L = self._dens.shape[2]
         rr = self.rng.randrange
+        tile_t = self._tile_t(tile_t)
         lows, highs = [], []
         for _ in range(int(selection_size)):
             f = rr(0, self.set_borders[0]) if is_training else rr(self.set_borders[0], self.set_borders[1])
+            fr = self._rand_frame(tile_t)
             low, high = self.low[f], self.high[f]  # [L,L,C], [S,S,Ch] views on the device
-            dens = self._dens[f]
+            if tile_t < self.dim_t:
+                C, Ch = low.shape[-1] // self.dim_t, high.shape[-1] // self.dim_t
+                low, high = low[..., fr * C:(fr + tile_t) * C], high[..., fr * Ch:(fr + tile_t) * Ch]
+            dens = self._dens[f, fr]
             if self.do_scaling:
                 sf = float(self.np_rng.uniform(self.scale_factor[0], self.scale_factor[1]))
                 tb = int(np.ceil(T * (1.0 / sf)))  # tile cut "for faster transformation" (:503-512)
@@ -201,7 +235,7 @@ class TileSampler:
                     # channel views and returns a new array, and special_aug (:648-663) only writes an op's result back
                     # for tile_t > 1 -- so with single frames the velocity vectors are NOT rotated with the tile
                     # (flipVelocities / scaleVelocities modify their views in place and do take effect).
-                    if self.dim_t > 1:  # multi-frame tiles: the result IS written back, every frame's vectors rotate
+                    if tile_t > 1:  # multi-frame tiles: the result IS written back, every frame's vectors rotate
                         a0, a1 = 2 - axes[0], 2 - axes[1]  # axes z,y,x = 0,1,2 -> velocity components x,y,z = 0,1,2
 
                         def rot(v, a0=a0, a1=a1):
@@ -229,15 +263,15 @@ class TileSampler:
         """Apply fn([vx, vy, vz]) -> [vx', vy', vz'] to the velocity channels (1, 2, 3) of every frame's channel group
         (special_aug :648-663 reshapes multi-frame data to [-1, tile_t, channels] before it calls the op)."""
         ch = list(low.unbind(-1))
-        C = len(ch) // self.dim_t
-        for k in range(self.dim_t):
+        C = self.low.shape[-1] // self.dim_t
+        for k in range(len(ch) // C):
             b = k * C
             ch[b + 1], ch[b + 2], ch[b + 3] = fn([ch[b + 1], ch[b + 2], ch[b + 3]])
         return torch.stack(ch, dim=-1)
 
-    def batch_rows(self, batch_size, is_training=True, augment=False):
+    def batch_rows(self, batch_size, is_training=True, augment=False, tile_t=None):
         """getinput (GAN/multipassGAN-4x.py:1017-1047) with useVelocities and no vorticity / velocity modification:
         (batch_xs [n, T*T*C], batch_ys [n, (T*u)^2 * Ch]) in device memory, ready for Trainer4x.iteration."""
-        low, high = self.select_random_tiles(batch_size, is_training, augment)
+        low, high = self.select_random_tiles(batch_size, is_training, augment, tile_t)
         n = low.shape[0]
         return low.reshape(n, -1), high.reshape(n, -1)

@@ -652,6 +652,19 @@ def make_augment_fixtures():
             ys.append(np.asarray(bh, np.float32))
         out.update({tag + "_low": low, tag + "_high": high, tag + "_aug_low": np.stack(xs), tag + "_aug_high": np.stack(ys),
                     tag + "_cfg": np.array([T, L, u, nframes, dmin, smin, smax, rot, flip, 2000 + seed, 3000 + seed], np.float64)})
+        if dim_t > 1:
+            # getinput of the 8x trainer on the same three-frame data: selectRandomTiles with the DEFAULT tile_t = 1 picks one
+            # frame of the sequence (getRandomDatum :548-560: randrange(0, dim_t - tile_t), i.e. never the last one)
+            for key, aug in (("single", False), ("single_aug", True)):
+                rnd.seed(4000 + seed)
+                np.random.seed(5000 + seed)
+                xs, ys = [], []
+                for call in range(3):
+                    bl, bh = st.selectRandomTiles(6, isTraining=True, augment=aug)
+                    xs.append(np.asarray(bl, np.float32))
+                    ys.append(np.asarray(bh, np.float32))
+                out.update({"%s_%s_low" % (tag, key): np.stack(xs), "%s_%s_high" % (tag, key): np.stack(ys)})
+            out[tag + "_single_seeds"] = np.array([4000 + seed, 5000 + seed], np.float64)
     np.savez_compressed(os.path.join(HERE, "tileaugment.npz"), **out)
     print("tileaugment.npz:", {k: v.shape for k, v in out.items()})
 

@@ -129,8 +129,8 @@ def test_tile_sampler_picks_stay_inside_and_pair_up(T, extra, u, n, seed):
     if s.set_borders[0] < 1:
         return
     picks = s.select_offsets(5)
-    assert all(0 <= f < s.set_borders[0] and 0 <= oy <= L - T and 0 <= ox <= L - T for f, oy, ox in picks)
+    assert all(0 <= f < s.set_borders[0] and 0 <= oy <= L - T and 0 <= ox <= L - T for f, oy, ox, _ in picks)
     lo, hi = s.gather(picks)
-    for i, (f, oy, ox) in enumerate(picks):
+    for i, (f, oy, ox, _) in enumerate(picks):
         assert np.array_equal(lo[i, 0].numpy(), low[f, 0, oy:oy + T, ox:ox + T])
         assert np.array_equal(hi[i, 0].numpy(), high[f, 0, oy * u:(oy + T) * u, ox * u:(ox + T) * u])

@@ -38,7 +38,7 @@ def test_density_rejection_retries_and_rows_layout():
     s = ts.TileSampler(T, u, densityMinimum=0.02, rng=random.Random(3))
     s.add_data(low, high)
     picks = s.select_offsets(64)
-    dens = [float(low[f, 0, oy:oy + T, ox:ox + T, 0].sum(dtype=np.float64)) for f, oy, ox in picks]
+    dens = [float(low[f, 0, oy:oy + T, ox:ox + T, 0].sum(dtype=np.float64)) for f, oy, ox, _ in picks]
     assert sum(d >= 0.02 * T * T for d in dens) >= 60
     x, y = s.batch_rows(6)
     assert tuple(x.shape) == (6, T * T * 4) and tuple(y.shape) == (6, (T * u) ** 2)
@@ -46,7 +46,7 @@ def test_density_rejection_retries_and_rows_layout():
     s2.add_data(low, high)
     p = s2.select_offsets(2)
     lo, hi = s2.gather(p)
-    f, oy, ox = p[1]
+    f, oy, ox, _ = p[1]
     np.testing.assert_array_equal(lo[1, 0].numpy(), low[f, 0, oy:oy + T, ox:ox + T])
     np.testing.assert_array_equal(hi[1, 0].numpy(), high[f, 0, oy * u:(oy + T) * u, ox * u:(ox + T) * u])
     calls = []
@@ -115,6 +115,28 @@ def test_augmented_tiles_match_reference_generate_tile(tag):
         else:
             np.testing.assert_allclose(low.numpy(), wl, rtol=0, atol=3e-6)
             np.testing.assert_allclose(high.numpy(), wh, rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("key,aug", [("single", False), ("single_aug", True)])
+def test_single_frame_tiles_from_three_frame_data_match_the_reference(key, aug):
+    """getinput of the 8x trainer on TileCreator(dim_t=3) data: selectRandomTiles with the reference's default tile_t = 1 first
+    draws which frame of the sequence the tile comes from (never the last one, getRandomDatum :548-560), the density test and
+    the augmentation then see that frame only (single-frame rule: rot90 leaves the velocity vectors alone)."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tileaugment.npz"))
+    T, L, u, nframes, dmin, smin, smax, rot, flip, _, _ = gold["t3_cfg"]
+    seed_py, seed_np = gold["t3_single_seeds"]
+    s = ts.TileSampler(int(T), int(u), densityMinimum=float(dmin), rng=random.Random(int(seed_py)), dim_t=3)
+    s.add_data(gold["t3_low"], gold["t3_high"])
+    s.init_data_augmentation(rot=int(rot), minScale=float(smin), maxScale=float(smax), flip=bool(flip),
+                             np_rng=np.random.RandomState(int(seed_np)))
+    for call in range(3):
+        low, high = s.select_random_tiles(6, is_training=True, augment=aug, tile_t=1)
+        wl, wh = gold["t3_%s_low" % key][call], gold["t3_%s_high" % key][call]
+        assert tuple(low.shape) == wl.shape and tuple(high.shape) == wh.shape
+        np.testing.assert_allclose(low.numpy(), wl, rtol=0, atol=0 if not aug else 3e-6)
+        np.testing.assert_allclose(high.numpy(), wh, rtol=0, atol=0 if not aug else 3e-6)
+    with pytest.raises(ts.TileSamplerError):
+        s.select_random_tiles(2, tile_t=4)
 
 
 def test_augmentation_free_rotation_is_refused():
