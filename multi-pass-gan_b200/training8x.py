@@ -653,13 +653,15 @@ class StageBatches:
     every growing event (GAN/multipassGAN-8x.py:1916-1960); here the frames of every stage stay resident on the device and
     the growing event only switches the sampler. getinput (:1497-1536) = selectRandomTiles + the reshape to rows."""
 
-    def __init__(self, samplers, batch_size, augment=False):
-        self.samplers, self.batch_size, self.augment = dict(samplers), int(batch_size), bool(augment)
+    def __init__(self, samplers, batch_size, augment=False, tile_t=None):
+        """tile_t: 1 when the samplers hold three-frame sequences (TileSampler(dim_t=3), the temporal training data): getinput
+        then draws single frames of them, as the reference's selectRandomTiles default does."""
+        self.samplers, self.batch_size, self.augment, self.tile_t = dict(samplers), int(batch_size), bool(augment), tile_t
 
     def __call__(self, currentUpres):
         if currentUpres not in self.samplers:
             raise KeyError("no training data at %dx (have %s)" % (currentUpres, sorted(self.samplers)))
-        return self.samplers[currentUpres].batch_rows(self.batch_size, augment=self.augment)
+        return self.samplers[currentUpres].batch_rows(self.batch_size, augment=self.augment, tile_t=self.tile_t)
 
 
 class TempoBatches:

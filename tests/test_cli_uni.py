@@ -130,3 +130,72 @@ def test_cli_4x_two_runs_hand_over_uni_like_the_reference_recipe(tmp_path):
     mp = P.MultiPass4x(L, weights_for(2, 31), weights_for(1, 32), upRes=u, precision="fp32")
     np.testing.assert_array_equal(first[..., 0], mp.pass1_only(x).cpu().numpy())
     np.testing.assert_array_equal(second[..., 0], mp(x).cpu().numpy())
+
+
+# the flags of the reference's first-network training command (GAN/example_run_training.py:4), sizes shrunk for the test
+_TRAIN_8X = ("randSeed 16131119 upRes 8 use_res_net 1 batchNorm 0 pixelNorm 1 out 0 pretrain 0 pretrainDisc 0 tileSize 4 simSize 8 "
+             "use_LSGAN 0 use_wgan_gp 1 lambda 1.0 lambda2 0.0 discRuns 1 genRuns 1 alwaysSave 1 fromSim 1000 toSim 1000 outputInterval 2 "
+             "genTestImg 1 dropout 0.5 dataDim 2 batchSize 6 useVelocities 1 useVorticities 0 useK_Eps_Turb 0 useFlags 0 gif 0 "
+             "genModel gen_resnet discModel disc_binclass lambda_t 1.0 lambda_t_l2 0.0 frame_max 5 frame_min 0 data_fraction 1.0 "
+             "adv_flag 1 adv_mode 0 dataAugmentation 1 premadeTiles 0 rot 1 minScale 0.85 maxScale 1.15 flip 1 decayLR 1 adam_beta1 0.0 "
+             "adam_beta2 0.99 learningRate 0.0001 lossScaling 1 stageIter 1 decayIter 1 maxFms 32 startFms 32 filterSize 3 upsamplingMode 2 "
+             "upsampledData 0 discRuns 1 load_model_test -1 load_model_no -1 firstNNArch 1 add_adj_idcs 1 usePixelShuffle 0 "
+             "addBicubicUpsample 1 startingIter 0 useVelInTDisc 0 upsampleMode 1 gpu 0")
+
+
+def test_cli_8x_flag_checks(tmp_path):
+    from mpgan_b200 import cli_8x
+    base = ["multipassGAN-8x.py"] + _TRAIN_8X.split() + ["packedSimPath", str(tmp_path) + "/", "basePath", str(tmp_path) + "/"]
+    with pytest.raises(SystemExit):
+        cli_8x.main(base + ["bogusFlag", "1"])                       # unused flag aborts (paramhelpers)
+    for k, v in (("out", "1"), ("upsamplingMode", "1"), ("use_wgan_gp", "0"), ("adv_mode", "2"), ("decayLR", "0")):
+        argv = list(base)
+        for i in [j for j in range(1, len(argv), 2) if argv[j] == k]:
+            argv[i + 1] = v                                          # (some flags appear twice in the shipped command)
+        with pytest.raises(SystemExit) as e:
+            cli_8x.main(argv)
+        assert "multipassGAN-8x" in str(e.value), (k, e.value)
+
+
+@pytest.mark.gpu
+def test_cli_8x_trains_from_uni_simulations_and_the_result_applies(tmp_path):
+    """`python multipassGAN-8x.py out 0 ...` with the flags of the reference's first-network training command on a tiny
+    synthetic simulation: three-frame slices of every growing stage are loaded from .uni files, the whole (tiny) schedule
+    runs with the spatial and the temporal critic, and the saved moving-average checkpoint restores into multipassGAN-out.py."""
+    import torch
+    from mpgan_b200 import cli_8x, synth, tfckpt
+    L = 8
+    sim = tmp_path / "data" / "sim_1000"
+    sim.mkdir(parents=True)
+    rng = np.random.default_rng(3)
+    for f in range(5):
+        x = synth.synthetic_volume(L, seed=10 + f)
+        x[..., 0] = np.maximum(x[..., 0], 0.05)                       # keep every slice above the density threshold
+        uni.write_uni(str(sim / ("density_low_%04d.uni" % f)), uni.make_header((L, L, L), 1), x[..., 0:1])
+        uni.write_uni(str(sim / ("velocity_low_%04d.uni" % f)), uni.make_header((L, L, L), 2), x[..., 1:4])
+        for cu, name in ((2, "density_low_2_%04d.uni"), (4, "density_low_4_%04d.uni"), (8, "density_high_%04d.uni")):
+            hi = rng.random((L * cu, L * cu, L * cu, 1), dtype=np.float32)
+            uni.write_uni(str(sim / (name % f)), uni.make_header((L * cu,) * 3, 1), hi)
+    base = tmp_path / "runs"
+    base.mkdir()
+    argv = ["multipassGAN-8x.py"] + _TRAIN_8X.split() + ["packedSimPath", str(tmp_path / "data") + "/", "basePath", str(base) + "/"]
+    assert cli_8x.main(argv) == 0
+    test_dir = base / "test_0000"
+    saved = sorted(p.name for p in test_dir.iterdir() if p.name.endswith(".index"))
+    assert "model_0000.ckpt.index" in saved and "model_ema_0000.ckpt.index" in saved and len(saved) >= 6   # 2 growing events + final
+    last = max(int(n[len("model_ema_"):len("model_ema_") + 4]) for n in saved if n.startswith("model_ema_"))
+    got = tfckpt.read_checkpoint(str(test_dir / ("model_ema_%04d.ckpt" % last)), verify_data=True)
+    assert any(k.startswith("generator/genBlock8/") for k in got) and any(k.startswith("tempo-disc/") for k in got)
+    assert all(np.isfinite(v).all() for v in got.values())
+    # apply the trained first network through the out.py command line (weights restored from the run's directory)
+    flags = dict(out=1, packedSimPath=str(tmp_path / "data") + "/", basePath=str(base) + "/", fromSim=1000, frame_min=0, frame_max=1,
+                 simSize=L, tileSize=L, upRes=8, useVelocities=1, genUni=1, transposeAxis=0, pixelNorm=1, batchNorm=0,
+                 addBicubicUpsample=1, upsampleMode=1, firstNNArch=1, velScale=1.0, loadEmas=1, precision="fp32",
+                 load_model_test_1=0, load_model_no_1=last, use_res_net1=1, add_adj_idcs1=1, startFms1=32, maxFms1=32, filterSize1=3,
+                 load_model_test_2=-1, load_model_no_2=-1, load_model_test_3=-1, load_model_no_3=-1)
+    argv = ["multipassGAN-out.py"]
+    for k, v in flags.items():
+        argv += [k, str(v)]
+    assert cli.main(argv) == 0
+    head, vol = uni.read_uni(str(sim / "source_0000.uni"))
+    assert (head["dimX"], head["dimY"], head["dimZ"]) == (64, 64, 64) and np.isfinite(vol).all()
