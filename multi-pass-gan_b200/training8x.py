@@ -1,6 +1,6 @@
-"""Pieces of the 8x progressive-growing trainer on the GPU (GAN/multipassGAN-8x.py), for the configuration of
-the shipped first-network training command (GAN/example_run_training.py:4: firstNNArch 1, upsamplingMode 2, use_wgan_gp 1,
-no batch norm / gDrop / minibatch stddev in the discriminator):
+"""The 8x progressive-growing trainer on the GPU (GAN/multipassGAN-8x.py), for the configurations of the two
+shipped training commands (GAN/example_run_training.py:4,7: use_wgan_gp 1, lambda_t 1.0, no batch norm / gDrop / minibatch
+stddev; first network = firstNNArch 1 + upsamplingMode 2, refinement network = upsamplingMode 1):
 
 * `GrowingDisc` -- growing_disc / growBlockDisc (:752-866): the spatial critic grown stage by stage, each stage blended in
   with lerp(old, new, percentage - (j-1)) (:596-597); forward, backward (parameter and input gradients) and the
