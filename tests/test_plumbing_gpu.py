@@ -267,3 +267,37 @@ def test_host_frame_loop_matches_direct_calls():
         assert np.array_equal(a, b)
     got2 = loop.result(loop.submit(frames[0])).numpy()  # numpy input goes through the pinned staging buffer
     assert np.array_equal(got2, want[0])
+
+
+@pytest.mark.parametrize("pass2", [False, True])
+def test_slice_assemble_fast_path_equals_generic_kernel_at_the_benchmarked_size(pass2):
+    """L = 128, upRes 4 (BASELINE config 2): the 4-channel fast path (one thread per in-plane position, all slices of the batch)
+    against the generic per-pixel kernel (selected by a wider output stride), ragged batches at several slice offsets; both
+    evaluate the same trilinear weights, in a different order of operations."""
+    from mpgan_b200 import synth
+    L, u = 128, 4
+    S = L * u
+    vol = torch.from_numpy(synth.synthetic_volume(L, seed=3)).cuda()
+    dens = torch.rand((24, S, S), device="cuda") if pass2 else None
+    geom = dict(axis_of=(2, 0, 1), zoom=(u, u, u), chans=(2, 3, 1), scale=(4.0, 4.0, 4.0)) if pass2 else \
+        dict(axis_of=(0, 1, 2), zoom=(u, 1, 1), chans=(0, 1, 2, 3), scale=(1.0, 0.5, 0.5, 0.5))
+    side = S if pass2 else L
+    fast = capi.make_assemble_desc((L, L, L), 4, geom["axis_of"], geom["zoom"], geom["chans"], geom["scale"], out_dtype=capi.F32,
+                                   out_cstride=4, dens_slice0=200 if pass2 else 0)
+    slow = capi.make_assemble_desc((L, L, L), 4, geom["axis_of"], geom["zoom"], geom["chans"], geom["scale"], out_dtype=capi.F32,
+                                   out_cstride=8, dens_slice0=200 if pass2 else 0)
+    for s0, count in ((200, 8), (205, 3), (216, 8)) if pass2 else ((0, 8), (251, 5), (504, 8)):
+        a = torch.full((count, side, side, 4), float("nan"), device="cuda")
+        b = torch.full((count, side, side, 8), float("nan"), device="cuda")
+        capi.slice_assemble(H(), fast, vol, dens, s0, count, a)
+        capi.slice_assemble(H(), slow, vol, dens, s0, count, b)
+        assert torch.isfinite(a).all() and float(b[..., 4:].abs().max()) == 0.0
+        scale = float(b[..., :4].abs().max())
+        assert float((a - b[..., :4]).abs().max()) <= 2e-6 * max(1.0, scale), (s0, count)
+    # a slice's value does not depend on the batch it is assembled in (sharded / tiled runs stay bit-identical)
+    one = torch.empty((1, side, side, 4), device="cuda")
+    many = torch.empty((8, side, side, 4), device="cuda")
+    s0 = 208 if pass2 else 96
+    capi.slice_assemble(H(), fast, vol, dens, s0, 8, many)
+    capi.slice_assemble(H(), fast, vol, dens, s0 + 5, 1, one)
+    assert torch.equal(one[0], many[5])
