@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(256) conv_tiled_kernel(const ConvArgs a) {
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < kKC; ++c) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[c][cg * 8]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[c][cg * 8 + 4]);
+      // a thread's 8 output channels are {4 cg .. 4 cg + 3} and {32 + 4 cg ..}: the 8 lanes of a quarter warp read 128
+      // contiguous bytes (8 contiguous channels per thread made both 128-bit loads 2-way bank conflicts, as in wgrad_kernel)
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[c][cg * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[c][32 + cg * 4]);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) conv_tiled_kernel(const ConvArgs a) {
     float* o = a.out + ((static_cast<size_t>(n) * a.oh + oy) * a.ow + ox) * a.cout;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int co = co0 + cg * 8 + j;
+      const int co = co0 + (j < 4 ? cg * 4 + j : 32 + cg * 4 + (j - 4));
       if (co < a.cout) {
         float v = acc[i][j] + ((a.bias && blockIdx.z == 0) ? a.bias[co] : 0.0f);
         if (split) {
