@@ -15,8 +15,10 @@ inputs `density_low_%04d.uni` + `velocity_low_%04d.uni` of three consecutive fra
 the intermediate stages and `density_high_%04d.uni` for the last one (`conv_slices`, conv_axis 0, the input z-zoomed by the
 stage's factor, empty slices removed, adjacent-slice densities appended with `add_adj_idcs 1`: slicedata.py).  The reference
 re-loads a stage's files at its growing event; here every stage is loaded up front and stays resident on the device.
-Deviation, stated: WHICH frames are loaded.  FluidDataLoader draws a random `data_fraction` of the files with numpy's
-global generator; here every `round(1 / data_fraction)`-th frame triplet of [frame_min, frame_max - 2) is taken.
+The frames are the ones FluidDataLoader picks (slicedata.frame_indices: `data_fraction` of the index range, evenly spread;
+the first stage loads max(data_fraction * 2 / currentUpres, 0.08) of [frame_min, frame_max) (:326), a later stage
+`data_fraction` of the range shifted by 3 * (log2(currentUpres) - 1) frames (:1930-1937)); each index is the FIRST frame of a
+triplet (multi_file_idxOff 0, 1, 2), so the files reach two frames past the last index.
 Not on this command line: output mode (`out 1`: multipassGAN-out.py), the refinement networks (`upsamplingMode 1 / 3`:
 Trainer8x(upsampling_mode=1) from Python), LSGAN, batch norm, dropout, pixel shuffle, 3-D data, the test / summary / PNG
 side outputs of the loop.
@@ -136,9 +138,7 @@ def main(argv=None):
     np.random.seed(randSeed)
     C = 1 + 3 + (2 if add_adj_idcs else 0)
     sched = schedule8x.GrowthSchedule(stageIter, decayIter, upRes, upsampling_mode, startingIter, decayLR)
-    stride = max(1, int(round(1.0 / max(data_fraction, 1e-6))))
-    frames = list(range(frame_min, frame_max - 2, stride))
-    need(len(frames) > 0, "no frame triplets in [frame_min, frame_max - 2)")
+    from . import slicedata
     # the test_%04d directory of this run (ph.getNextTestPath, :381-390)
     no = 0
     while os.path.exists(os.path.join(basePath, "test_%04d" % no)):
@@ -151,6 +151,11 @@ def main(argv=None):
     samplers = {}
     t0 = time.time()
     for cu in stages:
+        if cu == stages[0]:                                                              # :326 (min_data_fraction 0.08, :247)
+            frames = slicedata.frame_indices(frame_min, frame_max, max(data_fraction * 2 / cu, 0.08))
+        else:                                                                            # :1930-1937 (stride = 3, :1897)
+            shift = 3 * (int(round(np.log2(cu))) - 1)
+            frames = slicedata.frame_indices(frame_min + shift, frame_max + shift, data_fraction)
         x, y = load_stage_slices(packedSimPath, range(fromSim, toSim + 1), frames, cu, upRes, bool(add_adj_idcs),
                                  0.005 if cu == stages[0] else 0.002, 0.4, device)       # :326 / :1937
         s = tilesampler.TileSampler(tileSizeLow, cu, densityMinimum=0.002 if cu == stages[0] else 0.01, device=device,

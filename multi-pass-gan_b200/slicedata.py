@@ -93,3 +93,13 @@ def slices_from_volumes(fx, fy, conv_axis=0, axis_scaling=(1, 1, 1, 1), axis_sca
         raise ValueError("slice counts differ after axis scaling: %d vs %d" % (fx.shape[0], fy.shape[0]))
     fx, fy = remove_slices(fx, fy, density_threshold)
     return select_random_samples(fx, fy, select_random)
+
+
+def frame_indices(filename_index_min, filename_index_max, data_fraction):
+    """Which file indices FluidDataLoader loads from an index range (fluiddataloader.py:238-244, the "simple index range"
+    branch): n = max(1, int((max - min) * data_fraction)) indices spread evenly over the range, int(min + t * (max - min) / n).
+    Deterministic -- the loader's numpy seed does not enter.  Pinned by tests/golden/tempotiles.npz (frac_*)."""
+    lo, hi = int(filename_index_min), int(filename_index_max)
+    n = max(1, int((hi - lo) * data_fraction))
+    tf = float(hi - lo) / n
+    return [int(lo + t * tf) for t in range(n)]

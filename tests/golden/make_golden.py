@@ -837,8 +837,29 @@ def make_tempo_fixtures():
     out["vel"], out["dt"] = vel, dta.ravel()
     out["pos_up8"] = np.asarray(ns["getSemiLagrPosBatch"](vel, dta, 24), np.float64)
     out["pos_same"] = np.asarray(ns["getSemiLagrPosBatch"](vel, dta, 3), np.float64)
+    # which frames FluidDataLoader loads for a data_fraction (tools_wscale/fluiddataloader.py:238-244, the "simple index range"
+    # branch): the three statements that compute n, tf and filelist_index, executed for several ranges
+    fpath = os.path.join(REF, "tools_wscale", "fluiddataloader.py")
+    with open(fpath) as fh:
+        ftree = ast.parse(fh.read())
+    loops = [n for n in ast.walk(ftree) if isinstance(n, ast.For) and "self.filename_index_min + t * tf" in ast.unparse(n)]
+    assert len(loops) == 1
+    loop = loops[0]
+    parent = [n for n in ast.walk(ftree) if isinstance(n, ast.If) and loop in n.orelse][0]
+    pre = parent.orelse[:parent.orelse.index(loop)]
+    loop.body = [loop.body[0], ast.parse("picked.append(filelist_index)").body[0]]
+    fcode = compile(ast.fix_missing_locations(ast.Module(body=pre + [loop], type_ignores=[])), fpath, "exec")
+    cases = [(0, 120, 0.08), (0, 120, 0.16), (3, 123, 0.08), (6, 126, 0.08), (0, 5, 1.0), (10, 50, 0.3), (0, 200, 0.01), (0, 7, 0.0)]
+    rows = []
+    for lo, hi, frac in cases:
+        picked = []
+        exec(fcode, dict(self=types.SimpleNamespace(filename_index_min=lo, filename_index_max=hi, data_fraction=frac), picked=picked))
+        rows.append(picked)
+    out["frac_cases"] = np.array(cases, np.float64)
+    out["frac_picked"] = json.dumps(rows)
+    print("frames per data_fraction:", rows[0], rows[4])
     np.savez_compressed(os.path.join(HERE, "tempotiles.npz"), **out)
-    print("tempotiles.npz:", {k: v.shape for k, v in out.items()})
+    print("tempotiles.npz:", {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
 if __name__ == "__main__":

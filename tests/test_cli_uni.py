@@ -136,7 +136,7 @@ def test_cli_4x_two_runs_hand_over_uni_like_the_reference_recipe(tmp_path):
 _TRAIN_8X = ("randSeed 16131119 upRes 8 use_res_net 1 batchNorm 0 pixelNorm 1 out 0 pretrain 0 pretrainDisc 0 tileSize 4 simSize 8 "
              "use_LSGAN 0 use_wgan_gp 1 lambda 1.0 lambda2 0.0 discRuns 1 genRuns 1 alwaysSave 1 fromSim 1000 toSim 1000 outputInterval 2 "
              "genTestImg 1 dropout 0.5 dataDim 2 batchSize 6 useVelocities 1 useVorticities 0 useK_Eps_Turb 0 useFlags 0 gif 0 "
-             "genModel gen_resnet discModel disc_binclass lambda_t 1.0 lambda_t_l2 0.0 frame_max 5 frame_min 0 data_fraction 1.0 "
+             "genModel gen_resnet discModel disc_binclass lambda_t 1.0 lambda_t_l2 0.0 frame_max 3 frame_min 0 data_fraction 1.0 "
              "adv_flag 1 adv_mode 0 dataAugmentation 1 premadeTiles 0 rot 1 minScale 0.85 maxScale 1.15 flip 1 decayLR 1 adam_beta1 0.0 "
              "adam_beta2 0.99 learningRate 0.0001 lossScaling 1 stageIter 1 decayIter 1 maxFms 32 startFms 32 filterSize 3 upsamplingMode 2 "
              "upsampledData 0 discRuns 1 load_model_test -1 load_model_no -1 firstNNArch 1 add_adj_idcs 1 usePixelShuffle 0 "
@@ -168,7 +168,9 @@ def test_cli_8x_trains_from_uni_simulations_and_the_result_applies(tmp_path):
     sim = tmp_path / "data" / "sim_1000"
     sim.mkdir(parents=True)
     rng = np.random.default_rng(3)
-    for f in range(5):
+    # frames: stage 2x loads the triplets starting at 0, 1, 2; the 4x / 8x stages the index range shifted by 3 / 6 (:1930-1937),
+    # every triplet reaches two frames further -> files 0 .. 10
+    for f in range(11):
         x = synth.synthetic_volume(L, seed=10 + f)
         x[..., 0] = np.maximum(x[..., 0], 0.05)                       # keep every slice above the density threshold
         uni.write_uni(str(sim / ("density_low_%04d.uni" % f)), uni.make_header((L, L, L), 1), x[..., 0:1])
@@ -199,3 +201,33 @@ def test_cli_8x_trains_from_uni_simulations_and_the_result_applies(tmp_path):
     assert cli.main(argv) == 0
     head, vol = uni.read_uni(str(sim / "source_0000.uni"))
     assert (head["dimX"], head["dimY"], head["dimZ"]) == (64, 64, 64) and np.isfinite(vol).all()
+
+
+def test_cli_8x_stage_loading_builds_three_frame_slices(tmp_path):
+    """load_stage_slices on the CPU: frame triplets (multi_file_idxOff 0, 1, 2) of one simulation -> slices with the channel
+    groups (d, vx, vy, vz, d(z-1), d(z+1)) x 3 frames and the stage's targets x 3 frames, the input z-zoomed by the stage factor."""
+    import torch
+    from mpgan_b200 import cli_8x, slicedata, synth
+    L, cu = 4, 2
+    sim = tmp_path / "sim_1000"
+    sim.mkdir()
+    rng = np.random.default_rng(8)
+    vols, highs = [], []
+    for f in range(4):
+        x = synth.synthetic_volume(L, seed=30 + f)
+        x[..., 0] = np.maximum(x[..., 0], 0.05)
+        hi = rng.random((L * cu,) * 3 + (1,), dtype=np.float32)
+        uni.write_uni(str(sim / ("density_low_%04d.uni" % f)), uni.make_header((L, L, L), 1), x[..., 0:1])
+        uni.write_uni(str(sim / ("velocity_low_%04d.uni" % f)), uni.make_header((L, L, L), 2), x[..., 1:4])
+        uni.write_uni(str(sim / ("density_low_2_%04d.uni" % f)), uni.make_header((L * cu,) * 3, 1), hi)
+        vols.append(x)
+        highs.append(hi)
+    x, y = cli_8x.load_stage_slices(str(tmp_path) + "/", [1000], [0, 1], cu, 8, True, 0.005, 1.0, "cpu")
+    assert tuple(x.shape) == (2 * L * cu, L, L, 18) and tuple(y.shape) == (2 * L * cu, L * cu, L * cu, 3)
+    for t0 in (0, 1):                                   # the two triplets, L * cu slices each
+        xs, ys = x[t0 * L * cu:(t0 + 1) * L * cu], y[t0 * L * cu:(t0 + 1) * L * cu]
+        for k in range(3):
+            want = slicedata.zoom_linear(torch.from_numpy(vols[t0 + k]), (cu, 1, 1, 1))
+            assert torch.allclose(xs[..., 6 * k:6 * k + 4], want, atol=1e-6)
+            assert torch.equal(xs[1:, :, :, 6 * k + 4], xs[:-1, :, :, 6 * k]) and float(xs[0, :, :, 6 * k + 4].abs().max()) == 0.0
+            assert torch.equal(ys[..., k], torch.from_numpy(highs[t0 + k][..., 0]))

@@ -41,3 +41,15 @@ def test_convert_slices_axis_and_channel_bookkeeping():
     assert sd.convert_slices(v, 0) is v
     with pytest.raises(ValueError):
         sd.convert_slices(v, 3)
+
+
+def test_frame_indices_match_the_fluid_data_loader():
+    """Which frames a data_fraction selects: the loader's own statements (tools_wscale/fluiddataloader.py:238-244) executed for
+    several index ranges (tests/golden/tempotiles.npz frac_*), incl. the ranges of the shipped 8x training command."""
+    import json
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tempotiles.npz"))
+    want = json.loads(str(G["frac_picked"]))
+    for (lo, hi, frac), w in zip(G["frac_cases"], want):
+        assert sd.frame_indices(int(lo), int(hi), float(frac)) == w, (lo, hi, frac)
+    assert sd.frame_indices(0, 120, 0.08) == [0, 13, 26, 40, 53, 66, 80, 93, 106]
